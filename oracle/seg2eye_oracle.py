@@ -1,0 +1,488 @@
+"""CPU oracle for the Seg2Eye SPADE+Style G/D training step.
+
+TEST INFRASTRUCTURE ONLY.  This file is a plain fp32 PyTorch-CPU restatement of the
+reference algorithm, written functionally over flat ``state_dict``-style dictionaries.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` leg may import it; the product package ``seg2eye_b200`` never does.
+
+Parity pin: the reference ships no tests / golden vectors, so the
+oracle is pinned against the *reference itself*, executed in the build container by
+``oracle/make_golden.py`` (imports /root/reference with three import shims) which writes
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this file against them.
+
+Each function cites the reference file:line it follows (paths relative to the
+reference checkout).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------
+# options (options/base_options.py:21-64, options/train_options.py:25-51)
+# --------------------------------------------------------------------------------------
+def make_opt(**kw):
+    o = dict(
+        ngf=64, ndf=64, w_dim=16, input_ns=4, label_nc=4, semantic_nc=4, output_nc=1,
+        crop_size=256, aspect_ratio=0.8, num_upsampling_layers="normal",
+        norm_G="spectralspadebatch3x3", norm_D="spectralinstance", norm_E="spectralinstance",
+        num_D=2, n_layers_D=4, no_ganFeat_loss=False, gan_mode="hinge",
+        lambda_feat=10.0, lambda_l1=0.0, lambda_l2=0.0, style_aggr_method="mean",
+        lr=2e-4, beta1=0.5, beta2=0.999, no_TTUR=False, weight_decay=0.0,
+        niter=14, niter_decay=7, isTrain=True,
+    )
+    o.update(kw)
+    o["semantic_nc"] = o["label_nc"]
+    return SimpleNamespace(**o)
+
+
+def latent_size(opt):
+    """generator.py:52-67 -> (sw, sh)."""
+    n_up = {"normal": 5, "more": 6, "most": 7}[opt.num_upsampling_layers]
+    sw = opt.crop_size // (2 ** n_up)
+    sh = round(sw / opt.aspect_ratio)
+    return sw, sh
+
+
+# --------------------------------------------------------------------------------------
+# state-dict shapes (SURVEY 8(b) state_dict layout; probed from the reference classes)
+# --------------------------------------------------------------------------------------
+def _sn_conv_shapes(sd, p, cout, cin, k, bias):
+    # spectral_norm re-registers weight as weight_orig after bias; u/v are buffers
+    if bias:
+        sd[p + ".bias"] = (cout,)
+    sd[p + ".weight_orig"] = (cout, cin, k, k)
+    sd[p + ".weight_u"] = (cout,)
+    sd[p + ".weight_v"] = (cin * k * k,)
+
+
+def _spade_style_shapes(sd, p, c, opt):
+    sd[p + ".spade.param_free_norm.running_mean"] = (c,)
+    sd[p + ".spade.param_free_norm.running_var"] = (c,)
+    sd[p + ".spade.param_free_norm.num_batches_tracked"] = ()
+    sd[p + ".spade.mlp_shared.0.weight"] = (128, opt.semantic_nc, 3, 3)
+    sd[p + ".spade.mlp_shared.0.bias"] = (128,)
+    for g in ("mlp_gamma", "mlp_beta"):
+        sd[p + ".spade.%s.weight" % g] = (c, 128, 3, 3)
+        sd[p + ".spade.%s.bias" % g] = (c,)
+    sd[p + ".adain.linear.weight"] = (2 * c, opt.w_dim)
+    sd[p + ".adain.linear.bias"] = (2 * c,)
+
+
+def generator_blocks(opt):
+    nf = opt.ngf
+    return [("head_0", 16 * nf, 16 * nf), ("G_middle_0", 16 * nf, 16 * nf),
+            ("G_middle_1", 16 * nf, 16 * nf), ("up_0", 16 * nf, 8 * nf),
+            ("up_1", 8 * nf, 4 * nf), ("up_2", 4 * nf, 2 * nf), ("up_3", 2 * nf, nf)]
+
+
+def generator_shapes(opt):
+    """Key order follows module registration order in generator.py:22-50 /
+    architecture.py:17-42 / normalization.py:63-89,172-182."""
+    sd = {}
+    nf = opt.ngf
+    instance = "instance" in opt.norm_G
+    sd["fc.weight"] = (16 * nf, opt.semantic_nc, 3, 3)
+    sd["fc.bias"] = (16 * nf,)
+    for name, fin, fout in generator_blocks(opt):
+        fmid = min(fin, fout)
+        _sn_conv_shapes(sd, name + ".conv_0", fmid, fin, 3, True)
+        _sn_conv_shapes(sd, name + ".conv_1", fout, fmid, 3, True)
+        if fin != fout:
+            _sn_conv_shapes(sd, name + ".conv_s", fout, fin, 1, False)
+        norms = [("norm_0", fin), ("norm_1", fmid)] + ([("norm_s", fin)] if fin != fout else [])
+        for nn_, c in norms:
+            _spade_style_shapes(sd, "%s.%s" % (name, nn_), c, opt)
+    sd["conv_img.weight"] = (opt.output_nc, nf, 3, 3)
+    sd["conv_img.bias"] = (opt.output_nc,)
+    if instance:
+        sd = {k: v for k, v in sd.items() if "param_free_norm" not in k}
+    return sd
+
+
+def discriminator_shapes(opt):
+    """discriminator.py:70-100."""
+    sd = {}
+    for i in range(opt.num_D):
+        p = "discriminator_%d" % i
+        nf = opt.ndf
+        sd[p + ".model0.0.weight"] = (nf, opt.label_nc + opt.output_nc, 4, 4)
+        sd[p + ".model0.0.bias"] = (nf,)
+        for n in range(1, opt.n_layers_D):
+            nf_prev, nf = nf, min(nf * 2, 512)
+            _sn_conv_shapes(sd, p + ".model%d.0.0" % n, nf, nf_prev, 4, False)
+        sd[p + ".model%d.0.weight" % opt.n_layers_D] = (1, nf, 4, 4)
+        sd[p + ".model%d.0.bias" % opt.n_layers_D] = (1,)
+    return sd
+
+
+def encoder_shapes(opt):
+    """encoder.py:16-51."""
+    sd = {}
+    ndf = opt.ngf
+    chans = [1, ndf, ndf * 2, ndf * 4, ndf * 8, ndf * 8] + ([ndf * 8] if opt.crop_size >= 256 else [])
+    for i in range(len(chans) - 1):
+        _sn_conv_shapes(sd, "layer%d.0" % i, chans[i + 1], chans[i], 3, False)
+    for n in ("fc_mu", "fc_var"):
+        sd[n + ".weight"] = (opt.w_dim, ndf * 8 * 16)
+        sd[n + ".bias"] = (opt.w_dim,)
+    return sd
+
+
+def synth_state(shapes, seed, scale=None):
+    """Portable deterministic weights (numpy PCG64, stable across platforms).
+
+    Scales are O(0.05-1) rather than the reference's xavier(0.02) so that the gamma/beta
+    branch is numerically alive (SURVEY section 7 'hard parts').  u/v are unit vectors,
+    running_var positive, num_batches_tracked int64."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {}
+    for k, shp in shapes.items():
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.tensor(int(rng.integers(0, 5)), dtype=torch.int64)
+            continue
+        a = rng.standard_normal(shp).astype(np.float32)
+        if k.endswith("weight_u") or k.endswith("weight_v"):
+            a = a / max(float(np.linalg.norm(a)), 1e-12)
+        elif k.endswith("running_var"):
+            a = (0.5 + np.abs(a)).astype(np.float32)
+        elif k.endswith("running_mean"):
+            a = 0.1 * a
+        elif k.endswith("bias"):
+            a = 0.1 * a
+        elif a.ndim >= 2:
+            fan_in = int(np.prod(shp[1:]))
+            s = scale if scale is not None else 1.0
+            a = a * np.float32(s / math.sqrt(fan_in))
+        out[k] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return out
+
+
+def synth_batch(opt, batch, seed, hw=None):
+    """eye-shaped 4-class label ellipses, images/targets U(-1,1), 4-D label."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if hw is None:
+        w = opt.crop_size
+        h = round(opt.crop_size / opt.aspect_ratio)
+    else:
+        h, w = hw
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    label = np.zeros((batch, 1, h, w), dtype=np.uint8)
+    for b in range(batch):
+        cy = h * (0.4 + 0.2 * rng.random())
+        cx = w * (0.4 + 0.2 * rng.random())
+        ry = h * (0.15 + 0.1 * rng.random())
+        rx = w * (0.3 + 0.15 * rng.random())
+        r2 = min(ry, rx) * (0.6 + 0.2 * rng.random())
+        r3 = r2 * (0.3 + 0.3 * rng.random())
+        d_scl = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2
+        d_cir = (yy - cy) ** 2 + (xx - cx) ** 2
+        lab = np.zeros((h, w), dtype=np.uint8)
+        lab[d_scl <= 1.0] = 1
+        lab[(d_cir <= r2 * r2) & (d_scl <= 1.0)] = 2
+        lab[(d_cir <= r3 * r3) & (d_scl <= 1.0)] = 3
+        label[b, 0] = lab
+    style = rng.uniform(-1, 1, size=(batch, opt.input_ns, 1, h, w)).astype(np.float32)
+    target = rng.uniform(-1, 1, size=(batch, 1, h, w)).astype(np.float32)
+    return {"label": torch.from_numpy(label), "style_image": torch.from_numpy(style),
+            "target": torch.from_numpy(target)}
+
+
+# --------------------------------------------------------------------------------------
+# integer path: one-hot and nearest indices (bit-exact)
+# --------------------------------------------------------------------------------------
+def one_hot(label, nc):
+    """pix2pix_model.py:138-152: zeros(B,nc,H,W).scatter_(1, label.long(), 1.0)."""
+    lab = label.long()
+    if lab.dim() == 3:
+        lab = lab.unsqueeze(0)
+    b, _, h, w = lab.shape
+    return torch.zeros(b, nc, h, w).scatter_(1, lab, 1.0)
+
+
+def nearest_src_index(dst_len, src_len):
+    """ATen 'nearest' (legacy) index: floor(dst * (src/dst)) computed in fp32, clamped.
+    Used by F.interpolate at normalization.py:97 and generator.py:72."""
+    scale = np.float32(src_len) / np.float32(dst_len)
+    idx = np.floor(np.arange(dst_len, dtype=np.float32) * scale).astype(np.int64)
+    return np.minimum(idx, src_len - 1)
+
+
+def nearest_resize(x, size):
+    hi = torch.from_numpy(nearest_src_index(size[0], x.shape[2]))
+    wi = torch.from_numpy(nearest_src_index(size[1], x.shape[3]))
+    return x[:, :, hi][:, :, :, wi]
+
+
+# --------------------------------------------------------------------------------------
+# building blocks
+# --------------------------------------------------------------------------------------
+def spectral_weight(sd, p, training=True):
+    """torch.nn.utils.spectral_norm (torch/nn/utils/spectral_norm.py:62-117) as applied at
+    normalization.py:26 and architecture.py:31-34: one power iteration per forward in
+    training mode, in-place on the u/v buffers, sigma = u.(W v) with u,v constants."""
+    w = sd[p + ".weight_orig"]
+    u, v = sd[p + ".weight_u"], sd[p + ".weight_v"]
+    wm = w.reshape(w.shape[0], -1)
+    if training:
+        with torch.no_grad():
+            v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12))
+            u.copy_(F.normalize(torch.mv(wm, v), dim=0, eps=1e-12))
+    uc, vc = u.clone(), v.clone()
+    sigma = torch.dot(uc, torch.mv(wm, vc))
+    return w / sigma
+
+
+def batch_norm_train(x, sd, p):
+    """nn.BatchNorm2d(affine=False) in training mode (normalization.py:75): biased variance
+    for normalisation, unbiased for running_var, momentum 0.1, eps 1e-5."""
+    n = x.numel() // x.shape[1]
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=False)
+    with torch.no_grad():
+        sd[p + ".running_mean"].mul_(0.9).add_(0.1 * mean.detach())
+        sd[p + ".running_var"].mul_(0.9).add_(0.1 * var.detach() * (n / max(n - 1, 1)))
+        sd[p + ".num_batches_tracked"].add_(1)
+    return (x - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + 1e-5)
+
+
+def instance_norm(x):
+    """nn.InstanceNorm2d(affine=False, eps=1e-5) (normalization.py:41,73)."""
+    mean = x.mean(dim=(2, 3), keepdim=True)
+    var = x.var(dim=(2, 3), unbiased=False, keepdim=True)
+    return (x - mean) * torch.rsqrt(var + 1e-5)
+
+
+def spade(sd, p, x, seg, instance=False):
+    """SPADE.forward, normalization.py:91-105."""
+    if instance:
+        normalized = instance_norm(x)
+    else:
+        normalized = batch_norm_train(x, sd, p + ".param_free_norm")
+    seg_r = nearest_resize(seg, x.shape[2:])
+    actv = F.relu(F.conv2d(seg_r, sd[p + ".mlp_shared.0.weight"], sd[p + ".mlp_shared.0.bias"], padding=1))
+    gamma = F.conv2d(actv, sd[p + ".mlp_gamma.weight"], sd[p + ".mlp_gamma.bias"], padding=1)
+    beta = F.conv2d(actv, sd[p + ".mlp_beta.weight"], sd[p + ".mlp_beta.bias"], padding=1)
+    return normalized * (1 + gamma) + beta
+
+
+def apply_style(sd, p, x, w):
+    """ApplyStyle.forward + FC.forward, normalization.py:134-169 (w_lrmul = b_lrmul = 1,
+    LeakyReLU(0.2) on the style vector, no normalisation of x)."""
+    style = F.leaky_relu(F.linear(w, sd[p + ".linear.weight"], sd[p + ".linear.bias"]), 0.2)
+    style = style.view(-1, 2, x.shape[1], 1, 1)
+    return x * (style[:, 0] + 1.0) + style[:, 1]
+
+
+def spade_style_block(sd, p, x, seg, w, opt):
+    """SPADE_STYLE_Block.forward, normalization.py:184-192."""
+    a = apply_style(sd, p + ".adain", x, w)
+    s = spade(sd, p + ".spade", x, seg, instance="instance" in opt.norm_G)
+    return (s + a) / 2
+
+
+def resblock(sd, p, x, seg, w, fin, fout, opt, training=True, taps=None):
+    """SPADE_STYLE_ResnetBlock.forward, architecture.py:44-62.  Evaluation order matters for
+    the BN buffers: shortcut (norm_s) first, then norm_0, then norm_1."""
+    sn = "spectral" in opt.norm_G
+
+    def conv(name, t, pad):
+        if sn:
+            wt = spectral_weight(sd, "%s.%s" % (p, name), training)
+        else:
+            wt = sd["%s.%s.weight" % (p, name)]
+        return F.conv2d(t, wt, sd.get("%s.%s.bias" % (p, name)), padding=pad)
+
+    if fin != fout:
+        ns = spade_style_block(sd, p + ".norm_s", x, seg, w, opt)
+        x_s = conv("conv_s", ns, 0)
+    else:
+        x_s = x
+    n0 = F.leaky_relu(spade_style_block(sd, p + ".norm_0", x, seg, w, opt), 0.2)
+    dx = conv("conv_0", n0, 1)
+    n1 = F.leaky_relu(spade_style_block(sd, p + ".norm_1", dx, seg, w, opt), 0.2)
+    dx = conv("conv_1", n1, 1)
+    out = x_s + dx
+    if taps is not None:
+        taps[p + ".norm_0"] = n0
+        taps[p] = out
+    return out
+
+
+def generator_forward(sd, seg, w, opt, training=True, taps=None):
+    """SPADESTYLEGenerator.forward, generator.py:69-102 ('normal'/'more' upsampling)."""
+    sw, sh = latent_size(opt)
+    x = nearest_resize(seg, (sh, sw))
+    x = F.conv2d(x, sd["fc.weight"], sd["fc.bias"], padding=1)
+    if taps is not None:
+        taps["fc"] = x
+    blocks = generator_blocks(opt)
+
+    def up(t):  # nn.Upsample(scale_factor=2), nearest
+        return t.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+
+    x = resblock(sd, blocks[0][0], x, seg, w, blocks[0][1], blocks[0][2], opt, training, taps)
+    x = up(x)
+    x = resblock(sd, blocks[1][0], x, seg, w, blocks[1][1], blocks[1][2], opt, training, taps)
+    if opt.num_upsampling_layers in ("more", "most"):
+        x = up(x)
+    x = resblock(sd, blocks[2][0], x, seg, w, blocks[2][1], blocks[2][2], opt, training, taps)
+    for name, fin, fout in blocks[3:]:
+        x = up(x)
+        x = resblock(sd, name, x, seg, w, fin, fout, opt, training, taps)
+    x = F.conv2d(F.leaky_relu(x, 0.2), sd["conv_img.weight"], sd["conv_img.bias"], padding=1)
+    return torch.tanh(x)
+
+
+def encoder_forward(sd, x, opt, training=True):
+    """ConvEncoder.forward, encoder.py:53-73: bilinear to 256x256 (align_corners=False),
+    [SN conv3x3 s2 p1 (no bias) -> InstanceNorm] x n with no activation in between,
+    LeakyReLU(0.2), flatten, fc_mu / fc_var."""
+    if x.shape[2] != 256 or x.shape[3] != 256:
+        x = F.interpolate(x, size=(256, 256), mode="bilinear", align_corners=False)
+    feats = []
+    n_layers = 6 if opt.crop_size >= 256 else 5
+    for i in range(n_layers):
+        wt = spectral_weight(sd, "layer%d.0" % i, training)
+        x = instance_norm(F.conv2d(x, wt, None, stride=2, padding=1))
+        feats.append(x)
+    out = F.leaky_relu(x, 0.2).reshape(x.shape[0], -1)
+    mu = F.linear(out, sd["fc_mu.weight"], sd["fc_mu.bias"])
+    logvar = F.linear(out, sd["fc_var.weight"], sd["fc_var.bias"])
+    return mu, logvar, feats
+
+
+def encode_w(sdE, style_image, opt, training=True):
+    """pix2pix_model.py:280-314: one netE call per batch sample over its ns style images,
+    mu stacked to (B, ns, w_dim) and aggregated (mean | max) over ns."""
+    assert style_image.dim() == 5
+    mus = [encoder_forward(sdE, style_image[b], opt, training)[0] for b in range(style_image.shape[0])]
+    mw = torch.stack(mus, dim=0)
+    if opt.style_aggr_method == "mean":
+        return mw.mean(dim=1)
+    return mw.max(dim=1).values
+
+
+def nlayer_discriminator(sd, p, x, opt, training=True):
+    """NLayerDiscriminator.forward, discriminator.py:78-116: 4x4 convs, padding 2."""
+    outs = []
+    x = F.leaky_relu(F.conv2d(x, sd[p + ".model0.0.weight"], sd[p + ".model0.0.bias"], stride=2, padding=2), 0.2)
+    outs.append(x)
+    for n in range(1, opt.n_layers_D):
+        stride = 1 if n == opt.n_layers_D - 1 else 2
+        wt = spectral_weight(sd, p + ".model%d.0.0" % n, training)
+        x = F.leaky_relu(instance_norm(F.conv2d(x, wt, None, stride=stride, padding=2)), 0.2)
+        outs.append(x)
+    n = opt.n_layers_D
+    x = F.conv2d(x, sd[p + ".model%d.0.weight" % n], sd[p + ".model%d.0.bias" % n], stride=1, padding=2)
+    outs.append(x)
+    return outs
+
+
+def discriminator_forward(sd, x, opt, training=True):
+    """MultiscaleDiscriminator.forward, discriminator.py:46-63."""
+    result = []
+    for i in range(opt.num_D):
+        result.append(nlayer_discriminator(sd, "discriminator_%d" % i, x, opt, training))
+        x = F.avg_pool2d(x, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
+    return result
+
+
+def hinge(pred, target_is_real, for_discriminator):
+    """GANLoss.loss, loss.py:66-77 (hinge)."""
+    if for_discriminator:
+        if target_is_real:
+            return -torch.mean(torch.clamp(pred - 1, max=0))
+        return -torch.mean(torch.clamp(-pred - 1, max=0))
+    return -torch.mean(pred)
+
+
+def gan_loss(preds, target_is_real, for_discriminator):
+    """GANLoss.__call__, loss.py:85-99: last tensor of each D, averaged over num_D, shape (1,)."""
+    loss = 0
+    for p in preds:
+        loss = loss + hinge(p[-1], target_is_real, for_discriminator).view(1)
+    return loss / len(preds)
+
+
+def discriminate(sdD, seg, fake, real, opt, training=True):
+    """pix2pix_model.py:328-358."""
+    both = torch.cat([torch.cat([seg, fake], 1), torch.cat([seg, real], 1)], 0)
+    out = discriminator_forward(sdD, both, opt, training)
+    nb = both.shape[0] // 2
+    return [[t[:nb] for t in d] for d in out], [[t[nb:] for t in d] for d in out]
+
+
+def generator_losses(sdG, sdD, sdE, batch, opt):
+    """compute_generator_loss, pix2pix_model.py:186-247 (GAN + L1/L2 + GAN_Feat)."""
+    seg = one_hot(batch["label"], opt.label_nc)
+    w = encode_w(sdE, batch["style_image"], opt)
+    fake = generator_forward(sdG, seg, w, opt)
+    pred_fake, pred_real = discriminate(sdD, seg, fake, batch["target"], opt)
+    losses = {"GAN": gan_loss(pred_fake, True, False)}
+    if opt.lambda_l2:
+        losses["L2/weighted"] = F.mse_loss(fake, batch["target"]) * opt.lambda_l2
+    if opt.lambda_l1:
+        losses["L1/weighted"] = F.l1_loss(fake, batch["target"]) * opt.lambda_l1
+    if not opt.no_ganFeat_loss:
+        fm = torch.zeros(1)
+        for i in range(len(pred_fake)):
+            for j in range(len(pred_fake[i]) - 1):
+                fm = fm + F.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) * opt.lambda_feat / len(pred_fake)
+        losses["GAN_Feat"] = fm
+    return losses, fake
+
+
+def discriminator_losses(sdG, sdD, sdE, batch, opt):
+    """compute_discriminator_loss, pix2pix_model.py:249-264."""
+    seg = one_hot(batch["label"], opt.label_nc)
+    with torch.no_grad():
+        w = encode_w(sdE, batch["style_image"], opt)
+        fake = generator_forward(sdG, seg, w, opt)
+    fake = fake.detach().requires_grad_()
+    pred_fake, pred_real = discriminate(sdD, seg, fake, batch["target"], opt)
+    return {"D/Fake": gan_loss(pred_fake, False, True), "D/real": gan_loss(pred_real, True, True)}
+
+
+# --------------------------------------------------------------------------------------
+# trainer (trainers/pix2pix_trainer.py:26-45, pix2pix_model.py:92-110)
+# --------------------------------------------------------------------------------------
+def _is_param(k):
+    return not (k.endswith("weight_u") or k.endswith("weight_v") or "running_" in k or k.endswith("num_batches_tracked"))
+
+
+class OracleTrainer:
+    """Adam(betas (0,0.9) under TTUR, lr/2 for G+E and lr*2 for D), one G step then one D step."""
+
+    def __init__(self, sdG, sdD, sdE, opt):
+        self.opt = opt
+        self.sdG, self.sdD, self.sdE = sdG, sdD, sdE
+        for sd in (sdG, sdD, sdE):
+            for k, v in sd.items():
+                if _is_param(k):
+                    v.requires_grad_(True)
+        if opt.no_TTUR:
+            b1, b2, glr, dlr = opt.beta1, opt.beta2, opt.lr, opt.lr
+        else:
+            b1, b2, glr, dlr = 0.0, 0.9, opt.lr / 2, opt.lr * 2
+        gp = [v for sd in (sdG, sdE) for k, v in sd.items() if _is_param(k)]
+        dp = [v for k, v in sdD.items() if _is_param(k)]
+        self.opt_G = torch.optim.Adam(gp, lr=glr, betas=(float(b1), float(b2)), weight_decay=opt.weight_decay)
+        self.opt_D = torch.optim.Adam(dp, lr=dlr, betas=(float(b1), float(b2)), weight_decay=opt.weight_decay)
+
+    def run_generator_one_step(self, batch):
+        self.opt_G.zero_grad()
+        self.g_losses, self.generated = generator_losses(self.sdG, self.sdD, self.sdE, batch, self.opt)
+        sum(self.g_losses.values()).mean().backward()
+        self.opt_G.step()
+
+    def run_discriminator_one_step(self, batch):
+        self.opt_D.zero_grad()
+        self.d_losses = discriminator_losses(self.sdG, self.sdD, self.sdE, batch, self.opt)
+        sum(self.d_losses.values()).mean().backward()
+        self.opt_D.step()
