@@ -1,0 +1,183 @@
+/* seg2eye_b200 -- C ABI of the B200-native (sm_100a) SPADE+Style G/D training-step kernels.
+ *
+ * The reference (mcbuehler/Seg2Eye) has no FFI of its own: its hot path is a chain of stock
+ * torch.nn calls.  Every entry point below therefore names the reference call site(s) whose
+ * arithmetic it replaces (paths relative to the reference checkout).  The Python host in
+ * seg2eye_b200/ binds these symbols with ctypes and mirrors the
+ * reference's models.networks / Pix2PixModel / Pix2PixTrainer interface on top.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless stated otherwise; nothing is allocated inside.
+ *   - Activations are bf16, NHWC ("pixels x channels"); statistics, losses, master weights,
+ *     gradients of weights and optimizer state are fp32.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous and re-entrant per stream.
+ *   - Return value: 0 = OK, negative = error (s2e_last_error() gives the message).
+ */
+#ifndef SEG2EYE_B200_H_
+#define SEG2EYE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2E_OK 0
+#define S2E_ERR_ARG (-1)
+#define S2E_ERR_CUDA (-2)
+#define S2E_ERR_UNSUPPORTED (-3)
+
+#define S2E_ACT_NONE 0
+#define S2E_ACT_LRELU 1 /* leaky_relu(., 0.2) */
+#define S2E_ACT_RELU 2
+
+#define S2E_IMPL_TC 0   /* tcgen05 + TMEM + TMA implicit GEMM (product path) */
+#define S2E_IMPL_SIMT 1 /* CUDA-core kernel: tiny / MMA-unfriendly layers and on-device cross-check */
+
+#define S2E_MAX_TAPS 16
+
+const char* s2e_last_error(void);
+int s2e_abi_version(void);
+/* debug knobs (bring-up only): key 0 = swap LBO/SBO in MN-major UMMA descriptors, key 1 = force SIMT. */
+int s2e_debug_set(int key, int value);
+
+/* ------------------------------------------------------------------------------------------
+ * Integer path (bit-exact).  pix2pix_model.py:138-152 (one-hot scatter_), normalization.py:97 and
+ * generator.py:72 (F.interpolate nearest: src = min(floor(dst * float(in)/float(out)), in-1)).
+ * ------------------------------------------------------------------------------------------ */
+int s2e_onehot_nchw(const int64_t* label, int B, int H, int W, int nc, float* out_nchw, void* stream);
+/* nearest-resize an NCHW fp32 map (one-hot or soft) to (Hd,Wd) and emit NHWC bf16 with Cpad >= C channels. */
+int s2e_seg_nearest_nhwc(const float* seg_nchw, int B, int C, int Hs, int Ws, int Hd, int Wd, int Cpad,
+                         void* out_nhwc_bf16, void* stream);
+
+/* layout / precision boundary of the module API (NCHW fp32 <-> NHWC bf16) */
+int s2e_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* y, void* stream);
+int s2e_nhwc_bf16_to_nchw_f32(const void* x, int B, int C, int H, int W, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution as a stride-1 "tap convolution":
+ *     y[b,ho,wo,:] = act( scale * sum_t  x[b, ho+dy[t], wo+dx[t], :] . Wp[t] + bias )
+ * with zero fill outside the input.  Replaces every nn.Conv2d on the path: normalization.py:85-89
+ * (mlp_shared/gamma/beta), architecture.py:24-27 (conv_0/1/s), generator.py:30,48 (fc, conv_img),
+ * encoder.py:23-38, discriminator.py:84-96.  Stride-2 convolutions are expressed on a
+ * space-to-depth input (s2e_space_to_depth) so one kernel family serves all geometries; the data
+ * gradient is the same operator with negated taps and transposed weights.
+ * Wp is bf16 [ntaps][Cout][Cin] (s2e_pack_weight).  `scale` is a device scalar (1/sigma of the
+ * spectral norm, normalization.py:26 / architecture.py:31-34) or NULL.
+ * impl = S2E_IMPL_TC requires Cin % 64 == 0 and Cout % 8 == 0; tile = tile_w*tile_h*tile_b <= 128 pixels.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B, Hi, Wi, Cin;
+  int Ho, Wo, Cout;
+  int ntaps;
+  int tap_dy[S2E_MAX_TAPS];
+  int tap_dx[S2E_MAX_TAPS];
+  int act;
+  int tile_w, tile_h, tile_b; /* TC forward tile (<=128 px); 0 = choose inside */
+  int ktile_w, ktile_h, ktile_b; /* TC wgrad pixel tile (multiple of 16, <=64 px); 0 = choose inside */
+} s2e_conv_t;
+
+int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
+                    void* y, int impl, void* stream);
+/* dWp[t][co][ci] += sum_pixels dy[p,co] * x[p+tap_t,ci]   (fp32, atomically accumulated; caller zeroes) */
+int s2e_tapconv_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, int impl, void* stream);
+
+/* OIHW fp32 master weight -> bf16 tap-major.  stride 1: taps (r,s) row-major, offset (r-pad, s-pad).
+ * stride 2: space-to-depth taps (a,b), a in [floor(-pad/2), floor((k-1-pad)/2)], channel (i*2+j)*Cin+ci,
+ * r = 2a+i+pad.  transposed=1 emits [t][Cin'][Cout] (data-gradient operand). */
+int s2e_pack_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int stride, int pad, int transposed,
+                    void* out_bf16, void* stream);
+int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, int* dx); /* host helper */
+/* tap-major fp32 weight gradient -> OIHW, with the spectral-norm chain rule when u != NULL:
+ * dW_orig = inv_sigma * (G - inv_sigma * <G, W_orig> u v^T).  `dot` is a 1-float device scratch. */
+int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, const float* w_orig,
+                     const float* u, const float* v, const float* inv_sigma, float* dot, float* dw_oihw,
+                     int accumulate, void* stream);
+/* torch.nn.utils.spectral_norm power iteration (one step) on W viewed as (rows, cols):
+ * v <- normalize(W^T u), u <- normalize(W v), inv_sigma <- 1 / (u . W v); eps 1e-12. scratch: rows+cols+4 floats */
+int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
+                            void* stream);
+
+/* [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] with channel (i*2+j)*C+c = x[2h+i, 2w+j, c] (zero beyond the edge),
+ * and its adjoint (gradient) */
+int s2e_space_to_depth(const void* x, int B, int H, int W, int C, void* y, void* stream);
+int s2e_depth_to_space(const void* dy, int B, int H, int W, int C, void* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SPADE+Style normalisation / modulation (normalization.py:91-105,161-169,184-192):
+ *   out = act( 0.5 * [ (x-mean)*rstd*(1+gamma) + beta  +  x*(1+s0) + s1 ] )
+ * x [B,HW,C] bf16, gb [B,HW,2C] bf16 (gamma | beta), style [B,2C] fp32 (s0 | s1).  mean/rstd are per
+ * channel (param-free BatchNorm2d, training mode) or per (sample, channel) (InstanceNorm2d).
+ * ------------------------------------------------------------------------------------------ */
+/* acc: double [G][2][C] (G = per_sample ? B : 1), zeroed inside. */
+int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* acc, void* stream);
+/* mean/rstd float [G][C]; running_* may be NULL; biased var for rstd, unbiased for running_var */
+int s2e_norm_finalize(const double* acc, int G, int C, double count, float eps, float* mean, float* rstd,
+                      float* running_mean, float* running_var, float momentum, int64_t* num_batches_tracked,
+                      void* stream);
+int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd,
+                        int B, int HW, int C, int per_sample, int act, void* out, void* stream);
+/* backward: racc double [B][4][C] zeroed inside. `out` = saved forward output (sign for the lrelu mask). */
+int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const void* gb, const float* style,
+                        const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act,
+                        double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, void* stream);
+
+/* InstanceNorm2d(affine=False)+optional LeakyReLU on NHWC bf16 (normalization.py:41; discriminator.py:88-92;
+ * encoder.py:23-38).  in_scale: optional device scalar multiplied into x first (1/sigma). */
+int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, double* acc, float* mean, float* rstd,
+                     void* y, void* stream);
+int s2e_instnorm_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, int B, int HW,
+                     int C, int act, double* racc, void* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------ elementwise */
+int s2e_upsample2x_fwd(const void* x, int B, int H, int W, int C, void* y, void* stream);     /* generator.py:50 */
+int s2e_upsample2x_bwd(const void* dy, int B, int H, int W, int C, void* dx, void* stream);
+int s2e_add(const void* a, const void* b, long long n, void* y, void* stream);                /* architecture.py:52 */
+int s2e_act_fwd(const void* x, long long n, int act, void* y, void* stream);                  /* generator.py:98 */
+int s2e_act_bwd(const void* dy, const void* y, long long n, int act, void* dx, void* stream); /* mask from output sign */
+/* F.avg_pool2d(3, stride 2, pad 1, count_include_pad=False) on NHWC bf16 (discriminator.py:46-49) */
+int s2e_avgpool3s2_fwd(const void* x, int B, int H, int W, int C, void* y, void* stream);
+int s2e_avgpool3s2_bwd(const void* dy, int B, int H, int W, int C, void* dx, void* stream);
+/* F.interpolate(bilinear, align_corners=False) of single-channel-style NCHW fp32 planes -> bf16 (encoder.py:55) */
+int s2e_bilinear_fwd(const float* x, int N, int Hs, int Ws, int Hd, int Wd, void* y_bf16, void* stream);
+int s2e_bilinear_bwd(const void* dy_bf16, int N, int Hs, int Ws, int Hd, int Wd, float* dx, void* stream);
+/* D input: cat([seg, fake],1) / cat([seg, real],1) / cat(.,0) as NHWC bf16 with Cpad channels (pix2pix_model.py:328-338) */
+int s2e_make_d_input(const float* seg_nchw, const float* fake, const float* real, int B, int nc, int H, int W,
+                     int Cpad, void* out, void* stream);
+/* tanh on fp32 output of conv_img and its backward (generator.py:99) */
+int s2e_tanh_fwd(const void* x_bf16, long long n, float* y, void* stream);
+int s2e_tanh_bwd(const float* dy, const float* y, long long n, void* dx_bf16, void* stream);
+/* gradient of the fake image w.r.t. the D input channel nc (first B samples) -> fp32 (B,1,H,W) */
+int s2e_d_input_grad(const void* dxin, int B, int nc, int H, int W, int Cpad, float* dfake, void* stream);
+
+/* small fp32 linear layers: y = act(x W^T + b).  FC 16->2C (normalization.py:134-141), fc_mu/fc_var
+ * (encoder.py:68-71).  in_nhwc_hw > 0: x is bf16 NHWC [M, hw, K/hw] flattened in NCHW order with LeakyReLU(0.2)
+ * applied to the input first (encoder.py:64-67). */
+int s2e_linear_fwd(const void* x, const float* w, const float* b, int M, int N, int K, int act, int in_nhwc_hw,
+                   float* y, void* stream);
+int s2e_linear_bwd(const float* dy, const float* y, const void* x, const float* w, int M, int N, int K, int act,
+                   int in_nhwc_hw, void* dx, float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------ losses
+ * Reductions write fp32 scalars: out[0] (+)= coef * sum(f(x)).  loss.py:58-83, pix2pix_model.py:193-241. */
+#define S2E_RED_SUM 0        /* x            (hinge G: -mean(x))        */
+#define S2E_RED_HINGE_REAL 1 /* min(x-1,0)                              */
+#define S2E_RED_HINGE_FAKE 2 /* min(-x-1,0)                             */
+#define S2E_RED_L1 3         /* |x-y|                                   */
+#define S2E_RED_L2 4         /* (x-y)^2                                 */
+int s2e_reduce_loss(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float* out,
+                    int accumulate, void* stream);
+/* dx (+)= gout[0] * coef * f'(x)   (dx same dtype as x) */
+int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef,
+                        const float* gout, void* dx, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------ optimizer
+ * torch.optim.Adam single-tensor step (pix2pix_model.py:105-108); step = 1-based step count. */
+int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream);
+int s2e_fill_f32(float* p, long long n, float value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEG2EYE_B200_H_ */

@@ -1,0 +1,596 @@
+// Tap-convolution as implicit GEMM on tcgen05 / TMEM, operands staged by TMA (sm_100a).
+//
+// Forward-like kernel (also used for the data gradient with transposed weights / negated taps):
+//   D[128 pixels x BN couts] = sum over taps, 64-channel blocks of  A(tap) [128 x 64] * W(tap)^T [64 x BN]
+//   A tile = one 4-D TMA box {64 ch, TW, TH, TB} of the NHWC input at (w0+dx, h0+dy): halo and padding are
+//   TMA out-of-bounds zero fill, so no im2col is ever materialised.  Both operands K-major, SWIZZLE_128B.
+//   Persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-5 = epilogue
+//   (tcgen05.ld -> scale/bias/act -> bf16 -> swizzled smem -> TMA store).  TMEM accumulator double buffered.
+//
+// Weight-gradient kernel:
+//   dW[tap][128 couts x BN cins] += sum over pixel tiles  dY^T [128 x KP] * X(tap) [KP x BN]
+//   Both operands are MN-major (channels contiguous, pixels = K), again straight out of 4-D TMA boxes.
+//   Split-K over pixel tiles; fp32 accumulators are reduced into global memory with vector red.add.
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements = 128 bytes = swizzle span
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int OUT_BUF_BYTES = BM * 128;
+constexpr int NUM_THREADS = 192;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// NHWC bf16 tensor [B][H][W][C] -> 4-D map {C, W, H, B}, box {64, bw, bh, bb}
+int make_map_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bb) {
+  EncodeTiledFn enc = get_encode();
+  S2E_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  S2E_REQUIRE(((uintptr_t)ptr & 15) == 0 && (C % 8) == 0, "TMA needs 16B-aligned base and C %% 8 == 0 (C=%d)", C);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  S2E_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc B%d H%d W%d C%d box %d,%d,%d) failed: %d", B, H, W, C, bw,
+              bh, bb, (int)r);
+  return S2E_OK;
+}
+// packed weights [T][N][K] bf16 -> 3-D map {K, N, T}, box {64, bn, 1}
+int make_map_w(CUtensorMap* m, const void* ptr, int T, int N, int K, int bn) {
+  EncodeTiledFn enc = get_encode();
+  S2E_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  S2E_REQUIRE(((uintptr_t)ptr & 15) == 0 && (K % 8) == 0, "TMA needs 16B-aligned base and K %% 8 == 0");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)T};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  S2E_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights T%d N%d K%d) failed: %d", T, N, K, (int)r);
+  return S2E_OK;
+}
+
+struct TapTable {
+  int n;
+  int dy[S2E_MAX_TAPS];
+  int dx[S2E_MAX_TAPS];
+};
+
+// ================================================================================ forward-like kernel
+struct FwdParams {
+  int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles;
+  int TW, TH, TB;
+  int Cout, kc_per_tap, act;
+  uint32_t a_box_bytes;
+  const float* bias;
+  const float* scale;
+  TapTable taps;
+};
+
+template <int BN>
+struct FwdCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 5 : 6);
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BUF_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmY, const FwdParams p) {
+  using Cfg = FwdCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_buf = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(out_buf + 2 * OUT_BUF_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmY);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.taps.n * p.kc_per_tap;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int n_idx = t % p.tiles_n;
+        int m = t / p.tiles_n;
+        int w_idx = m % p.tiles_w;
+        m /= p.tiles_w;
+        int h_idx = m % p.tiles_h;
+        int b_idx = m / p.tiles_h;
+        const int w0 = w_idx * p.TW, h0 = h_idx * p.TH, b0 = b_idx * p.TB, n0 = n_idx * BN;
+        for (int tap = 0; tap < p.taps.n; ++tap) {
+          const int dy = p.taps.dy[tap], dx = p.taps.dx[tap];
+          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            ptx::mbar_expect_tx(&full[stage], p.a_box_bytes + Cfg::B_STAGE_BYTES);
+            ptx::tma_load_4d(sa, &tmA, &full[stage], kc * BK, w0 + dx, h0 + dy, b0);
+            ptx::tma_load_3d(sb, &tmB, &full[stage], kc * BK, n0, tap);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 32, 0, 1024);
+            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const bool store_thread = (threadIdx.x == 64);
+    const float scale = p.scale ? __ldg(p.scale) : 1.0f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int n_idx = t % p.tiles_n;
+      int m = t / p.tiles_n;
+      int w_idx = m % p.tiles_w;
+      m /= p.tiles_w;
+      int h_idx = m % p.tiles_h;
+      int b_idx = m / p.tiles_h;
+      const int w0 = w_idx * p.TW, h0 = h_idx * p.TH, b0 = b_idx * p.TB, n0 = n_idx * BN;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 64; ++ch) {
+        const int nbase = n0 + ch * 64;
+        if (nbase >= p.Cout) break;
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 64);
+        ptx::tmem_ld_32x32(taddr, r);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(taddr + 32, r + 32);
+        ptx::tmem_ld_wait();
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (store_thread) ptx::tma_store_wait_read<1>();
+        ptx::named_bar_sync(1, 128);
+        uint8_t* ob = out_buf + buf * OUT_BUF_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = j * 8 + e * 2;
+            float v0 = __uint_as_float(r[c]) * scale;
+            float v1 = __uint_as_float(r[c + 1]) * scale;
+            if (p.bias) {
+              v0 += (nbase + c < p.Cout) ? __ldg(p.bias + nbase + c) : 0.f;
+              v1 += (nbase + c + 1 < p.Cout) ? __ldg(p.bias + nbase + c + 1) : 0.f;
+            }
+            pk[e] = pack2_bf16(act_apply(v0, p.act), act_apply(v1, p.act));
+          }
+          *reinterpret_cast<uint4*>(ob + ((j ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(2, 128);
+        if (store_thread) {
+          ptx::tma_store_4d(&tmY, out_buf + buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
+          ptx::tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (store_thread) ptx::tma_store_wait<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+void choose_fwd_tile(int B, int H, int W, int* tw, int* th, int* tb) {
+  long long best = -1;
+  int bw = 1, bh = 1, bb = 1;
+  for (int w = 1; w <= W && w <= BM; ++w) {
+    for (int h = 1; h <= H && w * h <= BM; ++h) {
+      int b = BM / (w * h);
+      if (b > B) b = B;
+      if (b < 1) b = 1;
+      long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(B, b);
+      // prefer fewer tiles; tie -> wider rows (longer contiguous TMA runs)
+      long long score = tiles * 1024 - w;
+      if (best < 0 || score < best) {
+        best = score;
+        bw = w;
+        bh = h;
+        bb = b;
+      }
+    }
+  }
+  *tw = bw;
+  *th = bh;
+  *tb = bb;
+}
+
+template <int BN>
+int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale, void* y,
+               cudaStream_t stream) {
+  using Cfg = FwdCfg<BN>;
+  int tw = d->tile_w, th = d->tile_h, tb = d->tile_b;
+  if (tw <= 0 || th <= 0 || tb <= 0) choose_fwd_tile(d->B, d->Ho, d->Wo, &tw, &th, &tb);
+  S2E_REQUIRE(tw * th * tb <= BM && tw <= 256 && th <= 256 && tb <= 256, "bad forward tile %dx%dx%d", tw, th, tb);
+  CUtensorMap tmA, tmB, tmY;
+  int rc;
+  if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
+  if ((rc = make_map_w(&tmB, wp, d->ntaps, d->Cout, d->Cin, BN)) != S2E_OK) return rc;
+  if ((rc = make_map_nhwc(&tmY, y, d->B, d->Ho, d->Wo, d->Cout, tw, th, tb)) != S2E_OK) return rc;
+  FwdParams p;
+  p.tiles_w = ceil_div(d->Wo, tw);
+  p.tiles_h = ceil_div(d->Ho, th);
+  p.tiles_b = ceil_div(d->B, tb);
+  p.tiles_n = ceil_div(d->Cout, BN);
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+  p.TW = tw;
+  p.TH = th;
+  p.TB = tb;
+  p.Cout = d->Cout;
+  p.kc_per_tap = d->Cin / BK;
+  p.act = d->act;
+  p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);
+  p.bias = bias;
+  p.scale = scale;
+  p.taps.n = d->ntaps;
+  for (int i = 0; i < d->ntaps; ++i) {
+    p.taps.dy[i] = d->tap_dy[i];
+    p.taps.dx[i] = d->tap_dx[i];
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < s2e_num_sms() ? p.num_tiles : s2e_num_sms();
+  tapconv_fwd_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, p);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+// ================================================================================ weight-gradient kernel
+struct WgParams {
+  int Cout, Cin;
+  int mt, nt, ksplit;            // tiles over Cout (128), Cin (BN), split-K
+  int kt_w, kt_h, kt_b, kt_total;  // pixel tiles
+  int KTW, KTH, KTB, KP;
+  int swap_lbo_sbo;
+  float* dwp;
+  TapTable taps;
+};
+
+template <int BN>
+struct WgCfg {
+  static constexpr int A_BYTES = 2 * 64 * 128;          // 128 couts x 64 pixels max
+  static constexpr int B_BYTES = (BN / 64) * 64 * 128;  // BN cins x 64 pixels max
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgParams p) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmDY);
+    ptx::prefetch_tmap(&tmX);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item decode: blockIdx.x = ((tap * mt + m) * nt + n) * ksplit + ks
+  int wi = blockIdx.x;
+  const int ks = wi % p.ksplit;
+  wi /= p.ksplit;
+  const int n_idx = wi % p.nt;
+  wi /= p.nt;
+  const int m_idx = wi % p.mt;
+  const int tap = wi / p.mt;
+  const int m0 = m_idx * 128, n0 = n_idx * BN;
+  const int k_begin = (int)(((long long)p.kt_total * ks) / p.ksplit);
+  const int k_end = (int)(((long long)p.kt_total * (ks + 1)) / p.ksplit);
+  const int nk = k_end - k_begin;
+  const uint32_t blk_bytes = (uint32_t)p.KP * 128u;  // one 64-channel block of KP pixels
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int dy = p.taps.dy[tap], dx = p.taps.dx[tap];
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        int r = kt;
+        const int w_idx = r % p.kt_w;
+        r /= p.kt_w;
+        const int h_idx = r % p.kt_h;
+        const int b_idx = r / p.kt_h;
+        const int w0 = w_idx * p.KTW, h0 = h_idx * p.KTH, b0 = b_idx * p.KTB;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        ptx::mbar_expect_tx(&full[stage], blk_bytes * (2 + BN / 64));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) ptx::tma_load_4d(sa + j * blk_bytes, &tmDY, &full[stage], m0 + j * 64, w0, h0, b0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          ptx::tma_load_4d(sb + j * blk_bytes, &tmX, &full[stage], n0 + j * 64, w0 + dx, h0 + dy, b0);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int kmma = p.KP / 16;
+    const uint32_t lbo = p.swap_lbo_sbo ? 1024u : blk_bytes;
+    const uint32_t sbo = p.swap_lbo_sbo ? blk_bytes : 1024u;
+    for (int i = 0; i < nk; ++i) {
+      ptx::mbar_wait(&full[stage], phase);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        for (int k = 0; k < kmma; ++k) {
+          const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 2048, lbo, sbo);
+          const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 2048, lbo, sbo);
+          ptx::umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[stage]);
+        if (i == nk - 1) ptx::umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == Cfg::STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (nk > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int co = m0 + row;
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    float* dst_row = p.dwp + ((size_t)tap * p.Cout + (size_t)(co < p.Cout ? co : 0)) * p.Cin + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.Cin) break;  // warp-uniform
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (co < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + c0 + j + 3 < p.Cin) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + j),
+                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                         "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (n0 + c0 + j + e < p.Cin) atomicAdd(dst_row + c0 + j + e, __uint_as_float(r[j + e]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+void choose_k_tile(int B, int H, int W, int* tw, int* th, int* tb) {
+  long long best = -1;
+  int bw = 16, bh = 1, bb = 1;
+  for (int w = 1; w <= 64; ++w) {
+    for (int h = 1; w * h <= 64; ++h) {
+      for (int b = 1; w * h * b <= 64; ++b) {
+        int prod = w * h * b;
+        if (prod % 16) continue;
+        if ((w > W && w > 16) || (h > H && h > 1 && prod > 16) || (b > B && b > 1)) continue;
+        long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(B, b);
+        long long padded = tiles * prod;
+        long long score = padded * 4096 + tiles * 8 - (w >= 8 ? 1 : 0);
+        if (best < 0 || score < best) {
+          best = score;
+          bw = w;
+          bh = h;
+          bb = b;
+        }
+      }
+    }
+  }
+  *tw = bw;
+  *th = bh;
+  *tb = bb;
+}
+
+template <int BN>
+int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {
+  using Cfg = WgCfg<BN>;
+  int tw = d->ktile_w, th = d->ktile_h, tb = d->ktile_b;
+  if (tw <= 0 || th <= 0 || tb <= 0) choose_k_tile(d->B, d->Ho, d->Wo, &tw, &th, &tb);
+  const int KP = tw * th * tb;
+  S2E_REQUIRE(KP % 16 == 0 && KP <= 64, "bad wgrad pixel tile %dx%dx%d", tw, th, tb);
+  CUtensorMap tmDY, tmX;
+  int rc;
+  if ((rc = make_map_nhwc(&tmDY, dy, d->B, d->Ho, d->Wo, d->Cout, tw, th, tb)) != S2E_OK) return rc;
+  if ((rc = make_map_nhwc(&tmX, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
+  WgParams p;
+  p.Cout = d->Cout;
+  p.Cin = d->Cin;
+  p.mt = ceil_div(d->Cout, 128);
+  p.nt = ceil_div(d->Cin, BN);
+  p.kt_w = ceil_div(d->Wo, tw);
+  p.kt_h = ceil_div(d->Ho, th);
+  p.kt_b = ceil_div(d->B, tb);
+  p.kt_total = p.kt_w * p.kt_h * p.kt_b;
+  p.KTW = tw;
+  p.KTH = th;
+  p.KTB = tb;
+  p.KP = KP;
+  p.swap_lbo_sbo = s2e_debug_get(0);
+  p.dwp = dwp;
+  p.taps.n = d->ntaps;
+  for (int i = 0; i < d->ntaps; ++i) {
+    p.taps.dy[i] = d->tap_dy[i];
+    p.taps.dx[i] = d->tap_dx[i];
+  }
+  const int base = d->ntaps * p.mt * p.nt;
+  int ksplit = ceil_div(2 * s2e_num_sms(), base);
+  int max_split = p.kt_total / 4;  // keep at least ~4 pipeline stages of work per CTA
+  if (max_split < 1) max_split = 1;
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  static bool attr_set = false;
+  if (!attr_set) {
+    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  tapconv_wgrad_kernel<BN><<<base * ksplit, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmDY, tmX, p);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+}  // namespace
+
+int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
+                       void* y, cudaStream_t stream) {
+  S2E_REQUIRE(d->Cin % 64 == 0 && d->Cout % 8 == 0, "tcgen05 tapconv needs Cin %% 64 == 0, Cout %% 8 == 0 (Cin=%d Cout=%d)",
+              d->Cin, d->Cout);
+  if (d->Cout >= 256) return launch_fwd<256>(d, x, wp, bias, scale, y, stream);
+  if (d->Cout >= 128) return launch_fwd<128>(d, x, wp, bias, scale, y, stream);
+  return launch_fwd<64>(d, x, wp, bias, scale, y, stream);
+}
+
+int s2e_tapconv_wgrad_tc(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {
+  S2E_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0 && d->Cin >= 64 && d->Cout >= 64,
+              "tcgen05 wgrad needs Cin,Cout %% 8 == 0 and >= 64 (Cin=%d Cout=%d)", d->Cin, d->Cout);
+  if (d->Cin >= 256) return launch_wgrad<256>(d, x, dy, dwp, stream);
+  if (d->Cin >= 128) return launch_wgrad<128>(d, x, dy, dwp, stream);
+  return launch_wgrad<64>(d, x, dy, dwp, stream);
+}

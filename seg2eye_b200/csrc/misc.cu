@@ -1,0 +1,860 @@
+// Integer path, layout, weight packing, spectral norm, resampling, small linear layers, losses, Adam.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------ host state
+static thread_local char g_err[512] = "";
+static int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+void s2e_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int s2e_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+int s2e_debug_get(int key) { return (key >= 0 && key < 8) ? g_debug[key] : 0; }
+
+int s2e_tapconv_fwd_tc(const s2e_conv_t*, const void*, const void*, const float*, const float*, void*, cudaStream_t);
+int s2e_tapconv_wgrad_tc(const s2e_conv_t*, const void*, const void*, float*, cudaStream_t);
+int s2e_tapconv_fwd_simt(const s2e_conv_t*, const void*, const void*, const float*, const float*, void*, cudaStream_t);
+int s2e_tapconv_wgrad_simt(const s2e_conv_t*, const void*, const void*, float*, cudaStream_t);
+
+namespace {
+
+constexpr int NT = 256;
+inline int grid1d(long long n, int per = NT) {
+  long long g = (n + per - 1) / per;
+  const long long cap = (long long)s2e_num_sms() * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+#define GRID_STRIDE(i, n) for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float sh[32];
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_sum(v);
+  return v;  // valid in thread 0
+}
+
+inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+__device__ __forceinline__ int d_floor_div2(int a) { return (a >= 0) ? (a >> 1) : -((-a + 1) >> 1); }
+
+// ------------------------------------------------------------------------------------------ integer path
+__global__ void onehot_kernel(const long long* __restrict__ label, long long HW, int nc, long long n, float* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    const long long hw = i % HW;
+    const int c = (int)((i / HW) % nc);
+    const long long b = i / (HW * nc);
+    out[i] = (label[b * HW + hw] == c) ? 1.0f : 0.0f;
+  }
+}
+
+__global__ void seg_nearest_kernel(const float* __restrict__ seg, int C, int Hs, int Ws, int Hd, int Wd, int Cpad, float sh,
+                                   float sw, long long n, bf16* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % Cpad);
+    long long p = i / Cpad;
+    const int wd = (int)(p % Wd);
+    p /= Wd;
+    const int hd = (int)(p % Hd);
+    const int b = (int)(p / Hd);
+    float v = 0.f;
+    if (c < C) {
+      const int hs = min((int)floorf(hd * sh), Hs - 1);
+      const int ws = min((int)floorf(wd * sw), Ws - 1);
+      v = seg[(((long long)b * C + c) * Hs + hs) * Ws + ws];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void nchw2nhwc_kernel(const float* __restrict__ x, int C, int H, int W, long long n, bf16* __restrict__ y) {
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const long long b = p / H;
+    y[i] = __float2bfloat16(x[((b * C + c) * H + h) * W + w]);
+  }
+}
+__global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, int C, int H, int W, long long n, float* __restrict__ y) {
+  GRID_STRIDE(i, n) {
+    const int w = (int)(i % W);
+    long long p = i / W;
+    const int h = (int)(p % H);
+    p /= H;
+    const int c = (int)(p % C);
+    const long long b = p / C;
+    y[i] = __bfloat162float(x[((b * H + h) * W + w) * C + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+struct PackGeom {
+  int Cout, Cin, kh, kw, stride, pad;
+  int amin, bmin, na, nb;  // stride-2 tap grid
+};
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, PackGeom g, int transposed, long long n, bf16* __restrict__ out) {
+  const int CinP = g.stride == 2 ? 4 * g.Cin : g.Cin;
+  GRID_STRIDE(i, n) {
+    int cp, co;
+    long long r0 = i;
+    if (transposed) {
+      co = (int)(r0 % g.Cout);
+      r0 /= g.Cout;
+      cp = (int)(r0 % CinP);
+      r0 /= CinP;
+    } else {
+      cp = (int)(r0 % CinP);
+      r0 /= CinP;
+      co = (int)(r0 % g.Cout);
+      r0 /= g.Cout;
+    }
+    const int t = (int)r0;
+    int r, s, ci;
+    if (g.stride == 1) {
+      r = t / g.kw;
+      s = t % g.kw;
+      ci = cp;
+    } else {
+      const int a = g.amin + t / g.nb, b = g.bmin + t % g.nb;
+      const int ph = cp / g.Cin;
+      ci = cp % g.Cin;
+      r = 2 * a + (ph >> 1) + g.pad;
+      s = 2 * b + (ph & 1) + g.pad;
+    }
+    float v = 0.f;
+    if (r >= 0 && r < g.kh && s >= 0 && s < g.kw) v = w[(((long long)co * g.Cin + ci) * g.kh + r) * g.kw + s];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+__device__ __forceinline__ long long packed_index(const PackGeom& g, int co, int ci, int r, int s) {
+  if (g.stride == 1) return ((long long)(r * g.kw + s) * g.Cout + co) * g.Cin + ci;
+  const int rr = r - g.pad, ss = s - g.pad;
+  const int i = ((rr % 2) + 2) % 2, j = ((ss % 2) + 2) % 2;
+  const int a = (rr - i) / 2, b = (ss - j) / 2;
+  const int t = (a - g.amin) * g.nb + (b - g.bmin);
+  return ((long long)t * g.Cout + co) * (4 * g.Cin) + (i * 2 + j) * g.Cin + ci;
+}
+
+__global__ void wgrad_dot_kernel(const float* __restrict__ dwp, const float* __restrict__ w, PackGeom g, long long n, float* dot) {
+  float acc = 0.f;
+  GRID_STRIDE(i, n) {
+    const int s = (int)(i % g.kw);
+    long long r0 = i / g.kw;
+    const int r = (int)(r0 % g.kh);
+    r0 /= g.kh;
+    const int ci = (int)(r0 % g.Cin);
+    const int co = (int)(r0 / g.Cin);
+    acc = fmaf(dwp[packed_index(g, co, ci, r, s)], w[i], acc);
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(dot, acc);
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, PackGeom g, const float* __restrict__ u, const float* __restrict__ v,
+                                    const float* __restrict__ inv_sigma, const float* __restrict__ dot, long long n, int accumulate,
+                                    float* __restrict__ dw) {
+  const float is = inv_sigma ? *inv_sigma : 1.f;
+  const float dt = u ? *dot : 0.f;
+  const int kk = g.kh * g.kw;
+  GRID_STRIDE(i, n) {
+    const int s = (int)(i % g.kw);
+    long long r0 = i / g.kw;
+    const int r = (int)(r0 % g.kh);
+    r0 /= g.kh;
+    const int ci = (int)(r0 % g.Cin);
+    const int co = (int)(r0 / g.Cin);
+    float gval = dwp[packed_index(g, co, ci, r, s)];
+    if (u) gval = is * (gval - is * dt * u[co] * v[ci * kk + r * g.kw + s]);
+    dw[i] = accumulate ? dw[i] + gval : gval;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ spectral norm
+// t[c] += sum_{r in chunk} W[r][c] u[r]      grid (col blocks, row chunks)
+__global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows, int cols, int rchunk, float* t) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rchunk, r1 = min(rows, r0 + rchunk);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc = fmaf(w[(long long)r * cols + c], u[r], acc);
+  atomicAdd(t + c, acc);
+}
+// x <- x / max(||x||, eps) ; single block.  If sigma_out: also *sigma_out = 1 / dot(x_normalized, x_raw)
+__global__ void sn_normalize_kernel(const float* __restrict__ raw, int n, float* __restrict__ outv, float* inv_sigma) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(raw[i], raw[i], acc);
+  __shared__ float s_norm;
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) s_norm = acc;
+  __syncthreads();
+  const float nsq = s_norm;
+  const float denom = fmaxf(sqrtf(nsq), 1e-12f);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) outv[i] = raw[i] / denom;
+  if (inv_sigma && threadIdx.x == 0) *inv_sigma = 1.f / (nsq / denom);  // sigma = u . (W v) = ||Wv||^2 / max(||Wv||,eps)
+}
+// s[r] = W[r][:] . v   one warp per row
+__global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ v, int rows, int cols, float* s) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int c = lane; c < cols; c += 32) acc = fmaf(w[(long long)r * cols + c], v[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) s[r] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ space <-> depth
+__global__ void s2d_kernel(const bf16* __restrict__ x, int H, int W, int C, int H2, int W2, long long n, bf16* __restrict__ y) {
+  GRID_STRIDE(i, n) {  // i over output [B][H2][W2][4][C]
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int ph = (int)(p % 4);
+    p /= 4;
+    const int w2 = (int)(p % W2);
+    p /= W2;
+    const int h2 = (int)(p % H2);
+    const long long b = p / H2;
+    const int h = 2 * h2 + (ph >> 1), w = 2 * w2 + (ph & 1);
+    y[i] = (h < H && w < W) ? x[((b * H + h) * W + w) * C + c] : __float2bfloat16(0.f);
+  }
+}
+__global__ void d2s_kernel(const bf16* __restrict__ dy, int H, int W, int C, int H2, int W2, long long n, bf16* __restrict__ dx) {
+  GRID_STRIDE(i, n) {  // i over dx [B][H][W][C]
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const long long b = p / H;
+    const int ph = (h & 1) * 2 + (w & 1);
+    dx[i] = dy[(((b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + ph) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ resampling
+__global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x, int H, int W, int C8, long long n, bf16* __restrict__ y) {
+  GRID_STRIDE(i, n) {  // over output vectors [B][2H][2W][C8]
+    const int c = (int)(i % C8);
+    long long p = i / C8;
+    const int w = (int)(p % (2 * W));
+    p /= 2 * W;
+    const int h = (int)(p % (2 * H));
+    const long long b = p / (2 * H);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (((b * H + (h >> 1)) * W + (w >> 1)) * C8 + c) * 8);
+    *reinterpret_cast<uint4*>(y + i * 8) = v;
+  }
+}
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, int H, int W, int C8, long long n, bf16* __restrict__ dx) {
+  GRID_STRIDE(i, n) {  // over input vectors [B][H][W][C8]
+    const int c = (int)(i % C8);
+    long long p = i / C8;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const long long b = p / H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, f[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long src = (((b * 2 * H + 2 * h + (q >> 1)) * 2 * W + 2 * w + (q & 1)) * C8 + c) * 8;
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + src), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    *reinterpret_cast<bf16x8*>(dx + i * 8) = pack8(acc);
+  }
+}
+
+__global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, int H, int W, int C, int Ho, int Wo, long long n, bf16* __restrict__ y) {
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int wo = (int)(p % Wo);
+    p /= Wo;
+    const int ho = (int)(p % Ho);
+    const long long b = p / Ho;
+    float acc = 0.f;
+    int cnt = 0;
+    for (int dh = -1; dh <= 1; ++dh)
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int h = 2 * ho + dh, w = 2 * wo + dw;
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          acc += __bfloat162float(x[((b * H + h) * W + w) * C + c]);
+          ++cnt;
+        }
+      }
+    y[i] = __float2bfloat16(acc / (float)cnt);
+  }
+}
+__device__ __forceinline__ int pool_cnt(int o, int L) {  // valid taps of window o along a length-L axis
+  int c = 0;
+  for (int d = -1; d <= 1; ++d) c += (2 * o + d >= 0 && 2 * o + d < L);
+  return c;
+}
+__global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, int H, int W, int C, int Ho, int Wo, long long n, bf16* __restrict__ dx) {
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const long long b = p / H;
+    float acc = 0.f;
+    for (int ho = (h) / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      for (int wo = (w) / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo < 0 || wo >= Wo) continue;
+        acc += __bfloat162float(dy[((b * Ho + ho) * Wo + wo) * C + c]) / (float)(pool_cnt(ho, H) * pool_cnt(wo, W));
+      }
+    }
+    dx[i] = __float2bfloat16(acc);
+  }
+}
+
+__device__ __forceinline__ void bilin_src(int d, float scale, int in, int* i0, int* i1, float* l1) {
+  float s = ((float)d + 0.5f) * scale - 0.5f;
+  if (s < 0.f) s = 0.f;
+  int a = (int)s;
+  if (a > in - 1) a = in - 1;
+  *i0 = a;
+  *i1 = a + ((a < in - 1) ? 1 : 0);
+  *l1 = s - (float)a;
+}
+__global__ void bilinear_fwd_kernel(const float* __restrict__ x, int Hs, int Ws, int Hd, int Wd, float sh, float sw, long long n,
+                                    bf16* __restrict__ y) {
+  GRID_STRIDE(i, n) {
+    const int wd = (int)(i % Wd);
+    long long p = i / Wd;
+    const int hd = (int)(p % Hd);
+    const long long nn = p / Hd;
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilin_src(hd, sh, Hs, &h0, &h1, &lh);
+    bilin_src(wd, sw, Ws, &w0, &w1, &lw);
+    const float* src = x + nn * Hs * Ws;
+    const float v = (1.f - lh) * ((1.f - lw) * src[h0 * Ws + w0] + lw * src[h0 * Ws + w1]) +
+                    lh * ((1.f - lw) * src[h1 * Ws + w0] + lw * src[h1 * Ws + w1]);
+    y[i] = __float2bfloat16(v);
+  }
+}
+__global__ void bilinear_bwd_kernel(const bf16* __restrict__ dy, int Hs, int Ws, int Hd, int Wd, float sh, float sw, long long n,
+                                    float* __restrict__ dx) {
+  GRID_STRIDE(i, n) {
+    const int wd = (int)(i % Wd);
+    long long p = i / Wd;
+    const int hd = (int)(p % Hd);
+    const long long nn = p / Hd;
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilin_src(hd, sh, Hs, &h0, &h1, &lh);
+    bilin_src(wd, sw, Ws, &w0, &w1, &lw);
+    const float g = __bfloat162float(dy[i]);
+    float* dst = dx + nn * Hs * Ws;
+    atomicAdd(dst + h0 * Ws + w0, g * (1.f - lh) * (1.f - lw));
+    atomicAdd(dst + h0 * Ws + w1, g * (1.f - lh) * lw);
+    atomicAdd(dst + h1 * Ws + w0, g * lh * (1.f - lw));
+    atomicAdd(dst + h1 * Ws + w1, g * lh * lw);
+  }
+}
+
+__global__ void make_d_input_kernel(const float* __restrict__ seg, const float* __restrict__ fake, const float* __restrict__ real, int B,
+                                    int nc, long long HW, int Cpad, long long n, bf16* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % Cpad);
+    long long p = i / Cpad;
+    const long long hw = p % HW;
+    const int b2 = (int)(p / HW);
+    const int b = b2 % B;
+    float v = 0.f;
+    if (c < nc) v = seg[((long long)b * nc + c) * HW + hw];
+    else if (c == nc) v = (b2 < B ? fake : real)[(long long)b * HW + hw];
+    out[i] = __float2bfloat16(v);
+  }
+}
+__global__ void d_input_grad_kernel(const bf16* __restrict__ dxin, int nc, int Cpad, long long n, float* __restrict__ dfake) {
+  GRID_STRIDE(i, n) dfake[i] = __bfloat162float(dxin[i * Cpad + nc]);
+}
+
+// ------------------------------------------------------------------------------------------ elementwise
+__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long nvec, long long n, bf16* __restrict__ y) {
+  GRID_STRIDE(i, nvec) {
+    float fa[8], fb[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(a + i * 8), fa);
+    unpack8(*reinterpret_cast<const bf16x8*>(b + i * 8), fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+    *reinterpret_cast<bf16x8*>(y + i * 8) = pack8(fa);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x)
+      y[i] = __float2bfloat16(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+__global__ void act_fwd_kernel(const bf16* __restrict__ x, long long n, int act, bf16* __restrict__ y) {
+  GRID_STRIDE(i, n) y[i] = __float2bfloat16(act_apply(__bfloat162float(x[i]), act));
+}
+__global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, long long n, int act, bf16* __restrict__ dx) {
+  GRID_STRIDE(i, n) {
+    const float o = __bfloat162float(y[i]);
+    float g = __bfloat162float(dy[i]);
+    if (act == S2E_ACT_LRELU) g *= (o > 0.f ? 1.f : 0.2f);
+    if (act == S2E_ACT_RELU) g *= (o > 0.f ? 1.f : 0.f);
+    dx[i] = __float2bfloat16(g);
+  }
+}
+__global__ void tanh_fwd_kernel(const bf16* __restrict__ x, long long n, float* __restrict__ y) {
+  GRID_STRIDE(i, n) y[i] = tanhf(__bfloat162float(x[i]));
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n, bf16* __restrict__ dx) {
+  GRID_STRIDE(i, n) dx[i] = __float2bfloat16(dy[i] * (1.f - y[i] * y[i]));
+}
+__global__ void fill_kernel(float* p, long long n, float v) { GRID_STRIDE(i, n) p[i] = v; }
+
+// ------------------------------------------------------------------------------------------ small linear layers
+__device__ __forceinline__ float lin_x(const void* x, int m, int k, int K, int hw) {
+  if (hw <= 0) return ((const float*)x)[(long long)m * K + k];
+  const int Cc = K / hw, c = k / hw, s = k % hw;  // flattened NCHW index k = c*hw + s ; stored NHWC
+  const float v = __bfloat162float(((const bf16*)x)[((long long)m * hw + s) * Cc + c]);
+  return v > 0.f ? v : 0.2f * v;
+}
+__global__ void linear_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int M, int N,
+                                  int K, int act, int hw, float* __restrict__ y) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (o >= M * N) return;
+  const int lane = threadIdx.x & 31, m = o / N, n = o % N;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(lin_x(x, m, k, K, hw), w[(long long)n * K + k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[o] = act_apply(acc + (b ? b[n] : 0.f), act);
+}
+__device__ __forceinline__ float lin_dpre(const float* dy, const float* y, int idx, int act) {
+  float g = dy[idx];
+  if (act == S2E_ACT_LRELU) g *= (y[idx] > 0.f ? 1.f : 0.2f);
+  if (act == S2E_ACT_RELU) g *= (y[idx] > 0.f ? 1.f : 0.f);
+  return g;
+}
+__global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ y, const void* __restrict__ x,
+                                     const float* __restrict__ w, int M, int N, int K, int act, int hw, void* __restrict__ dx) {
+  GRID_STRIDE(i, (long long)M * K) {
+    const int m = (int)(i / K), k = (int)(i % K);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(lin_dpre(dy, y, m * N + n, act), w[(long long)n * K + k], acc);
+    if (hw <= 0) {
+      ((float*)dx)[i] = acc;
+    } else {
+      const int Cc = K / hw, c = k / hw, s = k % hw;
+      const long long xi = ((long long)m * hw + s) * Cc + c;
+      const float xv = __bfloat162float(((const bf16*)x)[xi]);
+      ((bf16*)dx)[xi] = __float2bfloat16(acc * (xv > 0.f ? 1.f : 0.2f));
+    }
+  }
+}
+__global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ y, const void* __restrict__ x, int M, int N,
+                                     int K, int act, int hw, float* __restrict__ dw, float* __restrict__ db) {
+  GRID_STRIDE(i, (long long)N * K) {
+    const int n = (int)(i / K), k = (int)(i % K);
+    float acc = 0.f, accb = 0.f;
+    for (int m = 0; m < M; ++m) {
+      const float g = lin_dpre(dy, y, m * N + n, act);
+      acc = fmaf(g, lin_x(x, m, k, K, hw), acc);
+      accb += g;
+    }
+    dw[i] = acc;
+    if (k == 0 && db) db[n] = accb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ losses
+__device__ __forceinline__ float ld_any(const void* p, long long i, int f32) {
+  return f32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
+}
+__global__ void reduce_loss_kernel(const void* __restrict__ x, const void* __restrict__ y, long long n, int f32, int kind, float coef,
+                                   float* out) {
+  float acc = 0.f;
+  GRID_STRIDE(i, n) {
+    const float a = ld_any(x, i, f32);
+    float v;
+    if (kind == S2E_RED_SUM) v = a;
+    else if (kind == S2E_RED_HINGE_REAL) v = fminf(a - 1.f, 0.f);
+    else if (kind == S2E_RED_HINGE_FAKE) v = fminf(-a - 1.f, 0.f);
+    else {
+      const float d = a - ld_any(y, i, f32);
+      v = (kind == S2E_RED_L1) ? fabsf(d) : d * d;
+    }
+    acc += v;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc * coef);
+}
+__global__ void reduce_loss_bwd_kernel(const void* __restrict__ x, const void* __restrict__ y, long long n, int f32, int kind, float coef,
+                                       const float* __restrict__ gout, void* __restrict__ dx, int accumulate) {
+  const float g0 = gout[0] * coef;
+  GRID_STRIDE(i, n) {
+    const float a = ld_any(x, i, f32);
+    float d;
+    if (kind == S2E_RED_SUM) d = 1.f;
+    else if (kind == S2E_RED_HINGE_REAL) d = (a - 1.f < 0.f) ? 1.f : 0.f;
+    else if (kind == S2E_RED_HINGE_FAKE) d = (-a - 1.f < 0.f) ? -1.f : 0.f;
+    else {
+      const float df = a - ld_any(y, i, f32);
+      d = (kind == S2E_RED_L1) ? (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) : 2.f * df;
+    }
+    d *= g0;
+    if (f32) {
+      float* o = (float*)dx;
+      o[i] = accumulate ? o[i] + d : d;
+    } else {
+      bf16* o = (bf16*)dx;
+      o[i] = __float2bfloat16(accumulate ? __bfloat162float(o[i]) + d : d);
+    }
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  GRID_STRIDE(i, n) {
+    float gi = g[i];
+    if (wd != 0.f) gi = fmaf(wd, p[i], gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+PackGeom make_pack_geom(int Cout, int Cin, int kh, int kw, int stride, int pad) {
+  PackGeom g;
+  g.Cout = Cout;
+  g.Cin = Cin;
+  g.kh = kh;
+  g.kw = kw;
+  g.stride = stride;
+  g.pad = pad;
+  g.amin = floor_div(-pad, 2);
+  g.bmin = floor_div(-pad, 2);
+  g.na = floor_div(kh - 1 - pad, 2) - g.amin + 1;
+  g.nb = floor_div(kw - 1 - pad, 2) - g.bmin + 1;
+  return g;
+}
+
+}  // namespace
+
+// ========================================================================================== C ABI
+extern "C" {
+
+const char* s2e_last_error(void) { return g_err; }
+int s2e_abi_version(void) { return 1; }
+int s2e_debug_set(int key, int value) {
+  if (key < 0 || key >= 8) return S2E_ERR_ARG;
+  g_debug[key] = value;
+  return S2E_OK;
+}
+
+int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale, void* y,
+                    int impl, void* stream) {
+  S2E_REQUIRE(d && d->ntaps >= 1 && d->ntaps <= S2E_MAX_TAPS, "tapconv_fwd: bad tap count");
+  if (impl == S2E_IMPL_SIMT || g_debug[1]) return s2e_tapconv_fwd_simt(d, x, wp, bias, scale, y, (cudaStream_t)stream);
+  return s2e_tapconv_fwd_tc(d, x, wp, bias, scale, y, (cudaStream_t)stream);
+}
+int s2e_tapconv_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, int impl, void* stream) {
+  S2E_REQUIRE(d && d->ntaps >= 1 && d->ntaps <= S2E_MAX_TAPS, "tapconv_wgrad: bad tap count");
+  if (impl == S2E_IMPL_SIMT || g_debug[1]) return s2e_tapconv_wgrad_simt(d, x, dy, dwp, (cudaStream_t)stream);
+  return s2e_tapconv_wgrad_tc(d, x, dy, dwp, (cudaStream_t)stream);
+}
+
+int s2e_onehot_nchw(const int64_t* label, int B, int H, int W, int nc, float* out, void* stream) {
+  const long long n = (long long)B * nc * H * W;
+  if (!n) return S2E_OK;
+  onehot_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const long long*)label, (long long)H * W, nc, n, out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_seg_nearest_nhwc(const float* seg, int B, int C, int Hs, int Ws, int Hd, int Wd, int Cpad, void* out, void* stream) {
+  S2E_REQUIRE(Cpad >= C, "seg_nearest: Cpad < C");
+  const long long n = (long long)B * Hd * Wd * Cpad;
+  if (!n) return S2E_OK;
+  const float sh = (float)Hs / (float)Hd, sw = (float)Ws / (float)Wd;
+  seg_nearest_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(seg, C, Hs, Ws, Hd, Wd, Cpad, sh, sw, n, (bf16*)out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* y, void* stream) {
+  const long long n = (long long)B * C * H * W;
+  if (!n) return S2E_OK;
+  nchw2nhwc_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(x, C, H, W, n, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_nhwc_bf16_to_nchw_f32(const void* x, int B, int C, int H, int W, float* y, void* stream) {
+  const long long n = (long long)B * C * H * W;
+  if (!n) return S2E_OK;
+  nhwc2nchw_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, C, H, W, n, y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, int* dx) {
+  S2E_REQUIRE(stride == 1 || stride == 2, "packed_taps: stride must be 1 or 2");
+  PackGeom g = make_pack_geom(1, 1, kh, kw, stride, pad);
+  int n = 0;
+  if (stride == 1) {
+    for (int r = 0; r < kh; ++r)
+      for (int s = 0; s < kw; ++s) {
+        if (n >= S2E_MAX_TAPS) return S2E_ERR_UNSUPPORTED;
+        dy[n] = r - pad;
+        dx[n] = s - pad;
+        ++n;
+      }
+  } else {
+    for (int a = 0; a < g.na; ++a)
+      for (int b = 0; b < g.nb; ++b) {
+        if (n >= S2E_MAX_TAPS) return S2E_ERR_UNSUPPORTED;
+        dy[n] = g.amin + a;
+        dx[n] = g.bmin + b;
+        ++n;
+      }
+  }
+  *ntaps = n;
+  return S2E_OK;
+}
+int s2e_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, int stride, int pad, int transposed, void* out,
+                    void* stream) {
+  S2E_REQUIRE(stride == 1 || stride == 2, "pack_weight: stride must be 1 or 2");
+  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad);
+  const int T = stride == 1 ? kh * kw : g.na * g.nb;
+  const long long n = (long long)T * Cout * (stride == 2 ? 4 * Cin : Cin);
+  pack_weight_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(w, g, transposed, n, (bf16*)out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, const float* w_orig,
+                     const float* u, const float* v, const float* inv_sigma, float* dot, float* dw, int accumulate,
+                     void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad);
+  const long long n = (long long)Cout * Cin * kh * kw;
+  if (u) {
+    S2E_REQUIRE(v && inv_sigma && dot && w_orig, "unpack_wgrad: spectral args incomplete");
+    S2E_CHECK_CUDA(cudaMemsetAsync(dot, 0, sizeof(float), st));
+    wgrad_dot_kernel<<<grid1d(n), NT, 0, st>>>(dwp, w_orig, g, n, dot);
+    S2E_LAUNCH_CHECK();
+  }
+  unpack_wgrad_kernel<<<grid1d(n), NT, 0, st>>>(dwp, g, u, v, inv_sigma, dot, n, accumulate, dw);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* t = scratch;         // cols
+  float* s = scratch + cols;  // rows
+  S2E_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, st));
+  const int rchunk = 64;
+  dim3 g1(ceil_div(cols, 128), ceil_div(rows, rchunk));
+  sn_wt_u_kernel<<<g1, 128, 0, st>>>(w, u, rows, cols, rchunk, t);
+  S2E_LAUNCH_CHECK();
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(t, cols, v, nullptr);
+  S2E_LAUNCH_CHECK();
+  sn_w_v_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(w, v, rows, cols, s);
+  S2E_LAUNCH_CHECK();
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(s, rows, u, inv_sigma);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_space_to_depth(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const long long n = (long long)B * H2 * W2 * 4 * C;
+  if (!n) return S2E_OK;
+  s2d_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, H2, W2, n, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_depth_to_space(const void* dy, int B, int H, int W, int C, void* dx, void* stream) {
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const long long n = (long long)B * H * W * C;
+  if (!n) return S2E_OK;
+  d2s_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C, H2, W2, n, (bf16*)dx);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_upsample2x_fwd(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  S2E_REQUIRE(C % 8 == 0, "upsample2x needs C %% 8 == 0");
+  const long long n = (long long)B * 4 * H * W * (C / 8);
+  if (!n) return S2E_OK;
+  upsample2x_fwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C / 8, n, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_upsample2x_bwd(const void* dy, int B, int H, int W, int C, void* dx, void* stream) {
+  S2E_REQUIRE(C % 8 == 0, "upsample2x needs C %% 8 == 0");
+  const long long n = (long long)B * H * W * (C / 8);
+  if (!n) return S2E_OK;
+  upsample2x_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C / 8, n, (bf16*)dx);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_add(const void* a, const void* b, long long n, void* y, void* stream) {
+  if (!n) return S2E_OK;
+  S2E_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0, "add: pointers must be 16B aligned");
+  add_kernel<<<grid1d(n / 8 + 1), NT, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, n / 8, n, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_act_fwd(const void* x, long long n, int act, void* y, void* stream) {
+  if (!n) return S2E_OK;
+  act_fwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, n, act, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_act_bwd(const void* dy, const void* y, long long n, int act, void* dx, void* stream) {
+  if (!n) return S2E_OK;
+  act_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)y, n, act, (bf16*)dx);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_avgpool3s2_fwd(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long n = (long long)B * Ho * Wo * C;
+  if (!n) return S2E_OK;
+  avgpool_fwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, Ho, Wo, n, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_avgpool3s2_bwd(const void* dy, int B, int H, int W, int C, void* dx, void* stream) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long n = (long long)B * H * W * C;
+  if (!n) return S2E_OK;
+  avgpool_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C, Ho, Wo, n, (bf16*)dx);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_bilinear_fwd(const float* x, int N, int Hs, int Ws, int Hd, int Wd, void* y, void* stream) {
+  const long long n = (long long)N * Hd * Wd;
+  if (!n) return S2E_OK;
+  bilinear_fwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(x, Hs, Ws, Hd, Wd, (float)Hs / Hd, (float)Ws / Wd, n, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_bilinear_bwd(const void* dy, int N, int Hs, int Ws, int Hd, int Wd, float* dx, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)N * Hd * Wd;
+  S2E_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * Hs * Ws, st));
+  if (!n) return S2E_OK;
+  bilinear_bwd_kernel<<<grid1d(n), NT, 0, st>>>((const bf16*)dy, Hs, Ws, Hd, Wd, (float)Hs / Hd, (float)Ws / Wd, n, dx);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_make_d_input(const float* seg, const float* fake, const float* real, int B, int nc, int H, int W, int Cpad,
+                     void* out, void* stream) {
+  S2E_REQUIRE(Cpad > nc, "make_d_input: Cpad must exceed nc");
+  const long long n = (long long)2 * B * H * W * Cpad;
+  if (!n) return S2E_OK;
+  make_d_input_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(seg, fake, real, B, nc, (long long)H * W, Cpad, n, (bf16*)out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_d_input_grad(const void* dxin, int B, int nc, int H, int W, int Cpad, float* dfake, void* stream) {
+  const long long n = (long long)B * H * W;
+  if (!n) return S2E_OK;
+  d_input_grad_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dxin, nc, Cpad, n, dfake);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_tanh_fwd(const void* x, long long n, float* y, void* stream) {
+  if (!n) return S2E_OK;
+  tanh_fwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, n, y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_tanh_bwd(const float* dy, const float* y, long long n, void* dx, void* stream) {
+  if (!n) return S2E_OK;
+  tanh_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(dy, y, n, (bf16*)dx);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_linear_fwd(const void* x, const float* w, const float* b, int M, int N, int K, int act, int in_nhwc_hw, float* y,
+                   void* stream) {
+  S2E_REQUIRE(in_nhwc_hw <= 0 || K % in_nhwc_hw == 0, "linear_fwd: K must be a multiple of hw");
+  const long long threads = (long long)M * N * 32;
+  if (!threads) return S2E_OK;
+  linear_fwd_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, (cudaStream_t)stream>>>(x, w, b, M, N, K, act, in_nhwc_hw, y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_linear_bwd(const float* dy, const float* y, const void* x, const float* w, int M, int N, int K, int act,
+                   int in_nhwc_hw, void* dx, float* dw, float* db, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx) {
+    linear_bwd_dx_kernel<<<grid1d((long long)M * K), NT, 0, st>>>(dy, y, x, w, M, N, K, act, in_nhwc_hw, dx);
+    S2E_LAUNCH_CHECK();
+  }
+  if (dw) {
+    linear_bwd_dw_kernel<<<grid1d((long long)N * K), NT, 0, st>>>(dy, y, x, M, N, K, act, in_nhwc_hw, dw, db);
+    S2E_LAUNCH_CHECK();
+  }
+  return S2E_OK;
+}
+
+int s2e_reduce_loss(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float* out,
+                    int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) S2E_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  if (!n) return S2E_OK;
+  int g = grid1d(n, NT * 8);
+  reduce_loss_kernel<<<g, NT, 0, st>>>(x, y, n, x_is_f32, kind, coef, out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, const float* gout,
+                        void* dx, int accumulate, void* stream) {
+  if (!n) return S2E_OK;
+  reduce_loss_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(x, y, n, x_is_f32, kind, coef, gout, dx, accumulate);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, void* stream) {
+  if (!n) return S2E_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_fill_f32(float* p, long long n, float value, void* stream) {
+  if (!n) return S2E_OK;
+  fill_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(p, n, value);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+}  // extern "C"

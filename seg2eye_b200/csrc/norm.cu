@@ -1,0 +1,389 @@
+// SPADE+Style normalisation / modulation and InstanceNorm kernels (HBM-bound; NHWC bf16, fp32/fp64 statistics).
+// One 16-byte vector (8 channels) per thread access, fully coalesced along the channel axis; per-channel
+// partial sums live in registers, are combined across the block through shared memory and leave the block as one
+// fp64 atomic per channel (so E[x^2]-E[x]^2 is formed without cancellation trouble).
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+// ---------------------------------------------------------------- per-channel sum / sum of squares
+// grid = (chunks, G) ; G = B when per_sample else 1 (then the chunk range spans all samples)
+template <int NACC, typename F>
+__device__ __forceinline__ void block_channel_reduce(int C, long long pix_begin, long long pix_end, double* out /*[NACC][C]*/,
+                                                     F&& body) {
+  extern __shared__ float red[];  // [NT][NACC*8] worst case handled by looping
+  const int cg = C >> 3;          // channel groups of 8
+  const int tid = threadIdx.x;
+  // thread -> (channel group, pixel lane); when cg > NT loop over channel-group passes
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = tid % ncg, my_lane = tid / ncg;
+    float acc[NACC][8];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+    if (my_lane < lanes) {
+      for (long long p = pix_begin + my_lane; p < pix_end; p += lanes) body(p, (cg0 + my_cg) * 8, acc);
+    }
+    // combine pixel lanes through smem: layout [lane][ncg][NACC*8]
+    for (int a = 0; a < NACC; ++a) {
+      __syncthreads();
+      if (my_lane < lanes) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(my_lane * ncg + my_cg) * 8 + j] = acc[a][j];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < ncg * 8; idx += NT) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * ncg * 8 + idx];
+        atomicAdd(out + (size_t)a * C + cg0 * 8 + idx, (double)s);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) stats_kernel(const bf16* __restrict__ x, int HW, int C, long long pix_total,
+                                                   int per_sample, double* __restrict__ acc) {
+  const int g = blockIdx.y;
+  const long long span = per_sample ? HW : pix_total;
+  const long long base = per_sample ? (long long)g * HW : 0;
+  const long long chunk = (span + gridDim.x - 1) / gridDim.x;
+  const long long b0 = base + (long long)blockIdx.x * chunk;
+  const long long b1 = min(base + span, b0 + chunk);
+  block_channel_reduce<2>(C, b0, b1, acc + (size_t)g * 2 * C, [&](long long p, int c, float(*a)[8]) {
+    float f[8];
+    unpack8(ld_stream8(x + p * C + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[0][j] += f[j];
+      a[1][j] = fmaf(f[j], f[j], a[1][j]);
+    }
+  });
+}
+
+__global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, double count, float eps, float* mean,
+                                float* rstd, float* running_mean, float* running_var, float momentum,
+                                long long* nbt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && nbt) *nbt += 1;
+  if (i >= G * C) return;
+  const int g = i / C, c = i % C;
+  const double s = acc[(size_t)g * 2 * C + c], ss = acc[(size_t)g * 2 * C + C + c];
+  const double m = s / count;
+  double var = ss / count - m * m;
+  if (var < 0) var = 0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean && g == 0) {
+    const double unb = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+// ---------------------------------------------------------------- SPADE+Style forward (elementwise, 8 B/elem)
+__global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
+                                                             const float* __restrict__ style, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, int HW, int C, long long nvec,
+                                                             int per_sample, int act, bf16* __restrict__ out) {
+  const int cg = C >> 3;
+  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
+    const long long p = v / cg;
+    const int c = (int)(v - p * cg) * 8;
+    const int b = (int)(p / HW);
+    float xf[8], gf[8], bf[8], o[8];
+    unpack8(ld_stream8(x + p * C + c), xf);
+    unpack8(ld_stream8(gb + p * 2 * C + c), gf);
+    unpack8(ld_stream8(gb + p * 2 * C + C + c), bf);
+    const float* mu = mean + (per_sample ? b * C : 0) + c;
+    const float* rs = rstd + (per_sample ? b * C : 0) + c;
+    const float* s0 = style + (size_t)b * 2 * C + c;
+    const float* s1 = s0 + C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xf[j] - __ldg(mu + j)) * __ldg(rs + j);
+      const float r = 0.5f * (fmaf(xh, 1.f + gf[j], bf[j]) + fmaf(xf[j], 1.f + __ldg(s0 + j), __ldg(s1 + j)));
+      o[j] = act_apply(r, act);
+    }
+    st_stream8(out + p * C + c, pack8(o));
+  }
+}
+
+// ---------------------------------------------------------------- SPADE+Style backward
+// pass 1: per (sample, channel) sums  S1 = sum dxh, S2 = sum dxh*xh, S3 = sum g*x, S4 = sum g
+__global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ outp,
+                                                                    const bf16* __restrict__ x, const bf16* __restrict__ gb,
+                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                    int HW, int C, int per_sample, int act, double* __restrict__ racc) {
+  const int b = blockIdx.y;
+  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
+  const long long b1 = min((long long)(b + 1) * HW, b0 + chunk);
+  const float* mu = mean + (per_sample ? b * C : 0);
+  const float* rs = rstd + (per_sample ? b * C : 0);
+  block_channel_reduce<4>(C, b0, b1, racc + (size_t)b * 4 * C, [&](long long p, int c, float(*a)[8]) {
+    float df[8], of[8], xf[8], gf[8];
+    unpack8(ld_stream8(dout + p * C + c), df);
+    unpack8(ld_stream8(x + p * C + c), xf);
+    unpack8(ld_stream8(gb + p * 2 * C + c), gf);
+    if (act != S2E_ACT_NONE) unpack8(ld_stream8(outp + p * C + c), of);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = 0.5f * df[j];
+      if (act == S2E_ACT_LRELU) g *= (of[j] > 0.f ? 1.f : 0.2f);
+      if (act == S2E_ACT_RELU) g *= (of[j] > 0.f ? 1.f : 0.f);
+      const float xh = (xf[j] - __ldg(mu + c + j)) * __ldg(rs + c + j);
+      const float dxh = g * (1.f + gf[j]);
+      a[0][j] += dxh;
+      a[1][j] = fmaf(dxh, xh, a[1][j]);
+      a[2][j] = fmaf(g, xf[j], a[2][j]);
+      a[3][j] += g;
+    }
+  });
+}
+
+// fold the per-sample sums: m1/m2 per stat group (float [G][2][C]) and dstyle [B][2C]
+__global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int B, int C, int per_sample, double count,
+                                            float* __restrict__ m12, float* __restrict__ dstyle) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const double* r = racc + (size_t)b * 4 * C;
+  if (dstyle) {
+    dstyle[(size_t)b * 2 * C + c] = (float)r[2 * C + c];
+    dstyle[(size_t)b * 2 * C + C + c] = (float)r[3 * C + c];
+  }
+  if (per_sample) {
+    m12[(size_t)b * 2 * C + c] = (float)(r[c] / count);
+    m12[(size_t)b * 2 * C + C + c] = (float)(r[C + c] / count);
+  } else if (b == 0) {
+    double s1 = 0, s2 = 0;
+    for (int bb = 0; bb < B; ++bb) {
+      s1 += racc[(size_t)bb * 4 * C + c];
+      s2 += racc[(size_t)bb * 4 * C + C + c];
+    }
+    m12[c] = (float)(s1 / count);
+    m12[C + c] = (float)(s2 / count);
+  }
+}
+
+// pass 2: dx = rstd*(dxh - m1 - xh*m2) + g*(1+s0) ; dgamma = g*xh ; dbeta = g
+__global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ outp,
+                                                                   const bf16* __restrict__ x, const bf16* __restrict__ gb,
+                                                                   const float* __restrict__ style, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, const float* __restrict__ m12,
+                                                                   int HW, int C, long long nvec, int per_sample, int act,
+                                                                   bf16* __restrict__ dx, int dx_acc, bf16* __restrict__ dgb) {
+  const int cg = C >> 3;
+  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
+    const long long p = v / cg;
+    const int c = (int)(v - p * cg) * 8;
+    const int b = (int)(p / HW);
+    const int so = per_sample ? b * C : 0;
+    float df[8], of[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
+    unpack8(ld_stream8(dout + p * C + c), df);
+    unpack8(ld_stream8(x + p * C + c), xf);
+    unpack8(ld_stream8(gb + p * 2 * C + c), gf);
+    if (act != S2E_ACT_NONE) unpack8(ld_stream8(outp + p * C + c), of);
+    if (dx_acc) unpack8(*reinterpret_cast<const bf16x8*>(dx + p * C + c), prev);
+    const float* m1 = m12 + (per_sample ? (size_t)b * 2 * C : 0) + c;
+    const float* m2 = m1 + C;
+    const float* s0 = style + (size_t)b * 2 * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = 0.5f * df[j];
+      if (act == S2E_ACT_LRELU) g *= (of[j] > 0.f ? 1.f : 0.2f);
+      if (act == S2E_ACT_RELU) g *= (of[j] > 0.f ? 1.f : 0.f);
+      const float rsd = __ldg(rstd + so + c + j);
+      const float xh = (xf[j] - __ldg(mean + so + c + j)) * rsd;
+      const float dxh = g * (1.f + gf[j]);
+      float d = rsd * (dxh - __ldg(m1 + j) - xh * __ldg(m2 + j)) + g * (1.f + __ldg(s0 + j));
+      if (dx_acc) d += prev[j];
+      odx[j] = d;
+      odg[j] = g * xh;
+      odb[j] = g;
+    }
+    *reinterpret_cast<bf16x8*>(dx + p * C + c) = pack8(odx);
+    st_stream8(dgb + p * 2 * C + c, pack8(odg));
+    st_stream8(dgb + p * 2 * C + C + c, pack8(odb));
+  }
+}
+
+// ---------------------------------------------------------------- InstanceNorm (+act)
+__global__ void __launch_bounds__(NT) instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, int HW, int C, long long nvec, int act,
+                                                            bf16* __restrict__ y) {
+  const int cg = C >> 3;
+  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
+    const long long p = v / cg;
+    const int c = (int)(v - p * cg) * 8;
+    const int b = (int)(p / HW);
+    float xf[8], o[8];
+    unpack8(ld_stream8(x + p * C + c), xf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_apply((xf[j] - __ldg(mean + b * C + c + j)) * __ldg(rstd + b * C + c + j), act);
+    st_stream8(y + p * C + c, pack8(o));
+  }
+}
+
+// reduce: S1 = sum g, S2 = sum g*xh  (g = dy * act'(y))
+__global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                                 const bf16* __restrict__ x, const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd, int HW, int C, int act,
+                                                                 double* __restrict__ racc) {
+  const int b = blockIdx.y;
+  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
+  const long long b1 = min((long long)(b + 1) * HW, b0 + chunk);
+  block_channel_reduce<2>(C, b0, b1, racc + (size_t)b * 2 * C, [&](long long p, int c, float(*a)[8]) {
+    float df[8], yf[8], xf[8];
+    unpack8(ld_stream8(dy + p * C + c), df);
+    unpack8(ld_stream8(x + p * C + c), xf);
+    if (act != S2E_ACT_NONE) unpack8(ld_stream8(y + p * C + c), yf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = df[j];
+      if (act == S2E_ACT_LRELU) g *= (yf[j] > 0.f ? 1.f : 0.2f);
+      const float xh = (xf[j] - __ldg(mean + b * C + c + j)) * __ldg(rstd + b * C + c + j);
+      a[0][j] += g;
+      a[1][j] = fmaf(g, xh, a[1][j]);
+    }
+  });
+}
+
+__global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                                const bf16* __restrict__ x, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const double* __restrict__ racc,
+                                                                int HW, int C, long long nvec, int act, bf16* __restrict__ dx) {
+  const int cg = C >> 3;
+  const float inv = 1.f / (float)HW;
+  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
+    const long long p = v / cg;
+    const int c = (int)(v - p * cg) * 8;
+    const int b = (int)(p / HW);
+    float df[8], yf[8], xf[8], o[8];
+    unpack8(ld_stream8(dy + p * C + c), df);
+    unpack8(ld_stream8(x + p * C + c), xf);
+    if (act != S2E_ACT_NONE) unpack8(ld_stream8(y + p * C + c), yf);
+    const double* r = racc + (size_t)b * 2 * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = df[j];
+      if (act == S2E_ACT_LRELU) g *= (yf[j] > 0.f ? 1.f : 0.2f);
+      const float rsd = __ldg(rstd + b * C + c + j);
+      const float xh = (xf[j] - __ldg(mean + b * C + c + j)) * rsd;
+      o[j] = rsd * (g - (float)r[j] * inv - xh * (float)r[C + j] * inv);
+    }
+    st_stream8(dx + p * C + c, pack8(o));
+  }
+}
+
+int ew_grid(long long nvec) {
+  long long g = (nvec + NT - 1) / NT;
+  const long long cap = (long long)s2e_num_sms() * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+int red_chunks(long long pixels, int G) {
+  // aim for ~4 blocks per SM overall, at least 64 pixels per block
+  long long want = ((long long)s2e_num_sms() * 4 + G - 1) / G;
+  long long maxc = (pixels + 63) / 64;
+  if (want > maxc) want = maxc;
+  return (int)(want < 1 ? 1 : want);
+}
+size_t red_smem(int C) {
+  int ncg = (C >> 3) < NT ? (C >> 3) : NT;
+  int lanes = NT / ncg;
+  return (size_t)lanes * ncg * 8 * sizeof(float);
+}
+
+}  // namespace
+
+extern "C" {
+
+int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* acc, void* stream) {
+  S2E_REQUIRE(C % 8 == 0 && C >= 8, "norm_stats needs C %% 8 == 0 (C=%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = per_sample ? B : 1;
+  S2E_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * G * 2 * C, st));
+  const long long span = per_sample ? HW : (long long)B * HW;
+  dim3 grid(red_chunks(span, G), G);
+  stats_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)x, HW, C, (long long)B * HW, per_sample, acc);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_norm_finalize(const double* acc, int G, int C, double count, float eps, float* mean, float* rstd,
+                      float* running_mean, float* running_var, float momentum, int64_t* nbt, void* stream) {
+  finalize_kernel<<<ceil_div(G * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, G, C, count, eps, mean, rstd, running_mean,
+                                                                           running_var, momentum, (long long*)nbt);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd, int B,
+                        int HW, int C, int per_sample, int act, void* out, void* stream) {
+  S2E_REQUIRE(C % 8 == 0, "spade_style_fwd needs C %% 8 == 0 (C=%d)", C);
+  const long long nvec = (long long)B * HW * (C >> 3);
+  if (nvec == 0) return S2E_OK;
+  spade_style_fwd_kernel<<<ew_grid(nvec), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gb, style, mean, rstd, HW,
+                                                                          C, nvec, per_sample, act, (bf16*)out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const void* gb, const float* style,
+                        const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act, double* racc,
+                        void* dx, int dx_accumulate, void* dgb, float* dstyle, void* stream) {
+  S2E_REQUIRE(C % 8 == 0, "spade_style_bwd needs C %% 8 == 0 (C=%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  // racc: double [B][4][C] followed by float m12 [B][2][C]
+  S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 4 * C, st));
+  float* m12 = (float*)(racc + (size_t)B * 4 * C);
+  dim3 grid(red_chunks(HW, B), B);
+  spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x,
+                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc);
+  S2E_LAUNCH_CHECK();
+  const double count = per_sample ? (double)HW : (double)B * HW;
+  spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, m12, dstyle);
+  S2E_LAUNCH_CHECK();
+  const long long nvec = (long long)B * HW * (C >> 3);
+  spade_style_bwd_apply_kernel<<<ew_grid(nvec), NT, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x,
+                                                             (const bf16*)gb, style, mean, rstd, m12, HW, C, nvec, per_sample,
+                                                             act, (bf16*)dx, dx_accumulate, (bf16*)dgb);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, double* acc, float* mean, float* rstd,
+                     void* y, void* stream) {
+  int rc = s2e_norm_stats(x, B, HW, C, 1, acc, stream);
+  if (rc) return rc;
+  rc = s2e_norm_finalize(acc, B, C, (double)HW, eps, mean, rstd, nullptr, nullptr, 0.f, nullptr, stream);
+  if (rc) return rc;
+  const long long nvec = (long long)B * HW * (C >> 3);
+  instnorm_apply_kernel<<<ew_grid(nvec), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, rstd, HW, C, nvec, act, (bf16*)y);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_instnorm_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, int B, int HW,
+                     int C, int act, double* racc, void* dx, void* stream) {
+  S2E_REQUIRE(C % 8 == 0, "instnorm_bwd needs C %% 8 == 0 (C=%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 2 * C, st));
+  dim3 grid(red_chunks(HW, B), B);
+  instnorm_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)x, mean, rstd, HW, C,
+                                                            act, racc);
+  S2E_LAUNCH_CHECK();
+  const long long nvec = (long long)B * HW * (C >> 3);
+  instnorm_bwd_apply_kernel<<<ew_grid(nvec), NT, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)x, mean, rstd, racc, HW,
+                                                          C, nvec, act, (bf16*)dx);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+}  // extern "C"
