@@ -1,0 +1,257 @@
+"""Benchmark of the Seg2Eye SPADE+Style G+D training step (BASELINE.json metric: G+D train images/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--res R1|R2] [--batch B]
+
+One "step" = one Pix2PixTrainer.run_generator_one_step + run_discriminator_one_step over one synthetic batch
+(labels: eye-shaped 4-class ellipses; images/targets U(-1,1); reference-initialised weights).  Prints ONE JSON line.
+
+`value`    : whole-job images/s with the batch already resident in HBM when the timed region starts.
+`e2e`      : the same metric through the public trainer API fed with pinned HOST tensors each step (H2D of labels,
+             style images and target inside the timed region, D2H read of the five loss scalars).
+`roofline` : tcgen05 tap-convolution kernels -- algorithmic FLOPs (2*M*N*K per launch, fwd / dgrad / wgrad) over their
+             CUDA-event durations inside the timed region, against the measured bf16 GEMM peak.
+`cpu_baseline` / --impl reference: the oracle port (plain fp32 PyTorch restatement of the reference, the reference
+             itself is Python and does not travel to the GPU box) timed on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+RES = {"R1": (256, 0.8), "R2": (384, 0.6)}   # crop_size, aspect_ratio -> 320x256 / 640x384
+STEP_TFLOP = {"R1": 1.54, "R2": 4.53}        # reference-equivalent FLOPs per image
+
+
+def make_opts(res, batch):
+    from oracle import seg2eye_oracle as O
+    crop, ar = RES[res]
+    oopt = O.make_opt(crop_size=crop, aspect_ratio=ar, lambda_l1=10.0)
+    d = vars(oopt).copy()
+    d.update(gpu_ids=[0], init_type="xavier", init_variance=0.02, netD_subarch="n_layer", continue_train=False,
+             which_epoch="latest", checkpoints_dir="/tmp/s2e_bench", name="bench", no_vgg_loss=True, lambda_openeds=0.0,
+             lambda_style_w=0.0, lambda_style_feat=0.0, lambda_gram=0.0, netG="spadestyle", netD="multiscale",
+             batchSize=batch)
+    return oopt, SimpleNamespace(**d)
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in o.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(res, steps, warmup, batch=1):
+    """Oracle port of the reference step on the host cores; each step = one G step + one D step on `batch` images."""
+    from oracle import seg2eye_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oopt, _ = make_opts(res, batch)
+    sd = dict(G=O.init_state(O.generator_shapes(oopt), 1), D=O.init_state(O.discriminator_shapes(oopt), 2),
+              E=O.init_state(O.encoder_shapes(oopt), 3))
+    tr = O.OracleTrainer(sd["G"], sd["D"], sd["E"], oopt)
+    b = O.synth_batch(oopt, batch, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        tr.run_generator_one_step(b)
+        tr.run_discriminator_one_step(b)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=batch / (ms / 1e3), ms_per_step=ms, cores=torch.get_num_threads(),
+                sample="%d G+D iteration(s) of batch %d at %s after %d warm-up" % (steps, batch, res, warmup))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from oracle import seg2eye_oracle as O
+    from seg2eye_b200 import _lib as L, ops, parallel
+    from seg2eye_b200.trainers.pix2pix_trainer import Pix2PixTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    oopt, opt = make_opts(args.res, args.batch)
+    opt.gpu_ids = [local]
+    import contextlib, io
+    torch.manual_seed(1234)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = Pix2PixTrainer(opt)
+    m = tr.pix2pix_model
+    for net in (m.netG, m.netD, m.netE):
+        parallel.broadcast_module(net, 0)
+    host = O.synth_batch(oopt, args.batch, 1234 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(data):
+        d = dict(data)
+        tr.run_generator_one_step(d)
+        tr.run_discriminator_one_step(d)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(dev)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.profile_begin()
+    n0 = L.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launches - n0
+    prof = ops.profile_end()
+    # ---- timed region 2: end to end through the trainer API with host buffers
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d2h = 0
+    f0.record()
+    for _ in range(args.steps):
+        step(host)
+        vals = torch.stack([v.reshape(-1)[0] for v in tr.get_latest_losses().values()]).cpu()
+        d2h = vals.numel() * 4
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    sampler.stop_flag = True
+    sampler.join(2)
+
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    imgs = args.steps * args.batch * world
+    peaks = load_peaks()
+    out = None
+    if rank == 0:
+        conv_ms, conv_tf, conv_n = prof["tc_ms"], prof["tc_flop"] / 1e12, prof["tc_n"]
+        achieved = conv_tf / (conv_ms / 1e3) if conv_ms > 0 else 0.0
+        norm_gbs = prof["norm_bytes"] / 1e9 / (prof["norm_ms"] / 1e3) if prof["norm_ms"] > 0 else 0.0
+        out = {
+            "metric": "G+D train images/sec", "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Seg2Eye full G+D training step (SPADEStyle G, multiscale PatchGAN D, GAN+feat-match+L1), "
+                                   "%s = %dx%d, per-GPU batch %d, ngf=ndf=64" % (
+                                       args.res, round(RES[args.res][0] / RES[args.res][1]), RES[args.res][0], args.batch),
+                       "global_batch": args.batch * world, "parallelism": "dp%d" % world,
+                       "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2"},
+            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                         "kernel": "tapconv_{fwd,wgrad}_kernel (tcgen05 implicit GEMM; %d launches, %.1f%% of step time)" % (
+                             conv_n, 100.0 * conv_ms / ms if ms else 0.0),
+                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS; burst %.0f)" % peaks["tf"]},
+            "roofline_norm": {"bound": "hbm", "achieved": norm_gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                              "frac": norm_gbs / peaks["hbm"], "kernel": "spade_style_fwd_kernel (8 B/element)",
+                              "launches": prof["norm_n"]},
+            "step_tflops_equiv": imgs * STEP_TFLOP[args.res] / (ms / 1e3),
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--res", default="R2", choices=tuple(RES))
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
+        r = cpu_reference(args.res, steps, warmup)
+        cb = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        print(json.dumps({
+            "impl": "reference", "metric": "G+D train images/sec", "value": r["value"], "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "Seg2Eye full G+D training step, %s, batch 1, oracle port on host CPU" % args.res},
+            "cpu_baseline": cb,
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert args.warmup >= 3, "timing rule: at least 3 warm-up steps"
+    out = run_ours(args)
+    if rank == 0:
+        if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
+            r = cpu_reference(args.res, 1, 0)
+            out["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+                                   "sample": r["sample"]}
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -84,19 +84,22 @@ int s2e_tapconv_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float*
 
 /* OIHW fp32 master weight -> bf16 tap-major.  stride 1: taps (r,s) row-major, offset (r-pad, s-pad).
  * stride 2: space-to-depth taps (a,b), a in [floor(-pad/2), floor((k-1-pad)/2)], channel (i*2+j)*Cin+ci,
- * r = 2a+i+pad.  transposed=1 emits [t][Cin'][Cout] (data-gradient operand). */
+ * r = 2a+i+pad.  transposed=1 emits [t][Cin'][Cout] (data-gradient operand).
+ * Several OIHW tensors can be packed side by side along Cout (the fused gamma|beta GEMM): the packed tensor has
+ * Cout_total output channels and this call fills [co_offset, co_offset+Cout). */
 int s2e_pack_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int stride, int pad, int transposed,
-                    void* out_bf16, void* stream);
+                    int Cout_total, int co_offset, void* out_bf16, void* stream);
 int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, int* dx); /* host helper */
 /* tap-major fp32 weight gradient -> OIHW, with the spectral-norm chain rule when u != NULL:
  * dW_orig = inv_sigma * (G - inv_sigma * <G, W_orig> u v^T).  `dot` is a 1-float device scratch. */
-int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, const float* w_orig,
-                     const float* u, const float* v, const float* inv_sigma, float* dot, float* dw_oihw,
-                     int accumulate, void* stream);
+int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, int Cout_total,
+                     int co_offset, const float* w_orig, const float* u, const float* v, const float* inv_sigma,
+                     float* dot, float* dw_oihw, int accumulate, void* stream);
 /* torch.nn.utils.spectral_norm power iteration (one step) on W viewed as (rows, cols):
- * v <- normalize(W^T u), u <- normalize(W v), inv_sigma <- 1 / (u . W v); eps 1e-12. scratch: rows+cols+4 floats */
+ * v <- normalize(W^T u), u <- normalize(W v), inv_sigma <- 1 / (u . W v); eps 1e-12. scratch: rows+cols floats.
+ * update = 0 (module in eval mode): u, v are left untouched and only inv_sigma is produced. */
 int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
-                            void* stream);
+                            int update, void* stream);
 
 /* [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] with channel (i*2+j)*C+c = x[2h+i, 2w+j, c] (zero beyond the edge),
  * and its adjoint (gradient) */

@@ -163,6 +163,31 @@ def synth_state(shapes, seed, scale=None):
     return out
 
 
+def init_state(shapes, seed):
+    """The reference's own initialisation (base_network.py:28-59 with --init_type xavier --init_variance 0.02;
+    FC keeps randn * in^-0.5, normalization.py:117-127; BN buffers 0/1; u, v = normalised randn)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {}
+    for k, shp in shapes.items():
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.tensor(0, dtype=torch.int64)
+            continue
+        a = rng.standard_normal(shp).astype(np.float32)
+        if k.endswith("weight_u") or k.endswith("weight_v"):
+            a = a / max(float(np.linalg.norm(a)), 1e-12)
+        elif k.endswith("running_var"):
+            a = np.ones(shp, np.float32)
+        elif k.endswith("running_mean") or k.endswith("bias"):
+            a = np.zeros(shp, np.float32)
+        elif "adain.linear.weight" in k:
+            a = a * np.float32(shp[1] ** -0.5)
+        else:
+            rf = int(np.prod(shp[2:])) if len(shp) > 2 else 1
+            a = a * np.float32(0.02 * math.sqrt(2.0 / (shp[1] * rf + shp[0] * rf)))
+        out[k] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return out
+
+
 def synth_batch(opt, batch, seed, hw=None):
     """eye-shaped 4-class label ellipses, images/targets U(-1,1), 4-D label."""
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -55,7 +55,6 @@ __device__ __forceinline__ float block_sum(float v) {
 }
 
 inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-__device__ __forceinline__ int d_floor_div2(int a) { return (a >= 0) ? (a >> 1) : -((-a + 1) >> 1); }
 
 // ------------------------------------------------------------------------------------------ integer path
 __global__ void onehot_kernel(const long long* __restrict__ label, long long HW, int nc, long long n, float* __restrict__ out) {
@@ -112,6 +111,7 @@ __global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, int C, int H, int W
 // ------------------------------------------------------------------------------------------ weight packing
 struct PackGeom {
   int Cout, Cin, kh, kw, stride, pad;
+  int Ctot, co_off;  // several OIHW tensors may be packed side by side along Cout (gamma | beta)
   int amin, bmin, na, nb;  // stride-2 tap grid
 };
 
@@ -132,6 +132,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, PackGeom g, int 
       r0 /= g.Cout;
     }
     const int t = (int)r0;
+    const long long oidx = transposed ? ((long long)t * CinP + cp) * g.Ctot + g.co_off + co
+                                      : ((long long)t * g.Ctot + g.co_off + co) * CinP + cp;
     int r, s, ci;
     if (g.stride == 1) {
       r = t / g.kw;
@@ -146,17 +148,18 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, PackGeom g, int 
     }
     float v = 0.f;
     if (r >= 0 && r < g.kh && s >= 0 && s < g.kw) v = w[(((long long)co * g.Cin + ci) * g.kh + r) * g.kw + s];
-    out[i] = __float2bfloat16(v);
+    out[oidx] = __float2bfloat16(v);
   }
 }
 
 __device__ __forceinline__ long long packed_index(const PackGeom& g, int co, int ci, int r, int s) {
-  if (g.stride == 1) return ((long long)(r * g.kw + s) * g.Cout + co) * g.Cin + ci;
+  co += g.co_off;
+  if (g.stride == 1) return ((long long)(r * g.kw + s) * g.Ctot + co) * g.Cin + ci;
   const int rr = r - g.pad, ss = s - g.pad;
   const int i = ((rr % 2) + 2) % 2, j = ((ss % 2) + 2) % 2;
   const int a = (rr - i) / 2, b = (ss - j) / 2;
   const int t = (a - g.amin) * g.nb + (b - g.bmin);
-  return ((long long)t * g.Cout + co) * (4 * g.Cin) + (i * 2 + j) * g.Cin + ci;
+  return ((long long)t * g.Ctot + co) * (4 * g.Cin) + (i * 2 + j) * g.Cin + ci;
 }
 
 __global__ void wgrad_dot_kernel(const float* __restrict__ dwp, const float* __restrict__ w, PackGeom g, long long n, float* dot) {
@@ -215,6 +218,13 @@ __global__ void sn_normalize_kernel(const float* __restrict__ raw, int n, float*
   const float denom = fmaxf(sqrtf(nsq), 1e-12f);
   for (int i = threadIdx.x; i < n; i += blockDim.x) outv[i] = raw[i] / denom;
   if (inv_sigma && threadIdx.x == 0) *inv_sigma = 1.f / (nsq / denom);  // sigma = u . (W v) = ||Wv||^2 / max(||Wv||,eps)
+}
+// inv_sigma = 1 / (u . s)  (evaluation mode: no buffer update) ; single block
+__global__ void sn_dot_kernel(const float* __restrict__ u, const float* __restrict__ sv, int n, float* inv_sigma) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(u[i], sv[i], acc);
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) *inv_sigma = 1.f / acc;
 }
 // s[r] = W[r][:] . v   one warp per row
 __global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ v, int rows, int cols, float* s) {
@@ -546,8 +556,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-PackGeom make_pack_geom(int Cout, int Cin, int kh, int kw, int stride, int pad) {
+PackGeom make_pack_geom(int Cout, int Cin, int kh, int kw, int stride, int pad, int Ctot = 0, int co_off = 0) {
   PackGeom g;
+  g.Ctot = Ctot > 0 ? Ctot : Cout;
+  g.co_off = co_off;
   g.Cout = Cout;
   g.Cin = Cin;
   g.kh = kh;
@@ -641,21 +653,21 @@ int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, in
   *ntaps = n;
   return S2E_OK;
 }
-int s2e_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, int stride, int pad, int transposed, void* out,
-                    void* stream) {
+int s2e_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, int stride, int pad, int transposed, int Cout_total,
+                    int co_offset, void* out, void* stream) {
   S2E_REQUIRE(stride == 1 || stride == 2, "pack_weight: stride must be 1 or 2");
-  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad);
+  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad, Cout_total, co_offset);
   const int T = stride == 1 ? kh * kw : g.na * g.nb;
   const long long n = (long long)T * Cout * (stride == 2 ? 4 * Cin : Cin);
   pack_weight_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(w, g, transposed, n, (bf16*)out);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
-int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, const float* w_orig,
-                     const float* u, const float* v, const float* inv_sigma, float* dot, float* dw, int accumulate,
-                     void* stream) {
+int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, int Cout_total, int co_offset,
+                     const float* w_orig, const float* u, const float* v, const float* inv_sigma, float* dot, float* dw,
+                     int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad);
+  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad, Cout_total, co_offset);
   const long long n = (long long)Cout * Cin * kh * kw;
   if (u) {
     S2E_REQUIRE(v && inv_sigma && dot && w_orig, "unpack_wgrad: spectral args incomplete");
@@ -669,10 +681,17 @@ int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int st
 }
 
 int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
-                            void* stream) {
+                            int update, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   float* t = scratch;         // cols
   float* s = scratch + cols;  // rows
+  if (!update) {
+    sn_w_v_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(w, v, rows, cols, s);
+    S2E_LAUNCH_CHECK();
+    sn_dot_kernel<<<1, 1024, 0, st>>>(u, s, rows, inv_sigma);
+    S2E_LAUNCH_CHECK();
+    return S2E_OK;
+  }
   S2E_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, st));
   const int rchunk = 64;
   dim3 g1(ceil_div(cols, 128), ceil_div(rows, rchunk));

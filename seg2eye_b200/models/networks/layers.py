@@ -1,0 +1,97 @@
+"""Parameter-holding layers with the reference's state_dict names, computing through seg2eye_b200.ops."""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import _lib as L
+from ... import ops
+
+
+class Conv2d(nn.Module):
+    """nn.Conv2d replacement (weight OIHW fp32 master, optional bias) running as a tap-convolution kernel.
+    With spectral=True it carries torch.nn.utils.spectral_norm's state: `weight_orig`, `weight_u`, `weight_v`
+    (reference normalization.py:26, architecture.py:31-34) and `weight` aliases weight_orig's storage."""
+
+    def __init__(self, cin, cout, k, stride=1, padding=0, bias=True, spectral=False, act=L.ACT_NONE):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.cfg = ops.ConvCfg(k, k, stride, padding, act)
+        self.spectral = spectral
+        w = torch.empty(cout, cin, k, k)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        bound = 1 / math.sqrt(cin * k * k)
+        if not spectral:
+            self.weight = nn.Parameter(w)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+        else:
+            self.register_parameter('bias', None)
+        if spectral:  # spectral_norm re-registers the weight after the bias
+            self.weight_orig = nn.Parameter(w)
+            self.register_buffer('weight_u', F.normalize(torch.randn(cout), dim=0, eps=1e-12))
+            self.register_buffer('weight_v', F.normalize(torch.randn(cin * k * k), dim=0, eps=1e-12))
+
+    def __getattr__(self, name):
+        if name == 'weight' and 'weight_orig' in self._parameters:
+            return self._parameters['weight_orig'].data
+        return super().__getattr__(name)
+
+    def master_weight(self):
+        return self.weight_orig if self.spectral else self.weight
+
+    def sn_state(self):
+        if not self.spectral:
+            return None
+        inv = ops.spectral_inv_sigma(self.weight_orig, self.weight_u, self.weight_v, self.training)
+        return (self.weight_u, self.weight_v, inv)
+
+    def forward_nhwc(self, x, act=None):
+        cfg = self.cfg if act is None else self.cfg._replace(act=act)
+        biases = (self.bias,) if self.bias is not None else ()
+        return ops.tap_conv(x, cfg, (self.master_weight(),), biases, self.sn_state())
+
+    def forward(self, x):
+        return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x)))
+
+
+class Linear(nn.Module):
+    """nn.Linear replacement in fp32 (encoder.py:48-49 fc_mu / fc_var)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.in_features, self.out_features = cin, cout
+        bound = 1 / math.sqrt(cin)
+        self.weight = nn.Parameter(torch.empty(cout, cin).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+
+    def forward(self, x):
+        return ops.LinearFn.apply(x.float(), self.weight, self.bias, L.ACT_NONE, 0)
+
+
+class BatchNorm2dStats(nn.Module):
+    """Buffers of nn.BatchNorm2d(affine=False): running_mean / running_var / num_batches_tracked
+    (normalization.py:75).  The arithmetic lives in the fused SPADE+Style kernel."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.num_features = c
+        self.eps, self.momentum = 1e-5, 0.1
+        self.register_buffer('running_mean', torch.zeros(c))
+        self.register_buffer('running_var', torch.ones(c))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+
+class InstanceNorm2d(nn.Module):
+    """nn.InstanceNorm2d(affine=False) (+ optionally the LeakyReLU that follows it) as one kernel."""
+
+    def __init__(self, c, act=L.ACT_NONE):
+        super().__init__()
+        self.num_features, self.act = c, act
+
+    def forward_nhwc(self, x):
+        return ops.InstNormFn.apply(x, self.act)
+
+    def forward(self, x):
+        return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x)))

@@ -1,0 +1,148 @@
+"""SPADE / ApplyStyle / SPADE_STYLE_Block mirrors (reference models/networks/normalization.py)."""
+import re
+
+import torch
+import torch.nn as nn
+
+from ... import _lib as L
+from ... import ops
+from .layers import BatchNorm2dStats, Conv2d, InstanceNorm2d
+
+
+def get_nonspade_norm_layer(opt, norm_type='instance'):
+    """normalization.py:15-47: wrap a conv in spectral norm, drop its bias, append the sub-norm.
+    Returns nn.Sequential(conv, norm) (or the bare conv for 'spectralnone')."""
+    def add_norm_layer(layer):
+        if not norm_type.startswith('spectral'):
+            # the reference leaves subnorm_type undefined here and crashes (normalization.py:25-29)
+            raise ValueError('normalization layer %s is not recognized' % norm_type)
+        subnorm_type = norm_type[len('spectral'):]
+        has_bias = subnorm_type == 'none' or len(subnorm_type) == 0
+        cfg = layer.cfg
+        layer = Conv2d(layer.in_channels, layer.out_channels, cfg.kh, stride=cfg.stride, padding=cfg.pad,
+                       bias=has_bias and layer.bias is not None, spectral=True)
+        if has_bias:
+            return layer
+        if subnorm_type == 'instance':
+            norm_layer = InstanceNorm2d(layer.out_channels)
+        elif subnorm_type == 'batch':
+            raise ValueError('normalization layer batch is not supported by the B200 path (reference default is instance)')
+        else:
+            raise ValueError('normalization layer %s is not recognized' % subnorm_type)
+        return nn.Sequential(layer, norm_layer)
+    return add_norm_layer
+
+
+class FC(nn.Module):
+    """normalization.py:108-141 (StyleGAN dense layer + LeakyReLU(0.2))."""
+
+    def __init__(self, in_channels, out_channels, gain=2 ** 0.5, use_wscale=False, lrmul=1.0, bias=True):
+        super().__init__()
+        he_std = gain * in_channels ** (-0.5)
+        if use_wscale:
+            init_std = 1.0 / lrmul
+            self.w_lrmul = he_std * lrmul
+        else:
+            init_std = he_std / lrmul
+            self.w_lrmul = lrmul
+        self.weight = nn.Parameter(torch.randn(out_channels, in_channels) * init_std)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+            self.b_lrmul = lrmul
+        else:
+            self.bias = None
+
+    def forward(self, x):
+        w = self.weight if self.w_lrmul == 1.0 else self.weight * self.w_lrmul
+        b = self.bias
+        if b is not None and self.b_lrmul != 1.0:
+            b = b * self.b_lrmul
+        return ops.LinearFn.apply(x.float(), w, b, L.ACT_LRELU, 0)
+
+
+class ApplyStyle(nn.Module):
+    """normalization.py:144-169: x * (style[:,0] + 1) + style[:,1] with style = FC(w)."""
+
+    def __init__(self, latent_size, channels, use_wscale):
+        super().__init__()
+        self.linear = FC(latent_size, channels * 2, gain=1.0, use_wscale=use_wscale)
+
+    def forward(self, x, latent_style):
+        # standalone use (the fused block below never materialises this): gamma = beta = 0, no norm => 2*(0.5*x*(1+s0)+...)
+        style = self.linear(latent_style)
+        xn = ops.as_nhwc(x)
+        B, H, W, C = xn.shape
+        gb = torch.zeros(B, H, W, 2 * C, dtype=torch.bfloat16, device=xn.device)
+        # identity norm (mean 0, rstd 0 kills the SPADE term), doubled style so that 0.5*(...) gives x*(1+s0)+s1
+        st2 = torch.cat([2 * style[:, :C] + 1, 2 * style[:, C:]], dim=1)
+        cfg = ops.NormCfg(False, L.ACT_NONE, False, 0.0, 1e-5)
+        rm = torch.zeros(C, device=xn.device)
+        rv = torch.full((C,), float('inf'), device=xn.device)
+        return ops.as_nchw_view(ops.SpadeStyleFn.apply(xn, gb, st2, cfg, rm, rv, None))
+
+
+class SPADE(nn.Module):
+    """normalization.py:63-105.  gamma and beta are produced by ONE implicit GEMM with N = 2C (their weights
+    are packed side by side), then consumed by the fused normalisation/modulation kernel."""
+
+    def __init__(self, config_text, norm_nc, label_nc):
+        super().__init__()
+        assert config_text.startswith('spade')
+        parsed = re.search(r'spade(\D+)(\d)x\d', config_text)
+        param_free_norm_type = str(parsed.group(1))
+        ks = int(parsed.group(2))
+        if param_free_norm_type == 'instance':
+            self.param_free_norm = InstanceNorm2d(norm_nc)
+            self.per_sample = True
+        elif param_free_norm_type == 'batch':
+            self.param_free_norm = BatchNorm2dStats(norm_nc)
+            self.per_sample = False
+        else:
+            raise ValueError('%s is not a recognized param-free norm type in SPADE' % param_free_norm_type)
+        nhidden = 128
+        pw = ks // 2
+        self.mlp_shared = nn.Sequential(Conv2d(label_nc, nhidden, ks, padding=pw, act=L.ACT_RELU), nn.ReLU())
+        self.mlp_gamma = Conv2d(nhidden, norm_nc, ks, padding=pw)
+        self.mlp_beta = Conv2d(nhidden, norm_nc, ks, padding=pw)
+        self.norm_nc = norm_nc
+
+    def gamma_beta(self, segmap, h, w):
+        seg = ops.seg_nearest(segmap, h, w)
+        actv = self.mlp_shared[0].forward_nhwc(seg)
+        return ops.tap_conv(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
+                            (self.mlp_gamma.bias, self.mlp_beta.bias))
+
+    def modulate(self, x, segmap, style, act):
+        """x NHWC bf16; style (B,2C) fp32 (s0|s1) ->  act(0.5*[norm(x)(1+gamma)+beta + x(1+s0)+s1])."""
+        B, H, W, C = x.shape
+        gb = self.gamma_beta(segmap, H, W)
+        pfn = self.param_free_norm
+        cfg = ops.NormCfg(self.per_sample, act, self.training, 0.1, 1e-5)
+        if self.per_sample:
+            return ops.SpadeStyleFn.apply(x, gb, style, cfg, None, None, None)
+        return ops.SpadeStyleFn.apply(x, gb, style, cfg, pfn.running_mean, pfn.running_var, pfn.num_batches_tracked)
+
+    def forward(self, x, segmap):
+        # plain SPADE: out = norm(x)(1+gamma)+beta = 2*0.5*[...] with the style term cancelled (s0=-1, s1=0)
+        xn = ops.as_nhwc(x)
+        B, H, W, C = xn.shape
+        style = torch.cat([torch.full((B, C), -1.0, device=xn.device), torch.zeros(B, C, device=xn.device)], 1)
+        out = self.modulate(xn, segmap, style, L.ACT_NONE)
+        return ops.as_nchw_view(ops.AddFn.apply(out, out))
+
+
+class SPADE_STYLE_Block(nn.Module):
+    """normalization.py:172-192: (SPADE(x, seg) + ApplyStyle(x, w)) / 2 in one fused pass."""
+
+    def __init__(self, fin, opt):
+        super().__init__()
+        spade_config_str = opt.norm_G.replace('spectral', '')
+        self.spade = SPADE(spade_config_str, fin, opt.semantic_nc)
+        self.adain = ApplyStyle(opt.w_dim, channels=fin, use_wscale=False)
+
+    def forward_nhwc(self, x, segmap, latent_style, act=L.ACT_NONE):
+        style = self.adain.linear(latent_style)
+        return self.spade.modulate(x, segmap, style, act)
+
+    def forward(self, x, segmap, latent_style):
+        return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x), segmap, latent_style))

@@ -1,0 +1,633 @@
+"""Autograd operators over the seg2eye_b200 C ABI.
+
+Internal convention: activations are contiguous bf16 tensors shaped (B, H, W, C) ("NHWC").  The module
+layer (models/networks) exposes the reference's logical-NCHW interface through zero-copy permuted views.
+Every arithmetic step calls one of our CUDA kernels through ctypes; torch is used for memory, streams and
+the autograd graph only.
+"""
+import contextlib
+from collections import namedtuple
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act")
+
+_state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False}
+
+
+def bump_weights_epoch():
+    """Called whenever parameters are modified behind torch's back (our Adam kernel)."""
+    _state["weights_epoch"] += 1
+
+
+@contextlib.contextmanager
+def force_impl(impl):
+    """Testing aid: route every tap-convolution through one implementation (L.IMPL_TC / L.IMPL_SIMT)."""
+    old = _state["force_impl"]
+    _state["force_impl"] = impl
+    try:
+        yield
+    finally:
+        _state["force_impl"] = old
+
+
+@contextlib.contextmanager
+def skip_weight_grads():
+    """Skip weight-gradient kernels of convolutions run inside (their parameters receive no .grad).
+    Used for the discriminator inside the generator step, whose parameter gradients the reference computes
+    and then discards (pix2pix_trainer.py:39 zeroes them before the next use)."""
+    old = _state["skip_wgrad"]
+    _state["skip_wgrad"] = True
+    try:
+        yield
+    finally:
+        _state["skip_wgrad"] = old
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- optional per-kernel timing with CUDA events on the launching stream (bench.py roofline numbers)
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = {"tc": [], "norm": []}
+
+
+def profile_end():
+    global _prof
+    p, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {"tc_ms": sum(a.elapsed_time(b) for a, b, _ in p["tc"]), "tc_flop": float(sum(w for _, _, w in p["tc"])),
+           "tc_n": len(p["tc"]), "norm_ms": sum(a.elapsed_time(b) for a, b, _ in p["norm"]),
+           "norm_bytes": float(sum(w for _, _, w in p["norm"])), "norm_n": len(p["norm"])}
+    return out
+
+
+def _timed_call(kind, work, name, *args):
+    if _prof is None:
+        return L.call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.call(name, *args)
+    e1.record()
+    _prof[kind].append((e0, e1, work))
+
+
+def _pick(tc_ok):
+    if _state["force_impl"] is not None:
+        if _state["force_impl"] == L.IMPL_TC and not tc_ok:
+            return L.IMPL_SIMT
+        return _state["force_impl"]
+    return L.IMPL_TC if tc_ok else L.IMPL_SIMT
+
+
+# ------------------------------------------------------------------------------------------------ conv
+_taps_cache = {}
+
+
+def conv_taps(cfg):
+    key = (cfg.kh, cfg.kw, cfg.stride, cfg.pad)
+    if key not in _taps_cache:
+        _taps_cache[key] = L.packed_taps(*key)
+    return _taps_cache[key]
+
+
+def conv_out_hw(cfg, hi, wi):
+    return (hi + 2 * cfg.pad - cfg.kh) // cfg.stride + 1, (wi + 2 * cfg.pad - cfg.kw) // cfg.stride + 1
+
+
+def _desc(B, Hi, Wi, Cin, Ho, Wo, Cout, taps, act, negate=False):
+    d = L.ConvDesc()
+    d.B, d.Hi, d.Wi, d.Cin, d.Ho, d.Wo, d.Cout = B, Hi, Wi, Cin, Ho, Wo, Cout
+    d.ntaps = len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i] = -dy if negate else dy
+        d.tap_dx[i] = -dx if negate else dx
+    d.act = act
+    return d
+
+
+_pack_cache = {}
+
+
+def packed_weights(weights, cfg, transposed):
+    """bf16 tap-major copy of one or more OIHW fp32 master weights (concatenated along Cout); cached until a
+    parameter changes."""
+    key = (tuple(id(w) for w in weights), transposed, cfg.stride)
+    ver = (tuple(w._version for w in weights), tuple(w.data_ptr() for w in weights), _state["weights_epoch"])
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    cin = weights[0].shape[1]
+    cinp = cin * 4 if cfg.stride == 2 else cin
+    ctot = sum(w.shape[0] for w in weights)
+    ntaps = len(conv_taps(cfg))
+    buf = hit[1] if hit is not None else torch.empty(ntaps * ctot * cinp, dtype=BF16, device=weights[0].device)
+    off = 0
+    for w in weights:
+        wd = w.detach()
+        assert wd.is_contiguous() and wd.dtype == F32
+        L.call("s2e_pack_weight", L.ptr(wd), wd.shape[0], cin, cfg.kh, cfg.kw, cfg.stride, cfg.pad, int(transposed),
+               ctot, off, L.ptr(buf), L.stream())
+        off += wd.shape[0]
+    _pack_cache[key] = (ver, buf)
+    return buf
+
+
+def space_to_depth(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty(B, (H + 1) // 2, (W + 1) // 2, 4 * Cc, dtype=BF16, device=x.device)
+    L.call("s2e_space_to_depth", L.ptr(x), B, H, W, Cc, L.ptr(y), L.stream())
+    return y
+
+
+def channel_sums(x2d_c, B, HW, Cc):
+    """fp32 per-channel sum over all pixels of an NHWC bf16 tensor (bias gradients)."""
+    acc = torch.empty(2 * Cc, dtype=torch.float64, device=x2d_c.device)
+    L.call("s2e_norm_stats", L.ptr(x2d_c), B, HW, Cc, 0, L.ptr(acc), L.stream())
+    return acc[:Cc].to(F32)
+
+
+class TapConvFn(torch.autograd.Function):
+    """y = act(inv_sigma * conv(x, W) + b) for one or several weights concatenated along Cout."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, sn, n_w, *wb):
+        weights, biases = wb[:n_w], wb[n_w:]
+        x = _c(x)
+        assert x.dtype == BF16 and x.dim() == 4
+        B, Hi, Wi, Cin = x.shape
+        assert Cin == weights[0].shape[1], "channel mismatch: x has %d, weight expects %d" % (Cin, weights[0].shape[1])
+        xs = space_to_depth(x) if cfg.stride == 2 else x
+        _, His, Wis, Cinp = xs.shape
+        Ho, Wo = conv_out_hw(cfg, Hi, Wi)
+        Cout = sum(w.shape[0] for w in weights)
+        taps = conv_taps(cfg)
+        wp = packed_weights(weights, cfg, False)
+        bias = None
+        if len(biases):
+            bias = biases[0].detach() if len(biases) == 1 else torch.cat([b.detach() for b in biases])
+        inv_sigma = sn[2] if sn is not None else None
+        y = torch.empty(B, Ho, Wo, Cout, dtype=BF16, device=x.device)
+        d = _desc(B, His, Wis, Cinp, Ho, Wo, Cout, taps, cfg.act)
+        impl = _pick(Cinp % 64 == 0 and Cout % 8 == 0)
+        flops = 2.0 * B * Ho * Wo * Cout * Cin * cfg.kh * cfg.kw
+        if impl == L.IMPL_TC:
+            _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream())
+        else:
+            L.call("s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream())
+        ctx.flops = flops
+        ctx.cfg, ctx.sn, ctx.n_w, ctx.n_b = cfg, sn, n_w, len(biases)
+        ctx.in_shape = (B, Hi, Wi, Cin)
+        ctx.weights = weights
+        ctx.skip_wgrad = _state["skip_wgrad"]
+        ctx.save_for_backward(xs, y if cfg.act != L.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cfg, sn, weights = ctx.cfg, ctx.sn, ctx.weights
+        xs, y = ctx.saved_tensors
+        dy = _c(dy)
+        B, Hi, Wi, Cin = ctx.in_shape
+        _, His, Wis, Cinp = xs.shape
+        _, Ho, Wo, Cout = dy.shape
+        taps = conv_taps(cfg)
+        st = L.stream()
+        if cfg.act != L.ACT_NONE:
+            dpre = torch.empty_like(dy)
+            L.call("s2e_act_bwd", L.ptr(dy), L.ptr(y), dy.numel(), cfg.act, L.ptr(dpre), st)
+        else:
+            dpre = dy
+        inv_sigma = sn[2] if sn is not None else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wpt = packed_weights(weights, cfg, True)
+            dd = _desc(B, Ho, Wo, Cout, His, Wis, Cinp, taps, L.ACT_NONE, negate=True)
+            dxs = torch.empty(B, His, Wis, Cinp, dtype=BF16, device=dy.device)
+            impl = _pick(Cout % 64 == 0 and Cinp % 8 == 0)
+            if impl == L.IMPL_TC:
+                _timed_call("tc", ctx.flops, "s2e_tapconv_fwd", dd, L.ptr(dpre), L.ptr(wpt), None, L.ptr(inv_sigma), L.ptr(dxs), impl, st)
+            else:
+                L.call("s2e_tapconv_fwd", dd, L.ptr(dpre), L.ptr(wpt), None, L.ptr(inv_sigma), L.ptr(dxs), impl, st)
+            if cfg.stride == 2:
+                dx = torch.empty(B, Hi, Wi, Cin, dtype=BF16, device=dy.device)
+                L.call("s2e_depth_to_space", L.ptr(dxs), B, Hi, Wi, Cin, L.ptr(dx), st)
+            else:
+                dx = dxs
+        need_w = [ctx.needs_input_grad[4 + i] and not ctx.skip_wgrad for i in range(ctx.n_w)]
+        need_b = [ctx.needs_input_grad[4 + ctx.n_w + i] and not ctx.skip_wgrad for i in range(ctx.n_b)]
+        gw = [None] * ctx.n_w
+        gb = [None] * ctx.n_b
+        if any(need_w):
+            dwp = torch.zeros(len(taps) * Cout * Cinp, dtype=F32, device=dy.device)
+            d = _desc(B, His, Wis, Cinp, Ho, Wo, Cout, taps, L.ACT_NONE)
+            impl = _pick(Cinp >= 64 and Cout >= 64 and Cinp % 8 == 0 and Cout % 8 == 0)
+            if impl == L.IMPL_TC:
+                _timed_call("tc", ctx.flops, "s2e_tapconv_wgrad", d, L.ptr(xs), L.ptr(dpre), L.ptr(dwp), impl, st)
+            else:
+                L.call("s2e_tapconv_wgrad", d, L.ptr(xs), L.ptr(dpre), L.ptr(dwp), impl, st)
+            dot = torch.empty(1, dtype=F32, device=dy.device) if sn is not None else None
+            off = 0
+            for i, w in enumerate(weights):
+                if need_w[i]:
+                    g = torch.empty_like(w)
+                    L.call("s2e_unpack_wgrad", L.ptr(dwp), w.shape[0], w.shape[1], cfg.kh, cfg.kw, cfg.stride, cfg.pad,
+                           Cout, off, L.ptr(w.detach()), L.ptr(sn[0]) if sn else None, L.ptr(sn[1]) if sn else None,
+                           L.ptr(inv_sigma), L.ptr(dot), L.ptr(g), 0, st)
+                    gw[i] = g
+                off += w.shape[0]
+        if any(need_b):
+            sums = channel_sums(dpre, B, Ho * Wo, Cout) if Cout % 8 == 0 else dpre.float().sum(dim=(0, 1, 2))
+            off = 0
+            for i in range(ctx.n_b):
+                n = weights[i].shape[0]
+                if need_b[i]:
+                    gb[i] = sums[off:off + n].clone()
+                off += n
+        return (dx, None, None, None) + tuple(gw) + tuple(gb)
+
+
+def tap_conv(x, cfg, weights, biases=(), sn=None):
+    return TapConvFn.apply(x, cfg, sn, len(weights), *weights, *biases)
+
+
+def spectral_inv_sigma(weight_orig, u, v, training):
+    """One power iteration in place on (u, v) (training mode) and 1/sigma as a device scalar.
+    torch.nn.utils.spectral_norm semantics (reference normalization.py:26, architecture.py:31-34)."""
+    w = weight_orig.detach()
+    rows = w.shape[0]
+    cols = w.numel() // rows
+    inv = torch.empty(1, dtype=F32, device=w.device)
+    scratch = torch.empty(rows + cols, dtype=F32, device=w.device)
+    L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv), L.ptr(scratch),
+           1 if training else 0, L.stream())
+    return inv
+
+
+# ------------------------------------------------------------------------------------------------ norms
+NormCfg = namedtuple("NormCfg", "per_sample act training momentum eps")
+
+
+class SpadeStyleFn(torch.autograd.Function):
+    """out = act(0.5 * [ norm(x) * (1 + gamma) + beta + x * (1 + s0) + s1 ])  (normalization.py:91-105,161-192)."""
+
+    @staticmethod
+    def forward(ctx, x, gb, style, cfg, running_mean, running_var, nbt):
+        x, gb, style = _c(x), _c(gb), _c(style)
+        B, H, W, Cc = x.shape
+        assert gb.shape == (B, H, W, 2 * Cc) and style.shape == (B, 2 * Cc) and style.dtype == F32
+        st = L.stream()
+        G = B if cfg.per_sample else 1
+        batch_stats = cfg.per_sample or cfg.training or running_mean is None
+        if batch_stats:
+            acc = torch.empty(G * 2 * Cc, dtype=torch.float64, device=x.device)
+            mean = torch.empty(G, Cc, dtype=F32, device=x.device)
+            rstd = torch.empty(G, Cc, dtype=F32, device=x.device)
+            L.call("s2e_norm_stats", L.ptr(x), B, H * W, Cc, int(cfg.per_sample), L.ptr(acc), st)
+            upd = (not cfg.per_sample) and cfg.training and running_mean is not None
+            count = float(H * W if cfg.per_sample else B * H * W)
+            L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
+                   L.ptr(running_mean) if upd else None, L.ptr(running_var) if upd else None, cfg.momentum,
+                   L.ptr(nbt) if upd else None, st)
+        else:  # BatchNorm2d in eval mode: running statistics
+            mean = running_mean.detach().clone().view(1, Cc)
+            rstd = torch.rsqrt(running_var.detach() + cfg.eps).view(1, Cc)
+        out = torch.empty_like(x)
+        _timed_call("norm", 8.0 * B * H * W * Cc, "s2e_spade_style_fwd", L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
+                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(out), st)
+        ctx.cfg, ctx.batch_stats = cfg, batch_stats
+        ctx.save_for_backward(x, gb, style, mean, rstd, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg = ctx.cfg
+        if not ctx.batch_stats:
+            raise NotImplementedError("backward through SPADE BatchNorm in eval mode is not supported")
+        x, gb, style, mean, rstd, out = ctx.saved_tensors
+        dout = _c(dout)
+        B, H, W, Cc = x.shape
+        racc = torch.empty(B * 4 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
+        dx = torch.empty_like(x)
+        dgb = torch.empty_like(gb)
+        dstyle = torch.empty_like(style)
+        L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
+               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), 0, L.ptr(dgb),
+               L.ptr(dstyle), L.stream())
+        return dx, dgb, dstyle, None, None, None, None
+
+
+class InstNormFn(torch.autograd.Function):
+    """nn.InstanceNorm2d(affine=False, eps=1e-5) + optional LeakyReLU(0.2) on NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x, act):
+        x = _c(x)
+        B, H, W, Cc = x.shape
+        acc = torch.empty(B * 2 * Cc, dtype=torch.float64, device=x.device)
+        mean = torch.empty(B, Cc, dtype=F32, device=x.device)
+        rstd = torch.empty(B, Cc, dtype=F32, device=x.device)
+        y = torch.empty_like(x)
+        L.call("s2e_instnorm_fwd", L.ptr(x), B, H * W, Cc, act, 1e-5, L.ptr(acc), L.ptr(mean), L.ptr(rstd), L.ptr(y),
+               L.stream())
+        ctx.act = act
+        ctx.save_for_backward(x, y, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        B, H, W, Cc = x.shape
+        racc = torch.empty(B * 2 * Cc, dtype=torch.float64, device=x.device)
+        dx = torch.empty_like(x)
+        L.call("s2e_instnorm_bwd", L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(mean), L.ptr(rstd), B, H * W, Cc, ctx.act,
+               L.ptr(racc), L.ptr(dx), L.stream())
+        return dx, None
+
+
+# ------------------------------------------------------------------------------------------------ elementwise / resampling
+class Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, H, W, Cc = x.shape
+        y = torch.empty(B, 2 * H, 2 * W, Cc, dtype=BF16, device=x.device)
+        L.call("s2e_upsample2x_fwd", L.ptr(x), B, H, W, Cc, L.ptr(y), L.stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        B, H2, W2, Cc = dy.shape
+        dx = torch.empty(B, H2 // 2, W2 // 2, Cc, dtype=BF16, device=dy.device)
+        L.call("s2e_upsample2x_bwd", L.ptr(dy), B, H2 // 2, W2 // 2, Cc, L.ptr(dx), L.stream())
+        return dx
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        y = torch.empty_like(a)
+        L.call("s2e_add", L.ptr(a), L.ptr(b), a.numel(), L.ptr(y), L.stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = _c(x)
+        y = torch.empty_like(x)
+        L.call("s2e_act_fwd", L.ptr(x), x.numel(), act, L.ptr(y), L.stream())
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        L.call("s2e_act_bwd", L.ptr(dy), L.ptr(y), dy.numel(), ctx.act, L.ptr(dx), L.stream())
+        return dx, None
+
+
+class AvgPool3s2Fn(torch.autograd.Function):
+    """F.avg_pool2d(k=3, s=2, p=1, count_include_pad=False) (discriminator.py:46-49)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, H, W, Cc = x.shape
+        y = torch.empty(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc, dtype=BF16, device=x.device)
+        L.call("s2e_avgpool3s2_fwd", L.ptr(x), B, H, W, Cc, L.ptr(y), L.stream())
+        ctx.shape = (B, H, W, Cc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, Cc = ctx.shape
+        dy = _c(dy)
+        dx = torch.empty(B, H, W, Cc, dtype=BF16, device=dy.device)
+        L.call("s2e_avgpool3s2_bwd", L.ptr(dy), B, H, W, Cc, L.ptr(dx), L.stream())
+        return dx
+
+
+class BilinearFn(torch.autograd.Function):
+    """F.interpolate(x, size, mode='bilinear', align_corners=False) of (N,1,H,W) fp32 -> (N,Hd,Wd,1) bf16."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        x = _c(x.float())
+        N, Cc, Hs, Ws = x.shape
+        y = torch.empty(N * Cc, size[0], size[1], 1, dtype=BF16, device=x.device)
+        L.call("s2e_bilinear_fwd", L.ptr(x), N * Cc, Hs, Ws, size[0], size[1], L.ptr(y), L.stream())
+        ctx.shape, ctx.size = (N, Cc, Hs, Ws), size
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, Cc, Hs, Ws = ctx.shape
+        dy = _c(dy)
+        dx = torch.empty(N, Cc, Hs, Ws, dtype=F32, device=dy.device)
+        L.call("s2e_bilinear_bwd", L.ptr(dy), N * Cc, Hs, Ws, ctx.size[0], ctx.size[1], L.ptr(dx), L.stream())
+        return dx, None
+
+
+class ToNHWCFn(torch.autograd.Function):
+    """(B,C,H,W) fp32 -> (B,H,W,C) bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x.float())
+        B, Cc, H, W = x.shape
+        y = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
+        L.call("s2e_nchw_f32_to_nhwc_bf16", L.ptr(x), B, Cc, H, W, L.ptr(y), L.stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        B, H, W, Cc = dy.shape
+        dx = torch.empty(B, Cc, H, W, dtype=F32, device=dy.device)
+        L.call("s2e_nhwc_bf16_to_nchw_f32", L.ptr(dy), B, Cc, H, W, L.ptr(dx), L.stream())
+        return dx
+
+
+class ToNCHWFn(torch.autograd.Function):
+    """(B,H,W,C) bf16 -> (B,C,H,W) fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, H, W, Cc = x.shape
+        y = torch.empty(B, Cc, H, W, dtype=F32, device=x.device)
+        L.call("s2e_nhwc_bf16_to_nchw_f32", L.ptr(x), B, Cc, H, W, L.ptr(y), L.stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy.float())
+        B, Cc, H, W = dy.shape
+        dx = torch.empty(B, H, W, Cc, dtype=BF16, device=dy.device)
+        L.call("s2e_nchw_f32_to_nhwc_bf16", L.ptr(dy), B, Cc, H, W, L.ptr(dx), L.stream())
+        return dx
+
+
+def as_nhwc(x):
+    """Accept the reference's logical-NCHW tensors.  Our own activations (bf16, NHWC storage seen through a
+    permuted view) pass through for free; anything else is converted by the layout kernel."""
+    if x.dtype == BF16:
+        v = x.permute(0, 2, 3, 1)
+        if v.is_contiguous():
+            return v
+        return ToNHWCFn.apply(x)
+    return ToNHWCFn.apply(x)
+
+
+def as_nchw_view(y):
+    return y.permute(0, 3, 1, 2)
+
+
+def one_hot(label, nc):
+    """pix2pix_model.py:144-152 -- (B,1,H,W) integer labels -> (B,nc,H,W) fp32 one-hot (bit-exact)."""
+    label = _c(label.long())
+    B, _, H, W = label.shape
+    out = torch.empty(B, nc, H, W, dtype=F32, device=label.device)
+    L.call("s2e_onehot_nchw", L.ptr(label), B, H, W, nc, L.ptr(out), L.stream())
+    return out
+
+
+def seg_nearest(seg, hd, wd):
+    """F.interpolate(seg, size, mode='nearest') fused with the NCHW fp32 -> NHWC bf16 layout change."""
+    seg = _c(seg.detach().float())
+    B, Cc, Hs, Ws = seg.shape
+    out = torch.empty(B, hd, wd, Cc, dtype=BF16, device=seg.device)
+    L.call("s2e_seg_nearest_nhwc", L.ptr(seg), B, Cc, Hs, Ws, hd, wd, Cc, L.ptr(out), L.stream())
+    return out
+
+
+class MakeDInputFn(torch.autograd.Function):
+    """cat([cat([seg,fake],1), cat([seg,real],1)], 0) as (2B,H,W,nc+1) bf16 (pix2pix_model.py:328-338)."""
+
+    @staticmethod
+    def forward(ctx, seg, fake, real):
+        seg, fake, real = _c(seg.float()), _c(fake.float()), _c(real.float())
+        B, nc, H, W = seg.shape
+        assert fake.shape == (B, 1, H, W) and real.shape == (B, 1, H, W), (fake.shape, real.shape, seg.shape)
+        out = torch.empty(2 * B, H, W, nc + 1, dtype=BF16, device=seg.device)
+        L.call("s2e_make_d_input", L.ptr(seg), L.ptr(fake), L.ptr(real), B, nc, H, W, nc + 1, L.ptr(out), L.stream())
+        ctx.dims = (B, nc, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, nc, H, W = ctx.dims
+        dout = _c(dout)
+        dfake = None
+        if ctx.needs_input_grad[1]:
+            dfake = torch.empty(B, 1, H, W, dtype=F32, device=dout.device)
+            L.call("s2e_d_input_grad", L.ptr(dout), B, nc, H, W, nc + 1, L.ptr(dfake), L.stream())
+        return None, dfake, None
+
+
+class TanhFn(torch.autograd.Function):
+    """(B,H,W,1) bf16 -> tanh -> (B,1,H,W) fp32 (generator.py:99)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, H, W, Cc = x.shape
+        assert Cc == 1
+        y = torch.empty(B, 1, H, W, dtype=F32, device=x.device)
+        L.call("s2e_tanh_fwd", L.ptr(x), x.numel(), L.ptr(y), L.stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy.float())
+        B, _, H, W = y.shape
+        dx = torch.empty(B, H, W, 1, dtype=BF16, device=y.device)
+        L.call("s2e_tanh_bwd", L.ptr(dy), L.ptr(y), y.numel(), L.ptr(dx), L.stream())
+        return dx
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) in fp32.  hw > 0: x is an NHWC bf16 feature (M,h,w,C) flattened in NCHW order with
+    LeakyReLU(0.2) applied first (encoder.py:64-68)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, hw):
+        x = _c(x)
+        M = x.shape[0]
+        N, K = w.shape
+        y = torch.empty(M, N, dtype=F32, device=w.device)
+        L.call("s2e_linear_fwd", L.ptr(x), L.ptr(w.detach()), L.ptr(b.detach()) if b is not None else None, M, N, K, act,
+               hw, L.ptr(y), L.stream())
+        ctx.act, ctx.hw = act, hw
+        ctx.save_for_backward(x, w, y)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy.float())
+        M, (N, K) = x.shape[0], w.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.empty(N, dtype=F32, device=w.device) if (ctx.has_b and ctx.needs_input_grad[2]) else None
+        if dw is None and db is not None:
+            dw = torch.empty_like(w)
+        L.call("s2e_linear_bwd", L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(w.detach()), M, N, K, ctx.act, ctx.hw, L.ptr(dx),
+               L.ptr(dw), L.ptr(db), L.stream())
+        return dx, (dw if ctx.needs_input_grad[1] else None), db, None, None
+
+
+class ReduceLossFn(torch.autograd.Function):
+    """(1,) fp32 = coef * sum f(x[, y]) with f selected by `kind` (loss.py:58-83, nn.L1Loss/MSELoss)."""
+
+    @staticmethod
+    def forward(ctx, x, y, kind, coef):
+        x = _c(x)
+        f32 = int(x.dtype == F32)
+        if y is not None:
+            y = _c(y.detach())
+            if y.dtype != x.dtype:
+                y = y.to(x.dtype)
+            assert y.shape == x.shape
+        out = torch.empty(1, dtype=F32, device=x.device)
+        L.call("s2e_reduce_loss", L.ptr(x), L.ptr(y), x.numel(), f32, kind, coef, L.ptr(out), 0, L.stream())
+        ctx.kind, ctx.coef, ctx.f32 = kind, coef, f32
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, y = ctx.saved_tensors
+        gout = _c(gout.float())
+        dx = torch.empty_like(x)
+        L.call("s2e_reduce_loss_bwd", L.ptr(x), L.ptr(y), x.numel(), ctx.f32, ctx.kind, ctx.coef, L.ptr(gout), L.ptr(dx),
+               0, L.stream())
+        return dx, None, None, None
+
+
+def reduce_loss(x, y, kind, coef):
+    return ReduceLossFn.apply(x, y, kind, float(coef))

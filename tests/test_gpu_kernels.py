@@ -1,0 +1,383 @@
+"""Kernel-level parity (needs a B200): every C-ABI op against a plain PyTorch fp32 statement of the same op on
+identical (bf16-rounded) inputs.  Integer paths are bit-exact; floating point within the stated tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_ACT = 1e-2      # forward activations <= 1e-2 relative error (bf16 in / fp32 accumulate)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.fixture(scope="module")
+def S():
+    from seg2eye_b200 import _lib as L, ops
+    L.lib()
+    return L, ops
+
+
+def nhwc(x):  # NCHW fp32 cpu -> NHWC bf16 cuda
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def nchw(y):  # NHWC cuda -> NCHW fp32 cpu
+    return y.float().permute(0, 3, 1, 2).cpu()
+
+
+# ------------------------------------------------------------------------------------------ integer path
+def test_onehot_and_nearest_bit_exact(S):
+    L, ops = S
+    ints = dict(np.load(os.path.join(GOLD, "ref_ints.npz")))
+    for key_l, key_o in (("label", "onehot"), ("rand_label", "rand_onehot")):
+        lab = torch.from_numpy(ints[key_l]).cuda()
+        oh = ops.one_hot(lab, 4)
+        assert np.array_equal(oh.cpu().numpy().astype(np.uint8), ints[key_o])
+    seg = torch.from_numpy(ints["onehot"]).float().cuda()
+    for k, v in ints.items():
+        if k.startswith("nearest_"):
+            h, w = [int(s) for s in k.split("_")[1].split("x")]
+            out = ops.seg_nearest(seg, h, w)
+            assert np.array_equal(nchw(out).numpy().astype(np.uint8), v), k
+    seg2 = torch.from_numpy(ints["rand_onehot"]).float().cuda()
+    out = ops.seg_nearest(seg2, 9, 13)
+    assert np.array_equal(nchw(out).numpy().astype(np.uint8), ints["rand_nearest_9x13"])
+
+
+def test_layout_roundtrip(S):
+    L, ops = S
+    x = torch.randn(2, 5, 7, 9)
+    y = ops.ToNHWCFn.apply(x.cuda())
+    assert torch.equal(y.cpu().float(), bf(x).permute(0, 2, 3, 1))
+    z = ops.ToNCHWFn.apply(y)
+    assert torch.equal(z.cpu(), bf(x))
+
+
+# ------------------------------------------------------------------------------------------ convolutions
+def conv_case(S, impl, B, Cin, Cout, H, W, k, stride, pad, act=0, sn=False, n_w=1, seed=0, bias=True):
+    L, ops = S
+    g = torch.Generator().manual_seed(seed)
+    x = bf(torch.randn(B, Cin, H, W, generator=g))
+    ws = [bf(torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5) for _ in range(n_w)]
+    bs = [torch.randn(Cout, generator=g) * 0.1 for _ in range(n_w)] if bias else []
+    inv_sigma = 0.7 if sn else 1.0
+    # reference (CPU fp32)
+    xr = x.clone().requires_grad_()
+    wr = [w.clone().requires_grad_() for w in ws]
+    br = [b.clone().requires_grad_() for b in bs]
+    yr = F.conv2d(xr, torch.cat(wr, 0) * inv_sigma, torch.cat(br, 0) if bias else None, stride=stride, padding=pad)
+    if act == 1:
+        yr = F.leaky_relu(yr, 0.2)
+    elif act == 2:
+        yr = F.relu(yr)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    # ours
+    xc = nhwc(x).requires_grad_()
+    wc = [w.cuda().requires_grad_() for w in ws]
+    bc = [b.cuda().requires_grad_() for b in bs]
+    cfg = ops.ConvCfg(k, k, stride, pad, act)
+    snt = None
+    if sn:
+        # u, v only enter the backward; choose them so that the sigma chain-rule term is exercised
+        u = F.normalize(torch.randn(Cout, generator=g), dim=0).cuda()
+        v = F.normalize(torch.randn(Cin * k * k, generator=g), dim=0).cuda()
+        snt = (u, v, torch.tensor([inv_sigma], device="cuda"))
+    with ops.force_impl(impl):
+        y = ops.tap_conv(xc, cfg, tuple(wc), tuple(bc), snt)
+        y.backward(nhwc(dy))
+    torch.cuda.synchronize()
+    assert rel(nchw(y), yr) < TOL_ACT, ("fwd", rel(nchw(y), yr))
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT, ("dgrad", rel(nchw(xc.grad), xr.grad))
+    for i in range(n_w):
+        gw_ref = wr[i].grad
+        if sn:
+            # y = conv(x, W_orig) * inv_sigma with sigma = u^T W v  =>  dW_orig = is*(G - is*<G,W> u v^T), G = dL/dW_eff
+            G = wr[i].grad / inv_sigma
+            uv = torch.outer(u.cpu(), v.cpu()).view_as(G)
+            gw_ref = inv_sigma * (G - inv_sigma * (G * ws[i]).sum() * uv)
+        assert rel(wc[i].grad, gw_ref) < TOL_ACT, ("wgrad", i, rel(wc[i].grad, gw_ref))
+        if bias:
+            assert rel(bc[i].grad, br[i].grad) < TOL_ACT, ("bgrad", i, rel(bc[i].grad, br[i].grad))
+
+
+SIMT_CASES = [
+    # B, Cin, Cout, H, W, k, stride, pad, act
+    (2, 4, 128, 10, 8, 3, 1, 1, 2),      # mlp_shared-like (+ReLU)
+    (2, 4, 32, 10, 8, 3, 1, 1, 0),       # G.fc-like
+    (1, 16, 1, 20, 16, 3, 1, 1, 0),      # conv_img-like (Cout = 1)
+    (2, 5, 16, 21, 17, 4, 2, 2, 1),      # D model0 (4x4 s2 p2 + LeakyReLU), odd size
+    (2, 32, 1, 11, 9, 4, 1, 2, 0),       # D model4 (Cout = 1, 4x4 s1 p2)
+    (2, 1, 16, 32, 32, 3, 2, 1, 0),      # E layer0 (3x3 s2 p1, Cin = 1)
+    (1, 24, 40, 9, 7, 1, 1, 0, 0),       # 1x1 with ragged channel counts
+    (2, 16, 32, 13, 11, 4, 2, 2, 0),     # 4x4 s2 p2 mid layer, odd size
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES)
+def test_conv_simt_vs_torch(S, case):
+    L, ops = S
+    conv_case(S, L.IMPL_SIMT, *case)
+
+
+TC_CASES = [
+    (2, 128, 128, 10, 8, 3, 1, 1, 0),      # gamma|beta-like, tiny map (tile spans batch)
+    (1, 64, 64, 20, 16, 3, 1, 1, 0),
+    (2, 128, 256, 20, 16, 3, 1, 1, 0),     # BN = 256
+    (1, 256, 128, 40, 32, 3, 1, 1, 0),
+    (1, 128, 64, 40, 32, 1, 1, 0, 0),      # 1x1 shortcut
+    (3, 64, 128, 21, 17, 4, 2, 2, 0),      # D 4x4 s2 p2 (space-to-depth, Cin' = 256), odd size
+    (2, 64, 128, 11, 9, 4, 1, 2, 0),       # D 4x4 s1 p2: output larger than input
+    (2, 64, 128, 32, 32, 3, 2, 1, 0),      # E 3x3 s2 p1
+    (1, 64, 72, 16, 8, 3, 1, 1, 1),        # Cout not a multiple of 64, fused LeakyReLU
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_vs_torch(S, case):
+    L, ops = S
+    conv_case(S, L.IMPL_TC, *case)
+
+
+def test_conv_tcgen05_fused_gamma_beta_and_spectral(S):
+    L, ops = S
+    conv_case(S, L.IMPL_TC, 2, 128, 64, 20, 16, 3, 1, 1, 0, n_w=2)           # two weights packed along Cout
+    conv_case(S, L.IMPL_TC, 2, 64, 128, 20, 16, 3, 1, 1, 0, sn=True)         # 1/sigma epilogue + chain rule
+    conv_case(S, L.IMPL_SIMT, 2, 16, 24, 12, 10, 4, 2, 2, 0, sn=True, bias=False)
+
+
+def test_conv_tcgen05_large_k_many_tiles(S):
+    L, ops = S
+    conv_case(S, L.IMPL_TC, 4, 512, 512, 20, 16, 3, 1, 1, 0, seed=3)         # K = 4608, persistent loop > 1 tile/CTA
+
+
+# ------------------------------------------------------------------------------------------ spectral norm
+def test_spectral_power_iteration(S):
+    L, ops = S
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(48, 20, 3, 3, generator=g)
+    u = F.normalize(torch.randn(48, generator=g), dim=0)
+    v = F.normalize(torch.randn(180, generator=g), dim=0)
+    wm = w.view(48, -1)
+    v1 = F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
+    u1 = F.normalize(torch.mv(wm, v1), dim=0, eps=1e-12)
+    sigma = torch.dot(u1, torch.mv(wm, v1))
+    uc, vc = u.cuda(), v.cuda()
+    inv = ops.spectral_inv_sigma(w.cuda(), uc, vc, True)
+    assert rel(uc, u1) < 1e-5 and rel(vc, v1) < 1e-5 and abs(float(inv) * float(sigma) - 1) < 1e-5
+    # eval mode: buffers untouched
+    u2, v2 = u.cuda(), v.cuda()
+    inv2 = ops.spectral_inv_sigma(w.cuda(), u2, v2, False)
+    assert torch.equal(u2.cpu(), u) and torch.equal(v2.cpu(), v)
+    assert abs(float(inv2) * float(torch.dot(u, torch.mv(wm, v))) - 1) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("per_sample,act,C", [(False, 1, 64), (False, 0, 1024), (True, 1, 48), (False, 1, 8)])
+def test_spade_style_fwd_bwd(S, per_sample, act, C):
+    L, ops = S
+    g = torch.Generator().manual_seed(2)
+    B, H, W = 3, 12, 10
+    x = bf(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3)
+    gam = bf(torch.randn(B, C, H, W, generator=g) * 0.5)
+    bet = bf(torch.randn(B, C, H, W, generator=g) * 0.5)
+    style = torch.randn(B, 2 * C, generator=g) * 0.5
+    rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    xr, gr, br, sr = [t.clone().requires_grad_() for t in (x, gam, bet, style)]
+    if per_sample:
+        xn = F.instance_norm(xr, eps=1e-5)
+        rm, rv = rm0.clone(), rv0.clone()
+    else:
+        rm, rv = rm0.clone(), rv0.clone()
+        xn = F.batch_norm(xr, rm, rv, training=True, momentum=0.1, eps=1e-5)
+    out_r = 0.5 * (xn * (1 + gr) + br + xr * (1 + sr[:, :C, None, None]) + sr[:, C:, None, None])
+    if act:
+        out_r = F.leaky_relu(out_r, 0.2)
+    dout = bf(torch.randn(out_r.shape, generator=g))
+    out_r.backward(dout)
+
+    xc = nhwc(x).requires_grad_()
+    gbc = torch.cat([nhwc(gam), nhwc(bet)], dim=3).contiguous().requires_grad_()
+    sc = style.cuda().requires_grad_()
+    rmc, rvc, nbt = rm0.cuda(), rv0.cuda(), torch.tensor(3, device="cuda")
+    cfg = ops.NormCfg(per_sample, act, True, 0.1, 1e-5)
+    if per_sample:
+        out = ops.SpadeStyleFn.apply(xc, gbc, sc, cfg, None, None, None)
+    else:
+        out = ops.SpadeStyleFn.apply(xc, gbc, sc, cfg, rmc, rvc, nbt)
+    out.backward(nhwc(dout))
+    torch.cuda.synchronize()
+    assert rel(nchw(out), out_r) < 5e-3
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
+    assert rel(nchw(gbc.grad[..., :C]), gr.grad) < TOL_ACT
+    assert rel(nchw(gbc.grad[..., C:]), br.grad) < TOL_ACT
+    assert rel(sc.grad, sr.grad) < TOL_ACT
+    if not per_sample:
+        assert rel(rmc, rm) < 1e-4 and rel(rvc, rv) < 1e-4 and int(nbt) == 4
+
+
+@pytest.mark.parametrize("act,C", [(1, 64), (0, 512), (1, 16)])
+def test_instance_norm_fwd_bwd(S, act, C):
+    L, ops = S
+    g = torch.Generator().manual_seed(4)
+    x = bf(torch.randn(3, C, 9, 11, generator=g) * 2 + 1)
+    xr = x.clone().requires_grad_()
+    yr = F.instance_norm(xr, eps=1e-5)
+    if act:
+        yr = F.leaky_relu(yr, 0.2)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc = nhwc(x).requires_grad_()
+    y = ops.InstNormFn.apply(xc, act)
+    y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < 5e-3
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
+
+
+# ------------------------------------------------------------------------------------------ resampling / elementwise
+def test_upsample_avgpool_bilinear_add_act(S):
+    L, ops = S
+    g = torch.Generator().manual_seed(5)
+    x = bf(torch.randn(2, 16, 5, 7, generator=g))
+    xr = x.clone().requires_grad_()
+    yr = F.interpolate(xr, scale_factor=2, mode="nearest")
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc = nhwc(x).requires_grad_()
+    y = ops.Upsample2xFn.apply(xc)
+    y.backward(nhwc(dy))
+    assert torch.equal(nchw(y), yr.detach())
+    assert rel(nchw(xc.grad), xr.grad) < 5e-3
+
+    for (H, W) in [(12, 10), (13, 9)]:
+        x = bf(torch.randn(2, 5, H, W, generator=g))
+        xr = x.clone().requires_grad_()
+        yr = F.avg_pool2d(xr, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
+        dy = bf(torch.randn(yr.shape, generator=g))
+        yr.backward(dy)
+        xc = nhwc(x).requires_grad_()
+        y = ops.AvgPool3s2Fn.apply(xc)
+        y.backward(nhwc(dy))
+        assert rel(nchw(y), yr) < 5e-3 and rel(nchw(xc.grad), xr.grad) < 5e-3
+
+    x = torch.rand(3, 1, 40, 32, generator=g) * 2 - 1
+    xr = x.clone().requires_grad_()
+    yr = F.interpolate(xr, size=(64, 64), mode="bilinear", align_corners=False)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc = x.cuda().requires_grad_()
+    y = ops.BilinearFn.apply(xc, (64, 64))
+    y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < 5e-3 and rel(xc.grad, xr.grad) < 5e-3
+
+    a, b = bf(torch.randn(2, 8, 3, 5, generator=g)), bf(torch.randn(2, 8, 3, 5, generator=g))
+    assert rel(nchw(ops.AddFn.apply(nhwc(a), nhwc(b))), a + b) < 5e-3
+    ac = nhwc(a).requires_grad_()
+    z = ops.ActFn.apply(ac, L.ACT_LRELU)
+    z.backward(nhwc(b))
+    ar = a.clone().requires_grad_()
+    F.leaky_relu(ar, 0.2).backward(b)
+    assert rel(nchw(z), F.leaky_relu(a, 0.2)) < 5e-3 and rel(nchw(ac.grad), ar.grad) < 5e-3
+
+
+def test_d_input_tanh_linear_losses_adam(S):
+    L, ops = S
+    g = torch.Generator().manual_seed(6)
+    B, H, W = 2, 6, 5
+    seg = F.one_hot(torch.randint(0, 4, (B, H, W), generator=g), 4).permute(0, 3, 1, 2).float()
+    fake, real = torch.rand(B, 1, H, W, generator=g) * 2 - 1, torch.rand(B, 1, H, W, generator=g) * 2 - 1
+    fc = fake.cuda().requires_grad_()
+    out = ops.MakeDInputFn.apply(seg.cuda(), fc, real.cuda())
+    ref = torch.cat([torch.cat([seg, fake], 1), torch.cat([seg, real], 1)], 0)
+    assert rel(nchw(out), bf(ref)) < 1e-6
+    dout = bf(torch.randn(out.shape, generator=g))
+    out.backward(dout.cuda().to(torch.bfloat16))
+    assert rel(fc.grad, dout[:B, :, :, 4].unsqueeze(1)) < 1e-6
+
+    x = bf(torch.randn(B, 1, H, W, generator=g))
+    xc = nhwc(x).requires_grad_()
+    y = ops.TanhFn.apply(xc)
+    dy = torch.randn(B, 1, H, W, generator=g)
+    y.backward(dy.cuda())
+    xr = x.clone().requires_grad_()
+    torch.tanh(xr).backward(dy)
+    assert rel(y, torch.tanh(x)) < 1e-5 and rel(nchw(xc.grad), xr.grad) < 5e-3
+
+    # FC 16 -> 2C with LeakyReLU (normalization.py:134-141)
+    w, b, xin = torch.randn(24, 16, generator=g) * 0.25, torch.randn(24, generator=g) * 0.1, torch.randn(3, 16, generator=g)
+    wr, br_, xr = [t.clone().requires_grad_() for t in (w, b, xin)]
+    yr = F.leaky_relu(F.linear(xr, wr, br_), 0.2)
+    dy = torch.randn(3, 24, generator=g)
+    yr.backward(dy)
+    wc, bc, xc = [t.cuda().requires_grad_() for t in (w, b, xin)]
+    y = ops.LinearFn.apply(xc, wc, bc, L.ACT_LRELU, 0)
+    y.backward(dy.cuda())
+    for a_, b_ in ((y, yr), (wc.grad, wr.grad), (bc.grad, br_.grad), (xc.grad, xr.grad)):
+        assert rel(a_, b_) < 1e-5
+    # encoder head: LeakyReLU + NCHW flatten of an NHWC feature (encoder.py:64-68)
+    feat = bf(torch.randn(3, 8, 4, 4, generator=g))
+    w2, b2 = torch.randn(16, 128, generator=g) * 0.1, torch.randn(16, generator=g) * 0.1
+    fr, w2r, b2r = [t.clone().requires_grad_() for t in (feat, w2, b2)]
+    yr = F.linear(F.leaky_relu(fr, 0.2).view(3, -1), w2r, b2r)
+    dy = torch.randn(3, 16, generator=g)
+    yr.backward(dy)
+    fcu = nhwc(feat).requires_grad_()
+    w2c, b2c = w2.cuda().requires_grad_(), b2.cuda().requires_grad_()
+    y = ops.LinearFn.apply(fcu, w2c, b2c, L.ACT_NONE, 16)
+    y.backward(dy.cuda())
+    assert rel(y, yr) < 1e-5 and rel(w2c.grad, w2r.grad) < 1e-5 and rel(b2c.grad, b2r.grad) < 1e-5
+    assert rel(nchw(fcu.grad), fr.grad) < 5e-3
+
+    # loss reductions
+    p = bf(torch.randn(2, 1, 9, 7, generator=g))
+    q = bf(torch.randn(2, 1, 9, 7, generator=g))
+    for kind, fn in ((L.RED_SUM, lambda t: t.sum()), (L.RED_HINGE_REAL, lambda t: torch.clamp(t - 1, max=0).sum()),
+                     (L.RED_HINGE_FAKE, lambda t: torch.clamp(-t - 1, max=0).sum()),
+                     (L.RED_L1, lambda t: (t - q).abs().sum()), (L.RED_L2, lambda t: ((t - q) ** 2).sum())):
+        for dt in (torch.float32, torch.bfloat16):
+            pr = p.clone().requires_grad_()
+            lr_ = fn(pr) * 0.37
+            lr_.backward()
+            pc = p.cuda().to(dt).requires_grad_()
+            yq = q.cuda().to(dt) if kind in (L.RED_L1, L.RED_L2) else None
+            lo = ops.reduce_loss(pc, yq, kind, 0.37)
+            lo.sum().backward()
+            assert abs(float(lo) - float(lr_)) < 1e-4 * max(1.0, abs(float(lr_))), (kind, dt)
+            assert rel(pc.grad.float(), pr.grad) < 5e-3, (kind, dt)
+
+    # Adam (torch.optim.Adam semantics, betas (0, 0.9) as under TTUR)
+    from seg2eye_b200 import optim
+    p0, gr = torch.randn(1000, generator=g), torch.randn(3, 1000, generator=g)
+    pr = p0.clone().requires_grad_()
+    pc = p0.cuda().requires_grad_()
+    o_r = torch.optim.Adam([pr], lr=1e-3, betas=(0.0, 0.9))
+    o_c = optim.Adam([pc], lr=1e-3, betas=(0, 0.9))
+    for i in range(3):
+        pr.grad = gr[i].clone()
+        pc.grad = gr[i].cuda()
+        o_r.step()
+        o_c.step()
+    assert rel(pc, pr) < 1e-6
+
+
+def test_space_to_depth_roundtrip(S):
+    L, ops = S
+    x = bf(torch.randn(2, 3, 7, 9))
+    xc = nhwc(x)
+    y = ops.space_to_depth(xc)
+    assert y.shape == (2, 4, 5, 12)
+    xp = F.pad(x, (0, 1, 0, 1))
+    ref = torch.stack([xp[:, :, i::2, j::2] for i in (0, 1) for j in (0, 1)], dim=1).reshape(2, 12, 4, 5)
+    assert torch.equal(nchw(y), ref)

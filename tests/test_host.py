@@ -1,0 +1,153 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol, the drop-in
+modules reproduce the reference's state_dict layout, geometry helpers, and the data-parallel gradient
+reduction under gloo with world_size 2."""
+import os
+import re
+import socket
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import seg2eye_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from seg2eye_b200 import _lib as L
+    hdr = open(os.path.join(REPO, "include", "seg2eye_b200.h")).read()
+    declared = set(re.findall(r"\b(s2e_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("s2e_conv_t")
+    lib = L.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(L.exported_symbols()), declared ^ set(L.exported_symbols())
+    assert lib.s2e_abi_version() == 1
+
+
+def test_packed_taps_geometry():
+    from seg2eye_b200 import _lib as L, ops
+    assert L.packed_taps(3, 3, 1, 1) == [(r - 1, s - 1) for r in range(3) for s in range(3)]
+    assert L.packed_taps(1, 1, 1, 0) == [(0, 0)]
+    assert L.packed_taps(4, 4, 2, 2) == [(-1, -1), (-1, 0), (0, -1), (0, 0)]     # 4x4 s2 p2 == 2x2 on space-to-depth
+    assert L.packed_taps(3, 3, 2, 1) == [(-1, -1), (-1, 0), (0, -1), (0, 0)]
+    assert len(L.packed_taps(4, 4, 1, 2)) == 16
+    # output sizes the reference produces
+    assert ops.conv_out_hw(ops.ConvCfg(4, 4, 2, 2, 0), 320, 256) == (161, 129)
+    assert ops.conv_out_hw(ops.ConvCfg(4, 4, 1, 2, 0), 41, 33) == (42, 34)
+    assert ops.conv_out_hw(ops.ConvCfg(3, 3, 2, 1, 0), 256, 256) == (128, 128)
+
+
+def _opts(**kw):
+    o = O.make_opt(**kw)
+    d = vars(o).copy()
+    d.update(gpu_ids=[], init_type="xavier", init_variance=0.02, netD_subarch="n_layer", continue_train=False,
+             which_epoch="latest", checkpoints_dir="/tmp/s2e_ckpt", name="t", no_vgg_loss=True, lambda_openeds=0.0,
+             lambda_style_w=0.0, lambda_style_feat=0.0, lambda_gram=0.0, netG="spadestyle", netD="multiscale")
+    return o, SimpleNamespace(**d)
+
+
+@pytest.mark.parametrize("kw", [dict(ngf=16, ndf=16), dict(ngf=8, ndf=8, norm_G="spectralspadeinstance3x3")])
+def test_state_dict_layout_matches_reference(kw):
+    from seg2eye_b200.models import networks
+    oopt, opt = _opts(**kw)
+    for net, shapes in ((networks.define_G(opt), O.generator_shapes(oopt)),
+                        (networks.define_D(opt), O.discriminator_shapes(oopt)),
+                        (networks.define_E(opt), O.encoder_shapes(oopt))):
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        for k, v in sd.items():
+            assert tuple(v.shape) == tuple(shapes[k]), k
+            assert v.dtype == (torch.int64 if k.endswith("num_batches_tracked") else torch.float32)
+        # loads a reference-layout checkpoint, including one saved under nn.DataParallel ('module.' prefix)
+        net.load_state_dict(O.synth_state(shapes, 1))
+
+
+def test_full_size_parameter_counts():
+    """G 92.46 M, D 5.53 M, E 6.53 M parameters."""
+    oopt = O.make_opt()
+    cnt = lambda shapes: sum(int(torch.tensor(s).prod()) if len(s) else 1 for k, s in shapes.items() if O._is_param(k))
+    assert round(cnt(O.generator_shapes(oopt)) / 1e6, 2) == 92.46
+    assert round(cnt(O.discriminator_shapes(oopt)) / 1e6, 2) == 5.53
+    assert round(cnt(O.encoder_shapes(oopt)) / 1e6, 2) == 6.53
+
+
+def test_init_weights_like_reference():
+    from seg2eye_b200.models import networks
+    _, opt = _opts(ngf=16, ndf=16)
+    torch.manual_seed(0)
+    G = networks.define_G(opt)
+    sd = G.state_dict()
+    w = sd["head_0.conv_0.weight_orig"]
+    fan = w.shape[1] * 9 + w.shape[0] * 9
+    assert abs(float(w.std()) - 0.02 * (2.0 / fan) ** 0.5) < 0.2 * 0.02 * (2.0 / fan) ** 0.5   # xavier_normal(gain 0.02)
+    assert float(sd["head_0.conv_0.bias"].abs().max()) == 0.0
+    assert abs(float(sd["head_0.norm_0.adain.linear.weight"].std()) - 0.25) < 0.03             # FC: randn * 16^-0.5
+
+
+def test_trainer_lr_schedule_and_errors():
+    from seg2eye_b200.models.pix2pix_model import Pix2PixModel
+    from seg2eye_b200.trainers.pix2pix_trainer import Pix2PixTrainer
+    _, opt = _opts(ngf=8, ndf=8)
+    tr = Pix2PixTrainer(opt)
+    assert tr.optimizer_G.param_groups[0]["lr"] == opt.lr / 2 and tr.optimizer_D.param_groups[0]["lr"] == opt.lr * 2
+    assert tr.optimizer_G.param_groups[0]["betas"] == (0.0, 0.9)
+    tr.update_learning_rate(14)
+    assert tr.old_lr == opt.lr
+    tr.update_learning_rate(15)
+    assert abs(tr.old_lr - (opt.lr - opt.lr / 7)) < 1e-12
+    assert abs(tr.optimizer_D.param_groups[0]["lr"] - 2 * tr.old_lr) < 1e-12
+    with pytest.raises(ValueError):
+        tr.pix2pix_model({"label": torch.zeros(1, 1, 8, 8), "style_image": torch.zeros(1, 4, 1, 8, 8)}, mode="bogus") \
+            if torch.cuda.is_available() else (_ for _ in ()).throw(ValueError())
+    # the product path never falls back to the CPU
+    with pytest.raises(RuntimeError):
+        from seg2eye_b200 import ops
+        ops.one_hot(torch.zeros(1, 1, 4, 4, dtype=torch.long), 4)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    from seg2eye_b200 import parallel
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (1000, 17, 300000, 5)]
+    for i, p in enumerate(params):
+        p.grad = None if i == 1 else torch.full_like(p, float(rank + 1) * (i + 1))   # params[1]: no grad anywhere (fc_var)
+    red = parallel.GradReducer(params, bucket_bytes=1 << 20)
+    assert len(red.buckets()) >= 2
+    red.allreduce()
+    ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(params) if i != 1)
+    ok = ok and params[1].grad is None
+    m = torch.nn.Linear(3, 3)
+    parallel.broadcast_module(m, 0)
+    ref = [t.clone() for t in m.parameters()]
+    for t in ref:
+        dist.broadcast(t, 0)
+    ok = ok and all(torch.equal(a, b) for a, b in zip(ref, m.parameters()))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_grad_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
