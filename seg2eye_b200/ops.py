@@ -121,17 +121,21 @@ _pack_cache = {}
 
 def packed_weights(weights, cfg, transposed):
     """bf16 tap-major copy of one or more OIHW fp32 master weights (concatenated along Cout); cached until a
-    parameter changes."""
-    key = (tuple(id(w) for w in weights), transposed, cfg.stride)
+    parameter changes.  Entries hold weak references so a recycled id() can never alias a dead tensor."""
+    import weakref
+    key = (tuple(id(w) for w in weights), transposed, cfg.stride, cfg.pad)
     ver = (tuple(w._version for w in weights), tuple(w.data_ptr() for w in weights), _state["weights_epoch"])
     hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    if hit is not None and not all(r() is w for r, w in zip(hit[0], weights)):
+        hit = None
+    if hit is not None and hit[1] == ver:
+        return hit[2]
     cin = weights[0].shape[1]
     cinp = cin * 4 if cfg.stride == 2 else cin
     ctot = sum(w.shape[0] for w in weights)
     ntaps = len(conv_taps(cfg))
-    buf = hit[1] if hit is not None else torch.empty(ntaps * ctot * cinp, dtype=BF16, device=weights[0].device)
+    n = ntaps * ctot * cinp
+    buf = hit[2] if (hit is not None and hit[2].numel() == n) else torch.empty(n, dtype=BF16, device=weights[0].device)
     off = 0
     for w in weights:
         wd = w.detach()
@@ -139,7 +143,10 @@ def packed_weights(weights, cfg, transposed):
         L.call("s2e_pack_weight", L.ptr(wd), wd.shape[0], cin, cfg.kh, cfg.kw, cfg.stride, cfg.pad, int(transposed),
                ctot, off, L.ptr(buf), L.stream())
         off += wd.shape[0]
-    _pack_cache[key] = (ver, buf)
+    if len(_pack_cache) > 4096:
+        for k in [k for k, v in _pack_cache.items() if any(r() is None for r in v[0])]:
+            del _pack_cache[k]
+    _pack_cache[key] = (tuple(weakref.ref(w) for w in weights), ver, buf)
     return buf
 
 

@@ -342,6 +342,7 @@ def test_d_input_tanh_linear_losses_adam(S):
 
     # loss reductions
     p = bf(torch.randn(2, 1, 9, 7, generator=g))
+    p = bf(torch.where((p.abs() - 1).abs() < 1e-2, p * 1.1, p))   # keep away from the hinge kink (sub-gradient ties)
     q = bf(torch.randn(2, 1, 9, 7, generator=g))
     for kind, fn in ((L.RED_SUM, lambda t: t.sum()), (L.RED_HINGE_REAL, lambda t: torch.clamp(t - 1, max=0).sum()),
                      (L.RED_HINGE_FAKE, lambda t: torch.clamp(-t - 1, max=0).sum()),
