@@ -38,7 +38,8 @@ extern "C" {
 
 const char* s2e_last_error(void);
 int s2e_abi_version(void);
-/* debug knobs (bring-up only): key 0 = swap LBO/SBO in MN-major UMMA descriptors, key 1 = force SIMT. */
+/* debug knobs (bring-up only): key 0 = swap LBO/SBO in MN-major UMMA descriptors, key 1 = force SIMT,
+ * key 2 = keep thin-channel layers on the generic SIMT kernel. */
 int s2e_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------------------------
@@ -175,9 +176,12 @@ int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32,
                         const float* gout, void* dx, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------ optimizer
- * torch.optim.Adam single-tensor step (pix2pix_model.py:105-108); step = 1-based step count. */
-int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, void* stream);
+ * torch.optim.Adam (pix2pix_model.py:105-108).  The step count, learning rate and bias corrections live in a 4-float
+ * DEVICE array `state` = {step, lr, lr/(1-b1^step), sqrt(1-b2^step)} so that a whole training step can be replayed
+ * from a CUDA graph: s2e_adam_prepare advances it once per optimizer step, s2e_adam_step applies it to one tensor. */
+int s2e_adam_prepare(float* state, float beta1, float beta2, void* stream);
+int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* state, float beta1,
+                  float beta2, float eps, float weight_decay, void* stream);
 int s2e_fill_f32(float* p, long long n, float value, void* stream);
 
 #ifdef __cplusplus

@@ -62,7 +62,8 @@ _SIGS = {
     "s2e_linear_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "s2e_reduce_loss": [_P, _P, _LL, _I, _I, _F, _P, _I, _P],
     "s2e_reduce_loss_bwd": [_P, _P, _LL, _I, _I, _F, _P, _P, _I, _P],
-    "s2e_adam_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _P],
+    "s2e_adam_prepare": [_P, _F, _F, _P],
+    "s2e_adam_step": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P],
     "s2e_fill_f32": [_P, _LL, _F, _P],
 }
 

@@ -185,8 +185,15 @@ Geom make_geom(const s2e_conv_t* d) {
 
 }  // namespace
 
+int s2e_thin_fwd(const s2e_conv_t*, const void*, const void*, const float*, const float*, void*, cudaStream_t);
+int s2e_thin_wgrad(const s2e_conv_t*, const void*, const void*, float*, cudaStream_t);
+
 int s2e_tapconv_fwd_simt(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
                          void* y, cudaStream_t stream) {
+  if (!s2e_debug_get(2)) {  // debug key 2 = keep thin layers on the generic kernel
+    const int rc = s2e_thin_fwd(d, x, wp, bias, scale, y, stream);
+    if (rc != 0) return rc < 0 ? rc : S2E_OK;
+  }
   Geom g = make_geom(d);
   const long long P = (long long)d->B * d->Ho * d->Wo;
   if (P == 0) return S2E_OK;
@@ -202,6 +209,10 @@ int s2e_tapconv_fwd_simt(const s2e_conv_t* d, const void* x, const void* wp, con
 }
 
 int s2e_tapconv_wgrad_simt(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {
+  if (!s2e_debug_get(2)) {
+    const int rc = s2e_thin_wgrad(d, x, dy, dwp, stream);
+    if (rc != 0) return rc < 0 ? rc : S2E_OK;
+  }
   Geom g = make_geom(d);
   const long long P = (long long)d->B * d->Ho * d->Wo;
   if (P == 0) return S2E_OK;

@@ -1,0 +1,285 @@
+// "Thin" tap-convolutions: one side has only a handful of channels (the 4-class segmap, the 5-channel D input, the
+// 1-channel image / PatchGAN logit).  These layers are < 1.5 % of the step's FLOPs but K or N is 1..36, so they are
+// bandwidth-bound CUDA-core work, not tensor-core work.  Same contract as s2e_tapconv_{fwd,wgrad}.
+//   K1 thin input  : y[p][co]  = act(scale * sum_t sum_cs x[p+t][cs] W[t][co][cs] + b)      (mlp_shared, G.fc, D model0,
+//                                                                                            E layer0, dgrad of conv_img/model4)
+//   K2 thin output : y[p][cs]  = act(scale * sum_t sum_ci x[p+t][ci] W[t][cs][ci] + b)      (conv_img, D model4, dgrad of D model0)
+//   K3 thin wgrad  : dW[t][co][ci] += sum_p dy[p][co] x[p+t][ci]  with either Cin or Cout thin
+#include "common.cuh"
+
+namespace {
+
+struct ThinGeom {
+  int B, Hi, Wi, Cin, Ho, Wo, Cout, ntaps, act;
+  int dy[S2E_MAX_TAPS], dx[S2E_MAX_TAPS];
+};
+
+constexpr int K1_CO_TILE = 256;  // couts per block (weights staged in smem as float)
+
+// ------------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(256) thin_in_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                          const float* __restrict__ bias, const float* __restrict__ scale,
+                                                          bf16* __restrict__ y, const ThinGeom g, long long P) {
+  extern __shared__ float ws[];  // [T][Cs][cot]  (cot = couts of this block)
+  const int co0 = blockIdx.y * K1_CO_TILE;
+  const int cot = min(K1_CO_TILE, g.Cout - co0);
+  const int Cs = g.Cin;
+  for (int i = threadIdx.x; i < g.ntaps * Cs * cot; i += blockDim.x) {
+    const int co = i % cot, r = i / cot, cs = r % Cs, t = r / Cs;
+    ws[i] = __bfloat162float(wp[((long long)t * g.Cout + co0 + co) * Cs + cs]);
+  }
+  __syncthreads();
+  const int ncog = cot >> 3;
+  const float sc = scale ? __ldg(scale) : 1.f;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < P * ncog; v += (long long)gridDim.x * blockDim.x) {
+    const long long p = v / ncog;
+    const int cog = (int)(v - p * ncog);
+    int wo = (int)(p % g.Wo);
+    long long r = p / g.Wo;
+    const int ho = (int)(r % g.Ho);
+    const int b = (int)(r / g.Ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < g.ntaps; ++t) {
+      const int hi = ho + g.dy[t], wi = wo + g.dx[t];
+      if (hi < 0 || hi >= g.Hi || wi < 0 || wi >= g.Wi) continue;
+      const bf16* xp = x + (((long long)b * g.Hi + hi) * g.Wi + wi) * Cs;
+      const float* wt = ws + (size_t)t * Cs * cot + cog * 8;
+      for (int cs = 0; cs < Cs; ++cs) {
+        const float xv = __bfloat162float(xp[cs]);
+        const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot);
+        const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]);
+        acc[1] = fmaf(xv, w0.y, acc[1]);
+        acc[2] = fmaf(xv, w0.z, acc[2]);
+        acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]);
+        acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]);
+        acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+    const int cbase = co0 + cog * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = act_apply(acc[j] * sc + (bias ? __ldg(bias + cbase + j) : 0.f), g.act);
+    st_stream8(y + p * g.Cout + cbase, pack8(acc));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+// LPP lanes cooperate on one output pixel, each owning 16-byte channel chunks of the wide input.
+template <int CS_MAX>
+__global__ void __launch_bounds__(256) thin_out_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                           const float* __restrict__ bias, const float* __restrict__ scale,
+                                                           bf16* __restrict__ y, const ThinGeom g, long long P, int lpp) {
+  extern __shared__ float ws[];  // [T][Cs][Cin]
+  const int Cs = g.Cout, Cin = g.Cin;
+  for (int i = threadIdx.x; i < g.ntaps * Cs * Cin; i += blockDim.x) ws[i] = __bfloat162float(wp[i]);
+  __syncthreads();
+  const int nchunk = Cin >> 3;
+  const int sub = threadIdx.x % lpp;
+  const long long gpix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lpp;
+  const long long gstride = (long long)gridDim.x * blockDim.x / lpp;
+  const float sc = scale ? __ldg(scale) : 1.f;
+  for (long long p = gpix; p < P + (gstride - P % gstride) % gstride; p += gstride) {  // uniform trip count per warp
+    const bool pv = p < P;
+    long long pp = pv ? p : 0;
+    const int wo = (int)(pp % g.Wo);
+    pp /= g.Wo;
+    const int ho = (int)(pp % g.Ho);
+    const int b = (int)(pp / g.Ho);
+    float acc[CS_MAX];
+#pragma unroll
+    for (int c = 0; c < CS_MAX; ++c) acc[c] = 0.f;
+    if (pv) {
+      for (int t = 0; t < g.ntaps; ++t) {
+        const int hi = ho + g.dy[t], wi = wo + g.dx[t];
+        if (hi < 0 || hi >= g.Hi || wi < 0 || wi >= g.Wi) continue;
+        const bf16* xp = x + (((long long)b * g.Hi + hi) * g.Wi + wi) * Cin;
+        for (int ch = sub; ch < nchunk; ch += lpp) {
+          float xf[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(xp + ch * 8), xf);
+#pragma unroll
+          for (int c = 0; c < CS_MAX; ++c) {
+            if (c < Cs) {
+              const float* wt = ws + ((size_t)t * Cs + c) * Cin + ch * 8;
+              const float4 w0 = *reinterpret_cast<const float4*>(wt);
+              const float4 w1 = *reinterpret_cast<const float4*>(wt + 4);
+              acc[c] += xf[0] * w0.x + xf[1] * w0.y + xf[2] * w0.z + xf[3] * w0.w + xf[4] * w1.x + xf[5] * w1.y +
+                        xf[6] * w1.z + xf[7] * w1.w;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CS_MAX; ++c) {
+      if (c < Cs) {
+        float v = acc[c];
+        for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (pv && sub == 0) y[p * Cs + c] = __float2bfloat16(act_apply(v * sc + (bias ? __ldg(bias + c) : 0.f), g.act));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// wide tensor A [.., Cw] walked pixel by pixel, thin tensor S [.., Cs] sampled at (pixel + sgn*tap).
+// thread = (8-channel chunk of A, one thin channel); acc[T][8] in registers; one atomic per output at the end.
+//   thin_x = 1 : A = dy (Cout wide), S = x (Cin thin), S coord = p + tap,  out[t][cw][cs]
+//   thin_x = 0 : A = x  (Cin wide),  S = dy (Cout thin), S coord = q - tap, out[t][cs][cw]
+template <int TMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict__ A, const bf16* __restrict__ S, float* __restrict__ dwp,
+                                                         int Bn, int HA, int WA, int Cw, int HS, int WS, int Cs, const ThinGeom g,
+                                                         int thin_x, long long pix_per_block) {
+  const int ncw = Cw >> 3;
+  const int tid = threadIdx.x;
+  const int cw = tid % ncw, cs = tid / ncw;
+  const bool active = cs < Cs;
+  const long long PA = (long long)Bn * HA * WA;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(PA, p0 + pix_per_block);
+  float acc[TMAX][8];
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  if (active) {
+    const int sgn = thin_x ? 1 : -1;
+    for (long long p = p0; p < p1; ++p) {
+      const int w = (int)(p % WA);
+      long long r = p / WA;
+      const int h = (int)(r % HA);
+      const int b = (int)(r / HA);
+      float a[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(A + p * Cw + cw * 8), a);
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t) {
+        if (t < g.ntaps) {
+          const int hs = h + sgn * g.dy[t], wss = w + sgn * g.dx[t];
+          if (hs >= 0 && hs < HS && wss >= 0 && wss < WS) {
+            const float sv = __bfloat162float(S[(((long long)b * HS + hs) * WS + wss) * Cs + cs]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], sv, acc[t][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      if (t < g.ntaps) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = cw * 8 + j;
+          const long long o = thin_x ? ((long long)t * Cw + c) * Cs + cs : ((long long)t * Cs + cs) * Cw + c;
+          atomicAdd(dwp + o, acc[t][j]);
+        }
+      }
+    }
+  }
+}
+
+ThinGeom make_thin_geom(const s2e_conv_t* d) {
+  ThinGeom g;
+  g.B = d->B;
+  g.Hi = d->Hi;
+  g.Wi = d->Wi;
+  g.Cin = d->Cin;
+  g.Ho = d->Ho;
+  g.Wo = d->Wo;
+  g.Cout = d->Cout;
+  g.ntaps = d->ntaps;
+  g.act = d->act;
+  for (int i = 0; i < d->ntaps; ++i) {
+    g.dy[i] = d->tap_dy[i];
+    g.dx[i] = d->tap_dx[i];
+  }
+  return g;
+}
+
+}  // namespace
+
+// returns 1 if handled, 0 if the shape is not "thin", < 0 on error
+int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale, void* y,
+                 cudaStream_t stream) {
+  const long long P = (long long)d->B * d->Ho * d->Wo;
+  if (P == 0) return 1;
+  ThinGeom g = make_thin_geom(d);
+  if (d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8) {
+    const int cot = d->Cout < K1_CO_TILE ? d->Cout : K1_CO_TILE;
+    if (d->Cout % K1_CO_TILE != 0 && d->Cout > K1_CO_TILE) return 0;
+    const size_t smem = (size_t)d->ntaps * d->Cin * cot * sizeof(float);
+    if (smem > 200 * 1024) return 0;
+    static bool attr = false;
+    if (!attr) {
+      S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_in_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    long long work = P * (cot / 8);
+    long long gx = (work + 255) / 256;
+    const long long cap = (long long)s2e_num_sms() * 8;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, (unsigned)ceil_div(d->Cout, K1_CO_TILE));
+    thin_in_fwd_kernel<<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, P);
+    S2E_LAUNCH_CHECK();
+    return 1;
+  }
+  if (d->Cout <= 32 && d->Cin % 8 == 0 && d->Cin >= 8) {
+    const size_t smem = (size_t)d->ntaps * d->Cout * d->Cin * sizeof(float);
+    if (smem > 200 * 1024) return 0;
+    int lpp = 1;
+    while (lpp < 32 && lpp * 2 <= d->Cin / 8) lpp *= 2;
+    long long gx = (P * lpp + 255) / 256;
+    const long long cap = (long long)s2e_num_sms() * 8;
+    if (gx > cap) gx = cap;
+    static bool attr = false;
+    if (!attr) {
+      S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    if (d->Cout == 1)
+      thin_out_fwd_kernel<1><<<(unsigned)gx, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, P, lpp);
+    else if (d->Cout <= 8)
+      thin_out_fwd_kernel<8><<<(unsigned)gx, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, P, lpp);
+    else
+      thin_out_fwd_kernel<32><<<(unsigned)gx, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, P, lpp);
+    S2E_LAUNCH_CHECK();
+    return 1;
+  }
+  return 0;
+}
+
+int s2e_thin_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {
+  ThinGeom g = make_thin_geom(d);
+  int thin_x;
+  if (d->Cin <= 32 && d->Cout % 8 == 0 && (d->Cout / 8) * d->Cin <= 512)
+    thin_x = 1;
+  else if (d->Cout <= 32 && d->Cin % 8 == 0 && (d->Cin / 8) * d->Cout <= 512)
+    thin_x = 0;
+  else
+    return 0;
+  if (d->ntaps > 16) return 0;
+  const bf16* A = thin_x ? (const bf16*)dy : (const bf16*)x;
+  const bf16* S = thin_x ? (const bf16*)x : (const bf16*)dy;
+  const int HA = thin_x ? d->Ho : d->Hi, WA = thin_x ? d->Wo : d->Wi, Cw = thin_x ? d->Cout : d->Cin;
+  const int HS = thin_x ? d->Hi : d->Ho, WS = thin_x ? d->Wi : d->Wo, Cs = thin_x ? d->Cin : d->Cout;
+  const long long PA = (long long)d->B * HA * WA;
+  if (PA == 0) return 1;
+  int threads = (Cw / 8) * Cs;
+  threads = ((threads + 31) / 32) * 32;
+  long long blocks = (long long)s2e_num_sms() * (threads <= 128 ? 16 : (threads <= 256 ? 8 : 4));
+  long long ppb = (PA + blocks - 1) / blocks;
+  if (ppb < 64) ppb = 64;
+  blocks = (PA + ppb - 1) / ppb;
+  if (d->ntaps <= 4)
+    thin_wgrad_kernel<4, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb);
+  else if (d->ntaps <= 9)
+    thin_wgrad_kernel<9, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb);
+  else if (threads <= 128)
+    thin_wgrad_kernel<16, 128><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb);
+  else
+    return 0;
+  S2E_LAUNCH_CHECK();
+  return 1;
+}

@@ -481,6 +481,35 @@ __global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* 
     }
   }
 }
+template <int KMAX>
+__global__ void __launch_bounds__(256) linear_bwd_dx_smallk_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                                    const float* __restrict__ w, int N, int K, int act,
+                                                                    float* __restrict__ dx) {
+  __shared__ float red[8][KMAX];
+  const int m = blockIdx.x;
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float g = lin_dpre(dy, y, m * N + n, act);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) acc[k] = fmaf(g, w[(long long)n * K + k], acc[k]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += red[i][threadIdx.x];
+    dx[(long long)m * K + threadIdx.x] = v;
+  }
+}
+
 __global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ y, const void* __restrict__ x, int M, int N,
                                      int K, int act, int hw, float* __restrict__ dw, float* __restrict__ db) {
   GRID_STRIDE(i, (long long)N * K) {
@@ -542,8 +571,16 @@ __global__ void reduce_loss_bwd_kernel(const void* __restrict__ x, const void* _
   }
 }
 
+// state[0] = step count, state[1] = lr, state[2] = lr / (1 - b1^step), state[3] = sqrt(1 - b2^step)
+__global__ void adam_prepare_kernel(float* state, float b1, float b2) {
+  const float step = state[0] + 1.f;
+  state[0] = step;
+  state[2] = state[1] / (1.f - powf(b1, step));
+  state[3] = sqrtf(1.f - powf(b2, step));
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+                            const float* __restrict__ state, float b1, float b2, float eps, float wd) {
+  const float step_size = state[2], bc2_sqrt = state[3];
   GRID_STRIDE(i, n) {
     float gi = g[i];
     if (wd != 0.f) gi = fmaf(wd, p[i], gi);
@@ -552,7 +589,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= (lr / bc1) * (mi / denom);
+    p[i] -= step_size * (mi / denom);
   }
 }
 
@@ -832,7 +869,10 @@ int s2e_linear_bwd(const float* dy, const float* y, const void* x, const float* 
                    int in_nhwc_hw, void* dx, float* dw, float* db, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
-    linear_bwd_dx_kernel<<<grid1d((long long)M * K), NT, 0, st>>>(dy, y, x, w, M, N, K, act, in_nhwc_hw, dx);
+    if (in_nhwc_hw <= 0 && K <= 32 && N >= 256)
+      linear_bwd_dx_smallk_kernel<32><<<M, 256, 0, st>>>(dy, y, w, N, K, act, (float*)dx);
+    else
+      linear_bwd_dx_kernel<<<grid1d((long long)M * K), NT, 0, st>>>(dy, y, x, w, M, N, K, act, in_nhwc_hw, dx);
     S2E_LAUNCH_CHECK();
   }
   if (dw) {
@@ -860,12 +900,15 @@ int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32,
   return S2E_OK;
 }
 
-int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, int step, void* stream) {
+int s2e_adam_prepare(float* state, float beta1, float beta2, void* stream) {
+  adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* state, float beta1, float beta2,
+                  float eps, float weight_decay, void* stream) {
   if (!n) return S2E_OK;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+  adam_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state, beta1, beta2, eps, weight_decay);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

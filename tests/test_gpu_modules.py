@@ -268,6 +268,28 @@ def test_tcgen05_and_simt_paths_agree_on_a_step(ctx):
         assert abs(out[None][0][k] - out[L.IMPL_SIMT][0][k]) <= TOL_LOSS * abs(out[L.IMPL_SIMT][0][k]) + 2e-2, k
 
 
+def test_cuda_graph_steps_match_eager(ctx):
+    """enable_cuda_graphs() must be side-effect free and replayed iterations must equal eager iterations."""
+    eager, graph = _make_trainer(ctx), _make_trainer(ctx)
+    dev = {k: v.cuda() for k, v in ctx.batch.items()}
+    before = {k: v.clone() for k, v in graph.pix2pix_model.netG.state_dict().items()}
+    graph.enable_cuda_graphs(dev, warmup=2)
+    after = graph.pix2pix_model.netG.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before), "graph capture changed the model state"
+    for it in range(2):
+        for tr in (eager, graph):
+            data = {k: v.clone() for k, v in ctx.batch.items()}
+            tr.run_generator_one_step(data)
+            tr.run_discriminator_one_step(data)
+        le, lg = eager.get_latest_losses(), graph.get_latest_losses()
+        for k in le:
+            a, b = float(le[k].reshape(-1)[0]), float(lg[k].reshape(-1)[0])
+            assert abs(a - b) <= (1e-4 if it == 0 else TOL_LOSS) * abs(a) + (1e-5 if it == 0 else 2e-2), (it, k, a, b)
+    assert rel(graph.get_latest_generated(), eager.get_latest_generated()) < TOL_CHAIN
+    nbt = "up_3.norm_0.spade.param_free_norm.num_batches_tracked"
+    assert int(graph.pix2pix_model.netG.state_dict()[nbt]) == int(eager.pix2pix_model.netG.state_dict()[nbt])
+
+
 def test_checkpoint_roundtrip_in_reference_layout(ctx, tmp_path):
     from seg2eye_b200 import util
     tr = _make_trainer(ctx)
