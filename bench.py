@@ -217,6 +217,7 @@ def run_ours(args):
                        "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2"},
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
+            "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
             "execution": ("2 CUDA graphs per iteration (G step, D step); eager ms_per_step %.1f" % ms_eager) if ms_eager else "eager",
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",

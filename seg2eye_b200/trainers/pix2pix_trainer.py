@@ -48,6 +48,17 @@ class Pix2PixTrainer():
             raise RuntimeError("CUDA-graph steps are single-process for now; multi-GPU runs use the eager path")
         dev = self.pix2pix_model.device()
         self.pix2pix_model.train()
+        # autograd graphs of earlier eager steps keep the parameters' AccumulateGrad nodes bound to the legacy stream,
+        # which cannot be joined from a capturing stream: drop every reference to them before warming up
+        if getattr(self, 'g_losses', None) is not None:
+            self.g_losses = {k: v.detach() for k, v in self.g_losses.items()}
+        if getattr(self, 'd_losses', None) is not None:
+            self.d_losses = {k: v.detach() for k, v in self.d_losses.items()}
+        if self.generated is not None:
+            self.generated = self.generated.detach()
+        self.pix2pix_model.reset_loss_log()
+        import gc
+        gc.collect()
         self._static = {'label': example_data['label'].long().to(dev).clone(),
                         'style_image': example_data['style_image'].float().to(dev).clone(),
                         'target': example_data['target'].float().to(dev).clone()}
@@ -89,6 +100,7 @@ class Pix2PixTrainer():
                 self._d_step_body(dict(self._static))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()    # the graphs allocate from a private pool; give the eager cache back first
         self._graph_G, self._graph_D = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         self.optimizer_G.zero_grad(set_to_none=True)
         with torch.cuda.graph(self._graph_G):

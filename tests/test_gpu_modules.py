@@ -284,7 +284,10 @@ def test_cuda_graph_steps_match_eager(ctx):
         le, lg = eager.get_latest_losses(), graph.get_latest_losses()
         for k in le:
             a, b = float(le[k].reshape(-1)[0]), float(lg[k].reshape(-1)[0])
-            assert abs(a - b) <= (1e-4 if it == 0 else TOL_LOSS) * abs(a) + (1e-5 if it == 0 else 2e-2), (it, k, a, b)
+            # iteration 0, G losses: same kernels on the same data.  Everything later sees weights updated through
+            # atomically-accumulated (order-dependent) weight gradients followed by Adam(beta1=0) ~ lr*sign(g)
+            tight = it == 0 and not k.startswith("D/")
+            assert abs(a - b) <= (1e-4 if tight else TOL_LOSS) * abs(a) + (1e-5 if tight else 2e-2), (it, k, a, b)
     assert rel(graph.get_latest_generated(), eager.get_latest_generated()) < TOL_CHAIN
     nbt = "up_3.norm_0.spade.param_free_norm.num_batches_tracked"
     assert int(graph.pix2pix_model.netG.state_dict()[nbt]) == int(eager.pix2pix_model.netG.state_dict()[nbt])
