@@ -154,7 +154,7 @@ def run_ours(args):
     for _ in range(2):
         step(dev)
     launches_per_step = (L.launches - n0) // 2
-    prof = ops.profile_end()
+    prof = ops.profile_end(os.path.join(REPO, 'gpurun_out', 'kernel_profile_%s_b%d.tsv' % (args.res, args.batch)) if os.path.isdir(os.path.join(REPO, 'gpurun_out')) else None)
     barrier()
     ms_eager = None
     if args.mode == "graph" and world == 1:

@@ -345,6 +345,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
 
 // ================================================================================ weight-gradient kernel
 struct WgParams {
+  int swap;  // 0: D[Cout x Cin] = dY^T X ; 1: D[Cin x Cout] = X^T dY (chosen so that the N tile is as wide as possible)
   int Cout, Cin;
   int mt, nt, ksplit;            // tiles over Cout (128), Cin (BN), split-K
   int kt_w, kt_h, kt_b, kt_total;  // pixel tiles
@@ -430,11 +431,14 @@ tapconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
         ptx::mbar_expect_tx(&full[stage], blk_bytes * (2 + BN / 64));
+        const CUtensorMap* mapA = p.swap ? &tmX : &tmDY;
+        const CUtensorMap* mapB = p.swap ? &tmDY : &tmX;
+        const int ax = p.swap ? dx : 0, ay = p.swap ? dy : 0, bx = p.swap ? 0 : dx, by = p.swap ? 0 : dy;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) ptx::tma_load_4d(sa + j * blk_bytes, &tmDY, &full[stage], m0 + j * 64, w0, h0, b0);
+        for (int j = 0; j < 2; ++j) ptx::tma_load_4d(sa + j * blk_bytes, mapA, &full[stage], m0 + j * 64, w0 + ax, h0 + ay, b0);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          ptx::tma_load_4d(sb + j * blk_bytes, &tmX, &full[stage], n0 + j * 64, w0 + dx, h0 + dy, b0);
+          ptx::tma_load_4d(sb + j * blk_bytes, mapB, &full[stage], n0 + j * 64, w0 + bx, h0 + by, b0);
         if (++stage == Cfg::STAGES) {
           stage = 0;
           phase ^= 1;
@@ -471,28 +475,36 @@ tapconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   } else if (nk > 0) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int co = m0 + row;
+    const int mrow = m0 + row;
+    const int Mdim = p.swap ? p.Cin : p.Cout, Ndim = p.swap ? p.Cout : p.Cin;
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
-    float* dst_row = p.dwp + ((size_t)tap * p.Cout + (size_t)(co < p.Cout ? co : 0)) * p.Cin + n0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.Cin) break;  // warp-uniform
+      if (n0 + c0 >= Ndim) break;  // warp-uniform
       uint32_t r[32];
       ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       ptx::tmem_ld_wait();
-      if (co < p.Cout) {
+      if (mrow < Mdim) {
+        if (!p.swap) {
+          float* dst_row = p.dwp + ((size_t)tap * p.Cout + mrow) * p.Cin + n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (n0 + c0 + j + 3 < p.Cin) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + j),
-                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                         "f"(__uint_as_float(r[j + 3]))
-                         : "memory");
-          } else {
-            for (int e = 0; e < 4; ++e)
-              if (n0 + c0 + j + e < p.Cin) atomicAdd(dst_row + c0 + j + e, __uint_as_float(r[j + e]));
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + c0 + j + 3 < Ndim) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + j), "f"(__uint_as_float(r[j])),
+                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                           : "memory");
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (n0 + c0 + j + e < Ndim) atomicAdd(dst_row + j + e, __uint_as_float(r[j + e]));
+            }
           }
+        } else {
+          // accumulator row = input channel (contiguous across the warp's lanes -> coalesced reductions)
+          float* dst = p.dwp + ((size_t)tap * p.Cout + n0 + c0) * p.Cin + mrow;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < Ndim) atomicAdd(dst + (size_t)j * p.Cin, __uint_as_float(r[j]));
         }
       }
     }
@@ -529,7 +541,7 @@ void choose_k_tile(int B, int H, int W, int* tw, int* th, int* tb) {
 }
 
 template <int BN>
-int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {
+int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, int swap, cudaStream_t stream) {
   using Cfg = WgCfg<BN>;
   int tw = d->ktile_w, th = d->ktile_h, tb = d->ktile_b;
   if (tw <= 0 || th <= 0 || tb <= 0) choose_k_tile(d->B, d->Ho, d->Wo, &tw, &th, &tb);
@@ -540,10 +552,11 @@ int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp,
   if ((rc = make_map_nhwc(&tmDY, dy, d->B, d->Ho, d->Wo, d->Cout, tw, th, tb)) != S2E_OK) return rc;
   if ((rc = make_map_nhwc(&tmX, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
   WgParams p;
+  p.swap = swap;
   p.Cout = d->Cout;
   p.Cin = d->Cin;
-  p.mt = ceil_div(d->Cout, 128);
-  p.nt = ceil_div(d->Cin, BN);
+  p.mt = ceil_div(swap ? d->Cin : d->Cout, 128);
+  p.nt = ceil_div(swap ? d->Cout : d->Cin, BN);
   p.kt_w = ceil_div(d->Wo, tw);
   p.kt_h = ceil_div(d->Ho, th);
   p.kt_b = ceil_div(d->B, tb);
@@ -590,7 +603,11 @@ int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const
 int s2e_tapconv_wgrad_tc(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {
   S2E_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0 && d->Cin >= 64 && d->Cout >= 64,
               "tcgen05 wgrad needs Cin,Cout %% 8 == 0 and >= 64 (Cin=%d Cout=%d)", d->Cin, d->Cout);
-  if (d->Cin >= 256) return launch_wgrad<256>(d, x, dy, dwp, stream);
-  if (d->Cin >= 128) return launch_wgrad<128>(d, x, dy, dwp, stream);
-  return launch_wgrad<64>(d, x, dy, dwp, stream);
+  // orientation: the N side of the accumulator should be the wide one (N = 256 halves the shared-memory traffic
+  // per MMA), and a 64-channel side should not occupy the 128-row M side
+  const int swap = (d->Cout > d->Cin) || (d->Cout < 128 && d->Cin >= 128);
+  const int nside = swap ? d->Cout : d->Cin;
+  if (nside >= 256) return launch_wgrad<256>(d, x, dy, dwp, swap, stream);
+  if (nside >= 128) return launch_wgrad<128>(d, x, dy, dwp, swap, stream);
+  return launch_wgrad<64>(d, x, dy, dwp, swap, stream);
 }

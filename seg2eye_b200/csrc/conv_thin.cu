@@ -17,9 +17,13 @@ struct ThinGeom {
 constexpr int K1_CO_TILE = 256;  // couts per block (weights staged in smem as float)
 
 // ------------------------------------------------------------------------------------------------ K1
+// thread = 8 couts x 4 consecutive output pixels of one row: each weight vector read from shared memory feeds four
+// pixels (the kernel is FMA-bound instead of shared-memory-bound); coordinates are decoded once per quad.
+constexpr int K1_PX = 4;
+template <int CS4>  // CS4 = 1: Cin == 4 (one 8-byte load per pixel-tap); 0: generic Cin <= 32
 __global__ void __launch_bounds__(256) thin_in_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, const float* __restrict__ scale,
-                                                          bf16* __restrict__ y, const ThinGeom g, long long P) {
+                                                          bf16* __restrict__ y, const ThinGeom g, int quads_per_row, long long nquads) {
   extern __shared__ float ws[];  // [T][Cs][cot]  (cot = couts of this block)
   const int co0 = blockIdx.y * K1_CO_TILE;
   const int cot = min(K1_CO_TILE, g.Cout - co0);
@@ -31,37 +35,80 @@ __global__ void __launch_bounds__(256) thin_in_fwd_kernel(const bf16* __restrict
   __syncthreads();
   const int ncog = cot >> 3;
   const float sc = scale ? __ldg(scale) : 1.f;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < P * ncog; v += (long long)gridDim.x * blockDim.x) {
-    const long long p = v / ncog;
-    const int cog = (int)(v - p * ncog);
-    int wo = (int)(p % g.Wo);
-    long long r = p / g.Wo;
+  const long long nwork = nquads * ncog;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nwork; v += (long long)gridDim.x * blockDim.x) {
+    const long long q = v / ncog;
+    const int cog = (int)(v - q * ncog);
+    const int qw = (int)(q % quads_per_row);
+    const long long r = q / quads_per_row;
     const int ho = (int)(r % g.Ho);
     const int b = (int)(r / g.Ho);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int wo0 = qw * K1_PX;
+    float acc[K1_PX][8];
+#pragma unroll
+    for (int i = 0; i < K1_PX; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     for (int t = 0; t < g.ntaps; ++t) {
-      const int hi = ho + g.dy[t], wi = wo + g.dx[t];
-      if (hi < 0 || hi >= g.Hi || wi < 0 || wi >= g.Wi) continue;
-      const bf16* xp = x + (((long long)b * g.Hi + hi) * g.Wi + wi) * Cs;
+      const int hi = ho + g.dy[t];
+      if (hi < 0 || hi >= g.Hi) continue;
+      const bf16* xrow = x + ((long long)b * g.Hi + hi) * g.Wi * Cs;
       const float* wt = ws + (size_t)t * Cs * cot + cog * 8;
-      for (int cs = 0; cs < Cs; ++cs) {
-        const float xv = __bfloat162float(xp[cs]);
-        const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot);
-        const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot + 4);
-        acc[0] = fmaf(xv, w0.x, acc[0]);
-        acc[1] = fmaf(xv, w0.y, acc[1]);
-        acc[2] = fmaf(xv, w0.z, acc[2]);
-        acc[3] = fmaf(xv, w0.w, acc[3]);
-        acc[4] = fmaf(xv, w1.x, acc[4]);
-        acc[5] = fmaf(xv, w1.y, acc[5]);
-        acc[6] = fmaf(xv, w1.z, acc[6]);
-        acc[7] = fmaf(xv, w1.w, acc[7]);
+      const int wbase = wo0 + g.dx[t];
+      if (CS4) {
+        float xv[K1_PX][4];
+#pragma unroll
+        for (int i = 0; i < K1_PX; ++i) {
+          const int wi = wbase + i;
+          uint2 raw = make_uint2(0u, 0u);
+          if (wi >= 0 && wi < g.Wi) raw = *reinterpret_cast<const uint2*>(xrow + (long long)wi * 4);
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          xv[i][0] = a.x; xv[i][1] = a.y; xv[i][2] = c.x; xv[i][3] = c.y;
+        }
+#pragma unroll
+        for (int cs = 0; cs < 4; ++cs) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot + 4);
+#pragma unroll
+          for (int i = 0; i < K1_PX; ++i) {
+            const float xx = xv[i][cs];
+            acc[i][0] = fmaf(xx, w0.x, acc[i][0]); acc[i][1] = fmaf(xx, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(xx, w0.z, acc[i][2]); acc[i][3] = fmaf(xx, w0.w, acc[i][3]);
+            acc[i][4] = fmaf(xx, w1.x, acc[i][4]); acc[i][5] = fmaf(xx, w1.y, acc[i][5]);
+            acc[i][6] = fmaf(xx, w1.z, acc[i][6]); acc[i][7] = fmaf(xx, w1.w, acc[i][7]);
+          }
+        }
+      } else {
+        for (int cs = 0; cs < Cs; ++cs) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)cs * cot + 4);
+#pragma unroll
+          for (int i = 0; i < K1_PX; ++i) {
+            const int wi = wbase + i;
+            const float xx = (wi >= 0 && wi < g.Wi) ? __bfloat162float(xrow[(long long)wi * Cs + cs]) : 0.f;
+            acc[i][0] = fmaf(xx, w0.x, acc[i][0]); acc[i][1] = fmaf(xx, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(xx, w0.z, acc[i][2]); acc[i][3] = fmaf(xx, w0.w, acc[i][3]);
+            acc[i][4] = fmaf(xx, w1.x, acc[i][4]); acc[i][5] = fmaf(xx, w1.y, acc[i][5]);
+            acc[i][6] = fmaf(xx, w1.z, acc[i][6]); acc[i][7] = fmaf(xx, w1.w, acc[i][7]);
+          }
+        }
       }
     }
     const int cbase = co0 + cog * 8;
+    float bv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = act_apply(acc[j] * sc + (bias ? __ldg(bias + cbase + j) : 0.f), g.act);
-    st_stream8(y + p * g.Cout + cbase, pack8(acc));
+    for (int j = 0; j < 8; ++j) bv[j] = bias ? __ldg(bias + cbase + j) : 0.f;
+    bf16* yrow = y + (((long long)b * g.Ho + ho) * g.Wo) * g.Cout + cbase;
+#pragma unroll
+    for (int i = 0; i < K1_PX; ++i) {
+      if (wo0 + i < g.Wo) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = act_apply(acc[i][j] * sc + bv[j], g.act);
+        st_stream8(yrow + (long long)(wo0 + i) * g.Cout, pack8(o));
+      }
+    }
   }
 }
 
@@ -145,22 +192,37 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (active) {
     const int sgn = thin_x ? 1 : -1;
-    for (long long p = p0; p < p1; ++p) {
-      const int w = (int)(p % WA);
-      long long r = p / WA;
-      const int h = (int)(r % HA);
-      const int b = (int)(r / HA);
+    int w = (int)(p0 % WA);
+    long long r0 = p0 / WA;
+    int h = (int)(r0 % HA);
+    int b = (int)(r0 / HA);
+    int tdy[TMAX], tdx[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      tdy[t] = t < g.ntaps ? sgn * g.dy[t] : 0;
+      tdx[t] = t < g.ntaps ? sgn * g.dx[t] : 0;
+    }
+    const bf16* ap = A + p0 * Cw + cw * 8;
+    for (long long p = p0; p < p1; ++p, ap += Cw) {
       float a[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(A + p * Cw + cw * 8), a);
+      unpack8(*reinterpret_cast<const bf16x8*>(ap), a);
+      const bf16* sb = S + ((long long)b * HS * WS) * Cs + cs;
 #pragma unroll
       for (int t = 0; t < TMAX; ++t) {
         if (t < g.ntaps) {
-          const int hs = h + sgn * g.dy[t], wss = w + sgn * g.dx[t];
+          const int hs = h + tdy[t], wss = w + tdx[t];
           if (hs >= 0 && hs < HS && wss >= 0 && wss < WS) {
-            const float sv = __bfloat162float(S[(((long long)b * HS + hs) * WS + wss) * Cs + cs]);
+            const float sv = __bfloat162float(sb[((long long)hs * WS + wss) * Cs]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], sv, acc[t][j]);
           }
+        }
+      }
+      if (++w == WA) {
+        w = 0;
+        if (++h == HA) {
+          h = 0;
+          ++b;
         }
       }
     }
@@ -211,15 +273,21 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     if (smem > 200 * 1024) return 0;
     static bool attr = false;
     if (!attr) {
-      S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_in_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_in_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_in_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = true;
     }
-    long long work = P * (cot / 8);
+    const int qpr = ceil_div(d->Wo, K1_PX);
+    const long long nquads = (long long)d->B * d->Ho * qpr;
+    long long work = nquads * (cot / 8);
     long long gx = (work + 255) / 256;
     const long long cap = (long long)s2e_num_sms() * 8;
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, (unsigned)ceil_div(d->Cout, K1_CO_TILE));
-    thin_in_fwd_kernel<<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, P);
+    if (d->Cin == 4)
+      thin_in_fwd_kernel<1><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads);
+    else
+      thin_in_fwd_kernel<0><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads);
     S2E_LAUNCH_CHECK();
     return 1;
   }

@@ -86,30 +86,68 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, do
 }
 
 // ---------------------------------------------------------------- SPADE+Style forward (elementwise, 8 B/elem)
+// grid = (pixel chunks, B).  A thread owns one 8-channel group: its per-channel constants (mean, rstd, style) are
+// loaded once into registers, then it streams pixels: 3 x 16-byte loads + 1 x 16-byte store per pixel, two pixels in
+// flight per iteration.
 __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                              const float* __restrict__ style, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, int HW, int C, long long nvec,
-                                                             int per_sample, int act, bf16* __restrict__ out) {
+                                                             const float* __restrict__ rstd, int HW, int C, int per_sample,
+                                                             int act, bf16* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const long long q0 = (long long)blockIdx.x * chunk;
+  const long long q1 = min((long long)HW, q0 + chunk);
   const int cg = C >> 3;
-  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
-    const long long p = v / cg;
-    const int c = (int)(v - p * cg) * 8;
-    const int b = (int)(p / HW);
-    float xf[8], gf[8], bf[8], o[8];
-    unpack8(ld_stream8(x + p * C + c), xf);
-    unpack8(ld_stream8(gb + p * 2 * C + c), gf);
-    unpack8(ld_stream8(gb + p * 2 * C + C + c), bf);
-    const float* mu = mean + (per_sample ? b * C : 0) + c;
-    const float* rs = rstd + (per_sample ? b * C : 0) + c;
-    const float* s0 = style + (size_t)b * 2 * C + c;
-    const float* s1 = s0 + C;
+  const float* mu_b = mean + (per_sample ? b * C : 0);
+  const float* rs_b = rstd + (per_sample ? b * C : 0);
+  const float* st_b = style + (size_t)b * 2 * C;
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
+    if (my_lane >= lanes) continue;
+    const int c = (cg0 + my_cg) * 8;
+    float k_a[8], k_b[8], k_c[8];  // out = 0.5*( (x*rs - mu*rs)*(1+g) + beta + x*(1+s0) + s1 )
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (xf[j] - __ldg(mu + j)) * __ldg(rs + j);
-      const float r = 0.5f * (fmaf(xh, 1.f + gf[j], bf[j]) + fmaf(xf[j], 1.f + __ldg(s0 + j), __ldg(s1 + j)));
-      o[j] = act_apply(r, act);
+      const float rs = rs_b[c + j];
+      k_a[j] = rs;
+      k_b[j] = -mu_b[c + j] * rs;
+      k_c[j] = 1.f + st_b[c + j];
     }
-    st_stream8(out + p * C + c, pack8(o));
+    float s1v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1v[j] = st_b[C + c + j];
+    const long long base = (long long)b * HW;
+    long long q = q0 + my_lane;
+    for (; q + lanes < q1; q += 2 * lanes) {
+      const long long pA = base + q, pB = base + q + lanes;
+      const bf16x8 xa = ld_stream8(x + pA * C + c), xb = ld_stream8(x + pB * C + c);
+      const bf16x8 ga = ld_stream8(gb + pA * 2 * C + c), gbb = ld_stream8(gb + pB * 2 * C + c);
+      const bf16x8 ba = ld_stream8(gb + pA * 2 * C + C + c), bb = ld_stream8(gb + pB * 2 * C + C + c);
+      float xf[8], gf[8], bf_[8], o[8];
+      unpack8(xa, xf); unpack8(ga, gf); unpack8(ba, bf_);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
+      st_stream8(out + pA * C + c, pack8(o));
+      unpack8(xb, xf); unpack8(gbb, gf); unpack8(bb, bf_);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
+      st_stream8(out + pB * C + c, pack8(o));
+    }
+    for (; q < q1; q += lanes) {
+      const long long pA = base + q;
+      float xf[8], gf[8], bf_[8], o[8];
+      unpack8(ld_stream8(x + pA * C + c), xf);
+      unpack8(ld_stream8(gb + pA * 2 * C + c), gf);
+      unpack8(ld_stream8(gb + pA * 2 * C + C + c), bf_);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
+      st_stream8(out + pA * C + c, pack8(o));
+    }
   }
 }
 
@@ -171,45 +209,60 @@ __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int
   }
 }
 
-// pass 2: dx = rstd*(dxh - m1 - xh*m2) + g*(1+s0) ; dgamma = g*xh ; dbeta = g
+// pass 2: dx = rstd*(dxh - m1 - xh*m2) + g*(1+s0) ; dgamma = g*xh ; dbeta = g     (same thread mapping as the forward)
 __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ outp,
                                                                    const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                                    const float* __restrict__ style, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ m12,
-                                                                   int HW, int C, long long nvec, int per_sample, int act,
+                                                                   int HW, int C, int per_sample, int act,
                                                                    bf16* __restrict__ dx, int dx_acc, bf16* __restrict__ dgb) {
+  const int b = blockIdx.y;
+  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const long long q0 = (long long)blockIdx.x * chunk;
+  const long long q1 = min((long long)HW, q0 + chunk);
   const int cg = C >> 3;
-  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
-    const long long p = v / cg;
-    const int c = (int)(v - p * cg) * 8;
-    const int b = (int)(p / HW);
-    const int so = per_sample ? b * C : 0;
-    float df[8], of[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
-    unpack8(ld_stream8(dout + p * C + c), df);
-    unpack8(ld_stream8(x + p * C + c), xf);
-    unpack8(ld_stream8(gb + p * 2 * C + c), gf);
-    if (act != S2E_ACT_NONE) unpack8(ld_stream8(outp + p * C + c), of);
-    if (dx_acc) unpack8(*reinterpret_cast<const bf16x8*>(dx + p * C + c), prev);
-    const float* m1 = m12 + (per_sample ? (size_t)b * 2 * C : 0) + c;
-    const float* m2 = m1 + C;
-    const float* s0 = style + (size_t)b * 2 * C + c;
+  const int so = per_sample ? b * C : 0;
+  const float* m1p = m12 + (per_sample ? (size_t)b * 2 * C : 0);
+  const float* s0p = style + (size_t)b * 2 * C;
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
+    if (my_lane >= lanes) continue;
+    const int c = (cg0 + my_cg) * 8;
+    float rsd[8], mu[8], m1[8], m2[8], s0[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float g = 0.5f * df[j];
-      if (act == S2E_ACT_LRELU) g *= (of[j] > 0.f ? 1.f : 0.2f);
-      if (act == S2E_ACT_RELU) g *= (of[j] > 0.f ? 1.f : 0.f);
-      const float rsd = __ldg(rstd + so + c + j);
-      const float xh = (xf[j] - __ldg(mean + so + c + j)) * rsd;
-      const float dxh = g * (1.f + gf[j]);
-      float d = rsd * (dxh - __ldg(m1 + j) - xh * __ldg(m2 + j)) + g * (1.f + __ldg(s0 + j));
-      if (dx_acc) d += prev[j];
-      odx[j] = d;
-      odg[j] = g * xh;
-      odb[j] = g;
+      rsd[j] = rstd[so + c + j];
+      mu[j] = mean[so + c + j];
+      m1[j] = m1p[c + j];
+      m2[j] = m1p[C + c + j];
+      s0[j] = 1.f + s0p[c + j];
     }
-    *reinterpret_cast<bf16x8*>(dx + p * C + c) = pack8(odx);
-    st_stream8(dgb + p * 2 * C + c, pack8(odg));
-    st_stream8(dgb + p * 2 * C + C + c, pack8(odb));
+    for (long long q = q0 + my_lane; q < q1; q += lanes) {
+      const long long p = (long long)b * HW + q;
+      float df[8], of[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
+      const bf16x8 vd = ld_stream8(dout + p * C + c), vx = ld_stream8(x + p * C + c), vg = ld_stream8(gb + p * 2 * C + c);
+      if (act != S2E_ACT_NONE) unpack8(ld_stream8(outp + p * C + c), of);
+      if (dx_acc) unpack8(*reinterpret_cast<const bf16x8*>(dx + p * C + c), prev);
+      unpack8(vd, df); unpack8(vx, xf); unpack8(vg, gf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = 0.5f * df[j];
+        if (act == S2E_ACT_LRELU) g *= (of[j] > 0.f ? 1.f : 0.2f);
+        if (act == S2E_ACT_RELU) g *= (of[j] > 0.f ? 1.f : 0.f);
+        const float xh = (xf[j] - mu[j]) * rsd[j];
+        const float dxh = g * (1.f + gf[j]);
+        float d = rsd[j] * (dxh - m1[j] - xh * m2[j]) + g * s0[j];
+        if (dx_acc) d += prev[j];
+        odx[j] = d;
+        odg[j] = g * xh;
+        odb[j] = g;
+      }
+      *reinterpret_cast<bf16x8*>(dx + p * C + c) = pack8(odx);
+      st_stream8(dgb + p * 2 * C + c, pack8(odg));
+      st_stream8(dgb + p * 2 * C + C + c, pack8(odb));
+    }
   }
 }
 
@@ -287,6 +340,16 @@ int ew_grid(long long nvec) {
   const long long cap = (long long)s2e_num_sms() * 16;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
+// pixel chunks per sample for the streaming elementwise kernels: ~16 resident blocks per SM in total, and at least
+// 8 pixels per pixel-lane so the per-thread constant setup is amortised
+int ew_chunks(int HW, int B, int C) {
+  const int ncg = (C >> 3) < NT ? (C >> 3) : NT;
+  const int lanes = NT / ncg;
+  long long want = ((long long)s2e_num_sms() * 16 + B - 1) / B;
+  long long maxc = ((long long)HW + 8LL * lanes - 1) / (8LL * lanes);
+  if (want > maxc) want = maxc;
+  return (int)(want < 1 ? 1 : want);
+}
 int red_chunks(long long pixels, int G) {
   // aim for ~4 blocks per SM overall, at least 64 pixels per block
   long long want = ((long long)s2e_num_sms() * 4 + G - 1) / G;
@@ -327,10 +390,10 @@ int s2e_norm_finalize(const double* acc, int G, int C, double count, float eps, 
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd, int B,
                         int HW, int C, int per_sample, int act, void* out, void* stream) {
   S2E_REQUIRE(C % 8 == 0, "spade_style_fwd needs C %% 8 == 0 (C=%d)", C);
-  const long long nvec = (long long)B * HW * (C >> 3);
-  if (nvec == 0) return S2E_OK;
-  spade_style_fwd_kernel<<<ew_grid(nvec), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gb, style, mean, rstd, HW,
-                                                                          C, nvec, per_sample, act, (bf16*)out);
+  if ((long long)B * HW == 0) return S2E_OK;
+  dim3 grid(ew_chunks(HW, B, C), B);
+  spade_style_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gb, style, mean, rstd, HW, C,
+                                                                 per_sample, act, (bf16*)out);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -350,10 +413,10 @@ int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const 
   const double count = per_sample ? (double)HW : (double)B * HW;
   spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, m12, dstyle);
   S2E_LAUNCH_CHECK();
-  const long long nvec = (long long)B * HW * (C >> 3);
-  spade_style_bwd_apply_kernel<<<ew_grid(nvec), NT, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x,
-                                                             (const bf16*)gb, style, mean, rstd, m12, HW, C, nvec, per_sample,
-                                                             act, (bf16*)dx, dx_accumulate, (bf16*)dgb);
+  dim3 grid2(ew_chunks(HW, B, C), B);
+  spade_style_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x, (const bf16*)gb, style,
+                                                     mean, rstd, m12, HW, C, per_sample, act, (bf16*)dx, dx_accumulate,
+                                                     (bf16*)dgb);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

@@ -62,24 +62,38 @@ def profile_begin():
     _prof = {"tc": [], "norm": []}
 
 
-def profile_end():
+def profile_end(dump_path=None):
     global _prof
     p, _prof = _prof, None
     torch.cuda.synchronize()
+    if dump_path:
+        agg = {}
+        for kind in p:
+            for a, b, w, tag in p[kind]:
+                e = agg.setdefault((kind, tag), [0, 0.0, 0.0])
+                e[0] += 1
+                e[1] += a.elapsed_time(b)
+                e[2] += w
+        with open(dump_path, "w") as f:
+            f.write("kind\ttag\tlaunches\tms_total\twork\trate(TFLOP/s|GB/s)\n")
+            for (kind, tag), (n, ms, w) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                rate = (w / 1e12 if kind == "tc" else w / 1e9) / (ms / 1e3) if ms > 0 else 0
+                f.write("%s\t%s\t%d\t%.3f\t%.4g\t%.1f\n" % (kind, tag, n, ms, w, rate))
+    p = {k: [(a, b, w) for a, b, w, _ in v] for k, v in p.items()}
     out = {"tc_ms": sum(a.elapsed_time(b) for a, b, _ in p["tc"]), "tc_flop": float(sum(w for _, _, w in p["tc"])),
            "tc_n": len(p["tc"]), "norm_ms": sum(a.elapsed_time(b) for a, b, _ in p["norm"]),
            "norm_bytes": float(sum(w for _, _, w in p["norm"])), "norm_n": len(p["norm"])}
     return out
 
 
-def _timed_call(kind, work, name, *args):
+def _timed_call(kind, work, name, *args, tag=""):
     if _prof is None:
         return L.call(name, *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     L.call(name, *args)
     e1.record()
-    _prof[kind].append((e0, e1, work))
+    _prof[kind].append((e0, e1, work, tag))
 
 
 def _pick(tc_ok):
@@ -189,7 +203,8 @@ class TapConvFn(torch.autograd.Function):
         impl = _pick(Cinp % 64 == 0 and Cout % 8 == 0)
         flops = 2.0 * B * Ho * Wo * Cout * Cin * cfg.kh * cfg.kw
         if impl == L.IMPL_TC:
-            _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream())
+            _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream(),
+                        tag="fwd B%d %dx%d Cin%d Cout%d T%d" % (B, Ho, Wo, Cinp, Cout, len(taps)))
         else:
             L.call("s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream())
         ctx.flops = flops
@@ -223,7 +238,8 @@ class TapConvFn(torch.autograd.Function):
             dxs = torch.empty(B, His, Wis, Cinp, dtype=BF16, device=dy.device)
             impl = _pick(Cout % 64 == 0 and Cinp % 8 == 0)
             if impl == L.IMPL_TC:
-                _timed_call("tc", ctx.flops, "s2e_tapconv_fwd", dd, L.ptr(dpre), L.ptr(wpt), None, L.ptr(inv_sigma), L.ptr(dxs), impl, st)
+                _timed_call("tc", ctx.flops, "s2e_tapconv_fwd", dd, L.ptr(dpre), L.ptr(wpt), None, L.ptr(inv_sigma), L.ptr(dxs), impl, st,
+                            tag="dgrad B%d %dx%d Cin%d Cout%d T%d" % (B, His, Wis, Cout, Cinp, len(taps)))
             else:
                 L.call("s2e_tapconv_fwd", dd, L.ptr(dpre), L.ptr(wpt), None, L.ptr(inv_sigma), L.ptr(dxs), impl, st)
             if cfg.stride == 2:
@@ -240,7 +256,8 @@ class TapConvFn(torch.autograd.Function):
             d = _desc(B, His, Wis, Cinp, Ho, Wo, Cout, taps, L.ACT_NONE)
             impl = _pick(Cinp >= 64 and Cout >= 64 and Cinp % 8 == 0 and Cout % 8 == 0)
             if impl == L.IMPL_TC:
-                _timed_call("tc", ctx.flops, "s2e_tapconv_wgrad", d, L.ptr(xs), L.ptr(dpre), L.ptr(dwp), impl, st)
+                _timed_call("tc", ctx.flops, "s2e_tapconv_wgrad", d, L.ptr(xs), L.ptr(dpre), L.ptr(dwp), impl, st,
+                            tag="wgrad B%d %dx%d Cin%d Cout%d T%d" % (B, Ho, Wo, Cinp, Cout, len(taps)))
             else:
                 L.call("s2e_tapconv_wgrad", d, L.ptr(xs), L.ptr(dpre), L.ptr(dwp), impl, st)
             dot = torch.empty(1, dtype=F32, device=dy.device) if sn is not None else None
@@ -311,7 +328,7 @@ class SpadeStyleFn(torch.autograd.Function):
             rstd = torch.rsqrt(running_var.detach() + cfg.eps).view(1, Cc)
         out = torch.empty_like(x)
         _timed_call("norm", 8.0 * B * H * W * Cc, "s2e_spade_style_fwd", L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
-                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(out), st)
+                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(out), st, tag="B%d HW%d C%d" % (B, H * W, Cc))
         ctx.cfg, ctx.batch_stats = cfg, batch_stats
         ctx.save_for_backward(x, gb, style, mean, rstd, out)
         return out

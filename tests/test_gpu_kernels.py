@@ -142,6 +142,9 @@ TC_CASES = [
     (2, 64, 128, 11, 9, 4, 1, 2, 0),       # D 4x4 s1 p2: output larger than input
     (2, 64, 128, 32, 32, 3, 2, 1, 0),      # E 3x3 s2 p1
     (1, 64, 72, 16, 8, 3, 1, 1, 1),        # Cout not a multiple of 64, fused LeakyReLU
+    (2, 128, 512, 16, 16, 3, 1, 1, 0),     # wgrad orientation swapped (Cout > Cin): accumulator [Cin x Cout], N = 256
+    (2, 128, 64, 24, 16, 3, 1, 1, 0),      # wgrad swapped because Cout < 128 <= Cin
+    (2, 64, 64, 24, 16, 3, 1, 1, 0),
 ]
 
 
