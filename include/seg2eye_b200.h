@@ -97,7 +97,8 @@ int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int st
                      int co_offset, const float* w_orig, const float* u, const float* v, const float* inv_sigma,
                      float* dot, float* dw_oihw, int accumulate, void* stream);
 /* torch.nn.utils.spectral_norm power iteration (one step) on W viewed as (rows, cols):
- * v <- normalize(W^T u), u <- normalize(W v), inv_sigma <- 1 / (u . W v); eps 1e-12. scratch: rows+cols floats.
+ * v <- normalize(W^T u), u <- normalize(W v), inv_sigma <- 1 / (u . W v); eps 1e-12. scratch: rows + cols + ceil(rows/64)*cols floats
+ * (fixed-order partial sums: the iteration is bitwise reproducible).
  * update = 0 (module in eval mode): u, v are left untouched and only inv_sigma is produced. */
 int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
                             int update, void* stream);

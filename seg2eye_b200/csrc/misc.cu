@@ -197,26 +197,32 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, PackGeom g, c
 }
 
 // ------------------------------------------------------------------------------------------ spectral norm
-// t[c] += sum_{r in chunk} W[r][c] u[r]      grid (col blocks, row chunks)
-__global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows, int cols, int rchunk, float* t) {
+// part[chunk][c] = sum_{r in chunk} W[r][c] u[r]      grid (col blocks, row chunks); partials are summed in a fixed
+// order by the normalise kernel, so the power iteration is bitwise reproducible (no floating-point atomics)
+__global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows, int cols, int rchunk, float* part) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const int r0 = blockIdx.y * rchunk, r1 = min(rows, r0 + rchunk);
   float acc = 0.f;
   for (int r = r0; r < r1; ++r) acc = fmaf(w[(long long)r * cols + c], u[r], acc);
-  atomicAdd(t + c, acc);
+  part[(long long)blockIdx.y * cols + c] = acc;
 }
-// x <- x / max(||x||, eps) ; single block.  If sigma_out: also *sigma_out = 1 / dot(x_normalized, x_raw)
-__global__ void sn_normalize_kernel(const float* __restrict__ raw, int n, float* __restrict__ outv, float* inv_sigma) {
+// x = sum_k raw[k][:] ; x <- x / max(||x||, eps) ; single block.  If inv_sigma: *inv_sigma = 1 / dot(x_normalized, x)
+__global__ void sn_normalize_kernel(const float* __restrict__ raw, int nparts, int n, float* __restrict__ outv, float* inv_sigma) {
   float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(raw[i], raw[i], acc);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = 0.f;
+    for (int k = 0; k < nparts; ++k) v += raw[(long long)k * n + i];
+    outv[i] = v;  // staged un-normalised; rescaled below by the same thread
+    acc = fmaf(v, v, acc);
+  }
   __shared__ float s_norm;
   acc = block_sum(acc);
   if (threadIdx.x == 0) s_norm = acc;
   __syncthreads();
   const float nsq = s_norm;
   const float denom = fmaxf(sqrtf(nsq), 1e-12f);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) outv[i] = raw[i] / denom;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) outv[i] = outv[i] / denom;
   if (inv_sigma && threadIdx.x == 0) *inv_sigma = 1.f / (nsq / denom);  // sigma = u . (W v) = ||Wv||^2 / max(||Wv||,eps)
 }
 // inv_sigma = 1 / (u . s)  (evaluation mode: no buffer update) ; single block
@@ -729,16 +735,18 @@ int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float*
     S2E_LAUNCH_CHECK();
     return S2E_OK;
   }
-  S2E_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, st));
   const int rchunk = 64;
-  dim3 g1(ceil_div(cols, 128), ceil_div(rows, rchunk));
-  sn_wt_u_kernel<<<g1, 128, 0, st>>>(w, u, rows, cols, rchunk, t);
+  const int nparts = ceil_div(rows, rchunk);
+  float* part = scratch + cols + rows;  // nparts * cols
+  (void)t;
+  dim3 g1(ceil_div(cols, 128), nparts);
+  sn_wt_u_kernel<<<g1, 128, 0, st>>>(w, u, rows, cols, rchunk, part);
   S2E_LAUNCH_CHECK();
-  sn_normalize_kernel<<<1, 1024, 0, st>>>(t, cols, v, nullptr);
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(part, nparts, cols, v, nullptr);
   S2E_LAUNCH_CHECK();
   sn_w_v_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(w, v, rows, cols, s);
   S2E_LAUNCH_CHECK();
-  sn_normalize_kernel<<<1, 1024, 0, st>>>(s, rows, u, inv_sigma);
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(s, 1, rows, u, inv_sigma);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

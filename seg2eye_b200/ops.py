@@ -292,7 +292,7 @@ def spectral_inv_sigma(weight_orig, u, v, training):
     rows = w.shape[0]
     cols = w.numel() // rows
     inv = torch.empty(1, dtype=F32, device=w.device)
-    scratch = torch.empty(rows + cols, dtype=F32, device=w.device)
+    scratch = torch.empty(rows + cols + ((rows + 63) // 64) * cols, dtype=F32, device=w.device)
     L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv), L.ptr(scratch),
            1 if training else 0, L.stream())
     return inv
