@@ -156,6 +156,12 @@ def run_ours(args):
     launches_per_step = (L.launches - n0) // 2
     prof = ops.profile_end(os.path.join(REPO, 'gpurun_out', 'kernel_profile_%s_b%d.tsv' % (args.res, args.batch)) if os.path.isdir(os.path.join(REPO, 'gpurun_out')) else None)
     barrier()
+    if args.ncu_step:   # one eager step delimited by cudaProfilerStart/Stop (ncu --profile-from-start off)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     ms_eager = None
     if args.mode == "graph" and world == 1:
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -247,6 +253,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="graph", choices=("graph", "eager"))
+    ap.add_argument("--ncu-step", action="store_true", help="bracket one eager step with cudaProfilerStart/Stop")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
 

@@ -51,6 +51,14 @@ int s2e_onehot_nchw(const int64_t* label, int B, int H, int W, int nc, float* ou
 int s2e_seg_nearest_nhwc(const float* seg_nchw, int B, int C, int Hs, int Ws, int Hd, int Wd, int Cpad,
                          void* out_nhwc_bf16, void* stream);
 
+/* nearest-resize + 3x3 im2col (zero padded) of a thin map (9*C <= 64) into 64 bf16 channels per pixel, channel
+ * (r*3+s)*C + c.  SPADE's mlp_shared (normalization.py:85-88,98) then runs as a K=64 GEMM on the tensor-core kernels;
+ * the matching weight layouts are [Cout][64] (pack) and its adjoint (unpack of the fp32 weight gradient). */
+int s2e_seg_im2col3x3(const float* seg_nchw, int B, int C, int Hs, int Ws, int Hd, int Wd, void* out_nhwc64_bf16,
+                      void* stream);
+int s2e_pack_weight_im2col3x3(const float* w_oihw, int Cout, int C, void* out_bf16, void* stream);
+int s2e_unpack_wgrad_im2col3x3(const float* dwp, int Cout, int C, float* dw_oihw, void* stream);
+
 /* layout / precision boundary of the module API (NCHW fp32 <-> NHWC bf16) */
 int s2e_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* y, void* stream);
 int s2e_nhwc_bf16_to_nchw_f32(const void* x, int B, int C, int H, int W, float* y, void* stream);

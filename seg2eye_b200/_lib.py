@@ -29,6 +29,9 @@ _SIGS = {
     "s2e_debug_set": [_I, _I],
     "s2e_onehot_nchw": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_seg_nearest_nhwc": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "s2e_seg_im2col3x3": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "s2e_pack_weight_im2col3x3": [_P, _I, _I, _P, _P],
+    "s2e_unpack_wgrad_im2col3x3": [_P, _I, _I, _P, _P],
     "s2e_nchw_f32_to_nhwc_bf16": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_nhwc_bf16_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_tapconv_fwd": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _I, _P],

@@ -85,6 +85,57 @@ __global__ void seg_nearest_kernel(const float* __restrict__ seg, int C, int Hs,
   }
 }
 
+// nearest resize + 3x3 im2col of a thin NCHW fp32 map into 64 bf16 channels per pixel: channel (r*3+s)*C + c holds
+// seg[b][c][src(h+r-1)][src(w+s-1)] (zero outside the resized map and for channels >= 9*C).
+__global__ void seg_im2col_kernel(const float* __restrict__ seg, int C, int Hs, int Ws, int Hd, int Wd, float sh, float sw,
+                                  long long n, bf16* __restrict__ out) {
+  GRID_STRIDE(i, n) {  // one thread per (pixel, 8-channel chunk)
+    const int ch = (int)(i & 7);
+    long long p = i >> 3;
+    const int wd = (int)(p % Wd);
+    p /= Wd;
+    const int hd = (int)(p % Hd);
+    const int b = (int)(p / Hd);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ch * 8 + j;
+      float val = 0.f;
+      if (k < 9 * C) {
+        const int t = k / C, c = k - t * C;
+        const int h = hd + t / 3 - 1, w = wd + t % 3 - 1;
+        if (h >= 0 && h < Hd && w >= 0 && w < Wd) {
+          const int hs = min((int)floorf(h * sh), Hs - 1);
+          const int ws = min((int)floorf(w * sw), Ws - 1);
+          val = seg[(((long long)b * C + c) * Hs + hs) * Ws + ws];
+        }
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(v);
+  }
+}
+// OIHW (Cout, C, 3, 3) fp32 -> bf16 [Cout][64] with k = (r*3+s)*C + c   (and the adjoint for the weight gradient)
+__global__ void pack_im2col_kernel(const float* __restrict__ w, int Cout, int C, bf16* __restrict__ out) {
+  GRID_STRIDE(i, (long long)Cout * 64) {
+    const int k = (int)(i & 63), co = (int)(i >> 6);
+    float v = 0.f;
+    if (k < 9 * C) {
+      const int t = k / C, c = k - t * C;
+      v = w[((long long)co * C + c) * 9 + t];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+__global__ void unpack_im2col_kernel(const float* __restrict__ dwp, int Cout, int C, float* __restrict__ dw) {
+  GRID_STRIDE(i, (long long)Cout * C * 9) {
+    const int t = (int)(i % 9);
+    const long long r = i / 9;
+    const int c = (int)(r % C), co = (int)(r / C);
+    dw[i] = dwp[(long long)co * 64 + t * C + c];
+  }
+}
+
 __global__ void nchw2nhwc_kernel(const float* __restrict__ x, int C, int H, int W, long long n, bf16* __restrict__ y) {
   GRID_STRIDE(i, n) {
     const int c = (int)(i % C);
@@ -654,6 +705,26 @@ int s2e_seg_nearest_nhwc(const float* seg, int B, int C, int Hs, int Ws, int Hd,
   if (!n) return S2E_OK;
   const float sh = (float)Hs / (float)Hd, sw = (float)Ws / (float)Wd;
   seg_nearest_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(seg, C, Hs, Ws, Hd, Wd, Cpad, sh, sw, n, (bf16*)out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_seg_im2col3x3(const float* seg, int B, int C, int Hs, int Ws, int Hd, int Wd, void* out, void* stream) {
+  S2E_REQUIRE(9 * C <= 64, "seg_im2col3x3: 9*C must fit 64 channels (C=%d)", C);
+  const long long n = (long long)B * Hd * Wd * 8;
+  if (!n) return S2E_OK;
+  seg_im2col_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(seg, C, Hs, Ws, Hd, Wd, (float)Hs / (float)Hd, (float)Ws / (float)Wd,
+                                                                n, (bf16*)out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_pack_weight_im2col3x3(const float* w, int Cout, int C, void* out, void* stream) {
+  S2E_REQUIRE(9 * C <= 64, "pack_weight_im2col3x3: 9*C must fit 64 channels");
+  pack_im2col_kernel<<<grid1d((long long)Cout * 64), NT, 0, (cudaStream_t)stream>>>(w, Cout, C, (bf16*)out);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_unpack_wgrad_im2col3x3(const float* dwp, int Cout, int C, float* dw, void* stream) {
+  unpack_im2col_kernel<<<grid1d((long long)Cout * C * 9), NT, 0, (cudaStream_t)stream>>>(dwp, Cout, C, dw);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

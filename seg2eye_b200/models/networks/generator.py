@@ -51,6 +51,8 @@ class SPADESTYLEGenerator(BaseNetwork):
         return ops.Upsample2xFn.apply(x)
 
     def forward(self, input, w=None):
+        from .normalization import clear_seg_cache
+        clear_seg_cache()   # im2col'd segmaps are shared by the SPADE blocks of one forward only
         seg = input
         x = self.fc.forward_nhwc(ops.seg_nearest(seg, self.sh, self.sw))
         x = self.head_0.forward_nhwc(x, seg, w)
@@ -71,6 +73,7 @@ class SPADESTYLEGenerator(BaseNetwork):
             x = self.up(x)
             x = self.up_4.forward_nhwc(x, seg, w)
         x = self.conv_img.forward_nhwc(ops.ActFn.apply(x, L.ACT_LRELU))
+        clear_seg_cache()
         if self.opt.output_nc == 1:
             return ops.TanhFn.apply(x)
         raise ValueError('output_nc != 1 is not supported by the B200 path (OpenEDS images are single channel)')

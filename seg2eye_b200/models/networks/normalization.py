@@ -33,6 +33,26 @@ def get_nonspade_norm_layer(opt, norm_type='instance'):
     return add_norm_layer
 
 
+_col_cache = {"key": None, "cols": {}}
+
+
+def seg_im2col_cached(segmap, h, w):
+    """im2col of `segmap` at (h, w), memoised for as long as the same segmap tensor object (and version) is in use."""
+    key = (id(segmap), segmap._version, segmap.data_ptr(), tuple(segmap.shape))
+    if _col_cache["key"] != key or (_col_cache.get("ref") is None or _col_cache["ref"]() is not segmap):
+        import weakref
+        _col_cache["key"], _col_cache["cols"] = key, {}
+        _col_cache["ref"] = weakref.ref(segmap)
+    cols = _col_cache["cols"]
+    if (h, w) not in cols:
+        cols[(h, w)] = ops.seg_im2col(segmap, h, w)
+    return cols[(h, w)]
+
+
+def clear_seg_cache():
+    _col_cache["key"], _col_cache["cols"] = None, {}
+
+
 class FC(nn.Module):
     """normalization.py:108-141 (StyleGAN dense layer + LeakyReLU(0.2))."""
 
@@ -107,8 +127,14 @@ class SPADE(nn.Module):
         self.norm_nc = norm_nc
 
     def gamma_beta(self, segmap, h, w):
-        seg = ops.seg_nearest(segmap, h, w)
-        actv = self.mlp_shared[0].forward_nhwc(seg)
+        conv = self.mlp_shared[0]
+        if 9 * conv.in_channels <= 64 and conv.cfg.kh == 3:
+            # thin segmap: its 64-channel im2col (shared by every SPADE of this resolution within one generator
+            # forward) turns mlp_shared into a K=64 GEMM on the tensor-core path, forward and weight gradient
+            col = seg_im2col_cached(segmap, h, w)
+            actv = ops.SegConvFn.apply(col, conv.weight, conv.bias, L.ACT_RELU)
+        else:
+            actv = conv.forward_nhwc(ops.seg_nearest(segmap, h, w))
         return ops.tap_conv(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
                             (self.mlp_gamma.bias, self.mlp_beta.bias))
 

@@ -546,6 +546,79 @@ def seg_nearest(seg, hd, wd):
     return out
 
 
+def seg_im2col(seg, hd, wd):
+    """Nearest-resize + 3x3 im2col of the segmap to (B,hd,wd,64) bf16 (see s2e_seg_im2col3x3)."""
+    seg = _c(seg.detach().float())
+    B, Cc, Hs, Ws = seg.shape
+    out = torch.empty(B, hd, wd, 64, dtype=BF16, device=seg.device)
+    L.call("s2e_seg_im2col3x3", L.ptr(seg), B, Cc, Hs, Ws, hd, wd, L.ptr(out), L.stream())
+    return out
+
+
+_pack_im2col_cache = {}
+
+
+class SegConvFn(torch.autograd.Function):
+    """act(conv3x3(seg, W) + b) for a thin segmap given as its 64-channel im2col: one K=64 GEMM on the tcgen05
+    kernels, forward and weight gradient (the segmap itself needs no gradient)."""
+
+    @staticmethod
+    def forward(ctx, col, weight, bias, act):
+        import weakref
+        B, H, W, K = col.shape
+        Cout, Cs = weight.shape[0], weight.shape[1]
+        assert K == 64 and weight.shape[2:] == (3, 3) and 9 * Cs <= 64
+        ver = (weight._version, weight.data_ptr(), _state["weights_epoch"])
+        hit = _pack_im2col_cache.get(id(weight))
+        if hit is not None and hit[0]() is weight and hit[1] == ver:
+            wp = hit[2]
+        else:
+            wp = hit[2] if (hit is not None and hit[0]() is weight) else torch.empty(Cout * 64, dtype=BF16, device=col.device)
+            L.call("s2e_pack_weight_im2col3x3", L.ptr(weight.detach()), Cout, Cs, L.ptr(wp), L.stream())
+            _pack_im2col_cache[id(weight)] = (weakref.ref(weight), ver, wp)
+        y = torch.empty(B, H, W, Cout, dtype=BF16, device=col.device)
+        d = _desc(B, H, W, 64, H, W, Cout, [(0, 0)], act)
+        flops = 2.0 * B * H * W * Cout * Cs * 9
+        impl = _pick(Cout % 8 == 0)
+        if impl == L.IMPL_TC:
+            _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(col), L.ptr(wp), L.ptr(bias.detach()) if bias is not None else None,
+                        None, L.ptr(y), impl, L.stream(), tag="fwd-seg B%d %dx%d Cin64 Cout%d T1" % (B, H, W, Cout))
+        else:
+            L.call("s2e_tapconv_fwd", d, L.ptr(col), L.ptr(wp), L.ptr(bias.detach()) if bias is not None else None, None,
+                   L.ptr(y), impl, L.stream())
+        ctx.act, ctx.flops, ctx.cs, ctx.has_b = act, flops, Cs, bias is not None
+        ctx.skip_wgrad = _state["skip_wgrad"]
+        ctx.save_for_backward(col, y, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        col, y, weight = ctx.saved_tensors
+        dy = _c(dy)
+        B, H, W, Cout = dy.shape
+        st = L.stream()
+        if ctx.act != L.ACT_NONE:
+            dpre = torch.empty_like(dy)
+            L.call("s2e_act_bwd", L.ptr(dy), L.ptr(y), dy.numel(), ctx.act, L.ptr(dpre), st)
+        else:
+            dpre = dy
+        gw = gb = None
+        if ctx.needs_input_grad[1] and not ctx.skip_wgrad:
+            dwp = torch.zeros(Cout * 64, dtype=F32, device=dy.device)
+            d = _desc(B, H, W, 64, H, W, Cout, [(0, 0)], L.ACT_NONE)
+            impl = _pick(Cout >= 64 and Cout % 8 == 0)
+            if impl == L.IMPL_TC:
+                _timed_call("tc", ctx.flops, "s2e_tapconv_wgrad", d, L.ptr(col), L.ptr(dpre), L.ptr(dwp), impl, st,
+                            tag="wgrad-seg B%d %dx%d Cin64 Cout%d T1" % (B, H, W, Cout))
+            else:
+                L.call("s2e_tapconv_wgrad", d, L.ptr(col), L.ptr(dpre), L.ptr(dwp), impl, st)
+            gw = torch.empty_like(weight)
+            L.call("s2e_unpack_wgrad_im2col3x3", L.ptr(dwp), Cout, ctx.cs, L.ptr(gw), st)
+        if ctx.has_b and ctx.needs_input_grad[2] and not ctx.skip_wgrad:
+            gb = channel_sums(dpre, B, H * W, Cout) if Cout % 8 == 0 else dpre.float().sum(dim=(0, 1, 2))
+        return None, gw, gb, None
+
+
 class MakeDInputFn(torch.autograd.Function):
     """cat([cat([seg,fake],1), cat([seg,real],1)], 0) as (2B,H,W,nc+1) bf16 (pix2pix_model.py:328-338)."""
 

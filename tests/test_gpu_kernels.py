@@ -161,6 +161,32 @@ def test_conv_tcgen05_fused_gamma_beta_and_spectral(S):
     conv_case(S, L.IMPL_SIMT, 2, 16, 24, 12, 10, 4, 2, 2, 0, sn=True, bias=False)
 
 
+@pytest.mark.parametrize("impl_name", ["tc", "simt"])
+def test_seg_im2col_conv_matches_conv3x3(S, impl_name):
+    """SPADE's mlp_shared on the 64-channel im2col of the (nearest-resized) segmap == ReLU(conv3x3(seg))."""
+    L, ops = S
+    g = torch.Generator().manual_seed(9)
+    B, C, Hs, Ws, hd, wd, Cout = 2, 4, 40, 32, 20, 16, 128
+    seg = F.one_hot(torch.randint(0, C, (B, Hs, Ws), generator=g), C).permute(0, 3, 1, 2).float()
+    w = bf(torch.randn(Cout, C, 3, 3, generator=g) / 6.0)
+    b = torch.randn(Cout, generator=g) * 0.1
+    segr = F.interpolate(seg, size=(hd, wd), mode="nearest")
+    wr, br = w.clone().requires_grad_(), b.clone().requires_grad_()
+    yr = F.relu(F.conv2d(segr, wr, br, padding=1))
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    col = ops.seg_im2col(seg.cuda(), hd, wd)
+    # bit-exact im2col: channel (r*3+s)*C + c
+    ref_col = F.unfold(segr, 3, padding=1).view(B, C, 9, hd, wd).permute(0, 3, 4, 2, 1).reshape(B, hd, wd, 9 * C)
+    assert torch.equal(col[..., :9 * C].float().cpu(), ref_col) and float(col[..., 9 * C:].abs().max()) == 0.0
+    wc, bc = w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    with ops.force_impl(L.IMPL_TC if impl_name == "tc" else L.IMPL_SIMT):
+        y = ops.SegConvFn.apply(col, wc, bc, L.ACT_RELU)
+        y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < TOL_ACT
+    assert rel(wc.grad, wr.grad) < TOL_ACT and rel(bc.grad, br.grad) < TOL_ACT
+
+
 def test_conv_tcgen05_large_k_many_tiles(S):
     L, ops = S
     conv_case(S, L.IMPL_TC, 4, 512, 512, 20, 16, 3, 1, 1, 0, seed=3)         # K = 4608, persistent loop > 1 tile/CTA
