@@ -84,6 +84,8 @@ typedef struct {
   int act;
   int tile_w, tile_h, tile_b; /* TC forward tile (<=128 px); 0 = choose inside */
   int ktile_w, ktile_h, ktile_b; /* TC wgrad pixel tile (multiple of 16, <=64 px); 0 = choose inside */
+  const void* relu_mask;         /* optional bf16 tensor shaped like y: y is zeroed where mask <= 0 (fused ReLU backward
+                                    when the operator computes the data gradient of a layer whose input came from a ReLU) */
 } s2e_conv_t;
 
 int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,

@@ -20,7 +20,7 @@ class ConvDesc(C.Structure):
                 ("Ho", C.c_int), ("Wo", C.c_int), ("Cout", C.c_int), ("ntaps", C.c_int),
                 ("tap_dy", C.c_int * MAX_TAPS), ("tap_dx", C.c_int * MAX_TAPS), ("act", C.c_int),
                 ("tile_w", C.c_int), ("tile_h", C.c_int), ("tile_b", C.c_int),
-                ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int)]
+                ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p)]
 
 
 _P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double

@@ -14,7 +14,7 @@ struct Geom {
 template <int TN>
 __global__ void __launch_bounds__(256) simt_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                        const float* __restrict__ bias, const float* __restrict__ scale,
-                                                       bf16* __restrict__ y, const Geom g) {
+                                                       bf16* __restrict__ y, const Geom g, const bf16* __restrict__ mask) {
   constexpr int BNT = 16 * TN;
   __shared__ float As[16][64 + 1];
   __shared__ float Bs[16][BNT + 1];
@@ -86,8 +86,9 @@ __global__ void __launch_bounds__(256) simt_fwd_kernel(const bf16* __restrict__ 
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx + 16 * j;
       if (n >= g.Cout) continue;
-      float v = acc[i][j] * sc + (bias ? __ldg(bias + n) : 0.f);
-      y[p * g.Cout + n] = __float2bfloat16(act_apply(v, g.act));
+      float v = act_apply(acc[i][j] * sc + (bias ? __ldg(bias + n) : 0.f), g.act);
+      if (mask && !(__bfloat162float(mask[p * g.Cout + n]) > 0.f)) v = 0.f;
+      y[p * g.Cout + n] = __float2bfloat16(v);
     }
   }
 }
@@ -190,7 +191,7 @@ int s2e_thin_wgrad(const s2e_conv_t*, const void*, const void*, float*, cudaStre
 
 int s2e_tapconv_fwd_simt(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
                          void* y, cudaStream_t stream) {
-  if (!s2e_debug_get(2)) {  // debug key 2 = keep thin layers on the generic kernel
+  if (!s2e_debug_get(2) && !d->relu_mask) {  // debug key 2 = keep thin layers on the generic kernel
     const int rc = s2e_thin_fwd(d, x, wp, bias, scale, y, stream);
     if (rc != 0) return rc < 0 ? rc : S2E_OK;
   }
@@ -199,10 +200,10 @@ int s2e_tapconv_fwd_simt(const s2e_conv_t* d, const void* x, const void* wp, con
   if (P == 0) return S2E_OK;
   if (d->Cout > 16) {
     dim3 grid((unsigned)ceil_div_ll(P, 64), (unsigned)ceil_div(d->Cout, 64));
-    simt_fwd_kernel<4><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g);
+    simt_fwd_kernel<4><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, (const bf16*)d->relu_mask);
   } else {
     dim3 grid((unsigned)ceil_div_ll(P, 64), (unsigned)ceil_div(d->Cout, 16));
-    simt_fwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g);
+    simt_fwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, (const bf16*)d->relu_mask);
   }
   S2E_LAUNCH_CHECK();
   return S2E_OK;

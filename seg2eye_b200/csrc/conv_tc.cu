@@ -4,7 +4,7 @@
 //   D[128 pixels x BN couts] = sum over taps, 64-channel blocks of  A(tap) [128 x 64] * W(tap)^T [64 x BN]
 //   A tile = one 4-D TMA box {64 ch, TW, TH, TB} of the NHWC input at (w0+dx, h0+dy): halo and padding are
 //   TMA out-of-bounds zero fill, so no im2col is ever materialised.  Both operands K-major, SWIZZLE_128B.
-//   Persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-5 = epilogue
+//   Persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-9 = epilogue
 //   (tcgen05.ld -> scale/bias/act -> bf16 -> swizzled smem -> TMA store).  TMEM accumulator double buffered.
 //
 // Weight-gradient kernel:
@@ -21,7 +21,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements = 128 bytes = swizzle span
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int OUT_BUF_BYTES = BM * 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;      // weight-gradient kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int FWD_THREADS = 320;      // forward kernel: TMA warp, MMA warp, 8 epilogue warps
+constexpr int FWD_EPI_THREADS = 256;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -78,9 +80,12 @@ struct TapTable {
 
 // ================================================================================ forward-like kernel
 struct FwdParams {
+  int dbg;  // timing experiments only (debug key 3): bit0 skip TMA store, bit1 skip math, bit2 skip tmem ld
   int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles;
   int TW, TH, TB;
   int Cout, kc_per_tap, act;
+  int B, Ho, Wo;
+  const bf16* mask;
   uint32_t a_box_bytes;
   const float* bias;
   const float* scale;
@@ -93,11 +98,18 @@ struct FwdCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 5 : 6);
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BUF_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BUF_BYTES + 1024 + 256 + BN * 4;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == S2E_ACT_LRELU) return fmaxf(v, 0.2f * v);
+  if (ACT == S2E_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const FwdParams p) {
   using Cfg = FwdCfg<BN>;
@@ -110,6 +122,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* s_bias = (float*)((uint8_t*)bars + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,7 +134,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 128);
+      ptx::mbar_init(&tmem_empty[i], FWD_EPI_THREADS);
     }
     ptx::fence_barrier_init();
   }
@@ -207,10 +220,14 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter (hardware: warp_id % 4 selects the 32 lanes a warp may read); each takes one
+    // 32-column half of every 64-column chunk.  Bias is staged in shared memory once per tile.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const bool store_thread = (threadIdx.x == 64);
+    const int et = threadIdx.x - 64;
+    const bool store_thread = (et == 0);
     const float scale = p.scale ? __ldg(p.scale) : 1.0f;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -223,41 +240,62 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int h_idx = m % p.tiles_h;
       int b_idx = m / p.tiles_h;
       const int w0 = w_idx * p.TW, h0 = h_idx * p.TH, b0 = b_idx * p.TB, n0 = n_idx * BN;
+      if (et < BN) s_bias[et] = (p.bias && n0 + et < p.Cout) ? __ldg(p.bias + n0 + et) : 0.f;
+      const bf16* mrow = nullptr;
+      if (p.mask) {
+        const int tw = row % p.TW, r2 = row / p.TW;
+        const int th = r2 % p.TH, tb = r2 / p.TH;
+        if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo)
+          mrow = p.mask + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
+      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < BN / 64; ++ch) {
         const int nbase = n0 + ch * 64;
         if (nbase >= p.Cout) break;
-        uint32_t r[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 64);
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 64 + half * 32);
         ptx::tmem_ld_32x32(taddr, r);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32(taddr + 32, r + 32);
-        ptx::tmem_ld_wait();
+        uint4 mk[4] = {make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u),
+                       make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u)};
+        if (mrow) {  // host guarantees Cout % 64 == 0 when a mask is given
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + half * 32) + j);
+        }
         // the TMA store that last read this staging buffer must have finished reading it
         if (store_thread) ptx::tma_store_wait_read<1>();
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
+        ptx::tmem_ld_wait();
         uint8_t* ob = out_buf + buf * OUT_BUF_BYTES + row * 128;
+        const float4* bsrc = reinterpret_cast<const float4*>(s_bias + ch * 64 + half * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0v = bsrc[2 * j], b1v = bsrc[2 * j + 1];
           uint32_t pk[4];
+          pk[0] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 0]), scale, b0v.x)),
+                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 1]), scale, b0v.y)));
+          pk[1] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 2]), scale, b0v.z)),
+                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 3]), scale, b0v.w)));
+          pk[2] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 4]), scale, b1v.x)),
+                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 5]), scale, b1v.y)));
+          pk[3] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 6]), scale, b1v.z)),
+                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 7]), scale, b1v.w)));
+          if (p.mask) {  // keep a value only where the bf16 mask element is > 0 (sign clear and magnitude non-zero)
+            const uint32_t mw[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = j * 8 + e * 2;
-            float v0 = __uint_as_float(r[c]) * scale;
-            float v1 = __uint_as_float(r[c + 1]) * scale;
-            if (p.bias) {
-              v0 += (nbase + c < p.Cout) ? __ldg(p.bias + nbase + c) : 0.f;
-              v1 += (nbase + c + 1 < p.Cout) ? __ldg(p.bias + nbase + c + 1) : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
+              const uint32_t keep = (((lo & 0x8000u) == 0u && (lo & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) |
+                                    (((hi & 0x8000u) == 0u && (hi & 0x7fffu) != 0u) ? 0xffff0000u : 0u);
+              pk[e] &= keep;
             }
-            pk[e] = pack2_bf16(act_apply(v0, p.act), act_apply(v1, p.act));
           }
-          *reinterpret_cast<uint4*>(ob + ((j ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(ob + (((half * 4 + j) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         ptx::fence_proxy_async_smem();
-        ptx::named_bar_sync(2, 128);
-        if (store_thread) {
+        ptx::named_bar_sync(2, FWD_EPI_THREADS);
+        if (store_thread && !(p.dbg & 1)) {
           ptx::tma_store_4d(&tmY, out_buf + buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
           ptx::tma_store_commit();
         }
@@ -300,7 +338,7 @@ void choose_fwd_tile(int B, int H, int W, int* tw, int* th, int* tb) {
   *tb = bb;
 }
 
-template <int BN>
+template <int BN, int ACT>
 int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale, void* y,
                cudaStream_t stream) {
   using Cfg = FwdCfg<BN>;
@@ -313,6 +351,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   if ((rc = make_map_w(&tmB, wp, d->ntaps, d->Cout, d->Cin, BN)) != S2E_OK) return rc;
   if ((rc = make_map_nhwc(&tmY, y, d->B, d->Ho, d->Wo, d->Cout, tw, th, tb)) != S2E_OK) return rc;
   FwdParams p;
+  p.dbg = s2e_debug_get(3);
   p.tiles_w = ceil_div(d->Wo, tw);
   p.tiles_h = ceil_div(d->Ho, th);
   p.tiles_b = ceil_div(d->B, tb);
@@ -324,6 +363,11 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.Cout = d->Cout;
   p.kc_per_tap = d->Cin / BK;
   p.act = d->act;
+  p.B = d->B;
+  p.Ho = d->Ho;
+  p.Wo = d->Wo;
+  p.mask = (const bf16*)d->relu_mask;
+  S2E_REQUIRE(!p.mask || d->Cout % 64 == 0, "tapconv_fwd: relu_mask needs Cout %% 64 == 0 on the tcgen05 path");
   p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);
   p.bias = bias;
   p.scale = scale;
@@ -334,11 +378,11 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_fwd_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   int grid = p.num_tiles < s2e_num_sms() ? p.num_tiles : s2e_num_sms();
-  tapconv_fwd_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, p);
+  tapconv_fwd_kernel<BN, ACT><<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, p);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -595,9 +639,16 @@ int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const
                        void* y, cudaStream_t stream) {
   S2E_REQUIRE(d->Cin % 64 == 0 && d->Cout % 8 == 0, "tcgen05 tapconv needs Cin %% 64 == 0, Cout %% 8 == 0 (Cin=%d Cout=%d)",
               d->Cin, d->Cout);
-  if (d->Cout >= 256) return launch_fwd<256>(d, x, wp, bias, scale, y, stream);
-  if (d->Cout >= 128) return launch_fwd<128>(d, x, wp, bias, scale, y, stream);
-  return launch_fwd<64>(d, x, wp, bias, scale, y, stream);
+#define S2E_FWD_DISPATCH(BN_)                                                                          \
+  switch (d->act) {                                                                                    \
+    case S2E_ACT_LRELU: return launch_fwd<BN_, S2E_ACT_LRELU>(d, x, wp, bias, scale, y, stream);       \
+    case S2E_ACT_RELU: return launch_fwd<BN_, S2E_ACT_RELU>(d, x, wp, bias, scale, y, stream);         \
+    default: return launch_fwd<BN_, S2E_ACT_NONE>(d, x, wp, bias, scale, y, stream);                   \
+  }
+  if (d->Cout >= 256) { S2E_FWD_DISPATCH(256) }
+  if (d->Cout >= 128) { S2E_FWD_DISPATCH(128) }
+  S2E_FWD_DISPATCH(64)
+#undef S2E_FWD_DISPATCH
 }
 
 int s2e_tapconv_wgrad_tc(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {

@@ -169,6 +169,56 @@ __global__ void __launch_bounds__(256) thin_out_fwd_kernel(const bf16* __restric
   }
 }
 
+// K2 fast path for a single output channel (conv_img 64->1, PatchGAN head): lane = one 8-channel chunk of one pixel,
+// its tap weights live in registers (TMAX*8 floats), LPP lanes are reduced with shuffles; a warp walks a contiguous
+// range of output pixels with incrementally updated coordinates.
+template <int TMAX, int LPP>
+__global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                            const float* __restrict__ bias, const float* __restrict__ scale,
+                                                            bf16* __restrict__ y, const ThinGeom g, long long P, long long pix_per_warp) {
+  constexpr int PPW = 32 / LPP;  // pixels processed per warp iteration
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPP, slot = lane / LPP;
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float wreg[TMAX][8];
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (t < g.ntaps) unpack8(*reinterpret_cast<const bf16x8*>(wp + (long long)t * g.Cin + sub * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wreg[t][j] = f[j];
+  }
+  const float sc = scale ? __ldg(scale) : 1.f;
+  const float bv = bias ? __ldg(bias) : 0.f;
+  const long long p0 = gwarp * pix_per_warp;
+  const long long p1 = min(P, p0 + pix_per_warp);
+  for (long long pb = p0; pb < p1; pb += PPW) {
+    const long long p = pb + slot;
+    const bool pv = p < p1;
+    long long pp = pv ? p : p0;
+    const int wo = (int)(pp % g.Wo);
+    pp /= g.Wo;
+    const int ho = (int)(pp % g.Ho);
+    const int b = (int)(pp / g.Ho);
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      if (t < g.ntaps) {
+        const int hi = ho + g.dy[t], wi = wo + g.dx[t];
+        if (pv && hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) {
+          float xf[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)b * g.Hi + hi) * g.Wi + wi) * g.Cin + sub * 8), xf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc = fmaf(xf[j], wreg[t][j], acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (pv && sub == 0) y[p] = __float2bfloat16(act_apply(acc * sc + bv, g.act));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 // wide tensor A [.., Cw] walked pixel by pixel, thin tensor S [.., Cs] sampled at (pixel + sgn*tap).
 // thread = (8-channel chunk of A, one thin channel); acc[T][8] in registers; one atomic per output at the end.
@@ -288,6 +338,17 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
       thin_in_fwd_kernel<1><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads);
     else
       thin_in_fwd_kernel<0><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads);
+    S2E_LAUNCH_CHECK();
+    return 1;
+  }
+  if (d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9) {
+    const long long warps = (long long)s2e_num_sms() * 32;
+    long long ppw = (P + warps - 1) / warps;
+    ppw = ((ppw + 3) / 4) * 4;
+    if (ppw < 4) ppw = 4;
+    const long long nwarps = (P + ppw - 1) / ppw;
+    thin_out1_fwd_kernel<9, 8><<<(unsigned)((nwarps * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale,
+                                                                                        (bf16*)y, g, P, ppw);
     S2E_LAUNCH_CHECK();
     return 1;
   }

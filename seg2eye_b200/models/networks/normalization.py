@@ -132,9 +132,11 @@ class SPADE(nn.Module):
             # thin segmap: its 64-channel im2col (shared by every SPADE of this resolution within one generator
             # forward) turns mlp_shared into a K=64 GEMM on the tensor-core path, forward and weight gradient
             col = seg_im2col_cached(segmap, h, w)
-            actv = ops.SegConvFn.apply(col, conv.weight, conv.bias, L.ACT_RELU)
-        else:
-            actv = conv.forward_nhwc(ops.seg_nearest(segmap, h, w))
+            actv = ops.SegConvFn.apply(col, conv.weight, conv.bias, L.ACT_RELU, True)
+            # the ReLU backward of actv is fused into the gamma|beta data-gradient epilogue (relu_in)
+            return ops.tap_conv(actv, self.mlp_gamma.cfg._replace(relu_in=True), (self.mlp_gamma.weight, self.mlp_beta.weight),
+                                (self.mlp_gamma.bias, self.mlp_beta.bias))
+        actv = conv.forward_nhwc(ops.seg_nearest(segmap, h, w))
         return ops.tap_conv(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
                             (self.mlp_gamma.bias, self.mlp_beta.bias))
 

@@ -15,7 +15,8 @@ from . import _lib as L
 BF16 = torch.bfloat16
 F32 = torch.float32
 
-ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act")
+ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in", defaults=(False,))
+# relu_in: the input of this convolution is the output of a ReLU whose backward is fused into our data-gradient epilogue
 
 _state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False}
 
@@ -235,6 +236,9 @@ class TapConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wpt = packed_weights(weights, cfg, True)
             dd = _desc(B, Ho, Wo, Cout, His, Wis, Cinp, taps, L.ACT_NONE, negate=True)
+            if cfg.relu_in:
+                assert cfg.stride == 1 and Cinp % 64 == 0
+                dd.relu_mask = L.ptr(xs)   # x = relu(.) > 0 exactly where the ReLU passed gradient
             dxs = torch.empty(B, His, Wis, Cinp, dtype=BF16, device=dy.device)
             impl = _pick(Cout % 64 == 0 and Cinp % 8 == 0)
             if impl == L.IMPL_TC:
@@ -563,8 +567,9 @@ class SegConvFn(torch.autograd.Function):
     kernels, forward and weight gradient (the segmap itself needs no gradient)."""
 
     @staticmethod
-    def forward(ctx, col, weight, bias, act):
+    def forward(ctx, col, weight, bias, act, act_grad_fused=False):
         import weakref
+        ctx.act_grad_fused = act_grad_fused   # the consumer already applied the ReLU mask to the gradient it sends back
         B, H, W, K = col.shape
         Cout, Cs = weight.shape[0], weight.shape[1]
         assert K == 64 and weight.shape[2:] == (3, 3) and 9 * Cs <= 64
@@ -597,7 +602,7 @@ class SegConvFn(torch.autograd.Function):
         dy = _c(dy)
         B, H, W, Cout = dy.shape
         st = L.stream()
-        if ctx.act != L.ACT_NONE:
+        if ctx.act != L.ACT_NONE and not ctx.act_grad_fused:
             dpre = torch.empty_like(dy)
             L.call("s2e_act_bwd", L.ptr(dy), L.ptr(y), dy.numel(), ctx.act, L.ptr(dpre), st)
         else:
@@ -616,7 +621,7 @@ class SegConvFn(torch.autograd.Function):
             L.call("s2e_unpack_wgrad_im2col3x3", L.ptr(dwp), Cout, ctx.cs, L.ptr(gw), st)
         if ctx.has_b and ctx.needs_input_grad[2] and not ctx.skip_wgrad:
             gb = channel_sums(dpre, B, H * W, Cout) if Cout % 8 == 0 else dpre.float().sum(dim=(0, 1, 2))
-        return None, gw, gb, None
+        return None, gw, gb, None, None
 
 
 class MakeDInputFn(torch.autograd.Function):

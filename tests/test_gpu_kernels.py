@@ -123,6 +123,7 @@ SIMT_CASES = [
     (2, 1, 16, 32, 32, 3, 2, 1, 0),      # E layer0 (3x3 s2 p1, Cin = 1)
     (1, 24, 40, 9, 7, 1, 1, 0, 0),       # 1x1 with ragged channel counts
     (2, 16, 32, 13, 11, 4, 2, 2, 0),     # 4x4 s2 p2 mid layer, odd size
+    (2, 64, 1, 21, 18, 3, 1, 1, 0),      # conv_img at ngf=64: register-weight single-output-channel kernel
 ]
 
 
@@ -185,6 +186,29 @@ def test_seg_im2col_conv_matches_conv3x3(S, impl_name):
         y.backward(nhwc(dy))
     assert rel(nchw(y), yr) < TOL_ACT
     assert rel(wc.grad, wr.grad) < TOL_ACT and rel(bc.grad, br.grad) < TOL_ACT
+
+
+@pytest.mark.parametrize("impl_name", ["tc", "simt"])
+def test_relu_backward_fused_into_dgrad_epilogue(S, impl_name):
+    """conv(relu(a)) with relu_in=True: the gradient returned for relu(a) is already masked by (relu(a) > 0)."""
+    L, ops = S
+    g = torch.Generator().manual_seed(11)
+    B, Cin, Cout, H, W = 2, 128, 64, 12, 20
+    a = bf(torch.randn(B, Cin, H, W, generator=g))
+    w = bf(torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5)
+    ar, wr = a.clone().requires_grad_(), w.clone().requires_grad_()
+    yr = F.conv2d(F.relu(ar), wr, None, padding=1)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc = nhwc(F.relu(a)).requires_grad_()
+    wc = w.cuda().requires_grad_()
+    with ops.force_impl(L.IMPL_TC if impl_name == "tc" else L.IMPL_SIMT):
+        y = ops.tap_conv(xc, ops.ConvCfg(3, 3, 1, 1, 0, True), (wc,), ())
+        y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < TOL_ACT
+    assert rel(nchw(xc.grad), ar.grad) < TOL_ACT          # masked gradient == gradient w.r.t. the pre-ReLU tensor
+    assert float((nchw(xc.grad)[F.relu(a) <= 0]).abs().max()) == 0.0
+    assert rel(wc.grad, wr.grad) < TOL_ACT
 
 
 def test_conv_tcgen05_large_k_many_tiles(S):
