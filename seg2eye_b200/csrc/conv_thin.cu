@@ -35,14 +35,14 @@ __global__ void __launch_bounds__(256) thin_in_fwd_kernel(const bf16* __restrict
   __syncthreads();
   const int ncog = cot >> 3;
   const float sc = scale ? __ldg(scale) : 1.f;
-  const long long nwork = nquads * ncog;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nwork; v += (long long)gridDim.x * blockDim.x) {
-    const long long q = v / ncog;
+  const unsigned nwork = (unsigned)(nquads * ncog);   // host guarantees < 2^31
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nwork; v += gridDim.x * blockDim.x) {
+    const unsigned q = v / (unsigned)ncog;
     const int cog = (int)(v - q * ncog);
-    const int qw = (int)(q % quads_per_row);
-    const long long r = q / quads_per_row;
-    const int ho = (int)(r % g.Ho);
-    const int b = (int)(r / g.Ho);
+    const int qw = (int)(q % (unsigned)quads_per_row);
+    const unsigned r = q / (unsigned)quads_per_row;
+    const int ho = (int)(r % (unsigned)g.Ho);
+    const int b = (int)(r / (unsigned)g.Ho);
     const int wo0 = qw * K1_PX;
     float acc[K1_PX][8];
 #pragma unroll
@@ -124,16 +124,17 @@ __global__ void __launch_bounds__(256) thin_out_fwd_kernel(const bf16* __restric
   __syncthreads();
   const int nchunk = Cin >> 3;
   const int sub = threadIdx.x % lpp;
-  const long long gpix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lpp;
-  const long long gstride = (long long)gridDim.x * blockDim.x / lpp;
+  const unsigned gpix = (blockIdx.x * blockDim.x + threadIdx.x) / (unsigned)lpp;
+  const unsigned gstride = gridDim.x * blockDim.x / (unsigned)lpp;
+  const unsigned Pu = (unsigned)P, Pend = ((Pu + gstride - 1) / gstride) * gstride;   // host guarantees P < 2^31
   const float sc = scale ? __ldg(scale) : 1.f;
-  for (long long p = gpix; p < P + (gstride - P % gstride) % gstride; p += gstride) {  // uniform trip count per warp
-    const bool pv = p < P;
-    long long pp = pv ? p : 0;
-    const int wo = (int)(pp % g.Wo);
-    pp /= g.Wo;
-    const int ho = (int)(pp % g.Ho);
-    const int b = (int)(pp / g.Ho);
+  for (unsigned p = gpix; p < Pend; p += gstride) {  // uniform trip count per warp
+    const bool pv = p < Pu;
+    unsigned pp = pv ? p : 0u;
+    const int wo = (int)(pp % (unsigned)g.Wo);
+    pp /= (unsigned)g.Wo;
+    const int ho = (int)(pp % (unsigned)g.Ho);
+    const int b = (int)(pp / (unsigned)g.Ho);
     float acc[CS_MAX];
 #pragma unroll
     for (int c = 0; c < CS_MAX; ++c) acc[c] = 0.f;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) thin_out_fwd_kernel(const bf16* __restric
       if (c < Cs) {
         float v = acc[c];
         for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (pv && sub == 0) y[p * Cs + c] = __float2bfloat16(act_apply(v * sc + (bias ? __ldg(bias + c) : 0.f), g.act));
+        if (pv && sub == 0) y[(long long)p * Cs + c] = __float2bfloat16(act_apply(v * sc + (bias ? __ldg(bias + c) : 0.f), g.act));
       }
     }
   }
@@ -192,14 +193,16 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
   const float bv = bias ? __ldg(bias) : 0.f;
   const long long p0 = gwarp * pix_per_warp;
   const long long p1 = min(P, p0 + pix_per_warp);
+  if (p0 >= p1) return;
+  // this lane's pixel coordinates, advanced by PPW pixels per iteration without divisions
+  unsigned pp0 = (unsigned)min(p0 + slot, P - 1);
+  int wo = (int)(pp0 % (unsigned)g.Wo);
+  pp0 /= (unsigned)g.Wo;
+  int ho = (int)(pp0 % (unsigned)g.Ho);
+  int b = (int)(pp0 / (unsigned)g.Ho);
   for (long long pb = p0; pb < p1; pb += PPW) {
     const long long p = pb + slot;
     const bool pv = p < p1;
-    long long pp = pv ? p : p0;
-    const int wo = (int)(pp % g.Wo);
-    pp /= g.Wo;
-    const int ho = (int)(pp % g.Ho);
-    const int b = (int)(pp / g.Ho);
     float acc = 0.f;
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) {
@@ -216,6 +219,14 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
 #pragma unroll
     for (int o = LPP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (pv && sub == 0) y[p] = __float2bfloat16(act_apply(acc * sc + bv, g.act));
+    wo += PPW;
+    while (wo >= g.Wo) {
+      wo -= g.Wo;
+      if (++ho == g.Ho) {
+        ho = 0;
+        ++b;
+      }
+    }
   }
 }
 
@@ -315,6 +326,7 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
                  cudaStream_t stream) {
   const long long P = (long long)d->B * d->Ho * d->Wo;
   if (P == 0) return 1;
+  if (P * 32 >= (1LL << 31)) return 0;  // 32-bit index math inside the thin kernels
   ThinGeom g = make_thin_geom(d);
   if (d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8) {
     const int cot = d->Cout < K1_CO_TILE ? d->Cout : K1_CO_TILE;

@@ -295,30 +295,47 @@ __global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------ space <-> depth
-__global__ void s2d_kernel(const bf16* __restrict__ x, int H, int W, int C, int H2, int W2, long long n, bf16* __restrict__ y) {
-  GRID_STRIDE(i, n) {  // i over output [B][H2][W2][4][C]
-    const int c = (int)(i % C);
-    long long p = i / C;
-    const int ph = (int)(p % 4);
-    p /= 4;
-    const int w2 = (int)(p % W2);
-    p /= W2;
-    const int h2 = (int)(p % H2);
-    const long long b = p / H2;
-    const int h = 2 * h2 + (ph >> 1), w = 2 * w2 + (ph & 1);
-    y[i] = (h < H && w < W) ? x[((b * H + h) * W + w) * C + c] : __float2bfloat16(0.f);
+// VEC = 8: one 16-byte vector of 8 channels per thread (C % 8 == 0); VEC = 1: scalar fallback.  32-bit index math.
+template <int VEC>
+__global__ void s2d_kernel(const bf16* __restrict__ x, int H, int W, int C, int H2, int W2, unsigned n, bf16* __restrict__ y) {
+  const unsigned CV = (unsigned)(C / VEC);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {  // output [B][H2][W2][4][CV]
+    const unsigned c = i % CV;
+    unsigned p = i / CV;
+    const unsigned ph = p & 3u;
+    p >>= 2;
+    const unsigned w2 = p % (unsigned)W2;
+    p /= (unsigned)W2;
+    const unsigned h2 = p % (unsigned)H2;
+    const unsigned b = p / (unsigned)H2;
+    const int h = 2 * (int)h2 + (int)(ph >> 1), w = 2 * (int)w2 + (int)(ph & 1);
+    const bool in = h < H && w < W;
+    const long long src = ((((long long)b * H + h) * W + w) * CV + c) * VEC;
+    if (VEC == 8) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (in) v = *reinterpret_cast<const uint4*>(x + src);
+      *reinterpret_cast<uint4*>(y + (long long)i * 8) = v;
+    } else {
+      y[i] = in ? x[src] : __float2bfloat16(0.f);
+    }
   }
 }
-__global__ void d2s_kernel(const bf16* __restrict__ dy, int H, int W, int C, int H2, int W2, long long n, bf16* __restrict__ dx) {
-  GRID_STRIDE(i, n) {  // i over dx [B][H][W][C]
-    const int c = (int)(i % C);
-    long long p = i / C;
-    const int w = (int)(p % W);
-    p /= W;
-    const int h = (int)(p % H);
-    const long long b = p / H;
-    const int ph = (h & 1) * 2 + (w & 1);
-    dx[i] = dy[(((b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + ph) * C + c];
+template <int VEC>
+__global__ void d2s_kernel(const bf16* __restrict__ dy, int H, int W, int C, int H2, int W2, unsigned n, bf16* __restrict__ dx) {
+  const unsigned CV = (unsigned)(C / VEC);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {  // dx [B][H][W][CV]
+    const unsigned c = i % CV;
+    unsigned p = i / CV;
+    const unsigned w = p % (unsigned)W;
+    p /= (unsigned)W;
+    const unsigned h = p % (unsigned)H;
+    const unsigned b = p / (unsigned)H;
+    const unsigned ph = (h & 1u) * 2u + (w & 1u);
+    const long long src = (((((long long)b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + ph) * CV + c) * VEC;
+    if (VEC == 8)
+      *reinterpret_cast<uint4*>(dx + (long long)i * 8) = *reinterpret_cast<const uint4*>(dy + src);
+    else
+      dx[i] = dy[src];
   }
 }
 
@@ -824,17 +841,27 @@ int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float*
 
 int s2e_space_to_depth(const void* x, int B, int H, int W, int C, void* y, void* stream) {
   const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
-  const long long n = (long long)B * H2 * W2 * 4 * C;
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  const long long n = (long long)B * H2 * W2 * 4 * (C / vec);
   if (!n) return S2E_OK;
-  s2d_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, H2, W2, n, (bf16*)y);
+  S2E_REQUIRE(n < (1LL << 31), "space_to_depth: tensor too large for 32-bit indexing");
+  if (vec == 8)
+    s2d_kernel<8><<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, H2, W2, (unsigned)n, (bf16*)y);
+  else
+    s2d_kernel<1><<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, H2, W2, (unsigned)n, (bf16*)y);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
 int s2e_depth_to_space(const void* dy, int B, int H, int W, int C, void* dx, void* stream) {
   const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
-  const long long n = (long long)B * H * W * C;
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  const long long n = (long long)B * H * W * (C / vec);
   if (!n) return S2E_OK;
-  d2s_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C, H2, W2, n, (bf16*)dx);
+  S2E_REQUIRE(n < (1LL << 31), "depth_to_space: tensor too large for 32-bit indexing");
+  if (vec == 8)
+    d2s_kernel<8><<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C, H2, W2, (unsigned)n, (bf16*)dx);
+  else
+    d2s_kernel<1><<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C, H2, W2, (unsigned)n, (bf16*)dx);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
