@@ -45,6 +45,8 @@ class Pix2PixTrainer():
         style_image (B,ns,1,H,W), target (B,1,H,W)).  Afterwards run_*_one_step copy the batch into static device
         buffers and replay.  Shapes must not change; call disable_cuda_graphs() to return to eager execution."""
         if parallel.world_size() > 1:
+            # capturing the NCCL all-reduce inside the step graph deadlocked on the 2-GPU box (round 1); multi-GPU
+            # runs use the eager path until the collective is moved outside the captured region
             raise RuntimeError("CUDA-graph steps are single-process for now; multi-GPU runs use the eager path")
         dev = self.pix2pix_model.device()
         self.pix2pix_model.train()

@@ -151,3 +151,34 @@ def test_data_parallel_grad_allreduce_gloo_world2():
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/options"), reason="reference checkout only exists in the build container")
+def test_reference_option_parsing_and_trainer_construction_with_dropin(tmp_path):
+    """The reference's own options package + train.py construction sequence on top of install_dropin()."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, types
+sys.path.insert(0, %r); sys.path.insert(1, "/root/reference")
+sys.dont_write_bytecode = True
+sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+import cv2; cv2.cv2 = cv2; sys.modules["cv2.cv2"] = cv2
+import seg2eye_b200; seg2eye_b200.install_dropin()
+sys.argv = ["train.py", "--dataroot", "/x", "--gpu_ids", "-1", "--name", "dropin", "--checkpoints_dir", %r,
+            "--ngf", "8", "--ndf", "8", "--lambda_l1", "10", "--num_D", "2"]
+from options.train_options import TrainOptions          # the reference's own option machinery
+opt = TrainOptions().parse()
+assert opt.num_D == 2 and opt.n_layers_D == 4 and opt.num_upsampling_layers == "normal" and opt.netD_subarch == "n_layer"
+from trainers.pix2pix_trainer import Pix2PixTrainer      # resolves to seg2eye_b200
+import models
+assert models.__name__ == "seg2eye_b200.models"
+tr = Pix2PixTrainer(opt)
+tr.save("latest")
+import os, torch
+sd = torch.load(os.path.join(%r, "dropin", "latest_net_G.pth"))
+assert "head_0.conv_0.weight_orig" in sd and "up_3.norm_s.spade.mlp_gamma.weight" in sd
+print("DROPIN_OK", type(tr.pix2pix_model).__module__)
+''' % (REPO, str(tmp_path), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "DROPIN_OK seg2eye_b200.models.pix2pix_model" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
