@@ -111,7 +111,7 @@ int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int st
  * (fixed-order partial sums: the iteration is bitwise reproducible).
  * update = 0 (module in eval mode): u, v are left untouched and only inv_sigma is produced. */
 int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
-                            int update, void* stream);
+                            int update, float* u_copy, float* v_copy, void* stream); /* *_copy: optional snapshots */
 
 /* [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] with channel (i*2+j)*C+c = x[2h+i, 2w+j, c] (zero beyond the edge),
  * and its adjoint (gradient) */
@@ -138,9 +138,15 @@ int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const 
                         double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, void* stream);
 
 /* InstanceNorm2d(affine=False)+optional LeakyReLU on NHWC bf16 (normalization.py:41; discriminator.py:88-92;
- * encoder.py:23-38).  in_scale: optional device scalar multiplied into x first (1/sigma). */
-int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, double* acc, float* mean, float* rstd,
-                     void* y, void* stream);
+ * encoder.py:23-38).  in_scale (nullable): one factor per `group` consecutive images, applied to x implicitly. */
+int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, const float* in_scale, int group,
+                     double* acc, float* mean, float* rstd, void* y, void* stream);
+/* Batched style encoder (pix2pix_model.py:285 calls netE once per sample, so sample b sees its own 1/sigma_b):
+ * the convolution runs unscaled, in_scale[n / group] folds 1/sigma_b into the InstanceNorm statistics, and the
+ * spectral chain-rule term  dW_orig -= sum_b c_b u_b v_b^T,  c_b = (eps/is_b) sum_{n in b, c} S2[n,c] rstd'[n,c]^2
+ * (S2 = sum_hw g*xhat, the second accumulator of s2e_instnorm_bwd) is produced here.  coef: B floats scratch. */
+int s2e_sn_in_correction(const double* racc, const float* rstd, const float* inv_sigma, int Bn, int group, int C,
+                         float eps, const float* U, const float* V, int K, float* coef, float* dw, void* stream);
 int s2e_instnorm_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, int B, int HW,
                      int C, int act, double* racc, void* dx, void* stream);
 

@@ -39,14 +39,15 @@ _SIGS = {
     "s2e_pack_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "s2e_packed_taps": [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)],
     "s2e_unpack_wgrad": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
-    "s2e_spectral_power_iter": [_P, _I, _I, _P, _P, _P, _P, _I, _P],
+    "s2e_spectral_power_iter": [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P],
+    "s2e_sn_in_correction": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P, _P, _P],
     "s2e_space_to_depth": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_depth_to_space": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_norm_stats": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_norm_finalize": [_P, _I, _I, _D, _F, _P, _P, _P, _P, _F, _P, _P],
     "s2e_spade_style_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P],
-    "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P, _P],
     "s2e_instnorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "s2e_upsample2x_fwd": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_upsample2x_bwd": [_P, _I, _I, _I, _I, _P, _P],

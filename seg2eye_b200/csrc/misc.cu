@@ -255,11 +255,20 @@ __global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restr
   if (c >= cols) return;
   const int r0 = blockIdx.y * rchunk, r1 = min(rows, r0 + rchunk);
   float acc = 0.f;
-  for (int r = r0; r < r1; ++r) acc = fmaf(w[(long long)r * cols + c], u[r], acc);
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {  // 8 independent loads in flight per thread
+    float wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = w[(long long)(r + j) * cols + c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(wv[j], u[r + j], acc);
+  }
+  for (; r < r1; ++r) acc = fmaf(w[(long long)r * cols + c], u[r], acc);
   part[(long long)blockIdx.y * cols + c] = acc;
 }
 // x = sum_k raw[k][:] ; x <- x / max(||x||, eps) ; single block.  If inv_sigma: *inv_sigma = 1 / dot(x_normalized, x)
-__global__ void sn_normalize_kernel(const float* __restrict__ raw, int nparts, int n, float* __restrict__ outv, float* inv_sigma) {
+__global__ void sn_normalize_kernel(const float* __restrict__ raw, int nparts, int n, float* __restrict__ outv, float* inv_sigma,
+                                    float* __restrict__ copy_out) {
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float v = 0.f;
@@ -273,7 +282,11 @@ __global__ void sn_normalize_kernel(const float* __restrict__ raw, int nparts, i
   __syncthreads();
   const float nsq = s_norm;
   const float denom = fmaxf(sqrtf(nsq), 1e-12f);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) outv[i] = outv[i] / denom;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = outv[i] / denom;
+    outv[i] = v;
+    if (copy_out) copy_out[i] = v;
+  }
   if (inv_sigma && threadIdx.x == 0) *inv_sigma = 1.f / (nsq / denom);  // sigma = u . (W v) = ||Wv||^2 / max(||Wv||,eps)
 }
 // inv_sigma = 1 / (u . s)  (evaluation mode: no buffer update) ; single block
@@ -812,7 +825,7 @@ int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int st
 }
 
 int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
-                            int update, void* stream) {
+                            int update, float* u_copy, float* v_copy, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   float* t = scratch;         // cols
   float* s = scratch + cols;  // rows
@@ -830,11 +843,11 @@ int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float*
   dim3 g1(ceil_div(cols, 128), nparts);
   sn_wt_u_kernel<<<g1, 128, 0, st>>>(w, u, rows, cols, rchunk, part);
   S2E_LAUNCH_CHECK();
-  sn_normalize_kernel<<<1, 1024, 0, st>>>(part, nparts, cols, v, nullptr);
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(part, nparts, cols, v, nullptr, v_copy);
   S2E_LAUNCH_CHECK();
   sn_w_v_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(w, v, rows, cols, s);
   S2E_LAUNCH_CHECK();
-  sn_normalize_kernel<<<1, 1024, 0, st>>>(s, 1, rows, u, inv_sigma);
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(s, 1, rows, u, inv_sigma, u_copy);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

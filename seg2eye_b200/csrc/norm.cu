@@ -65,9 +65,11 @@ __global__ void __launch_bounds__(NT) stats_kernel(const bf16* __restrict__ x, i
   });
 }
 
+// in_scale (optional, one value per `group` consecutive statistic groups): statistics are those of x * in_scale without
+// the product ever being formed: mean stays that of x, rstd' = s / sqrt(var * s^2 + eps), so (x - mean) * rstd' == norm(s x).
 __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, double count, float eps, float* mean,
                                 float* rstd, float* running_mean, float* running_var, float momentum,
-                                long long* nbt) {
+                                long long* nbt, const float* __restrict__ in_scale, int group) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && nbt) *nbt += 1;
   if (i >= G * C) return;
@@ -77,7 +79,8 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, do
   double var = ss / count - m * m;
   if (var < 0) var = 0;
   mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  const double sc = in_scale ? (double)in_scale[g / group] : 1.0;
+  rstd[i] = (float)(sc / sqrt(var * sc * sc + (double)eps));
   if (running_mean && g == 0) {
     const double unb = count > 1 ? var * count / (count - 1) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
@@ -382,9 +385,41 @@ int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* 
 int s2e_norm_finalize(const double* acc, int G, int C, double count, float eps, float* mean, float* rstd,
                       float* running_mean, float* running_var, float momentum, int64_t* nbt, void* stream) {
   finalize_kernel<<<ceil_div(G * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, G, C, count, eps, mean, rstd, running_mean,
-                                                                           running_var, momentum, (long long*)nbt);
+                                                                           running_var, momentum, (long long*)nbt, nullptr, 1);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
+}
+
+// c[b] = (eps / is_b) * sum_{n in sample b, c} S2[n][c] * rstd'[n][c]^2   (one block per sample)
+__global__ void sn_corr_coef_kernel(const double* __restrict__ racc, const float* __restrict__ rstd, const float* __restrict__ inv_sigma,
+                                    int C, int group, float eps, float* __restrict__ coef) {
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < group * C; i += blockDim.x) {
+    const int n = b * group + i / C, c = i % C;
+    const float r = rstd[(size_t)n * C + c];
+    acc += (float)racc[(size_t)n * 2 * C + C + c] * r * r;
+  }
+  __shared__ float sh[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) coef[b] = eps / inv_sigma[b] * v;
+  }
+}
+// dW[co][k] = - sum_b coef[b] * U[b][co] * V[b][k]
+__global__ void sn_corr_apply_kernel(const float* __restrict__ coef, const float* __restrict__ U, const float* __restrict__ V, int Bn,
+                                     int Cout, int K, float* __restrict__ dw) {
+  const long long n = (long long)Cout * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / K), k = (int)(i % K);
+    float acc = 0.f;
+    for (int b = 0; b < Bn; ++b) acc = fmaf(coef[b] * U[(size_t)b * Cout + co], V[(size_t)b * K + k], acc);
+    dw[i] = -acc;
+  }
 }
 
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd, int B,
@@ -421,12 +456,26 @@ int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const 
   return S2E_OK;
 }
 
-int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, double* acc, float* mean, float* rstd,
-                     void* y, void* stream) {
+int s2e_sn_in_correction(const double* racc, const float* rstd, const float* inv_sigma, int Bn, int group, int C, float eps,
+                         const float* U, const float* V, int K, float* coef, float* dw, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  sn_corr_coef_kernel<<<Bn, 256, 0, st>>>(racc, rstd, inv_sigma, C, group, eps, coef);
+  S2E_LAUNCH_CHECK();
+  const long long n = (long long)C * K;
+  long long g = (n + 255) / 256;
+  if (g > (long long)s2e_num_sms() * 16) g = (long long)s2e_num_sms() * 16;
+  sn_corr_apply_kernel<<<(unsigned)g, 256, 0, st>>>(coef, U, V, Bn, C, K, dw);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, const float* in_scale, int group, double* acc,
+                     float* mean, float* rstd, void* y, void* stream) {
   int rc = s2e_norm_stats(x, B, HW, C, 1, acc, stream);
   if (rc) return rc;
-  rc = s2e_norm_finalize(acc, B, C, (double)HW, eps, mean, rstd, nullptr, nullptr, 0.f, nullptr, stream);
-  if (rc) return rc;
+  finalize_kernel<<<ceil_div(B * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, B, C, (double)HW, eps, mean, rstd, nullptr, nullptr,
+                                                                           0.f, nullptr, in_scale, group > 0 ? group : 1);
+  S2E_LAUNCH_CHECK();
   const long long nvec = (long long)B * HW * (C >> 3);
   instnorm_apply_kernel<<<ew_grid(nvec), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, rstd, HW, C, nvec, act, (bf16*)y);
   S2E_LAUNCH_CHECK();

@@ -28,6 +28,29 @@ class ConvEncoder(BaseNetwork):
         self.actvn = nn.LeakyReLU(0.2, False)
         self.opt = opt
 
+    def forward_samples(self, x5):
+        """Equivalent of `[self(x5[b]) for b in range(B)]` (pix2pix_model.py:285) in one batched pass.
+
+        x5: (B, ns, 1, H, W).  Every spectral-normed layer still advances its (u, v) B times and sample b is
+        normalised with its own sigma_b: the convolutions run unscaled over all B*ns images, 1/sigma_b enters the
+        InstanceNorm statistics of sample b, and the sigma chain-rule term is added in backward.
+        Returns mu, logvar of shape (B, ns, w_dim) and the 6 feature maps, each (B*ns, C, h, w)."""
+        B, ns = x5.shape[0], x5.shape[1]
+        x = x5.reshape(B * ns, *x5.shape[2:])
+        if x.size(2) != 256 or x.size(3) != 256:
+            h = ops.BilinearFn.apply(x, (256, 256))
+        else:
+            h = ops.as_nhwc(x)
+        features = []
+        for n in range(self.len_sequence):
+            layer = getattr(self, 'layer' + str(n))
+            h = layer[1].forward_nhwc_spectral(layer[0].forward_nhwc_unscaled(h), layer[0], B)
+            features.append(ops.as_nchw_view(h))
+        hw = h.shape[1] * h.shape[2]
+        mu = ops.LinearFn.apply(h, self.fc_mu.weight, self.fc_mu.bias, L.ACT_NONE, hw)
+        logvar = ops.LinearFn.apply(h, self.fc_var.weight, self.fc_var.bias, L.ACT_NONE, hw)
+        return mu.view(B, ns, -1), logvar.view(B, ns, -1), features
+
     def forward(self, x, get_intermediate_features=False):
         # (ns,1,H,W) fp32 -> bilinear 256x256 (encoder.py:54-55) -> NHWC bf16
         if x.size(2) != 256 or x.size(3) != 256:

@@ -52,6 +52,11 @@ class Conv2d(nn.Module):
         biases = (self.bias,) if self.bias is not None else ()
         return ops.tap_conv(x, cfg, (self.master_weight(),), biases, self.sn_state())
 
+    def forward_nhwc_unscaled(self, x):
+        """conv(x, weight_orig) without the 1/sigma factor and without touching u/v (batched style encoder)."""
+        assert self.spectral and self.bias is None
+        return ops.tap_conv(x, self.cfg, (self.weight_orig,), (), None)
+
     def forward(self, x):
         return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x)))
 
@@ -92,6 +97,12 @@ class InstanceNorm2d(nn.Module):
 
     def forward_nhwc(self, x):
         return ops.InstNormFn.apply(x, self.act)
+
+    def forward_nhwc_spectral(self, z, conv, n_samples):
+        """z = UNSCALED output of the spectral conv `conv` over n_samples groups of images; equals what n_samples
+        successive conv->norm calls (one per group) would produce, buffers of `conv` advanced n_samples times."""
+        inv, U, V = ops.spectral_multi(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, n_samples)
+        return ops.InstNormFn.apply(z, self.act, inv, U, V, z.shape[0] // n_samples, conv.weight_orig)
 
     def forward(self, x):
         return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x)))

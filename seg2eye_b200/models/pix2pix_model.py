@@ -187,11 +187,16 @@ class Pix2PixModel(torch.nn.Module):
         raise ValueError(f"Aggregation method not found: {self.opt.style_aggr_method}")
 
     def _compute_multiple_netE(self, real_image):
-        # one encoder call per sample, as in the reference (pix2pix_model.py:285): the spectral-norm vectors of
-        # netE advance once per call
-        result = [self.netE(real_image[b]) for b in range(real_image.shape[0])]
-        mu, logvar, features = zip(*result)
-        out = torch.stack(mu, dim=0)
+        # The reference calls netE once per sample (pix2pix_model.py:285), advancing its spectral-norm vectors once
+        # per call.  forward_samples reproduces exactly that in one batched pass.
+        B, ns = real_image.shape[0], real_image.shape[1]
+        if hasattr(self.netE, 'forward_samples'):
+            out, _, feats = self.netE.forward_samples(real_image)
+            features = [[f[b * ns:(b + 1) * ns] for f in feats] for b in range(B)]
+        else:
+            result = [self.netE(real_image[b]) for b in range(B)]
+            mu, logvar, features = zip(*result)
+            out = torch.stack(mu, dim=0)
         assert out.shape == (*real_image.shape[:2], self.opt.w_dim)
         return out, features
 

@@ -298,8 +298,33 @@ def spectral_inv_sigma(weight_orig, u, v, training):
     inv = torch.empty(1, dtype=F32, device=w.device)
     scratch = torch.empty(rows + cols + ((rows + 63) // 64) * cols, dtype=F32, device=w.device)
     L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv), L.ptr(scratch),
-           1 if training else 0, L.stream())
+           1 if training else 0, None, None, L.stream())
     return inv
+
+
+def spectral_multi(weight_orig, u, v, training, n_calls):
+    """What `n_calls` successive forward calls of a spectral-normed layer do to (u, v): returns the n_calls values of
+    1/sigma and, per call, the u / v vectors it used (needed by the chain rule).  Used by the batched style encoder,
+    which replaces the reference's one-netE-call-per-sample loop (pix2pix_model.py:285)."""
+    w = weight_orig.detach()
+    rows = w.shape[0]
+    cols = w.numel() // rows
+    inv = torch.empty(n_calls, dtype=F32, device=w.device)
+    U = torch.empty(n_calls, rows, dtype=F32, device=w.device)
+    V = torch.empty(n_calls, cols, dtype=F32, device=w.device)
+    scratch = torch.empty(rows + cols + ((rows + 63) // 64) * cols, dtype=F32, device=w.device)
+    st = L.stream()
+    for b in range(n_calls):
+        if training:
+            L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv[b:]), L.ptr(scratch), 1,
+                   L.ptr(U[b]), L.ptr(V[b]), st)
+        else:
+            L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv[b:]), L.ptr(scratch), 0,
+                   None, None, st)
+    if not training:
+        U.copy_(u.expand_as(U))
+        V.copy_(v.expand_as(V))
+    return inv, U, V
 
 
 # ------------------------------------------------------------------------------------------------ norms
@@ -356,32 +381,47 @@ class SpadeStyleFn(torch.autograd.Function):
 
 
 class InstNormFn(torch.autograd.Function):
-    """nn.InstanceNorm2d(affine=False, eps=1e-5) + optional LeakyReLU(0.2) on NHWC bf16."""
+    """nn.InstanceNorm2d(affine=False, eps=1e-5) + optional LeakyReLU(0.2) on NHWC bf16.
+
+    With `sn = (inv_sigma (S,), U (S,Cout), V (S,K), group, weight_orig)` the input is the UNSCALED output z of a
+    spectral-normed convolution applied to S groups of `group` images; group s is normalised as IN(z / sigma_s)
+    (the scale only enters the statistics) and backward additionally returns, as the gradient of `weight_orig`, the
+    spectral chain-rule term  - sum_s c_s u_s v_s^T  (see s2e_sn_in_correction)."""
 
     @staticmethod
-    def forward(ctx, x, act):
+    def forward(ctx, x, act, sn_inv=None, sn_U=None, sn_V=None, group=1, weight_orig=None):
         x = _c(x)
         B, H, W, Cc = x.shape
         acc = torch.empty(B * 2 * Cc, dtype=torch.float64, device=x.device)
         mean = torch.empty(B, Cc, dtype=F32, device=x.device)
         rstd = torch.empty(B, Cc, dtype=F32, device=x.device)
         y = torch.empty_like(x)
-        L.call("s2e_instnorm_fwd", L.ptr(x), B, H * W, Cc, act, 1e-5, L.ptr(acc), L.ptr(mean), L.ptr(rstd), L.ptr(y),
-               L.stream())
-        ctx.act = act
-        ctx.save_for_backward(x, y, mean, rstd)
+        L.call("s2e_instnorm_fwd", L.ptr(x), B, H * W, Cc, act, 1e-5, L.ptr(sn_inv), group, L.ptr(acc), L.ptr(mean),
+               L.ptr(rstd), L.ptr(y), L.stream())
+        ctx.act, ctx.group = act, group
+        ctx.has_sn = sn_inv is not None
+        ctx.save_for_backward(x, y, mean, rstd, sn_inv, sn_U, sn_V, weight_orig)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, rstd = ctx.saved_tensors
+        x, y, mean, rstd, sn_inv, sn_U, sn_V, weight_orig = ctx.saved_tensors
         dy = _c(dy)
         B, H, W, Cc = x.shape
         racc = torch.empty(B * 2 * Cc, dtype=torch.float64, device=x.device)
         dx = torch.empty_like(x)
+        st = L.stream()
         L.call("s2e_instnorm_bwd", L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(mean), L.ptr(rstd), B, H * W, Cc, ctx.act,
-               L.ptr(racc), L.ptr(dx), L.stream())
-        return dx, None
+               L.ptr(racc), L.ptr(dx), st)
+        gw = None
+        if ctx.has_sn and weight_orig is not None and ctx.needs_input_grad[6] and not _state["skip_wgrad"]:
+            S = sn_inv.shape[0]
+            K = weight_orig.numel() // weight_orig.shape[0]
+            coef = torch.empty(S, dtype=F32, device=x.device)
+            gw = torch.empty_like(weight_orig)
+            L.call("s2e_sn_in_correction", L.ptr(racc), L.ptr(rstd), L.ptr(sn_inv), S, ctx.group, Cc, 1e-5, L.ptr(sn_U),
+                   L.ptr(sn_V), K, L.ptr(coef), L.ptr(gw), st)
+        return dx, None, None, None, None, None, gw
 
 
 # ------------------------------------------------------------------------------------------------ elementwise / resampling

@@ -81,6 +81,37 @@ def test_encoder_forward(ctx, gold):
     assert rel(E.state_dict()["layer0.0.weight_u"], gold["E_layer0_u_after"]) < 1e-4
 
 
+def test_batched_encoder_equals_per_sample_calls(ctx):
+    """ConvEncoder.forward_samples == the reference's loop of one netE call per sample (pix2pix_model.py:285):
+    same mu, same advanced u/v buffers, same parameter gradients (incl. the spectral chain-rule term)."""
+    from seg2eye_b200.models import networks
+    sd = O.synth_state(O.encoder_shapes(ctx.oopt), ctx.seeds["E"])
+    style = ctx.batch["style_image"].cuda()
+    B = style.shape[0]
+    g = torch.Generator().manual_seed(3)
+    dmu = torch.randn(B, style.shape[1], 16, generator=g).cuda()
+    res = {}
+    for mode in ("loop", "batched"):
+        E = load(networks.ConvEncoder(ctx.opt), sd).train()
+        if mode == "loop":
+            mu = torch.stack([E(style[b])[0] for b in range(B)], 0)
+        else:
+            mu = E.forward_samples(style)[0]
+        (mu * dmu).sum().backward()
+        res[mode] = (mu.detach(), {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None},
+                     {k: v.clone() for k, v in E.state_dict().items() if k.endswith("_u") or k.endswith("_v")})
+    assert rel(res["batched"][0], res["loop"][0]) < 2e-3
+    for k, v in res["loop"][2].items():
+        assert rel(res["batched"][2][k], v) < 1e-5, k
+    assert set(res["batched"][1]) == set(res["loop"][1])
+    for k, v in res["loop"][1].items():
+        assert rel(res["batched"][1][k], v) < 2e-2, (k, rel(res["batched"][1][k], v))
+    # and against the CPU oracle's per-sample loop
+    with torch.no_grad():
+        w_o = O.encode_w({k: v.clone() for k, v in sd.items()}, ctx.batch["style_image"], ctx.oopt)
+    assert rel(res["batched"][0].mean(1), w_o) < TOL_ACT
+
+
 def test_generator_forward(ctx, gold):
     from seg2eye_b200.models import networks
     sd = O.synth_state(O.generator_shapes(ctx.oopt), ctx.seeds["G"])
