@@ -80,8 +80,8 @@ struct TapTable {
 
 // ================================================================================ forward-like kernel
 struct FwdParams {
-  int dbg;  // timing experiments only (debug key 3): bit0 skip TMA store, bit1 skip math, bit2 skip tmem ld
-  int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles;
+  int dbg;  // timing experiments only (debug key 3): bit0 skip TMA store
+  int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles, tiles_m;  // tiles_m = pixel tiles; num_tiles = ceil(tiles_m/MT)*tiles_n
   int TW, TH, TB;
   int Cout, kc_per_tap, act;
   int B, Ho, Wo;
@@ -92,14 +92,35 @@ struct FwdParams {
   TapTable taps;
 };
 
+// MT = number of 128-pixel sub-tiles a CTA processes per k-step against ONE weight tile.  The kernel is bound by the
+// bytes it can keep in flight (TMA latency x shared-memory capacity), so narrow N tiles get MT = 2: a 256 x 128 tile
+// moves the same bytes per FLOP as the 128 x 256 one (ncu: tensor pipe 42 % -> see profiles/).
 template <int BN>
 struct FwdCfg {
+  static constexpr int MT = BN == 256 ? 1 : 2;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 5 : 6);
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int STAGE_BYTES = MT * A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = 4;
+  static constexpr int TMEM_COLS = 2 * MT * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BUF_BYTES + 1024 + 256 + BN * 4;
 };
+
+// pixel sub-tile m -> tile origin; sub-tiles past the end land fully out of bounds (TMA zero-fills loads, clips stores)
+__device__ __forceinline__ void subtile_origin(const FwdParams& p, int m, int& w0, int& h0, int& b0) {
+  if (m >= p.tiles_m) {
+    w0 = 0;
+    h0 = 0;
+    b0 = p.tiles_b * p.TB + p.TB;
+    return;
+  }
+  const int w_idx = m % p.tiles_w;
+  m /= p.tiles_w;
+  const int h_idx = m % p.tiles_h;
+  const int b_idx = m / p.tiles_h;
+  w0 = w_idx * p.TW;
+  h0 = h_idx * p.TH;
+  b0 = b_idx * p.TB;
+}
 
 template <int ACT>
 __device__ __forceinline__ float act_t(float v) {
@@ -160,21 +181,21 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        int n_idx = t % p.tiles_n;
-        int m = t / p.tiles_n;
-        int w_idx = m % p.tiles_w;
-        m /= p.tiles_w;
-        int h_idx = m % p.tiles_h;
-        int b_idx = m / p.tiles_h;
-        const int w0 = w_idx * p.TW, h0 = h_idx * p.TH, b0 = b_idx * p.TB, n0 = n_idx * BN;
+        const int n0 = (t % p.tiles_n) * BN;
+        const int grp = t / p.tiles_n;
+        int w0[Cfg::MT], h0[Cfg::MT], b0[Cfg::MT];
+#pragma unroll
+        for (int j = 0; j < Cfg::MT; ++j) subtile_origin(p, grp * Cfg::MT + j, w0[j], h0[j], b0[j]);
         for (int tap = 0; tap < p.taps.n; ++tap) {
           const int dy = p.taps.dy[tap], dx = p.taps.dx[tap];
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sb = sa + A_STAGE_BYTES;
-            ptx::mbar_expect_tx(&full[stage], p.a_box_bytes + Cfg::B_STAGE_BYTES);
-            ptx::tma_load_4d(sa, &tmA, &full[stage], kc * BK, w0 + dx, h0 + dy, b0);
+            uint8_t* sb = sa + Cfg::MT * A_STAGE_BYTES;
+            ptx::mbar_expect_tx(&full[stage], Cfg::MT * p.a_box_bytes + Cfg::B_STAGE_BYTES);
+#pragma unroll
+            for (int j = 0; j < Cfg::MT; ++j)
+              ptx::tma_load_4d(sa + j * A_STAGE_BYTES, &tmA, &full[stage], kc * BK, w0[j] + dx, h0[j] + dy, b0[j]);
             ptx::tma_load_3d(sb, &tmB, &full[stage], kc * BK, n0, tap);
             if (++stage == Cfg::STAGES) {
               stage = 0;
@@ -194,18 +215,21 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::MT * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint32_t b_addr = a_addr + Cfg::MT * A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 32, 0, 1024);
-            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < Cfg::MT; ++j) {
+              const uint64_t ad = ptx::umma_desc_sw128(a_addr + j * A_STAGE_BYTES + k * 32, 0, 1024);
+              ptx::umma_bf16(d_tmem + (uint32_t)(j * BN), ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty[stage]);
           if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[acc]);
@@ -233,73 +257,74 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t acc_phase = 0;
     int buf = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      int n_idx = t % p.tiles_n;
-      int m = t / p.tiles_n;
-      int w_idx = m % p.tiles_w;
-      m /= p.tiles_w;
-      int h_idx = m % p.tiles_h;
-      int b_idx = m / p.tiles_h;
-      const int w0 = w_idx * p.TW, h0 = h_idx * p.TH, b0 = b_idx * p.TB, n0 = n_idx * BN;
+      const int n0 = (t % p.tiles_n) * BN;
+      const int grp = t / p.tiles_n;
       if (et < BN) s_bias[et] = (p.bias && n0 + et < p.Cout) ? __ldg(p.bias + n0 + et) : 0.f;
-      const bf16* mrow = nullptr;
-      if (p.mask) {
-        const int tw = row % p.TW, r2 = row / p.TW;
-        const int th = r2 % p.TH, tb = r2 / p.TH;
-        if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo)
-          mrow = p.mask + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
-      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 64; ++ch) {
-        const int nbase = n0 + ch * 64;
-        if (nbase >= p.Cout) break;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 64 + half * 32);
-        ptx::tmem_ld_32x32(taddr, r);
-        uint4 mk[4] = {make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u),
-                       make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u)};
-        if (mrow) {  // host guarantees Cout % 64 == 0 when a mask is given
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + half * 32) + j);
+      for (int j = 0; j < Cfg::MT; ++j) {
+        int w0, h0, b0;
+        subtile_origin(p, grp * Cfg::MT + j, w0, h0, b0);
+        const bf16* mrow = nullptr;
+        if (p.mask) {
+          const int tw = row % p.TW, r2 = row / p.TW;
+          const int th = r2 % p.TH, tb = r2 / p.TH;
+          if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo)
+            mrow = p.mask + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
         }
-        // the TMA store that last read this staging buffer must have finished reading it
-        if (store_thread) ptx::tma_store_wait_read<1>();
-        ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
-        ptx::tmem_ld_wait();
-        uint8_t* ob = out_buf + buf * OUT_BUF_BYTES + row * 128;
-        const float4* bsrc = reinterpret_cast<const float4*>(s_bias + ch * 64 + half * 32);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 64; ++ch) {
+          const int nbase = n0 + ch * 64;
+          if (nbase >= p.Cout) break;
+          uint32_t r[32];
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::MT * BN + j * BN + ch * 64 + half * 32);
+          ptx::tmem_ld_32x32(taddr, r);
+          uint4 mk[4] = {make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u),
+                         make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u)};
+          if (mrow) {  // host guarantees Cout % 64 == 0 when a mask is given
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b0v = bsrc[2 * j], b1v = bsrc[2 * j + 1];
-          uint32_t pk[4];
-          pk[0] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 0]), scale, b0v.x)),
-                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 1]), scale, b0v.y)));
-          pk[1] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 2]), scale, b0v.z)),
-                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 3]), scale, b0v.w)));
-          pk[2] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 4]), scale, b1v.x)),
-                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 5]), scale, b1v.y)));
-          pk[3] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 6]), scale, b1v.z)),
-                             act_t<ACT>(fmaf(__uint_as_float(r[8 * j + 7]), scale, b1v.w)));
-          if (p.mask) {  // keep a value only where the bf16 mask element is > 0 (sign clear and magnitude non-zero)
-            const uint32_t mw[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
-              const uint32_t keep = (((lo & 0x8000u) == 0u && (lo & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) |
-                                    (((hi & 0x8000u) == 0u && (hi & 0x7fffu) != 0u) ? 0xffff0000u : 0u);
-              pk[e] &= keep;
-            }
+            for (int i = 0; i < 4; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + half * 32) + i);
           }
-          *reinterpret_cast<uint4*>(ob + (((half * 4 + j) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          // the TMA store that last read this staging buffer must have finished reading it
+          if (store_thread) ptx::tma_store_wait_read<1>();
+          ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
+          ptx::tmem_ld_wait();
+          uint8_t* ob = out_buf + buf * OUT_BUF_BYTES + row * 128;
+          const float4* bsrc = reinterpret_cast<const float4*>(s_bias + ch * 64 + half * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b0v = bsrc[2 * i], b1v = bsrc[2 * i + 1];
+            uint32_t pk[4];
+            pk[0] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 0]), scale, b0v.x)),
+                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 1]), scale, b0v.y)));
+            pk[1] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 2]), scale, b0v.z)),
+                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 3]), scale, b0v.w)));
+            pk[2] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 4]), scale, b1v.x)),
+                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 5]), scale, b1v.y)));
+            pk[3] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 6]), scale, b1v.z)),
+                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 7]), scale, b1v.w)));
+            if (p.mask) {  // keep a value only where the bf16 mask element is > 0 (sign clear and magnitude non-zero)
+              const uint32_t mw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
+                const uint32_t keep = (((lo & 0x8000u) == 0u && (lo & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) |
+                                      (((hi & 0x8000u) == 0u && (hi & 0x7fffu) != 0u) ? 0xffff0000u : 0u);
+                pk[e] &= keep;
+              }
+            }
+            *reinterpret_cast<uint4*>(ob + (((half * 4 + i) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(2, FWD_EPI_THREADS);
+          if (store_thread && !(p.dbg & 1)) {
+            ptx::tma_store_4d(&tmY, out_buf + buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
+            ptx::tma_store_commit();
+          }
+          buf ^= 1;
         }
-        ptx::fence_proxy_async_smem();
-        ptx::named_bar_sync(2, FWD_EPI_THREADS);
-        if (store_thread && !(p.dbg & 1)) {
-          ptx::tma_store_4d(&tmY, out_buf + buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
-          ptx::tma_store_commit();
-        }
-        buf ^= 1;
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
@@ -356,7 +381,8 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.tiles_h = ceil_div(d->Ho, th);
   p.tiles_b = ceil_div(d->B, tb);
   p.tiles_n = ceil_div(d->Cout, BN);
-  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
+  p.num_tiles = ceil_div(p.tiles_m, Cfg::MT) * p.tiles_n;
   p.TW = tw;
   p.TH = th;
   p.TB = tb;

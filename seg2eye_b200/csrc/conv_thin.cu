@@ -238,20 +238,25 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
 template <int TMAX, int MAXT>
 __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict__ A, const bf16* __restrict__ S, float* __restrict__ dwp,
                                                          int Bn, int HA, int WA, int Cw, int HS, int WS, int Cs, const ThinGeom g,
-                                                         int thin_x, long long pix_per_block) {
+                                                         int thin_x, long long pix_per_block, int nth_pad, int pl_count) {
+  // threads = pl_count pixel lanes x nth_pad (>= ncw*Cs, multiple of 32) channel slots; each pixel lane walks its own
+  // contiguous slice of the block's pixel range so that small channel counts still fill the block
   const int ncw = Cw >> 3;
-  const int tid = threadIdx.x;
-  const int cw = tid % ncw, cs = tid / ncw;
+  const int slot = threadIdx.x % nth_pad, pl = threadIdx.x / nth_pad;
+  const int cw = slot % ncw, cs = slot / ncw;
   const bool active = cs < Cs;
   const long long PA = (long long)Bn * HA * WA;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  const long long p1 = min(PA, p0 + pix_per_block);
+  const long long b0 = (long long)blockIdx.x * pix_per_block;
+  const long long b1 = min(PA, b0 + pix_per_block);
+  const long long per_lane = (b1 - b0 + pl_count - 1) / pl_count;
+  const long long p0 = min(b1, b0 + (long long)pl * per_lane);
+  const long long p1 = min(b1, p0 + per_lane);
   float acc[TMAX][8];
 #pragma unroll
   for (int t = 0; t < TMAX; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-  if (active) {
+  if (active && p0 < p1) {
     const int sgn = thin_x ? 1 : -1;
     int w = (int)(p0 % WA);
     long long r0 = p0 / WA;
@@ -407,18 +412,22 @@ int s2e_thin_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dw
   const int HS = thin_x ? d->Hi : d->Ho, WS = thin_x ? d->Wi : d->Wo, Cs = thin_x ? d->Cin : d->Cout;
   const long long PA = (long long)d->B * HA * WA;
   if (PA == 0) return 1;
-  int threads = (Cw / 8) * Cs;
-  threads = ((threads + 31) / 32) * 32;
+  int nth_pad = (Cw / 8) * Cs;
+  nth_pad = ((nth_pad + 31) / 32) * 32;
+  int pl = 256 / nth_pad;
+  if (pl < 1) pl = 1;
+  if (d->ntaps > 9 && pl * nth_pad > 128) pl = 128 / nth_pad > 0 ? 128 / nth_pad : 1;
+  const int threads = pl * nth_pad;
   long long blocks = (long long)s2e_num_sms() * (threads <= 128 ? 16 : (threads <= 256 ? 8 : 4));
   long long ppb = (PA + blocks - 1) / blocks;
-  if (ppb < 64) ppb = 64;
+  if (ppb < 64LL * pl) ppb = 64LL * pl;
   blocks = (PA + ppb - 1) / ppb;
   if (d->ntaps <= 4)
-    thin_wgrad_kernel<4, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb);
+    thin_wgrad_kernel<4, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
   else if (d->ntaps <= 9)
-    thin_wgrad_kernel<9, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb);
+    thin_wgrad_kernel<9, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
   else if (threads <= 128)
-    thin_wgrad_kernel<16, 128><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb);
+    thin_wgrad_kernel<16, 128><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
   else
     return 0;
   S2E_LAUNCH_CHECK();
