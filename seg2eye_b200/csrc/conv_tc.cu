@@ -642,12 +642,26 @@ int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp,
     p.taps.dy[i] = d->tap_dy[i];
     p.taps.dx[i] = d->tap_dx[i];
   }
+  // split-K so that the CTA count fills whole waves of SMs (a 297-CTA launch on 148 SMs runs 3 waves, the last with
+  // one CTA): try 1..4 waves, keep >= 4 pixel tiles per CTA, take the best fill (ties -> fewer waves, fewer atomics)
   const int base = d->ntaps * p.mt * p.nt;
-  int ksplit = ceil_div(2 * s2e_num_sms(), base);
-  int max_split = p.kt_total / 4;  // keep at least ~4 pipeline stages of work per CTA
+  const int sms = s2e_num_sms();
+  int max_split = p.kt_total / 4;
   if (max_split < 1) max_split = 1;
-  if (ksplit > max_split) ksplit = max_split;
-  if (ksplit < 1) ksplit = 1;
+  int ksplit = 1;
+  double best_fill = -1.0;
+  for (int w = 1; w <= 4; ++w) {
+    int ks = (sms * w) / base;
+    if (ks < 1) ks = 1;
+    if (ks > max_split) ks = max_split;
+    const int ctas = base * ks;
+    const int waves = ceil_div(ctas, sms);
+    const double fill = (double)ctas / ((double)waves * sms);
+    if (fill > best_fill + 0.02) {
+      best_fill = fill;
+      ksplit = ks;
+    }
+  }
   p.ksplit = ksplit;
   static bool attr_set = false;
   if (!attr_set) {

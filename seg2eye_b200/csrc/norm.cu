@@ -10,9 +10,11 @@ constexpr int NT = 256;
 
 // ---------------------------------------------------------------- per-channel sum / sum of squares
 // grid = (chunks, G) ; G = B when per_sample else 1 (then the chunk range spans all samples)
-template <int NACC, typename F>
+// body(p, c, acc) consumes one pixel; body4(p, stride, c, acc) consumes pixels p, p+stride, p+2 stride, p+3 stride with all
+// of their loads issued before the first use (memory-level parallelism).
+template <int NACC, typename F, typename F4>
 __device__ __forceinline__ void block_channel_reduce(int C, long long pix_begin, long long pix_end, double* out /*[NACC][C]*/,
-                                                     F&& body) {
+                                                     F&& body, F4&& body4) {
   extern __shared__ float red[];  // [NT][NACC*8] worst case handled by looping
   const int cg = C >> 3;          // channel groups of 8
   const int tid = threadIdx.x;
@@ -27,7 +29,9 @@ __device__ __forceinline__ void block_channel_reduce(int C, long long pix_begin,
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
     if (my_lane < lanes) {
-      for (long long p = pix_begin + my_lane; p < pix_end; p += lanes) body(p, (cg0 + my_cg) * 8, acc);
+      long long p = pix_begin + my_lane;
+      for (; p + 3LL * lanes < pix_end; p += 4LL * lanes) body4(p, (long long)lanes, (cg0 + my_cg) * 8, acc);
+      for (; p < pix_end; p += lanes) body(p, (cg0 + my_cg) * 8, acc);
     }
     // combine pixel lanes through smem: layout [lane][ncg][NACC*8]
     for (int a = 0; a < NACC; ++a) {
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(NT) stats_kernel(const bf16* __restrict__ x, i
   const long long chunk = (span + gridDim.x - 1) / gridDim.x;
   const long long b0 = base + (long long)blockIdx.x * chunk;
   const long long b1 = min(base + span, b0 + chunk);
-  block_channel_reduce<2>(C, b0, b1, acc + (size_t)g * 2 * C, [&](long long p, int c, float(*a)[8]) {
+  auto one = [&](long long p, int c, float(*a)[8]) {
     float f[8];
     unpack8(ld_stream8(x + p * C + c), f);
 #pragma unroll
@@ -62,7 +66,23 @@ __global__ void __launch_bounds__(NT) stats_kernel(const bf16* __restrict__ x, i
       a[0][j] += f[j];
       a[1][j] = fmaf(f[j], f[j], a[1][j]);
     }
-  });
+  };
+  auto four = [&](long long p, long long st, int c, float(*a)[8]) {
+    bf16x8 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = ld_stream8(x + (p + i * st) * C + c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[0][j] += f[j];
+        a[1][j] = fmaf(f[j], f[j], a[1][j]);
+      }
+    }
+  };
+  block_channel_reduce<2>(C, b0, b1, acc + (size_t)g * 2 * C, one, four);
 }
 
 // in_scale (optional, one value per `group` consecutive statistic groups): statistics are those of x * in_scale without
@@ -166,7 +186,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
   const long long b1 = min((long long)(b + 1) * HW, b0 + chunk);
   const float* mu = mean + (per_sample ? b * C : 0);
   const float* rs = rstd + (per_sample ? b * C : 0);
-  block_channel_reduce<4>(C, b0, b1, racc + (size_t)b * 4 * C, [&](long long p, int c, float(*a)[8]) {
+  auto one = [&](long long p, int c, float(*a)[8]) {
     float df[8], of[8], xf[8], gf[8];
     unpack8(ld_stream8(dout + p * C + c), df);
     unpack8(ld_stream8(x + p * C + c), xf);
@@ -184,7 +204,12 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
       a[2][j] = fmaf(g, xf[j], a[2][j]);
       a[3][j] += g;
     }
-  });
+  };
+  auto four = [&](long long p, long long st, int c, float(*a)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) one(p + i * st, c, a);   // the compiler hoists the independent streaming loads
+  };
+  block_channel_reduce<4>(C, b0, b1, racc + (size_t)b * 4 * C, one, four);
 }
 
 // fold the per-sample sums: m1/m2 per stat group (float [G][2][C]) and dstyle [B][2C]
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const bf16* __r
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
   const long long b1 = min((long long)(b + 1) * HW, b0 + chunk);
-  block_channel_reduce<2>(C, b0, b1, racc + (size_t)b * 2 * C, [&](long long p, int c, float(*a)[8]) {
+  auto one = [&](long long p, int c, float(*a)[8]) {
     float df[8], yf[8], xf[8];
     unpack8(ld_stream8(dy + p * C + c), df);
     unpack8(ld_stream8(x + p * C + c), xf);
@@ -308,7 +333,12 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const bf16* __r
       a[0][j] += g;
       a[1][j] = fmaf(g, xh, a[1][j]);
     }
-  });
+  };
+  auto four = [&](long long p, long long st, int c, float(*a)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) one(p + i * st, c, a);
+  };
+  block_channel_reduce<2>(C, b0, b1, racc + (size_t)b * 2 * C, one, four);
 }
 
 __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
