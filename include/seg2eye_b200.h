@@ -99,13 +99,15 @@ int s2e_tapconv_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float*
  * Several OIHW tensors can be packed side by side along Cout (the fused gamma|beta GEMM): the packed tensor has
  * Cout_total output channels and this call fills [co_offset, co_offset+Cout). */
 int s2e_pack_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int stride, int pad, int transposed,
-                    int Cout_total, int co_offset, void* out_bf16, void* stream);
+                    int Cout_total, int co_offset, int cin_pad, void* out_bf16, void* stream);
+/* cin_pad (0 = none): the activations carry cin_pad >= Cin channels (extra ones zero), e.g. the 5-channel D input
+ * stored with 16 channels so that discriminator.py:84's first conv also runs on the tensor-core path. */
 int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, int* dx); /* host helper */
 /* tap-major fp32 weight gradient -> OIHW, with the spectral-norm chain rule when u != NULL:
  * dW_orig = inv_sigma * (G - inv_sigma * <G, W_orig> u v^T).  `dot` is a 1-float device scratch. */
 int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, int Cout_total,
-                     int co_offset, const float* w_orig, const float* u, const float* v, const float* inv_sigma,
-                     float* dot, float* dw_oihw, int accumulate, void* stream);
+                     int co_offset, int cin_pad, const float* w_orig, const float* u, const float* v,
+                     const float* inv_sigma, float* dot, float* dw_oihw, int accumulate, void* stream);
 /* torch.nn.utils.spectral_norm power iteration (one step) on W viewed as (rows, cols):
  * v <- normalize(W^T u), u <- normalize(W v), inv_sigma <- 1 / (u . W v); eps 1e-12. scratch: rows + cols + ceil(rows/64)*cols floats
  * (fixed-order partial sums: the iteration is bitwise reproducible).

@@ -36,9 +36,9 @@ _SIGS = {
     "s2e_nhwc_bf16_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_tapconv_fwd": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _I, _P],
     "s2e_tapconv_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _I, _P],
-    "s2e_pack_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "s2e_pack_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "s2e_packed_taps": [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)],
-    "s2e_unpack_wgrad": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
+    "s2e_unpack_wgrad": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "s2e_spectral_power_iter": [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P],
     "s2e_sn_in_correction": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P, _P, _P],
     "s2e_space_to_depth": [_P, _I, _I, _I, _I, _P, _P],

@@ -292,15 +292,25 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
         }
       }
     }
+  }
+  // combine the pixel lanes of the block in shared memory, then one atomic per output element per block
+  extern __shared__ float red[];  // [pl_count][nth_pad] per (t, j) pass
+  for (int t = 0; t < g.ntaps; ++t) {
 #pragma unroll
-    for (int t = 0; t < TMAX; ++t) {
-      if (t < g.ntaps) {
+    for (int j = 0; j < 8; ++j) {
+      float v = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = cw * 8 + j;
-          const long long o = thin_x ? ((long long)t * Cw + c) * Cs + cs : ((long long)t * Cs + cs) * Cw + c;
-          atomicAdd(dwp + o, acc[t][j]);
-        }
+      for (int tt = 0; tt < TMAX; ++tt)
+        if (tt == t) v = acc[tt][j];
+      __syncthreads();
+      red[pl * nth_pad + slot] = v;
+      __syncthreads();
+      if (pl == 0 && active) {
+        float sum = 0.f;
+        for (int l = 0; l < pl_count; ++l) sum += red[l * nth_pad + slot];
+        const int c = cw * 8 + j;
+        const long long o = thin_x ? ((long long)t * Cw + c) * Cs + cs : ((long long)t * Cs + cs) * Cw + c;
+        atomicAdd(dwp + o, sum);
       }
     }
   }
@@ -418,16 +428,17 @@ int s2e_thin_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dw
   if (pl < 1) pl = 1;
   if (d->ntaps > 9 && pl * nth_pad > 128) pl = 128 / nth_pad > 0 ? 128 / nth_pad : 1;
   const int threads = pl * nth_pad;
-  long long blocks = (long long)s2e_num_sms() * (threads <= 128 ? 16 : (threads <= 256 ? 8 : 4));
+  long long blocks = (long long)s2e_num_sms() * (threads <= 128 ? 8 : (threads <= 256 ? 4 : 2));
   long long ppb = (PA + blocks - 1) / blocks;
   if (ppb < 64LL * pl) ppb = 64LL * pl;
   blocks = (PA + ppb - 1) / ppb;
+  const size_t red_bytes = (size_t)threads * sizeof(float);
   if (d->ntaps <= 4)
-    thin_wgrad_kernel<4, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
+    thin_wgrad_kernel<4, 512><<<(unsigned)blocks, threads, red_bytes, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
   else if (d->ntaps <= 9)
-    thin_wgrad_kernel<9, 512><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
+    thin_wgrad_kernel<9, 512><<<(unsigned)blocks, threads, red_bytes, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
   else if (threads <= 128)
-    thin_wgrad_kernel<16, 128><<<(unsigned)blocks, threads, 0, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
+    thin_wgrad_kernel<16, 128><<<(unsigned)blocks, threads, red_bytes, stream>>>(A, S, dwp, d->B, HA, WA, Cw, HS, WS, Cs, g, thin_x, ppb, nth_pad, pl);
   else
     return 0;
   S2E_LAUNCH_CHECK();

@@ -163,11 +163,12 @@ __global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, int C, int H, int W
 struct PackGeom {
   int Cout, Cin, kh, kw, stride, pad;
   int Ctot, co_off;  // several OIHW tensors may be packed side by side along Cout (gamma | beta)
+  int CinPad;        // packed input-channel count (>= Cin; extra channels carry zero weights)
   int amin, bmin, na, nb;  // stride-2 tap grid
 };
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, PackGeom g, int transposed, long long n, bf16* __restrict__ out) {
-  const int CinP = g.stride == 2 ? 4 * g.Cin : g.Cin;
+  const int CinP = g.stride == 2 ? 4 * g.CinPad : g.CinPad;
   GRID_STRIDE(i, n) {
     int cp, co;
     long long r0 = i;
@@ -192,25 +193,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, PackGeom g, int 
       ci = cp;
     } else {
       const int a = g.amin + t / g.nb, b = g.bmin + t % g.nb;
-      const int ph = cp / g.Cin;
-      ci = cp % g.Cin;
+      const int ph = cp / g.CinPad;
+      ci = cp % g.CinPad;
       r = 2 * a + (ph >> 1) + g.pad;
       s = 2 * b + (ph & 1) + g.pad;
     }
     float v = 0.f;
-    if (r >= 0 && r < g.kh && s >= 0 && s < g.kw) v = w[(((long long)co * g.Cin + ci) * g.kh + r) * g.kw + s];
+    if (ci < g.Cin && r >= 0 && r < g.kh && s >= 0 && s < g.kw) v = w[(((long long)co * g.Cin + ci) * g.kh + r) * g.kw + s];
     out[oidx] = __float2bfloat16(v);
   }
 }
 
 __device__ __forceinline__ long long packed_index(const PackGeom& g, int co, int ci, int r, int s) {
   co += g.co_off;
-  if (g.stride == 1) return ((long long)(r * g.kw + s) * g.Ctot + co) * g.Cin + ci;
+  if (g.stride == 1) return ((long long)(r * g.kw + s) * g.Ctot + co) * g.CinPad + ci;
   const int rr = r - g.pad, ss = s - g.pad;
   const int i = ((rr % 2) + 2) % 2, j = ((ss % 2) + 2) % 2;
   const int a = (rr - i) / 2, b = (ss - j) / 2;
   const int t = (a - g.amin) * g.nb + (b - g.bmin);
-  return ((long long)t * g.Ctot + co) * (4 * g.Cin) + (i * 2 + j) * g.Cin + ci;
+  return ((long long)t * g.Ctot + co) * (4 * g.CinPad) + (i * 2 + j) * g.CinPad + ci;
 }
 
 __global__ void wgrad_dot_kernel(const float* __restrict__ dwp, const float* __restrict__ w, PackGeom g, long long n, float* dot) {
@@ -680,8 +681,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-PackGeom make_pack_geom(int Cout, int Cin, int kh, int kw, int stride, int pad, int Ctot = 0, int co_off = 0) {
+PackGeom make_pack_geom(int Cout, int Cin, int kh, int kw, int stride, int pad, int Ctot = 0, int co_off = 0, int cin_pad = 0) {
   PackGeom g;
+  g.CinPad = cin_pad > Cin ? cin_pad : Cin;
   g.Ctot = Ctot > 0 ? Ctot : Cout;
   g.co_off = co_off;
   g.Cout = Cout;
@@ -798,20 +800,20 @@ int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, in
   return S2E_OK;
 }
 int s2e_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, int stride, int pad, int transposed, int Cout_total,
-                    int co_offset, void* out, void* stream) {
+                    int co_offset, int cin_pad, void* out, void* stream) {
   S2E_REQUIRE(stride == 1 || stride == 2, "pack_weight: stride must be 1 or 2");
-  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad, Cout_total, co_offset);
+  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad, Cout_total, co_offset, cin_pad);
   const int T = stride == 1 ? kh * kw : g.na * g.nb;
-  const long long n = (long long)T * Cout * (stride == 2 ? 4 * Cin : Cin);
+  const long long n = (long long)T * Cout * (stride == 2 ? 4 * g.CinPad : g.CinPad);
   pack_weight_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(w, g, transposed, n, (bf16*)out);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
 int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, int Cout_total, int co_offset,
-                     const float* w_orig, const float* u, const float* v, const float* inv_sigma, float* dot, float* dw,
-                     int accumulate, void* stream) {
+                     int cin_pad, const float* w_orig, const float* u, const float* v, const float* inv_sigma, float* dot,
+                     float* dw, int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad, Cout_total, co_offset);
+  PackGeom g = make_pack_geom(Cout, Cin, kh, kw, stride, pad, Cout_total, co_offset, cin_pad);
   const long long n = (long long)Cout * Cin * kh * kw;
   if (u) {
     S2E_REQUIRE(v && inv_sigma && dot && w_orig, "unpack_wgrad: spectral args incomplete");

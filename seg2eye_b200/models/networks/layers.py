@@ -49,6 +49,9 @@ class Conv2d(nn.Module):
 
     def forward_nhwc(self, x, act=None):
         cfg = self.cfg if act is None else self.cfg._replace(act=act)
+        if x.shape[-1] != self.in_channels:   # zero-padded activation channels (e.g. the 16-channel D input)
+            assert x.shape[-1] > self.in_channels, "input has fewer channels than the layer expects"
+            cfg = cfg._replace(cin_pad=x.shape[-1])
         biases = (self.bias,) if self.bias is not None else ()
         return ops.tap_conv(x, cfg, (self.master_weight(),), biases, self.sn_state())
 

@@ -226,7 +226,9 @@ class Pix2PixModel(torch.nn.Module):
 
     def discriminate(self, input_semantics, fake_image, real_image):
         # both concatenations of the reference (pix2pix_model.py:328-338) are one layout kernel
-        fake_and_real = ops.MakeDInputFn.apply(input_semantics, fake_image, real_image)
+        # channels zero-padded to 16 so that D's first 4x4-s2 convolution (5 -> 64) is tensor-core shaped after the
+        # space-to-depth step (4*16 = 64 input channels); the padded channels carry zero weights
+        fake_and_real = ops.MakeDInputFn.apply(input_semantics, fake_image, real_image, 16)
         discriminator_out = self.netD.forward_nhwc(fake_and_real)
         return self.divide_pred(discriminator_out)
 

@@ -15,7 +15,8 @@ from . import _lib as L
 BF16 = torch.bfloat16
 F32 = torch.float32
 
-ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in", defaults=(False,))
+ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad", defaults=(False, 0))
+# cin_pad: the activations carry cin_pad >= Cin channels (zero padded), packed weights get zero columns for them
 # relu_in: the input of this convolution is the output of a ReLU whose backward is fused into our data-gradient epilogue
 
 _state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False}
@@ -138,7 +139,7 @@ def packed_weights(weights, cfg, transposed):
     """bf16 tap-major copy of one or more OIHW fp32 master weights (concatenated along Cout); cached until a
     parameter changes.  Entries hold weak references so a recycled id() can never alias a dead tensor."""
     import weakref
-    key = (tuple(id(w) for w in weights), transposed, cfg.stride, cfg.pad)
+    key = (tuple(id(w) for w in weights), transposed, cfg.stride, cfg.pad, cfg.cin_pad)
     ver = (tuple(w._version for w in weights), tuple(w.data_ptr() for w in weights), _state["weights_epoch"])
     hit = _pack_cache.get(key)
     if hit is not None and not all(r() is w for r, w in zip(hit[0], weights)):
@@ -146,17 +147,18 @@ def packed_weights(weights, cfg, transposed):
     if hit is not None and hit[1] == ver:
         return hit[2]
     cin = weights[0].shape[1]
-    cinp = cin * 4 if cfg.stride == 2 else cin
+    cin_eff = max(cin, cfg.cin_pad)
+    cinp = cin_eff * 4 if cfg.stride == 2 else cin_eff
     ctot = sum(w.shape[0] for w in weights)
     ntaps = len(conv_taps(cfg))
     n = ntaps * ctot * cinp
-    buf = hit[2] if (hit is not None and hit[2].numel() == n) else torch.empty(n, dtype=BF16, device=weights[0].device)
+    buf = hit[2] if (hit is not None and hit[2].numel() == n) else torch.zeros(n, dtype=BF16, device=weights[0].device)
     off = 0
     for w in weights:
         wd = w.detach()
         assert wd.is_contiguous() and wd.dtype == F32
         L.call("s2e_pack_weight", L.ptr(wd), wd.shape[0], cin, cfg.kh, cfg.kw, cfg.stride, cfg.pad, int(transposed),
-               ctot, off, L.ptr(buf), L.stream())
+               ctot, off, cfg.cin_pad, L.ptr(buf), L.stream())
         off += wd.shape[0]
     if len(_pack_cache) > 4096:
         for k in [k for k, v in _pack_cache.items() if any(r() is None for r in v[0])]:
@@ -188,7 +190,8 @@ class TapConvFn(torch.autograd.Function):
         x = _c(x)
         assert x.dtype == BF16 and x.dim() == 4
         B, Hi, Wi, Cin = x.shape
-        assert Cin == weights[0].shape[1], "channel mismatch: x has %d, weight expects %d" % (Cin, weights[0].shape[1])
+        assert Cin == max(weights[0].shape[1], cfg.cin_pad), "channel mismatch: x has %d, weight expects %d" % (
+            Cin, max(weights[0].shape[1], cfg.cin_pad))
         xs = space_to_depth(x) if cfg.stride == 2 else x
         _, His, Wis, Cinp = xs.shape
         Ho, Wo = conv_out_hw(cfg, Hi, Wi)
@@ -202,7 +205,7 @@ class TapConvFn(torch.autograd.Function):
         y = torch.empty(B, Ho, Wo, Cout, dtype=BF16, device=x.device)
         d = _desc(B, His, Wis, Cinp, Ho, Wo, Cout, taps, cfg.act)
         impl = _pick(Cinp % 64 == 0 and Cout % 8 == 0)
-        flops = 2.0 * B * Ho * Wo * Cout * Cin * cfg.kh * cfg.kw
+        flops = 2.0 * B * Ho * Wo * Cout * weights[0].shape[1] * cfg.kh * cfg.kw
         if impl == L.IMPL_TC:
             _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream(),
                         tag="fwd B%d %dx%d Cin%d Cout%d T%d" % (B, Ho, Wo, Cinp, Cout, len(taps)))
@@ -270,7 +273,7 @@ class TapConvFn(torch.autograd.Function):
                 if need_w[i]:
                     g = torch.empty_like(w)
                     L.call("s2e_unpack_wgrad", L.ptr(dwp), w.shape[0], w.shape[1], cfg.kh, cfg.kw, cfg.stride, cfg.pad,
-                           Cout, off, L.ptr(w.detach()), L.ptr(sn[0]) if sn else None, L.ptr(sn[1]) if sn else None,
+                           Cout, off, cfg.cin_pad, L.ptr(w.detach()), L.ptr(sn[0]) if sn else None, L.ptr(sn[1]) if sn else None,
                            L.ptr(inv_sigma), L.ptr(dot), L.ptr(g), 0, st)
                     gw[i] = g
                 off += w.shape[0]
@@ -668,13 +671,15 @@ class MakeDInputFn(torch.autograd.Function):
     """cat([cat([seg,fake],1), cat([seg,real],1)], 0) as (2B,H,W,nc+1) bf16 (pix2pix_model.py:328-338)."""
 
     @staticmethod
-    def forward(ctx, seg, fake, real):
+    def forward(ctx, seg, fake, real, cpad=0):
         seg, fake, real = _c(seg.float()), _c(fake.float()), _c(real.float())
         B, nc, H, W = seg.shape
         assert fake.shape == (B, 1, H, W) and real.shape == (B, 1, H, W), (fake.shape, real.shape, seg.shape)
-        out = torch.empty(2 * B, H, W, nc + 1, dtype=BF16, device=seg.device)
-        L.call("s2e_make_d_input", L.ptr(seg), L.ptr(fake), L.ptr(real), B, nc, H, W, nc + 1, L.ptr(out), L.stream())
+        cpad = max(cpad, nc + 1)
+        out = torch.empty(2 * B, H, W, cpad, dtype=BF16, device=seg.device)
+        L.call("s2e_make_d_input", L.ptr(seg), L.ptr(fake), L.ptr(real), B, nc, H, W, cpad, L.ptr(out), L.stream())
         ctx.dims = (B, nc, H, W)
+        ctx.cpad = cpad
         return out
 
     @staticmethod
@@ -684,8 +689,8 @@ class MakeDInputFn(torch.autograd.Function):
         dfake = None
         if ctx.needs_input_grad[1]:
             dfake = torch.empty(B, 1, H, W, dtype=F32, device=dout.device)
-            L.call("s2e_d_input_grad", L.ptr(dout), B, nc, H, W, nc + 1, L.ptr(dfake), L.stream())
-        return None, dfake, None
+            L.call("s2e_d_input_grad", L.ptr(dout), B, nc, H, W, ctx.cpad, L.ptr(dfake), L.stream())
+        return None, dfake, None, None
 
 
 class TanhFn(torch.autograd.Function):

@@ -211,6 +211,29 @@ def test_relu_backward_fused_into_dgrad_epilogue(S, impl_name):
     assert rel(wc.grad, wr.grad) < TOL_ACT
 
 
+def test_channel_padded_input_runs_d_first_layer_on_tensor_cores(S):
+    """D model0 (5 -> 64, 4x4 s2 p2, LeakyReLU): activations zero-padded to 16 channels, weights keep their 5."""
+    L, ops = S
+    g = torch.Generator().manual_seed(13)
+    B, Cin, Cpad, Cout, H, W = 2, 5, 16, 64, 21, 18
+    x = bf(torch.randn(B, Cin, H, W, generator=g))
+    w = bf(torch.randn(Cout, Cin, 4, 4, generator=g) / (Cin * 16) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    yr = F.leaky_relu(F.conv2d(xr, wr, br, stride=2, padding=2), 0.2)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xp = torch.zeros(B, Cpad, H, W)
+    xp[:, :Cin] = x
+    xc = nhwc(xp).requires_grad_()
+    wc, bc = w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y = ops.tap_conv(xc, ops.ConvCfg(4, 4, 2, 2, L.ACT_LRELU, False, Cpad), (wc,), (bc,))
+    y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < TOL_ACT
+    assert rel(nchw(xc.grad)[:, :Cin], xr.grad) < TOL_ACT and float(nchw(xc.grad)[:, Cin:].abs().max()) == 0.0
+    assert rel(wc.grad, wr.grad) < TOL_ACT and rel(bc.grad, br.grad) < TOL_ACT
+
+
 def test_conv_tcgen05_large_k_many_tiles(S):
     L, ops = S
     conv_case(S, L.IMPL_TC, 4, 512, 512, 20, 16, 3, 1, 1, 0, seed=3)         # K = 4608, persistent loop > 1 tile/CTA
