@@ -43,6 +43,13 @@ def make_opts(res, batch):
     return oopt, SimpleNamespace(**d)
 
 
+def workload_config(res, batch, world):
+    return {"workload": "Seg2Eye full G+D training step (SPADEStyle G, multiscale PatchGAN D, GAN+feat-match+L1), "
+                        "%s = %dx%d, per-GPU batch %d, ngf=ndf=64" % (res, round(RES[res][0] / RES[res][1]), RES[res][0], batch),
+            "global_batch": batch * world, "parallelism": "dp%d" % world,
+            "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2"}
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -216,11 +223,7 @@ def run_ours(args):
             "metric": "G+D train images/sec", "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Seg2Eye full G+D training step (SPADEStyle G, multiscale PatchGAN D, GAN+feat-match+L1), "
-                                   "%s = %dx%d, per-GPU batch %d, ngf=ndf=64" % (
-                                       args.res, round(RES[args.res][0] / RES[args.res][1]), RES[args.res][0], args.batch),
-                       "global_batch": args.batch * world, "parallelism": "dp%d" % world,
-                       "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2"},
+            "config": workload_config(args.res, args.batch, world),
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
@@ -234,7 +237,9 @@ def run_ours(args):
                          "peak_source": peaks["source"] + " (sustained bf16 cuBLAS; burst %.0f)" % peaks["tf"]},
             "roofline_norm": {"bound": "hbm", "achieved": norm_gbs, "peak": peaks["hbm"], "unit": "GB/s",
                               "frac": norm_gbs / peaks["hbm"], "kernel": "spade_style_fwd_kernel (8 B/element)",
-                              "launches": prof["norm_n"]},
+                              "launches": prof["norm_n"],
+                              "traffic": 1.983e9, "traffic_note": "ncu --set full, launch B16 HW245760 C64: dram read 1.510 GB + write "
+                              "0.473 GB vs 2.013 GB algorithmic (profiles/r01_ncu_spade_style_fwd_C64_fullres.txt)"},
             "step_tflops_equiv": imgs * STEP_TFLOP[args.res] / (ms / 1e3),
         }
     if world > 1:
@@ -262,12 +267,14 @@ def main():
             return
         steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
         r = cpu_reference(args.res, steps, warmup)
-        cb = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cb = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+              "sample": r["sample"] + " (oracle/seg2eye_oracle.py: fp32 PyTorch-CPU restatement of the reference; the reference "
+                                      "itself is Python and its checkout does not exist on the GPU box)"}
         print(json.dumps({
             "impl": "reference", "metric": "G+D train images/sec", "value": r["value"], "unit": "images/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "Seg2Eye full G+D training step, %s, batch 1, oracle port on host CPU" % args.res},
+            "config": workload_config(args.res, args.batch, max(1, args.gpus)),
             "cpu_baseline": cb,
             "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
