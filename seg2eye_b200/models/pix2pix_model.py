@@ -121,6 +121,8 @@ class Pix2PixModel(torch.nn.Module):
         # D's parameter gradients from this step are discarded by the reference (zero_grad before the D step)
         with ops.skip_weight_grads():
             pred_fake, pred_real = self.discriminate(input_semantics, fake_image, target_image)
+        d_full = getattr(self, '_last_d_out', None)   # un-split [fake ; real] features of the same call
+        self._last_d_out = None
         G_losses['GAN'] = self.criterionGAN(pred_fake, True, for_discriminator=False)
         if self.opt.lambda_l2:
             l2_loss = self.criterionL2(fake_image, target_image)
@@ -149,7 +151,12 @@ class Pix2PixModel(torch.nn.Module):
             GAN_Feat_loss = torch.zeros(1, device=fake_image.device)
             for i in range(num_D):
                 for j in range(len(pred_fake[i]) - 1):
-                    unweighted = self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
+                    if d_full is not None:
+                        # nn.L1Loss(pred_fake, pred_real.detach()) evaluated on the un-split tensor (no slice copies)
+                        t = networks.loss._flat(d_full[i][j])
+                        unweighted = ops.HalvesLossFn.apply(t, L.RED_L1, 2.0 / t.numel()).view(())
+                    else:
+                        unweighted = self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
                     GAN_Feat_loss = GAN_Feat_loss + unweighted * self.opt.lambda_feat / num_D
             G_losses['GAN_Feat'] = GAN_Feat_loss
         return G_losses, fake_image
@@ -230,6 +237,7 @@ class Pix2PixModel(torch.nn.Module):
         # space-to-depth step (4*16 = 64 input channels); the padded channels carry zero weights
         fake_and_real = ops.MakeDInputFn.apply(input_semantics, fake_image, real_image, 16)
         discriminator_out = self.netD.forward_nhwc(fake_and_real)
+        self._last_d_out = discriminator_out
         return self.divide_pred(discriminator_out)
 
     def divide_pred(self, pred):

@@ -778,3 +778,33 @@ class ReduceLossFn(torch.autograd.Function):
 
 def reduce_loss(x, y, kind, coef):
     return ReduceLossFn.apply(x, y, kind, float(coef))
+
+
+class HalvesLossFn(torch.autograd.Function):
+    """Feature-matching term on a discriminator feature that holds [fake ; real] along the batch axis
+    (pix2pix_model.py:233-241): coef * sum f(t[:B] - t[B:]) with the real half detached.  Works on the whole tensor so
+    that autograd needs no slice / zero-pad / copy kernels: backward writes the full-size gradient in one pass."""
+
+    @staticmethod
+    def forward(ctx, t, kind, coef):
+        t = _c(t)
+        n2 = t.numel() // 2
+        f32 = int(t.dtype == F32)
+        out = torch.empty(1, dtype=F32, device=t.device)
+        flat = t.view(-1)
+        L.call("s2e_reduce_loss", L.ptr(flat), L.ptr(flat[n2:]), n2, f32, kind, coef, L.ptr(out), 0, L.stream())
+        ctx.kind, ctx.coef, ctx.f32 = kind, coef, f32
+        ctx.save_for_backward(t)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (t,) = ctx.saved_tensors
+        gout = _c(gout.float())
+        n2 = t.numel() // 2
+        dx = torch.empty_like(t)
+        flat, dflat = t.view(-1), dx.view(-1)
+        dflat[n2:].zero_()
+        L.call("s2e_reduce_loss_bwd", L.ptr(flat), L.ptr(flat[n2:]), n2, ctx.f32, ctx.kind, ctx.coef, L.ptr(gout), L.ptr(dflat),
+               0, L.stream())
+        return dx, None, None
