@@ -168,6 +168,7 @@ class Pix2PixModel(torch.nn.Module):
             fake_image = fake_image.detach()
         # the reference marks fake_image as requiring grad (pix2pix_model.py:254) but never reads that gradient
         pred_fake, pred_real = self.discriminate(input_semantics, fake_image, target_image)
+        self._last_d_out = None   # never keep an autograd graph alive across steps (CUDA-graph capture needs that)
         D_losses['D/Fake'] = self.criterionGAN(pred_fake, False, for_discriminator=True)
         D_losses['D/real'] = self.criterionGAN(pred_real, True, for_discriminator=True)
         return D_losses
