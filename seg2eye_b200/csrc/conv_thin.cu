@@ -203,18 +203,26 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
   for (long long pb = p0; pb < p1; pb += PPW) {
     const long long p = pb + slot;
     const bool pv = p < p1;
+    // issue every tap's 16-byte load first (clamped address, validity folded into a 0/1 factor): no branches between
+    // the loads, so all of them are in flight together
+    bf16x8 xv[TMAX];
+    float valid[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      const int hi = ho + g.dy[t], wi = wo + g.dx[t];
+      const bool ok = pv && t < g.ntaps && hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi;
+      const int hc = min(max(hi, 0), g.Hi - 1), wc = min(max(wi, 0), g.Wi - 1), bc = min(b, g.B - 1);
+      valid[t] = ok ? 1.f : 0.f;
+      xv[t] = *reinterpret_cast<const bf16x8*>(x + (((long long)bc * g.Hi + hc) * g.Wi + wc) * g.Cin + sub * 8);
+    }
     float acc = 0.f;
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) {
-      if (t < g.ntaps) {
-        const int hi = ho + g.dy[t], wi = wo + g.dx[t];
-        if (pv && hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) {
-          float xf[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)b * g.Hi + hi) * g.Wi + wi) * g.Cin + sub * 8), xf);
+      float xf[8], part = 0.f;
+      unpack8(xv[t], xf);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc = fmaf(xf[j], wreg[t][j], acc);
-        }
-      }
+      for (int j = 0; j < 8; ++j) part = fmaf(xf[j], wreg[t][j], part);
+      acc = fmaf(part, valid[t], acc);
     }
 #pragma unroll
     for (int o = LPP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -273,16 +281,19 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
       float a[8];
       unpack8(*reinterpret_cast<const bf16x8*>(ap), a);
       const bf16* sb = S + ((long long)b * HS * WS) * Cs + cs;
+      float sv[TMAX];
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t) {   // clamped, branch-free loads: all taps in flight together
+        const int hs = h + tdy[t], wss = w + tdx[t];
+        const bool ok = t < g.ntaps && hs >= 0 && hs < HS && wss >= 0 && wss < WS;
+        const int hc = min(max(hs, 0), HS - 1), wc = min(max(wss, 0), WS - 1);
+        const float v = __bfloat162float(sb[((long long)hc * WS + wc) * Cs]);
+        sv[t] = ok ? v : 0.f;
+      }
 #pragma unroll
       for (int t = 0; t < TMAX; ++t) {
-        if (t < g.ntaps) {
-          const int hs = h + tdy[t], wss = w + tdx[t];
-          if (hs >= 0 && hs < HS && wss >= 0 && wss < WS) {
-            const float sv = __bfloat162float(sb[((long long)hs * WS + wss) * Cs]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], sv, acc[t][j]);
-          }
-        }
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], sv[t], acc[t][j]);
       }
       if (++w == WA) {
         w = 0;

@@ -407,11 +407,41 @@ __global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, int H, int W, int
     y[i] = __float2bfloat16(acc / (float)cnt);
   }
 }
+// 8 channels per thread (C % 8 == 0), 32-bit index math
+__global__ void avgpool_fwd_vec_kernel(const bf16* __restrict__ x, int H, int W, int C8, int Ho, int Wo, unsigned n, bf16* __restrict__ y) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % (unsigned)C8;
+    unsigned p = i / (unsigned)C8;
+    const int wo = (int)(p % (unsigned)Wo);
+    p /= (unsigned)Wo;
+    const int ho = (int)(p % (unsigned)Ho);
+    const unsigned b = p / (unsigned)Ho;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, f[8];
+    int cnt = 0;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int h = 2 * ho + dh, w = 2 * wo + dw;
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          unpack8(*reinterpret_cast<const bf16x8*>(x + ((((long long)b * H + h) * W + w) * C8 + c) * 8), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          ++cnt;
+        }
+      }
+    const float inv = 1.f / (float)cnt;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    *reinterpret_cast<bf16x8*>(y + (long long)i * 8) = pack8(acc);
+  }
+}
 __device__ __forceinline__ int pool_cnt(int o, int L) {  // valid taps of window o along a length-L axis
   int c = 0;
   for (int d = -1; d <= 1; ++d) c += (2 * o + d >= 0 && 2 * o + d < L);
   return c;
 }
+__global__ void avgpool_bwd_vec_kernel(const bf16* __restrict__ dy, int H, int W, int C8, int Ho, int Wo, unsigned n, bf16* __restrict__ dx);
 __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, int H, int W, int C, int Ho, int Wo, long long n, bf16* __restrict__ dx) {
   GRID_STRIDE(i, n) {
     const int c = (int)(i % C);
@@ -429,6 +459,29 @@ __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, int H, int W, in
       }
     }
     dx[i] = __float2bfloat16(acc);
+  }
+}
+
+__global__ void avgpool_bwd_vec_kernel(const bf16* __restrict__ dy, int H, int W, int C8, int Ho, int Wo, unsigned n, bf16* __restrict__ dx) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % (unsigned)C8;
+    unsigned p = i / (unsigned)C8;
+    const int w = (int)(p % (unsigned)W);
+    p /= (unsigned)W;
+    const int h = (int)(p % (unsigned)H);
+    const unsigned b = p / (unsigned)H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, f[8];
+    for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho >= Ho) continue;
+      for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo >= Wo) continue;
+        const float sc = 1.f / (float)(pool_cnt(ho, H) * pool_cnt(wo, W));
+        unpack8(*reinterpret_cast<const bf16x8*>(dy + ((((long long)b * Ho + ho) * Wo + wo) * C8 + c) * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], sc, acc[j]);
+      }
+    }
+    *reinterpret_cast<bf16x8*>(dx + (long long)i * 8) = pack8(acc);
   }
 }
 
@@ -920,7 +973,10 @@ int s2e_avgpool3s2_fwd(const void* x, int B, int H, int W, int C, void* y, void*
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long n = (long long)B * Ho * Wo * C;
   if (!n) return S2E_OK;
-  avgpool_fwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, Ho, Wo, n, (bf16*)y);
+  if (C % 8 == 0 && n / 8 < (1LL << 31))
+    avgpool_fwd_vec_kernel<<<grid1d(n / 8), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C / 8, Ho, Wo, (unsigned)(n / 8), (bf16*)y);
+  else
+    avgpool_fwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, Ho, Wo, n, (bf16*)y);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -928,7 +984,10 @@ int s2e_avgpool3s2_bwd(const void* dy, int B, int H, int W, int C, void* dx, voi
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long n = (long long)B * H * W * C;
   if (!n) return S2E_OK;
-  avgpool_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C, Ho, Wo, n, (bf16*)dx);
+  if (C % 8 == 0 && n / 8 < (1LL << 31))
+    avgpool_bwd_vec_kernel<<<grid1d(n / 8), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C / 8, Ho, Wo, (unsigned)(n / 8), (bf16*)dx);
+  else
+    avgpool_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)dy, H, W, C, Ho, Wo, n, (bf16*)dx);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

@@ -337,8 +337,8 @@ def test_upsample_avgpool_bilinear_add_act(S):
     assert torch.equal(nchw(y), yr.detach())
     assert rel(nchw(xc.grad), xr.grad) < 5e-3
 
-    for (H, W) in [(12, 10), (13, 9)]:
-        x = bf(torch.randn(2, 5, H, W, generator=g))
+    for (H, W, Cp) in [(12, 10, 5), (13, 9, 5), (13, 10, 16)]:
+        x = bf(torch.randn(2, Cp, H, W, generator=g))
         xr = x.clone().requires_grad_()
         yr = F.avg_pool2d(xr, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
         dy = bf(torch.randn(yr.shape, generator=g))
