@@ -339,3 +339,51 @@ def test_checkpoint_roundtrip_in_reference_layout(ctx, tmp_path):
         assert all(v.device.type == "cpu" for v in sd.values())
         assert all(v.dtype == (torch.int64 if k.endswith("num_batches_tracked") else torch.float32) for k, v in sd.items())
     util.load_network(tr.pix2pix_model.netG, "G", "latest", opt)
+
+
+def test_inference_and_encode_only_modes(ctx, gold):
+    """BASELINE config 4 path: mode='encode_only' -> w, interpolate, mode='inference' with `latent_style`
+    (pix2pix_model.py:76-88).  Checked against the oracle's generator on the same w."""
+    from seg2eye_b200.models.pix2pix_model import Pix2PixModel
+    m = Pix2PixModel(ctx.opt)
+    load(m.netG, O.synth_state(O.generator_shapes(ctx.oopt), ctx.seeds["G"]))
+    load(m.netE, O.synth_state(O.encoder_shapes(ctx.oopt), ctx.seeds["E"]))
+    m.train()
+    data = {k: v.clone() for k, v in ctx.batch.items()}
+    w = m(data, mode="encode_only")
+    assert w.shape == (ctx.bs, 16) and rel(w, gold["w"]) < TOL_ACT
+    # interpolate between the two style codes, 3 steps, labels repeated
+    alphas = torch.tensor([0.0, 0.5, 1.0], device=w.device).view(-1, 1)
+    wi = (1 - alphas) * w[0:1] + alphas * w[1:2]
+    lab = ctx.batch["label"][0:1].repeat(3, 1, 1, 1)
+    out = m({"label": lab, "style_image": ctx.batch["style_image"][0:1].repeat(3, 1, 1, 1, 1), "latent_style": wi.detach()},
+            mode="inference")
+    assert out.shape == (3, 1, 320, 256) and out.dtype == torch.float32 and not out.requires_grad
+    sdG = O.synth_state(O.generator_shapes(ctx.oopt), ctx.seeds["G"])
+    with torch.no_grad():
+        ref = O.generator_forward(sdG, O.one_hot(lab, 4), wi.detach().cpu(), ctx.oopt)
+    assert rel(out, ref) < TOL_CHAIN
+    with pytest.raises(ValueError):
+        m(data, mode="bogus")
+
+
+@pytest.mark.parametrize("over", [dict(norm_G="spectralspadeinstance3x3"), dict(num_upsampling_layers="more", crop_size=512)])
+def test_generator_variants_vs_oracle(ctx, over):
+    """SPADE with InstanceNorm statistics (shard-invariant config of SURVEY 8(e)) and the 6-upsampling variant."""
+    from seg2eye_b200.models import networks
+    oopt = SimpleNamespace(**{**vars(ctx.oopt), **over})
+    opt = SimpleNamespace(**{**vars(ctx.opt), **over})
+    if "crop_size" in over:      # 'more' adds one upsampling: keep the 320x256 output (sw = 512 / 64 = 8, sh = 10)
+        oopt.aspect_ratio = opt.aspect_ratio = 0.8
+    sd = O.synth_state(O.generator_shapes(oopt), 77)
+    seg = O.one_hot(ctx.batch["label"], 4)
+    if "crop_size" in over:
+        seg = torch.nn.functional.interpolate(seg, size=(640, 512), mode="nearest")
+    w = O.synth_state({"w": (ctx.bs, 16)}, 5, scale=4.0)["w"]
+    with torch.no_grad():
+        ref = O.generator_forward({k: v.clone() for k, v in sd.items()}, seg, w, oopt)
+    G = load(networks.SPADESTYLEGenerator(opt), sd).train()
+    with torch.no_grad():
+        out = G(seg.cuda(), w.cuda())
+    assert out.shape == ref.shape
+    assert rel(out, ref) < TOL_CHAIN, rel(out, ref)
