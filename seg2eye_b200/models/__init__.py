@@ -1,16 +1,16 @@
-"""Drop-in for the reference's `models` package (models/__init__.py)."""
+"""Drop-in for the reference's `models` package: `get_option_setter(name)` / `create_model(opt)`, which
+options/base_options.py:78-81 and user scripts call with --model pix2pix."""
 import importlib
 
-import torch
+_MODEL_CLASSES = {"pix2pix": ("pix2pix_model", "Pix2PixModel")}
 
 
 def find_model_using_name(model_name):
-    modellib = importlib.import_module(__name__ + "." + model_name + "_model")
-    target = model_name.replace('_', '') + 'model'
-    for name, cls in modellib.__dict__.items():
-        if name.lower() == target.lower() and isinstance(cls, type) and issubclass(cls, torch.nn.Module):
-            return cls
-    raise ValueError("no model class matching %s" % target)
+    try:
+        module, cls = _MODEL_CLASSES[model_name.replace("_", "").lower()]
+    except KeyError:
+        raise ValueError("unknown --model %r (the B200 path provides: %s)" % (model_name, ", ".join(_MODEL_CLASSES)))
+    return getattr(importlib.import_module("%s.%s" % (__name__, module)), cls)
 
 
 def get_option_setter(model_name):
@@ -18,6 +18,6 @@ def get_option_setter(model_name):
 
 
 def create_model(opt):
-    instance = find_model_using_name(opt.model)(opt)
-    print("model [%s] was created" % (type(instance).__name__))
-    return instance
+    model = find_model_using_name(opt.model)(opt)
+    print("model [%s] was created" % type(model).__name__)
+    return model

@@ -1,50 +1,43 @@
-"""Drop-in for the reference's `models.networks` package (models/networks/__init__.py:6-60)."""
+"""Drop-in for the reference's `models.networks` package (models/networks/__init__.py:6-60): network factory,
+option hooks and the loss re-exports `Pix2PixModel` / `util.tester` import from here."""
 import torch
-import torch.nn as nn
 
+from .architecture import SPADE_STYLE_ResnetBlock
 from .base_network import BaseNetwork
 from .discriminator import MultiscaleDiscriminator, NLayerDiscriminator
 from .encoder import ConvEncoder
 from .generator import SPADESTYLEGenerator
-from .loss import GANLoss, MSECalculator, StyleLoss, gram_matrix, openEDSaccuracy, l1_loss, mse_loss
-from .normalization import SPADE, SPADE_STYLE_Block, ApplyStyle, FC, get_nonspade_norm_layer
-from .architecture import SPADE_STYLE_ResnetBlock
+from .loss import GANLoss, MSECalculator, StyleLoss, gram_matrix, l1_loss, mse_loss, openEDSaccuracy
+from .normalization import FC, SPADE, ApplyStyle, SPADE_STYLE_Block, get_nonspade_norm_layer
 
-_REGISTRY = {
-    ('spadestyle', 'generator'): SPADESTYLEGenerator,
-    ('multiscale', 'discriminator'): MultiscaleDiscriminator,
-    ('nlayer', 'discriminator'): NLayerDiscriminator,
-    ('conv', 'encoder'): ConvEncoder,
-}
+# the reference resolves '<name><kind>' by scanning a module for a class of that lower-cased name; the hot path has
+# exactly these four
+_NETWORKS = {'spadestylegenerator': SPADESTYLEGenerator, 'multiscalediscriminator': MultiscaleDiscriminator,
+             'nlayerdiscriminator': NLayerDiscriminator, 'convencoder': ConvEncoder}
 
 
 def find_network_using_name(target_network_name, filename):
-    key = (target_network_name.replace('_', '').lower(), filename)
-    if key not in _REGISTRY:
-        raise ValueError('In models.networks.%s there is no class matching %s%s' % (filename, target_network_name, filename))
-    network = _REGISTRY[key]
-    assert issubclass(network, BaseNetwork), "Class %s should be a subclass of BaseNetwork" % network
-    return network
+    cls = _NETWORKS.get((target_network_name + filename).replace('_', '').lower())
+    if cls is None:
+        raise ValueError('models.networks.%s has no network called %r' % (filename, target_network_name))
+    assert issubclass(cls, BaseNetwork), "Class %s should be a subclass of BaseNetwork" % cls
+    return cls
 
 
 def modify_commandline_options(parser, is_train):
     opt, _ = parser.parse_known_args()
-    netG_cls = find_network_using_name(opt.netG, 'generator')
-    parser = netG_cls.modify_commandline_options(parser, is_train)
-    if is_train:
-        netD_cls = find_network_using_name(opt.netD, 'discriminator')
-        parser = netD_cls.modify_commandline_options(parser, is_train)
-    netE_cls = find_network_using_name('conv', 'encoder')
-    parser = netE_cls.modify_commandline_options(parser, is_train)
+    wanted = [(opt.netG, 'generator')] + ([(opt.netD, 'discriminator')] if is_train else []) + [('conv', 'encoder')]
+    for name, kind in wanted:
+        parser = find_network_using_name(name, kind).modify_commandline_options(parser, is_train)
     return parser
 
 
 def create_network(cls, opt):
-    """models/networks/__init__.py:39-48.  One process drives one GPU (data parallelism is process-level,
-    see seg2eye_b200.parallel), so several gpu_ids are not wrapped in nn.DataParallel."""
+    """Instantiate, report size, move to the process's GPU, initialise.  One process drives one GPU (data parallelism
+    is process-level, seg2eye_b200.parallel), so there is no nn.DataParallel wrapper as in the reference."""
     net = cls(opt)
     net.print_network()
-    if len(opt.gpu_ids) > 0:
+    if opt.gpu_ids:
         assert torch.cuda.is_available()
         net.cuda()
     net.init_weights(opt.init_type, opt.init_variance)

@@ -1,4 +1,8 @@
-"""SPADE_STYLE_ResnetBlock mirror (reference models/networks/architecture.py:13-62)."""
+"""SPADE+Style ResNet block with the reference's interface (reference models/networks/architecture.py:13-62):
+
+    out = shortcut(x) + conv_1(lrelu(norm_1(conv_0(lrelu(norm_0(x))))))      shortcut = conv_s(norm_s(x)) if fin != fout
+
+The LeakyReLU(0.2) is fused into the normalisation kernel, the convolutions are spectral-normed tap convolutions."""
 import torch.nn as nn
 
 from ... import _lib as L
@@ -10,37 +14,36 @@ from .normalization import SPADE_STYLE_Block
 class SPADE_STYLE_ResnetBlock(nn.Module):
     def __init__(self, fin, fout, opt):
         super().__init__()
-        self.learned_shortcut = (fin != fout)
-        fmiddle = min(fin, fout)
+        mid = min(fin, fout)
         sn = 'spectral' in opt.norm_G
-        self.conv_0 = Conv2d(fin, fmiddle, 3, padding=1, spectral=sn)
-        self.conv_1 = Conv2d(fmiddle, fout, 3, padding=1, spectral=sn)
+        self.learned_shortcut = fin != fout
+        # registration order fixes the state_dict order: conv_0, conv_1, [conv_s], norm_0, norm_1, [norm_s]
+        self.conv_0 = Conv2d(fin, mid, 3, padding=1, spectral=sn)
+        self.conv_1 = Conv2d(mid, fout, 3, padding=1, spectral=sn)
         if self.learned_shortcut:
             self.conv_s = Conv2d(fin, fout, 1, bias=False, spectral=sn)
         self.norm_0 = SPADE_STYLE_Block(fin, opt)
-        self.norm_1 = SPADE_STYLE_Block(fmiddle, opt)
+        self.norm_1 = SPADE_STYLE_Block(mid, opt)
         if self.learned_shortcut:
             self.norm_s = SPADE_STYLE_Block(fin, opt)
 
+    def _shortcut_nhwc(self, x, seg, w):
+        if not self.learned_shortcut:
+            return x
+        return self.conv_s.forward_nhwc(self.norm_s.forward_nhwc(x, seg, w, L.ACT_NONE))
+
     def forward_nhwc(self, x, seg, latent_style):
-        # same evaluation order as the reference (shortcut first) so BN buffers / SN vectors advance identically;
-        # the LeakyReLU(0.2) of actvn() is fused into the modulation kernel
-        if self.learned_shortcut:
-            x_s = self.conv_s.forward_nhwc(self.norm_s.forward_nhwc(x, seg, latent_style, L.ACT_NONE))
-        else:
-            x_s = x
-        dx = self.conv_0.forward_nhwc(self.norm_0.forward_nhwc(x, seg, latent_style, L.ACT_LRELU))
-        dx = self.conv_1.forward_nhwc(self.norm_1.forward_nhwc(dx, seg, latent_style, L.ACT_LRELU))
-        return ops.AddFn.apply(x_s, dx)
+        # the shortcut runs first, as in the reference, so BN buffers / spectral vectors advance in the same order
+        skip = self._shortcut_nhwc(x, seg, latent_style)
+        h = self.conv_0.forward_nhwc(self.norm_0.forward_nhwc(x, seg, latent_style, L.ACT_LRELU))
+        h = self.conv_1.forward_nhwc(self.norm_1.forward_nhwc(h, seg, latent_style, L.ACT_LRELU))
+        return ops.AddFn.apply(skip, h)
 
     def forward(self, x, seg, latent_style):
         return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x), seg, latent_style))
 
     def shortcut(self, x, seg, latent_style):
-        if self.learned_shortcut:
-            xn = ops.as_nhwc(x)
-            return ops.as_nchw_view(self.conv_s.forward_nhwc(self.norm_s.forward_nhwc(xn, seg, latent_style, L.ACT_NONE)))
-        return x
+        return ops.as_nchw_view(self._shortcut_nhwc(ops.as_nhwc(x), seg, latent_style)) if self.learned_shortcut else x
 
     def actvn(self, x):
         return ops.as_nchw_view(ops.ActFn.apply(ops.as_nhwc(x), L.ACT_LRELU))

@@ -1,17 +1,28 @@
-"""SPADESTYLEGenerator mirror (reference models/networks/generator.py:13-102)."""
+"""SPADE+Style generator with the reference's interface and state_dict layout.
+
+Mirrors `SPADESTYLEGenerator` (reference models/networks/generator.py:13-102): a 3x3 conv on the down-sampled
+segmap, seven SPADE+Style ResNet blocks separated by nearest 2x up-sampling, LeakyReLU, 3x3 conv to one channel, tanh.
+Here the whole forward runs on NHWC bf16 activations through seg2eye_b200.ops; only the result is (B,1,H,W) fp32.
+"""
 from ... import _lib as L
 from ... import ops
 from .architecture import SPADE_STYLE_ResnetBlock
 from .base_network import BaseNetwork
 from .layers import Conv2d
+from .normalization import clear_seg_cache
+
+# (attribute name, input width, output width) in units of ngf, and whether a 2x up-sampling precedes the block
+_TRUNK = (("head_0", 16, 16), ("G_middle_0", 16, 16), ("G_middle_1", 16, 16),
+          ("up_0", 16, 8), ("up_1", 8, 4), ("up_2", 4, 2), ("up_3", 2, 1))
+_UPSAMPLINGS = {"normal": 5, "more": 6, "most": 7}
 
 
 class SPADESTYLEGenerator(BaseNetwork):
     @staticmethod
     def modify_commandline_options(parser, is_train):
-        parser.add_argument('--num_upsampling_layers', choices=('normal', 'more', 'most'), default='normal',
-                            help="If 'more', adds upsampling layer between the two middle resnet blocks. "
-                                 "If 'most', also add one more upsampling + resnet layer at the end of the generator")
+        parser.add_argument('--num_upsampling_layers', choices=tuple(_UPSAMPLINGS), default='normal',
+                            help="'more': one extra 2x up-sampling between the two middle blocks; "
+                                 "'most': additionally one more up-sampling + block before the output conv")
         return parser
 
     def __init__(self, opt):
@@ -20,60 +31,43 @@ class SPADESTYLEGenerator(BaseNetwork):
         nf = opt.ngf
         self.sw, self.sh = self.compute_latent_vector_size(opt)
         self.fc = Conv2d(opt.semantic_nc, 16 * nf, 3, padding=1)
-        self.head_0 = SPADE_STYLE_ResnetBlock(16 * nf, 16 * nf, opt)
-        self.G_middle_0 = SPADE_STYLE_ResnetBlock(16 * nf, 16 * nf, opt)
-        self.G_middle_1 = SPADE_STYLE_ResnetBlock(16 * nf, 16 * nf, opt)
-        self.up_0 = SPADE_STYLE_ResnetBlock(16 * nf, 8 * nf, opt)
-        self.up_1 = SPADE_STYLE_ResnetBlock(8 * nf, 4 * nf, opt)
-        self.up_2 = SPADE_STYLE_ResnetBlock(4 * nf, 2 * nf, opt)
-        self.up_3 = SPADE_STYLE_ResnetBlock(2 * nf, 1 * nf, opt)
-        final_nc = nf
+        for name, cin, cout in _TRUNK:
+            setattr(self, name, SPADE_STYLE_ResnetBlock(cin * nf, cout * nf, opt))
+        last = nf
         if opt.num_upsampling_layers == 'most':
-            # the reference calls an undefined helper here (generator.py:45); we build the block it intended
-            self.up_4 = SPADE_STYLE_ResnetBlock(1 * nf, nf // 2, opt)
-            final_nc = nf // 2
-        self.conv_img = Conv2d(final_nc, opt.output_nc, 3, padding=1)
+            # generator.py:45 refers to a helper that does not exist; this is the block it meant to create
+            self.up_4 = SPADE_STYLE_ResnetBlock(nf, nf // 2, opt)
+            last = nf // 2
+        self.conv_img = Conv2d(last, opt.output_nc, 3, padding=1)
 
     def compute_latent_vector_size(self, opt):
-        if opt.num_upsampling_layers == 'normal':
-            num_up_layers = 5
-        elif opt.num_upsampling_layers == 'more':
-            num_up_layers = 6
-        elif opt.num_upsampling_layers == 'most':
-            num_up_layers = 7
-        else:
+        """(sw, sh) of the coarsest map: width crop_size / 2^n_up, height from the aspect ratio (generator.py:52-67)."""
+        if opt.num_upsampling_layers not in _UPSAMPLINGS:
             raise ValueError('opt.num_upsampling_layers [%s] not recognized' % opt.num_upsampling_layers)
-        sw = opt.crop_size // (2 ** num_up_layers)
-        sh = round(sw / opt.aspect_ratio)
-        return sw, sh
+        sw = opt.crop_size // (2 ** _UPSAMPLINGS[opt.num_upsampling_layers])
+        return sw, round(sw / opt.aspect_ratio)
 
     def up(self, x):
         return ops.Upsample2xFn.apply(x)
 
-    def forward(self, input, w=None):
-        from .normalization import clear_seg_cache
-        clear_seg_cache()   # im2col'd segmaps are shared by the SPADE blocks of one forward only
-        seg = input
-        x = self.fc.forward_nhwc(ops.seg_nearest(seg, self.sh, self.sw))
-        x = self.head_0.forward_nhwc(x, seg, w)
-        x = self.up(x)
-        x = self.G_middle_0.forward_nhwc(x, seg, w)
-        if self.opt.num_upsampling_layers in ('more', 'most'):
-            x = self.up(x)
-        x = self.G_middle_1.forward_nhwc(x, seg, w)
-        x = self.up(x)
-        x = self.up_0.forward_nhwc(x, seg, w)
-        x = self.up(x)
-        x = self.up_1.forward_nhwc(x, seg, w)
-        x = self.up(x)
-        x = self.up_2.forward_nhwc(x, seg, w)
-        x = self.up(x)
-        x = self.up_3.forward_nhwc(x, seg, w)
+    def _schedule(self):
+        """Block names in execution order, each with a flag 'up-sample first'."""
+        extra = self.opt.num_upsampling_layers in ('more', 'most')
+        plan = [("head_0", False), ("G_middle_0", True), ("G_middle_1", extra)]
+        plan += [(n, True) for n in ("up_0", "up_1", "up_2", "up_3")]
         if self.opt.num_upsampling_layers == 'most':
-            x = self.up(x)
-            x = self.up_4.forward_nhwc(x, seg, w)
+            plan.append(("up_4", True))
+        return plan
+
+    def forward(self, input, w=None):
+        if self.opt.output_nc != 1:
+            raise ValueError('output_nc != 1 is not supported by the B200 path (OpenEDS images are single channel)')
+        clear_seg_cache()   # the im2col'd segmaps are shared by the SPADE blocks of this forward only
+        x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw))
+        for name, upsample_first in self._schedule():
+            if upsample_first:
+                x = self.up(x)
+            x = getattr(self, name).forward_nhwc(x, input, w)
         x = self.conv_img.forward_nhwc(ops.ActFn.apply(x, L.ACT_LRELU))
         clear_seg_cache()
-        if self.opt.output_nc == 1:
-            return ops.TanhFn.apply(x)
-        raise ValueError('output_nc != 1 is not supported by the B200 path (OpenEDS images are single channel)')
+        return ops.TanhFn.apply(x)
