@@ -121,21 +121,34 @@ def _dp_worker(rank, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=2)
     from seg2eye_b200 import parallel
+    ok = True
+    # (1) a small network trained for three steps on different shards; `unused` never receives a gradient (like fc_var)
     torch.manual_seed(0)
-    params = [torch.nn.Parameter(torch.zeros(n)) for n in (1000, 17, 300000, 5)]
-    for i, p in enumerate(params):
-        p.grad = None if i == 1 else torch.full_like(p, float(rank + 1) * (i + 1))   # params[1]: no grad anywhere (fc_var)
-    red = parallel.GradReducer(params, bucket_bytes=1 << 20)
-    assert len(red.buckets()) >= 2
-    red.allreduce()
-    ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(params) if i != 1)
-    ok = ok and params[1].grad is None
-    m = torch.nn.Linear(3, 3)
-    parallel.broadcast_module(m, 0)
-    ref = [t.clone() for t in m.parameters()]
+    net = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.Tanh(), torch.nn.Linear(256, 256), torch.nn.Tanh(),
+                              torch.nn.Linear(256, 8))
+    unused = torch.nn.Parameter(torch.zeros(5))
+    parallel.broadcast_module(net, 0)
+    ref = [p.detach().clone() for p in net.parameters()]
     for t in ref:
         dist.broadcast(t, 0)
-    ok = ok and all(torch.equal(a, b) for a, b in zip(ref, m.parameters()))
+    ok = ok and all(torch.equal(a, b) for a, b in zip(ref, net.parameters()))
+    red = parallel.GradReducer(list(net.parameters()) + [unused], bucket_bytes=64 << 10)
+    g = torch.Generator().manual_seed(100 + rank)
+    for step in range(3):
+        x = torch.randn(16, 64, generator=g)
+        for p in net.parameters():
+            p.grad = None
+        net(x).square().mean().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        red.allreduce()
+        # expected: the mean over ranks of the local gradients
+        for p, lg in zip(net.parameters(), local):
+            both = [torch.zeros_like(lg), torch.zeros_like(lg)]
+            dist.all_gather(both, lg)
+            ok = ok and torch.allclose(p.grad, (both[0] + both[1]) / 2, rtol=1e-5, atol=1e-7)
+        ok = ok and unused.grad is None
+    ok = ok and len(red.buckets) >= 3                       # several buckets
+    ok = ok and red.launched_during_backward >= 2 * len(red.buckets)   # steps 2 and 3 overlapped with backward
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
