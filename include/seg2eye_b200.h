@@ -128,10 +128,12 @@ int s2e_depth_to_space(const void* dy, int B, int H, int W, int C, void* dx, voi
  * ------------------------------------------------------------------------------------------ */
 /* acc: double [G][2][C] (G = per_sample ? B : 1), zeroed inside. */
 int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* acc, void* stream);
-/* mean/rstd float [G][C]; running_* may be NULL; biased var for rstd, unbiased for running_var */
-int s2e_norm_finalize(const double* acc, int G, int C, double count, float eps, float* mean, float* rstd,
-                      float* running_mean, float* running_var, float momentum, int64_t* num_batches_tracked,
-                      void* stream);
+/* mean/rstd float [G][C]; running_* may be NULL; biased var for rstd, unbiased for running_var.
+ * count = number of elements behind `acc`; count_unbiased (0 = count) = number of elements the normalised tensor has
+ * -- they differ when the statistics of a nearest-2x up-sampled tensor are taken from its 4x smaller source. */
+int s2e_norm_finalize(const double* acc, int G, int C, double count, double count_unbiased, float eps, float* mean,
+                      float* rstd, float* running_mean, float* running_var, float momentum,
+                      int64_t* num_batches_tracked, void* stream);
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd,
                         int B, int HW, int C, int per_sample, int act, void* out, void* stream);
 /* backward: racc double [B][4][C] zeroed inside. `out` = saved forward output (sign for the lrelu mask). */

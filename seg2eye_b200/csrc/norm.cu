@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NT) stats_kernel(const bf16* __restrict__ x, i
 // the product ever being formed: mean stays that of x, rstd' = s / sqrt(var * s^2 + eps), so (x - mean) * rstd' == norm(s x).
 __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, double count, float eps, float* mean,
                                 float* rstd, float* running_mean, float* running_var, float momentum,
-                                long long* nbt, const float* __restrict__ in_scale, int group) {
+                                long long* nbt, const float* __restrict__ in_scale, int group, double count_unbiased) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && nbt) *nbt += 1;
   if (i >= G * C) return;
@@ -102,7 +102,8 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, do
   const double sc = in_scale ? (double)in_scale[g / group] : 1.0;
   rstd[i] = (float)(sc / sqrt(var * sc * sc + (double)eps));
   if (running_mean && g == 0) {
-    const double unb = count > 1 ? var * count / (count - 1) : var;
+    const double cu = count_unbiased > 0 ? count_unbiased : count;   // element count BatchNorm sees (x4 when the statistics
+    const double unb = cu > 1 ? var * cu / (cu - 1) : var;           // come from the source of a nearest-2x up-sampling)
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
   }
@@ -295,19 +296,48 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
 }
 
 // ---------------------------------------------------------------- InstanceNorm (+act)
+// same streaming structure as the SPADE kernels: grid (pixel chunks, B), per-channel constants in registers
 __global__ void __launch_bounds__(NT) instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, int HW, int C, long long nvec, int act,
+                                                            const float* __restrict__ rstd, int HW, int C, int act,
                                                             bf16* __restrict__ y) {
+  const int b = blockIdx.y;
+  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const long long q0 = (long long)blockIdx.x * chunk;
+  const long long q1 = min((long long)HW, q0 + chunk);
   const int cg = C >> 3;
-  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
-    const long long p = v / cg;
-    const int c = (int)(v - p * cg) * 8;
-    const int b = (int)(p / HW);
-    float xf[8], o[8];
-    unpack8(ld_stream8(x + p * C + c), xf);
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
+    if (my_lane >= lanes) continue;
+    const int c = (cg0 + my_cg) * 8;
+    float ka[8], kb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = act_apply((xf[j] - __ldg(mean + b * C + c + j)) * __ldg(rstd + b * C + c + j), act);
-    st_stream8(y + p * C + c, pack8(o));
+    for (int j = 0; j < 8; ++j) {
+      ka[j] = rstd[(size_t)b * C + c + j];
+      kb[j] = -mean[(size_t)b * C + c + j] * ka[j];
+    }
+    const long long base = (long long)b * HW;
+    long long q = q0 + my_lane;
+    for (; q + lanes < q1; q += 2 * lanes) {
+      const bf16x8 va = ld_stream8(x + (base + q) * C + c), vb = ld_stream8(x + (base + q + lanes) * C + c);
+      float f[8], o[8];
+      unpack8(va, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
+      st_stream8(y + (base + q) * C + c, pack8(o));
+      unpack8(vb, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
+      st_stream8(y + (base + q + lanes) * C + c, pack8(o));
+    }
+    for (; q < q1; q += lanes) {
+      float f[8], o[8];
+      unpack8(ld_stream8(x + (base + q) * C + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
+      st_stream8(y + (base + q) * C + c, pack8(o));
+    }
   }
 }
 
@@ -344,35 +374,47 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const bf16* __r
 __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
                                                                 const bf16* __restrict__ x, const float* __restrict__ mean,
                                                                 const float* __restrict__ rstd, const double* __restrict__ racc,
-                                                                int HW, int C, long long nvec, int act, bf16* __restrict__ dx) {
+                                                                int HW, int C, int act, bf16* __restrict__ dx) {
+  const int b = blockIdx.y;
+  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const long long q0 = (long long)blockIdx.x * chunk;
+  const long long q1 = min((long long)HW, q0 + chunk);
   const int cg = C >> 3;
   const float inv = 1.f / (float)HW;
-  for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < nvec; v += (long long)gridDim.x * NT) {
-    const long long p = v / cg;
-    const int c = (int)(v - p * cg) * 8;
-    const int b = (int)(p / HW);
-    float df[8], yf[8], xf[8], o[8];
-    unpack8(ld_stream8(dy + p * C + c), df);
-    unpack8(ld_stream8(x + p * C + c), xf);
-    if (act != S2E_ACT_NONE) unpack8(ld_stream8(y + p * C + c), yf);
-    const double* r = racc + (size_t)b * 2 * C + c;
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
+    if (my_lane >= lanes) continue;
+    const int c = (cg0 + my_cg) * 8;
+    float rsd[8], mu[8], m1[8], m2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float g = df[j];
-      if (act == S2E_ACT_LRELU) g *= (yf[j] > 0.f ? 1.f : 0.2f);
-      const float rsd = __ldg(rstd + b * C + c + j);
-      const float xh = (xf[j] - __ldg(mean + b * C + c + j)) * rsd;
-      o[j] = rsd * (g - (float)r[j] * inv - xh * (float)r[C + j] * inv);
+      rsd[j] = rstd[(size_t)b * C + c + j];
+      mu[j] = mean[(size_t)b * C + c + j];
+      m1[j] = (float)racc[(size_t)b * 2 * C + c + j] * inv;
+      m2[j] = (float)racc[(size_t)b * 2 * C + C + c + j] * inv;
     }
-    st_stream8(dx + p * C + c, pack8(o));
+    const long long base = (long long)b * HW;
+    for (long long q = q0 + my_lane; q < q1; q += lanes) {
+      const long long p = base + q;
+      float df[8], yf[8], xf[8], o[8];
+      const bf16x8 vd = ld_stream8(dy + p * C + c), vx = ld_stream8(x + p * C + c);
+      if (act != S2E_ACT_NONE) unpack8(ld_stream8(y + p * C + c), yf);
+      unpack8(vd, df);
+      unpack8(vx, xf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = df[j];
+        if (act == S2E_ACT_LRELU) g *= (yf[j] > 0.f ? 1.f : 0.2f);
+        const float xh = (xf[j] - mu[j]) * rsd[j];
+        o[j] = rsd[j] * (g - m1[j] - xh * m2[j]);
+      }
+      st_stream8(dx + p * C + c, pack8(o));
+    }
   }
 }
 
-int ew_grid(long long nvec) {
-  long long g = (nvec + NT - 1) / NT;
-  const long long cap = (long long)s2e_num_sms() * 16;
-  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
-}
 // pixel chunks per sample for the streaming elementwise kernels: ~16 resident blocks per SM in total, and at least
 // 8 pixels per pixel-lane so the per-thread constant setup is amortised
 int ew_chunks(int HW, int B, int C) {
@@ -412,10 +454,11 @@ int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* 
   return S2E_OK;
 }
 
-int s2e_norm_finalize(const double* acc, int G, int C, double count, float eps, float* mean, float* rstd,
-                      float* running_mean, float* running_var, float momentum, int64_t* nbt, void* stream) {
+int s2e_norm_finalize(const double* acc, int G, int C, double count, double count_unbiased, float eps, float* mean,
+                      float* rstd, float* running_mean, float* running_var, float momentum, int64_t* nbt, void* stream) {
   finalize_kernel<<<ceil_div(G * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, G, C, count, eps, mean, rstd, running_mean,
-                                                                           running_var, momentum, (long long*)nbt, nullptr, 1);
+                                                                           running_var, momentum, (long long*)nbt, nullptr, 1,
+                                                                           count_unbiased);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -504,10 +547,10 @@ int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, co
   int rc = s2e_norm_stats(x, B, HW, C, 1, acc, stream);
   if (rc) return rc;
   finalize_kernel<<<ceil_div(B * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, B, C, (double)HW, eps, mean, rstd, nullptr, nullptr,
-                                                                           0.f, nullptr, in_scale, group > 0 ? group : 1);
+                                                                           0.f, nullptr, in_scale, group > 0 ? group : 1, 0.0);
   S2E_LAUNCH_CHECK();
-  const long long nvec = (long long)B * HW * (C >> 3);
-  instnorm_apply_kernel<<<ew_grid(nvec), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, rstd, HW, C, nvec, act, (bf16*)y);
+  dim3 grid(ew_chunks(HW, B, C), B);
+  instnorm_apply_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, rstd, HW, C, act, (bf16*)y);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -521,9 +564,9 @@ int s2e_instnorm_bwd(const void* dy, const void* y, const void* x, const float* 
   instnorm_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)x, mean, rstd, HW, C,
                                                             act, racc);
   S2E_LAUNCH_CHECK();
-  const long long nvec = (long long)B * HW * (C >> 3);
-  instnorm_bwd_apply_kernel<<<ew_grid(nvec), NT, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)x, mean, rstd, racc, HW,
-                                                          C, nvec, act, (bf16*)dx);
+  dim3 grid2(ew_chunks(HW, B, C), B);
+  instnorm_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)x, mean, rstd, racc, HW, C, act,
+                                                  (bf16*)dx);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

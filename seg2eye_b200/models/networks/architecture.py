@@ -27,15 +27,17 @@ class SPADE_STYLE_ResnetBlock(nn.Module):
         if self.learned_shortcut:
             self.norm_s = SPADE_STYLE_Block(fin, opt)
 
-    def _shortcut_nhwc(self, x, seg, w):
+    def _shortcut_nhwc(self, x, seg, w, stats_src=None):
         if not self.learned_shortcut:
             return x
-        return self.conv_s.forward_nhwc(self.norm_s.forward_nhwc(x, seg, w, L.ACT_NONE))
+        return self.conv_s.forward_nhwc(self.norm_s.forward_nhwc(x, seg, w, L.ACT_NONE, stats_src))
 
-    def forward_nhwc(self, x, seg, latent_style):
+    def forward_nhwc(self, x, seg, latent_style, stats_src=None):
+        """stats_src: the tensor x was nearest-2x up-sampled from, if any -- norm_0 / norm_s then read their batch
+        statistics from it (identical mean and variance, a quarter of the bytes)."""
         # the shortcut runs first, as in the reference, so BN buffers / spectral vectors advance in the same order
-        skip = self._shortcut_nhwc(x, seg, latent_style)
-        h = self.conv_0.forward_nhwc(self.norm_0.forward_nhwc(x, seg, latent_style, L.ACT_LRELU))
+        skip = self._shortcut_nhwc(x, seg, latent_style, stats_src)
+        h = self.conv_0.forward_nhwc(self.norm_0.forward_nhwc(x, seg, latent_style, L.ACT_LRELU, stats_src))
         h = self.conv_1.forward_nhwc(self.norm_1.forward_nhwc(h, seg, latent_style, L.ACT_LRELU))
         return ops.AddFn.apply(skip, h)
 

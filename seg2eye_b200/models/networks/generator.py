@@ -65,9 +65,10 @@ class SPADESTYLEGenerator(BaseNetwork):
         clear_seg_cache()   # the im2col'd segmaps are shared by the SPADE blocks of this forward only
         x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw))
         for name, upsample_first in self._schedule():
+            src = None
             if upsample_first:
-                x = self.up(x)
-            x = getattr(self, name).forward_nhwc(x, input, w)
+                src, x = x, self.up(x)
+            x = getattr(self, name).forward_nhwc(x, input, w, stats_src=src)
         x = self.conv_img.forward_nhwc(ops.ActFn.apply(x, L.ACT_LRELU))
         clear_seg_cache()
         return ops.TanhFn.apply(x)

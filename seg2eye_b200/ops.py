@@ -338,7 +338,8 @@ class SpadeStyleFn(torch.autograd.Function):
     """out = act(0.5 * [ norm(x) * (1 + gamma) + beta + x * (1 + s0) + s1 ])  (normalization.py:91-105,161-192)."""
 
     @staticmethod
-    def forward(ctx, x, gb, style, cfg, running_mean, running_var, nbt):
+    def forward(ctx, x, gb, style, cfg, running_mean, running_var, nbt, stats_src=None):
+        # stats_src: the tensor x was nearest-2x up-sampled from (same per-channel mean / variance, 4x fewer bytes)
         x, gb, style = _c(x), _c(gb), _c(style)
         B, H, W, Cc = x.shape
         assert gb.shape == (B, H, W, 2 * Cc) and style.shape == (B, 2 * Cc) and style.dtype == F32
@@ -349,10 +350,17 @@ class SpadeStyleFn(torch.autograd.Function):
             acc = torch.empty(G * 2 * Cc, dtype=torch.float64, device=x.device)
             mean = torch.empty(G, Cc, dtype=F32, device=x.device)
             rstd = torch.empty(G, Cc, dtype=F32, device=x.device)
-            L.call("s2e_norm_stats", L.ptr(x), B, H * W, Cc, int(cfg.per_sample), L.ptr(acc), st)
             upd = (not cfg.per_sample) and cfg.training and running_mean is not None
             count = float(H * W if cfg.per_sample else B * H * W)
-            L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
+            if stats_src is not None:
+                src = _c(stats_src)
+                assert src.shape == (B, H // 2, W // 2, Cc)
+                L.call("s2e_norm_stats", L.ptr(src), B, (H // 2) * (W // 2), Cc, int(cfg.per_sample), L.ptr(acc), st)
+                count_stats = count / 4
+            else:
+                L.call("s2e_norm_stats", L.ptr(x), B, H * W, Cc, int(cfg.per_sample), L.ptr(acc), st)
+                count_stats = count
+            L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count_stats, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
                    L.ptr(running_mean) if upd else None, L.ptr(running_var) if upd else None, cfg.momentum,
                    L.ptr(nbt) if upd else None, st)
         else:  # BatchNorm2d in eval mode: running statistics
@@ -380,7 +388,7 @@ class SpadeStyleFn(torch.autograd.Function):
         L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
                L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), 0, L.ptr(dgb),
                L.ptr(dstyle), L.stream())
-        return dx, dgb, dstyle, None, None, None, None
+        return dx, dgb, dstyle, None, None, None, None, None
 
 
 class InstNormFn(torch.autograd.Function):
