@@ -471,14 +471,15 @@ tapconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work item decode: blockIdx.x = ((tap * mt + m) * nt + n) * ksplit + ks
+  // work item decode: blockIdx.x = ((ks * mt + m) * nt + n) * ntaps + tap -- the taps of one pixel range are adjacent
+  // CTAs, i.e. co-resident, so the dY / X tiles they share are fetched from HBM once and served from L2 to the others
   int wi = blockIdx.x;
-  const int ks = wi % p.ksplit;
-  wi /= p.ksplit;
+  const int tap = wi % p.taps.n;
+  wi /= p.taps.n;
   const int n_idx = wi % p.nt;
   wi /= p.nt;
   const int m_idx = wi % p.mt;
-  const int tap = wi / p.mt;
+  const int ks = wi / p.mt;
   const int m0 = m_idx * 128, n0 = n_idx * BN;
   const int k_begin = (int)(((long long)p.kt_total * ks) / p.ksplit);
   const int k_end = (int)(((long long)p.kt_total * (ks + 1)) / p.ksplit);
