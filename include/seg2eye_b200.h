@@ -103,6 +103,15 @@ int s2e_pack_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int 
 /* cin_pad (0 = none): the activations carry cin_pad >= Cin channels (extra ones zero), e.g. the 5-channel D input
  * stored with 16 channels so that discriminator.py:84's first conv also runs on the tensor-core path. */
 int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, int* dx); /* host helper */
+/* Several s2e_pack_weight / s2e_pack_weight_im2col3x3 calls in one launch (all the packed copies that an optimizer
+ * step invalidated).  `jobs` is a HOST array; im2col3x3 != 0 selects the [Cout][64] layout (then only w, out, Cout,
+ * Cin are read). */
+typedef struct {
+  const float* w_oihw;
+  void* out_bf16;
+  int Cout, Cin, kh, kw, stride, pad, transposed, Cout_total, co_offset, cin_pad, im2col3x3;
+} s2e_pack_job_t;
+int s2e_pack_weight_multi(const s2e_pack_job_t* jobs, int n_jobs, void* stream);
 /* tap-major fp32 weight gradient -> OIHW, with the spectral-norm chain rule when u != NULL:
  * dW_orig = inv_sigma * (G - inv_sigma * <G, W_orig> u v^T).  `dot` is a 1-float device scratch. */
 int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int stride, int pad, int Cout_total,
@@ -114,6 +123,23 @@ int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int st
  * update = 0 (module in eval mode): u, v are left untouched and only inv_sigma is produced. */
 int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
                             int update, float* u_copy, float* v_copy, void* stream); /* *_copy: optional snapshots */
+/* The same iteration for a whole table of independent layers (all spectral-normed convolutions of one network, as
+ * generator.py / discriminator.py / encoder.py build them) in four launches per iteration instead of four per layer.
+ * `jobs` is a HOST array.  n_iters > 1 repeats the iteration (the reference calls netE once per sample,
+ * pix2pix_model.py:285, so its u / v advance B times per step): iteration i writes inv_sigma[i] and, when given,
+ * u_copy + i*rows / v_copy + i*cols.  Arithmetic per layer is identical to s2e_spectral_power_iter (which is this
+ * call with one job). */
+typedef struct {
+  const float* w;
+  float* u;
+  float* v;
+  float* inv_sigma;
+  float* scratch;
+  float* u_copy;
+  float* v_copy;
+  int rows, cols;
+} s2e_sn_job_t;
+int s2e_spectral_power_iter_multi(const s2e_sn_job_t* jobs, int n_jobs, int update, int n_iters, void* stream);
 
 /* [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] with channel (i*2+j)*C+c = x[2h+i, 2w+j, c] (zero beyond the edge),
  * and its adjoint (gradient) */
@@ -203,6 +229,11 @@ int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32,
 int s2e_adam_prepare(float* state, float beta1, float beta2, void* stream);
 int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* state, float beta1,
                   float beta2, float eps, float weight_decay, void* stream);
+/* s2e_adam_step for a list of tensors in one launch per 48 tensors (multi-tensor apply; pix2pix_model.py:92-110 hands
+ * ~200 tensors to torch.optim.Adam).  p/g/m/v/n are HOST arrays of n_tensors device pointers / element counts. */
+int s2e_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                   const long long* n, const float* state, float beta1, float beta2, float eps, float weight_decay,
+                   void* stream);
 int s2e_fill_f32(float* p, long long n, float value, void* stream);
 
 #ifdef __cplusplus

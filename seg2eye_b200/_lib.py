@@ -23,6 +23,17 @@ class ConvDesc(C.Structure):
                 ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p)]
 
 
+class SnJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("inv_sigma", C.c_void_p),
+                ("scratch", C.c_void_p), ("u_copy", C.c_void_p), ("v_copy", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int)]
+
+
+class PackJob(C.Structure):
+    _fields_ = [("w_oihw", C.c_void_p), ("out_bf16", C.c_void_p), ("Cout", C.c_int), ("Cin", C.c_int), ("kh", C.c_int),
+                ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("transposed", C.c_int), ("Cout_total", C.c_int),
+                ("co_offset", C.c_int), ("cin_pad", C.c_int), ("im2col3x3", C.c_int)]
+
+
 _P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 _SIGS = {
     "s2e_abi_version": [],
@@ -40,6 +51,9 @@ _SIGS = {
     "s2e_packed_taps": [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)],
     "s2e_unpack_wgrad": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "s2e_spectral_power_iter": [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P],
+    "s2e_spectral_power_iter_multi": [C.POINTER(SnJob), _I, _I, _I, _P],
+    "s2e_pack_weight_multi": [C.POINTER(PackJob), _I, _P],
+    "s2e_adam_multi": [_I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_LL), _P, _F, _F, _F, _F, _P],
     "s2e_sn_in_correction": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P, _P, _P],
     "s2e_space_to_depth": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_depth_to_space": [_P, _I, _I, _I, _I, _P, _P],

@@ -248,32 +248,134 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, PackGeom g, c
   }
 }
 
+// Multi-tensor packing: one launch re-packs every weight an optimizer step touched.  A thread owns one (co, ci) pair,
+// reads its kh*kw contiguous master values once and scatters them to their tap-major slots; lanes run along the
+// contiguous axis of the OUTPUT (ci, or co for the transposed layout) so the 2-byte stores coalesce.  Slots that no
+// (r, s) maps to (stride-2 phase padding, cin_pad columns, im2col columns >= 9C) are never written: the destination
+// must have been zero-filled once, when it was allocated.
+constexpr int PACK_MAX_JOBS = 40;
+struct PackJob {
+  const float* w;
+  bf16* out;
+  PackGeom g;
+  int transposed, im2col;
+  int blk0;
+};
+struct PackTable {
+  int n;
+  PackJob j[PACK_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const __grid_constant__ PackTable t) {
+  int k = 0;
+  while (k + 1 < t.n && (int)blockIdx.x >= t.j[k + 1].blk0) ++k;
+  const PackJob& J = t.j[k];
+  const PackGeom& g = J.g;
+  const long long q = (long long)(blockIdx.x - J.blk0) * 256 + threadIdx.x;
+  if (q >= (long long)g.Cout * g.Cin) return;
+  int co, ci;
+  if (J.transposed) {
+    co = (int)(q % g.Cout);
+    ci = (int)(q / g.Cout);
+  } else {
+    ci = (int)(q % g.Cin);
+    co = (int)(q / g.Cin);
+  }
+  const int kk = g.kh * g.kw;
+  const float* src = J.w + ((long long)co * g.Cin + ci) * kk;
+  if (J.im2col) {  // [Cout][64], k = (r*3+s)*C + c
+    for (int tt = 0; tt < 9; ++tt) J.out[(long long)co * 64 + tt * g.Cin + ci] = __float2bfloat16(src[tt]);
+    return;
+  }
+  const int CinP = g.stride == 2 ? 4 * g.CinPad : g.CinPad;
+  for (int r = 0; r < g.kh; ++r) {
+    for (int s2 = 0; s2 < g.kw; ++s2) {
+      int tt, cp;
+      if (g.stride == 1) {
+        tt = r * g.kw + s2;
+        cp = ci;
+      } else {
+        const int rr = r - g.pad, ss = s2 - g.pad;
+        const int i = ((rr % 2) + 2) % 2, jj = ((ss % 2) + 2) % 2;
+        const int a = (rr - i) / 2, b = (ss - jj) / 2;
+        tt = (a - g.amin) * g.nb + (b - g.bmin);
+        cp = (i * 2 + jj) * g.CinPad + ci;
+      }
+      const long long o = J.transposed ? ((long long)tt * CinP + cp) * g.Ctot + g.co_off + co
+                                       : ((long long)tt * g.Ctot + g.co_off + co) * CinP + cp;
+      J.out[o] = __float2bfloat16(src[r * g.kw + s2]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ spectral norm
-// part[chunk][c] = sum_{r in chunk} W[r][c] u[r]      grid (col blocks, row chunks); partials are summed in a fixed
-// order by the normalise kernel, so the power iteration is bitwise reproducible (no floating-point atomics)
-__global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows, int cols, int rchunk, float* part) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const int r0 = blockIdx.y * rchunk, r1 = min(rows, r0 + rchunk);
+// One power iteration of torch.nn.utils.spectral_norm for a whole TABLE of layers per launch (the layers of a network
+// are independent: each iteration depends on its own W, u, v only).  Four launches per iteration regardless of the
+// number of layers:  (1) part[chunk][c] = sum_{r in chunk} W[r][c] u[r]   (2) v = normalize(sum_chunk part)
+// (3) s[r] = W[r][:] . v   (4) u = normalize(s), 1/sigma = 1 / (u . s).   Partials are combined in a fixed order, no
+// floating-point atomics: the iteration is bitwise reproducible and independent of how layers are grouped in a table.
+constexpr int SN_MAX_JOBS = 32;
+constexpr int SN_RCHUNK = 64;
+struct SnJob {
+  const float* w;
+  float *u, *v, *inv, *scratch, *ucopy, *vcopy;
+  int rows, cols;
+  int blk_a, blk_c;  // first block of this job in kernels (1) and (3)
+};
+struct SnTable {
+  int n, it;  // it = iteration number (selects inv[it], ucopy + it*rows, vcopy + it*cols)
+  SnJob j[SN_MAX_JOBS];
+};
+__device__ __forceinline__ int sn_find_a(const SnTable& t, int blk) {
+  int k = 0;
+  while (k + 1 < t.n && blk >= t.j[k + 1].blk_a) ++k;
+  return k;
+}
+__device__ __forceinline__ int sn_find_c(const SnTable& t, int blk) {
+  int k = 0;
+  while (k + 1 < t.n && blk >= t.j[k + 1].blk_c) ++k;
+  return k;
+}
+// (1): 128 threads; block = (128 columns) x (one 64-row chunk)
+__global__ void __launch_bounds__(128) sn_wt_u_multi_kernel(const __grid_constant__ SnTable t) {
+  const int k = sn_find_a(t, blockIdx.x);
+  const SnJob& J = t.j[k];
+  const int local = blockIdx.x - J.blk_a;
+  const int cblocks = (J.cols + 127) >> 7;
+  const int chunk = local / cblocks, cb = local - chunk * cblocks;
+  const int c = cb * 128 + threadIdx.x;
+  __shared__ float su[SN_RCHUNK];
+  const int r0 = chunk * SN_RCHUNK, r1 = min(J.rows, r0 + SN_RCHUNK);
+  if (threadIdx.x < r1 - r0) su[threadIdx.x] = J.u[r0 + threadIdx.x];
+  __syncthreads();
+  if (c >= J.cols) return;
+  const float* w = J.w + (long long)r0 * J.cols + c;
   float acc = 0.f;
-  int r = r0;
-  for (; r + 8 <= r1; r += 8) {  // 8 independent loads in flight per thread
+  int r = 0;
+  const int nr = r1 - r0;
+  for (; r + 8 <= nr; r += 8) {  // 8 independent loads in flight per thread
     float wv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wv[j] = w[(long long)(r + j) * cols + c];
+    for (int q = 0; q < 8; ++q) wv[q] = w[(long long)(r + q) * J.cols];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc = fmaf(wv[j], u[r + j], acc);
+    for (int q = 0; q < 8; ++q) acc = fmaf(wv[q], su[r + q], acc);
   }
-  for (; r < r1; ++r) acc = fmaf(w[(long long)r * cols + c], u[r], acc);
-  part[(long long)blockIdx.y * cols + c] = acc;
+  for (; r < nr; ++r) acc = fmaf(w[(long long)r * J.cols], su[r], acc);
+  float* part = J.scratch + J.cols + J.rows;
+  part[(long long)chunk * J.cols + c] = acc;
 }
-// x = sum_k raw[k][:] ; x <- x / max(||x||, eps) ; single block.  If inv_sigma: *inv_sigma = 1 / dot(x_normalized, x)
-__global__ void sn_normalize_kernel(const float* __restrict__ raw, int nparts, int n, float* __restrict__ outv, float* inv_sigma,
-                                    float* __restrict__ copy_out) {
+// (2) / (4): one block per job.  which = 0: v <- normalize(sum of partials);  1: u <- normalize(s), inv_sigma
+__global__ void __launch_bounds__(1024) sn_normalize_multi_kernel(const __grid_constant__ SnTable t, int which) {
+  const SnJob& J = t.j[blockIdx.x];
+  const int n = which ? J.rows : J.cols;
+  const int nparts = which ? 1 : (J.rows + SN_RCHUNK - 1) / SN_RCHUNK;
+  const float* raw = which ? J.scratch + J.cols : J.scratch + J.cols + J.rows;
+  float* outv = which ? J.u : J.v;
+  float* copy = which ? (J.ucopy ? J.ucopy + (long long)t.it * J.rows : nullptr)
+                      : (J.vcopy ? J.vcopy + (long long)t.it * J.cols : nullptr);
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float v = 0.f;
-    for (int k = 0; k < nparts; ++k) v += raw[(long long)k * n + i];
+    for (int q = 0; q < nparts; ++q) v += raw[(long long)q * n + i];
     outv[i] = v;  // staged un-normalised; rescaled below by the same thread
     acc = fmaf(v, v, acc);
   }
@@ -286,26 +388,54 @@ __global__ void sn_normalize_kernel(const float* __restrict__ raw, int nparts, i
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float v = outv[i] / denom;
     outv[i] = v;
-    if (copy_out) copy_out[i] = v;
+    if (copy) copy[i] = v;
   }
-  if (inv_sigma && threadIdx.x == 0) *inv_sigma = 1.f / (nsq / denom);  // sigma = u . (W v) = ||Wv||^2 / max(||Wv||,eps)
+  // sigma = u . (W v) = ||Wv||^2 / max(||Wv||, eps)
+  if (which && threadIdx.x == 0) J.inv[t.it] = 1.f / (nsq / denom);
 }
-// inv_sigma = 1 / (u . s)  (evaluation mode: no buffer update) ; single block
-__global__ void sn_dot_kernel(const float* __restrict__ u, const float* __restrict__ sv, int n, float* inv_sigma) {
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(u[i], sv[i], acc);
-  acc = block_sum(acc);
-  if (threadIdx.x == 0) *inv_sigma = 1.f / acc;
-}
-// s[r] = W[r][:] . v   one warp per row
-__global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ v, int rows, int cols, float* s) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= rows) return;
+// (3): one warp per row, 8 rows per block; the row is read with 4 independent (vector) loads in flight per lane
+__global__ void __launch_bounds__(256) sn_w_v_multi_kernel(const __grid_constant__ SnTable t) {
+  const int k = sn_find_c(t, blockIdx.x);
+  const SnJob& J = t.j[k];
+  const int r = (blockIdx.x - J.blk_c) * 8 + (threadIdx.x >> 5);
+  if (r >= J.rows) return;
   const int lane = threadIdx.x & 31;
+  const float* w = J.w + (long long)r * J.cols;
+  const float* v = J.v;
   float acc = 0.f;
-  for (int c = lane; c < cols; c += 32) acc = fmaf(w[(long long)r * cols + c], v[c], acc);
+  if ((J.cols & 3) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    const int n4 = J.cols >> 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = lane;
+    for (; c + 96 < n4; c += 128) {
+      const float4 x0 = w4[c], x1 = w4[c + 32], x2 = w4[c + 64], x3 = w4[c + 96];
+      const float4 y0 = v4[c], y1 = v4[c + 32], y2 = v4[c + 64], y3 = v4[c + 96];
+      a0 = fmaf(x0.x, y0.x, fmaf(x0.y, y0.y, fmaf(x0.z, y0.z, fmaf(x0.w, y0.w, a0))));
+      a1 = fmaf(x1.x, y1.x, fmaf(x1.y, y1.y, fmaf(x1.z, y1.z, fmaf(x1.w, y1.w, a1))));
+      a2 = fmaf(x2.x, y2.x, fmaf(x2.y, y2.y, fmaf(x2.z, y2.z, fmaf(x2.w, y2.w, a2))));
+      a3 = fmaf(x3.x, y3.x, fmaf(x3.y, y3.y, fmaf(x3.z, y3.z, fmaf(x3.w, y3.w, a3))));
+    }
+    for (; c < n4; c += 32) {
+      const float4 x0 = w4[c], y0 = v4[c];
+      a0 = fmaf(x0.x, y0.x, fmaf(x0.y, y0.y, fmaf(x0.z, y0.z, fmaf(x0.w, y0.w, a0))));
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int c = lane; c < J.cols; c += 32) acc = fmaf(w[c], v[c], acc);
+  }
   acc = warp_sum(acc);
-  if (lane == 0) s[r] = acc;
+  if (lane == 0) J.scratch[J.cols + r] = acc;
+}
+// evaluation mode (no buffer update): inv_sigma = 1 / (u . (W v)); one block per job
+__global__ void __launch_bounds__(1024) sn_dot_multi_kernel(const __grid_constant__ SnTable t) {
+  const SnJob& J = t.j[blockIdx.x];
+  const float* s = J.scratch + J.cols;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < J.rows; i += blockDim.x) acc = fmaf(J.u[i], s[i], acc);
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) J.inv[t.it] = 1.f / acc;
 }
 
 // ------------------------------------------------------------------------------------------ space <-> depth
@@ -734,6 +864,67 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Multi-tensor Adam: a block owns one 4096-element chunk of one tensor of the table (float4 path when the chunk is
+// full; every pointer comes from the caching allocator, i.e. is at least 16-byte aligned).
+constexpr int ADAM_MAX_TENSORS = 48;
+constexpr int ADAM_CHUNK = 4096;
+struct AdamTable {
+  int nt;
+  float* p[ADAM_MAX_TENSORS];
+  const float* g[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  long long n[ADAM_MAX_TENSORS];
+  int blk0[ADAM_MAX_TENSORS];
+};
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps, float wd,
+                                         float step_size, float bc2_sqrt) {
+  if (wd != 0.f) g = fmaf(wd, p, g);
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  p -= step_size * (m / denom);
+}
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamTable t, const float* __restrict__ state,
+                                                         float b1, float b2, float eps, float wd) {
+  int k = 0;
+  while (k + 1 < t.nt && (int)blockIdx.x >= t.blk0[k + 1]) ++k;
+  const long long off = (long long)(blockIdx.x - t.blk0[k]) * ADAM_CHUNK;
+  const long long left = t.n[k] - off;
+  float* __restrict__ p = t.p[k] + off;
+  const float* __restrict__ g = t.g[k] + off;
+  float* __restrict__ m = t.m[k] + off;
+  float* __restrict__ v = t.v[k] + off;
+  const float step_size = state[2], bc2_sqrt = state[3];
+  const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  if (left >= ADAM_CHUNK && aligned) {
+#pragma unroll
+    for (int i = 0; i < ADAM_CHUNK / (256 * 4); ++i) {
+      const int e = (i * 256 + threadIdx.x) * 4;
+      float4 pv = *reinterpret_cast<float4*>(p + e);
+      const float4 gv = *reinterpret_cast<const float4*>(g + e);
+      float4 mv = *reinterpret_cast<float4*>(m + e);
+      float4 vv = *reinterpret_cast<float4*>(v + e);
+      adam_one(pv.x, gv.x, mv.x, vv.x, b1, b2, eps, wd, step_size, bc2_sqrt);
+      adam_one(pv.y, gv.y, mv.y, vv.y, b1, b2, eps, wd, step_size, bc2_sqrt);
+      adam_one(pv.z, gv.z, mv.z, vv.z, b1, b2, eps, wd, step_size, bc2_sqrt);
+      adam_one(pv.w, gv.w, mv.w, vv.w, b1, b2, eps, wd, step_size, bc2_sqrt);
+      *reinterpret_cast<float4*>(p + e) = pv;
+      *reinterpret_cast<float4*>(m + e) = mv;
+      *reinterpret_cast<float4*>(v + e) = vv;
+    }
+  } else {
+    const int cnt = (int)(left < ADAM_CHUNK ? left : ADAM_CHUNK);
+    for (int e = threadIdx.x; e < cnt; e += 256) {
+      float pv = p[e], mv = m[e], vv = v[e];
+      adam_one(pv, g[e], mv, vv, b1, b2, eps, wd, step_size, bc2_sqrt);
+      p[e] = pv;
+      m[e] = mv;
+      v[e] = vv;
+    }
+  }
+}
+
 PackGeom make_pack_geom(int Cout, int Cin, int kh, int kw, int stride, int pad, int Ctot = 0, int co_off = 0, int cin_pad = 0) {
   PackGeom g;
   g.CinPad = cin_pad > Cin ? cin_pad : Cin;
@@ -879,32 +1070,45 @@ int s2e_unpack_wgrad(const float* dwp, int Cout, int Cin, int kh, int kw, int st
   return S2E_OK;
 }
 
+int s2e_spectral_power_iter_multi(const s2e_sn_job_t* jobs, int n_jobs, int update, int n_iters, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2E_REQUIRE(n_jobs >= 0 && n_iters >= 1, "spectral_power_iter_multi: bad counts");
+  for (int base = 0; base < n_jobs; base += SN_MAX_JOBS) {
+    SnTable t;
+    t.n = n_jobs - base < SN_MAX_JOBS ? n_jobs - base : SN_MAX_JOBS;
+    int blk_a = 0, blk_c = 0;
+    for (int k = 0; k < t.n; ++k) {
+      const s2e_sn_job_t& s = jobs[base + k];
+      S2E_REQUIRE(s.w && s.u && s.v && s.inv_sigma && s.scratch && s.rows > 0 && s.cols > 0, "spectral_power_iter_multi: job %d incomplete", base + k);
+      SnJob& J = t.j[k];
+      J.w = s.w; J.u = s.u; J.v = s.v; J.inv = s.inv_sigma; J.scratch = s.scratch; J.ucopy = s.u_copy; J.vcopy = s.v_copy;
+      J.rows = s.rows; J.cols = s.cols;
+      J.blk_a = blk_a; J.blk_c = blk_c;
+      blk_a += ceil_div(s.cols, 128) * ceil_div(s.rows, SN_RCHUNK);
+      blk_c += ceil_div(s.rows, 8);
+    }
+    for (int it = 0; it < n_iters; ++it) {
+      t.it = it;
+      if (update) {
+        sn_wt_u_multi_kernel<<<blk_a, 128, 0, st>>>(t);
+        sn_normalize_multi_kernel<<<t.n, 1024, 0, st>>>(t, 0);
+        sn_w_v_multi_kernel<<<blk_c, 256, 0, st>>>(t);
+        sn_normalize_multi_kernel<<<t.n, 1024, 0, st>>>(t, 1);
+      } else {
+        sn_w_v_multi_kernel<<<blk_c, 256, 0, st>>>(t);
+        sn_dot_multi_kernel<<<t.n, 1024, 0, st>>>(t);
+      }
+      S2E_LAUNCH_CHECK();
+    }
+  }
+  return S2E_OK;
+}
 int s2e_spectral_power_iter(const float* w, int rows, int cols, float* u, float* v, float* inv_sigma, float* scratch,
                             int update, float* u_copy, float* v_copy, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  float* t = scratch;         // cols
-  float* s = scratch + cols;  // rows
-  if (!update) {
-    sn_w_v_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(w, v, rows, cols, s);
-    S2E_LAUNCH_CHECK();
-    sn_dot_kernel<<<1, 1024, 0, st>>>(u, s, rows, inv_sigma);
-    S2E_LAUNCH_CHECK();
-    return S2E_OK;
-  }
-  const int rchunk = 64;
-  const int nparts = ceil_div(rows, rchunk);
-  float* part = scratch + cols + rows;  // nparts * cols
-  (void)t;
-  dim3 g1(ceil_div(cols, 128), nparts);
-  sn_wt_u_kernel<<<g1, 128, 0, st>>>(w, u, rows, cols, rchunk, part);
-  S2E_LAUNCH_CHECK();
-  sn_normalize_kernel<<<1, 1024, 0, st>>>(part, nparts, cols, v, nullptr, v_copy);
-  S2E_LAUNCH_CHECK();
-  sn_w_v_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(w, v, rows, cols, s);
-  S2E_LAUNCH_CHECK();
-  sn_normalize_kernel<<<1, 1024, 0, st>>>(s, 1, rows, u, inv_sigma, u_copy);
-  S2E_LAUNCH_CHECK();
-  return S2E_OK;
+  s2e_sn_job_t j;
+  j.w = w; j.u = u; j.v = v; j.inv_sigma = inv_sigma; j.scratch = scratch; j.u_copy = u_copy; j.v_copy = v_copy;
+  j.rows = rows; j.cols = cols;
+  return s2e_spectral_power_iter_multi(&j, 1, update, 1, stream);
 }
 
 int s2e_space_to_depth(const void* x, int B, int H, int W, int C, void* y, void* stream) {
@@ -1090,6 +1294,64 @@ int s2e_adam_step(float* p, const float* g, float* m, float* v, long long n, con
   if (!n) return S2E_OK;
   adam_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state, beta1, beta2, eps, weight_decay);
   S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+int s2e_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                   const long long* n, const float* state, float beta1, float beta2, float eps, float weight_decay,
+                   void* stream) {
+  S2E_REQUIRE(n_tensors >= 0 && state, "adam_multi: bad arguments");
+  for (int base = 0; base < n_tensors;) {
+    AdamTable t;
+    t.nt = 0;
+    int blocks = 0;
+    while (base < n_tensors && t.nt < ADAM_MAX_TENSORS) {
+      if (n[base] > 0) {
+        S2E_REQUIRE(p[base] && g[base] && m[base] && v[base], "adam_multi: tensor %d has a null pointer", base);
+        const int k = t.nt++;
+        t.p[k] = p[base];
+        t.g[k] = g[base];
+        t.m[k] = m[base];
+        t.v[k] = v[base];
+        t.n[k] = n[base];
+        t.blk0[k] = blocks;
+        blocks += (int)ceil_div_ll(n[base], ADAM_CHUNK);
+      }
+      ++base;
+    }
+    if (t.nt == 0) break;
+    adam_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t, state, beta1, beta2, eps, weight_decay);
+    S2E_LAUNCH_CHECK();
+  }
+  return S2E_OK;
+}
+int s2e_pack_weight_multi(const s2e_pack_job_t* jobs, int n_jobs, void* stream) {
+  S2E_REQUIRE(n_jobs >= 0, "pack_weight_multi: bad job count");
+  for (int base = 0; base < n_jobs; base += PACK_MAX_JOBS) {
+    PackTable t;
+    t.n = n_jobs - base < PACK_MAX_JOBS ? n_jobs - base : PACK_MAX_JOBS;
+    int blocks = 0;
+    for (int k = 0; k < t.n; ++k) {
+      const s2e_pack_job_t& s = jobs[base + k];
+      S2E_REQUIRE(s.w_oihw && s.out_bf16 && s.Cout > 0 && s.Cin > 0, "pack_weight_multi: job %d incomplete", base + k);
+      PackJob& J = t.j[k];
+      J.w = s.w_oihw;
+      J.out = (bf16*)s.out_bf16;
+      J.im2col = s.im2col3x3;
+      J.transposed = s.transposed;
+      if (s.im2col3x3) {
+        S2E_REQUIRE(9 * s.Cin <= 64, "pack_weight_multi: im2col3x3 needs 9*C <= 64");
+        J.g = make_pack_geom(s.Cout, s.Cin, 3, 3, 1, 1);
+        J.transposed = 0;
+      } else {
+        S2E_REQUIRE(s.stride == 1 || s.stride == 2, "pack_weight_multi: stride must be 1 or 2");
+        J.g = make_pack_geom(s.Cout, s.Cin, s.kh, s.kw, s.stride, s.pad, s.Cout_total, s.co_offset, s.cin_pad);
+      }
+      J.blk0 = blocks;
+      blocks += (int)ceil_div_ll((long long)s.Cout * s.Cin, 256);
+    }
+    pack_weight_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t);
+    S2E_LAUNCH_CHECK();
+  }
   return S2E_OK;
 }
 int s2e_fill_f32(float* p, long long n, float value, void* stream) {

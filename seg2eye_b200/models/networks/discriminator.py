@@ -87,6 +87,7 @@ class MultiscaleDiscriminator(BaseNetwork):
 
     def forward_nhwc(self, x):
         keep_all = not self.opt.no_ganFeat_loss
+        ops.prepare_spectral([m for m in self.modules() if isinstance(m, Conv2d)], self.training)
         per_scale = []
         scales = list(self.children())
         for i, d in enumerate(scales):

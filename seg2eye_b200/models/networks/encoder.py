@@ -42,6 +42,7 @@ class ConvEncoder(BaseNetwork):
         else:
             h = ops.as_nhwc(x)
         features = []
+        ops.prepare_spectral([getattr(self, 'layer' + str(n))[0] for n in range(self.len_sequence)], self.training, B, True)
         for n in range(self.len_sequence):
             layer = getattr(self, 'layer' + str(n))
             h = layer[1].forward_nhwc_spectral(layer[0].forward_nhwc_unscaled(h), layer[0], B)

@@ -63,6 +63,7 @@ class SPADESTYLEGenerator(BaseNetwork):
         if self.opt.output_nc != 1:
             raise ValueError('output_nc != 1 is not supported by the B200 path (OpenEDS images are single channel)')
         clear_seg_cache()   # the im2col'd segmaps are shared by the SPADE blocks of this forward only
+        ops.prepare_spectral([m for m in self.modules() if isinstance(m, Conv2d)], self.training)
         x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw))
         for name, upsample_first in self._schedule():
             src = None

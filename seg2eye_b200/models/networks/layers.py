@@ -44,7 +44,11 @@ class Conv2d(nn.Module):
     def sn_state(self):
         if not self.spectral:
             return None
-        inv = ops.spectral_inv_sigma(self.weight_orig, self.weight_u, self.weight_v, self.training)
+        ready, self._sn_ready = getattr(self, '_sn_ready', None), None
+        if ready is not None:     # the enclosing network already iterated all of its layers (ops.prepare_spectral)
+            inv = ready[0]
+        else:
+            inv = ops.spectral_inv_sigma(self.weight_orig, self.weight_u, self.weight_v, self.training)
         return (self.weight_u, self.weight_v, inv)
 
     def forward_nhwc(self, x, act=None):
@@ -104,7 +108,11 @@ class InstanceNorm2d(nn.Module):
     def forward_nhwc_spectral(self, z, conv, n_samples):
         """z = UNSCALED output of the spectral conv `conv` over n_samples groups of images; equals what n_samples
         successive conv->norm calls (one per group) would produce, buffers of `conv` advanced n_samples times."""
-        inv, U, V = ops.spectral_multi(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, n_samples)
+        ready, conv._sn_ready = getattr(conv, '_sn_ready', None), None
+        if ready is not None and ready[1] is not None and ready[0].numel() == n_samples:
+            inv, U, V = ready
+        else:
+            inv, U, V = ops.spectral_multi(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, n_samples)
         return ops.InstNormFn.apply(z, self.act, inv, U, V, z.shape[0] // n_samples, conv.weight_orig)
 
     def forward(self, x):

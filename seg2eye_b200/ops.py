@@ -132,39 +132,114 @@ def _desc(B, Hi, Wi, Cin, Ho, Wo, Cout, taps, act, negate=False):
     return d
 
 
+# ---- packed bf16 weight copies ---------------------------------------------------------------------------------
+# One registry for every packed copy (tap-major forward / transposed layouts, im2col'd mlp_shared weights).  A copy is
+# stale when one of its master weights changed: torch's own version counter (copy_, load_state_dict, init) or the
+# per-tensor counter our Adam kernel bumps (it writes through raw pointers).  Stale copies are re-packed in ONE
+# multi-tensor launch: right after an optimizer step (optim.Adam.step -> repack_stale()), or lazily at first use.
+import ctypes as _C
+import weakref as _weakref
+
+
+class _PackEntry:
+    __slots__ = ("refs", "cfg", "transposed", "im2col", "buf", "ver")
+
+    def weights(self):
+        ws = [r() for r in self.refs]
+        return None if any(w is None for w in ws) else ws
+
+
 _pack_cache = {}
 
 
-def packed_weights(weights, cfg, transposed):
-    """bf16 tap-major copy of one or more OIHW fp32 master weights (concatenated along Cout); cached until a
-    parameter changes.  Entries hold weak references so a recycled id() can never alias a dead tensor."""
-    import weakref
-    key = (tuple(id(w) for w in weights), transposed, cfg.stride, cfg.pad, cfg.cin_pad)
-    ver = (tuple(w._version for w in weights), tuple(w.data_ptr() for w in weights), _state["weights_epoch"])
-    hit = _pack_cache.get(key)
-    if hit is not None and not all(r() is w for r, w in zip(hit[0], weights)):
-        hit = None
-    if hit is not None and hit[1] == ver:
-        return hit[2]
-    cin = weights[0].shape[1]
-    cin_eff = max(cin, cfg.cin_pad)
-    cinp = cin_eff * 4 if cfg.stride == 2 else cin_eff
+def _master_version(weights):
+    return (tuple(w._version for w in weights), tuple(w.data_ptr() for w in weights),
+            tuple(getattr(w, "_s2e_ver", 0) for w in weights), _state["weights_epoch"])
+
+
+def mark_updated(params):
+    """Our Adam kernel changed these tensors behind torch's back."""
+    for p_ in params:
+        p_._s2e_ver = getattr(p_, "_s2e_ver", 0) + 1
+
+
+def _pack_jobs(entry, weights):
+    jobs = []
+    if entry.im2col:
+        w = weights[0].detach()
+        j = L.PackJob()
+        j.w_oihw, j.out_bf16, j.Cout, j.Cin, j.im2col3x3 = w.data_ptr(), entry.buf.data_ptr(), w.shape[0], w.shape[1], 1
+        return [j]
+    cfg = entry.cfg
     ctot = sum(w.shape[0] for w in weights)
-    ntaps = len(conv_taps(cfg))
-    n = ntaps * ctot * cinp
-    buf = hit[2] if (hit is not None and hit[2].numel() == n) else torch.zeros(n, dtype=BF16, device=weights[0].device)
     off = 0
     for w in weights:
         wd = w.detach()
         assert wd.is_contiguous() and wd.dtype == F32
-        L.call("s2e_pack_weight", L.ptr(wd), wd.shape[0], cin, cfg.kh, cfg.kw, cfg.stride, cfg.pad, int(transposed),
-               ctot, off, cfg.cin_pad, L.ptr(buf), L.stream())
+        j = L.PackJob()
+        j.w_oihw, j.out_bf16 = wd.data_ptr(), entry.buf.data_ptr()
+        j.Cout, j.Cin, j.kh, j.kw, j.stride, j.pad = wd.shape[0], wd.shape[1], cfg.kh, cfg.kw, cfg.stride, cfg.pad
+        j.transposed, j.Cout_total, j.co_offset, j.cin_pad, j.im2col3x3 = int(entry.transposed), ctot, off, cfg.cin_pad, 0
+        jobs.append(j)
         off += wd.shape[0]
-    if len(_pack_cache) > 4096:
-        for k in [k for k, v in _pack_cache.items() if any(r() is None for r in v[0])]:
-            del _pack_cache[k]
-    _pack_cache[key] = (tuple(weakref.ref(w) for w in weights), ver, buf)
-    return buf
+    return jobs
+
+
+def _run_pack_jobs(jobs):
+    if jobs:
+        arr = (L.PackJob * len(jobs))(*jobs)
+        L.call("s2e_pack_weight_multi", arr, len(jobs), L.stream())
+
+
+def repack_stale():
+    """Re-pack every registered copy whose master weights changed, in one launch per 40 tensors."""
+    jobs, dead = [], []
+    for key, e in _pack_cache.items():
+        ws = e.weights()
+        if ws is None:
+            dead.append(key)
+            continue
+        ver = _master_version(ws)
+        if ver != e.ver:
+            jobs += _pack_jobs(e, ws)
+            e.ver = ver
+    for key in dead:
+        del _pack_cache[key]
+    _run_pack_jobs(jobs)
+    return len(jobs)
+
+
+def _packed(key, weights, cfg, transposed, im2col, numel):
+    e = _pack_cache.get(key)
+    if e is not None and not all(r() is w for r, w in zip(e.refs, weights)):
+        e = None     # a recycled id(): never alias a dead tensor's copy
+    ver = _master_version(weights)
+    if e is not None and e.ver == ver:
+        return e.buf
+    if e is None:
+        e = _PackEntry()
+        e.refs = tuple(_weakref.ref(w) for w in weights)
+        e.cfg, e.transposed, e.im2col = cfg, transposed, im2col
+        # zero-filled ONCE: padding slots (stride-2 phases, cin_pad / im2col filler columns) are never written again
+        e.buf = torch.zeros(numel, dtype=BF16, device=weights[0].device)
+        _pack_cache[key] = e
+    _run_pack_jobs(_pack_jobs(e, weights))
+    e.ver = ver
+    return e.buf
+
+
+def packed_weights(weights, cfg, transposed):
+    """bf16 tap-major copy of one or more OIHW fp32 master weights (concatenated along Cout)."""
+    key = (tuple(id(w) for w in weights), transposed, cfg.kh, cfg.kw, cfg.stride, cfg.pad, cfg.cin_pad)
+    cin_eff = max(weights[0].shape[1], cfg.cin_pad)
+    cinp = cin_eff * 4 if cfg.stride == 2 else cin_eff
+    ctot = sum(w.shape[0] for w in weights)
+    return _packed(key, weights, cfg, transposed, False, len(conv_taps(cfg)) * ctot * cinp)
+
+
+def packed_weight_im2col(weight):
+    """bf16 [Cout][64] copy of a thin 3x3 weight (k = (r*3+s)*C + c) for the im2col'd segmap GEMM."""
+    return _packed((id(weight), "im2col"), (weight,), None, False, True, weight.shape[0] * 64)
 
 
 def space_to_depth(x):
@@ -292,42 +367,70 @@ def tap_conv(x, cfg, weights, biases=(), sn=None):
     return TapConvFn.apply(x, cfg, sn, len(weights), *weights, *biases)
 
 
+def _sn_scratch_floats(rows, cols):
+    return rows + cols + ((rows + 63) // 64) * cols
+
+
+def spectral_batch(layers, training, n_calls=1, keep_uv=False):
+    """Power iteration for a list of independent spectral-normed layers [(weight_orig, u, v), ...] in four launches per
+    iteration (s2e_spectral_power_iter_multi) instead of four per layer.  torch.nn.utils.spectral_norm semantics
+    (reference normalization.py:26, architecture.py:31-34): in training mode u and v advance in place, once per call.
+
+    n_calls > 1 reproduces n_calls successive forward calls of every layer (the reference runs netE once per sample,
+    pix2pix_model.py:285).  Returns per layer: inv (n_calls,) = 1/sigma of each call and, with keep_uv, the (u, v) each
+    call used as U (n_calls, rows), V (n_calls, cols) -- needed by the chain rule of the batched style encoder."""
+    if not layers:
+        return []
+    dev = layers[0][0].device
+    dims = [(w.shape[0], w.numel() // w.shape[0]) for w, _, _ in layers]
+    inv_all = torch.empty(len(layers) * n_calls, dtype=F32, device=dev)
+    scratch = torch.empty(sum(_sn_scratch_floats(r, c) for r, c in dims), dtype=F32, device=dev)
+    jobs, out, soff = [], [], 0
+    for i, ((w, u, v), (rows, cols)) in enumerate(zip(layers, dims)):
+        inv = inv_all[i * n_calls:(i + 1) * n_calls]
+        U = V = None
+        if keep_uv:
+            U = torch.empty(n_calls, rows, dtype=F32, device=dev)
+            V = torch.empty(n_calls, cols, dtype=F32, device=dev)
+        j = L.SnJob()
+        j.w, j.u, j.v, j.inv_sigma = w.detach().data_ptr(), u.data_ptr(), v.data_ptr(), inv.data_ptr()
+        j.scratch = scratch.data_ptr() + 4 * soff
+        j.u_copy = U.data_ptr() if (keep_uv and training) else None
+        j.v_copy = V.data_ptr() if (keep_uv and training) else None
+        j.rows, j.cols = rows, cols
+        soff += _sn_scratch_floats(rows, cols)
+        jobs.append(j)
+        out.append((inv, U, V))
+    arr = (L.SnJob * len(jobs))(*jobs)
+    L.call("s2e_spectral_power_iter_multi", arr, len(jobs), 1 if training else 0, n_calls if training else 1, L.stream())
+    if not training:
+        for (inv, U, V), (w, u, v) in zip(out, layers):
+            if n_calls > 1:
+                inv.copy_(inv[:1].expand_as(inv))
+            if keep_uv:
+                U.copy_(u.expand_as(U))
+                V.copy_(v.expand_as(V))
+    return out
+
+
 def spectral_inv_sigma(weight_orig, u, v, training):
-    """One power iteration in place on (u, v) (training mode) and 1/sigma as a device scalar.
-    torch.nn.utils.spectral_norm semantics (reference normalization.py:26, architecture.py:31-34)."""
-    w = weight_orig.detach()
-    rows = w.shape[0]
-    cols = w.numel() // rows
-    inv = torch.empty(1, dtype=F32, device=w.device)
-    scratch = torch.empty(rows + cols + ((rows + 63) // 64) * cols, dtype=F32, device=w.device)
-    L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv), L.ptr(scratch),
-           1 if training else 0, None, None, L.stream())
-    return inv
+    """One power iteration in place on (u, v) (training mode) and 1/sigma as a device scalar."""
+    return spectral_batch([(weight_orig, u, v)], training)[0][0]
 
 
 def spectral_multi(weight_orig, u, v, training, n_calls):
-    """What `n_calls` successive forward calls of a spectral-normed layer do to (u, v): returns the n_calls values of
-    1/sigma and, per call, the u / v vectors it used (needed by the chain rule).  Used by the batched style encoder,
-    which replaces the reference's one-netE-call-per-sample loop (pix2pix_model.py:285)."""
-    w = weight_orig.detach()
-    rows = w.shape[0]
-    cols = w.numel() // rows
-    inv = torch.empty(n_calls, dtype=F32, device=w.device)
-    U = torch.empty(n_calls, rows, dtype=F32, device=w.device)
-    V = torch.empty(n_calls, cols, dtype=F32, device=w.device)
-    scratch = torch.empty(rows + cols + ((rows + 63) // 64) * cols, dtype=F32, device=w.device)
-    st = L.stream()
-    for b in range(n_calls):
-        if training:
-            L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv[b:]), L.ptr(scratch), 1,
-                   L.ptr(U[b]), L.ptr(V[b]), st)
-        else:
-            L.call("s2e_spectral_power_iter", L.ptr(w), rows, cols, L.ptr(u), L.ptr(v), L.ptr(inv[b:]), L.ptr(scratch), 0,
-                   None, None, st)
-    if not training:
-        U.copy_(u.expand_as(U))
-        V.copy_(v.expand_as(V))
-    return inv, U, V
+    """What `n_calls` successive forward calls of one spectral-normed layer do to (u, v): (inv, U, V)."""
+    return spectral_batch([(weight_orig, u, v)], training, n_calls, keep_uv=True)[0]
+
+
+def prepare_spectral(convs, training, n_calls=1, keep_uv=False):
+    """Run the power iteration of every spectral-normed layer of a network up front, in one batched call, and park
+    the results on the layers (`_sn_ready`); each layer's next forward consumes its entry instead of launching its own
+    iteration.  The layers are independent, so this is observationally identical to iterating at the point of use."""
+    convs = [c for c in convs if getattr(c, 'spectral', False)]
+    res = spectral_batch([(c.weight_orig, c.weight_u, c.weight_v) for c in convs], training, n_calls, keep_uv)
+    for c, r in zip(convs, res):
+        c._sn_ready = r
 
 
 # ------------------------------------------------------------------------------------------------ norms
@@ -610,28 +713,17 @@ def seg_im2col(seg, hd, wd):
     return out
 
 
-_pack_im2col_cache = {}
-
-
 class SegConvFn(torch.autograd.Function):
     """act(conv3x3(seg, W) + b) for a thin segmap given as its 64-channel im2col: one K=64 GEMM on the tcgen05
     kernels, forward and weight gradient (the segmap itself needs no gradient)."""
 
     @staticmethod
     def forward(ctx, col, weight, bias, act, act_grad_fused=False):
-        import weakref
         ctx.act_grad_fused = act_grad_fused   # the consumer already applied the ReLU mask to the gradient it sends back
         B, H, W, K = col.shape
         Cout, Cs = weight.shape[0], weight.shape[1]
         assert K == 64 and weight.shape[2:] == (3, 3) and 9 * Cs <= 64
-        ver = (weight._version, weight.data_ptr(), _state["weights_epoch"])
-        hit = _pack_im2col_cache.get(id(weight))
-        if hit is not None and hit[0]() is weight and hit[1] == ver:
-            wp = hit[2]
-        else:
-            wp = hit[2] if (hit is not None and hit[0]() is weight) else torch.empty(Cout * 64, dtype=BF16, device=col.device)
-            L.call("s2e_pack_weight_im2col3x3", L.ptr(weight.detach()), Cout, Cs, L.ptr(wp), L.stream())
-            _pack_im2col_cache[id(weight)] = (weakref.ref(weight), ver, wp)
+        wp = packed_weight_im2col(weight)
         y = torch.empty(B, H, W, Cout, dtype=BF16, device=col.device)
         d = _desc(B, H, W, 64, H, W, Cout, [(0, 0)], act)
         flops = 2.0 * B * H * W * Cout * Cs * 9

@@ -32,13 +32,18 @@ class Adam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        """One multi-tensor launch per 48 parameters, then one multi-tensor re-pack of the bf16 copies of the weights
+        that just changed (ops.repack_stale) -- both capturable in a CUDA graph."""
+        import ctypes as C
         s = L.stream()
+        touched = []
         for group in self.param_groups:
             b1, b2 = group['betas']
             st, ps = self._dev_state(group)
             if not ps:
                 continue
             L.call("s2e_adam_prepare", L.ptr(st), b1, b2, s)
+            rows = []
             for p in ps:
                 state = self.state[p]
                 if len(state) == 0:
@@ -46,6 +51,11 @@ class Adam(torch.optim.Optimizer):
                     state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 assert p.is_contiguous() and p.dtype == torch.float32 and g.dtype == torch.float32
-                L.call("s2e_adam_step", L.ptr(p), L.ptr(g), L.ptr(state['exp_avg']), L.ptr(state['exp_avg_sq']),
-                       p.numel(), L.ptr(st), b1, b2, group['eps'], group['weight_decay'], s)
-        ops.bump_weights_epoch()
+                rows.append((L.ptr(p), L.ptr(g), L.ptr(state['exp_avg']), L.ptr(state['exp_avg_sq']), p.numel(), g))
+            n = len(rows)
+            arr = lambda k: (C.c_void_p * n)(*[r[k] for r in rows])
+            L.call("s2e_adam_multi", n, arr(0), arr(1), arr(2), arr(3), (C.c_longlong * n)(*[r[4] for r in rows]),
+                   L.ptr(st), b1, b2, group['eps'], group['weight_decay'], s)
+            touched += ps
+        ops.mark_updated(touched)
+        ops.repack_stale()

@@ -114,6 +114,7 @@ class Pix2PixTrainer():
             t.detach().copy_(s0)
         from .. import ops
         ops.bump_weights_epoch()
+        ops.repack_stale()   # the graphs re-pack after their own Adam; the restored weights need it once, here
         self._graphs = True
 
     def disable_cuda_graphs(self):

@@ -458,3 +458,113 @@ def test_space_to_depth_roundtrip(S):
     xp = F.pad(x, (0, 1, 0, 1))
     ref = torch.stack([xp[:, :, i::2, j::2] for i in (0, 1) for j in (0, 1)], dim=1).reshape(2, 12, 4, 5)
     assert torch.equal(nchw(y), ref)
+
+
+# ------------------------------------------------------------------------------------------ multi-tensor ops
+def test_pack_weight_multi_equals_single_calls(S):
+    """One multi-tensor launch == the per-tensor s2e_pack_weight / s2e_pack_weight_im2col3x3 calls, bit for bit, for
+    every geometry on the path (3x3, 1x1, 4x4 s2 p2 with channel padding, 3x3 s2 p1, 4x4 s1 p2, gamma|beta pairs)."""
+    L, ops = S
+    g = torch.Generator().manual_seed(5)
+    cases = [(3, 3, 1, 1, 0, (72, 40), 24), (1, 1, 1, 0, 0, (64,), 136), (4, 4, 2, 2, 16, (64,), 5), (3, 3, 2, 1, 0, (32,), 8),
+             (4, 4, 1, 2, 0, (8,), 64)]
+    ops._pack_cache.clear()
+    expect = []
+    for kh, kw, st, pad, cpad, couts, cin in cases:
+        ws = [torch.randn(co, cin, kh, kw, generator=g).cuda() for co in couts]
+        cfg = ops.ConvCfg(kh, kw, st, pad, L.ACT_NONE, False, cpad)
+        for tr in (False, True):
+            cin_eff = max(cin, cpad) * (4 if st == 2 else 1)
+            n = len(ops.conv_taps(cfg)) * sum(couts) * cin_eff
+            ref = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+            off = 0
+            for w in ws:
+                L.call("s2e_pack_weight", L.ptr(w), w.shape[0], cin, kh, kw, st, pad, int(tr), sum(couts), off, cpad, L.ptr(ref),
+                       L.stream())
+                off += w.shape[0]
+            got = ops.packed_weights(tuple(ws), cfg, tr)
+            assert torch.equal(got, ref), (kh, st, tr)
+            expect.append((ws, cfg, tr))
+    wseg = torch.randn(128, 4, 3, 3, generator=g).cuda()
+    ref = torch.empty(128 * 64, dtype=torch.bfloat16, device="cuda")
+    L.call("s2e_pack_weight_im2col3x3", L.ptr(wseg), 128, 4, L.ptr(ref), L.stream())
+    assert torch.equal(ops.packed_weight_im2col(wseg), ref)
+    # change every master weight behind torch's back (as the Adam kernel does) and re-pack everything in one call
+    n0 = L.launches
+    for ws, _, _ in expect:
+        for w in ws:
+            w.detach().view(-1)[::3] += 1.0
+    ops.mark_updated([w for ws, _, _ in expect for w in ws] + [wseg])
+    njobs = ops.repack_stale()
+    assert njobs == sum(len(ws) for ws, _, _ in expect) + 1 and L.launches - n0 == 1
+    for ws, cfg, tr in expect:
+        cin, st = ws[0].shape[1], cfg.stride
+        ref = torch.zeros_like(ops.packed_weights(tuple(ws), cfg, tr))
+        off = 0
+        for w in ws:
+            L.call("s2e_pack_weight", L.ptr(w), w.shape[0], cin, cfg.kh, cfg.kw, st, cfg.pad, int(tr), sum(x.shape[0] for x in ws),
+                   off, cfg.cin_pad, L.ptr(ref), L.stream())
+            off += w.shape[0]
+        assert torch.equal(ops.packed_weights(tuple(ws), cfg, tr), ref)
+    ops._pack_cache.clear()
+
+
+def test_adam_multi_matches_torch(S):
+    L, ops = S
+    from seg2eye_b200 import optim
+    g = torch.Generator().manual_seed(9)
+    shapes = [(5,), (4096,), (4097,), (3, 1000, 3), (130, 72, 3, 3), (1,)] + [(17 + i,) for i in range(60)]
+    p0 = [torch.randn(*s, generator=g) for s in shapes]
+    pr = [p.clone().requires_grad_() for p in p0]
+    pc = [p.cuda().requires_grad_() for p in p0]
+    o_r = torch.optim.Adam(pr, lr=2e-3, betas=(0.0, 0.9), weight_decay=0.01)
+    o_c = optim.Adam(pc, lr=2e-3, betas=(0, 0.9), weight_decay=0.01)
+    for it in range(3):
+        for a, b in zip(pr, pc):
+            gr = torch.randn(a.shape, generator=g)
+            a.grad, b.grad = gr.clone(), gr.cuda()
+        pc[3].grad = pr[3].grad = None      # a parameter that never receives a gradient (fc_var) is skipped, like torch does
+        n0 = L.launches
+        o_r.step()
+        o_c.step()
+        assert L.launches - n0 <= 4    # prepare + ceil(66/48) multi launches (+ no re-pack: nothing registered)
+    for a, b in zip(pr, pc):
+        assert rel(b, a) < 1e-6
+    assert torch.equal(pc[3].detach().cpu(), p0[3])
+
+
+def test_spectral_batch_matches_torch(S):
+    """Several layers x several successive calls in one batched call == torch's power iteration applied call by call."""
+    L, ops = S
+    g = torch.Generator().manual_seed(4)
+    shapes = [(64, 1, 3, 3), (48, 20, 3, 3), (130, 64, 4, 4), (256, 129, 1, 1)]
+    layers, refs = [], []
+    for s in shapes:
+        w = torch.randn(*s, generator=g)
+        u = F.normalize(torch.randn(s[0], generator=g), dim=0)
+        v = F.normalize(torch.randn(w[0].numel(), generator=g), dim=0)
+        layers.append((w.cuda(), u.cuda(), v.cuda()))
+        refs.append((w.view(s[0], -1), u, v))
+    n_calls = 3
+    out = ops.spectral_batch(layers, True, n_calls, keep_uv=True)
+    for (inv, U, V), (wm, u, v), (wc, uc, vc) in zip(out, refs, layers):
+        for c in range(n_calls):
+            v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
+            u = F.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+            sigma = torch.dot(u, torch.mv(wm, v))
+            assert rel(U[c], u) < 2e-5 and rel(V[c], v) < 2e-5 and abs(float(inv[c]) * float(sigma) - 1) < 2e-5
+        assert rel(uc, u) < 2e-5 and rel(vc, v) < 2e-5
+    # batched == one layer at a time, bit for bit (grouping layers into a table does not change the arithmetic)
+    l2 = [(w.clone(), F.normalize(torch.ones_like(u), dim=0), F.normalize(torch.ones_like(v), dim=0)) for w, u, v in layers]
+    l3 = [(w.clone(), u.clone(), v.clone()) for w, u, v in l2]
+    a = ops.spectral_batch(l2, True)
+    b = [ops.spectral_batch([l], True)[0] for l in l3]
+    for (ia, _, _), (ib, _, _), x, y in zip(a, b, l2, l3):
+        assert torch.equal(ia, ib) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
+    # eval mode leaves the buffers alone
+    before = [(u.clone(), v.clone()) for _, u, v in layers]
+    ev = ops.spectral_batch(layers, False, 2, keep_uv=True)
+    for (inv, U, V), (w, u, v), (u0, v0) in zip(ev, layers, before):
+        assert torch.equal(u, u0) and torch.equal(v, v0) and torch.equal(U[1], u0) and float(inv[0]) == float(inv[1])
+        wm = w.view(w.shape[0], -1)
+        assert abs(float(inv[0]) * float(torch.dot(u, torch.mv(wm, v))) - 1) < 2e-5
