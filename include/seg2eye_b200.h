@@ -51,13 +51,17 @@ int s2e_onehot_nchw(const int64_t* label, int B, int H, int W, int nc, float* ou
 int s2e_seg_nearest_nhwc(const float* seg_nchw, int B, int C, int Hs, int Ws, int Hd, int Wd, int Cpad,
                          void* out_nhwc_bf16, void* stream);
 
-/* nearest-resize + 3x3 im2col (zero padded) of a thin map (9*C <= 64) into 64 bf16 channels per pixel, channel
- * (r*3+s)*C + c.  SPADE's mlp_shared (normalization.py:85-88,98) then runs as a K=64 GEMM on the tensor-core kernels;
- * the matching weight layouts are [Cout][64] (pack) and its adjoint (unpack of the fp32 weight gradient). */
+/* nearest-resize + 3x3 im2col (zero padded) of a thin map (9*C <= 62) into 64 bf16 channels per pixel: channel
+ * (r*3+s)*C + c, zeros up to channel 61 and a CONSTANT ONE in channels 62 and 63.  SPADE's mlp_shared
+ * (normalization.py:85-88,98) then runs as a K=64 GEMM on the tensor-core kernels.  The matching weight layout is
+ * [Cout][64] with the conv bias split into two bf16 columns (63: bf16(b), 62: bf16(b - bf16(b)); s2e_pack_weight_multi,
+ * im2col3x3 job with `bias`), so the bias add rides in the GEMM at ~fp32 precision, and the adjoint (unpack of the fp32
+ * weight gradient) returns the bias gradient from column 63. */
 int s2e_seg_im2col3x3(const float* seg_nchw, int B, int C, int Hs, int Ws, int Hd, int Wd, void* out_nhwc64_bf16,
                       void* stream);
-int s2e_pack_weight_im2col3x3(const float* w_oihw, int Cout, int C, void* out_bf16, void* stream);
-int s2e_unpack_wgrad_im2col3x3(const float* dwp, int Cout, int C, float* dw_oihw, void* stream);
+int s2e_pack_weight_im2col3x3(const float* w_oihw, int Cout, int C, void* out_bf16, void* stream); /* columns 62, 63 = 0 */
+int s2e_unpack_wgrad_im2col3x3(const float* dwp, int Cout, int C, float* dw_oihw, float* db /* nullable */,
+                               void* stream);
 
 /* layout / precision boundary of the module API (NCHW fp32 <-> NHWC bf16) */
 int s2e_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* y, void* stream);
@@ -108,6 +112,7 @@ int s2e_packed_taps(int kh, int kw, int stride, int pad, int* ntaps, int* dy, in
  * Cin are read). */
 typedef struct {
   const float* w_oihw;
+  const float* bias; /* im2col3x3 jobs only (nullable): written to columns 62 | 63 */
   void* out_bf16;
   int Cout, Cin, kh, kw, stride, pad, transposed, Cout_total, co_offset, cin_pad, im2col3x3;
 } s2e_pack_job_t;
@@ -162,10 +167,14 @@ int s2e_norm_finalize(const double* acc, int G, int C, double count, double coun
                       int64_t* num_batches_tracked, void* stream);
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd,
                         int B, int HW, int C, int per_sample, int act, void* out, void* stream);
-/* backward: racc double [B][4][C] zeroed inside. `out` = saved forward output (sign for the lrelu mask). */
+/* backward: racc = scratch of B*5*C doubles + B*2*C floats, zeroed inside. `out` = saved forward output (sign for the
+ * lrelu mask).  chsum (nullable, float [3][C]) receives the per-channel sums over the batch of dgamma, dbeta and dx --
+ * the bias gradients of the gamma|beta convolution (normalization.py:88-89) and of the convolution that produced x
+ * (architecture.py:24) -- which the statistics pass yields for free. */
 int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act,
-                        double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, void* stream);
+                        double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum,
+                        void* stream);
 
 /* InstanceNorm2d(affine=False)+optional LeakyReLU on NHWC bf16 (normalization.py:41; discriminator.py:88-92;
  * encoder.py:23-38).  in_scale (nullable): one factor per `group` consecutive images, applied to x implicitly. */

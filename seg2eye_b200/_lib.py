@@ -29,7 +29,7 @@ class SnJob(C.Structure):
 
 
 class PackJob(C.Structure):
-    _fields_ = [("w_oihw", C.c_void_p), ("out_bf16", C.c_void_p), ("Cout", C.c_int), ("Cin", C.c_int), ("kh", C.c_int),
+    _fields_ = [("w_oihw", C.c_void_p), ("bias", C.c_void_p), ("out_bf16", C.c_void_p), ("Cout", C.c_int), ("Cin", C.c_int), ("kh", C.c_int),
                 ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("transposed", C.c_int), ("Cout_total", C.c_int),
                 ("co_offset", C.c_int), ("cin_pad", C.c_int), ("im2col3x3", C.c_int)]
 
@@ -42,7 +42,7 @@ _SIGS = {
     "s2e_seg_nearest_nhwc": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "s2e_seg_im2col3x3": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "s2e_pack_weight_im2col3x3": [_P, _I, _I, _P, _P],
-    "s2e_unpack_wgrad_im2col3x3": [_P, _I, _I, _P, _P],
+    "s2e_unpack_wgrad_im2col3x3": [_P, _I, _I, _P, _P, _P],
     "s2e_nchw_f32_to_nhwc_bf16": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_nhwc_bf16_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_tapconv_fwd": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _I, _P],
@@ -60,7 +60,7 @@ _SIGS = {
     "s2e_norm_stats": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_norm_finalize": [_P, _I, _I, _D, _D, _F, _P, _P, _P, _P, _F, _P, _P],
     "s2e_spade_style_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
-    "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P],
+    "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P],
     "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P, _P],
     "s2e_instnorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "s2e_upsample2x_fwd": [_P, _I, _I, _I, _I, _P, _P],

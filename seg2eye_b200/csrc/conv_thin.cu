@@ -238,6 +238,66 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
   }
 }
 
+// K2 tiled variant for conv_img (64 -> 1, 3x3, stride 1): every input pixel is read from global memory ONCE per tile
+// (plus a one-pixel halo) instead of once per tap.  Phase 1: 8 lanes per input pixel form the nine per-tap dot products
+// d[pixel][t] = x[pixel] . W[t] (tap weights in registers) and park them in shared memory; phase 2: one thread per
+// output pixel adds its nine neighbours' entries  y[p] = sum_t d[p + tap_t][t].
+constexpr int T1_TW = 32, T1_TH = 8, T1_HW = T1_TW + 2, T1_NHP = (T1_TH + 2) * T1_HW;
+__global__ void __launch_bounds__(256) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                             const float* __restrict__ bias, const float* __restrict__ scale,
+                                                             bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h) {
+  __shared__ float d[T1_NHP * 9];
+  const int sub = threadIdx.x & 7;
+  float wreg[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (t < g.ntaps) unpack8(*reinterpret_cast<const bf16x8*>(wp + (long long)t * 64 + sub * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wreg[t][j] = f[j];
+  }
+  int tile = blockIdx.x;
+  const int tw_idx = tile % tiles_w;
+  tile /= tiles_w;
+  const int th_idx = tile % tiles_h;
+  const int b = tile / tiles_h;
+  const int h0 = th_idx * T1_TH - 1, w0 = tw_idx * T1_TW - 1;
+  const bf16* xb = x + (long long)b * g.Hi * g.Wi * 64 + sub * 8;
+#pragma unroll 2
+  for (int hp = threadIdx.x >> 3; hp < T1_NHP; hp += 32) {
+    const int hh = hp / T1_HW, ww = hp - hh * T1_HW;
+    const int hi = h0 + hh, wi = w0 + ww;
+    const bool ok = hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi;
+    float xf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) unpack8(ld_stream8(xb + ((long long)hi * g.Wi + wi) * 64), xf);
+    float part[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fmaf(xf[j], wreg[t][j], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      part[t] = a;
+    }
+    if (sub == 0) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) d[hp * 9 + t] = part[t];
+    }
+  }
+  __syncthreads();
+  const int th = threadIdx.x >> 5, tw = threadIdx.x & 31;
+  const int ho = th_idx * T1_TH + th, wo = tw_idx * T1_TW + tw;
+  if (ho < g.Ho && wo < g.Wo) {
+    float acc = 0.f;
+    for (int t = 0; t < g.ntaps; ++t) acc += d[((th + 1 + g.dy[t]) * T1_HW + (tw + 1 + g.dx[t])) * 9 + t];
+    const float sc = scale ? __ldg(scale) : 1.f;
+    const float bv = bias ? __ldg(bias) : 0.f;
+    y[((long long)b * g.Ho + ho) * g.Wo + wo] = __float2bfloat16(act_apply(acc * sc + bv, g.act));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 // wide tensor A [.., Cw] walked pixel by pixel, thin tensor S [.., Cs] sampled at (pixel + sgn*tap).
 // thread = (8-channel chunk of A, one thin channel); acc[T][8] in registers; one atomic per output at the end.
@@ -304,8 +364,13 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
       }
     }
   }
-  // combine the pixel lanes of the block in shared memory, then one atomic per output element per block
-  extern __shared__ float red[];  // [pl_count][nth_pad] per (t, j) pass
+  // combine the pixel lanes of the block (lanes that share a warp by shuffles, the rest through shared memory), then
+  // one atomic per output element per block
+  extern __shared__ float red[];  // [rows][nth_pad] per (t, j) pass
+  const bool sub_warp = nth_pad < 32;                      // host guarantees 32 % nth_pad == 0 in that case
+  const int rows = sub_warp ? (int)(blockDim.x >> 5) : pl_count;
+  const int my_row = sub_warp ? (int)(threadIdx.x >> 5) : pl;
+  const bool writer = sub_warp ? (int)(threadIdx.x & 31) < nth_pad : true;
   for (int t = 0; t < g.ntaps; ++t) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -313,12 +378,14 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
 #pragma unroll
       for (int tt = 0; tt < TMAX; ++tt)
         if (tt == t) v = acc[tt][j];
+      if (sub_warp)
+        for (int o = nth_pad; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       __syncthreads();
-      red[pl * nth_pad + slot] = v;
+      if (writer) red[my_row * nth_pad + slot] = v;
       __syncthreads();
       if (pl == 0 && active) {
         float sum = 0.f;
-        for (int l = 0; l < pl_count; ++l) sum += red[l * nth_pad + slot];
+        for (int l = 0; l < rows; ++l) sum += red[l * nth_pad + slot];
         const int c = cw * 8 + j;
         const long long o = thin_x ? ((long long)t * Cw + c) * Cs + cs : ((long long)t * Cs + cs) * Cw + c;
         atomicAdd(dwp + o, sum);
@@ -379,6 +446,17 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     S2E_LAUNCH_CHECK();
     return 1;
   }
+  if (d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9 && d->Hi == d->Ho && d->Wi == d->Wo) {
+    bool halo1 = true;
+    for (int t = 0; t < d->ntaps; ++t) halo1 = halo1 && d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
+    if (halo1) {
+      const int tiles_w = ceil_div(d->Wo, T1_TW), tiles_h = ceil_div(d->Ho, T1_TH);
+      thin_out1_tile_kernel<<<(unsigned)(d->B * tiles_h * tiles_w), 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale,
+                                                                                   (bf16*)y, g, tiles_w, tiles_h);
+      S2E_LAUNCH_CHECK();
+      return 1;
+    }
+  }
   if (d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9) {
     const long long warps = (long long)s2e_num_sms() * 32;
     long long ppw = (P + warps - 1) / warps;
@@ -433,8 +511,10 @@ int s2e_thin_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dw
   const int HS = thin_x ? d->Hi : d->Ho, WS = thin_x ? d->Wi : d->Wo, Cs = thin_x ? d->Cin : d->Cout;
   const long long PA = (long long)d->B * HA * WA;
   if (PA == 0) return 1;
+  // channel slots per pixel lane: exact when they tile a warp (conv_img's weight gradient: 8 slots -> 4 pixel lanes per
+  // warp, no idle lanes), otherwise padded to whole warps
   int nth_pad = (Cw / 8) * Cs;
-  nth_pad = ((nth_pad + 31) / 32) * 32;
+  if (32 % nth_pad != 0) nth_pad = ((nth_pad + 31) / 32) * 32;
   int pl = 256 / nth_pad;
   if (pl < 1) pl = 1;
   if (d->ntaps > 9 && pl * nth_pad > 128) pl = 128 / nth_pad > 0 ? 128 / nth_pad : 1;

@@ -100,7 +100,7 @@ __global__ void seg_im2col_kernel(const float* __restrict__ seg, int C, int Hs, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = ch * 8 + j;
-      float val = 0.f;
+      float val = k >= 62 ? 1.f : 0.f;   // two constant-one channels: carry the bias (hi + lo part) through the GEMM
       if (k < 9 * C) {
         const int t = k / C, c = k - t * C;
         const int h = hd + t / 3 - 1, w = wd + t % 3 - 1;
@@ -115,6 +115,46 @@ __global__ void seg_im2col_kernel(const float* __restrict__ seg, int C, int Hs, 
     *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(v);
   }
 }
+// C == 4 (the OpenEDS segmap): one thread per pixel gathers its 3x3 neighbourhood (36 values, neighbouring threads
+// share cache lines) and writes the whole 128-byte im2col row; two taps fill one 16-byte chunk.
+__global__ void seg_im2col_c4_kernel(const float* __restrict__ seg, int Hs, int Ws, int Hd, int Wd, float sh, float sw,
+                                     long long npix, bf16* __restrict__ out) {
+  GRID_STRIDE(p, npix) {
+    const int wd = (int)(p % Wd);
+    long long r0 = p / Wd;
+    const int hd = (int)(r0 % Hd);
+    const int b = (int)(r0 / Hd);
+    const float* sb = seg + (long long)b * 4 * Hs * Ws;
+    const long long plane = (long long)Hs * Ws;
+    int hs[3], ws[3];
+    bool hv[3], wv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int h = hd + k - 1, w = wd + k - 1;
+      hv[k] = h >= 0 && h < Hd;
+      wv[k] = w >= 0 && w < Wd;
+      hs[k] = min((int)floorf((hv[k] ? h : 0) * sh), Hs - 1);
+      ws[k] = min((int)floorf((wv[k] ? w : 0) * sw), Ws - 1);
+    }
+    float v[40];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const bool ok = hv[t / 3] && wv[t % 3];
+      const float* q = sb + (long long)hs[t / 3] * Ws + ws[t % 3];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[t * 4 + c] = ok ? q[c * plane] : 0.f;
+    }
+    v[36] = v[37] = v[38] = v[39] = 0.f;
+    bf16* o = out + p * 64;
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) st_stream8(o + ch * 8, pack8(v + ch * 8));
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float one[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1.f};   // channels 62, 63 = 1: the bias columns of the GEMM
+    st_stream8(o + 40, pack8(z));
+    st_stream8(o + 48, pack8(z));
+    st_stream8(o + 56, pack8(one));
+  }
+}
 // OIHW (Cout, C, 3, 3) fp32 -> bf16 [Cout][64] with k = (r*3+s)*C + c   (and the adjoint for the weight gradient)
 __global__ void pack_im2col_kernel(const float* __restrict__ w, int Cout, int C, bf16* __restrict__ out) {
   GRID_STRIDE(i, (long long)Cout * 64) {
@@ -127,15 +167,16 @@ __global__ void pack_im2col_kernel(const float* __restrict__ w, int Cout, int C,
     out[i] = __float2bfloat16(v);
   }
 }
-__global__ void unpack_im2col_kernel(const float* __restrict__ dwp, int Cout, int C, float* __restrict__ dw) {
+__global__ void unpack_im2col_kernel(const float* __restrict__ dwp, int Cout, int C, float* __restrict__ dw, float* __restrict__ db) {
   GRID_STRIDE(i, (long long)Cout * C * 9) {
     const int t = (int)(i % 9);
     const long long r = i / 9;
     const int c = (int)(r % C), co = (int)(r / C);
     dw[i] = dwp[(long long)co * 64 + t * C + c];
+    if (db && t == 0 && c == 0) db[co] = dwp[(long long)co * 64 + 63];   // gradient of the bias column
   }
 }
-
+// layout
 __global__ void nchw2nhwc_kernel(const float* __restrict__ x, int C, int H, int W, long long n, bf16* __restrict__ y) {
   GRID_STRIDE(i, n) {
     const int c = (int)(i % C);
@@ -256,6 +297,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, PackGeom g, c
 constexpr int PACK_MAX_JOBS = 40;
 struct PackJob {
   const float* w;
+  const float* bias;
   bf16* out;
   PackGeom g;
   int transposed, im2col;
@@ -282,8 +324,14 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const __grid_con
   }
   const int kk = g.kh * g.kw;
   const float* src = J.w + ((long long)co * g.Cin + ci) * kk;
-  if (J.im2col) {  // [Cout][64], k = (r*3+s)*C + c
+  if (J.im2col) {  // [Cout][64], k = (r*3+s)*C + c ; columns 62, 63 = bias (multiply the constant-one channels)
     for (int tt = 0; tt < 9; ++tt) J.out[(long long)co * 64 + tt * g.Cin + ci] = __float2bfloat16(src[tt]);
+    if (J.bias && ci == 0) {  // bias = hi + lo in two bf16 columns (2^-17 relative precision instead of 2^-9)
+      const float bv = J.bias[co];
+      const bf16 hi = __float2bfloat16(bv);
+      J.out[(long long)co * 64 + 63] = hi;
+      J.out[(long long)co * 64 + 62] = __float2bfloat16(bv - __bfloat162float(hi));
+    }
     return;
   }
   const int CinP = g.stride == 2 ? 4 * g.CinPad : g.CinPad;
@@ -661,18 +709,29 @@ __global__ void bilinear_bwd_kernel(const bf16* __restrict__ dy, int Hs, int Ws,
   }
 }
 
+// one thread per pixel of the (2B, H, W) batch: nc + 1 coalesced fp32 reads, Cpad bf16 written as 16-byte vectors
 __global__ void make_d_input_kernel(const float* __restrict__ seg, const float* __restrict__ fake, const float* __restrict__ real, int B,
-                                    int nc, long long HW, int Cpad, long long n, bf16* __restrict__ out) {
-  GRID_STRIDE(i, n) {
-    const int c = (int)(i % Cpad);
-    long long p = i / Cpad;
+                                    int nc, long long HW, int Cpad, long long npix, bf16* __restrict__ out) {
+  GRID_STRIDE(p, npix) {
     const long long hw = p % HW;
     const int b2 = (int)(p / HW);
     const int b = b2 % B;
-    float v = 0.f;
-    if (c < nc) v = seg[((long long)b * nc + c) * HW + hw];
-    else if (c == nc) v = (b2 < B ? fake : real)[(long long)b * HW + hw];
-    out[i] = __float2bfloat16(v);
+    const float* sp = seg + (long long)b * nc * HW + hw;
+    const float img = (b2 < B ? fake : real)[(long long)b * HW + hw];
+    bf16* o = out + p * Cpad;
+    if ((Cpad & 7) == 0) {
+      for (int c0 = 0; c0 < Cpad; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j;
+          v[j] = c < nc ? sp[(long long)c * HW] : (c == nc ? img : 0.f);
+        }
+        st_stream8(o + c0, pack8(v));
+      }
+    } else {
+      for (int c = 0; c < Cpad; ++c) o[c] = __float2bfloat16(c < nc ? sp[(long long)c * HW] : (c == nc ? img : 0.f));
+    }
   }
 }
 __global__ void d_input_grad_kernel(const bf16* __restrict__ dxin, int nc, int Cpad, long long n, float* __restrict__ dfake) {
@@ -985,11 +1044,15 @@ int s2e_seg_nearest_nhwc(const float* seg, int B, int C, int Hs, int Ws, int Hd,
   return S2E_OK;
 }
 int s2e_seg_im2col3x3(const float* seg, int B, int C, int Hs, int Ws, int Hd, int Wd, void* out, void* stream) {
-  S2E_REQUIRE(9 * C <= 64, "seg_im2col3x3: 9*C must fit 64 channels (C=%d)", C);
+  S2E_REQUIRE(9 * C <= 62, "seg_im2col3x3: 9*C + the two constant-one channels must fit 64 channels (C=%d)", C);
   const long long n = (long long)B * Hd * Wd * 8;
   if (!n) return S2E_OK;
-  seg_im2col_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(seg, C, Hs, Ws, Hd, Wd, (float)Hs / (float)Hd, (float)Ws / (float)Wd,
-                                                                n, (bf16*)out);
+  if (C == 4)
+    seg_im2col_c4_kernel<<<grid1d(n / 8, 128), 128, 0, (cudaStream_t)stream>>>(seg, Hs, Ws, Hd, Wd, (float)Hs / (float)Hd,
+                                                                              (float)Ws / (float)Wd, n / 8, (bf16*)out);
+  else
+    seg_im2col_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(seg, C, Hs, Ws, Hd, Wd, (float)Hs / (float)Hd, (float)Ws / (float)Wd,
+                                                                  n, (bf16*)out);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -999,8 +1062,8 @@ int s2e_pack_weight_im2col3x3(const float* w, int Cout, int C, void* out, void* 
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
-int s2e_unpack_wgrad_im2col3x3(const float* dwp, int Cout, int C, float* dw, void* stream) {
-  unpack_im2col_kernel<<<grid1d((long long)Cout * C * 9), NT, 0, (cudaStream_t)stream>>>(dwp, Cout, C, dw);
+int s2e_unpack_wgrad_im2col3x3(const float* dwp, int Cout, int C, float* dw, float* db, void* stream) {
+  unpack_im2col_kernel<<<grid1d((long long)Cout * C * 9), NT, 0, (cudaStream_t)stream>>>(dwp, Cout, C, dw, db);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -1216,7 +1279,8 @@ int s2e_make_d_input(const float* seg, const float* fake, const float* real, int
   S2E_REQUIRE(Cpad > nc, "make_d_input: Cpad must exceed nc");
   const long long n = (long long)2 * B * H * W * Cpad;
   if (!n) return S2E_OK;
-  make_d_input_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(seg, fake, real, B, nc, (long long)H * W, Cpad, n, (bf16*)out);
+  const long long npix = 2LL * B * H * W;
+  make_d_input_kernel<<<grid1d(npix), NT, 0, (cudaStream_t)stream>>>(seg, fake, real, B, nc, (long long)H * W, Cpad, npix, (bf16*)out);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -1335,11 +1399,12 @@ int s2e_pack_weight_multi(const s2e_pack_job_t* jobs, int n_jobs, void* stream) 
       S2E_REQUIRE(s.w_oihw && s.out_bf16 && s.Cout > 0 && s.Cin > 0, "pack_weight_multi: job %d incomplete", base + k);
       PackJob& J = t.j[k];
       J.w = s.w_oihw;
+      J.bias = s.im2col3x3 ? s.bias : nullptr;
       J.out = (bf16*)s.out_bf16;
       J.im2col = s.im2col3x3;
       J.transposed = s.transposed;
       if (s.im2col3x3) {
-        S2E_REQUIRE(9 * s.Cin <= 64, "pack_weight_multi: im2col3x3 needs 9*C <= 64");
+        S2E_REQUIRE(9 * s.Cin <= 62, "pack_weight_multi: im2col3x3 needs 9*C <= 62");
         J.g = make_pack_geom(s.Cout, s.Cin, 3, 3, 1, 1);
         J.transposed = 0;
       } else {

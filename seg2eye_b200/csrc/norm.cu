@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
 }
 
 // ---------------------------------------------------------------- SPADE+Style backward
-// pass 1: per (sample, channel) sums  S1 = sum dxh, S2 = sum dxh*xh, S3 = sum g*x, S4 = sum g
+// pass 1: per (sample, channel) sums  S1 = sum dxh, S2 = sum dxh*xh, S3 = sum g*x, S4 = sum g, S5 = sum g*xh
+// (S4 / S5 are also the per-channel sums of dbeta / dgamma, i.e. the bias gradients of the gamma|beta convolution)
 __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ outp,
                                                                     const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -204,22 +205,26 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
       a[1][j] = fmaf(dxh, xh, a[1][j]);
       a[2][j] = fmaf(g, xf[j], a[2][j]);
       a[3][j] += g;
+      a[4][j] = fmaf(g, xh, a[4][j]);
     }
   };
   auto four = [&](long long p, long long st, int c, float(*a)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) one(p + i * st, c, a);   // the compiler hoists the independent streaming loads
   };
-  block_channel_reduce<4>(C, b0, b1, racc + (size_t)b * 4 * C, one, four);
+  block_channel_reduce<5>(C, b0, b1, racc + (size_t)b * 5 * C, one, four);
 }
 
-// fold the per-sample sums: m1/m2 per stat group (float [G][2][C]) and dstyle [B][2C]
+// fold the per-sample sums: m1/m2 per stat group (float [G][2][C]), dstyle [B][2C] and, optionally, chsum [3][C] =
+// per-channel sums over the whole batch of dgamma, dbeta and dx.  The last one needs no extra pass: the normalisation
+// part of dx sums to zero over the pixels its statistics were taken from, so sum dx = sum_b (1 + s0[b]) * S4[b].
 __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int B, int C, int per_sample, double count,
-                                            float* __restrict__ m12, float* __restrict__ dstyle) {
+                                            const float* __restrict__ style, float* __restrict__ m12,
+                                            float* __restrict__ dstyle, float* __restrict__ chsum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
-  const double* r = racc + (size_t)b * 4 * C;
+  const double* r = racc + (size_t)b * 5 * C;
   if (dstyle) {
     dstyle[(size_t)b * 2 * C + c] = (float)r[2 * C + c];
     dstyle[(size_t)b * 2 * C + C + c] = (float)r[3 * C + c];
@@ -227,14 +232,26 @@ __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int
   if (per_sample) {
     m12[(size_t)b * 2 * C + c] = (float)(r[c] / count);
     m12[(size_t)b * 2 * C + C + c] = (float)(r[C + c] / count);
-  } else if (b == 0) {
-    double s1 = 0, s2 = 0;
+  }
+  if (b == 0 && (!per_sample || chsum)) {
+    double s1 = 0, s2 = 0, sg = 0, sb = 0, sx = 0;
     for (int bb = 0; bb < B; ++bb) {
-      s1 += racc[(size_t)bb * 4 * C + c];
-      s2 += racc[(size_t)bb * 4 * C + C + c];
+      const double* q = racc + (size_t)bb * 5 * C;
+      s1 += q[c];
+      s2 += q[C + c];
+      sb += q[3 * C + c];
+      sg += q[4 * C + c];
+      sx += (1.0 + (double)style[(size_t)bb * 2 * C + c]) * q[3 * C + c];
     }
-    m12[c] = (float)(s1 / count);
-    m12[C + c] = (float)(s2 / count);
+    if (!per_sample) {
+      m12[c] = (float)(s1 / count);
+      m12[C + c] = (float)(s2 / count);
+    }
+    if (chsum) {
+      chsum[c] = (float)sg;
+      chsum[C + c] = (float)sb;
+      chsum[2 * C + c] = (float)sx;
+    }
   }
 }
 
@@ -508,18 +525,19 @@ int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const
 
 int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act, double* racc,
-                        void* dx, int dx_accumulate, void* dgb, float* dstyle, void* stream) {
+                        void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, void* stream) {
   S2E_REQUIRE(C % 8 == 0, "spade_style_bwd needs C %% 8 == 0 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
-  // racc: double [B][4][C] followed by float m12 [B][2][C]
-  S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 4 * C, st));
-  float* m12 = (float*)(racc + (size_t)B * 4 * C);
+  // racc: double [B][5][C] followed by float m12 [B][2][C]
+  S2E_REQUIRE(!(chsum && dx_accumulate), "spade_style_bwd: chsum describes dx only when dx is not accumulated into");
+  S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 5 * C, st));
+  float* m12 = (float*)(racc + (size_t)B * 5 * C);
   dim3 grid(red_chunks(HW, B), B);
   spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x,
                                                                 (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc);
   S2E_LAUNCH_CHECK();
   const double count = per_sample ? (double)HW : (double)B * HW;
-  spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, m12, dstyle);
+  spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, m12, dstyle, chsum);
   S2E_LAUNCH_CHECK();
   dim3 grid2(ew_chunks(HW, B, C), B);
   spade_style_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x, (const bf16*)gb, style,

@@ -128,7 +128,7 @@ class SPADE(nn.Module):
 
     def gamma_beta(self, segmap, h, w):
         conv = self.mlp_shared[0]
-        if 9 * conv.in_channels <= 64 and conv.cfg.kh == 3:
+        if 9 * conv.in_channels <= 62 and conv.cfg.kh == 3:
             # thin segmap: its 64-channel im2col (shared by every SPADE of this resolution within one generator
             # forward) turns mlp_shared into a K=64 GEMM on the tensor-core path, forward and weight gradient
             col = seg_im2col_cached(segmap, h, w)

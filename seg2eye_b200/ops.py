@@ -165,10 +165,11 @@ def mark_updated(params):
 
 def _pack_jobs(entry, weights):
     jobs = []
-    if entry.im2col:
+    if entry.im2col:       # weights = (weight,) or (weight, bias): the bias goes to column 63
         w = weights[0].detach()
         j = L.PackJob()
         j.w_oihw, j.out_bf16, j.Cout, j.Cin, j.im2col3x3 = w.data_ptr(), entry.buf.data_ptr(), w.shape[0], w.shape[1], 1
+        j.bias = weights[1].detach().data_ptr() if len(weights) > 1 else None
         return [j]
     cfg = entry.cfg
     ctot = sum(w.shape[0] for w in weights)
@@ -237,9 +238,11 @@ def packed_weights(weights, cfg, transposed):
     return _packed(key, weights, cfg, transposed, False, len(conv_taps(cfg)) * ctot * cinp)
 
 
-def packed_weight_im2col(weight):
-    """bf16 [Cout][64] copy of a thin 3x3 weight (k = (r*3+s)*C + c) for the im2col'd segmap GEMM."""
-    return _packed((id(weight), "im2col"), (weight,), None, False, True, weight.shape[0] * 64)
+def packed_weight_im2col(weight, bias=None):
+    """bf16 [Cout][64] copy of a thin 3x3 weight (k = (r*3+s)*C + c) for the im2col'd segmap GEMM; `bias` fills
+    columns 62 | 63 (lo | hi part), which multiply the two constant-one channels of the im2col'd segmap."""
+    ws = (weight,) if bias is None else (weight, bias)
+    return _packed((tuple(id(w) for w in ws), "im2col"), ws, None, False, True, weight.shape[0] * 64)
 
 
 def space_to_depth(x):
@@ -353,7 +356,12 @@ class TapConvFn(torch.autograd.Function):
                     gw[i] = g
                 off += w.shape[0]
         if any(need_b):
-            sums = channel_sums(dpre, B, Ho * Wo, Cout) if Cout % 8 == 0 else dpre.float().sum(dim=(0, 1, 2))
+            pre = getattr(dy, '_s2e_chsum', None) if cfg.act == L.ACT_NONE else None
+            if pre is not None and pre.numel() == Cout:
+                _state["chsum_hits"] = _state.get("chsum_hits", 0) + 1
+                sums = pre      # the producer of dy (SPADE+Style backward) already reduced it over the pixels
+            else:
+                sums = channel_sums(dpre, B, Ho * Wo, Cout) if Cout % 8 == 0 else dpre.float().sum(dim=(0, 1, 2))
             off = 0
             for i in range(ctx.n_b):
                 n = weights[i].shape[0]
@@ -484,13 +492,18 @@ class SpadeStyleFn(torch.autograd.Function):
         x, gb, style, mean, rstd, out = ctx.saved_tensors
         dout = _c(dout)
         B, H, W, Cc = x.shape
-        racc = torch.empty(B * 4 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
+        racc = torch.empty(B * 5 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
         dx = torch.empty_like(x)
         dgb = torch.empty_like(gb)
         dstyle = torch.empty_like(style)
+        chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
         L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
                L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), 0, L.ptr(dgb),
-               L.ptr(dstyle), L.stream())
+               L.ptr(dstyle), L.ptr(chsum), L.stream())
+        # per-channel sums of the two gradients, for the bias gradients of the convolutions that receive them as dy
+        # (TapConvFn.backward picks the attribute up when the tensor reaches it unmodified; otherwise it sums itself)
+        dgb._s2e_chsum = chsum[:2 * Cc]
+        dx._s2e_chsum = chsum[2 * Cc:]
         return dx, dgb, dstyle, None, None, None, None, None
 
 
@@ -722,18 +735,17 @@ class SegConvFn(torch.autograd.Function):
         ctx.act_grad_fused = act_grad_fused   # the consumer already applied the ReLU mask to the gradient it sends back
         B, H, W, K = col.shape
         Cout, Cs = weight.shape[0], weight.shape[1]
-        assert K == 64 and weight.shape[2:] == (3, 3) and 9 * Cs <= 64
-        wp = packed_weight_im2col(weight)
+        assert K == 64 and weight.shape[2:] == (3, 3) and 9 * Cs <= 62
+        wp = packed_weight_im2col(weight, bias)    # the bias rides in column 63 of the GEMM (constant-one channel)
         y = torch.empty(B, H, W, Cout, dtype=BF16, device=col.device)
         d = _desc(B, H, W, 64, H, W, Cout, [(0, 0)], act)
         flops = 2.0 * B * H * W * Cout * Cs * 9
         impl = _pick(Cout % 8 == 0)
         if impl == L.IMPL_TC:
-            _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(col), L.ptr(wp), L.ptr(bias.detach()) if bias is not None else None,
-                        None, L.ptr(y), impl, L.stream(), tag="fwd-seg B%d %dx%d Cin64 Cout%d T1" % (B, H, W, Cout))
+            _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(col), L.ptr(wp), None, None, L.ptr(y), impl, L.stream(),
+                        tag="fwd-seg B%d %dx%d Cin64 Cout%d T1" % (B, H, W, Cout))
         else:
-            L.call("s2e_tapconv_fwd", d, L.ptr(col), L.ptr(wp), L.ptr(bias.detach()) if bias is not None else None, None,
-                   L.ptr(y), impl, L.stream())
+            L.call("s2e_tapconv_fwd", d, L.ptr(col), L.ptr(wp), None, None, L.ptr(y), impl, L.stream())
         ctx.act, ctx.flops, ctx.cs, ctx.has_b = act, flops, Cs, bias is not None
         ctx.skip_wgrad = _state["skip_wgrad"]
         ctx.save_for_backward(col, y, weight)
@@ -751,7 +763,8 @@ class SegConvFn(torch.autograd.Function):
         else:
             dpre = dy
         gw = gb = None
-        if ctx.needs_input_grad[1] and not ctx.skip_wgrad:
+        need_b = ctx.has_b and ctx.needs_input_grad[2] and not ctx.skip_wgrad
+        if (ctx.needs_input_grad[1] or need_b) and not ctx.skip_wgrad:
             dwp = torch.zeros(Cout * 64, dtype=F32, device=dy.device)
             d = _desc(B, H, W, 64, H, W, Cout, [(0, 0)], L.ACT_NONE)
             impl = _pick(Cout >= 64 and Cout % 8 == 0)
@@ -761,9 +774,8 @@ class SegConvFn(torch.autograd.Function):
             else:
                 L.call("s2e_tapconv_wgrad", d, L.ptr(col), L.ptr(dpre), L.ptr(dwp), impl, st)
             gw = torch.empty_like(weight)
-            L.call("s2e_unpack_wgrad_im2col3x3", L.ptr(dwp), Cout, ctx.cs, L.ptr(gw), st)
-        if ctx.has_b and ctx.needs_input_grad[2] and not ctx.skip_wgrad:
-            gb = channel_sums(dpre, B, H * W, Cout) if Cout % 8 == 0 else dpre.float().sum(dim=(0, 1, 2))
+            gb = torch.empty(Cout, dtype=F32, device=dy.device) if need_b else None   # column 63 = bias gradient
+            L.call("s2e_unpack_wgrad_im2col3x3", L.ptr(dwp), Cout, ctx.cs, L.ptr(gw), L.ptr(gb), st)
         return None, gw, gb, None, None
 
 

@@ -179,7 +179,8 @@ def test_seg_im2col_conv_matches_conv3x3(S, impl_name):
     col = ops.seg_im2col(seg.cuda(), hd, wd)
     # bit-exact im2col: channel (r*3+s)*C + c
     ref_col = F.unfold(segr, 3, padding=1).view(B, C, 9, hd, wd).permute(0, 3, 4, 2, 1).reshape(B, hd, wd, 9 * C)
-    assert torch.equal(col[..., :9 * C].float().cpu(), ref_col) and float(col[..., 9 * C:].abs().max()) == 0.0
+    assert torch.equal(col[..., :9 * C].float().cpu(), ref_col) and float(col[..., 9 * C:62].abs().max()) == 0.0
+    assert bool((col[..., 62:] == 1).all())    # constant-one channels: carry the bias (and its gradient) through the GEMM
     wc, bc = w.cuda().requires_grad_(), b.cuda().requires_grad_()
     with ops.force_impl(L.IMPL_TC if impl_name == "tc" else L.IMPL_SIMT):
         y = ops.SegConvFn.apply(col, wc, bc, L.ACT_RELU)
@@ -289,10 +290,14 @@ def test_spade_style_fwd_bwd(S, per_sample, act, C):
     sc = style.cuda().requires_grad_()
     rmc, rvc, nbt = rm0.cuda(), rv0.cuda(), torch.tensor(3, device="cuda")
     cfg = ops.NormCfg(per_sample, act, True, 0.1, 1e-5)
+    seen = {}
+    xin, gbin = ops.AddFn.apply(xc, torch.zeros_like(xc)), ops.AddFn.apply(gbc, torch.zeros_like(gbc))   # non-leaf inputs
+    xin.register_hook(lambda t: seen.__setitem__("x", t))
+    gbin.register_hook(lambda t: seen.__setitem__("gb", t))
     if per_sample:
-        out = ops.SpadeStyleFn.apply(xc, gbc, sc, cfg, None, None, None)
+        out = ops.SpadeStyleFn.apply(xin, gbin, sc, cfg, None, None, None)
     else:
-        out = ops.SpadeStyleFn.apply(xc, gbc, sc, cfg, rmc, rvc, nbt)
+        out = ops.SpadeStyleFn.apply(xin, gbin, sc, cfg, rmc, rvc, nbt)
     out.backward(nhwc(dout))
     torch.cuda.synchronize()
     assert rel(nchw(out), out_r) < 5e-3
@@ -302,6 +307,12 @@ def test_spade_style_fwd_bwd(S, per_sample, act, C):
     assert rel(sc.grad, sr.grad) < TOL_ACT
     if not per_sample:
         assert rel(rmc, rm) < 1e-4 and rel(rvc, rv) < 1e-4 and int(nbt) == 4
+    # per-channel sums of dgamma | dbeta and of dx that ride on the gradients (bias gradients of the neighbouring convs)
+    s_gb, s_x = seen["gb"]._s2e_chsum, seen["x"]._s2e_chsum
+    ref_gb = torch.cat([gr.grad.sum(dim=(0, 2, 3)), br.grad.sum(dim=(0, 2, 3))])
+    assert rel(s_gb, ref_gb) < 2e-3
+    ref_x = xr.grad.sum(dim=(0, 2, 3))
+    assert float((s_x.cpu() - ref_x).abs().max()) < 2e-3 * float(xr.grad.abs().sum(dim=(0, 2, 3)).max())
 
 
 @pytest.mark.parametrize("act,C", [(1, 64), (0, 512), (1, 16)])

@@ -244,8 +244,13 @@ def _grad_errors(ctx, **over):
     m = tr.pix2pix_model
     data = {k: v.clone() for k, v in ctx.batch.items()}
     m.train()
+    from seg2eye_b200 import ops
+    hits0 = ops._state.get("chsum_hits", 0)
     g_losses, _ = m(data, mode="generator")
     sum(g_losses.values()).mean().backward()
+    # the SPADE+Style backward hands per-channel sums to the gamma|beta convs (18) and to every conv_0 (7): their bias
+    # gradients must come from there, not from another pass over the gradient tensors
+    assert ops._state.get("chsum_hits", 0) - hits0 >= 25, ops._state.get("chsum_hits", 0) - hits0
     gG = {k: p.grad.detach().cpu().clone() for k, p in m.netG.named_parameters() if p.grad is not None}
     gE = {k: p.grad.detach().cpu().clone() for k, p in m.netE.named_parameters() if p.grad is not None}
     assert all(p.grad is None for p in m.netD.parameters())   # D weight gradients are skipped in the G step
