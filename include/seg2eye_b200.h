@@ -90,6 +90,9 @@ typedef struct {
   int ktile_w, ktile_h, ktile_b; /* TC wgrad pixel tile (multiple of 16, <=64 px); 0 = choose inside */
   const void* relu_mask;         /* optional bf16 tensor shaped like y: y is zeroed where mask <= 0 (fused ReLU backward
                                     when the operator computes the data gradient of a layer whose input came from a ReLU) */
+  const void* residual;          /* optional bf16 tensor shaped like y, added after the activation: the `x_s + dx` of
+                                    architecture.py:44 fused into conv_1's epilogue (tcgen05 path only) */
+  int bias_n;                    /* number of valid bias entries, 0 = Cout (a channel-padded output) */
 } s2e_conv_t;
 
 int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,

@@ -20,7 +20,8 @@ class ConvDesc(C.Structure):
                 ("Ho", C.c_int), ("Wo", C.c_int), ("Cout", C.c_int), ("ntaps", C.c_int),
                 ("tap_dy", C.c_int * MAX_TAPS), ("tap_dx", C.c_int * MAX_TAPS), ("act", C.c_int),
                 ("tile_w", C.c_int), ("tile_h", C.c_int), ("tile_b", C.c_int),
-                ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p)]
+                ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p),
+                ("residual", C.c_void_p), ("bias_n", C.c_int)]
 
 
 class SnJob(C.Structure):

@@ -85,7 +85,9 @@ struct FwdParams {
   int TW, TH, TB;
   int Cout, kc_per_tap, act;
   int B, Ho, Wo;
-  const bf16* mask;
+  const bf16* mask;   // fused ReLU backward: zero the output where mask <= 0
+  const bf16* res;    // fused residual: output += res (same shape as y); never together with mask
+  int bias_n;         // valid bias entries (<= Cout; the rest of a channel-padded output gets no bias)
   uint32_t a_box_bytes;
   const float* bias;
   const float* scale;
@@ -259,19 +261,20 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int n0 = (t % p.tiles_n) * BN;
       const int grp = t / p.tiles_n;
-      if (et < BN) s_bias[et] = (p.bias && n0 + et < p.Cout) ? __ldg(p.bias + n0 + et) : 0.f;
+      if (et < BN) s_bias[et] = (p.bias && n0 + et < p.bias_n) ? __ldg(p.bias + n0 + et) : 0.f;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < Cfg::MT; ++j) {
         int w0, h0, b0;
         subtile_origin(p, grp * Cfg::MT + j, w0, h0, b0);
+        const bf16* side = p.mask ? p.mask : p.res;   // per-pixel side input shaped like the output (mask or residual)
         const bf16* mrow = nullptr;
-        if (p.mask) {
+        if (side) {
           const int tw = row % p.TW, r2 = row / p.TW;
           const int th = r2 % p.TH, tb = r2 / p.TH;
           if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo)
-            mrow = p.mask + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
+            mrow = side + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
         }
 #pragma unroll 1
         for (int ch = 0; ch < BN / 64; ++ch) {
@@ -283,7 +286,8 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           ptx::tmem_ld_32x32(taddr, r);
           uint4 mk[4] = {make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u),
                          make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u)};
-          if (mrow) {  // host guarantees Cout % 64 == 0 when a mask is given
+          if (p.res) mk[0] = mk[1] = mk[2] = mk[3] = make_uint4(0u, 0u, 0u, 0u);   // rows outside the tensor add nothing
+          if (mrow) {  // host guarantees Cout % 64 == 0 when a mask / residual is given
 #pragma unroll
             for (int i = 0; i < 4; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + half * 32) + i);
           }
@@ -297,14 +301,25 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int i = 0; i < 4; ++i) {
             const float4 b0v = bsrc[2 * i], b1v = bsrc[2 * i + 1];
             uint32_t pk[4];
-            pk[0] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 0]), scale, b0v.x)),
-                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 1]), scale, b0v.y)));
-            pk[1] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 2]), scale, b0v.z)),
-                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 3]), scale, b0v.w)));
-            pk[2] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 4]), scale, b1v.x)),
-                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 5]), scale, b1v.y)));
-            pk[3] = pack2_bf16(act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 6]), scale, b1v.z)),
-                               act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 7]), scale, b1v.w)));
+            float v[8];
+            v[0] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 0]), scale, b0v.x));
+            v[1] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 1]), scale, b0v.y));
+            v[2] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 2]), scale, b0v.z));
+            v[3] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 3]), scale, b0v.w));
+            v[4] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 4]), scale, b1v.x));
+            v[5] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 5]), scale, b1v.y));
+            v[6] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 6]), scale, b1v.z));
+            v[7] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 7]), scale, b1v.w));
+            if (p.res) {  // residual add in fp32, one rounding on the sum (bf16 pair: low half = even channel)
+              const uint32_t rw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[2 * e] += __uint_as_float(rw[e] << 16);
+                v[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pk[e] = pack2_bf16(v[2 * e], v[2 * e + 1]);
             if (p.mask) {  // keep a value only where the bf16 mask element is > 0 (sign clear and magnitude non-zero)
               const uint32_t mw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
 #pragma unroll
@@ -393,7 +408,10 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.Ho = d->Ho;
   p.Wo = d->Wo;
   p.mask = (const bf16*)d->relu_mask;
-  S2E_REQUIRE(!p.mask || d->Cout % 64 == 0, "tapconv_fwd: relu_mask needs Cout %% 64 == 0 on the tcgen05 path");
+  p.res = (const bf16*)d->residual;
+  p.bias_n = d->bias_n > 0 ? d->bias_n : d->Cout;
+  S2E_REQUIRE(!(p.mask && p.res), "tapconv_fwd: relu_mask and residual are mutually exclusive");
+  S2E_REQUIRE(!(p.mask || p.res) || d->Cout % 64 == 0, "tapconv_fwd: relu_mask / residual need Cout %% 64 == 0 on the tcgen05 path");
   p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);
   p.bias = bias;
   p.scale = scale;

@@ -239,43 +239,53 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
 }
 
 // K2 tiled variant for conv_img (64 -> 1, 3x3, stride 1): every input pixel is read from global memory ONCE per tile
-// (plus a one-pixel halo) instead of once per tap.  Phase 1: 8 lanes per input pixel form the nine per-tap dot products
-// d[pixel][t] = x[pixel] . W[t] (tap weights in registers) and park them in shared memory; phase 2: one thread per
-// output pixel adds its nine neighbours' entries  y[p] = sum_t d[p + tap_t][t].
+// (plus a one-pixel halo) instead of once per tap.  Phase 0: the whole halo tile is staged in shared memory with
+// cp.async (every 16-byte chunk in flight at once; out-of-image pixels are zero-filled).  Phase 1: 8 lanes per input
+// pixel form the nine per-tap dot products d[pixel][t] = x[pixel] . W[t] (tap weights in shared memory, read as
+// broadcasts) and park them in shared memory.  Phase 2: one thread per output pixel adds its nine neighbours' entries
+// y[p] = sum_t d[p + tap_t][t].
 constexpr int T1_TW = 32, T1_TH = 8, T1_HW = T1_TW + 2, T1_NHP = (T1_TH + 2) * T1_HW;
-__global__ void __launch_bounds__(256) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
-                                                             const float* __restrict__ bias, const float* __restrict__ scale,
-                                                             bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h) {
-  __shared__ float d[T1_NHP * 9];
-  const int sub = threadIdx.x & 7;
-  float wreg[9][8];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (t < g.ntaps) unpack8(*reinterpret_cast<const bf16x8*>(wp + (long long)t * 64 + sub * 8), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wreg[t][j] = f[j];
-  }
+constexpr int T1_SMEM = T1_NHP * 128 + T1_NHP * 9 * 4 + 9 * 64 * 4;
+__global__ void __launch_bounds__(256, 3) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                                const float* __restrict__ bias, const float* __restrict__ scale,
+                                                                bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h) {
+  extern __shared__ __align__(16) uint8_t t1_smem[];
+  bf16* xs = reinterpret_cast<bf16*>(t1_smem);                               // [T1_NHP][64]
+  float* d = reinterpret_cast<float*>(t1_smem + T1_NHP * 128);               // [T1_NHP][9]
+  float* ws = d + T1_NHP * 9;                                                // [9][64]
   int tile = blockIdx.x;
   const int tw_idx = tile % tiles_w;
   tile /= tiles_w;
   const int th_idx = tile % tiles_h;
   const int b = tile / tiles_h;
   const int h0 = th_idx * T1_TH - 1, w0 = tw_idx * T1_TW - 1;
-  const bf16* xb = x + (long long)b * g.Hi * g.Wi * 64 + sub * 8;
-#pragma unroll 2
-  for (int hp = threadIdx.x >> 3; hp < T1_NHP; hp += 32) {
+  const bf16* xb = x + (long long)b * g.Hi * g.Wi * 64;
+  for (int i = threadIdx.x; i < T1_NHP * 8; i += 256) {
+    const int hp = i >> 3, ch = i & 7;
     const int hh = hp / T1_HW, ww = hp - hh * T1_HW;
     const int hi = h0 + hh, wi = w0 + ww;
     const bool ok = hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi;
-    float xf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (ok) unpack8(ld_stream8(xb + ((long long)hi * g.Wi + wi) * 64), xf);
+    const bf16* src = ok ? xb + ((long long)hi * g.Wi + wi) * 64 + ch * 8 : xb;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + hp * 64 + ch * 8);
+    const int nbytes = ok ? 16 : 0;   // src-size 0 => the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) ws[i] = i < g.ntaps * 64 ? __bfloat162float(wp[i]) : 0.f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  for (int hp = threadIdx.x >> 3; hp < T1_NHP; hp += 32) {
+    float xf[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(xs + hp * 64 + sub * 8), xf);
     float part[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      float a = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a = fmaf(xf[j], wreg[t][j], a);
+      const float4 wa = *reinterpret_cast<const float4*>(ws + t * 64 + sub * 8);
+      const float4 wb = *reinterpret_cast<const float4*>(ws + t * 64 + sub * 8 + 4);
+      float a = xf[0] * wa.x;
+      a = fmaf(xf[1], wa.y, a); a = fmaf(xf[2], wa.z, a); a = fmaf(xf[3], wa.w, a);
+      a = fmaf(xf[4], wb.x, a); a = fmaf(xf[5], wb.y, a); a = fmaf(xf[6], wb.z, a); a = fmaf(xf[7], wb.w, a);
       a += __shfl_xor_sync(0xffffffffu, a, 1);
       a += __shfl_xor_sync(0xffffffffu, a, 2);
       a += __shfl_xor_sync(0xffffffffu, a, 4);
@@ -451,7 +461,12 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     for (int t = 0; t < d->ntaps; ++t) halo1 = halo1 && d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
     if (halo1) {
       const int tiles_w = ceil_div(d->Wo, T1_TW), tiles_h = ceil_div(d->Ho, T1_TH);
-      thin_out1_tile_kernel<<<(unsigned)(d->B * tiles_h * tiles_w), 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale,
+      static bool attr1 = false;
+      if (!attr1) {
+        S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out1_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
+        attr1 = true;
+      }
+      thin_out1_tile_kernel<<<(unsigned)(d->B * tiles_h * tiles_w), 256, T1_SMEM, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale,
                                                                                    (bf16*)y, g, tiles_w, tiles_h);
       S2E_LAUNCH_CHECK();
       return 1;

@@ -38,8 +38,8 @@ class SPADE_STYLE_ResnetBlock(nn.Module):
         # the shortcut runs first, as in the reference, so BN buffers / spectral vectors advance in the same order
         skip = self._shortcut_nhwc(x, seg, latent_style, stats_src)
         h = self.conv_0.forward_nhwc(self.norm_0.forward_nhwc(x, seg, latent_style, L.ACT_LRELU, stats_src))
-        h = self.conv_1.forward_nhwc(self.norm_1.forward_nhwc(h, seg, latent_style, L.ACT_LRELU))
-        return ops.AddFn.apply(skip, h)
+        # out = x_s + dx: the residual add rides in conv_1's epilogue
+        return self.conv_1.forward_nhwc(self.norm_1.forward_nhwc(h, seg, latent_style, L.ACT_LRELU), residual=skip)
 
     def forward(self, x, seg, latent_style):
         return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x), seg, latent_style))

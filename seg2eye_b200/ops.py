@@ -15,9 +15,11 @@ from . import _lib as L
 BF16 = torch.bfloat16
 F32 = torch.float32
 
-ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad", defaults=(False, 0))
+ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad cout_pad", defaults=(False, 0, 0))
 # cin_pad: the activations carry cin_pad >= Cin channels (zero padded), packed weights get zero columns for them
 # relu_in: the input of this convolution is the output of a ReLU whose backward is fused into our data-gradient epilogue
+# cout_pad: run a layer with very few output channels (the 1-channel PatchGAN head, K = 8192) on the tensor-core kernels
+#           with its output channels zero-padded to cout_pad; the caller sees the first Cout channels only
 
 _state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False}
 
@@ -172,7 +174,7 @@ def _pack_jobs(entry, weights):
         j.bias = weights[1].detach().data_ptr() if len(weights) > 1 else None
         return [j]
     cfg = entry.cfg
-    ctot = sum(w.shape[0] for w in weights)
+    ctot = max(sum(w.shape[0] for w in weights), cfg.cout_pad)
     off = 0
     for w in weights:
         wd = w.detach()
@@ -231,10 +233,10 @@ def _packed(key, weights, cfg, transposed, im2col, numel):
 
 def packed_weights(weights, cfg, transposed):
     """bf16 tap-major copy of one or more OIHW fp32 master weights (concatenated along Cout)."""
-    key = (tuple(id(w) for w in weights), transposed, cfg.kh, cfg.kw, cfg.stride, cfg.pad, cfg.cin_pad)
+    key = (tuple(id(w) for w in weights), transposed, cfg.kh, cfg.kw, cfg.stride, cfg.pad, cfg.cin_pad, cfg.cout_pad)
     cin_eff = max(weights[0].shape[1], cfg.cin_pad)
     cinp = cin_eff * 4 if cfg.stride == 2 else cin_eff
-    ctot = sum(w.shape[0] for w in weights)
+    ctot = max(sum(w.shape[0] for w in weights), cfg.cout_pad)
     return _packed(key, weights, cfg, transposed, False, len(conv_taps(cfg)) * ctot * cinp)
 
 
@@ -260,10 +262,14 @@ def channel_sums(x2d_c, B, HW, Cc):
 
 
 class TapConvFn(torch.autograd.Function):
-    """y = act(inv_sigma * conv(x, W) + b) for one or several weights concatenated along Cout."""
+    """y = act(inv_sigma * conv(x, W) + b) [+ res] for one or several weights concatenated along Cout.
+
+    res (optional, shaped like y): residual added in the tcgen05 epilogue (architecture.py:44 `x_s + dx`).
+    cfg.cout_pad: a layer with fewer than 8 output channels and a long reduction (the PatchGAN logit head) runs on the
+    tensor-core kernels with zero-padded output channels; forward returns the first Cout channels of the padded result."""
 
     @staticmethod
-    def forward(ctx, x, cfg, sn, n_w, *wb):
+    def forward(ctx, x, cfg, sn, n_w, res, *wb):
         weights, biases = wb[:n_w], wb[n_w:]
         x = _c(x)
         assert x.dtype == BF16 and x.dim() == 4
@@ -274,28 +280,42 @@ class TapConvFn(torch.autograd.Function):
         _, His, Wis, Cinp = xs.shape
         Ho, Wo = conv_out_hw(cfg, Hi, Wi)
         Cout = sum(w.shape[0] for w in weights)
+        padded = cfg.cout_pad > Cout and Cinp % 64 == 0 and cfg.cout_pad % 8 == 0 and _pick(True) == L.IMPL_TC
+        if not padded:
+            cfg = cfg._replace(cout_pad=0)
+        Cp = cfg.cout_pad if padded else Cout
         taps = conv_taps(cfg)
         wp = packed_weights(weights, cfg, False)
         bias = None
         if len(biases):
             bias = biases[0].detach() if len(biases) == 1 else torch.cat([b.detach() for b in biases])
         inv_sigma = sn[2] if sn is not None else None
-        y = torch.empty(B, Ho, Wo, Cout, dtype=BF16, device=x.device)
-        d = _desc(B, His, Wis, Cinp, Ho, Wo, Cout, taps, cfg.act)
-        impl = _pick(Cinp % 64 == 0 and Cout % 8 == 0)
+        y = torch.empty(B, Ho, Wo, Cp, dtype=BF16, device=x.device)
+        d = _desc(B, His, Wis, Cinp, Ho, Wo, Cp, taps, cfg.act)
+        d.bias_n = Cout
+        impl = _pick(Cinp % 64 == 0 and Cp % 8 == 0)
+        fuse_res = res is not None and impl == L.IMPL_TC and Cp % 64 == 0
+        if res is not None:
+            res = _c(res)
+            assert cfg.act == L.ACT_NONE and not padded and res.shape == y.shape and res.dtype == BF16
+            if fuse_res:
+                d.residual = L.ptr(res)
         flops = 2.0 * B * Ho * Wo * Cout * weights[0].shape[1] * cfg.kh * cfg.kw
         if impl == L.IMPL_TC:
             _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream(),
-                        tag="fwd B%d %dx%d Cin%d Cout%d T%d" % (B, Ho, Wo, Cinp, Cout, len(taps)))
+                        tag="fwd B%d %dx%d Cin%d Cout%d T%d" % (B, Ho, Wo, Cinp, Cp, len(taps)))
         else:
             L.call("s2e_tapconv_fwd", d, L.ptr(xs), L.ptr(wp), L.ptr(bias), L.ptr(inv_sigma), L.ptr(y), impl, L.stream())
+        if res is not None and not fuse_res:
+            L.call("s2e_add", L.ptr(y), L.ptr(res), y.numel(), L.ptr(y), L.stream())
         ctx.flops = flops
         ctx.cfg, ctx.sn, ctx.n_w, ctx.n_b = cfg, sn, n_w, len(biases)
         ctx.in_shape = (B, Hi, Wi, Cin)
         ctx.weights = weights
+        ctx.cout, ctx.cp = Cout, Cp
         ctx.skip_wgrad = _state["skip_wgrad"]
         ctx.save_for_backward(xs, y if cfg.act != L.ACT_NONE else None)
-        return y
+        return y[..., :Cout] if padded else y
 
     @staticmethod
     def backward(ctx, dy):
@@ -304,9 +324,14 @@ class TapConvFn(torch.autograd.Function):
         dy = _c(dy)
         B, Hi, Wi, Cin = ctx.in_shape
         _, His, Wis, Cinp = xs.shape
-        _, Ho, Wo, Cout = dy.shape
+        _, Ho, Wo, _ = dy.shape
+        Cout_true, Cout = ctx.cout, ctx.cp
         taps = conv_taps(cfg)
         st = L.stream()
+        dy_true = dy
+        if Cout != Cout_true:     # zero-padded output channels: the kernels see the padded gradient
+            dy = torch.zeros(B, Ho, Wo, Cout, dtype=BF16, device=dy.device)
+            dy[..., :Cout_true].copy_(dy_true)
         if cfg.act != L.ACT_NONE:
             dpre = torch.empty_like(dy)
             L.call("s2e_act_bwd", L.ptr(dy), L.ptr(y), dy.numel(), cfg.act, L.ptr(dpre), st)
@@ -332,8 +357,8 @@ class TapConvFn(torch.autograd.Function):
                 L.call("s2e_depth_to_space", L.ptr(dxs), B, Hi, Wi, Cin, L.ptr(dx), st)
             else:
                 dx = dxs
-        need_w = [ctx.needs_input_grad[4 + i] and not ctx.skip_wgrad for i in range(ctx.n_w)]
-        need_b = [ctx.needs_input_grad[4 + ctx.n_w + i] and not ctx.skip_wgrad for i in range(ctx.n_b)]
+        need_w = [ctx.needs_input_grad[5 + i] and not ctx.skip_wgrad for i in range(ctx.n_w)]
+        need_b = [ctx.needs_input_grad[5 + ctx.n_w + i] and not ctx.skip_wgrad for i in range(ctx.n_b)]
         gw = [None] * ctx.n_w
         gb = [None] * ctx.n_b
         if any(need_w):
@@ -360,6 +385,8 @@ class TapConvFn(torch.autograd.Function):
             if pre is not None and pre.numel() == Cout:
                 _state["chsum_hits"] = _state.get("chsum_hits", 0) + 1
                 sums = pre      # the producer of dy (SPADE+Style backward) already reduced it over the pixels
+            elif Cout != Cout_true:
+                sums = dy_true.float().sum(dim=(0, 1, 2))
             else:
                 sums = channel_sums(dpre, B, Ho * Wo, Cout) if Cout % 8 == 0 else dpre.float().sum(dim=(0, 1, 2))
             off = 0
@@ -368,11 +395,12 @@ class TapConvFn(torch.autograd.Function):
                 if need_b[i]:
                     gb[i] = sums[off:off + n].clone()
                 off += n
-        return (dx, None, None, None) + tuple(gw) + tuple(gb)
+        gres = dy_true if ctx.needs_input_grad[4] else None
+        return (dx, None, None, None, gres) + tuple(gw) + tuple(gb)
 
 
-def tap_conv(x, cfg, weights, biases=(), sn=None):
-    return TapConvFn.apply(x, cfg, sn, len(weights), *weights, *biases)
+def tap_conv(x, cfg, weights, biases=(), sn=None, residual=None):
+    return TapConvFn.apply(x, cfg, sn, len(weights), residual, *weights, *biases)
 
 
 def _sn_scratch_floats(rows, cols):

@@ -579,3 +579,64 @@ def test_spectral_batch_matches_torch(S):
         assert torch.equal(u, u0) and torch.equal(v, v0) and torch.equal(U[1], u0) and float(inv[0]) == float(inv[1])
         wm = w.view(w.shape[0], -1)
         assert abs(float(inv[0]) * float(torch.dot(u, torch.mv(wm, v))) - 1) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------ fused residual / padded head
+@pytest.mark.parametrize("impl_name,Cout", [("tc", 128), ("tc", 64), ("tc", 72), ("simt", 64)])
+def test_conv_residual_in_epilogue(S, impl_name, Cout):
+    """x_s + conv_1(h) (architecture.py:44): the residual rides in the tcgen05 epilogue (Cout % 64 == 0) or is added by
+    the add kernel (other shapes / SIMT); either way one op, same gradients (d res = dy)."""
+    L, ops = S
+    g = torch.Generator().manual_seed(21)
+    B, Cin, H, W = 2, 64, 21, 17
+    x = bf(torch.randn(B, Cin, H, W, generator=g))
+    w = bf(torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    r = bf(torch.randn(B, Cout, H, W, generator=g))
+    xr, wr, br, rr = [t.clone().requires_grad_() for t in (x, w, b, r)]
+    yr = F.conv2d(xr, wr * 0.8, br, padding=1) + rr
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc, rc = nhwc(x).requires_grad_(), nhwc(r).requires_grad_()
+    wc, bc = w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    u = F.normalize(torch.randn(Cout, generator=g), dim=0).cuda()
+    v = F.normalize(torch.randn(Cin * 9, generator=g), dim=0).cuda()
+    with ops.force_impl(L.IMPL_TC if impl_name == "tc" else L.IMPL_SIMT):
+        y = ops.tap_conv(xc, ops.ConvCfg(3, 3, 1, 1, L.ACT_NONE), (wc,), (bc,), (u, v, torch.tensor([0.8], device="cuda")), rc)
+        y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < 5e-3
+    assert torch.equal(nchw(rc.grad), dy)
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT and rel(bc.grad, br.grad) < TOL_ACT
+
+
+def test_one_channel_head_on_tensor_cores(S):
+    """PatchGAN logit head (512 -> 1, 4x4 s1 p2; discriminator.py:96) with cout_pad: zero-padded output channels on the
+    tcgen05 kernels; forward, data gradient, weight and bias gradient vs torch."""
+    L, ops = S
+    g = torch.Generator().manual_seed(22)
+    B, Cin, H, W = 3, 128, 11, 9
+    x = bf(torch.randn(B, Cin, H, W, generator=g))
+    w = bf(torch.randn(1, Cin, 4, 4, generator=g) / (Cin * 16) ** 0.5)
+    b = torch.randn(1, generator=g) * 0.1
+    xr, wr, br = [t.clone().requires_grad_() for t in (x, w, b)]
+    yr = F.conv2d(xr, wr, br, padding=2)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc, wc, bc = nhwc(x).requires_grad_(), w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    from seg2eye_b200 import ops as O2
+    O2.profile_begin()
+    y = ops.tap_conv(xc, ops.ConvCfg(4, 4, 1, 2, L.ACT_NONE, False, 0, 64), (wc,), (bc,))
+    assert y.shape == (B, H + 1, W + 1, 1)
+    y.backward(nhwc(dy))
+    prof = O2.profile_end()
+    assert prof["tc_n"] == 3      # forward, data gradient and weight gradient all ran on the tcgen05 kernels
+    assert rel(nchw(y), yr) < TOL_ACT
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
+    assert rel(wc.grad, wr.grad) < TOL_ACT and rel(bc.grad, br.grad) < TOL_ACT
+    # the layer picks the padded path by itself
+    from seg2eye_b200.models.networks.layers import Conv2d
+    conv = Conv2d(512, 1, 4, stride=1, padding=2).cuda()
+    x2 = bf(torch.randn(2, 512, 6, 5, generator=g))
+    y2 = conv.forward_nhwc(nhwc(x2))
+    ref = F.conv2d(x2, bf(conv.weight.detach().cpu()), conv.bias.detach().cpu(), padding=2)
+    assert y2.shape == (2, 7, 6, 1) and rel(nchw(y2), ref) < TOL_ACT
