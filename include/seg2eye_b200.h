@@ -168,13 +168,17 @@ int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* 
 int s2e_norm_finalize(const double* acc, int G, int C, double count, double count_unbiased, float eps, float* mean,
                       float* rstd, float* running_mean, float* running_var, float momentum,
                       int64_t* num_batches_tracked, void* stream);
+/* act_mask (nullable): one BIT per element, [B*HW][C/8] bytes, bit j of byte (p, c/8) = (out[p][c+j] > 0); all the
+ * backward pass needs to know about `out` (read instead of it: 0.125 B/element instead of 2). */
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd,
-                        int B, int HW, int C, int per_sample, int act, void* out, void* stream);
-/* backward: racc = scratch of B*5*C doubles + B*2*C floats, zeroed inside. `out` = saved forward output (sign for the
- * lrelu mask).  chsum (nullable, float [3][C]) receives the per-channel sums over the batch of dgamma, dbeta and dx --
- * the bias gradients of the gamma|beta convolution (normalization.py:88-89) and of the convolution that produced x
- * (architecture.py:24) -- which the statistics pass yields for free. */
-int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const void* gb, const float* style,
+                        int B, int HW, int C, int per_sample, int act, void* out, uint8_t* act_mask, void* stream);
+/* backward: racc = scratch of B*5*C doubles + B*2*C floats, zeroed inside. `act_mask` = the forward pass's mask (may be
+ * NULL when act == NONE).  chsum (nullable, float [3][C]) receives the per-channel sums over the batch of dgamma, dbeta
+ * and dx -- the bias gradients of the gamma|beta convolution (normalization.py:88-89) and of the convolution that
+ * produced x (architecture.py:24) -- which the statistics pass yields for free.  dx_accumulate != 0 adds into dx
+ * (two SPADE+Style blocks that share their input, norm_0 / norm_s of architecture.py:51-58, write ONE gradient buffer);
+ * the third row of chsum then covers this call's contribution only. */
+int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act,
                         double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum,
                         void* stream);
@@ -228,10 +232,13 @@ int s2e_linear_bwd(const float* dy, const float* y, const void* x, const float* 
 #define S2E_RED_HINGE_FAKE 2 /* min(-x-1,0)                             */
 #define S2E_RED_L1 3         /* |x-y|                                   */
 #define S2E_RED_L2 4         /* (x-y)^2                                 */
-int s2e_reduce_loss(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float* out,
-                    int accumulate, void* stream);
+#define S2E_RED_LS 5         /* (x-target)^2          gan_mode ls       (loss.py:63-65: mse_loss against the label) */
+#define S2E_RED_BCE 6        /* BCE-with-logits(x, target)  gan_mode original (loss.py:59-62) */
+/* `target` is the constant label of the LS / BCE kinds (ignored by the others). */
+int s2e_reduce_loss(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float target,
+                    float* out, int accumulate, void* stream);
 /* dx (+)= gout[0] * coef * f'(x)   (dx same dtype as x) */
-int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef,
+int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float target,
                         const float* gout, void* dx, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------ optimizer

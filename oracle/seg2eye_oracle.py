@@ -427,11 +427,24 @@ def hinge(pred, target_is_real, for_discriminator):
     return -torch.mean(pred)
 
 
-def gan_loss(preds, target_is_real, for_discriminator):
+def gan_term(pred, target_is_real, for_discriminator, mode="hinge", real_label=1.0, fake_label=0.0):
+    """GANLoss.loss, loss.py:58-83: 'original' = BCE with logits against the label, 'ls' = MSE against the label,
+    'hinge', anything else = WGAN."""
+    label = real_label if target_is_real else fake_label
+    if mode == "original":
+        return F.binary_cross_entropy_with_logits(pred, torch.full_like(pred, label))
+    if mode == "ls":
+        return F.mse_loss(pred, torch.full_like(pred, label))
+    if mode == "hinge":
+        return hinge(pred, target_is_real, for_discriminator)
+    return -pred.mean() if target_is_real else pred.mean()
+
+
+def gan_loss(preds, target_is_real, for_discriminator, mode="hinge"):
     """GANLoss.__call__, loss.py:85-99: last tensor of each D, averaged over num_D, shape (1,)."""
     loss = 0
     for p in preds:
-        loss = loss + hinge(p[-1], target_is_real, for_discriminator).view(1)
+        loss = loss + gan_term(p[-1], target_is_real, for_discriminator, mode).view(1)
     return loss / len(preds)
 
 
@@ -449,7 +462,7 @@ def generator_losses(sdG, sdD, sdE, batch, opt):
     w = encode_w(sdE, batch["style_image"], opt)
     fake = generator_forward(sdG, seg, w, opt)
     pred_fake, pred_real = discriminate(sdD, seg, fake, batch["target"], opt)
-    losses = {"GAN": gan_loss(pred_fake, True, False)}
+    losses = {"GAN": gan_loss(pred_fake, True, False, getattr(opt, "gan_mode", "hinge"))}
     if opt.lambda_l2:
         losses["L2/weighted"] = F.mse_loss(fake, batch["target"]) * opt.lambda_l2
     if opt.lambda_l1:
@@ -471,7 +484,8 @@ def discriminator_losses(sdG, sdD, sdE, batch, opt):
         fake = generator_forward(sdG, seg, w, opt)
     fake = fake.detach().requires_grad_()
     pred_fake, pred_real = discriminate(sdD, seg, fake, batch["target"], opt)
-    return {"D/Fake": gan_loss(pred_fake, False, True), "D/real": gan_loss(pred_real, True, True)}
+    mode = getattr(opt, "gan_mode", "hinge")
+    return {"D/Fake": gan_loss(pred_fake, False, True, mode), "D/real": gan_loss(pred_real, True, True, mode)}
 
 
 # --------------------------------------------------------------------------------------

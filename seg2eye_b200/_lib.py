@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "libseg2eye_b200.so")
 MAX_TAPS = 16
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
 IMPL_TC, IMPL_SIMT = 0, 1
-RED_SUM, RED_HINGE_REAL, RED_HINGE_FAKE, RED_L1, RED_L2 = 0, 1, 2, 3, 4
+RED_SUM, RED_HINGE_REAL, RED_HINGE_FAKE, RED_L1, RED_L2, RED_LS, RED_BCE = 0, 1, 2, 3, 4, 5, 6
 
 
 class ConvDesc(C.Structure):
@@ -60,7 +60,7 @@ _SIGS = {
     "s2e_depth_to_space": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_norm_stats": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_norm_finalize": [_P, _I, _I, _D, _D, _F, _P, _P, _P, _P, _F, _P, _P],
-    "s2e_spade_style_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "s2e_spade_style_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P],
     "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P, _P],
     "s2e_instnorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
@@ -79,8 +79,8 @@ _SIGS = {
     "s2e_tanh_bwd": [_P, _P, _LL, _P, _P],
     "s2e_linear_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "s2e_linear_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
-    "s2e_reduce_loss": [_P, _P, _LL, _I, _I, _F, _P, _I, _P],
-    "s2e_reduce_loss_bwd": [_P, _P, _LL, _I, _I, _F, _P, _P, _I, _P],
+    "s2e_reduce_loss": [_P, _P, _LL, _I, _I, _F, _F, _P, _I, _P],
+    "s2e_reduce_loss_bwd": [_P, _P, _LL, _I, _I, _F, _F, _P, _P, _I, _P],
     "s2e_adam_prepare": [_P, _F, _F, _P],
     "s2e_adam_step": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P],
     "s2e_fill_f32": [_P, _LL, _F, _P],

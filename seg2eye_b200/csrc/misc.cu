@@ -860,7 +860,7 @@ __device__ __forceinline__ float ld_any(const void* p, long long i, int f32) {
   return f32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
 }
 __global__ void reduce_loss_kernel(const void* __restrict__ x, const void* __restrict__ y, long long n, int f32, int kind, float coef,
-                                   float* out) {
+                                   float target, float* out) {
   float acc = 0.f;
   GRID_STRIDE(i, n) {
     const float a = ld_any(x, i, f32);
@@ -868,6 +868,8 @@ __global__ void reduce_loss_kernel(const void* __restrict__ x, const void* __res
     if (kind == S2E_RED_SUM) v = a;
     else if (kind == S2E_RED_HINGE_REAL) v = fminf(a - 1.f, 0.f);
     else if (kind == S2E_RED_HINGE_FAKE) v = fminf(-a - 1.f, 0.f);
+    else if (kind == S2E_RED_LS) v = (a - target) * (a - target);
+    else if (kind == S2E_RED_BCE) v = fmaxf(a, 0.f) - a * target + log1pf(expf(-fabsf(a)));   // BCE with logits, stable form
     else {
       const float d = a - ld_any(y, i, f32);
       v = (kind == S2E_RED_L1) ? fabsf(d) : d * d;
@@ -878,7 +880,7 @@ __global__ void reduce_loss_kernel(const void* __restrict__ x, const void* __res
   if (threadIdx.x == 0) atomicAdd(out, acc * coef);
 }
 __global__ void reduce_loss_bwd_kernel(const void* __restrict__ x, const void* __restrict__ y, long long n, int f32, int kind, float coef,
-                                       const float* __restrict__ gout, void* __restrict__ dx, int accumulate) {
+                                       float target, const float* __restrict__ gout, void* __restrict__ dx, int accumulate) {
   const float g0 = gout[0] * coef;
   GRID_STRIDE(i, n) {
     const float a = ld_any(x, i, f32);
@@ -886,6 +888,8 @@ __global__ void reduce_loss_bwd_kernel(const void* __restrict__ x, const void* _
     if (kind == S2E_RED_SUM) d = 1.f;
     else if (kind == S2E_RED_HINGE_REAL) d = (a - 1.f < 0.f) ? 1.f : 0.f;
     else if (kind == S2E_RED_HINGE_FAKE) d = (-a - 1.f < 0.f) ? -1.f : 0.f;
+    else if (kind == S2E_RED_LS) d = 2.f * (a - target);
+    else if (kind == S2E_RED_BCE) d = 1.f / (1.f + expf(-a)) - target;
     else {
       const float df = a - ld_any(y, i, f32);
       d = (kind == S2E_RED_L1) ? (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) : 2.f * df;
@@ -1330,20 +1334,20 @@ int s2e_linear_bwd(const float* dy, const float* y, const void* x, const float* 
   return S2E_OK;
 }
 
-int s2e_reduce_loss(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float* out,
+int s2e_reduce_loss(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float target, float* out,
                     int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) S2E_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (!n) return S2E_OK;
   int g = grid1d(n, NT * 8);
-  reduce_loss_kernel<<<g, NT, 0, st>>>(x, y, n, x_is_f32, kind, coef, out);
+  reduce_loss_kernel<<<g, NT, 0, st>>>(x, y, n, x_is_f32, kind, coef, target, out);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
-int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, const float* gout,
-                        void* dx, int accumulate, void* stream) {
+int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float target,
+                        const float* gout, void* dx, int accumulate, void* stream) {
   if (!n) return S2E_OK;
-  reduce_loss_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(x, y, n, x_is_f32, kind, coef, gout, dx, accumulate);
+  reduce_loss_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(x, y, n, x_is_f32, kind, coef, target, gout, dx, accumulate);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

@@ -109,6 +109,14 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, do
   }
 }
 
+// bit j = (o[j] > 0): the activation mask of 8 channels in one byte
+__device__ __forceinline__ uint8_t sign_bits8(const float* o) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m |= (o[j] > 0.f ? 1u : 0u) << j;
+  return (uint8_t)m;
+}
+
 // ---------------------------------------------------------------- SPADE+Style forward (elementwise, 8 B/elem)
 // grid = (pixel chunks, B).  A thread owns one 8-channel group: its per-channel constants (mean, rstd, style) are
 // loaded once into registers, then it streams pixels: 3 x 16-byte loads + 1 x 16-byte store per pixel, two pixels in
@@ -116,7 +124,8 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, do
 __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                              const float* __restrict__ style, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, int HW, int C, int per_sample,
-                                                             int act, bf16* __restrict__ out) {
+                                                             int act, bf16* __restrict__ out, uint8_t* __restrict__ amask) {
+  // amask (optional): one bit per element, set where out > 0 -- all the backward pass needs of `out` (16x fewer bytes)
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long q0 = (long long)blockIdx.x * chunk;
@@ -155,11 +164,13 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
       for (int j = 0; j < 8; ++j)
         o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
       st_stream8(out + pA * C + c, pack8(o));
+      if (amask) amask[pA * cg + cg0 + my_cg] = sign_bits8(o);
       unpack8(xb, xf); unpack8(gbb, gf); unpack8(bb, bf_);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
       st_stream8(out + pB * C + c, pack8(o));
+      if (amask) amask[pB * cg + cg0 + my_cg] = sign_bits8(o);
     }
     for (; q < q1; q += lanes) {
       const long long pA = base + q;
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
       for (int j = 0; j < 8; ++j)
         o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
       st_stream8(out + pA * C + c, pack8(o));
+      if (amask) amask[pA * cg + cg0 + my_cg] = sign_bits8(o);
     }
   }
 }
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
 // ---------------------------------------------------------------- SPADE+Style backward
 // pass 1: per (sample, channel) sums  S1 = sum dxh, S2 = sum dxh*xh, S3 = sum g*x, S4 = sum g, S5 = sum g*xh
 // (S4 / S5 are also the per-channel sums of dbeta / dgamma, i.e. the bias gradients of the gamma|beta convolution)
-__global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ outp,
+__global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ amask,
                                                                     const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     int HW, int C, int per_sample, int act, double* __restrict__ racc) {
@@ -189,16 +201,16 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
   const float* mu = mean + (per_sample ? b * C : 0);
   const float* rs = rstd + (per_sample ? b * C : 0);
   auto one = [&](long long p, int c, float(*a)[8]) {
-    float df[8], of[8], xf[8], gf[8];
+    float df[8], xf[8], gf[8];
     unpack8(ld_stream8(dout + p * C + c), df);
     unpack8(ld_stream8(x + p * C + c), xf);
     unpack8(ld_stream8(gb + p * 2 * C + c), gf);
-    if (act != S2E_ACT_NONE) unpack8(ld_stream8(outp + p * C + c), of);
+    const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * (C >> 3) + (c >> 3)] : 0xffu;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float g = 0.5f * df[j];
-      if (act == S2E_ACT_LRELU) g *= (of[j] > 0.f ? 1.f : 0.2f);
-      if (act == S2E_ACT_RELU) g *= (of[j] > 0.f ? 1.f : 0.f);
+      if (act == S2E_ACT_LRELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.2f;
+      if (act == S2E_ACT_RELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.f;
       const float xh = (xf[j] - __ldg(mu + c + j)) * __ldg(rs + c + j);
       const float dxh = g * (1.f + gf[j]);
       a[0][j] += dxh;
@@ -256,7 +268,7 @@ __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int
 }
 
 // pass 2: dx = rstd*(dxh - m1 - xh*m2) + g*(1+s0) ; dgamma = g*xh ; dbeta = g     (same thread mapping as the forward)
-__global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ outp,
+__global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ amask,
                                                                    const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                                    const float* __restrict__ style, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ m12,
@@ -287,16 +299,16 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
     }
     for (long long q = q0 + my_lane; q < q1; q += lanes) {
       const long long p = (long long)b * HW + q;
-      float df[8], of[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
+      float df[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
       const bf16x8 vd = ld_stream8(dout + p * C + c), vx = ld_stream8(x + p * C + c), vg = ld_stream8(gb + p * 2 * C + c);
-      if (act != S2E_ACT_NONE) unpack8(ld_stream8(outp + p * C + c), of);
+      const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * cg + cg0 + my_cg] : 0xffu;
       if (dx_acc) unpack8(*reinterpret_cast<const bf16x8*>(dx + p * C + c), prev);
       unpack8(vd, df); unpack8(vx, xf); unpack8(vg, gf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float g = 0.5f * df[j];
-        if (act == S2E_ACT_LRELU) g *= (of[j] > 0.f ? 1.f : 0.2f);
-        if (act == S2E_ACT_RELU) g *= (of[j] > 0.f ? 1.f : 0.f);
+        if (act == S2E_ACT_LRELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.2f;
+        if (act == S2E_ACT_RELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.f;
         const float xh = (xf[j] - mu[j]) * rsd[j];
         const float dxh = g * (1.f + gf[j]);
         float d = rsd[j] * (dxh - m1[j] - xh * m2[j]) + g * s0[j];
@@ -513,34 +525,34 @@ __global__ void sn_corr_apply_kernel(const float* __restrict__ coef, const float
 }
 
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd, int B,
-                        int HW, int C, int per_sample, int act, void* out, void* stream) {
+                        int HW, int C, int per_sample, int act, void* out, uint8_t* act_mask, void* stream) {
   S2E_REQUIRE(C % 8 == 0, "spade_style_fwd needs C %% 8 == 0 (C=%d)", C);
   if ((long long)B * HW == 0) return S2E_OK;
   dim3 grid(ew_chunks(HW, B, C), B);
   spade_style_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gb, style, mean, rstd, HW, C,
-                                                                 per_sample, act, (bf16*)out);
+                                                                 per_sample, act, (bf16*)out, act_mask);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
 
-int s2e_spade_style_bwd(const void* dout, const void* out, const void* x, const void* gb, const float* style,
+int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act, double* racc,
                         void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, void* stream) {
   S2E_REQUIRE(C % 8 == 0, "spade_style_bwd needs C %% 8 == 0 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
   // racc: double [B][5][C] followed by float m12 [B][2][C]
-  S2E_REQUIRE(!(chsum && dx_accumulate), "spade_style_bwd: chsum describes dx only when dx is not accumulated into");
+  S2E_REQUIRE(act == S2E_ACT_NONE || act_mask, "spade_style_bwd: the activation mask written by the forward pass is required");
   S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 5 * C, st));
   float* m12 = (float*)(racc + (size_t)B * 5 * C);
   dim3 grid(red_chunks(HW, B), B);
-  spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x,
+  spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x,
                                                                 (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc);
   S2E_LAUNCH_CHECK();
   const double count = per_sample ? (double)HW : (double)B * HW;
   spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, m12, dstyle, chsum);
   S2E_LAUNCH_CHECK();
   dim3 grid2(ew_chunks(HW, B, C), B);
-  spade_style_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)x, (const bf16*)gb, style,
+  spade_style_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, style,
                                                      mean, rstd, m12, HW, C, per_sample, act, (bf16*)dx, dx_accumulate,
                                                      (bf16*)dgb);
   S2E_LAUNCH_CHECK();

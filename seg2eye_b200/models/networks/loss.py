@@ -22,13 +22,17 @@ class GANLoss(nn.Module):
         self.gan_mode, self.opt = gan_mode, opt
         if gan_mode not in ('ls', 'original', 'w', 'hinge'):
             raise ValueError('Unexpected gan_mode {}'.format(gan_mode))
-        if gan_mode in ('ls', 'original'):
-            # TODO(next): ls / original modes
-            raise ValueError('gan_mode %s is not implemented on the B200 path yet (hinge | w)' % gan_mode)
 
     def loss(self, input, target_is_real, for_discriminator=True):
+        """loss.py:58-83: 'original' = BCE with logits against the real / fake label, 'ls' = MSE against the label,
+        'hinge', else WGAN.  Each is one reduction kernel (and one elementwise kernel in backward)."""
         x = _flat(input)
         n = x.numel()
+        label = self.real_label if target_is_real else self.fake_label
+        if self.gan_mode == 'original':
+            return ops.reduce_loss(x, None, L.RED_BCE, 1.0 / n, label).view(())
+        if self.gan_mode == 'ls':
+            return ops.reduce_loss(x, None, L.RED_LS, 1.0 / n, label).view(())
         if self.gan_mode == 'hinge':
             if for_discriminator:
                 kind = L.RED_HINGE_REAL if target_is_real else L.RED_HINGE_FAKE

@@ -473,12 +473,24 @@ def prepare_spectral(convs, training, n_calls=1, keep_uv=False):
 NormCfg = namedtuple("NormCfg", "per_sample act training momentum eps")
 
 
+class GradSink:
+    """Shared gradient buffer of several SpadeStyleFn calls that consume the SAME input x (norm_0 and norm_s of a
+    ResNet block with a learned shortcut): the first backward to run allocates dx and returns it, the others add into
+    it in place and return nothing, so autograd never launches a separate add over the (large) gradient.  Safe because
+    the engine runs the producer of x only after every consumer's backward has finished."""
+    __slots__ = ("buf",)
+
+    def __init__(self):
+        self.buf = None
+
+
 class SpadeStyleFn(torch.autograd.Function):
     """out = act(0.5 * [ norm(x) * (1 + gamma) + beta + x * (1 + s0) + s1 ])  (normalization.py:91-105,161-192)."""
 
     @staticmethod
-    def forward(ctx, x, gb, style, cfg, running_mean, running_var, nbt, stats_src=None):
+    def forward(ctx, x, gb, style, cfg, running_mean, running_var, nbt, stats_src=None, sink=None):
         # stats_src: the tensor x was nearest-2x up-sampled from (same per-channel mean / variance, 4x fewer bytes)
+        ctx.sink = sink
         x, gb, style = _c(x), _c(gb), _c(style)
         B, H, W, Cc = x.shape
         assert gb.shape == (B, H, W, 2 * Cc) and style.shape == (B, 2 * Cc) and style.dtype == F32
@@ -506,10 +518,15 @@ class SpadeStyleFn(torch.autograd.Function):
             mean = running_mean.detach().clone().view(1, Cc)
             rstd = torch.rsqrt(running_var.detach() + cfg.eps).view(1, Cc)
         out = torch.empty_like(x)
+        # backward needs only the sign of `out` (LeakyReLU mask): one bit per element, written by the forward kernel
+        amask = None
+        if cfg.act != L.ACT_NONE and any(ctx.needs_input_grad[:3]):
+            amask = torch.empty(B * H * W * (Cc // 8), dtype=torch.uint8, device=x.device)
         _timed_call("norm", 8.0 * B * H * W * Cc, "s2e_spade_style_fwd", L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
-                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(out), st, tag="B%d HW%d C%d" % (B, H * W, Cc))
+                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(out), L.ptr(amask), st,
+                    tag="B%d HW%d C%d" % (B, H * W, Cc))
         ctx.cfg, ctx.batch_stats = cfg, batch_stats
-        ctx.save_for_backward(x, gb, style, mean, rstd, out)
+        ctx.save_for_backward(x, gb, style, mean, rstd, amask)
         return out
 
     @staticmethod
@@ -517,22 +534,27 @@ class SpadeStyleFn(torch.autograd.Function):
         cfg = ctx.cfg
         if not ctx.batch_stats:
             raise NotImplementedError("backward through SPADE BatchNorm in eval mode is not supported")
-        x, gb, style, mean, rstd, out = ctx.saved_tensors
+        x, gb, style, mean, rstd, amask = ctx.saved_tensors
         dout = _c(dout)
         B, H, W, Cc = x.shape
         racc = torch.empty(B * 5 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
-        dx = torch.empty_like(x)
+        sink = ctx.sink
+        shared = sink is not None and sink.buf is not None
+        dx = sink.buf if shared else torch.empty_like(x)
+        if sink is not None:
+            sink.buf = None if shared else dx     # (cleared by the last user: no reference outlives the backward pass)
         dgb = torch.empty_like(gb)
         dstyle = torch.empty_like(style)
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
-        L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
-               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), 0, L.ptr(dgb),
+        L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
+               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(shared), L.ptr(dgb),
                L.ptr(dstyle), L.ptr(chsum), L.stream())
         # per-channel sums of the two gradients, for the bias gradients of the convolutions that receive them as dy
         # (TapConvFn.backward picks the attribute up when the tensor reaches it unmodified; otherwise it sums itself)
         dgb._s2e_chsum = chsum[:2 * Cc]
-        dx._s2e_chsum = chsum[2 * Cc:]
-        return dx, dgb, dstyle, None, None, None, None, None
+        if sink is None:
+            dx._s2e_chsum = chsum[2 * Cc:]
+        return (None if shared else dx), dgb, dstyle, None, None, None, None, None, None
 
 
 class InstNormFn(torch.autograd.Function):
@@ -889,10 +911,11 @@ class LinearFn(torch.autograd.Function):
 
 
 class ReduceLossFn(torch.autograd.Function):
-    """(1,) fp32 = coef * sum f(x[, y]) with f selected by `kind` (loss.py:58-83, nn.L1Loss/MSELoss)."""
+    """(1,) fp32 = coef * sum f(x[, y]) with f selected by `kind` (loss.py:58-83, nn.L1Loss/MSELoss); `target` is the
+    constant label of the LS / BCE kinds."""
 
     @staticmethod
-    def forward(ctx, x, y, kind, coef):
+    def forward(ctx, x, y, kind, coef, target=0.0):
         x = _c(x)
         f32 = int(x.dtype == F32)
         if y is not None:
@@ -901,8 +924,8 @@ class ReduceLossFn(torch.autograd.Function):
                 y = y.to(x.dtype)
             assert y.shape == x.shape
         out = torch.empty(1, dtype=F32, device=x.device)
-        L.call("s2e_reduce_loss", L.ptr(x), L.ptr(y), x.numel(), f32, kind, coef, L.ptr(out), 0, L.stream())
-        ctx.kind, ctx.coef, ctx.f32 = kind, coef, f32
+        L.call("s2e_reduce_loss", L.ptr(x), L.ptr(y), x.numel(), f32, kind, coef, target, L.ptr(out), 0, L.stream())
+        ctx.kind, ctx.coef, ctx.f32, ctx.target = kind, coef, f32, target
         ctx.save_for_backward(x, y)
         return out
 
@@ -911,13 +934,13 @@ class ReduceLossFn(torch.autograd.Function):
         x, y = ctx.saved_tensors
         gout = _c(gout.float())
         dx = torch.empty_like(x)
-        L.call("s2e_reduce_loss_bwd", L.ptr(x), L.ptr(y), x.numel(), ctx.f32, ctx.kind, ctx.coef, L.ptr(gout), L.ptr(dx),
-               0, L.stream())
-        return dx, None, None, None
+        L.call("s2e_reduce_loss_bwd", L.ptr(x), L.ptr(y), x.numel(), ctx.f32, ctx.kind, ctx.coef, ctx.target, L.ptr(gout),
+               L.ptr(dx), 0, L.stream())
+        return dx, None, None, None, None
 
 
-def reduce_loss(x, y, kind, coef):
-    return ReduceLossFn.apply(x, y, kind, float(coef))
+def reduce_loss(x, y, kind, coef, target=0.0):
+    return ReduceLossFn.apply(x, y, kind, float(coef), float(target))
 
 
 class HalvesLossFn(torch.autograd.Function):
@@ -932,7 +955,7 @@ class HalvesLossFn(torch.autograd.Function):
         f32 = int(t.dtype == F32)
         out = torch.empty(1, dtype=F32, device=t.device)
         flat = t.view(-1)
-        L.call("s2e_reduce_loss", L.ptr(flat), L.ptr(flat[n2:]), n2, f32, kind, coef, L.ptr(out), 0, L.stream())
+        L.call("s2e_reduce_loss", L.ptr(flat), L.ptr(flat[n2:]), n2, f32, kind, coef, 0.0, L.ptr(out), 0, L.stream())
         ctx.kind, ctx.coef, ctx.f32 = kind, coef, f32
         ctx.save_for_backward(t)
         return out
@@ -945,6 +968,6 @@ class HalvesLossFn(torch.autograd.Function):
         dx = torch.empty_like(t)
         flat, dflat = t.view(-1), dx.view(-1)
         dflat[n2:].zero_()
-        L.call("s2e_reduce_loss_bwd", L.ptr(flat), L.ptr(flat[n2:]), n2, ctx.f32, ctx.kind, ctx.coef, L.ptr(gout), L.ptr(dflat),
-               0, L.stream())
+        L.call("s2e_reduce_loss_bwd", L.ptr(flat), L.ptr(flat[n2:]), n2, ctx.f32, ctx.kind, ctx.coef, 0.0, L.ptr(gout),
+               L.ptr(dflat), 0, L.stream())
         return dx, None, None

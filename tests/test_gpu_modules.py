@@ -395,3 +395,48 @@ def test_generator_variants_vs_oracle(ctx, over):
         out = G(seg.cuda(), w.cuda())
     assert out.shape == ref.shape
     assert rel(out, ref) < TOL_CHAIN, rel(out, ref)
+
+
+def test_gan_loss_modes_vs_reference_fixture():
+    """GANLoss (hinge | ls | original | w) on the device == the reference's GANLoss values recorded in
+    tests/golden/ref_ganloss.npz (fp32 predictions: 1e-5), gradients == autograd through the oracle restatement."""
+    from oracle.make_golden_ganloss import preds
+    from seg2eye_b200.models import networks
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ganloss.npz"))
+    for key in ref.files:
+        mode, real, for_d = key.rsplit("_", 2)
+        real, for_d = bool(int(real)), bool(int(for_d))
+        p_cpu = [[t.clone().requires_grad_() for t in d] for d in preds()]
+        p_dev = [[t.cuda().requires_grad_() for t in d] for d in preds()]
+        crit = networks.GANLoss(mode)
+        got = crit(p_dev, real, for_discriminator=for_d)
+        assert got.shape == (1,)
+        np.testing.assert_allclose(got.detach().cpu().numpy(), ref[key], rtol=1e-5, atol=1e-6, err_msg=key)
+        got.sum().backward()
+        O.gan_loss(p_cpu, real, for_d, mode).sum().backward()
+        for dc, dd in zip(p_cpu, p_dev):
+            assert rel(dd[-1].grad, dc[-1].grad) < 1e-5, key
+            assert dd[0].grad is None
+    with pytest.raises(ValueError):
+        networks.GANLoss("nope")
+
+
+@pytest.mark.parametrize("mode", ["ls", "original"])
+def test_training_iteration_other_gan_modes_vs_oracle(ctx, mode):
+    """One full G + D iteration with gan_mode ls / original against the oracle trainer (losses within 2e-2)."""
+    over = dict(gan_mode=mode)
+    oopt = SimpleNamespace(**{**vars(ctx.oopt), **over})
+    opt = SimpleNamespace(**{**vars(ctx.opt), **over})
+    c2 = SimpleNamespace(oopt=oopt, opt=opt, bs=ctx.bs, seeds=ctx.seeds, batch=ctx.batch)
+    tr = _make_trainer(c2)
+    data = {k: v.clone() for k, v in ctx.batch.items()}
+    tr.run_generator_one_step(data)
+    tr.run_discriminator_one_step(data)
+    ours = {k: float(v.reshape(-1)[0]) for k, v in tr.get_latest_losses().items()}
+    sds = {n: O.synth_state(getattr(O, f + "_shapes")(oopt), ctx.seeds[n]) for n, f in (("G", "generator"), ("D", "discriminator"), ("E", "encoder"))}
+    ot = O.OracleTrainer(sds["G"], sds["D"], sds["E"], oopt)
+    ot.run_generator_one_step(ctx.batch)
+    ot.run_discriminator_one_step(ctx.batch)
+    ref = {k: float(v.reshape(-1)[0]) for k, v in {**ot.g_losses, **ot.d_losses}.items()}
+    for k in ref:
+        assert abs(ours[k] - ref[k]) <= TOL_LOSS * abs(ref[k]) + (2e-2 if k == "GAN" else 0.0), (k, ours[k], ref[k])

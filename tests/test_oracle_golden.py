@@ -135,3 +135,16 @@ def test_two_training_iterations(gold):
             close(post[net][name].detach().double(), v, 2e-3)
         n += 1
     assert n >= 15
+
+
+def test_gan_loss_modes_match_reference_ganloss():
+    """oracle.gan_loss in all four gan_modes == the reference's GANLoss (fixture from oracle/make_golden_ganloss.py)."""
+    from oracle.make_golden_ganloss import preds
+    ref = np.load(os.path.join(GOLD, "ref_ganloss.npz"))
+    p = preds()
+    assert len(ref.files) == 15
+    for key in ref.files:
+        mode, real, for_d = key.rsplit("_", 2)
+        got = O.gan_loss(p, bool(int(real)), bool(int(for_d)), mode)
+        assert got.shape == (1,)
+        np.testing.assert_allclose(got.numpy(), ref[key], rtol=1e-6, atol=1e-7, err_msg=key)
