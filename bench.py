@@ -29,6 +29,12 @@ import torch  # noqa: E402
 
 RES = {"R1": (256, 0.8), "R2": (384, 0.6)}   # crop_size, aspect_ratio -> 320x256 / 640x384
 STEP_TFLOP = {"R1": 1.54, "R2": 4.53}        # reference-equivalent FLOPs per image
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant tcgen05 launch class, from the committed
+# `ncu --set full` capture (a profiler number, so it is a constant here, never measured inside the timed region)
+NCU_DOMINANT = {"launch": "fwd B16 640x384 Cin128 Cout256 T9", "traffic": 2.969e9,
+                "note": "ncu --set full (profiles/r01_ncu_convprobe_fullres.txt): tapconv_fwd_kernel<256,0>, B16 640x384 128->256 3x3: "
+                        "dram read 1.010 GB + write 1.958 GB per launch vs 3.020 GB algorithmic (x 1.007 GB + y 2.013 GB); "
+                        "tensor pipe 78.8 % active at the power-capped clock (1.385 GHz)"}
 
 
 def make_opts(res, batch):
@@ -219,6 +225,13 @@ def run_ours(args):
         conv_ms, conv_tf, conv_n = prof["tc_ms"], prof["tc_flop"] / 1e12, prof["tc_n"]
         achieved = conv_tf / (conv_ms / 1e3) if conv_ms > 0 else 0.0
         norm_gbs = prof["norm_bytes"] / 1e9 / (prof["norm_ms"] / 1e3) if prof["norm_ms"] > 0 else 0.0
+        # the single launch class that takes the most time: the gamma|beta forward convolution at full resolution
+        dom_tag, dom = max(((t, v) for (k, t), v in prof["by_tag"].items() if k == "tc"), key=lambda kv: kv[1][1])
+        dominant = {"launch": dom_tag, "launches_per_step": dom[0] // 2, "ms_per_launch": dom[1] / dom[0],
+                    "tflops": dom[2] / 1e12 / (dom[1] / 1e3)}
+        traffic, traffic_note = None, None
+        if args.res == "R2" and args.batch == 16 and dom_tag == NCU_DOMINANT["launch"]:
+            traffic, traffic_note = NCU_DOMINANT["traffic"], NCU_DOMINANT["note"]
         out = {
             "metric": "G+D train images/sec", "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -230,7 +243,8 @@ def run_ours(args):
             "execution": ("2 CUDA graphs per iteration (G step, D step); eager ms_per_step %.1f" % ms_eager) if ms_eager else "eager",
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                         "frac": achieved / peaks["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
+                         "dominant": dominant,
                          "kernel": "tapconv_{fwd,wgrad}_kernel (tcgen05 implicit GEMM; %d launches/step, %.1f ms of the %.1f ms step; "
                                    "CUDA events around each launch in a 2-step eager pass)" % (
                              conv_n // 2, conv_ms / 2, ms / args.steps),

@@ -241,18 +241,17 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
 // K2 tiled variant for conv_img (64 -> 1, 3x3, stride 1): every input pixel is read from global memory ONCE per tile
 // (plus a one-pixel halo) instead of once per tap.  Phase 0: the whole halo tile is staged in shared memory with
 // cp.async (every 16-byte chunk in flight at once; out-of-image pixels are zero-filled).  Phase 1: 8 lanes per input
-// pixel form the nine per-tap dot products d[pixel][t] = x[pixel] . W[t] (tap weights in shared memory, read as
-// broadcasts) and park them in shared memory.  Phase 2: one thread per output pixel adds its nine neighbours' entries
+// pixel form the nine per-tap dot products d[pixel][t] = x[pixel] . W[t] (tap weights in registers) and park them in
+// shared memory.  Phase 2: one thread per output pixel adds its nine neighbours' entries
 // y[p] = sum_t d[p + tap_t][t].
 constexpr int T1_TW = 32, T1_TH = 8, T1_HW = T1_TW + 2, T1_NHP = (T1_TH + 2) * T1_HW;
-constexpr int T1_SMEM = T1_NHP * 128 + T1_NHP * 9 * 4 + 9 * 64 * 4;
-__global__ void __launch_bounds__(256, 3) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+constexpr int T1_SMEM = T1_NHP * 128 + T1_NHP * 9 * 4;
+__global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                                 const float* __restrict__ bias, const float* __restrict__ scale,
                                                                 bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h) {
   extern __shared__ __align__(16) uint8_t t1_smem[];
   bf16* xs = reinterpret_cast<bf16*>(t1_smem);                               // [T1_NHP][64]
   float* d = reinterpret_cast<float*>(t1_smem + T1_NHP * 128);               // [T1_NHP][9]
-  float* ws = d + T1_NHP * 9;                                                // [9][64]
   int tile = blockIdx.x;
   const int tw_idx = tile % tiles_w;
   tile /= tiles_w;
@@ -271,21 +270,26 @@ __global__ void __launch_bounds__(256, 3) thin_out1_tile_kernel(const bf16* __re
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = threadIdx.x; i < 9 * 64; i += 256) ws[i] = i < g.ntaps * 64 ? __bfloat162float(wp[i]) : 0.f;
+  const int sub = threadIdx.x & 7;
+  float wreg[9][8];   // this lane's 8-channel slice of every tap's weights (loaded while the tile is in flight)
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (t < g.ntaps) unpack8(*reinterpret_cast<const bf16x8*>(wp + (long long)t * 64 + sub * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wreg[t][j] = f[j];
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int sub = threadIdx.x & 7;
   for (int hp = threadIdx.x >> 3; hp < T1_NHP; hp += 32) {
     float xf[8];
     unpack8(*reinterpret_cast<const bf16x8*>(xs + hp * 64 + sub * 8), xf);
     float part[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const float4 wa = *reinterpret_cast<const float4*>(ws + t * 64 + sub * 8);
-      const float4 wb = *reinterpret_cast<const float4*>(ws + t * 64 + sub * 8 + 4);
-      float a = xf[0] * wa.x;
-      a = fmaf(xf[1], wa.y, a); a = fmaf(xf[2], wa.z, a); a = fmaf(xf[3], wa.w, a);
-      a = fmaf(xf[4], wb.x, a); a = fmaf(xf[5], wb.y, a); a = fmaf(xf[6], wb.z, a); a = fmaf(xf[7], wb.w, a);
+      float a = xf[0] * wreg[t][0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) a = fmaf(xf[j], wreg[t][j], a);
       a += __shfl_xor_sync(0xffffffffu, a, 1);
       a += __shfl_xor_sync(0xffffffffu, a, 2);
       a += __shfl_xor_sync(0xffffffffu, a, 4);

@@ -859,42 +859,66 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* 
 __device__ __forceinline__ float ld_any(const void* p, long long i, int f32) {
   return f32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
 }
-__global__ void reduce_loss_kernel(const void* __restrict__ x, const void* __restrict__ y, long long n, int f32, int kind, float coef,
-                                   float target, float* out) {
-  float acc = 0.f;
-  GRID_STRIDE(i, n) {
-    const float a = ld_any(x, i, f32);
-    float v;
-    if (kind == S2E_RED_SUM) v = a;
-    else if (kind == S2E_RED_HINGE_REAL) v = fminf(a - 1.f, 0.f);
-    else if (kind == S2E_RED_HINGE_FAKE) v = fminf(-a - 1.f, 0.f);
-    else if (kind == S2E_RED_LS) v = (a - target) * (a - target);
-    else if (kind == S2E_RED_BCE) v = fmaxf(a, 0.f) - a * target + log1pf(expf(-fabsf(a)));   // BCE with logits, stable form
-    else {
-      const float d = a - ld_any(y, i, f32);
-      v = (kind == S2E_RED_L1) ? fabsf(d) : d * d;
-    }
-    acc += v;
+__device__ __forceinline__ float loss_value(float a, float b, int kind, float target) {
+  switch (kind) {
+    case S2E_RED_SUM: return a;
+    case S2E_RED_HINGE_REAL: return fminf(a - 1.f, 0.f);
+    case S2E_RED_HINGE_FAKE: return fminf(-a - 1.f, 0.f);
+    case S2E_RED_LS: return (a - target) * (a - target);
+    case S2E_RED_BCE: return fmaxf(a, 0.f) - a * target + log1pf(expf(-fabsf(a)));   // BCE with logits, stable form
+    case S2E_RED_L1: return fabsf(a - b);
+    default: return (a - b) * (a - b);
   }
+}
+__device__ __forceinline__ float loss_grad(float a, float b, int kind, float target) {
+  switch (kind) {
+    case S2E_RED_SUM: return 1.f;
+    case S2E_RED_HINGE_REAL: return (a - 1.f < 0.f) ? 1.f : 0.f;
+    case S2E_RED_HINGE_FAKE: return (-a - 1.f < 0.f) ? -1.f : 0.f;
+    case S2E_RED_LS: return 2.f * (a - target);
+    case S2E_RED_BCE: return 1.f / (1.f + expf(-a)) - target;
+    case S2E_RED_L1: {
+      const float df = a - b;
+      return df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+    }
+    default: return 2.f * (a - b);
+  }
+}
+// bf16 tensors whose pointers are 16-byte aligned take the 8-wide path (the feature-matching loss runs over the big
+// discriminator features); everything else (fp32 images, ragged tails) goes element by element.
+__global__ void reduce_loss_kernel(const void* __restrict__ x, const void* __restrict__ y, long long n, int f32, int kind, float coef,
+                                   float target, int vec, float* out) {
+  float acc = 0.f;
+  const bool two = (kind == S2E_RED_L1 || kind == S2E_RED_L2);
+  const long long nv = vec ? n >> 3 : 0;
+  GRID_STRIDE(i, nv) {
+    float a[8], b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unpack8(ld_stream8((const bf16*)x + i * 8), a);
+    if (two) unpack8(ld_stream8((const bf16*)y + i * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += loss_value(a[j], b[j], kind, target);
+  }
+  for (long long i = nv * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += loss_value(ld_any(x, i, f32), two ? ld_any(y, i, f32) : 0.f, kind, target);
   acc = block_sum(acc);
   if (threadIdx.x == 0) atomicAdd(out, acc * coef);
 }
 __global__ void reduce_loss_bwd_kernel(const void* __restrict__ x, const void* __restrict__ y, long long n, int f32, int kind, float coef,
-                                       float target, const float* __restrict__ gout, void* __restrict__ dx, int accumulate) {
+                                       float target, int vec, const float* __restrict__ gout, void* __restrict__ dx, int accumulate) {
   const float g0 = gout[0] * coef;
-  GRID_STRIDE(i, n) {
-    const float a = ld_any(x, i, f32);
-    float d;
-    if (kind == S2E_RED_SUM) d = 1.f;
-    else if (kind == S2E_RED_HINGE_REAL) d = (a - 1.f < 0.f) ? 1.f : 0.f;
-    else if (kind == S2E_RED_HINGE_FAKE) d = (-a - 1.f < 0.f) ? -1.f : 0.f;
-    else if (kind == S2E_RED_LS) d = 2.f * (a - target);
-    else if (kind == S2E_RED_BCE) d = 1.f / (1.f + expf(-a)) - target;
-    else {
-      const float df = a - ld_any(y, i, f32);
-      d = (kind == S2E_RED_L1) ? (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) : 2.f * df;
-    }
-    d *= g0;
+  const bool two = (kind == S2E_RED_L1 || kind == S2E_RED_L2);
+  const long long nv = vec ? n >> 3 : 0;
+  GRID_STRIDE(i, nv) {
+    float a[8], b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8], prev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unpack8(ld_stream8((const bf16*)x + i * 8), a);
+    if (two) unpack8(ld_stream8((const bf16*)y + i * 8), b);
+    if (accumulate) unpack8(*reinterpret_cast<const bf16x8*>((bf16*)dx + i * 8), prev);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = prev[j] + g0 * loss_grad(a[j], b[j], kind, target);
+    *reinterpret_cast<bf16x8*>((bf16*)dx + i * 8) = pack8(o);
+  }
+  for (long long i = nv * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = g0 * loss_grad(ld_any(x, i, f32), two ? ld_any(y, i, f32) : 0.f, kind, target);
     if (f32) {
       float* o = (float*)dx;
       o[i] = accumulate ? o[i] + d : d;
@@ -1340,14 +1364,17 @@ int s2e_reduce_loss(const void* x, const void* y, long long n, int x_is_f32, int
   if (!accumulate) S2E_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (!n) return S2E_OK;
   int g = grid1d(n, NT * 8);
-  reduce_loss_kernel<<<g, NT, 0, st>>>(x, y, n, x_is_f32, kind, coef, target, out);
+  const int vec = !x_is_f32 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  reduce_loss_kernel<<<g, NT, 0, st>>>(x, y, n, x_is_f32, kind, coef, target, vec, out);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
 int s2e_reduce_loss_bwd(const void* x, const void* y, long long n, int x_is_f32, int kind, float coef, float target,
                         const float* gout, void* dx, int accumulate, void* stream) {
   if (!n) return S2E_OK;
-  reduce_loss_bwd_kernel<<<grid1d(n), NT, 0, (cudaStream_t)stream>>>(x, y, n, x_is_f32, kind, coef, target, gout, dx, accumulate);
+  const int vec = !x_is_f32 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)dx) & 15) == 0;
+  reduce_loss_bwd_kernel<<<grid1d(vec ? (n + 7) / 8 : n), NT, 0, (cudaStream_t)stream>>>(x, y, n, x_is_f32, kind, coef, target, vec, gout, dx,
+                                                                                       accumulate);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

@@ -297,11 +297,9 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
       m2[j] = m1p[C + c + j];
       s0[j] = 1.f + s0p[c + j];
     }
-    for (long long q = q0 + my_lane; q < q1; q += lanes) {
-      const long long p = (long long)b * HW + q;
+    // two pixels per iteration: all six 16-byte loads are issued before the first use (memory-level parallelism)
+    auto finish = [&](long long p, const bf16x8& vd, const bf16x8& vx, const bf16x8& vg, uint32_t mbits) {
       float df[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
-      const bf16x8 vd = ld_stream8(dout + p * C + c), vx = ld_stream8(x + p * C + c), vg = ld_stream8(gb + p * 2 * C + c);
-      const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * cg + cg0 + my_cg] : 0xffu;
       if (dx_acc) unpack8(*reinterpret_cast<const bf16x8*>(dx + p * C + c), prev);
       unpack8(vd, df); unpack8(vx, xf); unpack8(vg, gf);
 #pragma unroll
@@ -320,6 +318,24 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
       *reinterpret_cast<bf16x8*>(dx + p * C + c) = pack8(odx);
       st_stream8(dgb + p * 2 * C + c, pack8(odg));
       st_stream8(dgb + p * 2 * C + C + c, pack8(odb));
+    };
+    const long long base = (long long)b * HW;
+    const int mcol = cg0 + my_cg;
+    long long q = q0 + my_lane;
+    for (; q + lanes < q1; q += 2 * lanes) {
+      const long long pA = base + q, pB = base + q + lanes;
+      const bf16x8 da = ld_stream8(dout + pA * C + c), db = ld_stream8(dout + pB * C + c);
+      const bf16x8 xa = ld_stream8(x + pA * C + c), xb = ld_stream8(x + pB * C + c);
+      const bf16x8 ga = ld_stream8(gb + pA * 2 * C + c), gb2 = ld_stream8(gb + pB * 2 * C + c);
+      const uint32_t ma = act != S2E_ACT_NONE ? (uint32_t)amask[pA * cg + mcol] : 0xffu;
+      const uint32_t mb = act != S2E_ACT_NONE ? (uint32_t)amask[pB * cg + mcol] : 0xffu;
+      finish(pA, da, xa, ga, ma);
+      finish(pB, db, xb, gb2, mb);
+    }
+    for (; q < q1; q += lanes) {
+      const long long p = base + q;
+      const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * cg + mcol] : 0xffu;
+      finish(p, ld_stream8(dout + p * C + c), ld_stream8(x + p * C + c), ld_stream8(gb + p * 2 * C + c), mbits);
     }
   }
 }

@@ -70,23 +70,25 @@ def profile_end(dump_path=None):
     global _prof
     p, _prof = _prof, None
     torch.cuda.synchronize()
+    agg = {}
+    for kind in p:
+        for a, b, w, tag in p[kind]:
+            e = agg.setdefault((kind, tag), [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b)
+            e[2] += w
     if dump_path:
-        agg = {}
-        for kind in p:
-            for a, b, w, tag in p[kind]:
-                e = agg.setdefault((kind, tag), [0, 0.0, 0.0])
-                e[0] += 1
-                e[1] += a.elapsed_time(b)
-                e[2] += w
         with open(dump_path, "w") as f:
             f.write("kind\ttag\tlaunches\tms_total\twork\trate(TFLOP/s|GB/s)\n")
             for (kind, tag), (n, ms, w) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 rate = (w / 1e12 if kind == "tc" else w / 1e9) / (ms / 1e3) if ms > 0 else 0
                 f.write("%s\t%s\t%d\t%.3f\t%.4g\t%.1f\n" % (kind, tag, n, ms, w, rate))
-    p = {k: [(a, b, w) for a, b, w, _ in v] for k, v in p.items()}
-    out = {"tc_ms": sum(a.elapsed_time(b) for a, b, _ in p["tc"]), "tc_flop": float(sum(w for _, _, w in p["tc"])),
-           "tc_n": len(p["tc"]), "norm_ms": sum(a.elapsed_time(b) for a, b, _ in p["norm"]),
-           "norm_bytes": float(sum(w for _, _, w in p["norm"])), "norm_n": len(p["norm"])}
+    out = {"by_tag": agg}
+    for kind, key in (("tc", "flop"), ("norm", "bytes")):
+        rows = [v for (k, _), v in agg.items() if k == kind]
+        out[kind + "_ms"] = sum(v[1] for v in rows)
+        out[kind + "_" + key] = float(sum(v[2] for v in rows))
+        out[kind + "_n"] = sum(v[0] for v in rows)
     return out
 
 
