@@ -170,8 +170,12 @@ int s2e_norm_finalize(const double* acc, int G, int C, double count, double coun
                       int64_t* num_batches_tracked, void* stream);
 /* act_mask (nullable): one BIT per element, [B*HW][C/8] bytes, bit j of byte (p, c/8) = (out[p][c+j] > 0); all the
  * backward pass needs to know about `out` (read instead of it: 0.125 B/element instead of 2). */
+/* up_w != 0: x is the [B][H/2][W/2][C] tensor whose nearest-2x up-sampling (generator.py:50) is the block input; up_w = W
+ * of the up-sampled map.  The up-sampled copy is never materialised; mean / rstd of the two are identical.  In backward
+ * dx is still the gradient w.r.t. the UP-SAMPLED input (B*HW*C); reduce it with s2e_upsample2x_bwd. */
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd,
-                        int B, int HW, int C, int per_sample, int act, void* out, uint8_t* act_mask, void* stream);
+                        int B, int HW, int C, int per_sample, int act, void* out, uint8_t* act_mask, int up_w,
+                        void* stream);
 /* backward: racc = scratch of B*5*C doubles + B*2*C floats, zeroed inside. `act_mask` = the forward pass's mask (may be
  * NULL when act == NONE).  chsum (nullable, float [3][C]) receives the per-channel sums over the batch of dgamma, dbeta
  * and dx -- the bias gradients of the gamma|beta convolution (normalization.py:88-89) and of the convolution that
@@ -180,7 +184,7 @@ int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const
  * the third row of chsum then covers this call's contribution only. */
 int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act,
-                        double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum,
+                        double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, int up_w,
                         void* stream);
 
 /* InstanceNorm2d(affine=False)+optional LeakyReLU on NHWC bf16 (normalization.py:41; discriminator.py:88-92;

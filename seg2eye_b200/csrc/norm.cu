@@ -109,6 +109,16 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, do
   }
 }
 
+// Pixel index of x for output pixel q of sample b.  up_w == 0: x has the output's resolution.  up_w = W of the output:
+// x is the (H/2, W/2) tensor the block input was nearest-2x up-sampled from (generator.py:50,86-93); the up-sampled copy
+// is never materialised, the kernels read the source through this index map.
+__device__ __forceinline__ long long x_pixel(int b, long long q, int HW, int up_w) {
+  if (!up_w) return (long long)b * HW + q;
+  const unsigned qq = (unsigned)q, uw = (unsigned)up_w;   // q < HW < 2^31: 32-bit division
+  const unsigned h = qq / uw, w = qq - h * uw;
+  return (long long)b * (HW >> 2) + (long long)((h >> 1) * (uw >> 1) + (w >> 1));
+}
+
 // bit j = (o[j] > 0): the activation mask of 8 channels in one byte
 __device__ __forceinline__ uint8_t sign_bits8(const float* o) {
   uint32_t m = 0;
@@ -121,10 +131,10 @@ __device__ __forceinline__ uint8_t sign_bits8(const float* o) {
 // grid = (pixel chunks, B).  A thread owns one 8-channel group: its per-channel constants (mean, rstd, style) are
 // loaded once into registers, then it streams pixels: 3 x 16-byte loads + 1 x 16-byte store per pixel, two pixels in
 // flight per iteration.
-__global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
+__global__ void __launch_bounds__(NT, 3) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                              const float* __restrict__ style, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, int HW, int C, int per_sample,
-                                                             int act, bf16* __restrict__ out, uint8_t* __restrict__ amask) {
+                                                             int act, bf16* __restrict__ out, uint8_t* __restrict__ amask, int up_w) {
   // amask (optional): one bit per element, set where out > 0 -- all the backward pass needs of `out` (16x fewer bytes)
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
     long long q = q0 + my_lane;
     for (; q + lanes < q1; q += 2 * lanes) {
       const long long pA = base + q, pB = base + q + lanes;
-      const bf16x8 xa = ld_stream8(x + pA * C + c), xb = ld_stream8(x + pB * C + c);
+      const bf16x8 xa = ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), xb = ld_stream8(x + x_pixel(b, q + lanes, HW, up_w) * C + c);
       const bf16x8 ga = ld_stream8(gb + pA * 2 * C + c), gbb = ld_stream8(gb + pB * 2 * C + c);
       const bf16x8 ba = ld_stream8(gb + pA * 2 * C + C + c), bb = ld_stream8(gb + pB * 2 * C + C + c);
       float xf[8], gf[8], bf_[8], o[8];
@@ -175,7 +185,7 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
     for (; q < q1; q += lanes) {
       const long long pA = base + q;
       float xf[8], gf[8], bf_[8], o[8];
-      unpack8(ld_stream8(x + pA * C + c), xf);
+      unpack8(ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), xf);
       unpack8(ld_stream8(gb + pA * 2 * C + c), gf);
       unpack8(ld_stream8(gb + pA * 2 * C + C + c), bf_);
 #pragma unroll
@@ -193,7 +203,8 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
 __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ amask,
                                                                     const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                    int HW, int C, int per_sample, int act, double* __restrict__ racc) {
+                                                                    int HW, int C, int per_sample, int act, double* __restrict__ racc,
+                                                                    int up_w) {
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
   auto one = [&](long long p, int c, float(*a)[8]) {
     float df[8], xf[8], gf[8];
     unpack8(ld_stream8(dout + p * C + c), df);
-    unpack8(ld_stream8(x + p * C + c), xf);
+    unpack8(ld_stream8(x + x_pixel(b, p - (long long)b * HW, HW, up_w) * C + c), xf);
     unpack8(ld_stream8(gb + p * 2 * C + c), gf);
     const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * (C >> 3) + (c >> 3)] : 0xffu;
 #pragma unroll
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
                                                                    const float* __restrict__ style, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ m12,
                                                                    int HW, int C, int per_sample, int act,
-                                                                   bf16* __restrict__ dx, int dx_acc, bf16* __restrict__ dgb) {
+                                                                   bf16* __restrict__ dx, int dx_acc, bf16* __restrict__ dgb, int up_w) {
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long q0 = (long long)blockIdx.x * chunk;
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
     for (; q + lanes < q1; q += 2 * lanes) {
       const long long pA = base + q, pB = base + q + lanes;
       const bf16x8 da = ld_stream8(dout + pA * C + c), db = ld_stream8(dout + pB * C + c);
-      const bf16x8 xa = ld_stream8(x + pA * C + c), xb = ld_stream8(x + pB * C + c);
+      const bf16x8 xa = ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), xb = ld_stream8(x + x_pixel(b, q + lanes, HW, up_w) * C + c);
       const bf16x8 ga = ld_stream8(gb + pA * 2 * C + c), gb2 = ld_stream8(gb + pB * 2 * C + c);
       const uint32_t ma = act != S2E_ACT_NONE ? (uint32_t)amask[pA * cg + mcol] : 0xffu;
       const uint32_t mb = act != S2E_ACT_NONE ? (uint32_t)amask[pB * cg + mcol] : 0xffu;
@@ -335,7 +346,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
     for (; q < q1; q += lanes) {
       const long long p = base + q;
       const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * cg + mcol] : 0xffu;
-      finish(p, ld_stream8(dout + p * C + c), ld_stream8(x + p * C + c), ld_stream8(gb + p * 2 * C + c), mbits);
+      finish(p, ld_stream8(dout + p * C + c), ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), ld_stream8(gb + p * 2 * C + c), mbits);
     }
   }
 }
@@ -541,20 +552,22 @@ __global__ void sn_corr_apply_kernel(const float* __restrict__ coef, const float
 }
 
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd, int B,
-                        int HW, int C, int per_sample, int act, void* out, uint8_t* act_mask, void* stream) {
+                        int HW, int C, int per_sample, int act, void* out, uint8_t* act_mask, int up_w, void* stream) {
   S2E_REQUIRE(C % 8 == 0, "spade_style_fwd needs C %% 8 == 0 (C=%d)", C);
+  S2E_REQUIRE(up_w == 0 || (up_w % 2 == 0 && HW % up_w == 0 && (HW / up_w) % 2 == 0), "spade_style_fwd: bad up-sampled width %d", up_w);
   if ((long long)B * HW == 0) return S2E_OK;
   dim3 grid(ew_chunks(HW, B, C), B);
   spade_style_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gb, style, mean, rstd, HW, C,
-                                                                 per_sample, act, (bf16*)out, act_mask);
+                                                                 per_sample, act, (bf16*)out, act_mask, up_w);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
 
 int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act, double* racc,
-                        void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, void* stream) {
+                        void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, int up_w, void* stream) {
   S2E_REQUIRE(C % 8 == 0, "spade_style_bwd needs C %% 8 == 0 (C=%d)", C);
+  S2E_REQUIRE(up_w == 0 || (up_w % 2 == 0 && HW % up_w == 0 && (HW / up_w) % 2 == 0), "spade_style_bwd: bad up-sampled width %d", up_w);
   cudaStream_t st = (cudaStream_t)stream;
   // racc: double [B][5][C] followed by float m12 [B][2][C]
   S2E_REQUIRE(act == S2E_ACT_NONE || act_mask, "spade_style_bwd: the activation mask written by the forward pass is required");
@@ -562,7 +575,7 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
   float* m12 = (float*)(racc + (size_t)B * 5 * C);
   dim3 grid(red_chunks(HW, B), B);
   spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x,
-                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc);
+                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc, up_w);
   S2E_LAUNCH_CHECK();
   const double count = per_sample ? (double)HW : (double)B * HW;
   spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, m12, dstyle, chsum);
@@ -570,7 +583,7 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
   dim3 grid2(ew_chunks(HW, B, C), B);
   spade_style_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, style,
                                                      mean, rstd, m12, HW, C, per_sample, act, (bf16*)dx, dx_accumulate,
-                                                     (bf16*)dgb);
+                                                     (bf16*)dgb, up_w);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

@@ -27,19 +27,22 @@ class SPADE_STYLE_ResnetBlock(nn.Module):
         if self.learned_shortcut:
             self.norm_s = SPADE_STYLE_Block(fin, opt)
 
-    def _shortcut_nhwc(self, x, seg, w, stats_src=None, sink=None):
+    def _shortcut_nhwc(self, x, seg, w, up=False, sink=None):
         if not self.learned_shortcut:
             return x
-        return self.conv_s.forward_nhwc(self.norm_s.forward_nhwc(x, seg, w, L.ACT_NONE, stats_src, sink))
+        return self.conv_s.forward_nhwc(self.norm_s.forward_nhwc(x, seg, w, L.ACT_NONE, up, sink))
 
-    def forward_nhwc(self, x, seg, latent_style, stats_src=None):
-        """stats_src: the tensor x was nearest-2x up-sampled from, if any -- norm_0 / norm_s then read their batch
-        statistics from it (identical mean and variance, a quarter of the bytes)."""
+    def forward_nhwc(self, x, seg, latent_style, up=False):
+        """up: the block input is the nearest-2x up-sampling of x (generator.py:86-93).  With a learned shortcut only
+        norm_0 / norm_s read the input, so the up-sampled tensor is never written: both read x through an index map.
+        Otherwise (identity shortcut: the input itself is added to the output) it is materialised first."""
+        if up and not self.learned_shortcut:
+            x, up = ops.Upsample2xFn.apply(x), False
         # norm_s and norm_0 both read x: their backward passes write ONE gradient buffer (ops.GradSink)
         sink = ops.GradSink() if (self.learned_shortcut and x.requires_grad) else None
         # the shortcut runs first, as in the reference, so BN buffers / spectral vectors advance in the same order
-        skip = self._shortcut_nhwc(x, seg, latent_style, stats_src, sink)
-        h = self.conv_0.forward_nhwc(self.norm_0.forward_nhwc(x, seg, latent_style, L.ACT_LRELU, stats_src, sink))
+        skip = self._shortcut_nhwc(x, seg, latent_style, up, sink)
+        h = self.conv_0.forward_nhwc(self.norm_0.forward_nhwc(x, seg, latent_style, L.ACT_LRELU, up, sink))
         # out = x_s + dx: the residual add rides in conv_1's epilogue
         return self.conv_1.forward_nhwc(self.norm_1.forward_nhwc(h, seg, latent_style, L.ACT_LRELU), residual=skip)
 

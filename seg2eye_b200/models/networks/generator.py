@@ -66,10 +66,7 @@ class SPADESTYLEGenerator(BaseNetwork):
         ops.prepare_spectral([m for m in self.modules() if isinstance(m, Conv2d)], self.training)
         x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw))
         for name, upsample_first in self._schedule():
-            src = None
-            if upsample_first:
-                src, x = x, self.up(x)
-            x = getattr(self, name).forward_nhwc(x, input, w, stats_src=src)
+            x = getattr(self, name).forward_nhwc(x, input, w, up=upsample_first)
         x = self.conv_img.forward_nhwc(ops.ActFn.apply(x, L.ACT_LRELU))
         clear_seg_cache()
         return ops.TanhFn.apply(x)

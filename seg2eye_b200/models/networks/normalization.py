@@ -140,17 +140,19 @@ class SPADE(nn.Module):
         return ops.tap_conv(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
                             (self.mlp_gamma.bias, self.mlp_beta.bias))
 
-    def modulate(self, x, segmap, style, act, stats_src=None, sink=None):
+    def modulate(self, x, segmap, style, act, up=False, sink=None):
         """x NHWC bf16; style (B,2C) fp32 (s0|s1) ->  act(0.5*[norm(x)(1+gamma)+beta + x(1+s0)+s1]).
-        stats_src: optional tensor that x was nearest-2x up-sampled from (statistics are taken from it)."""
+        up: x is the half-resolution tensor whose nearest-2x up-sampling is the real input (never materialised)."""
         B, H, W, C = x.shape
+        if up:
+            H, W = 2 * H, 2 * W
         gb = self.gamma_beta(segmap, H, W)
         pfn = self.param_free_norm
         cfg = ops.NormCfg(self.per_sample, act, self.training, 0.1, 1e-5)
         if self.per_sample:
-            return ops.SpadeStyleFn.apply(x, gb, style, cfg, None, None, None, stats_src, sink)
+            return ops.SpadeStyleFn.apply(x, gb, style, cfg, None, None, None, up, sink)
         return ops.SpadeStyleFn.apply(x, gb, style, cfg, pfn.running_mean, pfn.running_var, pfn.num_batches_tracked,
-                                      stats_src, sink)
+                                      up, sink)
 
     def forward(self, x, segmap):
         # plain SPADE: out = norm(x)(1+gamma)+beta = 2*0.5*[...] with the style term cancelled (s0=-1, s1=0)
@@ -170,10 +172,11 @@ class SPADE_STYLE_Block(nn.Module):
         self.spade = SPADE(spade_config_str, fin, opt.semantic_nc)
         self.adain = ApplyStyle(opt.w_dim, channels=fin, use_wscale=False)
 
-    def forward_nhwc(self, x, segmap, latent_style, act=L.ACT_NONE, stats_src=None, sink=None):
-        """sink: ops.GradSink shared with the other SPADE_STYLE_Block that reads the same x (one gradient buffer)."""
+    def forward_nhwc(self, x, segmap, latent_style, act=L.ACT_NONE, up=False, sink=None):
+        """up: x is given at half resolution, its nearest-2x up-sampling is the input (read through an index map).
+        sink: ops.GradSink shared with the other SPADE_STYLE_Block that reads the same x (one gradient buffer)."""
         style = self.adain.linear(latent_style)
-        return self.spade.modulate(x, segmap, style, act, stats_src, sink)
+        return self.spade.modulate(x, segmap, style, act, up, sink)
 
     def forward(self, x, segmap, latent_style):
         return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x), segmap, latent_style))

@@ -476,25 +476,32 @@ NormCfg = namedtuple("NormCfg", "per_sample act training momentum eps")
 
 
 class GradSink:
-    """Shared gradient buffer of several SpadeStyleFn calls that consume the SAME input x (norm_0 and norm_s of a
-    ResNet block with a learned shortcut): the first backward to run allocates dx and returns it, the others add into
-    it in place and return nothing, so autograd never launches a separate add over the (large) gradient.  Safe because
-    the engine runs the producer of x only after every consumer's backward has finished."""
-    __slots__ = ("buf",)
+    """Shared gradient buffer of the SpadeStyleFn calls that consume the SAME input x (norm_0 and norm_s of a ResNet
+    block with a learned shortcut): the first backward to run allocates the buffer, the others add into it in place
+    (dx_accumulate), and only the LAST one hands the gradient to autograd, so no separate add over the (large)
+    gradient is ever launched.  Every registered user must take part in the backward pass (true for the block: both
+    branches reach the output)."""
+    __slots__ = ("buf", "users", "seen")
 
     def __init__(self):
-        self.buf = None
+        self.buf, self.users, self.seen = None, 0, 0
 
 
 class SpadeStyleFn(torch.autograd.Function):
-    """out = act(0.5 * [ norm(x) * (1 + gamma) + beta + x * (1 + s0) + s1 ])  (normalization.py:91-105,161-192)."""
+    """out = act(0.5 * [ norm(x) * (1 + gamma) + beta + x * (1 + s0) + s1 ])  (normalization.py:91-105,161-192).
+
+    up=True: x is the (B, H/2, W/2, C) tensor whose nearest-2x up-sampling (generator.py:50,86-93) is the block input; gb
+    and the output live at (H, W).  The up-sampled copy is never written: the kernels read x through an index map, the
+    batch statistics of x and of its up-sampling are identical, and backward reduces the (H, W) gradient 2x2."""
 
     @staticmethod
-    def forward(ctx, x, gb, style, cfg, running_mean, running_var, nbt, stats_src=None, sink=None):
-        # stats_src: the tensor x was nearest-2x up-sampled from (same per-channel mean / variance, 4x fewer bytes)
-        ctx.sink = sink
+    def forward(ctx, x, gb, style, cfg, running_mean, running_var, nbt, up=False, sink=None):
+        ctx.sink, ctx.up = sink, up
+        if sink is not None:
+            sink.users += 1
         x, gb, style = _c(x), _c(gb), _c(style)
-        B, H, W, Cc = x.shape
+        B, Hx, Wx, Cc = x.shape
+        H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
         assert gb.shape == (B, H, W, 2 * Cc) and style.shape == (B, 2 * Cc) and style.dtype == F32
         st = L.stream()
         G = B if cfg.per_sample else 1
@@ -504,59 +511,66 @@ class SpadeStyleFn(torch.autograd.Function):
             mean = torch.empty(G, Cc, dtype=F32, device=x.device)
             rstd = torch.empty(G, Cc, dtype=F32, device=x.device)
             upd = (not cfg.per_sample) and cfg.training and running_mean is not None
-            count = float(H * W if cfg.per_sample else B * H * W)
-            if stats_src is not None:
-                src = _c(stats_src)
-                assert src.shape == (B, H // 2, W // 2, Cc)
-                L.call("s2e_norm_stats", L.ptr(src), B, (H // 2) * (W // 2), Cc, int(cfg.per_sample), L.ptr(acc), st)
-                count_stats = count / 4
-            else:
-                L.call("s2e_norm_stats", L.ptr(x), B, H * W, Cc, int(cfg.per_sample), L.ptr(acc), st)
-                count_stats = count
+            count = float(H * W if cfg.per_sample else B * H * W)     # elements BatchNorm sees (unbiased running_var)
+            count_stats = count / 4 if up else count                  # elements actually summed (the 4x smaller source)
+            L.call("s2e_norm_stats", L.ptr(x), B, Hx * Wx, Cc, int(cfg.per_sample), L.ptr(acc), st)
             L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count_stats, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
                    L.ptr(running_mean) if upd else None, L.ptr(running_var) if upd else None, cfg.momentum,
                    L.ptr(nbt) if upd else None, st)
         else:  # BatchNorm2d in eval mode: running statistics
             mean = running_mean.detach().clone().view(1, Cc)
             rstd = torch.rsqrt(running_var.detach() + cfg.eps).view(1, Cc)
-        out = torch.empty_like(x)
+        out = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
         # backward needs only the sign of `out` (LeakyReLU mask): one bit per element, written by the forward kernel
         amask = None
         if cfg.act != L.ACT_NONE and any(ctx.needs_input_grad[:3]):
             amask = torch.empty(B * H * W * (Cc // 8), dtype=torch.uint8, device=x.device)
         _timed_call("norm", 8.0 * B * H * W * Cc, "s2e_spade_style_fwd", L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
-                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(out), L.ptr(amask), st,
-                    tag="B%d HW%d C%d" % (B, H * W, Cc))
-        ctx.cfg, ctx.batch_stats = cfg, batch_stats
+                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(out), L.ptr(amask), W if up else 0, st,
+                    tag="B%d HW%d C%d%s" % (B, H * W, Cc, " up" if up else ""))
+        ctx.cfg, ctx.batch_stats, ctx.hw = cfg, batch_stats, (H, W)
         ctx.save_for_backward(x, gb, style, mean, rstd, amask)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        cfg = ctx.cfg
+        cfg, up, sink = ctx.cfg, ctx.up, ctx.sink
         if not ctx.batch_stats:
             raise NotImplementedError("backward through SPADE BatchNorm in eval mode is not supported")
         x, gb, style, mean, rstd, amask = ctx.saved_tensors
         dout = _c(dout)
-        B, H, W, Cc = x.shape
+        B, Cc = x.shape[0], x.shape[3]
+        H, W = ctx.hw
+        st = L.stream()
         racc = torch.empty(B * 5 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
-        sink = ctx.sink
-        shared = sink is not None and sink.buf is not None
-        dx = sink.buf if shared else torch.empty_like(x)
+        accumulate = sink is not None and sink.buf is not None
+        dx = sink.buf if accumulate else torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)   # w.r.t. the (H, W) input
+        last = True
         if sink is not None:
-            sink.buf = None if shared else dx     # (cleared by the last user: no reference outlives the backward pass)
+            sink.seen += 1
+            last = sink.seen == sink.users
+            sink.buf = None if last else dx       # no reference outlives the backward pass
+            if last:
+                sink.seen = 0
         dgb = torch.empty_like(gb)
         dstyle = torch.empty_like(style)
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
         L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
-               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(shared), L.ptr(dgb),
-               L.ptr(dstyle), L.ptr(chsum), L.stream())
+               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
+               L.ptr(dstyle), L.ptr(chsum), W if up else 0, st)
         # per-channel sums of the two gradients, for the bias gradients of the convolutions that receive them as dy
         # (TapConvFn.backward picks the attribute up when the tensor reaches it unmodified; otherwise it sums itself)
         dgb._s2e_chsum = chsum[:2 * Cc]
-        if sink is None:
-            dx._s2e_chsum = chsum[2 * Cc:]
-        return (None if shared else dx), dgb, dstyle, None, None, None, None, None, None
+        gx = None
+        if last:
+            if up:      # adjoint of the nearest-2x up-sampling: 2x2 sums
+                gx = torch.empty_like(x)
+                L.call("s2e_upsample2x_bwd", L.ptr(dx), B, H // 2, W // 2, Cc, L.ptr(gx), st)
+            else:
+                gx = dx
+                if sink is None:
+                    gx._s2e_chsum = chsum[2 * Cc:]
+        return gx, dgb, dstyle, None, None, None, None, None, None
 
 
 class InstNormFn(torch.autograd.Function):

@@ -640,3 +640,54 @@ def test_one_channel_head_on_tensor_cores(S):
     y2 = conv.forward_nhwc(nhwc(x2))
     ref = F.conv2d(x2, bf(conv.weight.detach().cpu()), conv.bias.detach().cpu(), padding=2)
     assert y2.shape == (2, 7, 6, 1) and rel(nchw(y2), ref) < TOL_ACT
+
+
+@pytest.mark.parametrize("act,C", [(1, 64), (0, 128)])
+def test_spade_style_on_upsampled_input_without_materialising_it(S, act, C):
+    """SpadeStyleFn(up=True) on x == SpadeStyleFn on nearest-2x(x) (generator.py:50 + normalization.py:91-105), forward,
+    running statistics and all gradients; two consumers of the same x share one gradient buffer (GradSink)."""
+    L, ops = S
+    g = torch.Generator().manual_seed(12)
+    B, h, w = 2, 6, 5
+    x = bf(torch.randn(B, C, h, w, generator=g) + 0.2)
+    gam = [bf(torch.randn(B, C, 2 * h, 2 * w, generator=g) * 0.5) for _ in range(2)]
+    bet = [bf(torch.randn(B, C, 2 * h, 2 * w, generator=g) * 0.5) for _ in range(2)]
+    style = [torch.randn(B, 2 * C, generator=g) * 0.5 for _ in range(2)]
+    dout = [bf(torch.randn(B, C, 2 * h, 2 * w, generator=g)) for _ in range(2)]
+    acts = (act, 0)
+    # reference: materialised up-sampling, two SPADE+Style blocks on it (like norm_0 / norm_s)
+    xr = x.clone().requires_grad_()
+    grs, brs, srs = [t.clone().requires_grad_() for t in gam], [t.clone().requires_grad_() for t in bet], [t.clone().requires_grad_() for t in style]
+    xu = F.interpolate(xr, scale_factor=2, mode="nearest")
+    rms, rvs, refs, tot = [], [], [], 0
+    for i in range(2):
+        rm, rv = torch.zeros(C), torch.ones(C)
+        xn = F.batch_norm(xu, rm, rv, training=True, momentum=0.1, eps=1e-5)
+        o = 0.5 * (xn * (1 + grs[i]) + brs[i] + xu * (1 + srs[i][:, :C, None, None]) + srs[i][:, C:, None, None])
+        if acts[i]:
+            o = F.leaky_relu(o, 0.2)
+        tot = tot + (o * dout[i]).sum()
+        rms.append(rm), rvs.append(rv), refs.append(o.detach())
+    tot.backward()
+    # ours
+    xc0 = nhwc(x).requires_grad_()
+    xc = ops.AddFn.apply(xc0, torch.zeros_like(xc0))
+    sink = ops.GradSink()
+    outs, gbs, scs, bufs = [], [], [], []
+    for i in range(2):
+        gbc = torch.cat([nhwc(gam[i]), nhwc(bet[i])], dim=3).contiguous().requires_grad_()
+        sc = style[i].cuda().requires_grad_()
+        rmc, rvc, nbt = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.tensor(0, device="cuda")
+        cfg = ops.NormCfg(False, acts[i], True, 0.1, 1e-5)
+        outs.append(ops.SpadeStyleFn.apply(xc, gbc, sc, cfg, rmc, rvc, nbt, True, sink))
+        gbs.append(gbc), scs.append(sc), bufs.append((rmc, rvc))
+    assert outs[0].shape == (B, 2 * h, 2 * w, C)
+    sum((o.float() * nhwc(d).float()).sum() for o, d in zip(outs, dout)).backward()
+    for i in range(2):
+        assert rel(nchw(outs[i]), refs[i]) < 5e-3
+    assert rel(nchw(xc0.grad), xr.grad) < TOL_ACT
+    for i in range(2):
+        assert rel(nchw(gbs[i].grad[..., :C]), grs[i].grad) < TOL_ACT and rel(nchw(gbs[i].grad[..., C:]), brs[i].grad) < TOL_ACT
+        assert rel(scs[i].grad, srs[i].grad) < TOL_ACT
+        assert rel(bufs[i][0], rms[i]) < 1e-4 and rel(bufs[i][1], rvs[i]) < 1e-4
+    assert sink.buf is None and sink.seen == 0

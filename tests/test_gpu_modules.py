@@ -151,12 +151,13 @@ def test_generator_blocks_match_oracle_taps(ctx):
         O.generator_forward({k: v.clone() for k, v in sd.items()}, seg, w, ctx.oopt, taps=taps)
     G = load(networks.SPADESTYLEGenerator(ctx.opt), sd).train()
     G2 = load(networks.SPADESTYLEGenerator(ctx.opt), sd).train()
+    G3 = load(networks.SPADESTYLEGenerator(ctx.opt), sd).train()
     segc, wc = seg.cuda(), w.cuda()
     nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
     with torch.no_grad():
         x = G.fc.forward_nhwc(ops.seg_nearest(segc, G.sh, G.sw))
         assert rel(x.permute(0, 3, 1, 2), taps["fc"]) < TOL_ACT
-        chained, fed, prev = {}, {}, "fc"
+        chained, fed, fed_up, prev = {}, {}, {}, "fc"
         for name in ("head_0", "G_middle_0", "G_middle_1", "up_0", "up_1", "up_2", "up_3"):
             up = name != "head_0" and not (name == "G_middle_1" and ctx.opt.num_upsampling_layers == "normal")
             xin = taps[prev]
@@ -164,10 +165,13 @@ def test_generator_blocks_match_oracle_taps(ctx):
                 x = G.up(x)
                 xin = xin.repeat_interleave(2, 2).repeat_interleave(2, 3)
             fed[name] = rel(getattr(G2, name).forward_nhwc(nhwc(xin), segc, wc).permute(0, 3, 1, 2), taps[name])
+            if up:   # the same block fed with the LOW-resolution tensor: up-sampling folded into the SPADE kernels
+                fed_up[name] = rel(getattr(G3, name).forward_nhwc(nhwc(taps[prev]), segc, wc, up=True).permute(0, 3, 1, 2), taps[name])
             x = getattr(G, name).forward_nhwc(x, segc, wc)
             chained[name] = rel(x.permute(0, 3, 1, 2), taps[name])
             prev = name
     assert max(fed.values()) < TOL_ACT, fed
+    assert len(fed_up) == 5 and max(fed_up.values()) < TOL_ACT, fed_up
     assert max(chained.values()) < TOL_CHAIN, chained
 
 
