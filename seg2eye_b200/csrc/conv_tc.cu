@@ -4,7 +4,7 @@
 //   D[128 pixels x BN couts] = sum over taps, 64-channel blocks of  A(tap) [128 x 64] * W(tap)^T [64 x BN]
 //   A tile = one 4-D TMA box {64 ch, TW, TH, TB} of the NHWC input at (w0+dx, h0+dy): halo and padding are
 //   TMA out-of-bounds zero fill, so no im2col is ever materialised.  Both operands K-major, SWIZZLE_128B.
-//   Persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-9 = epilogue
+//   Persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-17 = epilogue
 //   (tcgen05.ld -> scale/bias/act -> bf16 -> swizzled smem -> TMA store).  TMEM accumulator double buffered.
 //
 // Weight-gradient kernel:
@@ -22,8 +22,8 @@ constexpr int BK = 64;  // bf16 elements = 128 bytes = swizzle span
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int OUT_BUF_BYTES = BM * 128;
 constexpr int NUM_THREADS = 192;      // weight-gradient kernel: TMA warp, MMA warp, 4 epilogue warps
-constexpr int FWD_THREADS = 320;      // forward kernel: TMA warp, MMA warp, 8 epilogue warps
-constexpr int FWD_EPI_THREADS = 256;
+constexpr int FWD_THREADS = 576;      // forward kernel: TMA warp, MMA warp, 16 epilogue warps
+constexpr int FWD_EPI_THREADS = 512;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -246,11 +246,14 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
-    // Two warps per TMEM lane quarter (hardware: warp_id % 4 selects the 32 lanes a warp may read); each takes one
-    // 32-column half of every 64-column chunk.  Bias is staged in shared memory once per tile.
+    // ------------------------------------------------------------------ epilogue (warps 2..17)
+    // Four warps per TMEM lane quarter (hardware: warp_id % 4 selects the 32 lanes a warp may read); each takes one
+    // 16-column slice of every 64-column chunk.  Sixteen warps, not eight: the epilogue is a chain of dependent
+    // short-latency steps (tcgen05.ld -> convert -> st.shared -> barrier), so its throughput is set by how many warps
+    // the schedulers can interleave (ncu: 41 % issue slots busy with two epilogue warps per scheduler).
+    // Bias is staged in shared memory once per tile.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;          // 0..3: columns [sub*16, sub*16+16) of the chunk
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
     const bool store_thread = (et == 0);
@@ -280,25 +283,24 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int ch = 0; ch < BN / 64; ++ch) {
           const int nbase = n0 + ch * 64;
           if (nbase >= p.Cout) break;
-          uint32_t r[32];
+          uint32_t r[16];
           const uint32_t taddr =
-              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::MT * BN + j * BN + ch * 64 + half * 32);
-          ptx::tmem_ld_32x32(taddr, r);
-          uint4 mk[4] = {make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u),
-                         make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u)};
-          if (p.res) mk[0] = mk[1] = mk[2] = mk[3] = make_uint4(0u, 0u, 0u, 0u);   // rows outside the tensor add nothing
+              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::MT * BN + j * BN + ch * 64 + sub * 16);
+          ptx::tmem_ld_32x16(taddr, r);
+          const uint32_t dflt = p.res ? 0u : 0x3f803f80u;   // residual: add nothing / mask: keep everything
+          uint4 mk[2] = {make_uint4(dflt, dflt, dflt, dflt), make_uint4(dflt, dflt, dflt, dflt)};
           if (mrow) {  // host guarantees Cout % 64 == 0 when a mask / residual is given
 #pragma unroll
-            for (int i = 0; i < 4; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + half * 32) + i);
+            for (int i = 0; i < 2; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + sub * 16) + i);
           }
           // the TMA store that last read this staging buffer must have finished reading it
           if (store_thread) ptx::tma_store_wait_read<1>();
           ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
           ptx::tmem_ld_wait();
           uint8_t* ob = out_buf + buf * OUT_BUF_BYTES + row * 128;
-          const float4* bsrc = reinterpret_cast<const float4*>(s_bias + ch * 64 + half * 32);
+          const float4* bsrc = reinterpret_cast<const float4*>(s_bias + ch * 64 + sub * 16);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             const float4 b0v = bsrc[2 * i], b1v = bsrc[2 * i + 1];
             uint32_t pk[4];
             float v[8];
@@ -330,7 +332,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 pk[e] &= keep;
               }
             }
-            *reinterpret_cast<uint4*>(ob + (((half * 4 + i) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(ob + (((sub * 2 + i) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(2, FWD_EPI_THREADS);

@@ -42,9 +42,43 @@ def run(B, H, W, Cin, Cout, k, once, n=5):
     print(line, flush=True)
 
 
+def run_seg(B, H, W, once, n=5):
+    """mlp_shared as the K=64 GEMM on the im2col'd segmap (SegConvFn) + ReLU."""
+    seg = torch.nn.functional.one_hot(torch.randint(0, 4, (B, H, W), device="cuda"), 4).permute(0, 3, 1, 2).float().contiguous()
+    col = ops.seg_im2col(seg, H, W)
+    w = (torch.randn(128, 4, 3, 3, device="cuda") / 6).requires_grad_()
+    b = torch.zeros(128, device="cuda").requires_grad_()
+    dy = torch.randn(B, H, W, 128, device="cuda").to(torch.bfloat16)
+    reps = 1 if once else n + 2
+    for i in range(reps):
+        if i == reps - n and not once:
+            ops.profile_begin()
+        y = ops.SegConvFn.apply(col, w, b, L.ACT_RELU, False)
+        y.backward(dy)
+        w.grad = b.grad = None
+    torch.cuda.synchronize()
+    if once:
+        return
+    res = {}
+    for a, e, fl, tag in ops._prof["tc"]:
+        res.setdefault(tag.split()[0], []).append((a.elapsed_time(e), fl))
+    ops.profile_end()
+    line = "%-34s" % ("seg B%d %dx%d 4->128 (K=64 GEMM)" % (B, H, W))
+    for kind in res:
+        ms = sorted(t for t, _ in res[kind])[len(res[kind]) // 2]
+        line += "  %s %.3f ms %5.0f TF/s" % (kind, ms, res[kind][0][1] / ms / 1e9)
+    print(line, flush=True)
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     once = "--once" in sys.argv
+    for a in sys.argv[1:]:
+        if a.startswith("--dbg4="):     # 2: force 4 stages + 2 output buffers, 8: force 2 stages + 8 output buffers
+            L.call("s2e_debug_set", 4, int(a.split("=")[1]))
     shapes = [tuple(int(v) for v in args[i:i + 6]) for i in range(0, len(args), 6)] or DEFAULT
-    for s in shapes:
-        run(*s, once)
+    if "--seg" in sys.argv:
+        run_seg(16, 640, 384, once)
+    else:
+        for s in shapes:
+            run(*s, once)
