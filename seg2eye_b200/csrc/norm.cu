@@ -131,7 +131,7 @@ __device__ __forceinline__ uint8_t sign_bits8(const float* o) {
 // grid = (pixel chunks, B).  A thread owns one 8-channel group: its per-channel constants (mean, rstd, style) are
 // loaded once into registers, then it streams pixels: 3 x 16-byte loads + 1 x 16-byte store per pixel, two pixels in
 // flight per iteration.
-__global__ void __launch_bounds__(NT, 3) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
+__global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                              const float* __restrict__ style, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, int HW, int C, int per_sample,
                                                              int act, bf16* __restrict__ out, uint8_t* __restrict__ amask, int up_w) {
