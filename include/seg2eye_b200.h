@@ -93,6 +93,10 @@ typedef struct {
   const void* residual;          /* optional bf16 tensor shaped like y, added after the activation: the `x_s + dx` of
                                     architecture.py:44 fused into conv_1's epilogue (tcgen05 path only) */
   int bias_n;                    /* number of valid bias entries, 0 = Cout (a channel-padded output) */
+  int in_act;                    /* activation applied to x as it is loaded (forward and weight gradient): the
+                                    F.leaky_relu(x, 2e-1) in front of conv_img, generator.py:97-98.  CUDA-core kernels only */
+  float mask_slope;              /* with relu_mask: where mask <= 0 the output is multiplied by this instead of zeroed
+                                    (LeakyReLU backward fused into a data gradient).  CUDA-core kernels only */
 } s2e_conv_t;
 
 int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,

@@ -21,7 +21,7 @@ class ConvDesc(C.Structure):
                 ("tap_dy", C.c_int * MAX_TAPS), ("tap_dx", C.c_int * MAX_TAPS), ("act", C.c_int),
                 ("tile_w", C.c_int), ("tile_h", C.c_int), ("tile_b", C.c_int),
                 ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p),
-                ("residual", C.c_void_p), ("bias_n", C.c_int)]
+                ("residual", C.c_void_p), ("bias_n", C.c_int), ("in_act", C.c_int), ("mask_slope", C.c_float)]
 
 
 class SnJob(C.Structure):

@@ -14,7 +14,8 @@ struct Geom {
 template <int TN>
 __global__ void __launch_bounds__(256) simt_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                        const float* __restrict__ bias, const float* __restrict__ scale,
-                                                       bf16* __restrict__ y, const Geom g, const bf16* __restrict__ mask) {
+                                                       bf16* __restrict__ y, const Geom g, const bf16* __restrict__ mask,
+                                                       float mask_slope) {
   constexpr int BNT = 16 * TN;
   __shared__ float As[16][64 + 1];
   __shared__ float Bs[16][BNT + 1];
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) simt_fwd_kernel(const bf16* __restrict__ 
       const int n = n0 + tx + 16 * j;
       if (n >= g.Cout) continue;
       float v = act_apply(acc[i][j] * sc + (bias ? __ldg(bias + n) : 0.f), g.act);
-      if (mask && !(__bfloat162float(mask[p * g.Cout + n]) > 0.f)) v = 0.f;
+      if (mask && !(__bfloat162float(mask[p * g.Cout + n]) > 0.f)) v *= mask_slope;
       y[p * g.Cout + n] = __float2bfloat16(v);
     }
   }
@@ -193,19 +194,20 @@ int s2e_tapconv_fwd_simt(const s2e_conv_t* d, const void* x, const void* wp, con
                          void* y, cudaStream_t stream) {
   S2E_REQUIRE(!d->residual && (d->bias_n == 0 || d->bias_n == d->Cout),
               "tapconv_fwd: fused residual / channel-padded bias exist on the tcgen05 path only");
-  if (!s2e_debug_get(2) && !d->relu_mask) {  // debug key 2 = keep thin layers on the generic kernel
+  if (!s2e_debug_get(2)) {  // debug key 2 = keep thin layers on the generic kernel
     const int rc = s2e_thin_fwd(d, x, wp, bias, scale, y, stream);
     if (rc != 0) return rc < 0 ? rc : S2E_OK;
   }
+  S2E_REQUIRE(d->in_act == S2E_ACT_NONE, "tapconv_fwd: in_act is implemented by the thin-layer kernels only");
   Geom g = make_geom(d);
   const long long P = (long long)d->B * d->Ho * d->Wo;
   if (P == 0) return S2E_OK;
   if (d->Cout > 16) {
     dim3 grid((unsigned)ceil_div_ll(P, 64), (unsigned)ceil_div(d->Cout, 64));
-    simt_fwd_kernel<4><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, (const bf16*)d->relu_mask);
+    simt_fwd_kernel<4><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, (const bf16*)d->relu_mask, d->mask_slope);
   } else {
     dim3 grid((unsigned)ceil_div_ll(P, 64), (unsigned)ceil_div(d->Cout, 16));
-    simt_fwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, (const bf16*)d->relu_mask);
+    simt_fwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, (const bf16*)d->relu_mask, d->mask_slope);
   }
   S2E_LAUNCH_CHECK();
   return S2E_OK;
@@ -216,6 +218,7 @@ int s2e_tapconv_wgrad_simt(const s2e_conv_t* d, const void* x, const void* dy, f
     const int rc = s2e_thin_wgrad(d, x, dy, dwp, stream);
     if (rc != 0) return rc < 0 ? rc : S2E_OK;
   }
+  S2E_REQUIRE(d->in_act == S2E_ACT_NONE, "tapconv_wgrad: in_act is implemented by the thin-layer kernels only");
   Geom g = make_geom(d);
   const long long P = (long long)d->B * d->Ho * d->Wo;
   if (P == 0) return S2E_OK;

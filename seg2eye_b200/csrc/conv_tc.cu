@@ -413,6 +413,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.res = (const bf16*)d->residual;
   p.bias_n = d->bias_n > 0 ? d->bias_n : d->Cout;
   S2E_REQUIRE(!(p.mask && p.res), "tapconv_fwd: relu_mask and residual are mutually exclusive");
+  S2E_REQUIRE(d->in_act == S2E_ACT_NONE && d->mask_slope == 0.f, "tapconv_fwd: in_act / mask_slope exist on the CUDA-core path only");
   S2E_REQUIRE(!(p.mask || p.res) || d->Cout % 64 == 0, "tapconv_fwd: relu_mask / residual need Cout %% 64 == 0 on the tcgen05 path");
   p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);
   p.bias = bias;
@@ -713,6 +714,7 @@ int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const
 }
 
 int s2e_tapconv_wgrad_tc(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, cudaStream_t stream) {
+  S2E_REQUIRE(d->in_act == S2E_ACT_NONE, "tapconv_wgrad: in_act exists on the CUDA-core path only");
   S2E_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0 && d->Cin >= 64 && d->Cout >= 64,
               "tcgen05 wgrad needs Cin,Cout %% 8 == 0 and >= 64 (Cin=%d Cout=%d)", d->Cin, d->Cout);
   // orientation: the N side of the accumulator should be the wide one (N = 256 halves the shared-memory traffic

@@ -10,7 +10,7 @@
 namespace {
 
 struct ThinGeom {
-  int B, Hi, Wi, Cin, Ho, Wo, Cout, ntaps, act;
+  int B, Hi, Wi, Cin, Ho, Wo, Cout, ntaps, act, in_act;
   int dy[S2E_MAX_TAPS], dx[S2E_MAX_TAPS];
 };
 
@@ -23,7 +23,9 @@ constexpr int K1_PX = 4;
 template <int CS4>  // CS4 = 1: Cin == 4 (one 8-byte load per pixel-tap); 0: generic Cin <= 32
 __global__ void __launch_bounds__(256) thin_in_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, const float* __restrict__ scale,
-                                                          bf16* __restrict__ y, const ThinGeom g, int quads_per_row, long long nquads) {
+                                                          bf16* __restrict__ y, const ThinGeom g, int quads_per_row, long long nquads,
+                                                          const bf16* __restrict__ mask, float mask_slope) {
+  // mask (optional, shaped like y): where mask <= 0 the output is multiplied by mask_slope (fused [Leaky]ReLU backward)
   extern __shared__ float ws[];  // [T][Cs][cot]  (cot = couts of this block)
   const int co0 = blockIdx.y * K1_CO_TILE;
   const int cot = min(K1_CO_TILE, g.Cout - co0);
@@ -106,6 +108,12 @@ __global__ void __launch_bounds__(256) thin_in_fwd_kernel(const bf16* __restrict
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = act_apply(acc[i][j] * sc + bv[j], g.act);
+        if (mask) {
+          float mf[8];
+          unpack8(ld_stream8(mask + (yrow - y) + (long long)(wo0 + i) * g.Cout), mf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= (mf[j] > 0.f ? 1.f : mask_slope);
+        }
         st_stream8(yrow + (long long)(wo0 + i) * g.Cout, pack8(o));
       }
     }
@@ -284,6 +292,10 @@ __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __re
   for (int hp = threadIdx.x >> 3; hp < T1_NHP; hp += 32) {
     float xf[8];
     unpack8(*reinterpret_cast<const bf16x8*>(xs + hp * 64 + sub * 8), xf);
+    if (g.in_act != S2E_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xf[j] = act_apply(xf[j], g.in_act);
+    }
     float part[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -354,6 +366,10 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
     for (long long p = p0; p < p1; ++p, ap += Cw) {
       float a[8];
       unpack8(*reinterpret_cast<const bf16x8*>(ap), a);
+      if (!thin_x && g.in_act != S2E_ACT_NONE) {   // A is the layer input x: activation applied on load
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = act_apply(a[j], g.in_act);
+      }
       const bf16* sb = S + ((long long)b * HS * WS) * Cs + cs;
       float sv[TMAX];
 #pragma unroll
@@ -361,7 +377,8 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
         const int hs = h + tdy[t], wss = w + tdx[t];
         const bool ok = t < g.ntaps && hs >= 0 && hs < HS && wss >= 0 && wss < WS;
         const int hc = min(max(hs, 0), HS - 1), wc = min(max(wss, 0), WS - 1);
-        const float v = __bfloat162float(sb[((long long)hc * WS + wc) * Cs]);
+        float v = __bfloat162float(sb[((long long)hc * WS + wc) * Cs]);
+        if (thin_x) v = act_apply(v, g.in_act);      // S is the layer input x
         sv[t] = ok ? v : 0.f;
       }
 #pragma unroll
@@ -419,6 +436,7 @@ ThinGeom make_thin_geom(const s2e_conv_t* d) {
   g.Cout = d->Cout;
   g.ntaps = d->ntaps;
   g.act = d->act;
+  g.in_act = d->in_act;
   for (int i = 0; i < d->ntaps; ++i) {
     g.dy[i] = d->tap_dy[i];
     g.dx[i] = d->tap_dx[i];
@@ -435,6 +453,11 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
   if (P == 0) return 1;
   if (P * 32 >= (1LL << 31)) return 0;  // 32-bit index math inside the thin kernels
   ThinGeom g = make_thin_geom(d);
+  const bf16* mask = (const bf16*)d->relu_mask;
+  // input activation: tiled conv_img kernel only; output mask: thin-input kernel only -- everything else declines
+  const bool tile_ok = d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9 && d->Hi == d->Ho && d->Wi == d->Wo;
+  if (d->in_act != S2E_ACT_NONE && !tile_ok) return 0;
+  if (mask && !(d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8)) return 0;
   if (d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8) {
     const int cot = d->Cout < K1_CO_TILE ? d->Cout : K1_CO_TILE;
     if (d->Cout % K1_CO_TILE != 0 && d->Cout > K1_CO_TILE) return 0;
@@ -454,9 +477,11 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, (unsigned)ceil_div(d->Cout, K1_CO_TILE));
     if (d->Cin == 4)
-      thin_in_fwd_kernel<1><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads);
+      thin_in_fwd_kernel<1><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads, mask,
+                                                       d->mask_slope);
     else
-      thin_in_fwd_kernel<0><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads);
+      thin_in_fwd_kernel<0><<<grid, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, qpr, nquads, mask,
+                                                       d->mask_slope);
     S2E_LAUNCH_CHECK();
     return 1;
   }
@@ -476,6 +501,7 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
       return 1;
     }
   }
+  if (d->in_act != S2E_ACT_NONE) return 0;
   if (d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9) {
     const long long warps = (long long)s2e_num_sms() * 32;
     long long ppw = (P + warps - 1) / warps;

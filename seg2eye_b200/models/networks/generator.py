@@ -67,6 +67,6 @@ class SPADESTYLEGenerator(BaseNetwork):
         x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw))
         for name, upsample_first in self._schedule():
             x = getattr(self, name).forward_nhwc(x, input, w, up=upsample_first)
-        x = self.conv_img.forward_nhwc(ops.ActFn.apply(x, L.ACT_LRELU))
+        x = self.conv_img.forward_nhwc(x, in_act=L.ACT_LRELU)     # leaky_relu(x, 0.2) -> conv_img, one kernel
         clear_seg_cache()
         return ops.TanhFn.apply(x)

@@ -51,9 +51,17 @@ class Conv2d(nn.Module):
             inv = ops.spectral_inv_sigma(self.weight_orig, self.weight_u, self.weight_v, self.training)
         return (self.weight_u, self.weight_v, inv)
 
-    def forward_nhwc(self, x, act=None, residual=None):
-        """residual: optional tensor shaped like the output, added in the convolution's epilogue."""
+    def forward_nhwc(self, x, act=None, residual=None, in_act=L.ACT_NONE):
+        """residual: optional tensor shaped like the output, added in the convolution's epilogue.
+        in_act: activation applied to x first; fused into the kernels for the conv_img shape (64 -> 1, 3x3), a separate
+        elementwise kernel otherwise."""
         cfg = self.cfg if act is None else self.cfg._replace(act=act)
+        if in_act != L.ACT_NONE:
+            if (self.out_channels == 1 and self.in_channels == 64 and x.shape[-1] == 64 and cfg.kh == 3 and cfg.stride == 1
+                    and cfg.pad == 1):
+                cfg = cfg._replace(in_act=in_act)
+            else:
+                x = ops.ActFn.apply(x, in_act)
         if x.shape[-1] != self.in_channels:   # zero-padded activation channels (e.g. the 16-channel D input)
             assert x.shape[-1] > self.in_channels, "input has fewer channels than the layer expects"
             cfg = cfg._replace(cin_pad=x.shape[-1])

@@ -15,9 +15,11 @@ from . import _lib as L
 BF16 = torch.bfloat16
 F32 = torch.float32
 
-ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad cout_pad", defaults=(False, 0, 0))
+ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad cout_pad in_act", defaults=(False, 0, 0, 0))
 # cin_pad: the activations carry cin_pad >= Cin channels (zero padded), packed weights get zero columns for them
 # relu_in: the input of this convolution is the output of a ReLU whose backward is fused into our data-gradient epilogue
+# in_act:  activation applied to the input as the kernel loads it (LeakyReLU in front of conv_img, generator.py:97-98);
+#          its backward rides in the data-gradient kernel (mask = the saved pre-activation input).  Thin-layer kernels only
 # cout_pad: run a layer with very few output channels (the 1-channel PatchGAN head, K = 8192) on the tensor-core kernels
 #           with its output channels zero-padded to cout_pad; the caller sees the first Cout channels only
 
@@ -295,7 +297,9 @@ class TapConvFn(torch.autograd.Function):
         y = torch.empty(B, Ho, Wo, Cp, dtype=BF16, device=x.device)
         d = _desc(B, His, Wis, Cinp, Ho, Wo, Cp, taps, cfg.act)
         d.bias_n = Cout
+        d.in_act = cfg.in_act
         impl = _pick(Cinp % 64 == 0 and Cp % 8 == 0)
+        assert cfg.in_act == L.ACT_NONE or (impl == L.IMPL_SIMT and cfg.stride == 1), "in_act: thin CUDA-core layers only"
         fuse_res = res is not None and impl == L.IMPL_TC and Cp % 64 == 0
         if res is not None:
             res = _c(res)
@@ -347,6 +351,9 @@ class TapConvFn(torch.autograd.Function):
             if cfg.relu_in:
                 assert cfg.stride == 1 and Cinp % 64 == 0
                 dd.relu_mask = L.ptr(xs)   # x = relu(.) > 0 exactly where the ReLU passed gradient
+            if cfg.in_act != L.ACT_NONE:   # gradient w.r.t. the PRE-activation input: act'(x) * conv^T(dy)
+                dd.relu_mask = L.ptr(xs)
+                dd.mask_slope = 0.2 if cfg.in_act == L.ACT_LRELU else 0.0
             dxs = torch.empty(B, His, Wis, Cinp, dtype=BF16, device=dy.device)
             impl = _pick(Cout % 64 == 0 and Cinp % 8 == 0)
             if impl == L.IMPL_TC:
@@ -366,6 +373,7 @@ class TapConvFn(torch.autograd.Function):
         if any(need_w):
             dwp = torch.zeros(len(taps) * Cout * Cinp, dtype=F32, device=dy.device)
             d = _desc(B, His, Wis, Cinp, Ho, Wo, Cout, taps, L.ACT_NONE)
+            d.in_act = cfg.in_act
             impl = _pick(Cinp >= 64 and Cout >= 64 and Cinp % 8 == 0 and Cout % 8 == 0)
             if impl == L.IMPL_TC:
                 _timed_call("tc", ctx.flops, "s2e_tapconv_wgrad", d, L.ptr(xs), L.ptr(dpre), L.ptr(dwp), impl, st,

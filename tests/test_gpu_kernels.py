@@ -691,3 +691,33 @@ def test_spade_style_on_upsampled_input_without_materialising_it(S, act, C):
         assert rel(scs[i].grad, srs[i].grad) < TOL_ACT
         assert rel(bufs[i][0], rms[i]) < 1e-4 and rel(bufs[i][1], rvs[i]) < 1e-4
     assert sink.buf is None and sink.seen == 0
+
+
+def test_conv_img_with_fused_leaky_relu_input(S):
+    """leaky_relu(x, 0.2) -> conv 64->1 3x3 (generator.py:97-98) as ONE forward kernel; its backward applies the
+    LeakyReLU derivative inside the data-gradient kernel and the activation inside the weight-gradient kernel."""
+    L, ops = S
+    from seg2eye_b200.models.networks.layers import Conv2d
+    g = torch.Generator().manual_seed(31)
+    B, H, W = 2, 21, 37
+    x = bf(torch.randn(B, 64, H, W, generator=g))
+    conv = Conv2d(64, 1, 3, padding=1).cuda()
+    w = bf(conv.weight.detach().cpu())
+    conv.weight.data.copy_(w)
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), conv.bias.detach().cpu().clone().requires_grad_()
+    yr = F.conv2d(F.leaky_relu(xr, 0.2), wr, br, padding=1)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc = nhwc(x).requires_grad_()
+    n0 = L.launches
+    y = conv.forward_nhwc(xc, in_act=L.ACT_LRELU)
+    assert L.launches - n0 <= 2          # (weight pack +) one convolution kernel: no separate activation pass
+    y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < TOL_ACT
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
+    assert rel(conv.weight.grad, wr.grad) < TOL_ACT and rel(conv.bias.grad, br.grad) < TOL_ACT
+    # other shapes fall back to the separate activation kernel with identical results
+    conv2 = Conv2d(16, 1, 3, padding=1).cuda()
+    x2 = bf(torch.randn(B, 16, H, W, generator=g))
+    ref2 = F.conv2d(F.leaky_relu(x2, 0.2), bf(conv2.weight.detach().cpu()), conv2.bias.detach().cpu(), padding=1)
+    assert rel(nchw(conv2.forward_nhwc(nhwc(x2), in_act=L.ACT_LRELU)), ref2) < TOL_ACT
