@@ -97,6 +97,14 @@ typedef struct {
                                     F.leaky_relu(x, 2e-1) in front of conv_img, generator.py:97-98.  CUDA-core kernels only */
   float mask_slope;              /* with relu_mask: where mask <= 0 the output is multiplied by this instead of zeroed
                                     (LeakyReLU backward fused into a data gradient).  CUDA-core kernels only */
+  /* Fused SPADE+Style modulation for inference / no-grad forwards (normalization.py:91-105,161-192): the convolution is
+   * the gamma|beta convolution (Cout = 2*spade_C, spade_C in {64, 128}) and instead of gamma|beta the kernel writes
+   *   y[B][Ho][Wo][spade_C] = act( 0.5 * [ (x*ka + kb) * (1 + gamma) + beta + x*kc + s1 ] )
+   * spade_x: the block input x (bf16 NHWC, spade_C channels; at half resolution when spade_up != 0, see s2e_spade_style_fwd);
+   * spade_par: float [B][4][spade_C] = ka (rstd), kb (-mean*rstd), kc (1 + s0), s1 (s2e_spade_params).  tcgen05 path only */
+  const void* spade_x;
+  const float* spade_par;
+  int spade_C, spade_act, spade_up;
 } s2e_conv_t;
 
 int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
@@ -177,6 +185,10 @@ int s2e_norm_finalize(const double* acc, int G, int C, double count, double coun
 /* up_w != 0: x is the [B][H/2][W/2][C] tensor whose nearest-2x up-sampling (generator.py:50) is the block input; up_w = W
  * of the up-sampled map.  The up-sampled copy is never materialised; mean / rstd of the two are identical.  In backward
  * dx is still the gradient w.r.t. the UP-SAMPLED input (B*HW*C); reduce it with s2e_upsample2x_bwd. */
+/* per-(sample, channel) constants of the fused variant (s2e_conv_t.spade_par): par[b][0..3][c] = rstd, -mean*rstd,
+ * 1 + style[b][c], style[b][C + c]; mean / rstd are [G][C] with G = per_sample ? B : 1 */
+int s2e_spade_params(const float* mean, const float* rstd, const float* style, int B, int C, int per_sample, float* par,
+                     void* stream);
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd,
                         int B, int HW, int C, int per_sample, int act, void* out, uint8_t* act_mask, int up_w,
                         void* stream);

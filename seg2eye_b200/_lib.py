@@ -21,7 +21,9 @@ class ConvDesc(C.Structure):
                 ("tap_dy", C.c_int * MAX_TAPS), ("tap_dx", C.c_int * MAX_TAPS), ("act", C.c_int),
                 ("tile_w", C.c_int), ("tile_h", C.c_int), ("tile_b", C.c_int),
                 ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p),
-                ("residual", C.c_void_p), ("bias_n", C.c_int), ("in_act", C.c_int), ("mask_slope", C.c_float)]
+                ("residual", C.c_void_p), ("bias_n", C.c_int), ("in_act", C.c_int), ("mask_slope", C.c_float),
+                ("spade_x", C.c_void_p), ("spade_par", C.c_void_p), ("spade_C", C.c_int), ("spade_act", C.c_int),
+                ("spade_up", C.c_int)]
 
 
 class SnJob(C.Structure):
@@ -60,6 +62,7 @@ _SIGS = {
     "s2e_depth_to_space": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_norm_stats": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_norm_finalize": [_P, _I, _I, _D, _D, _F, _P, _P, _P, _P, _F, _P, _P],
+    "s2e_spade_params": [_P, _P, _P, _I, _I, _I, _P, _P],
     "s2e_spade_style_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P],
     "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P, _P],

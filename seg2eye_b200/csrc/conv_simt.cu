@@ -192,8 +192,8 @@ int s2e_thin_wgrad(const s2e_conv_t*, const void*, const void*, float*, cudaStre
 
 int s2e_tapconv_fwd_simt(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
                          void* y, cudaStream_t stream) {
-  S2E_REQUIRE(!d->residual && (d->bias_n == 0 || d->bias_n == d->Cout),
-              "tapconv_fwd: fused residual / channel-padded bias exist on the tcgen05 path only");
+  S2E_REQUIRE(!d->residual && !d->spade_x && (d->bias_n == 0 || d->bias_n == d->Cout),
+              "tapconv_fwd: fused residual / SPADE epilogue / channel-padded bias exist on the tcgen05 path only");
   if (!s2e_debug_get(2)) {  // debug key 2 = keep thin layers on the generic kernel
     const int rc = s2e_thin_fwd(d, x, wp, bias, scale, y, stream);
     if (rc != 0) return rc < 0 ? rc : S2E_OK;

@@ -88,6 +88,11 @@ struct FwdParams {
   const bf16* mask;   // fused ReLU backward: zero the output where mask <= 0
   const bf16* res;    // fused residual: output += res (same shape as y); never together with mask
   int bias_n;         // valid bias entries (<= Cout; the rest of a channel-padded output gets no bias)
+  // fused SPADE+Style modulation (inference): the accumulator holds gamma | beta (sC channels each) and the kernel writes
+  // act(0.5 * [(x*ka + kb) * (1 + gamma) + beta + x*kc + s1]) with sC channels instead of gamma | beta
+  const bf16* sx;     // block input x, [B][Ho][Wo][sC] or, with sup != 0, its half-resolution source [B][Ho/2][Wo/2][sC]
+  const float* spar;  // [B][4][sC]: ka = rstd, kb = -mean*rstd, kc = 1 + s0, s1
+  int sC, sact, sup;
   uint32_t a_box_bytes;
   const float* bias;
   const float* scale;
@@ -264,7 +269,15 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int n0 = (t % p.tiles_n) * BN;
       const int grp = t / p.tiles_n;
-      if (et < BN) s_bias[et] = (p.bias && n0 + et < p.bias_n) ? __ldg(p.bias + n0 + et) : 0.f;
+      if (et < BN) {
+        float bv = (p.bias && n0 + et < p.bias_n) ? __ldg(p.bias + n0 + et) : 0.f;
+        if (p.sx && et >= p.sC && et < 2 * p.sC) {   // fused SPADE: beta's bias absorbs the style offset s1 of this tile's sample
+          int w0t, h0t, b0t;
+          subtile_origin(p, (t / p.tiles_n) * Cfg::MT, w0t, h0t, b0t);
+          bv += __ldg(p.spar + ((size_t)min(b0t, p.B - 1) * 4 + 3) * p.sC + (et - p.sC));
+        }
+        s_bias[et] = bv;
+      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -273,21 +286,32 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         subtile_origin(p, grp * Cfg::MT + j, w0, h0, b0);
         const bf16* side = p.mask ? p.mask : p.res;   // per-pixel side input shaped like the output (mask or residual)
         const bf16* mrow = nullptr;
-        if (side) {
+        const float* par = nullptr;
+        if (side || p.sx) {
           const int tw = row % p.TW, r2 = row / p.TW;
           const int th = r2 % p.TH, tb = r2 / p.TH;
-          if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo)
-            mrow = side + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
+          if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo) {
+            if (side) {
+              mrow = side + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
+            } else if (p.sup) {   // x lives at half resolution (nearest 2x up-sampling folded in)
+              mrow = p.sx + ((((size_t)(b0 + tb) * (p.Ho >> 1) + ((h0 + th) >> 1)) * (p.Wo >> 1) + ((w0 + tw) >> 1)) * p.sC);
+            } else {
+              mrow = p.sx + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.sC);
+            }
+          }
+          if (p.sx) par = p.spar + (size_t)min(b0, p.B - 1) * 4 * p.sC;   // host guarantees TB == 1: one sample per tile
         }
+        const int nch = p.sx ? (p.sC >> 6) : BN / 64;
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 64; ++ch) {
+        for (int ch = 0; ch < nch; ++ch) {
           const int nbase = n0 + ch * 64;
-          if (nbase >= p.Cout) break;
-          uint32_t r[16];
+          if (!p.sx && nbase >= p.Cout) break;
+          uint32_t r[16], rb[16];
           const uint32_t taddr =
               tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::MT * BN + j * BN + ch * 64 + sub * 16);
           ptx::tmem_ld_32x16(taddr, r);
-          const uint32_t dflt = p.res ? 0u : 0x3f803f80u;   // residual: add nothing / mask: keep everything
+          if (p.sx) ptx::tmem_ld_32x16(taddr + (uint32_t)p.sC, rb);   // beta sits sC columns after gamma
+          const uint32_t dflt = p.mask ? 0x3f803f80u : 0u;   // mask: keep everything / residual, x: zero
           uint4 mk[2] = {make_uint4(dflt, dflt, dflt, dflt), make_uint4(dflt, dflt, dflt, dflt)};
           if (mrow) {  // host guarantees Cout % 64 == 0 when a mask / residual is given
 #pragma unroll
@@ -318,6 +342,28 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int e = 0; e < 4; ++e) {
                 v[2 * e] += __uint_as_float(rw[e] << 16);
                 v[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+              }
+            }
+            if (p.sx) {  // v = gamma (+bias); form the SPADE+Style output from x, beta and the per-channel constants
+              const int c0 = ch * 64 + sub * 16 + 8 * i;
+              const float4* bb = reinterpret_cast<const float4*>(s_bias + p.sC + c0);
+              const float4 bb0 = bb[0], bb1 = bb[1];
+              const float betab[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+              const float4* pa = reinterpret_cast<const float4*>(par + c0);
+              const float4* pb = reinterpret_cast<const float4*>(par + p.sC + c0);
+              const float4* pc = reinterpret_cast<const float4*>(par + 2 * p.sC + c0);
+              const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), k0 = __ldg(pb), k1 = __ldg(pb + 1), c0v = __ldg(pc), c1v = __ldg(pc + 1);
+              const float ka[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float kb[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+              const float kc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+              const uint32_t xw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float xv = __uint_as_float((e & 1) ? (xw[e >> 1] & 0xffff0000u) : (xw[e >> 1] << 16));
+                const float beta = fmaf(__uint_as_float(rb[8 * i + e]), scale, betab[e]);   // includes the style offset s1
+                float o = 0.5f * (fmaf(fmaf(xv, ka[e], kb[e]), 1.f + v[e], beta) + xv * kc[e]);
+                if (p.sact == S2E_ACT_LRELU) o = fmaxf(o, 0.2f * o);
+                v[e] = o;
               }
             }
 #pragma unroll
@@ -391,7 +437,15 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   int rc;
   if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
   if ((rc = make_map_w(&tmB, wp, d->ntaps, d->Cout, d->Cin, BN)) != S2E_OK) return rc;
-  if ((rc = make_map_nhwc(&tmY, y, d->B, d->Ho, d->Wo, d->Cout, tw, th, tb)) != S2E_OK) return rc;
+  const bool spade = d->spade_x != nullptr;
+  if (spade) {
+    S2E_REQUIRE(d->spade_par && (d->spade_C == 64 || d->spade_C == 128) && d->Cout == 2 * d->spade_C && BN == d->Cout,
+                "tapconv_fwd: fused SPADE needs Cout = 2*C = the N tile, C in {64, 128} (C=%d Cout=%d)", d->spade_C, d->Cout);
+    S2E_REQUIRE(tb == 1 && d->act == S2E_ACT_NONE && !d->relu_mask && !d->residual && (d->bias_n == 0 || d->bias_n == d->Cout),
+                "tapconv_fwd: fused SPADE needs one sample per tile and a plain gamma|beta convolution");
+    S2E_REQUIRE(!d->spade_up || (d->Ho % 2 == 0 && d->Wo % 2 == 0), "tapconv_fwd: fused SPADE with up-sampling needs even H, W");
+  }
+  if ((rc = make_map_nhwc(&tmY, y, d->B, d->Ho, d->Wo, spade ? d->spade_C : d->Cout, tw, th, tb)) != S2E_OK) return rc;
   FwdParams p;
   p.dbg = s2e_debug_get(3);
   p.tiles_w = ceil_div(d->Wo, tw);
@@ -412,9 +466,15 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.mask = (const bf16*)d->relu_mask;
   p.res = (const bf16*)d->residual;
   p.bias_n = d->bias_n > 0 ? d->bias_n : d->Cout;
+  p.sx = (const bf16*)d->spade_x;
+  p.spar = d->spade_par;
+  p.sC = d->spade_C;
+  p.sact = d->spade_act;
+  p.sup = d->spade_up;
   S2E_REQUIRE(!(p.mask && p.res), "tapconv_fwd: relu_mask and residual are mutually exclusive");
   S2E_REQUIRE(d->in_act == S2E_ACT_NONE && d->mask_slope == 0.f, "tapconv_fwd: in_act / mask_slope exist on the CUDA-core path only");
   S2E_REQUIRE(!(p.mask || p.res) || d->Cout % 64 == 0, "tapconv_fwd: relu_mask / residual need Cout %% 64 == 0 on the tcgen05 path");
+  S2E_REQUIRE(!spade || (p.tiles_w * p.tiles_h) % Cfg::MT == 0, "tapconv_fwd: fused SPADE: sub-tiles of one tile must share a sample");
   p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);
   p.bias = bias;
   p.scale = scale;

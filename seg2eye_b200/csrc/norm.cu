@@ -127,6 +127,21 @@ __device__ __forceinline__ uint8_t sign_bits8(const float* o) {
   return (uint8_t)m;
 }
 
+// constants of the fused gamma|beta-convolution epilogue (conv_tc.cu): par[b][0..3][c]
+__global__ void spade_params_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ style,
+                                    int B, int C, int per_sample, float* __restrict__ par) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const int so = per_sample ? b * C : 0;
+  const float rs = rstd[so + c];
+  float* o = par + (size_t)b * 4 * C + c;
+  o[0] = rs;
+  o[C] = -mean[so + c] * rs;
+  o[2 * C] = 1.f + style[(size_t)b * 2 * C + c];
+  o[3 * C] = style[(size_t)b * 2 * C + C + c];
+}
+
 // ---------------------------------------------------------------- SPADE+Style forward (elementwise, 8 B/elem)
 // grid = (pixel chunks, B).  A thread owns one 8-channel group: its per-channel constants (mean, rstd, style) are
 // loaded once into registers, then it streams pixels: 3 x 16-byte loads + 1 x 16-byte store per pixel, two pixels in
@@ -549,6 +564,14 @@ __global__ void sn_corr_apply_kernel(const float* __restrict__ coef, const float
     for (int b = 0; b < Bn; ++b) acc = fmaf(coef[b] * U[(size_t)b * Cout + co], V[(size_t)b * K + k], acc);
     dw[i] = -acc;
   }
+}
+
+int s2e_spade_params(const float* mean, const float* rstd, const float* style, int B, int C, int per_sample, float* par,
+                     void* stream) {
+  if (B * C == 0) return S2E_OK;
+  spade_params_kernel<<<ceil_div(B * C, 256), 256, 0, (cudaStream_t)stream>>>(mean, rstd, style, B, C, per_sample, par);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
 }
 
 int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const float* mean, const float* rstd, int B,

@@ -126,19 +126,21 @@ class SPADE(nn.Module):
         self.mlp_beta = Conv2d(nhidden, norm_nc, ks, padding=pw)
         self.norm_nc = norm_nc
 
-    def gamma_beta(self, segmap, h, w):
+    def _actv(self, segmap, h, w):
+        """ReLU(mlp_shared(nearest(segmap))) and whether its ReLU backward is left to the gamma|beta data gradient."""
         conv = self.mlp_shared[0]
         if 9 * conv.in_channels <= 62 and conv.cfg.kh == 3:
             # thin segmap: its 64-channel im2col (shared by every SPADE of this resolution within one generator
             # forward) turns mlp_shared into a K=64 GEMM on the tensor-core path, forward and weight gradient
             col = seg_im2col_cached(segmap, h, w)
-            actv = ops.SegConvFn.apply(col, conv.weight, conv.bias, L.ACT_RELU, True)
-            # the ReLU backward of actv is fused into the gamma|beta data-gradient epilogue (relu_in)
-            return ops.tap_conv(actv, self.mlp_gamma.cfg._replace(relu_in=True), (self.mlp_gamma.weight, self.mlp_beta.weight),
-                                (self.mlp_gamma.bias, self.mlp_beta.bias))
-        actv = conv.forward_nhwc(ops.seg_nearest(segmap, h, w))
-        return ops.tap_conv(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
-                            (self.mlp_gamma.bias, self.mlp_beta.bias))
+            return ops.SegConvFn.apply(col, conv.weight, conv.bias, L.ACT_RELU, True), True
+        return conv.forward_nhwc(ops.seg_nearest(segmap, h, w)), False
+
+    def gamma_beta(self, segmap, h, w):
+        actv, fused_relu = self._actv(segmap, h, w)
+        # (the ReLU backward of actv is fused into the gamma|beta data-gradient epilogue: relu_in)
+        cfg = self.mlp_gamma.cfg._replace(relu_in=True) if fused_relu else self.mlp_gamma.cfg
+        return ops.tap_conv(actv, cfg, (self.mlp_gamma.weight, self.mlp_beta.weight), (self.mlp_gamma.bias, self.mlp_beta.bias))
 
     def modulate(self, x, segmap, style, act, up=False, sink=None):
         """x NHWC bf16; style (B,2C) fp32 (s0|s1) ->  act(0.5*[norm(x)(1+gamma)+beta + x(1+s0)+s1]).
@@ -146,13 +148,17 @@ class SPADE(nn.Module):
         B, H, W, C = x.shape
         if up:
             H, W = 2 * H, 2 * W
-        gb = self.gamma_beta(segmap, H, W)
         pfn = self.param_free_norm
         cfg = ops.NormCfg(self.per_sample, act, self.training, 0.1, 1e-5)
-        if self.per_sample:
-            return ops.SpadeStyleFn.apply(x, gb, style, cfg, None, None, None, up, sink)
-        return ops.SpadeStyleFn.apply(x, gb, style, cfg, pfn.running_mean, pfn.running_var, pfn.num_batches_tracked,
-                                      up, sink)
+        bufs = (None, None, None) if self.per_sample else (pfn.running_mean, pfn.running_var, pfn.num_batches_tracked)
+        if not torch.is_grad_enabled() and ops.spade_conv_fused_ok(x, up, self.mlp_gamma.in_channels):
+            # no autograd graph wanted (D step's generator pass, inference): gamma|beta are consumed in the epilogue of
+            # their own convolution and never written
+            actv, _ = self._actv(segmap, H, W)
+            return ops.spade_conv_fused(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
+                                        (self.mlp_gamma.bias, self.mlp_beta.bias), x, style, cfg, *bufs, up)
+        gb = self.gamma_beta(segmap, H, W)
+        return ops.SpadeStyleFn.apply(x, gb, style, cfg, *bufs, up, sink)
 
     def forward(self, x, segmap):
         # plain SPADE: out = norm(x)(1+gamma)+beta = 2*0.5*[...] with the style term cancelled (s0=-1, s1=0)

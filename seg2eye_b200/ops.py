@@ -483,6 +483,74 @@ def prepare_spectral(convs, training, n_calls=1, keep_uv=False):
 NormCfg = namedtuple("NormCfg", "per_sample act training momentum eps")
 
 
+def spade_statistics(x, cfg, running_mean, running_var, nbt, up):
+    """mean / rstd of the param-free norm of SPADE (normalization.py:73-75,91): batch statistics in training mode (also
+    advancing BatchNorm's running buffers exactly like torch does) or for InstanceNorm, running statistics in eval mode.
+    up: x is the half-resolution source of the real (nearest-2x up-sampled) input -- same mean and variance."""
+    B, Hx, Wx, Cc = x.shape
+    H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
+    st = L.stream()
+    G = B if cfg.per_sample else 1
+    batch_stats = cfg.per_sample or cfg.training or running_mean is None
+    if not batch_stats:   # BatchNorm2d in eval mode
+        return running_mean.detach().clone().view(1, Cc), torch.rsqrt(running_var.detach() + cfg.eps).view(1, Cc), False
+    acc = torch.empty(G * 2 * Cc, dtype=torch.float64, device=x.device)
+    mean = torch.empty(G, Cc, dtype=F32, device=x.device)
+    rstd = torch.empty(G, Cc, dtype=F32, device=x.device)
+    upd = (not cfg.per_sample) and cfg.training and running_mean is not None
+    count = float(H * W if cfg.per_sample else B * H * W)     # elements BatchNorm sees (unbiased running_var)
+    count_stats = count / 4 if up else count                  # elements actually summed (the 4x smaller source)
+    L.call("s2e_norm_stats", L.ptr(x), B, Hx * Wx, Cc, int(cfg.per_sample), L.ptr(acc), st)
+    L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count_stats, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
+           L.ptr(running_mean) if upd else None, L.ptr(running_var) if upd else None, cfg.momentum,
+           L.ptr(nbt) if upd else None, st)
+    return mean, rstd, True
+
+
+def spade_conv_fused_ok(x, up, n_hidden):
+    """Shapes the fused gamma|beta-convolution + modulation kernel takes: C in {64, 128} (gamma | beta = one N tile) and
+    maps large enough that a 128-pixel tile never spans two samples."""
+    B, Hx, Wx, Cc = x.shape
+    H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
+    if Cc not in (64, 128) or n_hidden % 64 or _state["force_impl"] == L.IMPL_SIMT:
+        return False
+    tw = min(W, 128)
+    while W % tw or 128 % tw:       # tile = tw x (128 / tw) pixels inside one image
+        tw -= 1
+    th = 128 // tw
+    tiles = (W // tw) * ((H + th - 1) // th)
+    return H % th == 0 and tiles % 2 == 0
+
+
+def spade_conv_fused(actv, conv_cfg, weights, biases, x, style, cfg, running_mean, running_var, nbt, up):
+    """Inference / no-grad SPADE+Style block: act(0.5*[norm(x)(1+gamma)+beta + x(1+s0)+s1]) with gamma|beta = conv(actv)
+    formed in the tcgen05 accumulator and consumed in the epilogue -- gamma|beta never reach HBM (saves 8 of the 12 bytes
+    per element that the convolution output + the modulation kernel move).  No autograd graph is built."""
+    assert not torch.is_grad_enabled()
+    x, actv, style = _c(x), _c(actv), _c(style)
+    B, Hx, Wx, Cc = x.shape
+    H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
+    assert actv.shape[:3] == (B, H, W) and style.shape == (B, 2 * Cc)
+    mean, rstd, _ = spade_statistics(x, cfg, running_mean, running_var, nbt, up)
+    st = L.stream()
+    par = torch.empty(B, 4, Cc, dtype=F32, device=x.device)
+    L.call("s2e_spade_params", L.ptr(mean), L.ptr(rstd), L.ptr(style), B, Cc, int(cfg.per_sample), L.ptr(par), st)
+    wp = packed_weights(weights, conv_cfg, False)
+    bias = torch.cat([b.detach() for b in biases])
+    taps = conv_taps(conv_cfg)
+    tw = min(W, 128)
+    while W % tw or 128 % tw:
+        tw -= 1
+    d = _desc(B, H, W, actv.shape[3], H, W, 2 * Cc, taps, L.ACT_NONE)
+    d.tile_w, d.tile_h, d.tile_b = tw, 128 // tw, 1
+    d.spade_x, d.spade_par, d.spade_C, d.spade_act, d.spade_up = L.ptr(x), L.ptr(par), Cc, cfg.act, int(up)
+    out = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
+    flops = 2.0 * B * H * W * 2 * Cc * weights[0].shape[1] * conv_cfg.kh * conv_cfg.kw
+    _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(actv), L.ptr(wp), L.ptr(bias), None, L.ptr(out), L.IMPL_TC, st,
+                tag="fwd+spade B%d %dx%d Cin%d Cout%d T%d" % (B, H, W, actv.shape[3], 2 * Cc, len(taps)))
+    return out
+
+
 class GradSink:
     """Shared gradient buffer of the SpadeStyleFn calls that consume the SAME input x (norm_0 and norm_s of a ResNet
     block with a learned shortcut): the first backward to run allocates the buffer, the others add into it in place
@@ -512,22 +580,7 @@ class SpadeStyleFn(torch.autograd.Function):
         H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
         assert gb.shape == (B, H, W, 2 * Cc) and style.shape == (B, 2 * Cc) and style.dtype == F32
         st = L.stream()
-        G = B if cfg.per_sample else 1
-        batch_stats = cfg.per_sample or cfg.training or running_mean is None
-        if batch_stats:
-            acc = torch.empty(G * 2 * Cc, dtype=torch.float64, device=x.device)
-            mean = torch.empty(G, Cc, dtype=F32, device=x.device)
-            rstd = torch.empty(G, Cc, dtype=F32, device=x.device)
-            upd = (not cfg.per_sample) and cfg.training and running_mean is not None
-            count = float(H * W if cfg.per_sample else B * H * W)     # elements BatchNorm sees (unbiased running_var)
-            count_stats = count / 4 if up else count                  # elements actually summed (the 4x smaller source)
-            L.call("s2e_norm_stats", L.ptr(x), B, Hx * Wx, Cc, int(cfg.per_sample), L.ptr(acc), st)
-            L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count_stats, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
-                   L.ptr(running_mean) if upd else None, L.ptr(running_var) if upd else None, cfg.momentum,
-                   L.ptr(nbt) if upd else None, st)
-        else:  # BatchNorm2d in eval mode: running statistics
-            mean = running_mean.detach().clone().view(1, Cc)
-            rstd = torch.rsqrt(running_var.detach() + cfg.eps).view(1, Cc)
+        mean, rstd, batch_stats = spade_statistics(x, cfg, running_mean, running_var, nbt, up)
         out = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
         # backward needs only the sign of `out` (LeakyReLU mask): one bit per element, written by the forward kernel
         amask = None

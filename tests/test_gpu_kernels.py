@@ -721,3 +721,48 @@ def test_conv_img_with_fused_leaky_relu_input(S):
     x2 = bf(torch.randn(B, 16, H, W, generator=g))
     ref2 = F.conv2d(F.leaky_relu(x2, 0.2), bf(conv2.weight.detach().cpu()), conv2.bias.detach().cpu(), padding=1)
     assert rel(nchw(conv2.forward_nhwc(nhwc(x2), in_act=L.ACT_LRELU)), ref2) < TOL_ACT
+
+
+@pytest.mark.parametrize("C,up,act,per_sample", [(64, False, 1, False), (128, True, 1, False), (128, False, 0, True), (64, True, 0, False)])
+def test_spade_modulation_fused_into_gamma_beta_conv(S, C, up, act, per_sample):
+    """No-grad SPADE+Style block with gamma|beta consumed in the epilogue of their own convolution
+    (ops.spade_conv_fused) == convolution followed by the modulation kernel == the fp32 statement of
+    normalization.py:91-105,161-192; BatchNorm running buffers advance identically."""
+    L, ops = S
+    g = torch.Generator().manual_seed(41)
+    B, H, W = 3, 16, 32
+    hx, wx = (H // 2, W // 2) if up else (H, W)
+    x = bf(torch.randn(B, C, hx, wx, generator=g) * 1.3 + 0.2)
+    actv = bf(torch.relu(torch.randn(B, 128, H, W, generator=g)))
+    wg = bf(torch.randn(C, 128, 3, 3, generator=g) / 34.0)
+    wb = bf(torch.randn(C, 128, 3, 3, generator=g) / 34.0)
+    bg, bb = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    style = torch.randn(B, 2 * C, generator=g) * 0.5
+    # fp32 reference
+    xu = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
+    gam, bet = F.conv2d(actv, wg, bg, padding=1), F.conv2d(actv, wb, bb, padding=1)
+    rm, rv = torch.zeros(C), torch.ones(C)
+    xn = F.instance_norm(xu, eps=1e-5) if per_sample else F.batch_norm(xu, rm, rv, training=True, momentum=0.1, eps=1e-5)
+    ref = 0.5 * (xn * (1 + gam) + bet + xu * (1 + style[:, :C, None, None]) + style[:, C:, None, None])
+    if act:
+        ref = F.leaky_relu(ref, 0.2)
+    cfg = ops.NormCfg(per_sample, act, True, 0.1, 1e-5)
+    ccfg = ops.ConvCfg(3, 3, 1, 1, L.ACT_NONE)
+    ws, bs = (wg.cuda(), wb.cuda()), (bg.cuda(), bb.cuda())
+    outs = []
+    with torch.no_grad():
+        assert ops.spade_conv_fused_ok(nhwc(x), up, 128)
+        for fused in (True, False):
+            rmc, rvc, nbt = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.tensor(0, device="cuda")
+            bufs = (None, None, None) if per_sample else (rmc, rvc, nbt)
+            if fused:
+                o = ops.spade_conv_fused(nhwc(actv), ccfg, ws, bs, nhwc(x), style.cuda(), cfg, *bufs, up)
+            else:
+                gb = ops.tap_conv(nhwc(actv), ccfg, ws, bs)
+                o = ops.SpadeStyleFn.apply(nhwc(x), gb, style.cuda(), cfg, *bufs, up)
+            outs.append(o)
+            if not per_sample:
+                assert rel(rmc, rm) < 1e-4 and rel(rvc, rv) < 1e-4 and int(nbt) == 1
+    assert outs[0].shape == (B, H, W, C)
+    assert rel(nchw(outs[0]), ref) < 5e-3 and rel(nchw(outs[1]), ref) < TOL_ACT
+    assert rel(outs[0], outs[1]) < TOL_ACT
