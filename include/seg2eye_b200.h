@@ -105,6 +105,9 @@ typedef struct {
   const void* spade_x;
   const float* spade_par;
   int spade_C, spade_act, spade_up;
+  void* spade_gamma_out;         /* training (nullable): gamma alone, bf16 [B][Ho][Wo][spade_C] -- all that backward needs
+                                    of gamma|beta (s2e_spade_style_bwd with gb_stride = spade_C) */
+  void* spade_mask_out;          /* training (nullable): the activation bit mask of s2e_spade_style_fwd */
 } s2e_conv_t;
 
 int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
@@ -201,6 +204,7 @@ int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const
 int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act,
                         double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, int up_w,
+                        int gb_stride /* channels per pixel of `gb`: 0 = 2C (gamma|beta); C when only gamma was kept */,
                         void* stream);
 
 /* InstanceNorm2d(affine=False)+optional LeakyReLU on NHWC bf16 (normalization.py:41; discriminator.py:88-92;

@@ -23,7 +23,7 @@ class ConvDesc(C.Structure):
                 ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p),
                 ("residual", C.c_void_p), ("bias_n", C.c_int), ("in_act", C.c_int), ("mask_slope", C.c_float),
                 ("spade_x", C.c_void_p), ("spade_par", C.c_void_p), ("spade_C", C.c_int), ("spade_act", C.c_int),
-                ("spade_up", C.c_int)]
+                ("spade_up", C.c_int), ("spade_gamma_out", C.c_void_p), ("spade_mask_out", C.c_void_p)]
 
 
 class SnJob(C.Structure):
@@ -64,7 +64,7 @@ _SIGS = {
     "s2e_norm_finalize": [_P, _I, _I, _D, _D, _F, _P, _P, _P, _P, _F, _P, _P],
     "s2e_spade_params": [_P, _P, _P, _I, _I, _I, _P, _P],
     "s2e_spade_style_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
-    "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P],
+    "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _P],
     "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P, _P],
     "s2e_instnorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "s2e_upsample2x_fwd": [_P, _I, _I, _I, _I, _P, _P],

@@ -93,6 +93,8 @@ struct FwdParams {
   const bf16* sx;     // block input x, [B][Ho][Wo][sC] or, with sup != 0, its half-resolution source [B][Ho/2][Wo/2][sC]
   const float* spar;  // [B][4][sC]: ka = rstd, kb = -mean*rstd, kc = 1 + s0, s1
   int sC, sact, sup;
+  int sgamma;         // training: gamma (sC channels, bf16) is written through tmG as well -- backward needs it
+  uint8_t* smask;     // training: one bit per output element, set where the output is > 0 ([B*Ho*Wo][sC/8] bytes)
   uint32_t a_box_bytes;
   const float* bias;
   const float* scale;
@@ -139,7 +141,7 @@ __device__ __forceinline__ float act_t(float v) {
 template <int BN, int ACT>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmY, const FwdParams p) {
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const FwdParams p) {
   using Cfg = FwdCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -170,6 +172,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::prefetch_tmap(&tmY);
+    if (p.sgamma) ptx::prefetch_tmap(&tmG);
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -287,10 +290,12 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const bf16* side = p.mask ? p.mask : p.res;   // per-pixel side input shaped like the output (mask or residual)
         const bf16* mrow = nullptr;
         const float* par = nullptr;
+        uint8_t* mask_row = nullptr;   // fused SPADE, training: this pixel's activation-mask bytes
         if (side || p.sx) {
           const int tw = row % p.TW, r2 = row / p.TW;
           const int th = r2 % p.TH, tb = r2 / p.TH;
           if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo) {
+            if (p.smask) mask_row = p.smask + (((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * (size_t)(p.sC >> 3);
             if (side) {
               mrow = side + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
             } else if (p.sup) {   // x lives at half resolution (nearest 2x up-sampling folded in)
@@ -318,7 +323,10 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int i = 0; i < 2; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + sub * 16) + i);
           }
           // the TMA store that last read this staging buffer must have finished reading it
-          if (store_thread) ptx::tma_store_wait_read<1>();
+          if (store_thread) {
+            if (p.sgamma) ptx::tma_store_wait_read<0>();   // this chunk fills BOTH staging buffers (output and gamma)
+            else ptx::tma_store_wait_read<1>();
+          }
           ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
           ptx::tmem_ld_wait();
           uint8_t* ob = out_buf + buf * OUT_BUF_BYTES + row * 128;
@@ -357,14 +365,22 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               const float kb[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
               const float kc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
               const uint32_t xw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+              if (p.sgamma) {   // gamma itself goes to the other staging buffer (rounded to bf16 exactly like backward reads it)
+                uint8_t* og = out_buf + (buf ^ 1) * OUT_BUF_BYTES + row * 128;
+                *reinterpret_cast<uint4*>(og + (((sub * 2 + i) ^ (row & 7)) << 4)) =
+                    make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
+              }
+              uint32_t bits = 0;
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float xv = __uint_as_float((e & 1) ? (xw[e >> 1] & 0xffff0000u) : (xw[e >> 1] << 16));
                 const float beta = fmaf(__uint_as_float(rb[8 * i + e]), scale, betab[e]);   // includes the style offset s1
                 float o = 0.5f * (fmaf(fmaf(xv, ka[e], kb[e]), 1.f + v[e], beta) + xv * kc[e]);
                 if (p.sact == S2E_ACT_LRELU) o = fmaxf(o, 0.2f * o);
+                bits |= (o > 0.f ? 1u : 0u) << e;
                 v[e] = o;
               }
+              if (mask_row) mask_row[(ch * 64 + sub * 16 + 8 * i) >> 3] = (uint8_t)bits;
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) pk[e] = pack2_bf16(v[2 * e], v[2 * e + 1]);
@@ -384,9 +400,10 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           ptx::named_bar_sync(2, FWD_EPI_THREADS);
           if (store_thread && !(p.dbg & 1)) {
             ptx::tma_store_4d(&tmY, out_buf + buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
+            if (p.sgamma) ptx::tma_store_4d(&tmG, out_buf + (buf ^ 1) * OUT_BUF_BYTES, nbase, w0, h0, b0);
             ptx::tma_store_commit();
           }
-          buf ^= 1;
+          if (!p.sgamma) buf ^= 1;
         }
       }
       ptx::tc_fence_before();
@@ -433,7 +450,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   int tw = d->tile_w, th = d->tile_h, tb = d->tile_b;
   if (tw <= 0 || th <= 0 || tb <= 0) choose_fwd_tile(d->B, d->Ho, d->Wo, &tw, &th, &tb);
   S2E_REQUIRE(tw * th * tb <= BM && tw <= 256 && th <= 256 && tb <= 256, "bad forward tile %dx%dx%d", tw, th, tb);
-  CUtensorMap tmA, tmB, tmY;
+  CUtensorMap tmA, tmB, tmY, tmG;
   int rc;
   if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
   if ((rc = make_map_w(&tmB, wp, d->ntaps, d->Cout, d->Cin, BN)) != S2E_OK) return rc;
@@ -446,6 +463,10 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
     S2E_REQUIRE(!d->spade_up || (d->Ho % 2 == 0 && d->Wo % 2 == 0), "tapconv_fwd: fused SPADE with up-sampling needs even H, W");
   }
   if ((rc = make_map_nhwc(&tmY, y, d->B, d->Ho, d->Wo, spade ? d->spade_C : d->Cout, tw, th, tb)) != S2E_OK) return rc;
+  tmG = tmY;
+  if (spade && d->spade_gamma_out &&
+      (rc = make_map_nhwc(&tmG, d->spade_gamma_out, d->B, d->Ho, d->Wo, d->spade_C, tw, th, tb)) != S2E_OK)
+    return rc;
   FwdParams p;
   p.dbg = s2e_debug_get(3);
   p.tiles_w = ceil_div(d->Wo, tw);
@@ -471,6 +492,8 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.sC = d->spade_C;
   p.sact = d->spade_act;
   p.sup = d->spade_up;
+  p.sgamma = (spade && d->spade_gamma_out) ? 1 : 0;
+  p.smask = spade ? (uint8_t*)d->spade_mask_out : nullptr;
   S2E_REQUIRE(!(p.mask && p.res), "tapconv_fwd: relu_mask and residual are mutually exclusive");
   S2E_REQUIRE(d->in_act == S2E_ACT_NONE && d->mask_slope == 0.f, "tapconv_fwd: in_act / mask_slope exist on the CUDA-core path only");
   S2E_REQUIRE(!(p.mask || p.res) || d->Cout % 64 == 0, "tapconv_fwd: relu_mask / residual need Cout %% 64 == 0 on the tcgen05 path");
@@ -489,7 +512,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
     attr_set = true;
   }
   int grid = p.num_tiles < s2e_num_sms() ? p.num_tiles : s2e_num_sms();
-  tapconv_fwd_kernel<BN, ACT><<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, p);
+  tapconv_fwd_kernel<BN, ACT><<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmG, p);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

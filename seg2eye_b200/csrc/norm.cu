@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
                                                                     const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     int HW, int C, int per_sample, int act, double* __restrict__ racc,
-                                                                    int up_w) {
+                                                                    int up_w, int gstride) {
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
     float df[8], xf[8], gf[8];
     unpack8(ld_stream8(dout + p * C + c), df);
     unpack8(ld_stream8(x + x_pixel(b, p - (long long)b * HW, HW, up_w) * C + c), xf);
-    unpack8(ld_stream8(gb + p * 2 * C + c), gf);
+    unpack8(ld_stream8(gb + p * gstride + c), gf);
     const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * (C >> 3) + (c >> 3)] : 0xffu;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
                                                                    const float* __restrict__ style, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ m12,
                                                                    int HW, int C, int per_sample, int act,
-                                                                   bf16* __restrict__ dx, int dx_acc, bf16* __restrict__ dgb, int up_w) {
+                                                                   bf16* __restrict__ dx, int dx_acc, bf16* __restrict__ dgb, int up_w,
+                                                                   int gstride) {
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long q0 = (long long)blockIdx.x * chunk;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
       const long long pA = base + q, pB = base + q + lanes;
       const bf16x8 da = ld_stream8(dout + pA * C + c), db = ld_stream8(dout + pB * C + c);
       const bf16x8 xa = ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), xb = ld_stream8(x + x_pixel(b, q + lanes, HW, up_w) * C + c);
-      const bf16x8 ga = ld_stream8(gb + pA * 2 * C + c), gb2 = ld_stream8(gb + pB * 2 * C + c);
+      const bf16x8 ga = ld_stream8(gb + pA * gstride + c), gb2 = ld_stream8(gb + pB * gstride + c);
       const uint32_t ma = act != S2E_ACT_NONE ? (uint32_t)amask[pA * cg + mcol] : 0xffu;
       const uint32_t mb = act != S2E_ACT_NONE ? (uint32_t)amask[pB * cg + mcol] : 0xffu;
       finish(pA, da, xa, ga, ma);
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
     for (; q < q1; q += lanes) {
       const long long p = base + q;
       const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * cg + mcol] : 0xffu;
-      finish(p, ld_stream8(dout + p * C + c), ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), ld_stream8(gb + p * 2 * C + c), mbits);
+      finish(p, ld_stream8(dout + p * C + c), ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), ld_stream8(gb + p * gstride + c), mbits);
     }
   }
 }
@@ -588,17 +589,20 @@ int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const
 
 int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act, double* racc,
-                        void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, int up_w, void* stream) {
+                        void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, int up_w, int gb_stride,
+                        void* stream) {
   S2E_REQUIRE(C % 8 == 0, "spade_style_bwd needs C %% 8 == 0 (C=%d)", C);
   S2E_REQUIRE(up_w == 0 || (up_w % 2 == 0 && HW % up_w == 0 && (HW / up_w) % 2 == 0), "spade_style_bwd: bad up-sampled width %d", up_w);
   cudaStream_t st = (cudaStream_t)stream;
   // racc: double [B][5][C] followed by float m12 [B][2][C]
   S2E_REQUIRE(act == S2E_ACT_NONE || act_mask, "spade_style_bwd: the activation mask written by the forward pass is required");
+  const int gstride = gb_stride > 0 ? gb_stride : 2 * C;
+  S2E_REQUIRE(gstride >= C && gstride % 8 == 0, "spade_style_bwd: bad gamma stride %d", gstride);
   S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 5 * C, st));
   float* m12 = (float*)(racc + (size_t)B * 5 * C);
   dim3 grid(red_chunks(HW, B), B);
   spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x,
-                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc, up_w);
+                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc, up_w, gstride);
   S2E_LAUNCH_CHECK();
   const double count = per_sample ? (double)HW : (double)B * HW;
   spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, m12, dstyle, chsum);
@@ -606,7 +610,7 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
   dim3 grid2(ew_chunks(HW, B, C), B);
   spade_style_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, style,
                                                      mean, rstd, m12, HW, C, per_sample, act, (bf16*)dx, dx_accumulate,
-                                                     (bf16*)dgb, up_w);
+                                                     (bf16*)dgb, up_w, gstride);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

@@ -157,6 +157,12 @@ class SPADE(nn.Module):
             actv, _ = self._actv(segmap, H, W)
             return ops.spade_conv_fused(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
                                         (self.mlp_gamma.bias, self.mlp_beta.bias), x, style, cfg, *bufs, up)
+        if self.training and ops._state["fuse_spade_training"] and ops.spade_conv_fused_ok(x, up, self.mlp_gamma.in_channels):
+            # training: same fusion, the kernel additionally keeps gamma and the activation mask for backward
+            actv, fused_relu = self._actv(segmap, H, W)
+            ccfg = self.mlp_gamma.cfg._replace(relu_in=True) if fused_relu else self.mlp_gamma.cfg
+            return ops.SpadeConvFn.apply(actv, x, style, self.mlp_gamma.weight, self.mlp_beta.weight, self.mlp_gamma.bias,
+                                         self.mlp_beta.bias, ccfg, cfg, *bufs, up, sink)
         gb = self.gamma_beta(segmap, H, W)
         return ops.SpadeStyleFn.apply(x, gb, style, cfg, *bufs, up, sink)
 

@@ -23,7 +23,11 @@ ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad cout_pad i
 # cout_pad: run a layer with very few output channels (the 1-channel PatchGAN head, K = 8192) on the tensor-core kernels
 #           with its output channels zero-padded to cout_pad; the caller sees the first Cout channels only
 
-_state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False}
+_state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False,
+          # SpadeConvFn (training-mode gamma|beta conv + modulation in one kernel) is correct and tested but, measured on
+          # B200 (round 1), 0.3 ms slower per full-resolution launch than it saves: writing gamma next to the output
+          # costs the epilogue its double buffering.  Inference / no-grad forwards always use the fused kernel.
+          "fuse_spade_training": False}
 
 
 def bump_weights_epoch():
@@ -514,9 +518,7 @@ def spade_conv_fused_ok(x, up, n_hidden):
     H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
     if Cc not in (64, 128) or n_hidden % 64 or _state["force_impl"] == L.IMPL_SIMT:
         return False
-    tw = min(W, 128)
-    while W % tw or 128 % tw:       # tile = tw x (128 / tw) pixels inside one image
-        tw -= 1
+    tw = _fused_tile_w(W)           # tile = tw x (128 / tw) pixels inside one image
     th = 128 // tw
     tiles = (W // tw) * ((H + th - 1) // th)
     return H % th == 0 and tiles % 2 == 0
@@ -538,9 +540,7 @@ def spade_conv_fused(actv, conv_cfg, weights, biases, x, style, cfg, running_mea
     wp = packed_weights(weights, conv_cfg, False)
     bias = torch.cat([b.detach() for b in biases])
     taps = conv_taps(conv_cfg)
-    tw = min(W, 128)
-    while W % tw or 128 % tw:
-        tw -= 1
+    tw = _fused_tile_w(W)
     d = _desc(B, H, W, actv.shape[3], H, W, 2 * Cc, taps, L.ACT_NONE)
     d.tile_w, d.tile_h, d.tile_b = tw, 128 // tw, 1
     d.spade_x, d.spade_par, d.spade_C, d.spade_act, d.spade_up = L.ptr(x), L.ptr(par), Cc, cfg.act, int(up)
@@ -618,7 +618,7 @@ class SpadeStyleFn(torch.autograd.Function):
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
         L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
                L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
-               L.ptr(dstyle), L.ptr(chsum), W if up else 0, st)
+               L.ptr(dstyle), L.ptr(chsum), W if up else 0, 0, st)
         # per-channel sums of the two gradients, for the bias gradients of the convolutions that receive them as dy
         # (TapConvFn.backward picks the attribute up when the tensor reaches it unmodified; otherwise it sums itself)
         dgb._s2e_chsum = chsum[:2 * Cc]
@@ -632,6 +632,127 @@ class SpadeStyleFn(torch.autograd.Function):
                 if sink is None:
                     gx._s2e_chsum = chsum[2 * Cc:]
         return gx, dgb, dstyle, None, None, None, None, None, None
+
+
+def _fused_tile_w(W):
+    tw = min(W, 128)
+    while W % tw or 128 % tw:
+        tw -= 1
+    return tw
+
+
+class SpadeConvFn(torch.autograd.Function):
+    """Training-mode SPADE+Style block with the gamma|beta convolution and the modulation in ONE tcgen05 kernel
+    (normalization.py:85-105,161-192):
+
+        gamma|beta = conv3x3(actv, W_gamma|W_beta) + b      (accumulator only)
+        out        = act(0.5 * [ norm(x) * (1 + gamma) + beta + x * (1 + s0) + s1 ])
+
+    The kernel writes `out`, gamma alone (backward needs it; beta is never needed again) and the 1-bit activation mask:
+    6 bytes per element instead of the 12 that the convolution output plus the modulation kernel move.  Backward = the
+    SPADE+Style backward kernels (dx, dgamma|dbeta, dstyle, bias sums) followed by the convolution's data / weight
+    gradients.  Shapes: see spade_conv_fused_ok.  `up` / `sink` as in SpadeStyleFn."""
+
+    @staticmethod
+    def forward(ctx, actv, x, style, wg, wb, bg, bb, conv_cfg, cfg, running_mean, running_var, nbt, up, sink):
+        ctx.sink, ctx.up = sink, up
+        if sink is not None:
+            sink.users += 1
+        actv, x, style = _c(actv), _c(x), _c(style)
+        B, Hx, Wx, Cc = x.shape
+        H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
+        Ca = actv.shape[3]
+        assert actv.shape == (B, H, W, Ca) and style.shape == (B, 2 * Cc) and cfg.training
+        mean, rstd, _ = spade_statistics(x, cfg, running_mean, running_var, nbt, up)
+        st = L.stream()
+        par = torch.empty(B, 4, Cc, dtype=F32, device=x.device)
+        L.call("s2e_spade_params", L.ptr(mean), L.ptr(rstd), L.ptr(style), B, Cc, int(cfg.per_sample), L.ptr(par), st)
+        weights = (wg, wb)
+        wp = packed_weights(weights, conv_cfg, False)
+        bias = torch.cat([bg.detach(), bb.detach()])
+        taps = conv_taps(conv_cfg)
+        out = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
+        gamma = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
+        amask = torch.empty(B * H * W * (Cc // 8), dtype=torch.uint8, device=x.device) if cfg.act != L.ACT_NONE else None
+        d = _desc(B, H, W, Ca, H, W, 2 * Cc, taps, L.ACT_NONE)
+        tw = _fused_tile_w(W)
+        d.tile_w, d.tile_h, d.tile_b = tw, 128 // tw, 1
+        d.spade_x, d.spade_par, d.spade_C, d.spade_act, d.spade_up = L.ptr(x), L.ptr(par), Cc, cfg.act, int(up)
+        d.spade_gamma_out, d.spade_mask_out = L.ptr(gamma), L.ptr(amask)
+        flops = 2.0 * B * H * W * 2 * Cc * Ca * conv_cfg.kh * conv_cfg.kw
+        _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(actv), L.ptr(wp), L.ptr(bias), None, L.ptr(out), L.IMPL_TC, st,
+                    tag="fwd+spade B%d %dx%d Cin%d Cout%d T%d" % (B, H, W, Ca, 2 * Cc, len(taps)))
+        ctx.cfg, ctx.conv_cfg, ctx.hw, ctx.flops = cfg, conv_cfg, (H, W), flops
+        ctx.skip_wgrad = _state["skip_wgrad"]
+        ctx.weights = weights
+        ctx.save_for_backward(actv, x, gamma, style, mean, rstd, amask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg, ccfg, up, sink = ctx.cfg, ctx.conv_cfg, ctx.up, ctx.sink
+        actv, x, gamma, style, mean, rstd, amask = ctx.saved_tensors
+        wg, wb = ctx.weights
+        dout = _c(dout)
+        B, Cc = x.shape[0], x.shape[3]
+        H, W = ctx.hw
+        Ca = actv.shape[3]
+        st = L.stream()
+        # ---- SPADE+Style backward (gamma kept alone: stride Cc)
+        racc = torch.empty(B * 5 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
+        accumulate = sink is not None and sink.buf is not None
+        dx = sink.buf if accumulate else torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
+        last = True
+        if sink is not None:
+            sink.seen += 1
+            last = sink.seen == sink.users
+            sink.buf = None if last else dx
+            if last:
+                sink.seen = 0
+        dgb = torch.empty(B, H, W, 2 * Cc, dtype=BF16, device=x.device)
+        dstyle = torch.empty_like(style)
+        chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
+        L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gamma), L.ptr(style), L.ptr(mean),
+               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
+               L.ptr(dstyle), L.ptr(chsum), W if up else 0, Cc, st)
+        gx = None
+        if last and ctx.needs_input_grad[1]:
+            if up:
+                gx = torch.empty_like(x)
+                L.call("s2e_upsample2x_bwd", L.ptr(dx), B, H // 2, W // 2, Cc, L.ptr(gx), st)
+            else:
+                gx = dx
+                if sink is None:
+                    gx._s2e_chsum = chsum[2 * Cc:]   # bias gradient of the convolution that produced x (see SpadeStyleFn)
+        # ---- gamma|beta convolution backward
+        taps = conv_taps(ccfg)
+        dactv = None
+        if ctx.needs_input_grad[0]:
+            wpt = packed_weights((wg, wb), ccfg, True)
+            dd = _desc(B, H, W, 2 * Cc, H, W, Ca, taps, L.ACT_NONE, negate=True)
+            if ccfg.relu_in:
+                dd.relu_mask = L.ptr(actv)   # actv = relu(.) > 0 exactly where the ReLU passed gradient
+            dactv = torch.empty_like(actv)
+            _timed_call("tc", ctx.flops, "s2e_tapconv_fwd", dd, L.ptr(dgb), L.ptr(wpt), None, None, L.ptr(dactv), L.IMPL_TC, st,
+                        tag="dgrad B%d %dx%d Cin%d Cout%d T%d" % (B, H, W, 2 * Cc, Ca, len(taps)))
+        gwg = gwb = gbg = gbb = None
+        if not ctx.skip_wgrad:
+            if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+                dwp = torch.zeros(len(taps) * 2 * Cc * Ca, dtype=F32, device=x.device)
+                d = _desc(B, H, W, Ca, H, W, 2 * Cc, taps, L.ACT_NONE)
+                _timed_call("tc", ctx.flops, "s2e_tapconv_wgrad", d, L.ptr(actv), L.ptr(dgb), L.ptr(dwp), L.IMPL_TC, st,
+                            tag="wgrad B%d %dx%d Cin%d Cout%d T%d" % (B, H, W, Ca, 2 * Cc, len(taps)))
+                outs = []
+                for i, w in enumerate((wg, wb)):
+                    g = torch.empty_like(w)
+                    L.call("s2e_unpack_wgrad", L.ptr(dwp), Cc, Ca, ccfg.kh, ccfg.kw, 1, ccfg.pad, 2 * Cc, i * Cc, 0,
+                           L.ptr(w.detach()), None, None, None, None, L.ptr(g), 0, st)
+                    outs.append(g)
+                gwg, gwb = outs
+            if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
+                gbg, gbb = chsum[:Cc].clone(), chsum[Cc:2 * Cc].clone()   # sum dgamma, sum dbeta: free from the reduce pass
+                _state["chsum_hits"] = _state.get("chsum_hits", 0) + 1
+        return dactv, gx, dstyle, gwg, gwb, gbg, gbb, None, None, None, None, None, None, None
 
 
 class InstNormFn(torch.autograd.Function):

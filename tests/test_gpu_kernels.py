@@ -766,3 +766,44 @@ def test_spade_modulation_fused_into_gamma_beta_conv(S, C, up, act, per_sample):
     assert outs[0].shape == (B, H, W, C)
     assert rel(nchw(outs[0]), ref) < 5e-3 and rel(nchw(outs[1]), ref) < TOL_ACT
     assert rel(outs[0], outs[1]) < TOL_ACT
+
+
+@pytest.mark.parametrize("C,up,act", [(64, False, 1), (128, True, 1), (128, False, 0)])
+def test_spade_conv_fused_training_forward_backward(S, C, up, act):
+    """SpadeConvFn (gamma|beta convolution + modulation in one kernel, gamma and the activation mask kept for backward)
+    against fp32 autograd through conv2d + batch_norm + the modulation formula: output, running buffers and the
+    gradients w.r.t. actv, x, style, both weights and both biases."""
+    L, ops = S
+    g = torch.Generator().manual_seed(43)
+    B, H, W = 2, 16, 32
+    hx, wx = (H // 2, W // 2) if up else (H, W)
+    x = bf(torch.randn(B, C, hx, wx, generator=g) * 1.3 + 0.2)
+    actv = bf(torch.relu(torch.randn(B, 128, H, W, generator=g)))
+    wg = bf(torch.randn(C, 128, 3, 3, generator=g) / 34.0)
+    wb = bf(torch.randn(C, 128, 3, 3, generator=g) / 34.0)
+    bg, bb = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    style = torch.randn(B, 2 * C, generator=g) * 0.5
+    dout = bf(torch.randn(B, C, H, W, generator=g))
+    ref_in = [t.clone().requires_grad_() for t in (actv, x, style, wg, wb, bg, bb)]
+    ar, xr, sr, wgr, wbr, bgr, bbr = ref_in
+    xu = F.interpolate(xr, scale_factor=2, mode="nearest") if up else xr
+    gam, bet = F.conv2d(ar, wgr, bgr, padding=1), F.conv2d(ar, wbr, bbr, padding=1)
+    rm, rv = torch.zeros(C), torch.ones(C)
+    xn = F.batch_norm(xu, rm, rv, training=True, momentum=0.1, eps=1e-5)
+    ref = 0.5 * (xn * (1 + gam) + bet + xu * (1 + sr[:, :C, None, None]) + sr[:, C:, None, None])
+    if act:
+        ref = F.leaky_relu(ref, 0.2)
+    ref.backward(dout)
+    ac, xc = nhwc(actv).requires_grad_(), nhwc(x).requires_grad_()
+    sc = style.cuda().requires_grad_()
+    wgc, wbc, bgc, bbc = [t.cuda().requires_grad_() for t in (wg, wb, bg, bb)]
+    rmc, rvc, nbt = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.tensor(0, device="cuda")
+    cfg = ops.NormCfg(False, act, True, 0.1, 1e-5)
+    out = ops.SpadeConvFn.apply(ac, xc, sc, wgc, wbc, bgc, bbc, ops.ConvCfg(3, 3, 1, 1, L.ACT_NONE), cfg, rmc, rvc, nbt, up, None)
+    out.backward(nhwc(dout))
+    assert rel(nchw(out), ref) < 5e-3
+    assert rel(rmc, rm) < 1e-4 and rel(rvc, rv) < 1e-4 and int(nbt) == 1
+    assert rel(nchw(ac.grad), ar.grad) < TOL_ACT and rel(nchw(xc.grad), xr.grad) < TOL_ACT
+    assert rel(sc.grad, sr.grad) < TOL_ACT
+    assert rel(wgc.grad, wgr.grad) < TOL_ACT and rel(wbc.grad, wbr.grad) < TOL_ACT
+    assert rel(bgc.grad, bgr.grad) < TOL_ACT and rel(bbc.grad, bbr.grad) < TOL_ACT
