@@ -138,11 +138,14 @@ __device__ __forceinline__ float act_t(float v) {
   return v;
 }
 
-template <int BN, int ACT>
+// MODE 0: plain convolution epilogue; 1: fused SPADE+Style modulation (inference); 2: the same, also writing gamma and the
+// activation mask for backward.  A template parameter so that the ordinary instantiations do not carry the extra code.
+template <int BN, int ACT, int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const FwdParams p) {
   using Cfg = FwdCfg<BN>;
+  constexpr bool SPADE = MODE != 0, SPADE_TRAIN = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* out_buf = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -172,7 +175,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::prefetch_tmap(&tmY);
-    if (p.sgamma) ptx::prefetch_tmap(&tmG);
+    if (SPADE_TRAIN) ptx::prefetch_tmap(&tmG);
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -274,7 +277,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int grp = t / p.tiles_n;
       if (et < BN) {
         float bv = (p.bias && n0 + et < p.bias_n) ? __ldg(p.bias + n0 + et) : 0.f;
-        if (p.sx && et >= p.sC && et < 2 * p.sC) {   // fused SPADE: beta's bias absorbs the style offset s1 of this tile's sample
+        if (SPADE && et >= p.sC && et < 2 * p.sC) {   // fused SPADE: beta's bias absorbs the style offset s1 of this tile's sample
           int w0t, h0t, b0t;
           subtile_origin(p, (t / p.tiles_n) * Cfg::MT, w0t, h0t, b0t);
           bv += __ldg(p.spar + ((size_t)min(b0t, p.B - 1) * 4 + 3) * p.sC + (et - p.sC));
@@ -291,31 +294,31 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const bf16* mrow = nullptr;
         const float* par = nullptr;
         uint8_t* mask_row = nullptr;   // fused SPADE, training: this pixel's activation-mask bytes
-        if (side || p.sx) {
+        if (side || SPADE) {
           const int tw = row % p.TW, r2 = row / p.TW;
           const int th = r2 % p.TH, tb = r2 / p.TH;
           if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo) {
-            if (p.smask) mask_row = p.smask + (((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * (size_t)(p.sC >> 3);
+            if (SPADE_TRAIN && p.smask) mask_row = p.smask + (((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * (size_t)(p.sC >> 3);
             if (side) {
               mrow = side + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
-            } else if (p.sup) {   // x lives at half resolution (nearest 2x up-sampling folded in)
+            } else if (SPADE && p.sup) {   // x lives at half resolution (nearest 2x up-sampling folded in)
               mrow = p.sx + ((((size_t)(b0 + tb) * (p.Ho >> 1) + ((h0 + th) >> 1)) * (p.Wo >> 1) + ((w0 + tw) >> 1)) * p.sC);
             } else {
               mrow = p.sx + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.sC);
             }
           }
-          if (p.sx) par = p.spar + (size_t)min(b0, p.B - 1) * 4 * p.sC;   // host guarantees TB == 1: one sample per tile
+          if (SPADE) par = p.spar + (size_t)min(b0, p.B - 1) * 4 * p.sC;   // host guarantees TB == 1: one sample per tile
         }
-        const int nch = p.sx ? (p.sC >> 6) : BN / 64;
+        const int nch = SPADE ? (p.sC >> 6) : BN / 64;
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
           const int nbase = n0 + ch * 64;
-          if (!p.sx && nbase >= p.Cout) break;
+          if (!SPADE && nbase >= p.Cout) break;
           uint32_t r[16], rb[16];
           const uint32_t taddr =
               tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::MT * BN + j * BN + ch * 64 + sub * 16);
           ptx::tmem_ld_32x16(taddr, r);
-          if (p.sx) ptx::tmem_ld_32x16(taddr + (uint32_t)p.sC, rb);   // beta sits sC columns after gamma
+          if (SPADE) ptx::tmem_ld_32x16(taddr + (uint32_t)p.sC, rb);   // beta sits sC columns after gamma
           const uint32_t dflt = p.mask ? 0x3f803f80u : 0u;   // mask: keep everything / residual, x: zero
           uint4 mk[2] = {make_uint4(dflt, dflt, dflt, dflt), make_uint4(dflt, dflt, dflt, dflt)};
           if (mrow) {  // host guarantees Cout % 64 == 0 when a mask / residual is given
@@ -324,7 +327,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           // the TMA store that last read this staging buffer must have finished reading it
           if (store_thread) {
-            if (p.sgamma) ptx::tma_store_wait_read<0>();   // this chunk fills BOTH staging buffers (output and gamma)
+            if (SPADE_TRAIN) ptx::tma_store_wait_read<0>();   // this chunk fills BOTH staging buffers (output and gamma)
             else ptx::tma_store_wait_read<1>();
           }
           ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
@@ -352,7 +355,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
               }
             }
-            if (p.sx) {  // v = gamma (+bias); form the SPADE+Style output from x, beta and the per-channel constants
+            if (SPADE) {  // v = gamma (+bias); form the SPADE+Style output from x, beta and the per-channel constants
               const int c0 = ch * 64 + sub * 16 + 8 * i;
               const float4* bb = reinterpret_cast<const float4*>(s_bias + p.sC + c0);
               const float4 bb0 = bb[0], bb1 = bb[1];
@@ -365,7 +368,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               const float kb[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
               const float kc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
               const uint32_t xw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
-              if (p.sgamma) {   // gamma itself goes to the other staging buffer (rounded to bf16 exactly like backward reads it)
+              if (SPADE_TRAIN) {   // gamma itself goes to the other staging buffer (rounded to bf16 exactly like backward reads it)
                 uint8_t* og = out_buf + (buf ^ 1) * OUT_BUF_BYTES + row * 128;
                 *reinterpret_cast<uint4*>(og + (((sub * 2 + i) ^ (row & 7)) << 4)) =
                     make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
@@ -380,7 +383,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 bits |= (o > 0.f ? 1u : 0u) << e;
                 v[e] = o;
               }
-              if (mask_row) mask_row[(ch * 64 + sub * 16 + 8 * i) >> 3] = (uint8_t)bits;
+              if (SPADE_TRAIN && mask_row) mask_row[(ch * 64 + sub * 16 + 8 * i) >> 3] = (uint8_t)bits;
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) pk[e] = pack2_bf16(v[2 * e], v[2 * e + 1]);
@@ -400,10 +403,10 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           ptx::named_bar_sync(2, FWD_EPI_THREADS);
           if (store_thread && !(p.dbg & 1)) {
             ptx::tma_store_4d(&tmY, out_buf + buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
-            if (p.sgamma) ptx::tma_store_4d(&tmG, out_buf + (buf ^ 1) * OUT_BUF_BYTES, nbase, w0, h0, b0);
+            if (SPADE_TRAIN) ptx::tma_store_4d(&tmG, out_buf + (buf ^ 1) * OUT_BUF_BYTES, nbase, w0, h0, b0);
             ptx::tma_store_commit();
           }
-          if (!p.sgamma) buf ^= 1;
+          if (!SPADE_TRAIN) buf ^= 1;
         }
       }
       ptx::tc_fence_before();
@@ -443,7 +446,7 @@ void choose_fwd_tile(int B, int H, int W, int* tw, int* th, int* tb) {
   *tb = bb;
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, int MODE>
 int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale, void* y,
                cudaStream_t stream) {
   using Cfg = FwdCfg<BN>;
@@ -454,7 +457,8 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   int rc;
   if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
   if ((rc = make_map_w(&tmB, wp, d->ntaps, d->Cout, d->Cin, BN)) != S2E_OK) return rc;
-  const bool spade = d->spade_x != nullptr;
+  const bool spade = MODE != 0;
+  S2E_REQUIRE(spade == (d->spade_x != nullptr) && (MODE == 2) == (spade && d->spade_gamma_out != nullptr), "tapconv_fwd: mode mismatch");
   if (spade) {
     S2E_REQUIRE(d->spade_par && (d->spade_C == 64 || d->spade_C == 128) && d->Cout == 2 * d->spade_C && BN == d->Cout,
                 "tapconv_fwd: fused SPADE needs Cout = 2*C = the N tile, C in {64, 128} (C=%d Cout=%d)", d->spade_C, d->Cout);
@@ -508,11 +512,11 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_fwd_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_fwd_kernel<BN, ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   int grid = p.num_tiles < s2e_num_sms() ? p.num_tiles : s2e_num_sms();
-  tapconv_fwd_kernel<BN, ACT><<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmG, p);
+  tapconv_fwd_kernel<BN, ACT, MODE><<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmG, p);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -786,9 +790,18 @@ int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const
               d->Cin, d->Cout);
 #define S2E_FWD_DISPATCH(BN_)                                                                          \
   switch (d->act) {                                                                                    \
-    case S2E_ACT_LRELU: return launch_fwd<BN_, S2E_ACT_LRELU>(d, x, wp, bias, scale, y, stream);       \
-    case S2E_ACT_RELU: return launch_fwd<BN_, S2E_ACT_RELU>(d, x, wp, bias, scale, y, stream);         \
-    default: return launch_fwd<BN_, S2E_ACT_NONE>(d, x, wp, bias, scale, y, stream);                   \
+    case S2E_ACT_LRELU: return launch_fwd<BN_, S2E_ACT_LRELU, 0>(d, x, wp, bias, scale, y, stream);    \
+    case S2E_ACT_RELU: return launch_fwd<BN_, S2E_ACT_RELU, 0>(d, x, wp, bias, scale, y, stream);      \
+    default: return launch_fwd<BN_, S2E_ACT_NONE, 0>(d, x, wp, bias, scale, y, stream);                \
+  }
+  if (d->spade_x) {   // fused SPADE+Style epilogue: gamma | beta fill exactly one N tile
+    S2E_REQUIRE(d->act == S2E_ACT_NONE && (d->Cout == 256 || d->Cout == 128), "tapconv_fwd: fused SPADE needs Cout in {128, 256}");
+    if (d->spade_gamma_out) {
+      if (d->Cout == 256) return launch_fwd<256, S2E_ACT_NONE, 2>(d, x, wp, bias, scale, y, stream);
+      return launch_fwd<128, S2E_ACT_NONE, 2>(d, x, wp, bias, scale, y, stream);
+    }
+    if (d->Cout == 256) return launch_fwd<256, S2E_ACT_NONE, 1>(d, x, wp, bias, scale, y, stream);
+    return launch_fwd<128, S2E_ACT_NONE, 1>(d, x, wp, bias, scale, y, stream);
   }
   if (d->Cout >= 256) { S2E_FWD_DISPATCH(256) }
   if (d->Cout >= 128) { S2E_FWD_DISPATCH(128) }

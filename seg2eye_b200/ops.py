@@ -24,10 +24,10 @@ ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad cout_pad i
 #           with its output channels zero-padded to cout_pad; the caller sees the first Cout channels only
 
 _state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False,
-          # SpadeConvFn (training-mode gamma|beta conv + modulation in one kernel) is correct and tested but, measured on
-          # B200 (round 1), 0.3 ms slower per full-resolution launch than it saves: writing gamma next to the output
-          # costs the epilogue its double buffering.  Inference / no-grad forwards always use the fused kernel.
-          "fuse_spade_training": False}
+          # SpadeConvFn: training-mode gamma|beta conv + modulation in one kernel (measured on B200, round 1: 111.3 ->
+          # 109.3 ms/step; it lost 2 ms before the fused epilogue became its own template instantiation, when its
+          # extra registers spilled in EVERY forward kernel).  S2E_FUSE_SPADE_TRAINING=0 restores the two-kernel path.
+          "fuse_spade_training": __import__("os").environ.get("S2E_FUSE_SPADE_TRAINING", "1") == "1"}
 
 
 def bump_weights_epoch():

@@ -444,3 +444,28 @@ def test_training_iteration_other_gan_modes_vs_oracle(ctx, mode):
     ref = {k: float(v.reshape(-1)[0]) for k, v in {**ot.g_losses, **ot.d_losses}.items()}
     for k in ref:
         assert abs(ours[k] - ref[k]) <= TOL_LOSS * abs(ref[k]) + (2e-2 if k == "GAN" else 0.0), (k, ours[k], ref[k])
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_training_iteration_with_and_without_fused_spade_conv_vs_oracle(ctx, fused):
+    """One full G + D iteration with the training-mode fused gamma|beta-conv + modulation kernel (ops.SpadeConvFn, the
+    default) and with the two-kernel path against the oracle trainer: losses within 2e-2, image within the chained bound."""
+    from seg2eye_b200 import ops
+    old = ops._state["fuse_spade_training"]
+    ops._state["fuse_spade_training"] = fused
+    try:
+        tr = _make_trainer(ctx)
+        data = {k: v.clone() for k, v in ctx.batch.items()}
+        tr.run_generator_one_step(data)
+        tr.run_discriminator_one_step(data)
+    finally:
+        ops._state["fuse_spade_training"] = old
+    ours = {k: float(v.reshape(-1)[0]) for k, v in tr.get_latest_losses().items()}
+    sds = {n: O.synth_state(getattr(O, f + "_shapes")(ctx.oopt), ctx.seeds[n]) for n, f in (("G", "generator"), ("D", "discriminator"), ("E", "encoder"))}
+    ot = O.OracleTrainer(sds["G"], sds["D"], sds["E"], ctx.oopt)
+    ot.run_generator_one_step(ctx.batch)
+    ot.run_discriminator_one_step(ctx.batch)
+    ref = {k: float(v.reshape(-1)[0]) for k, v in {**ot.g_losses, **ot.d_losses}.items()}
+    for k in ref:
+        assert abs(ours[k] - ref[k]) <= TOL_LOSS * abs(ref[k]) + (2e-2 if k == "GAN" else 0.0), (k, ours[k], ref[k])
+    assert rel(tr.generated, ot.generated) < TOL_CHAIN
