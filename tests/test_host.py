@@ -195,3 +195,54 @@ print("DROPIN_OK", type(tr.pix2pix_model).__module__)
 ''' % (REPO, str(tmp_path), str(tmp_path))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "DROPIN_OK seg2eye_b200.models.pix2pix_model" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors of s2e_conv_t / s2e_sn_job_t / s2e_pack_job_t must have the C compiler's size and field offsets
+    (a silent mismatch would shift every field after the first difference)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from seg2eye_b200 import _lib as L
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    structs = {"s2e_conv_t": L.ConvDesc, "s2e_sn_job_t": L.SnJob, "s2e_pack_job_t": L.PackJob}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "seg2eye_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([gcc, "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), (cname, got[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_fused_spade_shape_rules_and_bench_traffic_lookup():
+    """Host-side decisions that need no GPU: which SPADE blocks take the fused gamma|beta-conv + modulation kernel, and
+    which ncu capture a bench launch class maps to."""
+    import importlib.util
+    import torch
+    from seg2eye_b200 import ops
+    e = lambda *s: torch.empty(*s, device="meta")
+    assert ops._fused_tile_w(384) == 128 and ops._fused_tile_w(192) == 64 and ops._fused_tile_w(96) == 32
+    assert ops.spade_conv_fused_ok(e(16, 640, 384, 64), False, 128)          # up_3.norm_1
+    assert ops.spade_conv_fused_ok(e(16, 320, 192, 128), True, 128)          # up_3.norm_0 / norm_s read the half-res source
+    assert ops.spade_conv_fused_ok(e(16, 320, 192, 128), False, 128)         # up_2.norm_1
+    assert not ops.spade_conv_fused_ok(e(16, 160, 96, 256), True, 128)       # C = 256: gamma | beta span two N tiles
+    assert not ops.spade_conv_fused_ok(e(16, 20, 12, 128), False, 128)       # 12 columns: no 128-pixel tile inside one image
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t, note = bench.ncu_traffic_for("fwd B16 640x384 Cin128 Cout256 T9", "R2", 16)
+    assert t == 2.969e9 and "r01_ncu_convprobe_fullres" in note
+    assert bench.ncu_traffic_for("fwd+spade B16 640x384 Cin128 Cout256 T9", "R2", 16)[0] is None
+    assert bench.ncu_traffic_for("fwd B16 640x384 Cin128 Cout256 T9", "R1", 16) == (None, None)
