@@ -113,6 +113,12 @@ def lib():
             fn.restype = C.c_int
             fn.argtypes = sig
         _lib = l
+        # bring-up aid: S2E_DEBUG="key=value,key=value" sets the library's debug knobs (include/seg2eye_b200.h) at load
+        # time, e.g. S2E_DEBUG=5=3 runs every narrow weight gradient through the experimental multi-tap kernel
+        for item in filter(None, os.environ.get("S2E_DEBUG", "").split(",")):
+            k, v = item.split("=")
+            if l.s2e_debug_set(int(k), int(v)) != 0:
+                raise RuntimeError("S2E_DEBUG: bad debug key %s" % k)
     return _lib
 
 

@@ -782,6 +782,247 @@ int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp,
   return S2E_OK;
 }
 
+// ================================================================================ weight gradient, several taps per CTA
+// EXPERIMENTAL (round 2 work item 1, off unless debug key 5 = 3): one CTA accumulates TPC taps of the same (M, N) tile.
+// The tap-independent operand (dY) is staged ONCE per pixel tile and multiplied against TPC shifted copies of X, each
+// into its own TMEM accumulator, instead of TPC CTAs re-reading dY through L2.  Same operand layouts, descriptors and
+// split-K reduction as tapconv_wgrad_kernel; TPC * BN <= 512 TMEM columns.
+constexpr int WG_BLK = 64 * 128;   // one 64-channel block of up to 64 pixels
+
+template <int BN, int TPC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapconv_wgrad_mt_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgParams p,
+                        int stages, int ngroups) {
+  constexpr int MAX_STAGES = 6;
+  constexpr int TMEM_COLS = TPC * BN <= 32 ? 32 : (TPC * BN <= 64 ? 64 : (TPC * BN <= 128 ? 128 : (TPC * BN <= 256 ? 256 : 512)));
+  static_assert(TPC * BN <= 512, "accumulators of all taps must fit TMEM");
+  constexpr int A_BLOCKS = 2, B_BLOCKS = BN / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // stage = [shared operand (dY)] [tap 0 operand (X)] ... [tap TPC-1 operand]; which of A / B is shared depends on swap
+  const int shared_blocks = p.swap ? B_BLOCKS : A_BLOCKS;
+  const int tap_blocks = p.swap ? A_BLOCKS : B_BLOCKS;
+  const int stage_bytes = (shared_blocks + TPC * tap_blocks) * WG_BLK;
+  uint64_t* bars = (uint64_t*)(smem + stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmDY);
+    ptx::prefetch_tmap(&tmX);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item decode: blockIdx.x = ((ks * mt + m) * nt + n) * ngroups + tap group
+  int wi = blockIdx.x;
+  const int tg = wi % ngroups;
+  wi /= ngroups;
+  const int n_idx = wi % p.nt;
+  wi /= p.nt;
+  const int m_idx = wi % p.mt;
+  const int ks = wi / p.mt;
+  const int tap0 = tg * TPC;
+  const int ntap = min(TPC, p.taps.n - tap0);
+  const int m0 = m_idx * 128, n0 = n_idx * BN;
+  const int k_begin = (int)(((long long)p.kt_total * ks) / p.ksplit);
+  const int k_end = (int)(((long long)p.kt_total * (ks + 1)) / p.ksplit);
+  const int nk = k_end - k_begin;
+  const uint32_t blk_bytes = (uint32_t)p.KP * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const CUtensorMap* map_shared = &tmDY;
+      const CUtensorMap* map_tap = &tmX;
+      const int c_shared = p.swap ? n0 : m0;   // channel origin of the shared operand (dY: Cout axis)
+      const int c_tap = p.swap ? m0 : n0;      // channel origin of the per-tap operand (X: Cin axis)
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        int r = kt;
+        const int w_idx = r % p.kt_w;
+        r /= p.kt_w;
+        const int h_idx = r % p.kt_h;
+        const int b_idx = r / p.kt_h;
+        const int w0 = w_idx * p.KTW, h0 = h_idx * p.KTH, b0 = b_idx * p.KTB;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* ss = smem + stage * stage_bytes;
+        ptx::mbar_expect_tx(&full[stage], blk_bytes * (uint32_t)(shared_blocks + ntap * tap_blocks));
+        for (int j = 0; j < shared_blocks; ++j)
+          ptx::tma_load_4d(ss + j * blk_bytes, map_shared, &full[stage], c_shared + j * 64, w0, h0, b0);
+        for (int tt = 0; tt < ntap; ++tt) {
+          uint8_t* st = ss + (shared_blocks + tt * tap_blocks) * WG_BLK;
+          const int dy = p.taps.dy[tap0 + tt], dx = p.taps.dx[tap0 + tt];
+          for (int j = 0; j < tap_blocks; ++j)
+            ptx::tma_load_4d(st + j * blk_bytes, map_tap, &full[stage], c_tap + j * 64, w0 + dx, h0 + dy, b0);
+        }
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int kmma = p.KP / 16;
+    const uint32_t lbo = p.swap_lbo_sbo ? 1024u : blk_bytes;
+    const uint32_t sbo = p.swap_lbo_sbo ? blk_bytes : 1024u;
+    for (int i = 0; i < nk; ++i) {
+      ptx::mbar_wait(&full[stage], phase);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t s_addr = ptx::smem_u32(smem + stage * stage_bytes);
+        for (int tt = 0; tt < ntap; ++tt) {
+          const uint32_t t_addr = s_addr + (uint32_t)((shared_blocks + tt * tap_blocks) * WG_BLK);
+          const uint32_t a_addr = p.swap ? t_addr : s_addr;   // A = M side: dY (shared) unless swapped
+          const uint32_t b_addr = p.swap ? s_addr : t_addr;
+          for (int k = 0; k < kmma; ++k) {
+            const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 2048, lbo, sbo);
+            const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 2048, lbo, sbo);
+            ptx::umma_bf16(tmem_base + (uint32_t)(tt * BN), ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(&empty[stage]);
+        if (i == nk - 1) ptx::umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (nk > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int mrow = m0 + row;
+    const int Mdim = p.swap ? p.Cin : p.Cout, Ndim = p.swap ? p.Cout : p.Cin;
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int tt = 0; tt < ntap; ++tt) {
+      const int tap = tap0 + tt;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= Ndim) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tt * BN + c0), r);
+        ptx::tmem_ld_wait();
+        if (mrow < Mdim) {
+          if (!p.swap) {
+            float* dst_row = p.dwp + ((size_t)tap * p.Cout + mrow) * p.Cin + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + c0 + j + 3 < Ndim) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + j), "f"(__uint_as_float(r[j])),
+                             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                             : "memory");
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (n0 + c0 + j + e < Ndim) atomicAdd(dst_row + j + e, __uint_as_float(r[j + e]));
+              }
+            }
+          } else {
+            float* dst = p.dwp + ((size_t)tap * p.Cout + n0 + c0) * p.Cin + mrow;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < Ndim) atomicAdd(dst + (size_t)j * p.Cin, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int TPC>
+int launch_wgrad_mt(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, int swap, cudaStream_t stream) {
+  int tw = d->ktile_w, th = d->ktile_h, tb = d->ktile_b;
+  if (tw <= 0 || th <= 0 || tb <= 0) choose_k_tile(d->B, d->Ho, d->Wo, &tw, &th, &tb);
+  const int KP = tw * th * tb;
+  S2E_REQUIRE(KP % 16 == 0 && KP <= 64, "bad wgrad pixel tile %dx%dx%d", tw, th, tb);
+  CUtensorMap tmDY, tmX;
+  int rc;
+  if ((rc = make_map_nhwc(&tmDY, dy, d->B, d->Ho, d->Wo, d->Cout, tw, th, tb)) != S2E_OK) return rc;
+  if ((rc = make_map_nhwc(&tmX, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
+  WgParams p;
+  p.swap = swap;
+  p.Cout = d->Cout;
+  p.Cin = d->Cin;
+  p.mt = ceil_div(swap ? d->Cin : d->Cout, 128);
+  p.nt = ceil_div(swap ? d->Cout : d->Cin, BN);
+  p.kt_w = ceil_div(d->Wo, tw);
+  p.kt_h = ceil_div(d->Ho, th);
+  p.kt_b = ceil_div(d->B, tb);
+  p.kt_total = p.kt_w * p.kt_h * p.kt_b;
+  p.KTW = tw;
+  p.KTH = th;
+  p.KTB = tb;
+  p.KP = KP;
+  p.swap_lbo_sbo = s2e_debug_get(0);
+  p.dwp = dwp;
+  p.taps.n = d->ntaps;
+  for (int i = 0; i < d->ntaps; ++i) {
+    p.taps.dy[i] = d->tap_dy[i];
+    p.taps.dx[i] = d->tap_dx[i];
+  }
+  const int ngroups = ceil_div(d->ntaps, TPC);
+  const int shared_blocks = swap ? BN / 64 : 2, tap_blocks = swap ? 2 : BN / 64;
+  const int stage_bytes = (shared_blocks + TPC * tap_blocks) * WG_BLK;
+  int stages = (232448 - 1024 - 256) / stage_bytes;
+  if (stages > 6) stages = 6;
+  S2E_REQUIRE(stages >= 2, "wgrad_mt: stage of %d bytes leaves no pipeline", stage_bytes);
+  const int smem_bytes = stages * stage_bytes + 1024 + 256;
+  const int base = ngroups * p.mt * p.nt;
+  const int sms = s2e_num_sms();
+  int max_split = p.kt_total / 4;
+  if (max_split < 1) max_split = 1;
+  int ksplit = 1;
+  double best_fill = -1.0;
+  for (int w = 1; w <= 4; ++w) {
+    int ks = (sms * w) / base;
+    if (ks < 1) ks = 1;
+    if (ks > max_split) ks = max_split;
+    const int ctas = base * ks;
+    const int waves = ceil_div(ctas, sms);
+    const double fill = (double)ctas / ((double)waves * sms);
+    if (fill > best_fill + 0.02) {
+      best_fill = fill;
+      ksplit = ks;
+    }
+  }
+  p.ksplit = ksplit;
+  static bool attr_set = false;
+  if (!attr_set) {
+    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_wgrad_mt_kernel<BN, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  tapconv_wgrad_mt_kernel<BN, TPC><<<base * ksplit, NUM_THREADS, smem_bytes, stream>>>(tmDY, tmX, p, stages, ngroups);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
 }  // namespace
 
 int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
@@ -817,6 +1058,11 @@ int s2e_tapconv_wgrad_tc(const s2e_conv_t* d, const void* x, const void* dy, flo
   // per MMA), and a 64-channel side should not occupy the 128-row M side
   const int swap = (d->Cout > d->Cin) || (d->Cout < 128 && d->Cin >= 128);
   const int nside = swap ? d->Cout : d->Cin;
+  // experimental multi-tap kernel (debug key 5 = 3): narrow layers only, where one CTA per tap re-reads dY nine times
+  if (s2e_debug_get(5) == 3 && d->ntaps >= 3 && nside < 256) {
+    if (nside >= 128) return launch_wgrad_mt<128, 3>(d, x, dy, dwp, swap, stream);
+    return launch_wgrad_mt<64, 3>(d, x, dy, dwp, swap, stream);
+  }
   if (nside >= 256) return launch_wgrad<256>(d, x, dy, dwp, swap, stream);
   if (nside >= 128) return launch_wgrad<128>(d, x, dy, dwp, swap, stream);
   return launch_wgrad<64>(d, x, dy, dwp, swap, stream);

@@ -74,8 +74,9 @@ if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     once = "--once" in sys.argv
     for a in sys.argv[1:]:
-        if a.startswith("--dbg4="):     # 2: force 4 stages + 2 output buffers, 8: force 2 stages + 8 output buffers
-            L.call("s2e_debug_set", 4, int(a.split("=")[1]))
+        if a.startswith("--dbg"):       # --dbg5=3: experimental multi-tap weight-gradient kernel (see include/seg2eye_b200.h)
+            key, val = a[5:].split("=")
+            L.call("s2e_debug_set", int(key), int(val))
     shapes = [tuple(int(v) for v in args[i:i + 6]) for i in range(0, len(args), 6)] or DEFAULT
     if "--seg" in sys.argv:
         run_seg(16, 640, 384, once)
