@@ -148,3 +148,36 @@ def test_gan_loss_modes_match_reference_ganloss():
         got = O.gan_loss(p, bool(int(real)), bool(int(for_d)), mode)
         assert got.shape == (1,)
         np.testing.assert_allclose(got.numpy(), ref[key], rtol=1e-6, atol=1e-7, err_msg=key)
+
+
+def _variant_names():
+    from oracle.make_golden_variants import VARIANTS
+    return sorted(VARIANTS)
+
+
+@pytest.mark.parametrize("name", _variant_names())
+def test_option_variants_one_iteration(name):
+    """One G + D iteration of the oracle == the UNMODIFIED reference trainer for the option variants of SURVEY 8(f) rank 1
+    (spadeinstance, extra up-sampling, max aggregation, L2 loss, ls / original / wgan GAN modes, no feature matching,
+    no TTUR): losses, generated image and post-step weights / buffers (fixture: oracle/make_golden_variants.py)."""
+    from oracle.make_golden import SEEDS, SMALL
+    from oracle.make_golden_variants import VARIANTS
+    ref = np.load(os.path.join(GOLD, "ref_variants.npz"))
+    oopt = O.make_opt(**{**SMALL, **VARIANTS[name][1]})
+    sds = dict(G=O.synth_state(O.generator_shapes(oopt), SEEDS["G"]), D=O.synth_state(O.discriminator_shapes(oopt), SEEDS["D"]),
+               E=O.synth_state(O.encoder_shapes(oopt), SEEDS["E"]))
+    batch = O.synth_batch(oopt, 2, SEEDS["batch"])
+    tr = O.OracleTrainer(sds["G"], sds["D"], sds["E"], oopt)
+    tr.run_generator_one_step(batch)
+    tr.run_discriminator_one_step(batch)
+    losses = {**tr.g_losses, **tr.d_losses}
+    keys = [k.split("|")[2] for k in ref.files if k.startswith(name + "|loss|")]
+    assert sorted(keys) == sorted(losses), (keys, sorted(losses))
+    for k in keys:
+        np.testing.assert_allclose(losses[k].detach().reshape(-1).numpy(), ref["%s|loss|%s" % (name, k)], rtol=2e-4, atol=2e-5, err_msg=k)
+    s, st = sub(tr.generated)
+    close(s, ref[name + "|generated_sub"], tol=5e-4)
+    close(st[:2], ref[name + "|generated_stat"][:2], tol=5e-4)
+    close(sds["G"]["conv_img.weight"], ref[name + "|post_G_conv_img.weight"], tol=5e-4)
+    close(sds["G"]["up_1.conv_0.weight_u"], ref[name + "|post_G_up_1.conv_0.weight_u"], tol=5e-4)
+    close(sds["D"]["discriminator_1.model4.0.bias"], ref[name + "|post_D_model4_bias"], tol=5e-4, atol=1e-7)
