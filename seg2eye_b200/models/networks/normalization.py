@@ -157,7 +157,10 @@ class SPADE(nn.Module):
             actv, _ = self._actv(segmap, H, W)
             return ops.spade_conv_fused(actv, self.mlp_gamma.cfg, (self.mlp_gamma.weight, self.mlp_beta.weight),
                                         (self.mlp_gamma.bias, self.mlp_beta.bias), x, style, cfg, *bufs, up)
-        if self.training and ops._state["fuse_spade_training"] and ops.spade_conv_fused_ok(x, up, self.mlp_gamma.in_channels):
+        if (self.training and not self.per_sample and ops._state["fuse_spade_training"]
+                and ops.spade_conv_fused_ok(x, up, self.mlp_gamma.in_channels)):
+            # (InstanceNorm statistics -- `spadeinstance` -- keep the two-kernel path in training mode: the fused training
+            #  kernel has only been validated on hardware with BatchNorm statistics so far)
             # training: same fusion, the kernel additionally keeps gamma and the activation mask for backward
             actv, fused_relu = self._actv(segmap, H, W)
             ccfg = self.mlp_gamma.cfg._replace(relu_in=True) if fused_relu else self.mlp_gamma.cfg
