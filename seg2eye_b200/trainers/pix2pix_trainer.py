@@ -3,7 +3,7 @@ G+E and D gradients are averaged across ranks by bucketed NCCL all-reduce (seg2e
 
 Beyond the reference: `enable_cuda_graphs(example_batch)` captures the whole generator step and the whole
 discriminator step (forward, backward, all-reduce-free single-GPU case, Adam) into two CUDA graphs, so that a
-training iteration is two graph launches instead of ~2000 kernel launches driven from Python."""
+training iteration is two graph launches instead of ~1300 kernel launches driven from Python."""
 import torch
 
 from ..models.pix2pix_model import Pix2PixModel
