@@ -119,27 +119,132 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference(res, steps, warmup, batch=1):
-    """Oracle port of the reference step on the host cores; each step = one G step + one D step on `batch` images."""
+def cpu_reference(res, steps, warmup, batch=1, keep_first=False):
+    """Oracle port of the reference step on the host cores; each step = one G step + one D step on `batch` images.
+    keep_first: also return the losses / generated image of the FIRST iteration (from the initial weights) -- the
+    reference side of the in-bench parity check."""
     from oracle import seg2eye_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     oopt, _ = make_opts(res, batch)
-    sd = dict(G=O.init_state(O.generator_shapes(oopt), 1), D=O.init_state(O.discriminator_shapes(oopt), 2),
-              E=O.init_state(O.encoder_shapes(oopt), 3))
+    sd = parity_state(oopt)
     tr = O.OracleTrainer(sd["G"], sd["D"], sd["E"], oopt)
     b = O.synth_batch(oopt, batch, 1234)
-    times = []
+    times, first = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         tr.run_generator_one_step(b)
         tr.run_discriminator_one_step(b)
         dt = time.perf_counter() - t0
+        if i == 0 and keep_first:
+            first = ({k: float(v.reshape(-1)[0]) for k, v in {**tr.g_losses, **tr.d_losses}.items()}, tr.generated.detach().clone())
         if i >= warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    return dict(value=batch / (ms / 1e3), ms_per_step=ms, cores=torch.get_num_threads(),
+    return dict(value=batch / (ms / 1e3), ms_per_step=ms, cores=torch.get_num_threads(), first=first,
                 sample="%d G+D iteration(s) of batch %d at %s after %d warm-up" % (steps, batch, res, warmup))
+
+
+def parity_state(oopt):
+    """Reference-initialised weights (base_network.py:28-59) from portable seeds: the SAME state for the CPU arm and
+    for the in-bench parity run of the CUDA path."""
+    from oracle import seg2eye_oracle as O
+    return dict(G=O.init_state(O.generator_shapes(oopt), 1), D=O.init_state(O.discriminator_shapes(oopt), 2),
+                E=O.init_state(O.encoder_shapes(oopt), 3))
+
+
+def parity_ours(res, first, batch=1):
+    """One G step + one D step of the CUDA path at the BENCH size (ngf = ndf = 64, `res`), batch `batch`, from the same
+    weights and inputs as the oracle's first iteration; returns the comparison that goes into the JSON line.
+    Tolerances: BASELINE.md section 5 / north_star (losses 2e-2 relative, GAN term with a 2e-2 absolute floor because it is
+    a mean of signed logits that nearly cancels; image: chained bf16 bound)."""
+    import contextlib, io
+    from oracle import seg2eye_oracle as O
+    from seg2eye_b200.trainers.pix2pix_trainer import Pix2PixTrainer
+    oopt, opt = make_opts(res, batch)
+    opt.gpu_ids = [torch.cuda.current_device()]
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = Pix2PixTrainer(opt)
+    m = tr.pix2pix_model
+    sd = parity_state(oopt)
+    for net, k in ((m.netG, "G"), (m.netD, "D"), (m.netE, "E")):
+        net.load_state_dict({a: b.clone() for a, b in sd[k].items()})
+        net.cuda()
+    data = {k: v.clone() for k, v in O.synth_batch(oopt, batch, 1234).items()}
+    tr.run_generator_one_step(data)
+    tr.run_discriminator_one_step(data)
+    torch.cuda.synchronize()
+    ours = {k: float(v.reshape(-1)[0]) for k, v in tr.get_latest_losses().items()}
+    ref_losses, ref_img = first
+    img = tr.generated.detach().float().cpu()
+    img_err = float((img.double() - ref_img.double()).norm() / ref_img.double().norm())
+    rows, ok = {}, True
+    for k, r in ref_losses.items():
+        tol = 2e-2 * abs(r) + (2e-2 if k == "GAN" else 0.0)
+        rows[k] = {"ours": ours[k], "reference": r, "abs_err": abs(ours[k] - r), "tol": tol}
+        ok = ok and abs(ours[k] - r) <= tol
+    return {"config": "%s, batch %d, ngf=ndf=64, reference-initialised weights, first G+D iteration" % (res, batch),
+            "image_rel_l2_err": img_err, "image_tol": 2e-2, "losses": rows, "losses_tol": "2e-2 relative (+2e-2 absolute for GAN)",
+            "pass": bool(ok and img_err <= 2e-2)}
+
+
+# ------------------------------------------------------------------------------------------------ library arm (stock torch on the GPU)
+def library_reference(res, steps, warmup, batch, precision):
+    """The SAME restatement of the reference step, executed by stock PyTorch on the B200 (cuDNN / cuBLAS / ATen): the
+    "library baseline" of SURVEY 8(d) / BASELINE.md 6.5 -- what `--gpu_ids 0` of the reference costs on this GPU.
+    precision: 'tf32' (fp32 storage, TF32 tensor cores -- torch's default for cuDNN convolutions) or 'bf16'
+    (torch.autocast + channels_last).  Tries `batch` first and halves it on out-of-memory."""
+    from oracle import seg2eye_oracle as O
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    cl = precision == "bf16"
+
+    def to_dev(sd):
+        out = {}
+        for k, v in sd.items():
+            t = v.to(dev)
+            if cl and t.dim() == 4:
+                t = t.contiguous(memory_format=torch.channels_last)
+            out[k] = t
+        return out
+
+    b = batch
+    while b >= 1:
+        try:
+            oopt, _ = make_opts(res, b)
+            sd = dict(G=to_dev(O.init_state(O.generator_shapes(oopt), 1)), D=to_dev(O.init_state(O.discriminator_shapes(oopt), 2)),
+                      E=to_dev(O.init_state(O.encoder_shapes(oopt), 3)))
+            tr = O.OracleTrainer(sd["G"], sd["D"], sd["E"], oopt)
+            data = {k: v.to(dev) for k, v in O.synth_batch(oopt, b, 1234).items()}
+            ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if cl else (lambda: __import__("contextlib").nullcontext())
+
+            def step():
+                with ctx():
+                    tr.run_generator_one_step(data)
+                    tr.run_discriminator_one_step(data)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            return dict(value=b / (ms / 1e3), ms_per_step=ms, batch=b, precision=precision,
+                        peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 1),
+                        losses={k: float(v.reshape(-1)[0]) for k, v in {**tr.g_losses, **tr.d_losses}.items()})
+        except torch.cuda.OutOfMemoryError:
+            tr = sd = data = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+            b //= 2
+    raise RuntimeError("library baseline: batch 1 does not fit")
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -297,39 +402,77 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference", "library"))
     ap.add_argument("--res", default="R2", choices=tuple(RES))
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--mode", default="graph", choices=("graph", "eager"))
     ap.add_argument("--ncu-step", action="store_true", help="bracket one eager step with cudaProfilerStart/Stop")
+    ap.add_argument("--precision", default="bf16", choices=("bf16", "tf32"), help="--impl library only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
+        steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
         r = cpu_reference(args.res, steps, warmup)
         cb = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
               "sample": r["sample"] + " (oracle/seg2eye_oracle.py: fp32 PyTorch-CPU restatement of the reference; the reference "
                                       "itself is Python and its checkout does not exist on the GPU box)"}
+        cfg = workload_config(args.res, args.batch, max(1, args.gpus))
+        cfg["sample_batch"] = 1    # the CPU arm times a bounded sample of the workload: batch 1 per step, images/s is per image
         print(json.dumps({
             "impl": "reference", "metric": "G+D train images/sec", "value": r["value"], "unit": "images/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": workload_config(args.res, args.batch, max(1, args.gpus)),
-            "cpu_baseline": cb,
+            "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if args.impl == "library":
+        if rank != 0:
+            return
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        r = library_reference(args.res, max(1, min(args.steps, 5)), max(1, min(args.warmup, 3)), args.batch, args.precision)
+        print(json.dumps({
+            "impl": "library", "metric": "G+D train images/sec", "value": r["value"], "unit": "images/s", "n_gpus": 1,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(args.res, r["batch"], 1), "peak_mem_gb": r["peak_mem_gb"], "losses": r["losses"],
+            "note": "stock PyTorch (cuDNN/cuBLAS/ATen) executing the reference step on the same B200: %s" % (
+                "fp32 storage, TF32 convolutions" if args.precision == "tf32" else "torch.autocast(bf16) + channels_last")}))
         return
 
     assert args.warmup >= 3, "timing rule: at least 3 warm-up steps"
     out = run_ours(args)
     if rank == 0:
         if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
-            r = cpu_reference(args.res, 1, 0)
+            # rank 0, N = 1 only: the oracle port on the host cores; its first iteration doubles as the parity reference
+            r = cpu_reference(args.res, 2, 1, keep_first=True)
             out["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
                                    "sample": r["sample"]}
+            try:
+                out["parity"] = parity_ours(args.res, r["first"])
+            except Exception as e:   # the bench line must still be printed; a failed parity run is reported as such
+                out["parity"] = {"pass": False, "error": repr(e)[:300]}
+        if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_library_baseline:
+            # the library baselines run in their own processes so that their allocator / cuDNN workspaces never share
+            # the measured process
+            lib = {}
+            for prec in ("bf16", "tf32"):
+                try:
+                    o = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "library", "--precision", prec,
+                                        "--res", args.res, "--batch", str(args.batch), "--steps", "3", "--warmup", "2"],
+                                       capture_output=True, text=True, timeout=600)
+                    line = [l for l in o.stdout.splitlines() if l.startswith("{")][-1]
+                    d = json.loads(line)
+                    lib[prec] = {"value": d["value"], "unit": "images/s", "batch": d["config"]["global_batch"],
+                                 "ms_per_step": d["ms_per_step"], "peak_mem_gb": d["peak_mem_gb"],
+                                 "ratio_ours_over_library": out["value"] / d["value"]}
+                except Exception as e:
+                    lib[prec] = {"unavailable": repr(e)[:200]}
+            out["library_baseline"] = lib
         print(json.dumps(out))
 
 

@@ -227,7 +227,7 @@ def one_hot(label, nc):
     if lab.dim() == 3:
         lab = lab.unsqueeze(0)
     b, _, h, w = lab.shape
-    return torch.zeros(b, nc, h, w).scatter_(1, lab, 1.0)
+    return torch.zeros(b, nc, h, w, device=lab.device).scatter_(1, lab, 1.0)
 
 
 def nearest_src_index(dst_len, src_len):
@@ -239,8 +239,8 @@ def nearest_src_index(dst_len, src_len):
 
 
 def nearest_resize(x, size):
-    hi = torch.from_numpy(nearest_src_index(size[0], x.shape[2]))
-    wi = torch.from_numpy(nearest_src_index(size[1], x.shape[3]))
+    hi = torch.from_numpy(nearest_src_index(size[0], x.shape[2])).to(x.device)
+    wi = torch.from_numpy(nearest_src_index(size[1], x.shape[3])).to(x.device)
     return x[:, :, hi][:, :, :, wi]
 
 
@@ -468,7 +468,7 @@ def generator_losses(sdG, sdD, sdE, batch, opt):
     if opt.lambda_l1:
         losses["L1/weighted"] = F.l1_loss(fake, batch["target"]) * opt.lambda_l1
     if not opt.no_ganFeat_loss:
-        fm = torch.zeros(1)
+        fm = torch.zeros(1, device=fake.device)
         for i in range(len(pred_fake)):
             for j in range(len(pred_fake[i]) - 1):
                 fm = fm + F.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) * opt.lambda_feat / len(pred_fake)

@@ -21,7 +21,18 @@ def _init_weight(w, init_type, gain, module):
         raise NotImplementedError('initialization method [%s] is not implemented' % init_type)
 
 
+def _weights_replaced(module, incompatible_keys):
+    from ... import ops
+    ops.bump_weights_epoch()
+
+
 class BaseNetwork(nn.Module):
+    def __init__(self):
+        super().__init__()
+        # the bf16 tap-major weight copies the kernels read are keyed on the master tensors' versions; a wholesale load
+        # additionally raises the global epoch so that CUDA-graph replays (no host-side checks inside) re-pack first
+        self.register_load_state_dict_post_hook(_weights_replaced)
+
     @staticmethod
     def modify_commandline_options(parser, is_train):
         return parser

@@ -33,6 +33,14 @@ class Conv2d(nn.Module):
             self.register_buffer('weight_u', F.normalize(torch.randn(cout), dim=0, eps=1e-12))
             self.register_buffer('weight_v', F.normalize(torch.randn(cin * k * k), dim=0, eps=1e-12))
 
+    def reset_parameters(self):
+        """nn.Conv2d.reset_parameters (what --init_type none leaves in place, base_network.py:45-46)."""
+        w = self.master_weight()
+        nn.init.kaiming_uniform_(w.data, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1 / math.sqrt(w[0].numel())
+            nn.init.uniform_(self.bias.data, -bound, bound)
+
     def __getattr__(self, name):
         if name == 'weight' and 'weight_orig' in self._parameters:
             return self._parameters['weight_orig'].data
@@ -90,6 +98,11 @@ class Linear(nn.Module):
         bound = 1 / math.sqrt(cin)
         self.weight = nn.Parameter(torch.empty(cout, cin).uniform_(-bound, bound))
         self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+
+    def reset_parameters(self):
+        bound = 1 / math.sqrt(self.in_features)
+        nn.init.uniform_(self.weight.data, -bound, bound)
+        nn.init.uniform_(self.bias.data, -bound, bound)
 
     def forward(self, x):
         return ops.LinearFn.apply(x.float(), self.weight, self.bias, L.ACT_NONE, 0)

@@ -202,8 +202,16 @@ def _run_pack_jobs(jobs):
         L.call("s2e_pack_weight_multi", arr, len(jobs), L.stream())
 
 
+def repack_pending():
+    """True when weights were changed wholesale since the last re-pack (bump_weights_epoch: checkpoint load,
+    load_state_dict, state restore).  Cheap enough to ask before every CUDA-graph replay, whose captured kernels read the
+    packed copies without any host-side staleness check."""
+    return _state.get("packed_epoch") != _state["weights_epoch"]
+
+
 def repack_stale():
     """Re-pack every registered copy whose master weights changed, in one launch per 40 tensors."""
+    _state["packed_epoch"] = _state["weights_epoch"]
     jobs, dead = [], []
     for key, e in _pack_cache.items():
         ws = e.weights()
@@ -774,6 +782,7 @@ class InstNormFn(torch.autograd.Function):
         L.call("s2e_instnorm_fwd", L.ptr(x), B, H * W, Cc, act, 1e-5, L.ptr(sn_inv), group, L.ptr(acc), L.ptr(mean),
                L.ptr(rstd), L.ptr(y), L.stream())
         ctx.act, ctx.group = act, group
+        ctx.skip_wgrad = _state["skip_wgrad"]    # captured at forward time, like TapConvFn
         ctx.has_sn = sn_inv is not None
         ctx.save_for_backward(x, y, mean, rstd, sn_inv, sn_U, sn_V, weight_orig)
         return y
@@ -789,7 +798,7 @@ class InstNormFn(torch.autograd.Function):
         L.call("s2e_instnorm_bwd", L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(mean), L.ptr(rstd), B, H * W, Cc, ctx.act,
                L.ptr(racc), L.ptr(dx), st)
         gw = None
-        if ctx.has_sn and weight_orig is not None and ctx.needs_input_grad[6] and not _state["skip_wgrad"]:
+        if ctx.has_sn and weight_orig is not None and ctx.needs_input_grad[6] and not ctx.skip_wgrad:
             S = sn_inv.shape[0]
             K = weight_orig.numel() // weight_orig.shape[0]
             coef = torch.empty(S, dtype=F32, device=x.device)

@@ -44,6 +44,7 @@ class GradReducer:
         self._slot = {}
         self._hooks = []
         self.launched_during_backward = 0   # diagnostics: buckets whose all-reduce started from a hook
+        self.flat_bound = False
 
     # ---- bucket construction (first step: we now know which parameters receive gradients)
     def _build(self):
@@ -75,11 +76,53 @@ class GradReducer:
             b.handle = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, async_op=True)
             self.launched_during_backward += 1
 
+    # ---- CUDA-graph mode: gradients live INSIDE the flat buckets ------------------------------------------------
+    def bind_flat_grads(self):
+        """After one eager step (which tells us which parameters receive gradients): make every such parameter's .grad a
+        view into its bucket's flat buffer and drop the hooks.  Backward then accumulates straight into the buckets
+        (no copy-in), `allreduce_flat()` reduces them in place (no copy-out) and Adam reads the views.  The caller zeroes
+        the buckets (`zero_flat()`) at the start of every step instead of setting .grad to None."""
+        if self.buckets is None:
+            self._build()
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for b in self.buckets:
+            for p, off in zip(b.params, b.offsets):
+                p.grad = b.flat[off:off + p.numel()].view_as(p)
+        self.flat_bound = True
+
+    def unbind_flat_grads(self):
+        """Back to eager mode: gradients become ordinary per-parameter tensors again, the overlap hooks return."""
+        self.flat_bound = False
+        for b in self.buckets or []:
+            for p in b.params:
+                p.grad = None
+            b.pending, b.handle = len(b.params), None
+        if self.overlap and self.buckets:
+            for b in self.buckets:
+                for p in b.params:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def zero_flat(self):
+        for b in self.buckets:
+            b.flat.zero_()
+
+    def allreduce_flat(self):
+        """SUM all-reduce of the buckets in place; the 1/world_size factor is folded into the loss by the caller."""
+        if world_size() == 1:
+            return
+        hs = [dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, async_op=True) for b in self.buckets]
+        for h in hs:
+            h.wait()
+
     # ---- called once after backward
     def allreduce(self):
         ws = world_size()
         if ws == 1:
             return
+        if self.flat_bound:
+            raise RuntimeError("GradReducer: gradients are bound to the flat buckets (CUDA-graph mode); use allreduce_flat()")
         first = self.buckets is None
         if first:
             self._build()
@@ -100,6 +143,34 @@ class GradReducer:
                     p.grad.copy_(b.flat[off:off + p.numel()].view_as(p.grad)).mul_(inv)
             b.handle = None
             b.pending = len(b.params)
+
+
+def ensure_process_group():
+    """Called by Pix2PixTrainer: the reference's train.py knows nothing about torch.distributed, so when it is launched
+    under torchrun (WORLD_SIZE > 1 in the environment) the trainer itself joins the process group -- NCCL, one GPU per
+    process (LOCAL_RANK) -- instead of silently running N independent trainings.  Returns (rank, world_size)."""
+    import os
+    ws_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws_env > 1 and not (dist.is_available() and dist.is_initialized()):
+        if not dist.is_available():
+            raise RuntimeError("WORLD_SIZE=%d but torch.distributed is not available" % ws_env)
+        if torch.cuda.is_available():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    if ws_env > 1 and world_size() != ws_env:
+        raise RuntimeError("WORLD_SIZE=%d in the environment but the process group has %d ranks" % (ws_env, world_size()))
+    return rank(), world_size()
+
+
+def shard_of(n_items):
+    """Index range of this rank's shard of `n_items` samples (a data loader that is not rank-aware feeds every rank the
+    same global batch; the trainer can then keep only its own shard)."""
+    ws, r = world_size(), rank()
+    per = (n_items + ws - 1) // ws
+    return range(min(r * per, n_items), min((r + 1) * per, n_items))
 
 
 def broadcast_module(module, src=0):

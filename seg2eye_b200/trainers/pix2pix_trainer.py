@@ -1,125 +1,186 @@
-"""Pix2PixTrainer mirror (reference trainers/pix2pix_trainer.py:9-88).  With torch.distributed initialised the
-G+E and D gradients are averaged across ranks by bucketed NCCL all-reduce (seg2eye_b200.parallel).
+"""Pix2PixTrainer mirror (reference trainers/pix2pix_trainer.py:9-88).
 
-Beyond the reference: `enable_cuda_graphs(example_batch)` captures the whole generator step and the whole
-discriminator step (forward, backward, all-reduce-free single-GPU case, Adam) into two CUDA graphs, so that a
-training iteration is two graph launches instead of ~1300 kernel launches driven from Python."""
+Data parallelism (beyond the reference, whose README rules multi-GPU training out): launched under torchrun the
+trainer joins the NCCL process group itself (the reference's train.py never would), broadcasts rank 0's freshly
+initialised / loaded networks so that all replicas start identical, averages the G+E and D gradients across ranks
+(seg2eye_b200.parallel) and lets only rank 0 write checkpoints.
+
+`enable_cuda_graphs(example_batch)` captures the generator step and the discriminator step into CUDA graphs, so that a
+training iteration is a handful of graph launches instead of ~1300 kernel launches driven from Python:
+  * one process: [forward + backward + Adam] is ONE graph per step;
+  * several ranks: [forward + backward] and [Adam] are two graphs with the NCCL all-reduce issued eagerly between them;
+    gradients are accumulated straight into the flat all-reduce buckets (parallel.GradReducer.bind_flat_grads), the
+    1/world_size factor rides on the loss."""
 import torch
 
-from ..models.pix2pix_model import Pix2PixModel
 from .. import parallel
+from ..models.pix2pix_model import Pix2PixModel
 
 
 class Pix2PixTrainer():
     def __init__(self, opt):
         self.opt = opt
+        self.rank, self.world = parallel.ensure_process_group()
         self.pix2pix_model = Pix2PixModel(opt)
         self.pix2pix_model_on_one_gpu = self.pix2pix_model
         self.generated = None
+        m = self.pix2pix_model
+        if self.world > 1:
+            # every replica must start from the same weights AND the same spectral-norm u/v / BatchNorm buffers (both are
+            # randomly initialised per process)
+            for net in (m.netG, m.netD, m.netE):
+                if net is not None:
+                    parallel.broadcast_module(net, 0)
+            from .. import ops
+            ops.bump_weights_epoch()
         if opt.isTrain:
             self.optimizer_G, self.optimizer_D = self.pix2pix_model_on_one_gpu.create_optimizers(opt)
             self.old_lr = opt.lr
-            m = self.pix2pix_model
             self.reducer_G = parallel.GradReducer(list(m.netG.parameters()) + list(m.netE.parameters()))
             self.reducer_D = parallel.GradReducer(list(m.netD.parameters()))
+        self._graphs = False
+
+    # ------------------------------------------------------------------ step bodies
+    def _fb(self, which, data, scale=1.0):
+        """forward + backward of one step; `scale` multiplies the loss that is differentiated (1/world_size when the
+        gradients are summed across ranks afterwards), never the reported losses."""
+        m = self.pix2pix_model
+        if which == 'G':
+            losses, generated = m(data, mode='generator')
+        else:
+            losses, generated = m(data, mode='discriminator'), None
+        total = sum(losses.values()).mean()
+        (total if scale == 1.0 else total * scale).backward()
+        return losses, generated
+
+    def _eager_step(self, which, data):
+        opt_, red = (self.optimizer_G, self.reducer_G) if which == 'G' else (self.optimizer_D, self.reducer_D)
+        self.pix2pix_model.train()
+        opt_.zero_grad()
+        losses, generated = self._fb(which, data)
+        red.allreduce()
+        opt_.step()
+        return losses, generated
+
+    def _split_step(self, which, data):
+        """The multi-rank CUDA-graph step executed eagerly (warm-up / capture bodies share this code)."""
+        opt_, red = (self.optimizer_G, self.reducer_G) if which == 'G' else (self.optimizer_D, self.reducer_D)
+        red.zero_flat()
+        out = self._fb(which, data, 1.0 / self.world)
+        red.allreduce_flat()
+        opt_.step()
+        return out
 
     # ------------------------------------------------------------------ CUDA-graph fast path
-    def _g_step_body(self, data):
-        g_losses, generated = self.pix2pix_model(data, mode='generator')
-        g_loss = sum(g_losses.values()).mean()
-        g_loss.backward()
-        self.reducer_G.allreduce()
-        self.optimizer_G.step()
-        return g_losses, generated
-
-    def _d_step_body(self, data):
-        d_losses = self.pix2pix_model(data, mode='discriminator')
-        d_loss = sum(d_losses.values()).mean()
-        d_loss.backward()
-        self.reducer_D.allreduce()
-        self.optimizer_D.step()
-        return d_losses
-
     def enable_cuda_graphs(self, example_data, warmup=3):
         """Capture the G step and the D step for batches shaped like `example_data` (label (B,1,H,W),
         style_image (B,ns,1,H,W), target (B,1,H,W)).  Afterwards run_*_one_step copy the batch into static device
-        buffers and replay.  Shapes must not change; call disable_cuda_graphs() to return to eager execution."""
-        if parallel.world_size() > 1:
-            # capturing the NCCL all-reduce inside the step graph deadlocked on the 2-GPU box (round 1); multi-GPU
-            # runs use the eager path until the collective is moved outside the captured region
-            raise RuntimeError("CUDA-graph steps are single-process for now; multi-GPU runs use the eager path")
+        buffers and replay.  Shapes must not change; call disable_cuda_graphs() to return to eager execution.
+        Capture is side-effect free: every piece of state the warm-up iterations touch is restored afterwards."""
+        import gc
+        from .. import ops
         dev = self.pix2pix_model.device()
-        self.pix2pix_model.train()
+        m = self.pix2pix_model
+        m.train()
+        multi = self.world > 1
         # autograd graphs of earlier eager steps keep the parameters' AccumulateGrad nodes bound to the legacy stream,
         # which cannot be joined from a capturing stream: drop every reference to them before warming up
-        if getattr(self, 'g_losses', None) is not None:
-            self.g_losses = {k: v.detach() for k, v in self.g_losses.items()}
-        if getattr(self, 'd_losses', None) is not None:
-            self.d_losses = {k: v.detach() for k, v in self.d_losses.items()}
+        for name in ('g_losses', 'd_losses'):
+            if getattr(self, name, None) is not None:
+                setattr(self, name, {k: v.detach() for k, v in getattr(self, name).items()})
         if self.generated is not None:
             self.generated = self.generated.detach()
-        self.pix2pix_model.reset_loss_log()
-        import gc
+        m.reset_loss_log()
         gc.collect()
         self._static = {'label': example_data['label'].long().to(dev).clone(),
                         'style_image': example_data['style_image'].float().to(dev).clone(),
                         'target': example_data['target'].float().to(dev).clone()}
-        # the warm-up iterations below are real training steps: snapshot every piece of state they touch (weights,
-        # BN / spectral-norm buffers, Adam moments and step counters) and restore it in place after the capture
-        m = self.pix2pix_model
         tensors = [t for net in (m.netG, m.netD, m.netE) for t in list(net.parameters()) + list(net.buffers())]
+        opts = (self.optimizer_G, self.optimizer_D)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):   # one throw-away iteration so that optimizer state exists before the snapshot
-            self.optimizer_G.zero_grad(set_to_none=True)
-            self.optimizer_D.zero_grad(set_to_none=True)
-            had_state = len(self.optimizer_G.state) > 0
-            if not had_state:
+        with torch.cuda.stream(side):   # one throw-away iteration so that optimizer state (and the buckets) exist
+            for o in opts:
+                o.zero_grad(set_to_none=True)
+            if len(self.optimizer_G.state) == 0 or (multi and self.reducer_G.buckets is None):
                 snap0 = [t.detach().clone() for t in tensors]
-                self._g_step_body(dict(self._static))
-                self._d_step_body(dict(self._static))
-                for opt_ in (self.optimizer_G, self.optimizer_D):
-                    for st in opt_.state.values():
-                        st['exp_avg'].zero_()
-                        st['exp_avg_sq'].zero_()
-                    for g in opt_.param_groups:
-                        if g.get('_s2e_state') is not None:
-                            g['_s2e_state'][0].zero_()
+                fresh = len(self.optimizer_G.state) == 0
+                self._eager_step('G', dict(self._static))
+                self._eager_step('D', dict(self._static))
+                if fresh:
+                    for o in opts:
+                        for st in o.state.values():
+                            st['exp_avg'].zero_()
+                            st['exp_avg_sq'].zero_()
+                        for g in o.param_groups:
+                            if g.get('_s2e_state') is not None:
+                                g['_s2e_state'][0].zero_()
                 for t, s0 in zip(tensors, snap0):
                     t.detach().copy_(s0)
+            if multi:
+                self.reducer_G.bind_flat_grads()
+                self.reducer_D.bind_flat_grads()
         torch.cuda.current_stream().wait_stream(side)
-        opt_tensors = [st[k] for opt_ in (self.optimizer_G, self.optimizer_D) for st in opt_.state.values()
-                       for k in ('exp_avg', 'exp_avg_sq')]
-        opt_tensors += [g['_s2e_state'] for opt_ in (self.optimizer_G, self.optimizer_D) for g in opt_.param_groups
-                        if g.get('_s2e_state') is not None]
+        opt_tensors = [st[k] for o in opts for st in o.state.values() for k in ('exp_avg', 'exp_avg_sq')]
+        opt_tensors += [g['_s2e_state'] for o in opts for g in o.param_groups if g.get('_s2e_state') is not None]
         snap = [t.detach().clone() for t in tensors + opt_tensors]
+
+        def step(which):
+            if multi:
+                return self._split_step(which, dict(self._static))
+            (self.optimizer_G if which == 'G' else self.optimizer_D).zero_grad(set_to_none=True)
+            out = self._fb(which, dict(self._static))
+            (self.optimizer_G if which == 'G' else self.optimizer_D).step()
+            return out
+
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):     # allocates optimizer state, fills the packed-weight cache, sets func attributes
-                self.optimizer_G.zero_grad(set_to_none=True)
-                self._g_step_body(dict(self._static))
-                self.optimizer_D.zero_grad(set_to_none=True)
-                self._d_step_body(dict(self._static))
+            for _ in range(warmup):     # fills the packed-weight cache, sets function attributes, warms the allocator
+                step('G')
+                step('D')
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         torch.cuda.empty_cache()    # the graphs allocate from a private pool; give the eager cache back first
-        self._graph_G, self._graph_D = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        self.optimizer_G.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self._graph_G):
-            self._g_out = self._g_step_body(dict(self._static))
-        self.optimizer_D.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self._graph_D, pool=self._graph_G.pool()):
-            self._d_out = self._d_step_body(dict(self._static))
+        self._gr = {}
+        pool = None
+        for which in ('G', 'D'):
+            opt_, red = (self.optimizer_G, self.reducer_G) if which == 'G' else (self.optimizer_D, self.reducer_D)
+            m.reset_loss_log()
+            g_fb = torch.cuda.CUDAGraph()
+            if multi:
+                with torch.cuda.graph(g_fb, pool=pool):
+                    red.zero_flat()
+                    out = self._fb(which, dict(self._static), 1.0 / self.world)
+                pool = g_fb.pool()
+                red.allreduce_flat()
+                g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_opt, pool=pool):
+                    opt_.step()
+            else:
+                opt_.zero_grad(set_to_none=True)
+                with torch.cuda.graph(g_fb, pool=pool):
+                    out = self._fb(which, dict(self._static))
+                    opt_.step()
+                pool = g_fb.pool()
+                g_opt = None
+            # raw-loss tensors the model logged during the capture (L1/raw ...): static outputs of the graph, re-logged
+            # after every replay (the reference's train.py prints them)
+            log = {k: list(v) for k, v in m.loss_log.items()}
+            self._gr[which] = (g_fb, g_opt, out, log)
+        m.reset_loss_log()
         for t, s0 in zip(tensors + opt_tensors, snap):
             t.detach().copy_(s0)
-        from .. import ops
         ops.bump_weights_epoch()
         ops.repack_stale()   # the graphs re-pack after their own Adam; the restored weights need it once, here
         self._graphs = True
 
     def disable_cuda_graphs(self):
         self._graphs = False
-        self._graph_G = self._graph_D = self._g_out = self._d_out = None
+        self._gr = None
+        for red, opt_ in ((self.reducer_G, self.optimizer_G), (self.reducer_D, self.optimizer_D)):
+            if red.flat_bound:
+                red.unbind_flat_grads()
+            opt_.zero_grad(set_to_none=True)
 
     def _load_static(self, data):
         for k, buf in self._static.items():
@@ -130,36 +191,35 @@ class Pix2PixTrainer():
                 buf.copy_(src, non_blocking=True)
         data.update(self._static)   # the reference mutates `data` in place too (pix2pix_model.py:140-158)
 
+    def _replay(self, which, data):
+        """NOTE: the returned losses / image are the graph's static output buffers -- the next replay overwrites them
+        (clone what must outlive the step)."""
+        from .. import ops
+        if ops.repack_pending():     # weights changed behind the graphs' back (load_network, manual edits)
+            ops.repack_stale()
+        self._load_static(data)
+        g_fb, g_opt, out, log = self._gr[which]
+        g_fb.replay()
+        if g_opt is not None:
+            (self.reducer_G if which == 'G' else self.reducer_D).allreduce_flat()
+            g_opt.replay()
+        for k, vals in log.items():
+            for v in vals:
+                self.pix2pix_model.add_to_loss_log(k, v.clone())
+        return out
+
+    # ------------------------------------------------------------------ reference API
     def run_generator_one_step(self, data):
-        if getattr(self, '_graphs', False):
-            self._load_static(data)
-            self._graph_G.replay()
-            self.g_losses, self.generated = self._g_out
-            return
-        self.pix2pix_model.train()
-        self.optimizer_G.zero_grad()
-        g_losses, generated = self.pix2pix_model(data, mode='generator')
-        g_loss = sum(g_losses.values()).mean()
-        g_loss.backward()
-        self.reducer_G.allreduce()
-        self.optimizer_G.step()
-        self.g_losses = g_losses
-        self.generated = generated
+        if self._graphs:
+            self.g_losses, self.generated = self._replay('G', data)
+        else:
+            self.g_losses, self.generated = self._eager_step('G', data)
 
     def run_discriminator_one_step(self, data):
-        if getattr(self, '_graphs', False):
-            self._load_static(data)
-            self._graph_D.replay()
-            self.d_losses = self._d_out
-            return
-        self.pix2pix_model.train()
-        self.optimizer_D.zero_grad()
-        d_losses = self.pix2pix_model(data, mode='discriminator')
-        d_loss = sum(d_losses.values()).mean()
-        d_loss.backward()
-        self.reducer_D.allreduce()
-        self.optimizer_D.step()
-        self.d_losses = d_losses
+        if self._graphs:
+            self.d_losses = self._replay('D', data)[0]
+        else:
+            self.d_losses = self._eager_step('D', data)[0]
 
     def get_latest_losses(self, include_log_losses=False):
         losses = {**self.g_losses, **self.d_losses}
@@ -172,24 +232,23 @@ class Pix2PixTrainer():
         return self.generated
 
     def save(self, epoch):
-        self.pix2pix_model_on_one_gpu.save(epoch)
+        if self.rank == 0:      # replicas are identical; concurrent writers of the same file would corrupt it
+            self.pix2pix_model_on_one_gpu.save(epoch)
+        if self.world > 1:
+            torch.distributed.barrier()
 
     def update_learning_rate(self, epoch):
-        if epoch > self.opt.niter:
-            lrd = self.opt.lr / self.opt.niter_decay
-            new_lr = self.old_lr - lrd
-        else:
-            new_lr = self.old_lr
-        if new_lr != self.old_lr:
-            if self.opt.no_TTUR:
-                new_lr_G, new_lr_D = new_lr, new_lr
-            else:
-                new_lr_G, new_lr_D = new_lr / 2, new_lr * 2
-            for param_group in self.optimizer_D.param_groups:
-                param_group['lr'] = new_lr_D
-            for param_group in self.optimizer_G.param_groups:
-                param_group['lr'] = new_lr_G
-            self.optimizer_D.sync_hyperparams()
-            self.optimizer_G.sync_hyperparams()
-            print('update learning rate: %f -> %f' % (self.old_lr, new_lr))
-            self.old_lr = new_lr
+        """Linear decay (pix2pix_trainer.py:68-88): constant for the first `niter` epochs, then lr/niter_decay is taken
+        off once per epoch; under TTUR the generator runs at half and the discriminator at twice the nominal rate."""
+        if epoch <= self.opt.niter:
+            return
+        new_lr = self.old_lr - self.opt.lr / self.opt.niter_decay
+        if new_lr == self.old_lr:
+            return
+        g_scale, d_scale = (1.0, 1.0) if self.opt.no_TTUR else (0.5, 2.0)
+        for optimizer, scale in ((self.optimizer_G, g_scale), (self.optimizer_D, d_scale)):
+            for group in optimizer.param_groups:
+                group['lr'] = new_lr * scale
+            optimizer.sync_hyperparams()
+        print('update learning rate: %f -> %f' % (self.old_lr, new_lr))
+        self.old_lr = new_lr

@@ -155,6 +155,29 @@ def test_conv_tcgen05_vs_torch(S, case):
     conv_case(S, L.IMPL_TC, *case)
 
 
+MT_WGRAD_CASES = [
+    (2, 64, 64, 24, 16, 3, 1, 1, 0),       # M = 128 half empty, N = 64
+    (2, 128, 64, 24, 16, 3, 1, 1, 0),      # swapped orientation
+    (2, 64, 128, 24, 16, 3, 1, 1, 0),      # swapped (Cout > Cin)
+    (2, 128, 128, 24, 16, 3, 1, 1, 0),     # N = 128: three 128-column accumulators
+    (1, 64, 64, 37, 29, 3, 1, 1, 0),       # ragged map: partial pixel tiles at the right / bottom edge
+    (3, 128, 128, 40, 48, 3, 1, 1, 0),     # many pixel tiles per CTA, several split-K slices
+    (2, 64, 128, 11, 9, 4, 1, 2, 0),       # 16 taps: last group has one tap
+]
+
+
+@pytest.mark.parametrize("case", MT_WGRAD_CASES)
+def test_conv_tcgen05_multitap_wgrad(S, case):
+    """Weight gradients of narrow layers (N side < 256) through tapconv_wgrad_mt_kernel: several taps per CTA against
+    one staged dY tile (debug key 5 = 3 forces it for every eligible shape)."""
+    L, ops = S
+    L.call("s2e_debug_set", 5, 3)
+    try:
+        conv_case(S, L.IMPL_TC, *case)
+    finally:
+        L.call("s2e_debug_set", 5, 0)
+
+
 def test_conv_tcgen05_fused_gamma_beta_and_spectral(S):
     L, ops = S
     conv_case(S, L.IMPL_TC, 2, 128, 64, 20, 16, 3, 1, 1, 0, n_w=2)           # two weights packed along Cout

@@ -110,6 +110,63 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 64);
 }
 
+// Second question (weight-gradient kernel): both operands are MN-major there (pixels = K, one 128-byte row per pixel).
+// Can the B-operand descriptor of an MN-major SWIZZLE_128B tile start at an arbitrary pixel row, so that ONE staged X tile
+// with a halo serves the dx = -1 / 0 / +1 taps?  A = K-major selection matrix (A[m][k] = 1 iff k == m % 64), B = rows
+// [shift, shift + 64) of the staged [ROWS x 64] tile read MN-major, so D[m][n] = X[shift + m % 64][n].
+__global__ void __launch_bounds__(128, 1) probe_mn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmSel,
+                                                          int shift_rows, int use_base_offset, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                        // ROWS * 128 bytes
+  uint8_t* sSel = smem + ROWS * 128;         // 128 * 128 bytes (M = 128 rows x K = 64)
+  uint64_t* bar_load = (uint64_t*)(sSel + 128 * 128);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = (uint32_t*)(bar_mma + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar_load, 1);
+    ptx::mbar_init(bar_mma, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_slot, 64);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    ptx::mbar_expect_tx(bar_load, ROWS * 128 + 128 * 128);
+    for (int r0 = 0; r0 < ROWS; r0 += 256) tma_load_2d(sX + r0 * 128, &tmX, bar_load, 0, r0);
+    tma_load_2d(sSel, &tmSel, bar_load, 0, 0);
+    ptx::mbar_wait(bar_load, 0);
+    ptx::tc_fence_after();
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major
+    const uint32_t b0 = ptx::smem_u32(sX) + (uint32_t)shift_rows * 128u;
+    const uint32_t bo = use_base_offset ? ((b0 >> 7) & 7u) : 0u;
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t ad = desc_sw128(ptx::smem_u32(sSel) + k * 32, 0, 1024, 0);
+      const uint64_t bd = desc_sw128(b0 + k * 2048, 8192, 1024, bo);   // 16 pixel rows per K = 16 step
+      ptx::umma_bf16(tmem_base, ad, bd, idesc, k != 0 ? 1u : 0u);
+    }
+    ptx::umma_commit(bar_mma);
+  }
+  __syncthreads();
+  ptx::mbar_wait(bar_mma, 0);
+  ptx::tc_fence_after();
+  uint32_t r[32];
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    ptx::tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c0 + j] = __uint_as_float(r[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 64);
+}
+
 }  // namespace
 
 int main() {
@@ -153,6 +210,42 @@ int main() {
           for (int n = 0; n < 64; ++n)
             if (hOut[m * 64 + n] != __bfloat162float(hA[src * 64 + n])) ++bad;
         }
+        printf(" s%d:%s", shift, bad == 0 ? "OK" : "x ");
+      }
+      printf("\n");
+    }
+  }
+
+  // ---- MN-major B operand (weight-gradient layout) read from a shifted pixel row
+  {
+    std::vector<__nv_bfloat16> hSel(128 * 64);
+    for (int m = 0; m < 128; ++m)
+      for (int k = 0; k < 64; ++k) hSel[m * 64 + k] = __float2bfloat16(k == m % 64 ? 1.f : 0.f);
+    __nv_bfloat16* dSel;
+    cudaMalloc(&dSel, hSel.size() * 2);
+    cudaMemcpy(dSel, hSel.data(), hSel.size() * 2, cudaMemcpyHostToDevice);
+    CUtensorMap tmSel;
+    if (!make_map_2d(&tmSel, dSel, 128, 128)) {
+      printf("tensor map creation failed (sel)\n");
+      return 1;
+    }
+    const int smem2 = ROWS * 128 + 128 * 128 + 1024 + 256;
+    cudaFuncSetAttribute(probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    for (int bo = 0; bo < 2; ++bo) {
+      printf("MN-major B, base_offset %s :", bo ? "(addr>>7)&7" : "0          ");
+      for (int shift = 0; shift < 12; ++shift) {
+        cudaMemset(dOut, 0, 128 * 64 * 4);
+        probe_mn_kernel<<<1, 128, smem2>>>(tmA, tmSel, shift, bo, dOut);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+          printf(" [shift %d: %s]", shift, cudaGetErrorString(e));
+          return 2;
+        }
+        cudaMemcpy(hOut.data(), dOut, hOut.size() * 4, cudaMemcpyDeviceToHost);
+        int bad = 0;
+        for (int m = 0; m < 128; ++m)
+          for (int n = 0; n < 64; ++n)
+            if (hOut[m * 64 + n] != __bfloat162float(hA[(shift + m % 64) * 64 + n])) ++bad;
         printf(" s%d:%s", shift, bad == 0 ? "OK" : "x ");
       }
       printf("\n");
