@@ -110,6 +110,9 @@ typedef struct {
   void* spade_gamma_out;         /* training (nullable): gamma alone, bf16 [B][Ho][Wo][spade_C] -- all that backward needs
                                     of gamma|beta (s2e_spade_style_bwd with gb_stride = spade_C) */
   void* spade_mask_out;          /* training (nullable): the activation bit mask of s2e_spade_style_fwd */
+  int spade_plain;               /* != 0: plain SPADE (normalization.py:91-105 without the ApplyStyle half): the epilogue writes
+                                    act(norm(x) (1 + gamma) + beta) -- no style term, no factor 1/2 (s2e_spade_params with
+                                    style == NULL zeroes the style rows of `spade_par`) */
 } s2e_conv_t;
 
 int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,
@@ -280,6 +283,26 @@ int s2e_adam_multi(int n_tensors, float* const* p, const float* const* g, float*
                    const long long* n, const float* state, float beta1, float beta2, float eps, float weight_decay,
                    void* stream);
 int s2e_fill_f32(float* p, long long n, float value, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Validation / inference tail and style aggregation.
+ * ------------------------------------------------------------------------------------------ */
+/* data/postprocessor.py:57-114 (ImageProcessor.to_255resized_imagebatch, called from util/tester.py:44-47): fp32 images in
+ * [-1,1], (N,1,h,w) -> int32 (N,1,H,W) in [0,255]: cv2.resize(INTER_LINEAR) in float64, (x+1)*255/2, .int() -- bit-exact
+ * integer result.  f32_path = 1: ImageProcessor.to_255imagebatch on the tensor itself (no resize, fp32 arithmetic;
+ * models/networks/loss.py:143-144).  With `target` (int32, same shape as out) the per-image exact sum of squared
+ * differences goes to sqsum (N x u64 scratch) and, if `score` != NULL, score[n] = sqrt(sqsum[n]) / (H*W)
+ * (models/networks/loss.py:102-133 openEDSaccuracy / MSECalculator). */
+int s2e_to255_resize(const float* x, int N, int h, int w, int H, int W, int f32_path, const int* target, int* out,
+                     unsigned long long* sqsum, float* score, void* stream);
+/* MSECalculator.calculate_mse_for_images (loss.py:113-133) on two int32 (N,1,H,W) batches already on the device */
+int s2e_openeds_score(const int* produced, const int* target, int N, int H, int W, unsigned long long* sqsum, float* score,
+                      void* stream);
+/* Pix2PixModel._aggregate_tensor (pix2pix_model.py:271-278): mean (mode 0) | max (mode 1) over the ns style images:
+ * x [G][ns][n] (fp32 or bf16) -> out [G][n] fp32; argmax (u8, max only) feeds the backward pass. */
+int s2e_aggregate_fwd(const void* x, int x_is_f32, int G, int ns, long long n, int mode, float* out, uint8_t* argmax, void* stream);
+int s2e_aggregate_bwd(const float* dout, const uint8_t* argmax, int x_is_f32, int G, int ns, long long n, int mode, void* dx,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,8 +70,9 @@ def _spade_style_shapes(sd, p, c, opt):
     for g in ("mlp_gamma", "mlp_beta"):
         sd[p + ".spade.%s.weight" % g] = (c, 128, 3, 3)
         sd[p + ".spade.%s.bias" % g] = (c,)
-    sd[p + ".adain.linear.weight"] = (2 * c, opt.w_dim)
-    sd[p + ".adain.linear.bias"] = (2 * c,)
+    if getattr(opt, "netG", "spadestyle") != "spade":     # the style-less SPADE generator (BASELINE config 5) has no ApplyStyle
+        sd[p + ".adain.linear.weight"] = (2 * c, opt.w_dim)
+        sd[p + ".adain.linear.bias"] = (2 * c,)
 
 
 def generator_blocks(opt):
@@ -189,7 +190,8 @@ def init_state(shapes, seed):
 
 
 def synth_batch(opt, batch, seed, hw=None):
-    """eye-shaped 4-class label ellipses, images/targets U(-1,1), 4-D label."""
+    """eye-shaped 4-class label ellipses, images/targets U(-1,1), 4-D label.  For label_nc > 4 (config 5:
+    35 classes) the four regions are subdivided into vertical bands so that every class id occurs."""
     rng = np.random.Generator(np.random.PCG64(seed))
     if hw is None:
         w = opt.crop_size
@@ -211,6 +213,9 @@ def synth_batch(opt, batch, seed, hw=None):
         lab[d_scl <= 1.0] = 1
         lab[(d_cir <= r2 * r2) & (d_scl <= 1.0)] = 2
         lab[(d_cir <= r3 * r3) & (d_scl <= 1.0)] = 3
+        if opt.label_nc > 4:
+            bands = (xx.astype(np.int64) * ((opt.label_nc + 3) // 4) // w).astype(np.uint8)
+            lab = np.minimum(lab + 4 * bands, opt.label_nc - 1).astype(np.uint8)
         label[b, 0] = lab
     style = rng.uniform(-1, 1, size=(batch, opt.input_ns, 1, h, w)).astype(np.float32)
     target = rng.uniform(-1, 1, size=(batch, 1, h, w)).astype(np.float32)
@@ -305,9 +310,13 @@ def apply_style(sd, p, x, w):
 
 
 def spade_style_block(sd, p, x, seg, w, opt):
-    """SPADE_STYLE_Block.forward, normalization.py:184-192."""
-    a = apply_style(sd, p + ".adain", x, w)
+    """SPADE_STYLE_Block.forward, normalization.py:184-192.  w None: the block of the ORIGINAL SPADE generator
+    (BASELINE config 5; SURVEY 8(c) last bullet) -- SPADE.forward (normalization.py:91-105) alone, i.e. the same block
+    with the ApplyStyle term and the division by two removed."""
     s = spade(sd, p + ".spade", x, seg, instance="instance" in opt.norm_G)
+    if w is None:
+        return s
+    a = apply_style(sd, p + ".adain", x, w)
     return (s + a) / 2
 
 
@@ -382,15 +391,107 @@ def encoder_forward(sd, x, opt, training=True):
     return mu, logvar, feats
 
 
-def encode_w(sdE, style_image, opt, training=True):
-    """pix2pix_model.py:280-314: one netE call per batch sample over its ns style images,
-    mu stacked to (B, ns, w_dim) and aggregated (mean | max) over ns."""
-    assert style_image.dim() == 5
-    mus = [encoder_forward(sdE, style_image[b], opt, training)[0] for b in range(style_image.shape[0])]
-    mw = torch.stack(mus, dim=0)
+def aggregate(t, dim, opt):
+    """Pix2PixModel._aggregate_tensor, pix2pix_model.py:271-278."""
     if opt.style_aggr_method == "mean":
-        return mw.mean(dim=1)
-    return mw.max(dim=1).values
+        return t.mean(dim=dim)
+    return t.max(dim=dim).values
+
+
+def encode_w(sdE, style_image, opt, training=True, with_features=False):
+    """pix2pix_model.py:280-314: one netE call per batch sample over its ns style images,
+    mu stacked to (B, ns, w_dim) and aggregated (mean | max) over ns.  with_features: also the per-sample lists of
+    feature maps aggregated over the ns images (pix2pix_model.py:297-302)."""
+    assert style_image.dim() == 5
+    res = [encoder_forward(sdE, style_image[b], opt, training) for b in range(style_image.shape[0])]
+    w = aggregate(torch.stack([r[0] for r in res], dim=0), 1, opt)
+    if not with_features:
+        return w
+    return w, [[aggregate(f, 0, opt) for f in r[2]] for r in res]
+
+
+def gram_matrix(x):
+    """loss.py:177-189."""
+    a, b, c, d = x.shape
+    f = x.reshape(a * b, c * d)
+    return torch.mm(f, f.t()).div(a * b * c * d)
+
+
+def style_feature_loss(feats_fake, feats_real, kind):
+    """_compute_style_feature_loss / _compute_gram_loss, pix2pix_model.py:162-184: per encoder level, the per-sample
+    aggregated maps stacked over the batch, MSE (kind 'feat': both sides live) or StyleLoss (kind 'gram': loss.py:192-200,
+    Gram matrix of the real side detached), summed over the levels."""
+    total = []
+    for lvl in range(len(feats_fake[0])):
+        ff = torch.stack([f[lvl] for f in feats_fake])
+        fr = torch.stack([f[lvl] for f in feats_real])
+        if kind == "feat":
+            total.append(F.mse_loss(ff, fr))
+        else:
+            total.append(F.mse_loss(gram_matrix(ff), gram_matrix(fr).detach()))
+    return torch.sum(torch.stack(total))
+
+
+def to_255(image):
+    """ImageProcessor.to_255imagebatch on a tensor in [-1,1] (postprocessor.py:57-72,92-96): add 1, mul 255, div 2 in the
+    tensor's own dtype, then .int() (truncation)."""
+    if image.dim() == 3:
+        image = image.unsqueeze(0)
+    return torch.div(torch.mul(torch.add(image, 1), 255), 2).int()
+
+
+def openeds_accuracy(produced, target):
+    """openEDSaccuracy, loss.py:102-111 (one image)."""
+    diff = produced.float() - target.float()
+    h, w = diff.shape[-2:]
+    return torch.sqrt(torch.sum(diff * diff).float()) / (h * w)
+
+
+def mse_for_images(produced, target):
+    """MSECalculator.calculate_mse_for_images / _for_tensors, loss.py:113-157 (after the 0..255 conversion)."""
+    return torch.stack([openeds_accuracy(produced[i], target[i]) for i in range(produced.shape[0])])
+
+
+def _fma(a, b, c):
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def cv_linear_table(dst, src):
+    """Coefficient table of cv2.resize(INTER_LINEAR) for one axis (modules/imgproc/src/resize.cpp): source index and
+    fractional part of fx = (d + 0.5) * scale - 0.5 with scale = 1 / (dst / src).  The OpenCV build the reference runs
+    on (4.x wheels, AVX2 dispatch) contracts the multiply-add, so the product is not rounded before the subtraction."""
+    scale = 1.0 / (float(dst) / float(src))
+    idx, frac = np.empty(dst, np.int64), np.empty(dst, np.float64)
+    for d in range(dst):
+        c = _fma(d + 0.5, scale, -0.5)
+        idx[d] = math.floor(c)
+        frac[d] = c - math.floor(c)
+    return idx, frac
+
+
+def resize_linear_f64(img, w, h):
+    """cv2.resize(img.astype(float64), (w, h), interpolation=cv2.INTER_LINEAR) for one (H, W) image."""
+    H, W = img.shape
+    sx, fx = cv_linear_table(w, W)
+    sy, fy = cv_linear_table(h, H)
+    lo, hi = sx < 0, sx >= W - 1
+    fx[lo], sx[lo] = 0.0, 0
+    fx[hi], sx[hi] = 0.0, W - 1
+    s = img.astype(np.float64)
+    sx1 = np.minimum(sx + 1, W - 1)
+    rows = s[:, sx] * (1.0 - fx)[None] + s[:, sx1] * fx[None]
+    single = sx + 1 >= W
+    rows[:, single] = s[:, sx[single]]
+    r0, r1 = np.clip(sy, 0, H - 1), np.clip(sy + 1, 0, H - 1)
+    return rows[r0] * (1.0 - fy)[:, None] + rows[r1] * fy[:, None]
+
+
+def to_255_resized(fake, w=400, h=640):
+    """ImageProcessor.to_255resized_imagebatch (postprocessor.py:98-114), the tail of util/tester.py:44-47: per image
+    cv2.resize in float64, then the 0..255 mapping in float64 and .int().  (B,1,h0,w0) fp32 -> (B,1,h,w) int32."""
+    out = np.stack([resize_linear_f64(im[0], w, h)[None] for im in fake.detach().cpu().numpy()])
+    return to_255(torch.from_numpy(out))
 
 
 def nlayer_discriminator(sd, p, x, opt, training=True):
@@ -457,9 +558,12 @@ def discriminate(sdD, seg, fake, real, opt, training=True):
 
 
 def generator_losses(sdG, sdD, sdE, batch, opt):
-    """compute_generator_loss, pix2pix_model.py:186-247 (GAN + L1/L2 + GAN_Feat)."""
+    """compute_generator_loss, pix2pix_model.py:186-247 (GAN, L1 / L2, openEDS, style_w / style_feat / gram, GAN_Feat)."""
     seg = one_hot(batch["label"], opt.label_nc)
-    w = encode_w(sdE, batch["style_image"], opt)
+    if getattr(opt, "netG", "spadestyle") == "spade":
+        w, feats_real = None, []
+    else:
+        w, feats_real = encode_w(sdE, batch["style_image"], opt, with_features=True)
     fake = generator_forward(sdG, seg, w, opt)
     pred_fake, pred_real = discriminate(sdD, seg, fake, batch["target"], opt)
     losses = {"GAN": gan_loss(pred_fake, True, False, getattr(opt, "gan_mode", "hinge"))}
@@ -467,6 +571,17 @@ def generator_losses(sdG, sdD, sdE, batch, opt):
         losses["L2/weighted"] = F.mse_loss(fake, batch["target"]) * opt.lambda_l2
     if opt.lambda_l1:
         losses["L1/weighted"] = F.l1_loss(fake, batch["target"]) * opt.lambda_l1
+    if getattr(opt, "lambda_openeds", 0):     # pix2pix_model.py:209-213: the .int() inside makes it a constant
+        losses["openeds/weighted"] = mse_for_images(to_255(fake), to_255(batch["target"])) * opt.lambda_openeds
+    lw, lf, lg = (getattr(opt, k, 0) for k in ("lambda_style_w", "lambda_style_feat", "lambda_gram"))
+    if lw or lf or lg:                         # pix2pix_model.py:215-231
+        w_fake, feats_fake = encode_w(sdE, fake.unsqueeze(1), opt, with_features=True)
+        if lw > 0:
+            losses["style_w/weighted"] = F.mse_loss(w_fake, w) * lw
+        if lf > 0:
+            losses["style_feat/weighted"] = style_feature_loss(feats_fake, feats_real, "feat") * lf
+        if lg > 0:
+            losses["gram/weighted"] = style_feature_loss(feats_fake, feats_real, "gram") * lg
     if not opt.no_ganFeat_loss:
         fm = torch.zeros(1, device=fake.device)
         for i in range(len(pred_fake)):
@@ -480,7 +595,7 @@ def discriminator_losses(sdG, sdD, sdE, batch, opt):
     """compute_discriminator_loss, pix2pix_model.py:249-264."""
     seg = one_hot(batch["label"], opt.label_nc)
     with torch.no_grad():
-        w = encode_w(sdE, batch["style_image"], opt)
+        w = None if getattr(opt, "netG", "spadestyle") == "spade" else encode_w(sdE, batch["style_image"], opt)
         fake = generator_forward(sdG, seg, w, opt)
     fake = fake.detach().requires_grad_()
     pred_fake, pred_real = discriminate(sdD, seg, fake, batch["target"], opt)

@@ -23,7 +23,8 @@ class ConvDesc(C.Structure):
                 ("ktile_w", C.c_int), ("ktile_h", C.c_int), ("ktile_b", C.c_int), ("relu_mask", C.c_void_p),
                 ("residual", C.c_void_p), ("bias_n", C.c_int), ("in_act", C.c_int), ("mask_slope", C.c_float),
                 ("spade_x", C.c_void_p), ("spade_par", C.c_void_p), ("spade_C", C.c_int), ("spade_act", C.c_int),
-                ("spade_up", C.c_int), ("spade_gamma_out", C.c_void_p), ("spade_mask_out", C.c_void_p)]
+                ("spade_up", C.c_int), ("spade_gamma_out", C.c_void_p), ("spade_mask_out", C.c_void_p),
+                ("spade_plain", C.c_int)]
 
 
 class SnJob(C.Structure):
@@ -87,6 +88,10 @@ _SIGS = {
     "s2e_adam_prepare": [_P, _F, _F, _P],
     "s2e_adam_step": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P],
     "s2e_fill_f32": [_P, _LL, _F, _P],
+    "s2e_to255_resize": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "s2e_openeds_score": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "s2e_aggregate_fwd": [_P, _I, _I, _I, _LL, _I, _P, _P, _P],
+    "s2e_aggregate_bwd": [_P, _P, _I, _I, _I, _LL, _I, _P, _P],
 }
 
 _lib = None

@@ -93,6 +93,7 @@ struct FwdParams {
   const bf16* sx;     // block input x, [B][Ho][Wo][sC] or, with sup != 0, its half-resolution source [B][Ho/2][Wo/2][sC]
   const float* spar;  // [B][4][sC]: ka = rstd, kb = -mean*rstd, kc = 1 + s0, s1
   int sC, sact, sup;
+  float sscale;       // 0.5 for SPADE+Style (normalization.py:190), 1 for plain SPADE (par rows 2, 3 are zero then)
   int sgamma;         // training: gamma (sC channels, bf16) is written through tmG as well -- backward needs it
   uint8_t* smask;     // training: one bit per output element, set where the output is > 0 ([B*Ho*Wo][sC/8] bytes)
   uint32_t a_box_bytes;
@@ -378,7 +379,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int e = 0; e < 8; ++e) {
                 const float xv = __uint_as_float((e & 1) ? (xw[e >> 1] & 0xffff0000u) : (xw[e >> 1] << 16));
                 const float beta = fmaf(__uint_as_float(rb[8 * i + e]), scale, betab[e]);   // includes the style offset s1
-                float o = 0.5f * (fmaf(fmaf(xv, ka[e], kb[e]), 1.f + v[e], beta) + xv * kc[e]);
+                float o = p.sscale * (fmaf(fmaf(xv, ka[e], kb[e]), 1.f + v[e], beta) + xv * kc[e]);
                 if (p.sact == S2E_ACT_LRELU) o = fmaxf(o, 0.2f * o);
                 bits |= (o > 0.f ? 1u : 0u) << e;
                 v[e] = o;
@@ -496,6 +497,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.sC = d->spade_C;
   p.sact = d->spade_act;
   p.sup = d->spade_up;
+  p.sscale = d->spade_plain ? 1.0f : 0.5f;
   p.sgamma = (spade && d->spade_gamma_out) ? 1 : 0;
   p.smask = spade ? (uint8_t*)d->spade_mask_out : nullptr;
   S2E_REQUIRE(!(p.mask && p.res), "tapconv_fwd: relu_mask and residual are mutually exclusive");

@@ -138,8 +138,8 @@ __global__ void spade_params_kernel(const float* __restrict__ mean, const float*
   float* o = par + (size_t)b * 4 * C + c;
   o[0] = rs;
   o[C] = -mean[so + c] * rs;
-  o[2 * C] = 1.f + style[(size_t)b * 2 * C + c];
-  o[3 * C] = style[(size_t)b * 2 * C + C + c];
+  o[2 * C] = style ? 1.f + style[(size_t)b * 2 * C + c] : 0.f;   // style == NULL: plain SPADE, no style term
+  o[3 * C] = style ? style[(size_t)b * 2 * C + C + c] : 0.f;
 }
 
 // ---------------------------------------------------------------- SPADE+Style forward (elementwise, 8 B/elem)
@@ -158,24 +158,26 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
   const int cg = C >> 3;
   const float* mu_b = mean + (per_sample ? b * C : 0);
   const float* rs_b = rstd + (per_sample ? b * C : 0);
-  const float* st_b = style + (size_t)b * 2 * C;
+  // style == NULL: plain SPADE (normalization.py:91-105 alone): out = act((x*rs - mu*rs)*(1+g) + beta), no style term, no 1/2
+  const float* st_b = style ? style + (size_t)b * 2 * C : nullptr;
+  const float os = style ? 0.5f : 1.0f;
   for (int cg0 = 0; cg0 < cg; cg0 += NT) {
     const int ncg = min(NT, cg - cg0);
     const int lanes = NT / ncg;
     const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
     if (my_lane >= lanes) continue;
     const int c = (cg0 + my_cg) * 8;
-    float k_a[8], k_b[8], k_c[8];  // out = 0.5*( (x*rs - mu*rs)*(1+g) + beta + x*(1+s0) + s1 )
+    float k_a[8], k_b[8], k_c[8];  // out = os*( (x*rs - mu*rs)*(1+g) + beta + x*(1+s0) + s1 )
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float rs = rs_b[c + j];
       k_a[j] = rs;
       k_b[j] = -mu_b[c + j] * rs;
-      k_c[j] = 1.f + st_b[c + j];
+      k_c[j] = st_b ? 1.f + st_b[c + j] : 0.f;
     }
     float s1v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s1v[j] = st_b[C + c + j];
+    for (int j = 0; j < 8; ++j) s1v[j] = st_b ? st_b[C + c + j] : 0.f;
     const long long base = (long long)b * HW;
     long long q = q0 + my_lane;
     for (; q + lanes < q1; q += 2 * lanes) {
@@ -187,13 +189,13 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
       unpack8(xa, xf); unpack8(ga, gf); unpack8(ba, bf_);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
+        o[j] = act_apply(os * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
       st_stream8(out + pA * C + c, pack8(o));
       if (amask) amask[pA * cg + cg0 + my_cg] = sign_bits8(o);
       unpack8(xb, xf); unpack8(gbb, gf); unpack8(bb, bf_);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
+        o[j] = act_apply(os * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
       st_stream8(out + pB * C + c, pack8(o));
       if (amask) amask[pB * cg + cg0 + my_cg] = sign_bits8(o);
     }
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restr
       unpack8(ld_stream8(gb + pA * 2 * C + C + c), bf_);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        o[j] = act_apply(0.5f * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
+        o[j] = act_apply(os * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
       st_stream8(out + pA * C + c, pack8(o));
       if (amask) amask[pA * cg + cg0 + my_cg] = sign_bits8(o);
     }
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
                                                                     const bf16* __restrict__ x, const bf16* __restrict__ gb,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     int HW, int C, int per_sample, int act, double* __restrict__ racc,
-                                                                    int up_w, int gstride) {
+                                                                    int up_w, int gstride, float os) {
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* 
     const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * (C >> 3) + (c >> 3)] : 0xffu;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float g = 0.5f * df[j];
+      float g = os * df[j];
       if (act == S2E_ACT_LRELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.2f;
       if (act == S2E_ACT_RELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.f;
       const float xh = (xf[j] - __ldg(mu + c + j)) * __ldg(rs + c + j);
@@ -279,7 +281,7 @@ __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int
       s2 += q[C + c];
       sb += q[3 * C + c];
       sg += q[4 * C + c];
-      sx += (1.0 + (double)style[(size_t)bb * 2 * C + c]) * q[3 * C + c];
+      if (style) sx += (1.0 + (double)style[(size_t)bb * 2 * C + c]) * q[3 * C + c];
     }
     if (!per_sample) {
       m12[c] = (float)(s1 / count);
@@ -308,7 +310,8 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
   const int cg = C >> 3;
   const int so = per_sample ? b * C : 0;
   const float* m1p = m12 + (per_sample ? (size_t)b * 2 * C : 0);
-  const float* s0p = style + (size_t)b * 2 * C;
+  const float* s0p = style ? style + (size_t)b * 2 * C : nullptr;
+  const float os = style ? 0.5f : 1.0f;
   for (int cg0 = 0; cg0 < cg; cg0 += NT) {
     const int ncg = min(NT, cg - cg0);
     const int lanes = NT / ncg;
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
       mu[j] = mean[so + c + j];
       m1[j] = m1p[c + j];
       m2[j] = m1p[C + c + j];
-      s0[j] = 1.f + s0p[c + j];
+      s0[j] = s0p ? 1.f + s0p[c + j] : 0.f;
     }
     // two pixels per iteration: all six 16-byte loads are issued before the first use (memory-level parallelism)
     auto finish = [&](long long p, const bf16x8& vd, const bf16x8& vx, const bf16x8& vg, uint32_t mbits) {
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* _
       unpack8(vd, df); unpack8(vx, xf); unpack8(vg, gf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float g = 0.5f * df[j];
+        float g = os * df[j];
         if (act == S2E_ACT_LRELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.2f;
         if (act == S2E_ACT_RELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.f;
         const float xh = (xf[j] - mu[j]) * rsd[j];
@@ -598,11 +601,13 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
   S2E_REQUIRE(act == S2E_ACT_NONE || act_mask, "spade_style_bwd: the activation mask written by the forward pass is required");
   const int gstride = gb_stride > 0 ? gb_stride : 2 * C;
   S2E_REQUIRE(gstride >= C && gstride % 8 == 0, "spade_style_bwd: bad gamma stride %d", gstride);
+  S2E_REQUIRE(style || !dstyle, "spade_style_bwd: plain SPADE (style == NULL) has no style gradient");
   S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 5 * C, st));
   float* m12 = (float*)(racc + (size_t)B * 5 * C);
   dim3 grid(red_chunks(HW, B), B);
   spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x,
-                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc, up_w, gstride);
+                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc, up_w, gstride,
+                                                                style ? 0.5f : 1.0f);
   S2E_LAUNCH_CHECK();
   const double count = per_sample ? (double)HW : (double)B * HW;
   spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, m12, dstyle, chsum);

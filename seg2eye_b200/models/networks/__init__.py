@@ -2,17 +2,17 @@
 option hooks and the loss re-exports `Pix2PixModel` / `util.tester` import from here."""
 import torch
 
-from .architecture import SPADE_STYLE_ResnetBlock
+from .architecture import SPADE_STYLE_ResnetBlock, SPADEResnetBlock
 from .base_network import BaseNetwork
 from .discriminator import MultiscaleDiscriminator, NLayerDiscriminator
 from .encoder import ConvEncoder
-from .generator import SPADESTYLEGenerator
+from .generator import SPADEGenerator, SPADESTYLEGenerator
 from .loss import GANLoss, MSECalculator, StyleLoss, gram_matrix, l1_loss, mse_loss, openEDSaccuracy
 from .normalization import FC, SPADE, ApplyStyle, SPADE_STYLE_Block, get_nonspade_norm_layer
 
 # the reference resolves '<name><kind>' by scanning a module for a class of that lower-cased name; the hot path has
 # exactly these four
-_NETWORKS = {'spadestylegenerator': SPADESTYLEGenerator, 'multiscalediscriminator': MultiscaleDiscriminator,
+_NETWORKS = {'spadestylegenerator': SPADESTYLEGenerator, 'spadegenerator': SPADEGenerator, 'multiscalediscriminator': MultiscaleDiscriminator,
              'nlayerdiscriminator': NLayerDiscriminator, 'convencoder': ConvEncoder}
 
 
@@ -45,7 +45,8 @@ def create_network(cls, opt):
 
 
 def define_G(opt):
-    return create_network(SPADESTYLEGenerator, opt)
+    # --netG spadestyle (the reference's only generator) | spade (the style-less original, BASELINE config 5)
+    return create_network(find_network_using_name(getattr(opt, 'netG', 'spadestyle'), 'generator'), opt)
 
 
 def define_D(opt):

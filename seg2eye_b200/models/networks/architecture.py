@@ -8,10 +8,12 @@ import torch.nn as nn
 from ... import _lib as L
 from ... import ops
 from .layers import Conv2d
-from .normalization import SPADE_STYLE_Block
+from .normalization import SPADE_Block, SPADE_STYLE_Block
 
 
 class SPADE_STYLE_ResnetBlock(nn.Module):
+    norm_block = SPADE_STYLE_Block
+
     def __init__(self, fin, fout, opt):
         super().__init__()
         mid = min(fin, fout)
@@ -22,10 +24,10 @@ class SPADE_STYLE_ResnetBlock(nn.Module):
         self.conv_1 = Conv2d(mid, fout, 3, padding=1, spectral=sn)
         if self.learned_shortcut:
             self.conv_s = Conv2d(fin, fout, 1, bias=False, spectral=sn)
-        self.norm_0 = SPADE_STYLE_Block(fin, opt)
-        self.norm_1 = SPADE_STYLE_Block(mid, opt)
+        self.norm_0 = self.norm_block(fin, opt)
+        self.norm_1 = self.norm_block(mid, opt)
         if self.learned_shortcut:
-            self.norm_s = SPADE_STYLE_Block(fin, opt)
+            self.norm_s = self.norm_block(fin, opt)
 
     def _shortcut_nhwc(self, x, seg, w, up=False, sink=None):
         if not self.learned_shortcut:
@@ -54,3 +56,15 @@ class SPADE_STYLE_ResnetBlock(nn.Module):
 
     def actvn(self, x):
         return ops.as_nchw_view(ops.ActFn.apply(ops.as_nhwc(x), L.ACT_LRELU))
+
+
+class SPADEResnetBlock(SPADE_STYLE_ResnetBlock):
+    """architecture.py:13-62 with plain SPADE normalisation (no style branch): the ResNet block of the original SPADE
+    generator (BASELINE config 5).  forward(x, seg) -- a third argument is accepted and ignored."""
+    norm_block = SPADE_Block
+
+    def forward_nhwc(self, x, seg, latent_style=None, up=False):
+        return super().forward_nhwc(x, seg, None, up)
+
+    def forward(self, x, seg, latent_style=None):
+        return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x), seg))

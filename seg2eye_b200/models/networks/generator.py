@@ -6,7 +6,7 @@ Here the whole forward runs on NHWC bf16 activations through seg2eye_b200.ops; o
 """
 from ... import _lib as L
 from ... import ops
-from .architecture import SPADE_STYLE_ResnetBlock
+from .architecture import SPADE_STYLE_ResnetBlock, SPADEResnetBlock
 from .base_network import BaseNetwork
 from .layers import Conv2d
 from .normalization import clear_seg_cache
@@ -18,6 +18,8 @@ _UPSAMPLINGS = {"normal": 5, "more": 6, "most": 7}
 
 
 class SPADESTYLEGenerator(BaseNetwork):
+    block = SPADE_STYLE_ResnetBlock
+
     @staticmethod
     def modify_commandline_options(parser, is_train):
         parser.add_argument('--num_upsampling_layers', choices=tuple(_UPSAMPLINGS), default='normal',
@@ -32,11 +34,11 @@ class SPADESTYLEGenerator(BaseNetwork):
         self.sw, self.sh = self.compute_latent_vector_size(opt)
         self.fc = Conv2d(opt.semantic_nc, 16 * nf, 3, padding=1)
         for name, cin, cout in _TRUNK:
-            setattr(self, name, SPADE_STYLE_ResnetBlock(cin * nf, cout * nf, opt))
+            setattr(self, name, self.block(cin * nf, cout * nf, opt))
         last = nf
         if opt.num_upsampling_layers == 'most':
             # generator.py:45 refers to a helper that does not exist; this is the block it meant to create
-            self.up_4 = SPADE_STYLE_ResnetBlock(nf, nf // 2, opt)
+            self.up_4 = self.block(nf, nf // 2, opt)
             last = nf // 2
         self.conv_img = Conv2d(last, opt.output_nc, 3, padding=1)
 
@@ -64,9 +66,23 @@ class SPADESTYLEGenerator(BaseNetwork):
             raise ValueError('output_nc != 1 is not supported by the B200 path (OpenEDS images are single channel)')
         clear_seg_cache()   # the im2col'd segmaps are shared by the SPADE blocks of this forward only
         ops.prepare_spectral([m for m in self.modules() if isinstance(m, Conv2d)], self.training)
-        x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw))
+        # wide label maps are zero-padded to 64 channels so that fc runs on the tensor cores like mlp_shared does
+        cpad = -(-self.fc.in_channels // 64) * 64 if self.fc.in_channels >= 16 else 0
+        x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw, cpad))
         for name, upsample_first in self._schedule():
             x = getattr(self, name).forward_nhwc(x, input, w, up=upsample_first)
         x = self.conv_img.forward_nhwc(x, in_act=L.ACT_LRELU)     # leaky_relu(x, 0.2) -> conv_img, one kernel
         clear_seg_cache()
         return ops.TanhFn.apply(x)
+
+
+class SPADEGenerator(SPADESTYLEGenerator):
+    """The original SPADE generator (no style branch) -- BASELINE config 5: plain SPADE normalisation
+    (normalization.py:63-105) in the block / trunk structure of architecture.py:13-62 and generator.py:22-102, with the
+    ApplyStyle term and the division by two removed.  The reference defines no such class (only SPADESTYLEGenerator,
+    networks/__init__.py:9); state_dict keys = SPADESTYLEGenerator's without the `.adain.*` entries.
+    forward(input, w=None): `w` is ignored."""
+    block = SPADEResnetBlock
+
+    def forward(self, input, w=None):
+        return super().forward(input, None)

@@ -79,12 +79,27 @@ def openEDSaccuracy(produced, target):
 class MSECalculator:
     @classmethod
     def calculate_mse_for_images(cls, produced, target):
+        """loss.py:113-133: per-image OpenEDS error of two 0..255 batches shaped (B,1,640,400).  CUDA integer batches take
+        the exact-integer kernel (ops.openeds_score); anything else follows the reference's fp32 arithmetic."""
         assert produced.shape == target.shape
-        assert torch.min(produced) >= 0 and torch.max(produced) <= 255
+        assert torch.min(produced) >= 0 and torch.max(produced) <= 255, f"Min: {torch.min(produced)}, max: {torch.max(produced)}"
         assert torch.min(target) >= 0 and torch.max(target) <= 255
         assert produced.shape[-2:] == (640, 400), f"Invalid shape: {produced.shape}"
         assert len(produced.shape) == 4, "Please feed 4D tensors"
+        if produced.is_cuda and not produced.is_floating_point() and not target.is_floating_point():
+            return ops.openeds_score(produced, target)
         return torch.stack([openEDSaccuracy(produced[i], target[i]) for i in range(produced.shape[0])])
+
+    @classmethod
+    def calculate_mse_for_tensors(cls, produced, target):
+        """loss.py:136-157 (bound as criterionOpenEDS, pix2pix_model.py:36): both tensors in [-1,1] -> 0..255 integers
+        (ImageProcessor.to_255imagebatch, ending in .int(): the result carries no gradient) -> per-image error."""
+        assert produced.shape == target.shape
+        if not (produced.is_cuda and torch.cuda.is_current_stream_capturing()):   # range checks synchronise with the host
+            assert torch.min(produced) >= -1 and torch.max(produced) <= 1, f"Min: {torch.min(produced)}, max: {torch.max(produced)}"
+            assert torch.min(target) >= -1 and torch.max(target) <= 1
+        assert len(produced.shape) == 4, "Please feed 4D tensors"
+        return ops.openeds_score(ops.to255(produced), ops.to255(target))
 
     @classmethod
     def calculate_error_statistics(cls, all_errors, mode, dataset_key):
@@ -93,11 +108,21 @@ class MSECalculator:
 
 
 def gram_matrix(input):
+    """loss.py:177-189: F F^T / (a*b*c*d) with F = input viewed as (a*b, c*d); on the device through the tensor-core Gram
+    GEMM (ops.gram_matrix, value only -- the differentiable path is StyleLoss)."""
+    if input.is_cuda:
+        return ops.gram_matrix(input)
     a, b, c, d = input.size()
     features = input.float().reshape(a * b, c * d)
     return torch.mm(features, features.t()).div(a * b * c * d)
 
 
 class StyleLoss(nn.Module):
-    def forward(self, predicted_feature, target_feature):
-        return torch.nn.functional.mse_loss(gram_matrix(predicted_feature), gram_matrix(target_feature).detach())
+    """loss.py:192-200: mse(gram(predicted), gram(target).detach()).  Accepts the reference's NCHW tensors or our
+    aggregated (B, h, w, C) fp32 feature batches (`nhwc=True`, what Pix2PixModel passes)."""
+
+    def forward(self, predicted_feature, target_feature, nhwc=False):
+        if not nhwc:
+            predicted_feature = predicted_feature.float().permute(0, 2, 3, 1)
+            target_feature = target_feature.float().permute(0, 2, 3, 1)
+        return ops.gram_loss(predicted_feature, target_feature)

@@ -49,6 +49,19 @@ def seg_im2col_cached(segmap, h, w):
     return cols[(h, w)]
 
 
+def seg_nearest_cached(segmap, h, w, cpad):
+    """Nearest-resized (and channel-padded) segmap at (h, w), shared by the SPADE blocks of one generator forward."""
+    key = (id(segmap), segmap._version, segmap.data_ptr(), tuple(segmap.shape))
+    if _col_cache["key"] != key or (_col_cache.get("ref") is None or _col_cache["ref"]() is not segmap):
+        import weakref
+        _col_cache["key"], _col_cache["cols"] = key, {}
+        _col_cache["ref"] = weakref.ref(segmap)
+    cols = _col_cache["cols"]
+    if ("nearest", h, w, cpad) not in cols:
+        cols[("nearest", h, w, cpad)] = ops.seg_nearest(segmap, h, w, cpad)
+    return cols[("nearest", h, w, cpad)]
+
+
 def clear_seg_cache():
     _col_cache["key"], _col_cache["cols"] = None, {}
 
@@ -134,7 +147,10 @@ class SPADE(nn.Module):
             # forward) turns mlp_shared into a K=64 GEMM on the tensor-core path, forward and weight gradient
             col = seg_im2col_cached(segmap, h, w)
             return ops.SegConvFn.apply(col, conv.weight, conv.bias, L.ACT_RELU, True), True
-        return conv.forward_nhwc(ops.seg_nearest(segmap, h, w)), False
+        # wide label maps (e.g. 35 classes): channels zero-padded to a multiple of 64 so that mlp_shared is an ordinary
+        # tap convolution on the tensor cores, forward and weight gradient (K = 9 * 64)
+        cpad = -(-conv.in_channels // 64) * 64 if conv.in_channels >= 16 else 0
+        return conv.forward_nhwc(seg_nearest_cached(segmap, h, w, cpad)), False
 
     def gamma_beta(self, segmap, h, w):
         actv, fused_relu = self._actv(segmap, h, w)
@@ -143,7 +159,8 @@ class SPADE(nn.Module):
         return ops.tap_conv(actv, cfg, (self.mlp_gamma.weight, self.mlp_beta.weight), (self.mlp_gamma.bias, self.mlp_beta.bias))
 
     def modulate(self, x, segmap, style, act, up=False, sink=None):
-        """x NHWC bf16; style (B,2C) fp32 (s0|s1) ->  act(0.5*[norm(x)(1+gamma)+beta + x(1+s0)+s1]).
+        """x NHWC bf16; style (B,2C) fp32 (s0|s1) ->  act(0.5*[norm(x)(1+gamma)+beta + x(1+s0)+s1]);
+        style None -> plain SPADE: act(norm(x)(1+gamma)+beta)  (normalization.py:91-105).
         up: x is the half-resolution tensor whose nearest-2x up-sampling is the real input (never materialised)."""
         B, H, W, C = x.shape
         if up:
@@ -170,12 +187,23 @@ class SPADE(nn.Module):
         return ops.SpadeStyleFn.apply(x, gb, style, cfg, *bufs, up, sink)
 
     def forward(self, x, segmap):
-        # plain SPADE: out = norm(x)(1+gamma)+beta = 2*0.5*[...] with the style term cancelled (s0=-1, s1=0)
-        xn = ops.as_nhwc(x)
-        B, H, W, C = xn.shape
-        style = torch.cat([torch.full((B, C), -1.0, device=xn.device), torch.zeros(B, C, device=xn.device)], 1)
-        out = self.modulate(xn, segmap, style, L.ACT_NONE)
-        return ops.as_nchw_view(ops.AddFn.apply(out, out))
+        return ops.as_nchw_view(self.modulate(ops.as_nhwc(x), segmap, None, L.ACT_NONE))
+
+
+class SPADE_Block(nn.Module):
+    """The style-less counterpart of SPADE_STYLE_Block for the plain SPADE generator (BASELINE config 5): the block of
+    normalization.py:172-192 with the ApplyStyle half and the division by two removed, i.e. SPADE alone.  Same
+    `.spade.*` parameter names, no `.adain.*`."""
+
+    def __init__(self, fin, opt):
+        super().__init__()
+        self.spade = SPADE(opt.norm_G.replace('spectral', ''), fin, opt.semantic_nc)
+
+    def forward_nhwc(self, x, segmap, latent_style=None, act=L.ACT_NONE, up=False, sink=None):
+        return self.spade.modulate(x, segmap, None, act, up, sink)
+
+    def forward(self, x, segmap, latent_style=None):
+        return ops.as_nchw_view(self.forward_nhwc(ops.as_nhwc(x), segmap))
 
 
 class SPADE_STYLE_Block(nn.Module):

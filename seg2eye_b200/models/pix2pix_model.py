@@ -35,15 +35,11 @@ class Pix2PixModel(torch.nn.Module):
             return
         if not _opt(opt, 'no_vgg_loss', True):
             raise ValueError('VGG loss does not exist in the reference either (networks.VGGLoss is undefined)')
-        if _opt(opt, 'lambda_openeds'):
-            raise ValueError('lambda_openeds carries no gradient in the reference (postprocessor.py:72 .int()); unsupported')
         self.criterionGAN = networks.GANLoss(opt.gan_mode, opt=opt)
         self.criterionFeat = self.criterionL1 = networks.l1_loss
         self.criterionL2 = networks.mse_loss
-        if _opt(opt, 'lambda_style_feat') > 0:
-            self.criterion_style_feat = nn.MSELoss()
-        if _opt(opt, 'lambda_style_w') > 0:
-            self.criterion_style_w = nn.MSELoss()
+        self.criterionOpenEDS = networks.MSECalculator.calculate_mse_for_tensors
+        self.criterion_style_feat = self.criterion_style_w = ops.pair_mse
         if _opt(opt, 'lambda_gram') > 0:
             self.criterion_gram = networks.StyleLoss()
         self.reset_loss_log()
@@ -66,17 +62,20 @@ class Pix2PixModel(torch.nn.Module):
 
     def save(self, epoch):
         for net, tag in ((self.netG, 'G'), (self.netD, 'D'), (self.netE, 'E')):
-            util.save_network(net, tag, epoch, self.opt)
+            if net is not None:
+                util.save_network(net, tag, epoch, self.opt)
 
     def initialize_networks(self, opt):
         netG = networks.define_G(opt)
         netD = networks.define_D(opt) if opt.isTrain else None
-        netE = networks.define_E(opt)
+        # --netG spade: the original style-less SPADE generator (BASELINE config 5) has no style encoder
+        netE = networks.define_E(opt) if _opt(opt, 'netG', 'spadestyle') != 'spade' else None
         if not opt.isTrain or opt.continue_train:
             util.load_network(netG, 'G', opt.which_epoch, opt)
             if opt.isTrain:   # like the reference, test time keeps a freshly initialised style encoder
                 util.load_network(netD, 'D', opt.which_epoch, opt)
-                util.load_network(netE, 'E', opt.which_epoch, opt)
+                if netE is not None:
+                    util.load_network(netE, 'E', opt.which_epoch, opt)
         return netG, netD, netE
 
     def create_optimizers(self, opt):
@@ -86,7 +85,7 @@ class Pix2PixModel(torch.nn.Module):
         else:
             betas, g_lr, d_lr = (0, 0.9), opt.lr / 2, opt.lr * 2
         wd = _opt(opt, 'weight_decay', 0.0)
-        g_params = list(self.netG.parameters()) + list(self.netE.parameters())
+        g_params = list(self.netG.parameters()) + (list(self.netE.parameters()) if self.netE is not None else [])
         d_params = list(self.netD.parameters()) if opt.isTrain else []
         return (optim.Adam(g_params, lr=g_lr, betas=betas, weight_decay=wd),
                 optim.Adam(d_params, lr=d_lr, betas=betas, weight_decay=wd))
@@ -114,7 +113,8 @@ class Pix2PixModel(torch.nn.Module):
         """label -> int64 on the device -> one-hot (B, label_nc, H, W); `data` is updated in place like the reference's."""
         dev = self.device()
         data['label'] = data['label'].long().to(dev, non_blocking=True)
-        data['style_image'] = data['style_image'].to(dev, non_blocking=True)
+        if 'style_image' in data:      # (absent for the style-less generator, --netG spade)
+            data['style_image'] = data['style_image'].to(dev, non_blocking=True)
         lab = data['label']
         if lab.dim() == 3:   # (B,H,W) as the data loader collates it; the reference only handles B == 1 here
             lab = lab.unsqueeze(0) if lab.shape[0] == 1 else lab.unsqueeze(1)
@@ -122,7 +122,7 @@ class Pix2PixModel(torch.nn.Module):
         target = None
         if 'target' in data:
             target = data['target'] = data['target'].to(dev, non_blocking=True)
-        return seg, data['style_image'], target
+        return seg, data.get('style_image'), target
 
     # ------------------------------------------------------------------ losses
     def compute_generator_loss(self, input_semantics, style_image, target_image):
@@ -137,6 +137,12 @@ class Pix2PixModel(torch.nn.Module):
                 raw = crit(fake, target_image)
                 losses[key + '/weighted'] = raw * lam
                 self.add_to_loss_log(key + '/raw', raw.detach())
+        if _opt(opt, 'lambda_openeds'):
+            # (B,) values without a gradient: ImageProcessor.to_255imagebatch ends in .int() (postprocessor.py:72), so in the
+            # reference too this term only shifts the reported loss
+            raw = self.criterionOpenEDS(fake.detach(), target_image)
+            losses['openeds/weighted'] = raw * opt.lambda_openeds
+            self.add_to_loss_log('openeds/raw', raw)
         if _opt(opt, 'lambda_style_feat') or _opt(opt, 'lambda_style_w') or _opt(opt, 'lambda_gram'):
             w_fake, feats_fake = self.encode_w(fake.unsqueeze(1))
             extra = []
@@ -171,48 +177,50 @@ class Pix2PixModel(torch.nn.Module):
         return {'D/Fake': self.criterionGAN(pred_fake, False, for_discriminator=True),
                 'D/real': self.criterionGAN(pred_real, True, for_discriminator=True)}
 
-    def _per_level(self, crit, feats_fake, feats_real):
-        total = []
-        for lvl in range(len(feats_fake[0])):
-            total.append(crit(torch.stack([f[lvl].float() for f in feats_fake]),
-                              torch.stack([f[lvl].float() for f in feats_real])))
-        return torch.stack(total).sum()
-
     def _compute_style_feature_loss(self, features_fake, features_real):
-        return self._per_level(self.criterion_style_feat, features_fake, features_real)
+        """pix2pix_model.py:162-172: sum over the encoder levels of MSE(aggregated fake features, aggregated real
+        features) -- nothing is detached in the reference, so both sides receive gradients."""
+        return torch.stack([ops.pair_mse(f, r) for f, r in zip(features_fake, features_real)]).sum()
 
     def _compute_gram_loss(self, features_fake, features_real):
-        return self._per_level(self.criterion_gram, features_fake, features_real)
+        """pix2pix_model.py:174-184 + loss.py:177-200: per level MSE of the Gram matrices of the (B*C, h*w) feature
+        matrices, the real side detached (loss.py:198)."""
+        return torch.stack([self.criterion_gram(f, r, nhwc=True) for f, r in zip(features_fake, features_real)]).sum()
 
     # ------------------------------------------------------------------ style encoder
-    def _aggregate_tensor(self, tensor, dim=1):
+    def _aggregate_mode(self):
         how = self.opt.style_aggr_method
-        if how == 'mean':
-            return tensor.mean(dim=dim)
-        if how == 'max':
-            return tensor.max(dim=dim).values
-        raise ValueError(f"Aggregation method not found: {how}")
+        if how not in ('mean', 'max'):
+            raise ValueError(f"Aggregation method not found: {how}")
+        return 0 if how == 'mean' else 1
+
+    def _aggregate_tensor(self, tensor, dim=1):
+        """pix2pix_model.py:271-278 for a (G, ns, ...) tensor along dim 1 or a (ns, ...) tensor along dim 0."""
+        mode = self._aggregate_mode()
+        if dim == 0:
+            return ops.AggregateFn.apply(tensor, 1, tensor.shape[0], mode)[0]
+        assert dim == 1
+        G, ns = tensor.shape[:2]
+        return ops.AggregateFn.apply(tensor.reshape(G * ns, *tensor.shape[2:]), G, ns, mode)
 
     def _compute_multiple_netE(self, real_image):
-        """(B, ns, 1, H, W) -> mu (B, ns, w_dim).  The reference calls netE once per sample, advancing its spectral-norm
-        vectors once per call; ConvEncoder.forward_samples reproduces exactly that in one batched pass."""
+        """(B, ns, 1, H, W) -> mu (B, ns, w_dim) and the encoder's feature maps, each (B*ns, C, h, w).  The reference calls
+        netE once per sample, advancing its spectral-norm vectors once per call; ConvEncoder.forward_samples reproduces
+        exactly that in one batched pass."""
         n_b, ns = real_image.shape[:2]
-        if hasattr(self.netE, 'forward_samples'):
-            mu, _, feats = self.netE.forward_samples(real_image)
-            per_sample = [[f[b * ns:(b + 1) * ns] for f in feats] for b in range(n_b)]
-        else:
-            outs = [self.netE(real_image[b]) for b in range(n_b)]
-            mu = torch.stack([o[0] for o in outs], dim=0)
-            per_sample = [o[2] for o in outs]
+        mu, _, feats = self.netE.forward_samples(real_image)
         assert mu.shape == (n_b, ns, self.opt.w_dim)
-        return mu, per_sample
+        return mu, feats
 
     def _compute_aggregated_w(self, real_image):
+        """-> w (B, w_dim) and, when a style-feature / Gram loss needs them, one aggregated feature map per encoder level,
+        (B, h, w, C) fp32 (the reference keeps a per-sample list of (C, h, w) maps and stacks them per level later)."""
         mu, feats = self._compute_multiple_netE(real_image)
         w = self._aggregate_tensor(mu)
         agg = []
         if self.opt.isTrain and (_opt(self.opt, 'lambda_style_feat') or _opt(self.opt, 'lambda_gram')):
-            agg = [[self._aggregate_tensor(f.float(), dim=0) for f in sample] for sample in feats]
+            n_b, ns = real_image.shape[:2]
+            agg = [ops.AggregateFn.apply(ops.as_nhwc(f), n_b, ns, self._aggregate_mode()) for f in feats]
         return w, agg
 
     def encode_w(self, real_image):
@@ -224,6 +232,8 @@ class Pix2PixModel(torch.nn.Module):
         return self.netG(input_semantics, latent_style)
 
     def generate_fake(self, input_semantics, style_image):
+        if self.netE is None:       # plain SPADE generator: no style code
+            return self.netG(input_semantics), None, []
         w, feats = self.encode_w(style_image)
         return self.generate_fake_from_stylecode(input_semantics, w), w, feats
 
@@ -231,7 +241,8 @@ class Pix2PixModel(torch.nn.Module):
     def discriminate(self, input_semantics, fake_image, real_image):
         """cat([seg,fake],1) / cat([seg,real],1) / cat(.,0) of the reference as ONE layout kernel; channels are
         zero-padded to 16 so that D's first 4x4-s2 convolution is tensor-core shaped after space-to-depth."""
-        both = ops.MakeDInputFn.apply(input_semantics, fake_image, real_image, 16)
+        # (5 -> 16 channels for the 4-class OpenEDS maps; in general the next multiple of 16)
+        both = ops.MakeDInputFn.apply(input_semantics, fake_image, real_image, -(-(input_semantics.shape[1] + 1) // 16) * 16)
         out = self.netD.forward_nhwc(both)
         self._last_d_out = out
         return self.divide_pred(out)

@@ -537,10 +537,11 @@ def spade_conv_fused(actv, conv_cfg, weights, biases, x, style, cfg, running_mea
     formed in the tcgen05 accumulator and consumed in the epilogue -- gamma|beta never reach HBM (saves 8 of the 12 bytes
     per element that the convolution output + the modulation kernel move).  No autograd graph is built."""
     assert not torch.is_grad_enabled()
-    x, actv, style = _c(x), _c(actv), _c(style)
+    x, actv = _c(x), _c(actv)
+    style = _c(style) if style is not None else None      # None: plain SPADE (no style term, no 1/2)
     B, Hx, Wx, Cc = x.shape
     H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
-    assert actv.shape[:3] == (B, H, W) and style.shape == (B, 2 * Cc)
+    assert actv.shape[:3] == (B, H, W) and (style is None or style.shape == (B, 2 * Cc))
     mean, rstd, _ = spade_statistics(x, cfg, running_mean, running_var, nbt, up)
     st = L.stream()
     par = torch.empty(B, 4, Cc, dtype=F32, device=x.device)
@@ -552,6 +553,7 @@ def spade_conv_fused(actv, conv_cfg, weights, biases, x, style, cfg, running_mea
     d = _desc(B, H, W, actv.shape[3], H, W, 2 * Cc, taps, L.ACT_NONE)
     d.tile_w, d.tile_h, d.tile_b = tw, 128 // tw, 1
     d.spade_x, d.spade_par, d.spade_C, d.spade_act, d.spade_up = L.ptr(x), L.ptr(par), Cc, cfg.act, int(up)
+    d.spade_plain = int(style is None)
     out = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
     flops = 2.0 * B * H * W * 2 * Cc * weights[0].shape[1] * conv_cfg.kh * conv_cfg.kw
     _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(actv), L.ptr(wp), L.ptr(bias), None, L.ptr(out), L.IMPL_TC, st,
@@ -583,15 +585,17 @@ class SpadeStyleFn(torch.autograd.Function):
         ctx.sink, ctx.up = sink, up
         if sink is not None:
             sink.users += 1
-        x, gb, style = _c(x), _c(gb), _c(style)
+        x, gb = _c(x), _c(gb)
+        style = _c(style) if style is not None else None      # None: plain SPADE, out = act(norm(x)(1+gamma)+beta)
         B, Hx, Wx, Cc = x.shape
         H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
-        assert gb.shape == (B, H, W, 2 * Cc) and style.shape == (B, 2 * Cc) and style.dtype == F32
+        assert gb.shape == (B, H, W, 2 * Cc) and (style is None or (style.shape == (B, 2 * Cc) and style.dtype == F32))
         st = L.stream()
         mean, rstd, batch_stats = spade_statistics(x, cfg, running_mean, running_var, nbt, up)
         out = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
         # backward needs only the sign of `out` (LeakyReLU mask): one bit per element, written by the forward kernel
         amask = None
+        ctx.plain = style is None
         if cfg.act != L.ACT_NONE and any(ctx.needs_input_grad[:3]):
             amask = torch.empty(B * H * W * (Cc // 8), dtype=torch.uint8, device=x.device)
         _timed_call("norm", 8.0 * B * H * W * Cc, "s2e_spade_style_fwd", L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
@@ -622,7 +626,7 @@ class SpadeStyleFn(torch.autograd.Function):
             if last:
                 sink.seen = 0
         dgb = torch.empty_like(gb)
-        dstyle = torch.empty_like(style)
+        dstyle = torch.empty_like(style) if style is not None else None
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
         L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
                L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
@@ -666,11 +670,12 @@ class SpadeConvFn(torch.autograd.Function):
         ctx.sink, ctx.up = sink, up
         if sink is not None:
             sink.users += 1
-        actv, x, style = _c(actv), _c(x), _c(style)
+        actv, x = _c(actv), _c(x)
+        style = _c(style) if style is not None else None      # None: plain SPADE
         B, Hx, Wx, Cc = x.shape
         H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
         Ca = actv.shape[3]
-        assert actv.shape == (B, H, W, Ca) and style.shape == (B, 2 * Cc) and cfg.training
+        assert actv.shape == (B, H, W, Ca) and (style is None or style.shape == (B, 2 * Cc)) and cfg.training
         mean, rstd, _ = spade_statistics(x, cfg, running_mean, running_var, nbt, up)
         st = L.stream()
         par = torch.empty(B, 4, Cc, dtype=F32, device=x.device)
@@ -686,6 +691,7 @@ class SpadeConvFn(torch.autograd.Function):
         tw = _fused_tile_w(W)
         d.tile_w, d.tile_h, d.tile_b = tw, 128 // tw, 1
         d.spade_x, d.spade_par, d.spade_C, d.spade_act, d.spade_up = L.ptr(x), L.ptr(par), Cc, cfg.act, int(up)
+        d.spade_plain = int(style is None)
         d.spade_gamma_out, d.spade_mask_out = L.ptr(gamma), L.ptr(amask)
         flops = 2.0 * B * H * W * 2 * Cc * Ca * conv_cfg.kh * conv_cfg.kw
         _timed_call("tc", flops, "s2e_tapconv_fwd", d, L.ptr(actv), L.ptr(wp), L.ptr(bias), None, L.ptr(out), L.IMPL_TC, st,
@@ -718,7 +724,7 @@ class SpadeConvFn(torch.autograd.Function):
             if last:
                 sink.seen = 0
         dgb = torch.empty(B, H, W, 2 * Cc, dtype=BF16, device=x.device)
-        dstyle = torch.empty_like(style)
+        dstyle = torch.empty_like(style) if style is not None else None
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
         L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gamma), L.ptr(style), L.ptr(mean),
                L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
@@ -965,12 +971,15 @@ def one_hot(label, nc):
     return out
 
 
-def seg_nearest(seg, hd, wd):
-    """F.interpolate(seg, size, mode='nearest') fused with the NCHW fp32 -> NHWC bf16 layout change."""
+def seg_nearest(seg, hd, wd, cpad=0):
+    """F.interpolate(seg, size, mode='nearest') fused with the NCHW fp32 -> NHWC bf16 layout change.
+    cpad > C: the output carries cpad channels, the extra ones zero (a 35-class map padded to 64 channels runs mlp_shared /
+    G.fc as ordinary 64-channel tap convolutions on the tensor cores)."""
     seg = _c(seg.detach().float())
     B, Cc, Hs, Ws = seg.shape
-    out = torch.empty(B, hd, wd, Cc, dtype=BF16, device=seg.device)
-    L.call("s2e_seg_nearest_nhwc", L.ptr(seg), B, Cc, Hs, Ws, hd, wd, Cc, L.ptr(out), L.stream())
+    cp = max(cpad, Cc)
+    out = torch.empty(B, hd, wd, cp, dtype=BF16, device=seg.device)
+    L.call("s2e_seg_nearest_nhwc", L.ptr(seg), B, Cc, Hs, Ws, hd, wd, cp, L.ptr(out), L.stream())
     return out
 
 
@@ -1178,3 +1187,187 @@ class HalvesLossFn(torch.autograd.Function):
         L.call("s2e_reduce_loss_bwd", L.ptr(flat), L.ptr(flat[n2:]), n2, ctx.f32, ctx.kind, ctx.coef, 0.0, L.ptr(gout),
                L.ptr(dflat), 0, L.stream())
         return dx, None, None
+
+
+class PairLossFn(torch.autograd.Function):
+    """coef * sum f(a - b) with gradients to BOTH operands (nn.MSELoss / nn.L1Loss between two live tensors: the style
+    losses of pix2pix_model.py:162-184,212-229, whose "real" side is not detached in the reference)."""
+
+    @staticmethod
+    def forward(ctx, a, b, kind, coef):
+        a, b = _c(a), _c(b)
+        assert a.shape == b.shape and a.dtype == b.dtype and a.dtype in (F32, BF16)
+        f32 = int(a.dtype == F32)
+        out = torch.empty(1, dtype=F32, device=a.device)
+        L.call("s2e_reduce_loss", L.ptr(a), L.ptr(b), a.numel(), f32, kind, coef, 0.0, L.ptr(out), 0, L.stream())
+        ctx.kind, ctx.coef, ctx.f32 = kind, coef, f32
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        gout = _c(gout.float())
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            L.call("s2e_reduce_loss_bwd", L.ptr(a), L.ptr(b), a.numel(), ctx.f32, ctx.kind, ctx.coef, 0.0, L.ptr(gout), L.ptr(da), 0, L.stream())
+        if ctx.needs_input_grad[1]:     # f is even: d/db f(a - b) = d/da f(b - a)
+            db = torch.empty_like(b)
+            L.call("s2e_reduce_loss_bwd", L.ptr(b), L.ptr(a), a.numel(), ctx.f32, ctx.kind, ctx.coef, 0.0, L.ptr(gout), L.ptr(db), 0, L.stream())
+        return da, db, None, None
+
+
+def pair_mse(a, b):
+    """nn.MSELoss()(a, b) with gradients to both sides."""
+    return PairLossFn.apply(a, b, L.RED_L2, 1.0 / a.numel()).view(())
+
+
+class AggregateFn(torch.autograd.Function):
+    """Pix2PixModel._aggregate_tensor (pix2pix_model.py:271-278) over the ns style images of each sample:
+    x (G * ns, ...) fp32 or bf16 (the ns images of a sample adjacent)  ->  (G, ...) fp32, mean (mode 0) or max (mode 1)."""
+
+    @staticmethod
+    def forward(ctx, x, G, ns, mode):
+        x = _c(x)
+        assert x.shape[0] == G * ns
+        n = x.numel() // (G * ns)
+        out = torch.empty((G,) + tuple(x.shape[1:]), dtype=F32, device=x.device)
+        arg = torch.empty(G * n, dtype=torch.uint8, device=x.device) if mode == 1 else None
+        L.call("s2e_aggregate_fwd", L.ptr(x), int(x.dtype == F32), G, ns, n, mode, L.ptr(out), L.ptr(arg), L.stream())
+        ctx.dims = (G, ns, n, mode, x.shape, x.dtype)
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        G, ns, n, mode, shape, dtype = ctx.dims
+        (arg,) = ctx.saved_tensors
+        dout = _c(dout.float())
+        dx = torch.empty(shape, dtype=dtype, device=dout.device)
+        L.call("s2e_aggregate_bwd", L.ptr(dout), L.ptr(arg), int(dtype == F32), G, ns, n, mode, L.ptr(dx), L.stream())
+        return dx, None, None, None
+
+
+def to255_resize(images, size=(640, 400), target=None):
+    """ImageProcessor.to_255resized_imagebatch (data/postprocessor.py:98-102) on the device: fp32 (N,1,h,w) in [-1,1] ->
+    int32 (N,1,H,W) in [0,255] (cv2 INTER_LINEAR in float64, *255, .int(): bit-exact integers).  With an int target of the
+    output's shape also returns the per-image OpenEDS score (MSECalculator.calculate_mse_for_images)."""
+    x = _c(images.detach().float())
+    N, C, h, w = x.shape
+    H, W = size
+    out = torch.empty(N, C, H, W, dtype=torch.int32, device=x.device)
+    if target is None:
+        L.call("s2e_to255_resize", L.ptr(x), N * C, h, w, H, W, 0, None, L.ptr(out), None, None, L.stream())
+        return out
+    t = _c(target.to(device=x.device, dtype=torch.int32))
+    assert t.shape == out.shape
+    sq = torch.empty(N * C, dtype=torch.int64, device=x.device)
+    score = torch.empty(N * C, dtype=F32, device=x.device)
+    L.call("s2e_to255_resize", L.ptr(x), N * C, h, w, H, W, 0, L.ptr(t), L.ptr(out), L.ptr(sq), L.ptr(score), L.stream())
+    return out, score
+
+
+def to255(images):
+    """ImageProcessor.to_255imagebatch on an fp32 tensor (no resize, fp32 arithmetic): ((x + 1) * 255 / 2).int()."""
+    x = _c(images.detach().float())
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    N, C, h, w = x.shape
+    out = torch.empty(N, C, h, w, dtype=torch.int32, device=x.device)
+    L.call("s2e_to255_resize", L.ptr(x), N * C, h, w, h, w, 1, None, L.ptr(out), None, None, L.stream())
+    return out
+
+
+def openeds_score(produced, target):
+    """MSECalculator.calculate_mse_for_images (loss.py:113-133): per image sqrt(sum (p - t)^2) / (H * W) for two integer
+    (N,1,H,W) batches in [0,255]; the sum of squares is an exact 64-bit integer."""
+    p = _c(produced.to(torch.int32))
+    t = _c(target.to(device=p.device, dtype=torch.int32))
+    assert p.shape == t.shape and p.dim() == 4
+    N, C, H, W = p.shape
+    sq = torch.empty(N * C, dtype=torch.int64, device=p.device)
+    score = torch.empty(N * C, dtype=F32, device=p.device)
+    L.call("s2e_openeds_score", L.ptr(p), L.ptr(t), N * C, H, W, L.ptr(sq), L.ptr(score), L.stream())
+    return score
+
+
+# ------------------------------------------------------------------------------------------------ Gram / style loss
+def _pixel_major(x_bhwc):
+    """(B, h, w, C) fp32 contiguous -> (1, h, w, C*B) bf16: pixels x all (channel, sample) pairs, channel index c*B + b.
+    Read as NCHW with N=1, C=B, H=h*w, W=C, this is exactly the NCHW->NHWC layout kernel."""
+    B, h, w, Cc = x_bhwc.shape
+    y = torch.empty(1, h, w, Cc * B, dtype=BF16, device=x_bhwc.device)
+    L.call("s2e_nchw_f32_to_nhwc_bf16", L.ptr(x_bhwc), 1, B, h * w, Cc, L.ptr(y), L.stream())
+    return y
+
+
+def _gram_raw(xp):
+    """xp (1, h, w, M) bf16 -> G[i][j] = sum_p xp[p][i] xp[p][j] (fp32, M x M): the weight-gradient GEMM of a 1x1
+    convolution whose input and output gradient are both xp (pixels are the contraction axis)."""
+    _, h, w, M = xp.shape
+    G = torch.zeros(M * M, dtype=F32, device=xp.device)
+    d = _desc(1, h, w, M, h, w, M, [(0, 0)], L.ACT_NONE)
+    impl = _pick(M >= 64 and M % 8 == 0)
+    flops = 2.0 * h * w * M * M
+    if impl == L.IMPL_TC:
+        _timed_call("tc", flops, "s2e_tapconv_wgrad", d, L.ptr(xp), L.ptr(xp), L.ptr(G), impl, L.stream(), tag="gram %dx%d M%d" % (h, w, M))
+    else:
+        L.call("s2e_tapconv_wgrad", d, L.ptr(xp), L.ptr(xp), L.ptr(G), impl, L.stream())
+    return G.view(M, M)
+
+
+class GramLossFn(torch.autograd.Function):
+    """StyleLoss (loss.py:177-200) on two feature batches given as (B, h, w, C) fp32:
+    mse(gram(fake), gram(real).detach()) with gram(x) = F F^T / (B*C*h*w), F = x viewed as (B*C, h*w).
+    Forward: two Gram GEMMs on the tensor cores (weight-gradient kernel, K = h*w) + one reduction.  Backward:
+    dF = 2 D F with D = dL/dG (symmetric), i.e. a 1x1 convolution over the same pixel-major tensor."""
+
+    @staticmethod
+    def forward(ctx, ff, fr):
+        ff, fr = _c(ff.float()), _c(fr.detach().float())
+        B, h, w, Cc = ff.shape
+        M = B * Cc
+        xf, xr = _pixel_major(ff), _pixel_major(fr)
+        Gf, Gr = _gram_raw(xf), _gram_raw(xr)
+        norm = float(B * Cc * h * w)
+        coef = 1.0 / (norm * norm * M * M)
+        out = torch.empty(1, dtype=F32, device=ff.device)
+        L.call("s2e_reduce_loss", L.ptr(Gf), L.ptr(Gr), M * M, 1, L.RED_L2, coef, 0.0, L.ptr(out), 0, L.stream())
+        ctx.dims, ctx.coef = (B, h, w, Cc), coef
+        ctx.save_for_backward(xf, Gf, Gr)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        xf, Gf, Gr = ctx.saved_tensors
+        B, h, w, Cc = ctx.dims
+        M = B * Cc
+        st = L.stream()
+        gout = _c(gout.float())
+        D = torch.empty_like(Gf)     # dL/dG_raw = gout * coef * 2 (Gf - Gr), symmetric
+        L.call("s2e_reduce_loss_bwd", L.ptr(Gf), L.ptr(Gr), M * M, 1, L.RED_L2, ctx.coef, 0.0, L.ptr(gout), L.ptr(D), 0, st)
+        wp = torch.empty(M * M, dtype=BF16, device=D.device)
+        L.call("s2e_pack_weight", L.ptr(D), M, M, 1, 1, 1, 0, 0, M, 0, 0, L.ptr(wp), st)
+        two = torch.full((1,), 2.0, dtype=F32, device=D.device)
+        dxf = torch.empty_like(xf)
+        d = _desc(1, h, w, M, h, w, M, [(0, 0)], L.ACT_NONE)
+        impl = _pick(M % 64 == 0)
+        L.call("s2e_tapconv_fwd", d, L.ptr(xf), L.ptr(wp), None, L.ptr(two), L.ptr(dxf), impl, st)
+        dff = torch.empty(B, h, w, Cc, dtype=F32, device=D.device)
+        L.call("s2e_nhwc_bf16_to_nchw_f32", L.ptr(dxf), 1, B, h * w, Cc, L.ptr(dff), st)
+        return dff, None
+
+
+def gram_loss(ff, fr):
+    return GramLossFn.apply(ff, fr).view(())
+
+
+def gram_matrix(x_nchw):
+    """loss.py:177-189 for an NCHW tensor (a, b, c, d) on the device: (a*b, a*b) fp32 = F F^T / (a*b*c*d) through the
+    tensor-core Gram GEMM (inputs rounded to bf16)."""
+    x = _c(x_nchw.detach().float())
+    a, b, c, d = x.shape
+    xp = torch.empty(1, c, d, a * b, dtype=BF16, device=x.device)
+    L.call("s2e_nchw_f32_to_nhwc_bf16", L.ptr(x), 1, a * b, c, d, L.ptr(xp), L.stream())
+    return _gram_raw(xp) / float(a * b * c * d)

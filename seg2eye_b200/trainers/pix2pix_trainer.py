@@ -36,7 +36,7 @@ class Pix2PixTrainer():
         if opt.isTrain:
             self.optimizer_G, self.optimizer_D = self.pix2pix_model_on_one_gpu.create_optimizers(opt)
             self.old_lr = opt.lr
-            self.reducer_G = parallel.GradReducer(list(m.netG.parameters()) + list(m.netE.parameters()))
+            self.reducer_G = parallel.GradReducer(list(m.netG.parameters()) + (list(m.netE.parameters()) if m.netE is not None else []))
             self.reducer_D = parallel.GradReducer(list(m.netD.parameters()))
         self._graphs = False
 
@@ -93,9 +93,10 @@ class Pix2PixTrainer():
         m.reset_loss_log()
         gc.collect()
         self._static = {'label': example_data['label'].long().to(dev).clone(),
-                        'style_image': example_data['style_image'].float().to(dev).clone(),
                         'target': example_data['target'].float().to(dev).clone()}
-        tensors = [t for net in (m.netG, m.netD, m.netE) for t in list(net.parameters()) + list(net.buffers())]
+        if 'style_image' in example_data:
+            self._static['style_image'] = example_data['style_image'].float().to(dev).clone()
+        tensors = [t for net in (m.netG, m.netD, m.netE) if net is not None for t in list(net.parameters()) + list(net.buffers())]
         opts = (self.optimizer_G, self.optimizer_D)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

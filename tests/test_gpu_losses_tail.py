@@ -1,0 +1,199 @@
+"""GPU parity of the optional loss branches and of the inference / validation tail:
+  * style aggregation (mean | max), two-sided MSE, Gram matrix / StyleLoss on the tensor-core GEMM -- against plain fp32
+    PyTorch statements of the same ops;
+  * one full trainer iteration with the style_w / style_feat / Gram / openEDS losses, `max` aggregation and the WGAN
+    mode -- against the losses the UNMODIFIED reference recorded (tests/golden/ref_variants*.npz);
+  * bilinear-to-640x400 + 0..255 + .int() + OpenEDS score -- BIT-EXACT against the reference's cv2-based tail
+    (tests/golden/ref_tail.npz: SHA-256 over every integer pixel)."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import seg2eye_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------------------------------ validation tail
+def test_to255_resize_bit_exact_vs_reference_fixture():
+    from oracle.make_golden_tail import CASES, digest, tail_inputs
+    from seg2eye_b200 import ops, postprocessor
+    from seg2eye_b200.models import networks
+    ref = np.load(os.path.join(GOLD, "ref_tail.npz"))
+    for name in CASES:
+        fake, target = tail_inputs(name)
+        got, score = ops.to255_resize(fake.cuda(), (640, 400), target=target.cuda())
+        assert got.dtype == torch.int32 and got.shape == (fake.shape[0], 1, 640, 400)
+        g = got.cpu().numpy()
+        assert np.array_equal(g.reshape(-1)[::997].astype(np.uint8), ref[name + "|sub"]), name
+        assert np.array_equal(digest(g), ref[name + "|sha256"]), name             # every pixel
+        assert np.array_equal(g, O.to_255_resized(fake).numpy())                    # and the oracle's restatement
+        np.testing.assert_allclose(score.cpu().numpy(), ref[name + "|errors"], rtol=2e-6)
+        # the reference-named entry points on CUDA tensors
+        again = postprocessor.ImageProcessor.to_255resized_imagebatch(fake.cuda())
+        assert torch.equal(again, got)
+        errs = networks.MSECalculator.calculate_mse_for_images(got, target.cuda())
+        np.testing.assert_allclose(errs.cpu().numpy(), ref[name + "|errors"], rtol=2e-6)
+    rng = np.random.Generator(np.random.PCG64(77))
+    a = torch.from_numpy(rng.uniform(-1, 1, size=(3, 1, 64, 48)).astype(np.float32))
+    b = torch.from_numpy(rng.uniform(-1, 1, size=(3, 1, 64, 48)).astype(np.float32))
+    assert np.array_equal(digest(ops.to255(a.cuda()).cpu().numpy()), ref["tensors|sha256"])
+    errs = networks.MSECalculator.calculate_mse_for_tensors(a.cuda(), b.cuda())
+    np.testing.assert_allclose(errs.cpu().numpy(), ref["tensors|errors"], rtol=2e-6)
+    with pytest.raises(AssertionError):
+        networks.MSECalculator.calculate_mse_for_tensors(2 * a.cuda(), b.cuda())
+
+
+def test_validation_tail_through_the_model():
+    """postprocessor.validation_tail == Tester.run_batch: inference -> 640x400 integers -> per-image error, on the device."""
+    from seg2eye_b200 import postprocessor
+    from seg2eye_b200.models.pix2pix_model import Pix2PixModel
+    oopt = O.make_opt(ngf=16, ndf=16)
+    d = vars(oopt).copy()
+    d.update(gpu_ids=[0], init_type="xavier", init_variance=0.02, netD_subarch="n_layer", continue_train=False,
+             which_epoch="latest", checkpoints_dir="/tmp/s2e_ckpt", name="t", no_vgg_loss=True, netG="spadestyle", netD="multiscale")
+    m = Pix2PixModel(SimpleNamespace(**d))
+    sdG, sdE = O.synth_state(O.generator_shapes(oopt), 5), O.synth_state(O.encoder_shapes(oopt), 6)
+    m.netG.load_state_dict({k: v.clone() for k, v in sdG.items()})
+    m.netE.load_state_dict({k: v.clone() for k, v in sdE.items()})
+    m.cuda().train()
+    batch = O.synth_batch(oopt, 2, 7)
+    rng = np.random.Generator(np.random.PCG64(8))
+    data = {"label": batch["label"], "style_image": batch["style_image"],
+            "target_original": torch.from_numpy(rng.integers(0, 256, size=(2, 640, 400)).astype(np.int32))}
+    errors, fake, fake_resized = postprocessor.validation_tail(m, data)
+    assert fake.shape == (2, 1, 320, 256) and fake_resized.shape == (2, 1, 640, 400) and fake_resized.dtype == torch.int32
+    want = O.to_255_resized(fake.cpu())
+    assert torch.equal(fake_resized.cpu(), want)
+    ref_err = O.mse_for_images(want, data["target_original"].unsqueeze(1))
+    np.testing.assert_allclose(errors.cpu().numpy(), ref_err.numpy(), rtol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------ aggregation / pair loss / Gram
+@pytest.mark.parametrize("mode,dtype", [(0, torch.float32), (1, torch.float32), (0, torch.bfloat16), (1, torch.bfloat16)])
+def test_aggregate_fwd_bwd(mode, dtype):
+    from seg2eye_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    G, ns = 3, 4
+    x = torch.randn(G * ns, 5, 7, 8, generator=g).to(dtype)
+    xr = x.float().view(G, ns, 5, 7, 8).clone().requires_grad_()
+    ref = xr.mean(1) if mode == 0 else xr.max(1).values
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    xc = x.cuda().requires_grad_()
+    out = ops.AggregateFn.apply(xc, G, ns, mode)
+    out.backward(dy.cuda())
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    assert rel(out, ref) < 1e-6
+    assert rel(xc.grad.float(), xr.grad.view(G * ns, 5, 7, 8)) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+def test_pair_mse_gradients_to_both_sides():
+    from seg2eye_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    a, b = torch.randn(2, 9, 11, 16, generator=g), torch.randn(2, 9, 11, 16, generator=g)
+    ar, br = a.clone().requires_grad_(), b.clone().requires_grad_()
+    (F.mse_loss(ar, br) * 3).backward()
+    ac, bc = a.cuda().requires_grad_(), b.cuda().requires_grad_()
+    l = ops.pair_mse(ac, bc)
+    (l * 3).backward()
+    assert abs(float(l) - float(F.mse_loss(a, b))) < 1e-5
+    assert rel(ac.grad, ar.grad) < 1e-5 and rel(bc.grad, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,h,w", [(2, 16, 12, 10), (2, 64, 16, 16), (1, 128, 8, 8), (3, 64, 32, 32)])
+def test_gram_matrix_and_style_loss(B, C, h, w):
+    """gram_matrix / StyleLoss (loss.py:177-200): tensor-core Gram GEMM (SIMT below 64 rows) vs torch.mm, forward and the
+    gradient w.r.t. the predicted features."""
+    from seg2eye_b200 import ops
+    from seg2eye_b200.models import networks
+    bf = lambda t: t.to(torch.bfloat16).float()
+    g = torch.Generator().manual_seed(5)
+    xf, xr = bf(torch.randn(B, C, h, w, generator=g)), bf(torch.randn(B, C, h, w, generator=g))
+    gm = networks.gram_matrix(xf.cuda())
+    assert rel(gm, O.gram_matrix(xf)) < 1e-5
+    pr = xf.clone().requires_grad_()
+    lref = F.mse_loss(O.gram_matrix(pr), O.gram_matrix(xr).detach())
+    lref.backward()
+    pc, rc = xf.cuda().requires_grad_(), xr.cuda().requires_grad_()
+    l = networks.StyleLoss()(pc, rc)
+    l.backward()
+    assert abs(float(l) - float(lref)) <= 1e-4 * abs(float(lref))
+    assert rc.grad is None
+    assert rel(pc.grad, pr.grad) < 1e-2, rel(pc.grad, pr.grad)      # D and dF pass through bf16
+    # NHWC entry used by Pix2PixModel
+    p2 = xf.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_()
+    l2 = ops.gram_loss(p2, xr.permute(0, 2, 3, 1).contiguous().cuda())
+    l2.backward()
+    assert abs(float(l2) - float(lref)) <= 1e-4 * abs(float(lref))
+    assert rel(p2.grad.permute(0, 3, 1, 2), pr.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------ trainer iterations vs the reference
+def _opts(over):
+    from oracle.make_golden import SMALL
+    o = O.make_opt(**{**SMALL, **over})
+    d = vars(o).copy()
+    base = dict(gpu_ids=[0], init_type="xavier", init_variance=0.02, netD_subarch="n_layer", continue_train=False,
+                which_epoch="latest", checkpoints_dir="/tmp/s2e_ckpt", name="t", no_vgg_loss=True, lambda_openeds=0.0,
+                lambda_style_w=0.0, lambda_style_feat=0.0, lambda_gram=0.0, netG="spadestyle", netD="multiscale")
+    d = {**base, **d}
+    return o, SimpleNamespace(**d)
+
+
+def _iteration(over):
+    from oracle.make_golden import SEEDS
+    from seg2eye_b200.trainers.pix2pix_trainer import Pix2PixTrainer
+    oopt, opt = _opts(over)
+    tr = Pix2PixTrainer(opt)
+    m = tr.pix2pix_model
+    for net, k, f in ((m.netG, "G", O.generator_shapes), (m.netD, "D", O.discriminator_shapes), (m.netE, "E", O.encoder_shapes)):
+        net.load_state_dict({a: b.clone() for a, b in O.synth_state(f(oopt), SEEDS[k]).items()})
+        net.cuda()
+    batch = O.synth_batch(oopt, 2, SEEDS["batch"])
+    data = {k: v.clone() for k, v in batch.items()}
+    tr.run_generator_one_step(data)
+    tr.run_discriminator_one_step(data)
+    return tr
+
+
+def _check(tr, ref, name, loose=()):
+    losses = tr.get_latest_losses()
+    keys = [k.split("|")[2] for k in ref.files if k.startswith(name + "|loss|") and not k.endswith("/raw")]
+    assert sorted(keys) == sorted(losses), (keys, sorted(losses))
+    for k in keys:
+        want = ref["%s|loss|%s" % (name, k)]
+        got = losses[k].detach().reshape(-1).cpu().numpy()
+        assert got.shape == want.shape, (k, got.shape, want.shape)
+        tol = 5e-2 if k in loose else 2e-2
+        assert np.all(np.abs(got - want) <= tol * np.abs(want) + (2e-2 if k == "GAN" else 0.0)), (k, got, want)
+
+
+@pytest.mark.parametrize("name", ["style_losses", "style_mean", "openeds"])
+def test_iteration_with_style_gram_openeds_losses_vs_reference(name):
+    from oracle.make_golden_variants import VARIANTS2
+    ref = np.load(os.path.join(GOLD, "ref_variants2.npz"))
+    tr = _iteration(VARIANTS2[name][1])
+    # the Gram / feature losses are quadratic in differences of nearly equal bf16 features: 5e-2
+    _check(tr, ref, name, loose=("gram/weighted", "style_feat/weighted"))
+    log = tr.pix2pix_model.get_loss_log()
+    for k in ref.files:
+        if k.startswith(name + "|loss|") and k.endswith("/raw"):
+            assert k.split("|")[2] in log, k
+
+
+@pytest.mark.parametrize("name", ["aggr_max", "gan_w"])
+def test_iteration_max_aggregation_and_wgan_vs_reference(name):
+    from oracle.make_golden_variants import VARIANTS
+    ref = np.load(os.path.join(GOLD, "ref_variants.npz"))
+    _check(_iteration(VARIANTS[name][1]), ref, name)

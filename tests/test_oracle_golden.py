@@ -181,3 +181,79 @@ def test_option_variants_one_iteration(name):
     close(sds["G"]["conv_img.weight"], ref[name + "|post_G_conv_img.weight"], tol=5e-4)
     close(sds["G"]["up_1.conv_0.weight_u"], ref[name + "|post_G_up_1.conv_0.weight_u"], tol=5e-4)
     close(sds["D"]["discriminator_1.model4.0.bias"], ref[name + "|post_D_model4_bias"], tol=5e-4, atol=1e-7)
+
+
+def _variant2_names():
+    from oracle.make_golden_variants import VARIANTS2
+    return sorted(VARIANTS2)
+
+
+@pytest.mark.parametrize("name", _variant2_names())
+def test_style_gram_openeds_losses_one_iteration(name):
+    """The optional loss branches of compute_generator_loss (pix2pix_model.py:209-231: openEDS, style_w, style_feat, Gram;
+    max / mean aggregation of the encoder features): oracle == the UNMODIFIED reference trainer, one G + D iteration
+    (fixture: oracle/make_golden_variants.py --second)."""
+    from oracle.make_golden import SEEDS, SMALL
+    from oracle.make_golden_variants import VARIANTS2
+    ref = np.load(os.path.join(GOLD, "ref_variants2.npz"))
+    oopt = O.make_opt(**{**SMALL, **VARIANTS2[name][1]})
+    sds = dict(G=O.synth_state(O.generator_shapes(oopt), SEEDS["G"]), D=O.synth_state(O.discriminator_shapes(oopt), SEEDS["D"]),
+               E=O.synth_state(O.encoder_shapes(oopt), SEEDS["E"]))
+    batch = O.synth_batch(oopt, 2, SEEDS["batch"])
+    tr = O.OracleTrainer(sds["G"], sds["D"], sds["E"], oopt)
+    tr.run_generator_one_step(batch)
+    tr.run_discriminator_one_step(batch)
+    losses = {**tr.g_losses, **tr.d_losses}
+    keys = [k.split("|")[2] for k in ref.files if k.startswith(name + "|loss|") and not k.endswith("/raw")]
+    assert sorted(keys) == sorted(losses), (keys, sorted(losses))
+    for k in keys:
+        np.testing.assert_allclose(losses[k].detach().reshape(-1).numpy(), ref["%s|loss|%s" % (name, k)], rtol=3e-4, atol=2e-5, err_msg=k)
+    s, st = sub(tr.generated)
+    close(s, ref[name + "|generated_sub"], tol=5e-4)
+    # the style losses reach the ENCODER through both the real and the fake features: its weights after the step pin that
+    close(sds["G"]["conv_img.weight"], ref[name + "|post_G_conv_img.weight"], tol=5e-4)
+    close(sds["G"]["up_1.conv_0.weight_u"], ref[name + "|post_G_up_1.conv_0.weight_u"], tol=5e-4)
+
+
+def test_validation_tail_bit_exact_vs_reference_fixture():
+    """oracle.to_255_resized / mse_for_images / to_255 == the reference's ImageProcessor.to_255resized_imagebatch (cv2
+    INTER_LINEAR in float64, *255, .int()) and MSECalculator on the fixture inputs: every integer pixel (SHA-256 of the
+    full result) and the per-image errors (fixture: oracle/make_golden_tail.py)."""
+    from oracle.make_golden_tail import CASES, digest, tail_inputs
+    ref = np.load(os.path.join(GOLD, "ref_tail.npz"))
+    for name in CASES:
+        fake, target = tail_inputs(name)
+        got = O.to_255_resized(fake)
+        assert got.dtype == torch.int32 and got.shape == (fake.shape[0], 1, 640, 400)
+        assert np.array_equal(got.numpy().reshape(-1)[::997].astype(np.uint8), ref[name + "|sub"]), name
+        assert np.array_equal(digest(got.numpy()), ref[name + "|sha256"]), name
+        np.testing.assert_allclose(O.mse_for_images(got, target).numpy(), ref[name + "|errors"], rtol=1e-6)
+    rng = np.random.Generator(np.random.PCG64(77))
+    a = torch.from_numpy(rng.uniform(-1, 1, size=(3, 1, 64, 48)).astype(np.float32))
+    b = torch.from_numpy(rng.uniform(-1, 1, size=(3, 1, 64, 48)).astype(np.float32))
+    assert np.array_equal(digest(O.to_255(a).numpy()), ref["tensors|sha256"])
+    np.testing.assert_allclose(O.mse_for_images(O.to_255(a), O.to_255(b)).numpy(), ref["tensors|errors"], rtol=1e-6)
+
+
+def test_spade_layer_with_35_classes_vs_reference_fixture():
+    """BASELINE config 5 per-layer pin: oracle.spade == the reference's SPADE module (normalization.py:63-105) with
+    label_nc = 35, BatchNorm and InstanceNorm statistics, output / input gradient / mlp_shared weight gradient / running_var
+    (fixture: oracle/make_golden_spade35.py)."""
+    from oracle.make_golden_spade35 import CASES, inputs
+    ref = np.load(os.path.join(GOLD, "ref_spade35.npz"))
+    for name, (cfg, c, nc, _) in CASES.items():
+        x, seg, sd = inputs(name)
+        sd = {"L." + k: v.clone() for k, v in sd.items()}
+        for k, v in sd.items():
+            if v.dtype == torch.float32 and "running" not in k:
+                v.requires_grad_(True)
+        xr = x.clone().requires_grad_()
+        y = O.spade(sd, "L", xr, seg, instance="instance" in cfg)
+        y.square().mean().backward()
+        s, st = sub(y)
+        close(s, ref[name + "|out_sub"], tol=2e-5)
+        close(st[:2], ref[name + "|out_stat"][:2], tol=2e-5)
+        close(sub(xr.grad)[0], ref[name + "|dx_sub"], tol=2e-4)
+        close(sub(sd["L.mlp_shared.0.weight"].grad)[0], ref[name + "|dw_shared_sub"], tol=2e-4)
+        if "batch" in cfg:
+            close(sd["L.param_free_norm.running_var"], ref[name + "|running_var"], tol=1e-5)
