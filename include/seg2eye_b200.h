@@ -113,6 +113,11 @@ typedef struct {
   int spade_plain;               /* != 0: plain SPADE (normalization.py:91-105 without the ApplyStyle half): the epilogue writes
                                     act(norm(x) (1 + gamma) + beta) -- no style term, no factor 1/2 (s2e_spade_params with
                                     style == NULL zeroes the style rows of `spade_par`) */
+  /* image head (generator.py:97-99 conv_img -> tanh, 64 -> 1 channel, 3x3; CUDA-core tile kernel only): */
+  float* img_out;                /* != NULL: tanh(conv) is written here as fp32 (B,1,H,W); `y` is not written */
+  const float* img_target;       /* nullable: the target image, same shape */
+  float* img_sums;               /* with img_target: [0] += sum |tanh(conv) - target|, [1] += sum (.)^2 (caller zeroes): the
+                                    reductions of the L1 / L2 image losses (pix2pix_model.py:197-208) ride in this kernel */
 } s2e_conv_t;
 
 int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale,

@@ -288,12 +288,20 @@ def instance_norm(x):
     return (x - mean) * torch.rsqrt(var + 1e-5)
 
 
-def spade(sd, p, x, seg, instance=False):
+def batch_norm_eval(x, sd, p):
+    """nn.BatchNorm2d(affine=False) in eval mode (test.py: model.eval()): running statistics, nothing is updated."""
+    m, v = sd[p + ".running_mean"], sd[p + ".running_var"]
+    return (x - m[None, :, None, None]) * torch.rsqrt(v[None, :, None, None] + 1e-5)
+
+
+def spade(sd, p, x, seg, instance=False, training=True):
     """SPADE.forward, normalization.py:91-105."""
     if instance:
         normalized = instance_norm(x)
-    else:
+    elif training:
         normalized = batch_norm_train(x, sd, p + ".param_free_norm")
+    else:
+        normalized = batch_norm_eval(x, sd, p + ".param_free_norm")
     seg_r = nearest_resize(seg, x.shape[2:])
     actv = F.relu(F.conv2d(seg_r, sd[p + ".mlp_shared.0.weight"], sd[p + ".mlp_shared.0.bias"], padding=1))
     gamma = F.conv2d(actv, sd[p + ".mlp_gamma.weight"], sd[p + ".mlp_gamma.bias"], padding=1)
@@ -309,11 +317,11 @@ def apply_style(sd, p, x, w):
     return x * (style[:, 0] + 1.0) + style[:, 1]
 
 
-def spade_style_block(sd, p, x, seg, w, opt):
+def spade_style_block(sd, p, x, seg, w, opt, training=True):
     """SPADE_STYLE_Block.forward, normalization.py:184-192.  w None: the block of the ORIGINAL SPADE generator
     (BASELINE config 5; SURVEY 8(c) last bullet) -- SPADE.forward (normalization.py:91-105) alone, i.e. the same block
     with the ApplyStyle term and the division by two removed."""
-    s = spade(sd, p + ".spade", x, seg, instance="instance" in opt.norm_G)
+    s = spade(sd, p + ".spade", x, seg, instance="instance" in opt.norm_G, training=training)
     if w is None:
         return s
     a = apply_style(sd, p + ".adain", x, w)
@@ -333,13 +341,13 @@ def resblock(sd, p, x, seg, w, fin, fout, opt, training=True, taps=None):
         return F.conv2d(t, wt, sd.get("%s.%s.bias" % (p, name)), padding=pad)
 
     if fin != fout:
-        ns = spade_style_block(sd, p + ".norm_s", x, seg, w, opt)
+        ns = spade_style_block(sd, p + ".norm_s", x, seg, w, opt, training)
         x_s = conv("conv_s", ns, 0)
     else:
         x_s = x
-    n0 = F.leaky_relu(spade_style_block(sd, p + ".norm_0", x, seg, w, opt), 0.2)
+    n0 = F.leaky_relu(spade_style_block(sd, p + ".norm_0", x, seg, w, opt, training), 0.2)
     dx = conv("conv_0", n0, 1)
-    n1 = F.leaky_relu(spade_style_block(sd, p + ".norm_1", dx, seg, w, opt), 0.2)
+    n1 = F.leaky_relu(spade_style_block(sd, p + ".norm_1", dx, seg, w, opt, training), 0.2)
     dx = conv("conv_1", n1, 1)
     out = x_s + dx
     if taps is not None:

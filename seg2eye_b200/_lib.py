@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
                 ("residual", C.c_void_p), ("bias_n", C.c_int), ("in_act", C.c_int), ("mask_slope", C.c_float),
                 ("spade_x", C.c_void_p), ("spade_par", C.c_void_p), ("spade_C", C.c_int), ("spade_act", C.c_int),
                 ("spade_up", C.c_int), ("spade_gamma_out", C.c_void_p), ("spade_mask_out", C.c_void_p),
-                ("spade_plain", C.c_int)]
+                ("spade_plain", C.c_int), ("img_out", C.c_void_p), ("img_target", C.c_void_p), ("img_sums", C.c_void_p)]
 
 
 class SnJob(C.Structure):

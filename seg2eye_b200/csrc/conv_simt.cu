@@ -198,7 +198,7 @@ int s2e_tapconv_fwd_simt(const s2e_conv_t* d, const void* x, const void* wp, con
     const int rc = s2e_thin_fwd(d, x, wp, bias, scale, y, stream);
     if (rc != 0) return rc < 0 ? rc : S2E_OK;
   }
-  S2E_REQUIRE(d->in_act == S2E_ACT_NONE, "tapconv_fwd: in_act is implemented by the thin-layer kernels only");
+  S2E_REQUIRE(d->in_act == S2E_ACT_NONE && !d->img_out, "tapconv_fwd: in_act / the tanh image head are implemented by the thin-layer kernels only");
   Geom g = make_geom(d);
   const long long P = (long long)d->B * d->Ho * d->Wo;
   if (P == 0) return S2E_OK;

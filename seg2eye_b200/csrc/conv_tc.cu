@@ -501,7 +501,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.sgamma = (spade && d->spade_gamma_out) ? 1 : 0;
   p.smask = spade ? (uint8_t*)d->spade_mask_out : nullptr;
   S2E_REQUIRE(!(p.mask && p.res), "tapconv_fwd: relu_mask and residual are mutually exclusive");
-  S2E_REQUIRE(d->in_act == S2E_ACT_NONE && d->mask_slope == 0.f, "tapconv_fwd: in_act / mask_slope exist on the CUDA-core path only");
+  S2E_REQUIRE(d->in_act == S2E_ACT_NONE && d->mask_slope == 0.f && !d->img_out, "tapconv_fwd: in_act / mask_slope / image head exist on the CUDA-core path only");
   S2E_REQUIRE(!(p.mask || p.res) || d->Cout % 64 == 0, "tapconv_fwd: relu_mask / residual need Cout %% 64 == 0 on the tcgen05 path");
   S2E_REQUIRE(!spade || (p.tiles_w * p.tiles_h) % Cfg::MT == 0, "tapconv_fwd: fused SPADE: sub-tiles of one tile must share a sample");
   p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);

@@ -256,7 +256,12 @@ constexpr int T1_TW = 32, T1_TH = 8, T1_HW = T1_TW + 2, T1_NHP = (T1_TH + 2) * T
 constexpr int T1_SMEM = T1_NHP * 128 + T1_NHP * 9 * 4;
 __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                                 const float* __restrict__ bias, const float* __restrict__ scale,
-                                                                bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h) {
+                                                                bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h,
+                                                                float* __restrict__ img_out, const float* __restrict__ img_target,
+                                                                float* __restrict__ img_sums) {
+  // img_out != NULL: the image head of the generator (generator.py:97-99): tanh is applied to the fp32 accumulator and the
+  // result is written as fp32 (no bf16 rounding of the pre-activation); with img_target the block also adds its partial
+  // sums of |fake - target| and (fake - target)^2 to img_sums[0..1] (the L1 / L2 image losses, pix2pix_model.py:197-208)
   extern __shared__ __align__(16) uint8_t t1_smem[];
   bf16* xs = reinterpret_cast<bf16*>(t1_smem);                               // [T1_NHP][64]
   float* d = reinterpret_cast<float*>(t1_smem + T1_NHP * 128);               // [T1_NHP][9]
@@ -315,12 +320,41 @@ __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __re
   __syncthreads();
   const int th = threadIdx.x >> 5, tw = threadIdx.x & 31;
   const int ho = th_idx * T1_TH + th, wo = tw_idx * T1_TW + tw;
+  float l1 = 0.f, l2 = 0.f;
   if (ho < g.Ho && wo < g.Wo) {
     float acc = 0.f;
     for (int t = 0; t < g.ntaps; ++t) acc += d[((th + 1 + g.dy[t]) * T1_HW + (tw + 1 + g.dx[t])) * 9 + t];
     const float sc = scale ? __ldg(scale) : 1.f;
     const float bv = bias ? __ldg(bias) : 0.f;
-    y[((long long)b * g.Ho + ho) * g.Wo + wo] = __float2bfloat16(act_apply(acc * sc + bv, g.act));
+    const float v = act_apply(acc * sc + bv, g.act);
+    const long long idx = ((long long)b * g.Ho + ho) * g.Wo + wo;
+    if (img_out) {
+      const float tv = tanhf(v);
+      img_out[idx] = tv;
+      if (img_target) {
+        const float df = tv - __ldg(img_target + idx);
+        l1 = fabsf(df);
+        l2 = df * df;
+      }
+    } else {
+      y[idx] = __float2bfloat16(v);
+    }
+  }
+  if (img_out && img_target) {   // block-uniform branch
+    __shared__ float red[2][8];
+    l1 = warp_sum(l1);
+    l2 = warp_sum(l2);
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = l1;
+      red[1][threadIdx.x >> 5] = l2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+      atomicAdd(img_sums + threadIdx.x, t);
+    }
   }
 }
 
@@ -456,7 +490,7 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
   const bf16* mask = (const bf16*)d->relu_mask;
   // input activation: tiled conv_img kernel only; output mask: thin-input kernel only -- everything else declines
   const bool tile_ok = d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9 && d->Hi == d->Ho && d->Wi == d->Wo;
-  if (d->in_act != S2E_ACT_NONE && !tile_ok) return 0;
+  if ((d->in_act != S2E_ACT_NONE || d->img_out) && !tile_ok) return 0;
   if (mask && !(d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8)) return 0;
   if (d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8) {
     const int cot = d->Cout < K1_CO_TILE ? d->Cout : K1_CO_TILE;
@@ -496,12 +530,13 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
         attr1 = true;
       }
       thin_out1_tile_kernel<<<(unsigned)(d->B * tiles_h * tiles_w), 256, T1_SMEM, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale,
-                                                                                   (bf16*)y, g, tiles_w, tiles_h);
+                                                                                   (bf16*)y, g, tiles_w, tiles_h, d->img_out,
+                                                                                   d->img_target, d->img_sums);
       S2E_LAUNCH_CHECK();
       return 1;
     }
   }
-  if (d->in_act != S2E_ACT_NONE) return 0;
+  if (d->in_act != S2E_ACT_NONE || d->img_out) return 0;
   if (d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9) {
     const long long warps = (long long)s2e_num_sms() * 32;
     long long ppw = (P + warps - 1) / warps;

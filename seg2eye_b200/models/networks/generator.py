@@ -62,6 +62,8 @@ class SPADESTYLEGenerator(BaseNetwork):
         return plan
 
     def forward(self, input, w=None):
+        """`self.loss_target` (optional, consumed by this call): the target image of the L1 / L2 losses, (B,1,H,W) fp32 on the
+        device -- when set, the image-head kernel also reduces the two loss sums (see ops.ImageHeadFn)."""
         if self.opt.output_nc != 1:
             raise ValueError('output_nc != 1 is not supported by the B200 path (OpenEDS images are single channel)')
         clear_seg_cache()   # the im2col'd segmaps are shared by the SPADE blocks of this forward only
@@ -71,8 +73,16 @@ class SPADESTYLEGenerator(BaseNetwork):
         x = self.fc.forward_nhwc(ops.seg_nearest(input, self.sh, self.sw, cpad))
         for name, upsample_first in self._schedule():
             x = getattr(self, name).forward_nhwc(x, input, w, up=upsample_first)
-        x = self.conv_img.forward_nhwc(x, in_act=L.ACT_LRELU)     # leaky_relu(x, 0.2) -> conv_img, one kernel
         clear_seg_cache()
+        target, self.loss_target = getattr(self, 'loss_target', None), None
+        if x.shape[-1] == 64 and self.conv_img.in_channels == 64 and ops._state["force_impl"] is None:
+            # leaky_relu -> conv_img -> tanh (-> partial sums of the L1 / L2 image losses) in one kernel
+            cfg = self.conv_img.cfg._replace(in_act=L.ACT_LRELU)
+            img, sums = ops.ImageHeadFn.apply(x, cfg, self.conv_img.weight, self.conv_img.bias, target)
+            if sums is not None:
+                img._s2e_img_sums = (sums, target)
+            return img
+        x = self.conv_img.forward_nhwc(x, in_act=L.ACT_LRELU)     # leaky_relu(x, 0.2) -> conv_img, one kernel
         return ops.TanhFn.apply(x)
 
 

@@ -127,6 +127,10 @@ class Pix2PixModel(torch.nn.Module):
     # ------------------------------------------------------------------ losses
     def compute_generator_loss(self, input_semantics, style_image, target_image):
         opt = self.opt
+        if (opt.lambda_l1 or opt.lambda_l2) and target_image is not None:
+            # the image head of the generator reduces the L1 / L2 sums against this target in its own kernel
+            target_image = target_image.float().contiguous()
+            self.netG.loss_target = target_image
         fake, w_real, feats_real = self.generate_fake(input_semantics, style_image)
         with ops.skip_weight_grads():
             pred_fake, pred_real = self.discriminate(input_semantics, fake, target_image)

@@ -69,7 +69,7 @@ _prof = None
 
 def profile_begin():
     global _prof
-    _prof = {"tc": [], "norm": []}
+    _prof = {"tc": [], "norm": [], "normb": []}
 
 
 def profile_end(dump_path=None):
@@ -90,7 +90,7 @@ def profile_end(dump_path=None):
                 rate = (w / 1e12 if kind == "tc" else w / 1e9) / (ms / 1e3) if ms > 0 else 0
                 f.write("%s\t%s\t%d\t%.3f\t%.4g\t%.1f\n" % (kind, tag, n, ms, w, rate))
     out = {"by_tag": agg}
-    for kind, key in (("tc", "flop"), ("norm", "bytes")):
+    for kind, key in (("tc", "flop"), ("norm", "bytes"), ("normb", "bytes")):
         rows = [v for (k, _), v in agg.items() if k == kind]
         out[kind + "_ms"] = sum(v[1] for v in rows)
         out[kind + "_" + key] = float(sum(v[2] for v in rows))
@@ -628,9 +628,9 @@ class SpadeStyleFn(torch.autograd.Function):
         dgb = torch.empty_like(gb)
         dstyle = torch.empty_like(style) if style is not None else None
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
-        L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
-               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
-               L.ptr(dstyle), L.ptr(chsum), W if up else 0, 0, st)
+        _timed_call("normb", 12.0 * B * H * W * Cc, "s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
+                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
+                    L.ptr(dstyle), L.ptr(chsum), W if up else 0, 0, st, tag="bwd B%d HW%d C%d%s" % (B, H * W, Cc, " up" if up else ""))
         # per-channel sums of the two gradients, for the bias gradients of the convolutions that receive them as dy
         # (TapConvFn.backward picks the attribute up when the tensor reaches it unmodified; otherwise it sums itself)
         dgb._s2e_chsum = chsum[:2 * Cc]
@@ -726,9 +726,9 @@ class SpadeConvFn(torch.autograd.Function):
         dgb = torch.empty(B, H, W, 2 * Cc, dtype=BF16, device=x.device)
         dstyle = torch.empty_like(style) if style is not None else None
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
-        L.call("s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gamma), L.ptr(style), L.ptr(mean),
-               L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
-               L.ptr(dstyle), L.ptr(chsum), W if up else 0, Cc, st)
+        _timed_call("normb", 12.0 * B * H * W * Cc, "s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gamma), L.ptr(style), L.ptr(mean),
+                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
+                    L.ptr(dstyle), L.ptr(chsum), W if up else 0, Cc, st, tag="bwd B%d HW%d C%d%s" % (B, H * W, Cc, " up" if up else ""))
         gx = None
         if last and ctx.needs_input_grad[1]:
             if up:
@@ -1371,3 +1371,78 @@ def gram_matrix(x_nchw):
     xp = torch.empty(1, c, d, a * b, dtype=BF16, device=x.device)
     L.call("s2e_nchw_f32_to_nhwc_bf16", L.ptr(x), 1, a * b, c, d, L.ptr(xp), L.stream())
     return _gram_raw(xp) / float(a * b * c * d)
+
+
+# ------------------------------------------------------------------------------------------------ image head
+class _ConvCtx:
+    """Stand-in for an autograd ctx so that ImageHeadFn can reuse TapConvFn.backward for its convolution part."""
+
+
+class ImageHeadFn(torch.autograd.Function):
+    """leaky_relu(x, 0.2) -> conv_img (64 -> 1, 3x3, pad 1) -> tanh (generator.py:97-99) in ONE kernel: the activation is
+    applied as the input tile is read, tanh to the fp32 accumulator (the pre-activation is never rounded to bf16), the image
+    leaves as fp32 (B,1,H,W).  With `target` (the image the L1 / L2 losses compare against, pix2pix_model.py:197-208) the
+    same kernel also reduces sum|fake - target| and sum (fake - target)^2 into `sums` (2,), so the image losses need no
+    pass of their own over the image.  Returns (image, sums | None)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, weight, bias, target):
+        x = _c(x)
+        B, H, W, Cin = x.shape
+        assert x.dtype == BF16 and Cin == 64 and tuple(weight.shape) == (1, 64, 3, 3) and cfg.stride == 1 and cfg.pad == 1
+        taps = conv_taps(cfg)
+        wp = packed_weights((weight,), cfg, False)
+        img = torch.empty(B, 1, H, W, dtype=F32, device=x.device)
+        sums = None
+        if target is not None:
+            target = _c(target.detach().float())
+            assert target.shape == img.shape
+            sums = torch.zeros(2, dtype=F32, device=x.device)
+        d = _desc(B, H, W, 64, H, W, 1, taps, L.ACT_NONE)
+        d.bias_n, d.in_act = 1, cfg.in_act
+        d.img_out, d.img_target, d.img_sums = L.ptr(img), L.ptr(target), L.ptr(sums)
+        L.call("s2e_tapconv_fwd", d, L.ptr(x), L.ptr(wp), L.ptr(bias.detach()) if bias is not None else None, None, None,
+               L.IMPL_SIMT, L.stream())
+        ctx.cfg, ctx.weight, ctx.has_bias = cfg, weight, bias is not None
+        ctx.skip_wgrad = _state["skip_wgrad"]
+        ctx.save_for_backward(x, img)
+        if sums is not None:
+            ctx.mark_non_differentiable(sums)
+        return img, sums
+
+    @staticmethod
+    def backward(ctx, dimg, _dsums):
+        x, img = ctx.saved_tensors
+        B, H, W, _ = x.shape
+        dz = torch.empty(B, H, W, 1, dtype=BF16, device=x.device)          # d tanh = 1 - y^2
+        L.call("s2e_tanh_bwd", L.ptr(_c(dimg.float())), L.ptr(img), img.numel(), L.ptr(dz), L.stream())
+        c = _ConvCtx()
+        c.cfg, c.sn, c.n_w, c.n_b = ctx.cfg, None, 1, int(ctx.has_bias)
+        c.in_shape, c.weights, c.cout, c.cp = tuple(x.shape), (ctx.weight,), 1, 1
+        c.skip_wgrad, c.flops = ctx.skip_wgrad, 2.0 * B * H * W * 64 * 9
+        c.saved_tensors = (x, None)
+        c.needs_input_grad = (ctx.needs_input_grad[0], False, False, False, False, ctx.needs_input_grad[2]) + (
+            (ctx.needs_input_grad[3],) if ctx.has_bias else ())
+        res = TapConvFn.backward(c, dz)
+        return res[0], None, res[5], (res[6] if ctx.has_bias else None), None
+
+
+class PrecomputedLossFn(torch.autograd.Function):
+    """coef * sums[idx] where sums[idx] = sum f(a - b) was already reduced by the kernel that produced `a` (ImageHeadFn);
+    backward is the ordinary elementwise gradient of the loss."""
+
+    @staticmethod
+    def forward(ctx, a, b, sums, idx, kind, coef):
+        ctx.kind, ctx.coef = kind, coef
+        ctx.save_for_backward(a, b)
+        return sums[idx:idx + 1] * coef
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        a, b = _c(a), _c(b)
+        gout = _c(gout.float())
+        da = torch.empty_like(a)
+        L.call("s2e_reduce_loss_bwd", L.ptr(a), L.ptr(b), a.numel(), int(a.dtype == F32), ctx.kind, ctx.coef, 0.0, L.ptr(gout),
+               L.ptr(da), 0, L.stream())
+        return da, None, None, None, None, None

@@ -197,3 +197,39 @@ def test_iteration_max_aggregation_and_wgan_vs_reference(name):
     from oracle.make_golden_variants import VARIANTS
     ref = np.load(os.path.join(GOLD, "ref_variants.npz"))
     _check(_iteration(VARIANTS[name][1]), ref, name)
+
+
+# ------------------------------------------------------------------------------------------ image head (conv_img + tanh + loss sums)
+@pytest.mark.parametrize("B,H,W,with_target", [(2, 40, 32, True), (1, 21, 18, True), (2, 16, 64, False)])
+def test_image_head_conv_tanh_and_loss_sums_in_one_kernel(B, H, W, with_target):
+    """leaky_relu -> conv_img (64 -> 1) -> tanh -> sum|fake - target|, sum(fake - target)^2 in one kernel (generator.py:97-99,
+    pix2pix_model.py:197-208) against plain fp32 PyTorch, forward and backward (through the L1 + L2 losses)."""
+    from seg2eye_b200 import _lib as L, ops
+    from seg2eye_b200.models.networks import loss as LS
+    bf = lambda t: t.to(torch.bfloat16).float()
+    g = torch.Generator().manual_seed(11)
+    x = bf(torch.randn(B, 64, H, W, generator=g))
+    w = bf(torch.randn(1, 64, 3, 3, generator=g) / 24)
+    b = torch.randn(1, generator=g) * 0.1
+    target = torch.rand(B, 1, H, W, generator=g) * 2 - 1
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    fr = torch.tanh(F.conv2d(F.leaky_relu(xr, 0.2), wr, br, padding=1))
+    lref = 10 * F.l1_loss(fr, target) + 15 * F.mse_loss(fr, target)
+    lref.backward()
+    xc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda().requires_grad_()
+    wc, bc, tc = w.cuda().requires_grad_(), b.cuda().requires_grad_(), target.cuda()
+    cfg = ops.ConvCfg(3, 3, 1, 1, L.ACT_NONE)._replace(in_act=L.ACT_LRELU)
+    img, sums = ops.ImageHeadFn.apply(xc, cfg, wc, bc, tc if with_target else None)
+    assert img.dtype == torch.float32 and img.shape == (B, 1, H, W)
+    assert rel(img, fr) < 2e-3, rel(img, fr)        # fp32 tanh of the fp32 accumulator: no bf16 rounding of the output
+    if with_target:
+        img._s2e_img_sums = (sums, tc)
+        assert abs(float(sums[0]) - float((fr - target).abs().sum())) <= 2e-3 * float((fr - target).abs().sum())
+        assert abs(float(sums[1]) - float((fr - target).square().sum())) <= 2e-3 * float((fr - target).square().sum())
+    else:
+        assert sums is None
+    l = 10 * LS.l1_loss(img, tc) + 15 * LS.mse_loss(img, tc)     # uses the precomputed sums when they belong to (img, tc)
+    l.backward()
+    assert abs(float(l) - float(lref)) <= 2e-3 * abs(float(lref))
+    assert rel(xc.grad.float().permute(0, 3, 1, 2), xr.grad) < 1e-2
+    assert rel(wc.grad, wr.grad) < 1e-2 and rel(bc.grad, br.grad) < 1e-2

@@ -469,3 +469,30 @@ def test_training_iteration_with_and_without_fused_spade_conv_vs_oracle(ctx, fus
     for k in ref:
         assert abs(ours[k] - ref[k]) <= TOL_LOSS * abs(ref[k]) + (2e-2 if k == "GAN" else 0.0), (k, ours[k], ref[k])
     assert rel(tr.generated, ot.generated) < TOL_CHAIN
+
+
+def test_eval_mode_inference_sweep_vs_oracle(ctx):
+    """test.py runs the model in eval mode (BatchNorm running statistics, spectral-norm vectors frozen): the config-4
+    sweep -- encode two style sets, interpolate, batch inference with `latent_style` -- against the oracle in eval mode;
+    nothing in the state dicts may change."""
+    from seg2eye_b200.models.pix2pix_model import Pix2PixModel
+    m = Pix2PixModel(ctx.opt)
+    sdG, sdE = O.synth_state(O.generator_shapes(ctx.oopt), ctx.seeds["G"]), O.synth_state(O.encoder_shapes(ctx.oopt), ctx.seeds["E"])
+    load(m.netG, sdG)
+    load(m.netE, sdE)
+    m.eval()
+    before = {k: v.clone() for k, v in m.netG.state_dict().items()}
+    data = {k: v.clone() for k, v in ctx.batch.items()}
+    w = m(data, mode="encode_only")
+    with torch.no_grad():
+        w_o = O.encode_w({k: v.clone() for k, v in sdE.items()}, ctx.batch["style_image"], ctx.oopt, training=False)
+    assert rel(w, w_o) < TOL_ACT
+    alphas = torch.linspace(0, 1, 5, device=w.device).view(-1, 1)
+    wi = (1 - alphas) * w[0:1] + alphas * w[1:2]
+    lab = ctx.batch["label"][0:1].repeat(5, 1, 1, 1)
+    out = m({"label": lab, "style_image": ctx.batch["style_image"], "latent_style": wi.detach()}, mode="inference")
+    with torch.no_grad():
+        ref = O.generator_forward({k: v.clone() for k, v in sdG.items()}, O.one_hot(lab, 4), wi.detach().cpu(), ctx.oopt, training=False)
+    assert out.shape == ref.shape and rel(out, ref) < TOL_CHAIN, rel(out, ref)
+    after = m.netG.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before), "eval-mode inference changed buffers"
