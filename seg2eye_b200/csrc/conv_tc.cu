@@ -97,6 +97,8 @@ struct FwdParams {
   int sgamma;         // training: gamma (sC channels, bf16) is written through tmG as well -- backward needs it
   uint8_t* smask;     // training: one bit per output element, set where the output is > 0 ([B*Ho*Wo][sC/8] bytes)
   uint32_t a_box_bytes;
+  uint32_t halo_box_bytes;   // HALO kernels: bytes of one {64 ch, TW+2, TH+2, 1} box
+  int halo_bo;               // HALO kernels: put (addr >> 7) & 7 into the descriptor's base-offset field
   const float* bias;
   const float* scale;
   TapTable taps;
@@ -113,6 +115,25 @@ struct FwdCfg {
   static constexpr int STAGES = 4;
   static constexpr int TMEM_COLS = 2 * MT * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BUF_BYTES + 1024 + 256 + BN * 4;
+};
+
+// HALO variant (3x3 / stride 1, tile = 8 wide x 16 high): per 64-channel block ONE input tile with a one-pixel halo
+// ({64 ch, 10, 18, 1} = 23 KB) is staged and serves all nine taps -- the A operand of tap (dy, dx) is the window of that
+// tile starting at row (dy+1)*10 + (dx+1), read through a UMMA descriptor whose 8-row group stride (SBO) is the halo
+// pitch 10*128 B (tools/umma_shift_probe.cu: the tensor core swizzles on absolute shared-memory address bits, so a
+// window may start at any 128-byte row).  Only the weight tiles still stream once per tap: shared-memory fill per FLOP
+// drops 2.3x for N = 128 and 3.5x for N = 64 (the N <= 128 kernels were bound by exactly that).
+template <int BN>
+struct HaloCfg {
+  static constexpr int MT = BN == 256 ? 1 : 2;
+  static constexpr int TW = 8, TH = 16;
+  static constexpr int HALO_ROWS = (TW + 2) * (TH + 2);
+  static constexpr int HALO_BYTES = ((HALO_ROWS * 128 + 1023) / 1024) * 1024;
+  static constexpr int A_SLOTS = 2;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGES = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int TMEM_COLS = 2 * MT * BN;
+  static constexpr int SMEM_BYTES = A_SLOTS * MT * HALO_BYTES + B_STAGES * B_STAGE_BYTES + 2 * OUT_BUF_BYTES + 1024 + 256 + BN * 4;
 };
 
 // pixel sub-tile m -> tile origin; sub-tiles past the end land fully out of bounds (TMA zero-fills loads, clips stores)
@@ -141,19 +162,25 @@ __device__ __forceinline__ float act_t(float v) {
 
 // MODE 0: plain convolution epilogue; 1: fused SPADE+Style modulation (inference); 2: the same, also writing gamma and the
 // activation mask for backward.  A template parameter so that the ordinary instantiations do not carry the extra code.
-template <int BN, int ACT, int MODE>
+template <int BN, int ACT, int MODE, bool HALO>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const FwdParams p) {
   using Cfg = FwdCfg<BN>;
+  using HCfg = HaloCfg<BN>;
   constexpr bool SPADE = MODE != 0, SPADE_TRAIN = MODE == 2;
+  // ring barriers: non-HALO: full/empty[STAGES] guard (A | B) stages.  HALO: full/empty[0..B_STAGES) guard the weight
+  // ring, full/empty[B_STAGES .. B_STAGES + A_SLOTS) guard the halo tiles
+  constexpr int NBARS = HALO ? HCfg::B_STAGES + HCfg::A_SLOTS : Cfg::STAGES;
+  constexpr int PIPE_BYTES = HALO ? HCfg::A_SLOTS * HCfg::MT * HCfg::HALO_BYTES + HCfg::B_STAGES * HCfg::B_STAGE_BYTES
+                                  : Cfg::STAGES * Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* out_buf = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint8_t* out_buf = smem + PIPE_BYTES;
   uint64_t* bars = (uint64_t*)(out_buf + 2 * OUT_BUF_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::STAGES;
-  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* empty = bars + NBARS;
+  uint64_t* tmem_full = bars + 2 * NBARS;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
   float* s_bias = (float*)((uint8_t*)bars + 256);
@@ -162,7 +189,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) {
+    for (int i = 0; i < NBARS; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
@@ -189,7 +216,96 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int num_kb = p.taps.n * p.kc_per_tap;
 
-  if (warp == 0) {
+  if (warp == 0 && HALO) {
+    // ------------------------------------------------------------------ TMA producer, one halo tile per 64-channel block
+    if (lane == 0) {
+      int bs = 0, as = 0;
+      uint32_t bph = 0, aph = 0;
+      uint8_t* sB = smem + HCfg::A_SLOTS * HCfg::MT * HCfg::HALO_BYTES;
+      uint64_t* fullA = full + HCfg::B_STAGES;
+      uint64_t* emptyA = empty + HCfg::B_STAGES;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int n0 = (t % p.tiles_n) * BN;
+        const int grp = t / p.tiles_n;
+        int w0[HCfg::MT], h0[HCfg::MT], b0[HCfg::MT];
+#pragma unroll
+        for (int j = 0; j < HCfg::MT; ++j) subtile_origin(p, grp * HCfg::MT + j, w0[j], h0[j], b0[j]);
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          ptx::mbar_wait(&emptyA[as], aph ^ 1);
+          ptx::mbar_expect_tx(&fullA[as], HCfg::MT * p.halo_box_bytes);
+#pragma unroll
+          for (int j = 0; j < HCfg::MT; ++j)
+            ptx::tma_load_4d(smem + (as * HCfg::MT + j) * HCfg::HALO_BYTES, &tmA, &fullA[as], kc * BK, w0[j] - 1, h0[j] - 1, b0[j]);
+          if (++as == HCfg::A_SLOTS) {
+            as = 0;
+            aph ^= 1;
+          }
+          for (int tap = 0; tap < p.taps.n; ++tap) {
+            ptx::mbar_wait(&empty[bs], bph ^ 1);
+            ptx::mbar_expect_tx(&full[bs], HCfg::B_STAGE_BYTES);
+            ptx::tma_load_3d(sB + bs * HCfg::B_STAGE_BYTES, &tmB, &full[bs], kc * BK, n0, tap);
+            if (++bs == HCfg::B_STAGES) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && HALO) {
+    // ------------------------------------------------------------------ MMA issuer, shifted windows of the halo tile
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t SBO_A = (HCfg::TW + 2) * 128;     // 8-row groups of the window are one halo row (10 pixels) apart
+    int bs = 0, as = 0;
+    uint32_t bph = 0, aph = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint8_t* sB = smem + HCfg::A_SLOTS * HCfg::MT * HCfg::HALO_BYTES;
+    uint64_t* fullA = full + HCfg::B_STAGES;
+    uint64_t* emptyA = empty + HCfg::B_STAGES;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * HCfg::MT * BN);
+      for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+        ptx::mbar_wait(&fullA[as], aph);
+        const uint32_t a_base = ptx::smem_u32(smem + as * HCfg::MT * HCfg::HALO_BYTES);
+        for (int tap = 0; tap < p.taps.n; ++tap) {
+          ptx::mbar_wait(&full[bs], bph);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t b_addr = ptx::smem_u32(sB + bs * HCfg::B_STAGE_BYTES);
+            const uint32_t win = (uint32_t)((p.taps.dy[tap] + 1) * (HCfg::TW + 2) + (p.taps.dx[tap] + 1)) * 128u;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 32, 0, 1024);
+#pragma unroll
+              for (int j = 0; j < HCfg::MT; ++j) {
+                const uint32_t a_addr = a_base + j * HCfg::HALO_BYTES + win + k * 32;
+                uint64_t ad = ptx::umma_desc_sw128(a_addr, 0, SBO_A);
+                if (p.halo_bo) ad |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+                ptx::umma_bf16(d_tmem + (uint32_t)(j * BN), ad, bd, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit(&empty[bs]);
+            if (tap == p.taps.n - 1) ptx::umma_commit(&emptyA[as]);
+            if (tap == p.taps.n - 1 && kc == p.kc_per_tap - 1) ptx::umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++bs == HCfg::B_STAGES) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+        if (++as == HCfg::A_SLOTS) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -447,16 +563,42 @@ void choose_fwd_tile(int B, int H, int W, int* tw, int* th, int* tb) {
   *tb = bb;
 }
 
-template <int BN, int ACT, int MODE>
+// 3x3 / stride-1 tap set (possibly negated: data gradient) on a map large enough for 8 x 16 tiles
+bool halo_eligible(const s2e_conv_t* d) {
+  if (d->ntaps != 9 || d->Wo < 8 || d->Ho < 16 || d->Hi != d->Ho || d->Wi != d->Wo) return false;
+  if (d->tile_w > 0 && !(d->tile_w == 8 && d->tile_h == 16 && d->tile_b == 1)) return false;
+  int seen = 0;
+  for (int i = 0; i < 9; ++i) {
+    const int dy = d->tap_dy[i], dx = d->tap_dx[i];
+    if (dy < -1 || dy > 1 || dx < -1 || dx > 1) return false;
+    seen |= 1 << ((dy + 1) * 3 + dx + 1);
+  }
+  return seen == 0x1ff;
+}
+
+template <int BN, int ACT, int MODE, bool HALO>
 int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* bias, const float* scale, void* y,
                cudaStream_t stream) {
   using Cfg = FwdCfg<BN>;
+  using HCfg = HaloCfg<BN>;
+  constexpr int SMEM = HALO ? HCfg::SMEM_BYTES : Cfg::SMEM_BYTES;
+  static_assert(SMEM <= 232448, "shared memory budget");
   int tw = d->tile_w, th = d->tile_h, tb = d->tile_b;
-  if (tw <= 0 || th <= 0 || tb <= 0) choose_fwd_tile(d->B, d->Ho, d->Wo, &tw, &th, &tb);
+  if (HALO) {
+    tw = HCfg::TW;
+    th = HCfg::TH;
+    tb = 1;
+  } else if (tw <= 0 || th <= 0 || tb <= 0) {
+    choose_fwd_tile(d->B, d->Ho, d->Wo, &tw, &th, &tb);
+  }
   S2E_REQUIRE(tw * th * tb <= BM && tw <= 256 && th <= 256 && tb <= 256, "bad forward tile %dx%dx%d", tw, th, tb);
   CUtensorMap tmA, tmB, tmY, tmG;
   int rc;
-  if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
+  if (HALO) {
+    if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw + 2, th + 2, 1)) != S2E_OK) return rc;
+  } else {
+    if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
+  }
   if ((rc = make_map_w(&tmB, wp, d->ntaps, d->Cout, d->Cin, BN)) != S2E_OK) return rc;
   const bool spade = MODE != 0;
   S2E_REQUIRE(spade == (d->spade_x != nullptr) && (MODE == 2) == (spade && d->spade_gamma_out != nullptr), "tapconv_fwd: mode mismatch");
@@ -503,8 +645,11 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   S2E_REQUIRE(!(p.mask && p.res), "tapconv_fwd: relu_mask and residual are mutually exclusive");
   S2E_REQUIRE(d->in_act == S2E_ACT_NONE && d->mask_slope == 0.f && !d->img_out, "tapconv_fwd: in_act / mask_slope / image head exist on the CUDA-core path only");
   S2E_REQUIRE(!(p.mask || p.res) || d->Cout % 64 == 0, "tapconv_fwd: relu_mask / residual need Cout %% 64 == 0 on the tcgen05 path");
+  // fused SPADE: the MT sub-tiles of one work item must belong to one sample; a partial last row of tiles is fine (TMA clips)
   S2E_REQUIRE(!spade || (p.tiles_w * p.tiles_h) % Cfg::MT == 0, "tapconv_fwd: fused SPADE: sub-tiles of one tile must share a sample");
   p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);
+  p.halo_box_bytes = (uint32_t)((tw + 2) * (th + 2) * BK * 2);
+  p.halo_bo = s2e_debug_get(6) & 2 ? 1 : 0;
   p.bias = bias;
   p.scale = scale;
   p.taps.n = d->ntaps;
@@ -512,13 +657,15 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
     p.taps.dy[i] = d->tap_dy[i];
     p.taps.dx[i] = d->tap_dx[i];
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_fwd_kernel<BN, ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+  static int attr_dev_mask = 0;     // per device: one process may drive several GPUs
+  int dev = 0;
+  S2E_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask & (1 << (dev & 31)))) {
+    S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_fwd_kernel<BN, ACT, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_dev_mask |= 1 << (dev & 31);
   }
   int grid = p.num_tiles < s2e_num_sms() ? p.num_tiles : s2e_num_sms();
-  tapconv_fwd_kernel<BN, ACT, MODE><<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmG, p);
+  tapconv_fwd_kernel<BN, ACT, MODE, HALO><<<grid, FWD_THREADS, SMEM, stream>>>(tmA, tmB, tmY, tmG, p);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -774,10 +921,12 @@ int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp,
     }
   }
   p.ksplit = ksplit;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_dev_mask = 0;     // per device: one process may drive several GPUs
+  int dev = 0;
+  S2E_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask & (1 << (dev & 31)))) {
     S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_dev_mask |= 1 << (dev & 31);
   }
   tapconv_wgrad_kernel<BN><<<base * ksplit, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmDY, tmX, p);
   S2E_LAUNCH_CHECK();
@@ -1015,10 +1164,12 @@ int launch_wgrad_mt(const s2e_conv_t* d, const void* x, const void* dy, float* d
     }
   }
   p.ksplit = ksplit;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  S2E_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask & (1 << (dev & 31)))) {
     S2E_CHECK_CUDA(cudaFuncSetAttribute(tapconv_wgrad_mt_kernel<BN, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+    attr_dev_mask |= 1 << (dev & 31);
   }
   tapconv_wgrad_mt_kernel<BN, TPC><<<base * ksplit, NUM_THREADS, smem_bytes, stream>>>(tmDY, tmX, p, stages, ngroups);
   S2E_LAUNCH_CHECK();
@@ -1031,24 +1182,33 @@ int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const
                        void* y, cudaStream_t stream) {
   S2E_REQUIRE(d->Cin % 64 == 0 && d->Cout % 8 == 0, "tcgen05 tapconv needs Cin %% 64 == 0, Cout %% 8 == 0 (Cin=%d Cout=%d)",
               d->Cin, d->Cout);
-#define S2E_FWD_DISPATCH(BN_)                                                                          \
-  switch (d->act) {                                                                                    \
-    case S2E_ACT_LRELU: return launch_fwd<BN_, S2E_ACT_LRELU, 0>(d, x, wp, bias, scale, y, stream);    \
-    case S2E_ACT_RELU: return launch_fwd<BN_, S2E_ACT_RELU, 0>(d, x, wp, bias, scale, y, stream);      \
-    default: return launch_fwd<BN_, S2E_ACT_NONE, 0>(d, x, wp, bias, scale, y, stream);                \
+  // debug key 6, bit 0: 3x3 / stride-1 layers with an N tile <= 128 take the halo-tile kernel (one staged input tile per
+  // 64-channel block serves all nine taps); bit 1: descriptors carry an explicit base offset
+  const bool halo = (s2e_debug_get(6) & 1) && halo_eligible(d);
+#define S2E_FWD_DISPATCH(BN_, HALO_)                                                                          \
+  switch (d->act) {                                                                                           \
+    case S2E_ACT_LRELU: return launch_fwd<BN_, S2E_ACT_LRELU, 0, HALO_>(d, x, wp, bias, scale, y, stream);    \
+    case S2E_ACT_RELU: return launch_fwd<BN_, S2E_ACT_RELU, 0, HALO_>(d, x, wp, bias, scale, y, stream);      \
+    default: return launch_fwd<BN_, S2E_ACT_NONE, 0, HALO_>(d, x, wp, bias, scale, y, stream);                \
   }
   if (d->spade_x) {   // fused SPADE+Style epilogue: gamma | beta fill exactly one N tile
     S2E_REQUIRE(d->act == S2E_ACT_NONE && (d->Cout == 256 || d->Cout == 128), "tapconv_fwd: fused SPADE needs Cout in {128, 256}");
     if (d->spade_gamma_out) {
-      if (d->Cout == 256) return launch_fwd<256, S2E_ACT_NONE, 2>(d, x, wp, bias, scale, y, stream);
-      return launch_fwd<128, S2E_ACT_NONE, 2>(d, x, wp, bias, scale, y, stream);
+      if (d->Cout == 256) return launch_fwd<256, S2E_ACT_NONE, 2, false>(d, x, wp, bias, scale, y, stream);
+      if (halo) return launch_fwd<128, S2E_ACT_NONE, 2, true>(d, x, wp, bias, scale, y, stream);
+      return launch_fwd<128, S2E_ACT_NONE, 2, false>(d, x, wp, bias, scale, y, stream);
     }
-    if (d->Cout == 256) return launch_fwd<256, S2E_ACT_NONE, 1>(d, x, wp, bias, scale, y, stream);
-    return launch_fwd<128, S2E_ACT_NONE, 1>(d, x, wp, bias, scale, y, stream);
+    if (d->Cout == 256) return launch_fwd<256, S2E_ACT_NONE, 1, false>(d, x, wp, bias, scale, y, stream);
+    if (halo) return launch_fwd<128, S2E_ACT_NONE, 1, true>(d, x, wp, bias, scale, y, stream);
+    return launch_fwd<128, S2E_ACT_NONE, 1, false>(d, x, wp, bias, scale, y, stream);
   }
-  if (d->Cout >= 256) { S2E_FWD_DISPATCH(256) }
-  if (d->Cout >= 128) { S2E_FWD_DISPATCH(128) }
-  S2E_FWD_DISPATCH(64)
+  if (d->Cout >= 256) { S2E_FWD_DISPATCH(256, false) }
+  if (d->Cout >= 128) {
+    if (halo) { S2E_FWD_DISPATCH(128, true) }
+    S2E_FWD_DISPATCH(128, false)
+  }
+  if (halo) { S2E_FWD_DISPATCH(64, true) }
+  S2E_FWD_DISPATCH(64, false)
 #undef S2E_FWD_DISPATCH
 }
 

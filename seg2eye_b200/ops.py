@@ -30,6 +30,23 @@ _state = {"force_impl": None, "weights_epoch": 0, "skip_wgrad": False,
           "fuse_spade_training": __import__("os").environ.get("S2E_FUSE_SPADE_TRAINING", "1") == "1"}
 
 
+def set_halo(on, base_offset=False):
+    """3x3 / stride-1 tensor-core convolutions with an N tile <= 128 take the halo-tile kernel (library debug key 6)."""
+    _state["halo"] = bool(on)
+    L.call("s2e_debug_set", 6, (1 if on else 0) | (2 if base_offset else 0))
+
+
+def halo_on():
+    if "halo" not in _state:      # first use: S2E_DEBUG may have set the key at load time; S2E_HALO=0/1 overrides
+        import os
+        env = os.environ.get("S2E_HALO")
+        if env is not None:
+            set_halo(env == "1")
+        else:
+            _state["halo"] = any(item.strip() in ("6=1", "6=3") for item in os.environ.get("S2E_DEBUG", "").split(","))
+    return _state["halo"]
+
+
 def bump_weights_epoch():
     """Called whenever parameters are modified behind torch's back (our Adam kernel)."""
     _state["weights_epoch"] += 1
@@ -526,10 +543,9 @@ def spade_conv_fused_ok(x, up, n_hidden):
     H, W = (2 * Hx, 2 * Wx) if up else (Hx, Wx)
     if Cc not in (64, 128) or n_hidden % 64 or _state["force_impl"] == L.IMPL_SIMT:
         return False
-    tw = _fused_tile_w(W)           # tile = tw x (128 / tw) pixels inside one image
-    th = 128 // tw
-    tiles = (W // tw) * ((H + th - 1) // th)
-    return H % th == 0 and tiles % 2 == 0
+    tw, th = _fused_tile(H, W, Cc)  # tile = tw x th pixels inside one image
+    tiles = ((W + tw - 1) // tw) * ((H + th - 1) // th)
+    return (tw == 8 or H % th == 0) and tiles % 2 == 0
 
 
 def spade_conv_fused(actv, conv_cfg, weights, biases, x, style, cfg, running_mean, running_var, nbt, up):
@@ -549,9 +565,9 @@ def spade_conv_fused(actv, conv_cfg, weights, biases, x, style, cfg, running_mea
     wp = packed_weights(weights, conv_cfg, False)
     bias = torch.cat([b.detach() for b in biases])
     taps = conv_taps(conv_cfg)
-    tw = _fused_tile_w(W)
+    tw, th = _fused_tile(H, W, Cc)
     d = _desc(B, H, W, actv.shape[3], H, W, 2 * Cc, taps, L.ACT_NONE)
-    d.tile_w, d.tile_h, d.tile_b = tw, 128 // tw, 1
+    d.tile_w, d.tile_h, d.tile_b = tw, th, 1
     d.spade_x, d.spade_par, d.spade_C, d.spade_act, d.spade_up = L.ptr(x), L.ptr(par), Cc, cfg.act, int(up)
     d.spade_plain = int(style is None)
     out = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
@@ -653,6 +669,15 @@ def _fused_tile_w(W):
     return tw
 
 
+def _fused_tile(H, W, Cc):
+    """(tile_w, tile_h) of the fused gamma|beta + modulation kernel: 8 x 16 when the halo-tile kernel applies (N = 2C = 128
+    only), else the widest row tile."""
+    if Cc == 64 and halo_on() and W >= 8 and H >= 16 and (((W + 7) // 8) * ((H + 15) // 16)) % 2 == 0:
+        return 8, 16
+    tw = _fused_tile_w(W)
+    return tw, 128 // tw
+
+
 class SpadeConvFn(torch.autograd.Function):
     """Training-mode SPADE+Style block with the gamma|beta convolution and the modulation in ONE tcgen05 kernel
     (normalization.py:85-105,161-192):
@@ -688,8 +713,8 @@ class SpadeConvFn(torch.autograd.Function):
         gamma = torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
         amask = torch.empty(B * H * W * (Cc // 8), dtype=torch.uint8, device=x.device) if cfg.act != L.ACT_NONE else None
         d = _desc(B, H, W, Ca, H, W, 2 * Cc, taps, L.ACT_NONE)
-        tw = _fused_tile_w(W)
-        d.tile_w, d.tile_h, d.tile_b = tw, 128 // tw, 1
+        tw, th = _fused_tile(H, W, Cc)
+        d.tile_w, d.tile_h, d.tile_b = tw, th, 1
         d.spade_x, d.spade_par, d.spade_C, d.spade_act, d.spade_up = L.ptr(x), L.ptr(par), Cc, cfg.act, int(up)
         d.spade_plain = int(style is None)
         d.spade_gamma_out, d.spade_mask_out = L.ptr(gamma), L.ptr(amask)

@@ -830,3 +830,43 @@ def test_spade_conv_fused_training_forward_backward(S, C, up, act):
     assert rel(sc.grad, sr.grad) < TOL_ACT
     assert rel(wgc.grad, wgr.grad) < TOL_ACT and rel(wbc.grad, wbr.grad) < TOL_ACT
     assert rel(bgc.grad, bgr.grad) < TOL_ACT and rel(bbc.grad, bbr.grad) < TOL_ACT
+
+
+# ------------------------------------------------------------------------------------------ halo-tile forward kernel
+HALO_CASES = [
+    (2, 128, 128, 24, 16, 3, 1, 1, 0),     # N = 128, two sub-tiles
+    (1, 64, 64, 20, 16, 3, 1, 1, 0),       # N = 64, partial tile at the bottom (H = 20)
+    (1, 256, 128, 40, 32, 3, 1, 1, 1),     # four 64-channel blocks, fused LeakyReLU
+    (2, 128, 64, 24, 16, 3, 1, 1, 0),
+    (1, 64, 64, 37, 29, 3, 1, 1, 0),       # ragged: partial tiles right and bottom, odd tile count
+    (3, 128, 128, 40, 48, 3, 1, 1, 0),     # many tiles per CTA
+    (1, 64, 72, 16, 8, 3, 1, 1, 1),        # Cout not a multiple of 64
+    (2, 64, 256, 24, 16, 3, 1, 1, 0),      # forward N = 256 (plain kernel), data gradient N = 64 (halo kernel)
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_tcgen05_halo_kernel(S, case):
+    """3x3 / stride-1 convolutions with an N tile <= 128 through the halo-tile kernel (one staged {64, 10, 18} input tile
+    per 64-channel block serves all nine taps via UMMA descriptors on shifted windows): forward and data gradient."""
+    L, ops = S
+    ops.set_halo(True)
+    try:
+        conv_case(S, L.IMPL_TC, *case)
+    finally:
+        ops.set_halo(False)
+
+
+def test_halo_kernel_epilogue_variants(S):
+    """Residual add, fused ReLU-backward mask and the fused SPADE+Style epilogues (no-grad and training) on the halo kernel."""
+    L, ops = S
+    ops.set_halo(True)
+    try:
+        test_conv_residual_in_epilogue(S, "tc", 128)
+        test_conv_residual_in_epilogue(S, "tc", 64)
+        test_relu_backward_fused_into_dgrad_epilogue(S, "tc")
+        test_spade_modulation_fused_into_gamma_beta_conv(S, 64, False, 1, False)
+        test_spade_modulation_fused_into_gamma_beta_conv(S, 64, True, 0, False)
+        test_spade_conv_fused_training_forward_backward(S, 64, False, 1)
+    finally:
+        ops.set_halo(False)
