@@ -934,7 +934,7 @@ int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp,
 }
 
 // ================================================================================ weight gradient, several taps per CTA
-// EXPERIMENTAL (round 2 work item 1, off unless debug key 5 = 3): one CTA accumulates TPC taps of the same (M, N) tile.
+// One CTA accumulates TPC taps of the same (M, N) tile (the default for N sides < 256).
 // The tap-independent operand (dY) is staged ONCE per pixel tile and multiplied against TPC shifted copies of X, each
 // into its own TMEM accumulator, instead of TPC CTAs re-reading dY through L2.  Same operand layouts, descriptors and
 // split-K reduction as tapconv_wgrad_kernel; TPC * BN <= 512 TMEM columns.
@@ -1220,8 +1220,10 @@ int s2e_tapconv_wgrad_tc(const s2e_conv_t* d, const void* x, const void* dy, flo
   // per MMA), and a 64-channel side should not occupy the 128-row M side
   const int swap = (d->Cout > d->Cin) || (d->Cout < 128 && d->Cin >= 128);
   const int nside = swap ? d->Cout : d->Cin;
-  // experimental multi-tap kernel (debug key 5 = 3): narrow layers only, where one CTA per tap re-reads dY nine times
-  if (s2e_debug_get(5) == 3 && d->ntaps >= 3 && nside < 256) {
+  // narrow layers (N side < 256): several taps per CTA against one staged dY tile instead of one CTA per tap re-reading dY
+  // nine times through L2 (B200, round 2: 64->64 196 -> 243, 128->64 389 -> 482, 128->128 752 -> 937 TFLOP/s at 640x384 x 16).
+  // Debug key 5 = 1 restores the one-tap-per-CTA kernel.
+  if (s2e_debug_get(5) != 1 && d->ntaps >= 3 && nside < 256) {
     if (nside >= 128) return launch_wgrad_mt<128, 3>(d, x, dy, dwp, swap, stream);
     return launch_wgrad_mt<64, 3>(d, x, dy, dwp, swap, stream);
   }

@@ -168,10 +168,11 @@ MT_WGRAD_CASES = [
 
 @pytest.mark.parametrize("case", MT_WGRAD_CASES)
 def test_conv_tcgen05_multitap_wgrad(S, case):
-    """Weight gradients of narrow layers (N side < 256) through tapconv_wgrad_mt_kernel: several taps per CTA against
-    one staged dY tile (debug key 5 = 3 forces it for every eligible shape)."""
+    """Weight gradients of narrow layers (N side < 256): tapconv_wgrad_mt_kernel (several taps per CTA against one staged dY
+    tile, the default) and, with debug key 5 = 1, the one-tap-per-CTA kernel it replaced."""
     L, ops = S
-    L.call("s2e_debug_set", 5, 3)
+    conv_case(S, L.IMPL_TC, *case)
+    L.call("s2e_debug_set", 5, 1)
     try:
         conv_case(S, L.IMPL_TC, *case)
     finally:
