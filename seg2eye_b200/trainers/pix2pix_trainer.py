@@ -38,7 +38,15 @@ class Pix2PixTrainer():
             self.old_lr = opt.lr
             self.reducer_G = parallel.GradReducer(list(m.netG.parameters()) + (list(m.netE.parameters()) if m.netE is not None else []))
             self.reducer_D = parallel.GradReducer(list(m.netD.parameters()))
+            if getattr(opt, 'continue_train', False):     # Adam moments / step counts, when a previous run saved them
+                from .. import util
+                util.load_optimizer(self.optimizer_G, 'G', opt.which_epoch, opt, self._opt_nets('G'))
+                util.load_optimizer(self.optimizer_D, 'D', opt.which_epoch, opt, self._opt_nets('D'))
         self._graphs = False
+
+    def _opt_nets(self, which):
+        m = self.pix2pix_model
+        return (('G', m.netG), ('E', m.netE)) if which == 'G' else (('D', m.netD),)
 
     # ------------------------------------------------------------------ step bodies
     def _fb(self, which, data, scale=1.0):
@@ -235,6 +243,10 @@ class Pix2PixTrainer():
     def save(self, epoch):
         if self.rank == 0:      # replicas are identical; concurrent writers of the same file would corrupt it
             self.pix2pix_model_on_one_gpu.save(epoch)
+            if self.opt.isTrain:
+                from .. import util
+                util.save_optimizer(self.optimizer_G, 'G', epoch, self.opt, self._opt_nets('G'))
+                util.save_optimizer(self.optimizer_D, 'D', epoch, self.opt, self._opt_nets('D'))
         if self.world > 1:
             torch.distributed.barrier()
 

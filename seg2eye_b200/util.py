@@ -25,3 +25,48 @@ def load_network(net, label, epoch, opt, save_dir=None):
     ops.bump_weights_epoch()
     print(f"Loaded network from {save_path} for epoch {epoch}")
     return net
+
+
+def _named_params(nets):
+    """'G.fc.weight' style names for the parameters of the (tag, network) pairs, in optimizer order."""
+    return [("%s.%s" % (tag, n), p_) for tag, net in nets if net is not None for n, p_ in net.named_parameters()]
+
+
+def save_optimizer(optimizer, label, epoch, opt, nets):
+    """Beyond the reference (which restarts Adam from zero moments on --continue_train, util/util.py:195-221 saves
+    networks only): `<epoch>_optim_<G|D>.pth` next to the network files -- fp32 CPU tensors keyed by parameter NAME
+    ('G.up_0.conv_0.weight_orig': {'exp_avg', 'exp_avg_sq'}), plus the step count and learning rate.  Files the reference
+    never reads; its own checkpoints are untouched."""
+    save_path = os.path.join(opt.checkpoints_dir, opt.name, '%s_optim_%s.pth' % (epoch, label))
+    os.makedirs(os.path.dirname(save_path), exist_ok=True)
+    names = {id(p_): n for n, p_ in _named_params(nets)}
+    out = {"state": {}, "groups": []}
+    for group in optimizer.param_groups:
+        st = group.get('_s2e_state')
+        out["groups"].append({"lr": group['lr'], "betas": tuple(group['betas']), "eps": group['eps'],
+                              "weight_decay": group['weight_decay'], "step": float(st[0]) if st is not None else 0.0})
+        for p_ in group['params']:
+            s_ = optimizer.state.get(p_)
+            if s_:
+                out["state"][names[id(p_)]] = {k: s_[k].detach().to('cpu') for k in ('exp_avg', 'exp_avg_sq')}
+    torch.save(out, save_path)
+
+
+def load_optimizer(optimizer, label, epoch, opt, nets):
+    """Restore what save_optimizer wrote; returns False (and leaves the optimizer fresh, like the reference) if the file
+    does not exist."""
+    path = os.path.join(opt.checkpoints_dir, opt.name, '%s_optim_%s.pth' % (epoch, label))
+    if not os.path.exists(path):
+        return False
+    blob = torch.load(path, map_location='cpu')
+    params = dict(_named_params(nets))
+    for name, s_ in blob["state"].items():
+        p_ = params[name]
+        optimizer.state[p_] = {k: v.to(device=p_.device, dtype=torch.float32).clone() for k, v in s_.items()}
+    for group, g in zip(optimizer.param_groups, blob["groups"]):
+        group['lr'] = g["lr"]
+        dev = group['params'][0].device
+        group['_s2e_state'] = torch.tensor([g["step"], g["lr"], 0.0, 0.0], dtype=torch.float32, device=dev)
+        group['_s2e_lr'] = g["lr"]
+    print(f"Loaded optimizer state from {path}")
+    return True

@@ -6,8 +6,10 @@ Tolerances (BASELINE.md section 5, bf16 inputs / fp32 accumulation):
   * module level (every SPADE_STYLE ResBlock / D level / E level given the oracle's input):
     forward activations <= 1e-2 relative L2 error (measured 3.5e-3 .. 4.4e-3 per ResBlock);
   * the chained 7-block generator accumulates those independent bf16 roundings: a CPU emulation that rounds the
-    oracle at the same points (conv inputs / weights / outputs) predicts 1.15e-2 at up_3 and 1.7e-2 on the image for
-    these O(1)-scale weights; the device measures 1.2e-2 / 1.9e-2, so the end-to-end image bound is TOL_CHAIN = 3e-2;
+    oracle at the same points (tools/precision_floor.py) predicts 1.1e-2 at up_3 and 1.8e-2 on the image for this small
+    model, 1.4e-2 on the image from the bf16 OPERANDS alone; the device measures 1.2e-2 / 1.7-1.9e-2, so the end-to-end
+    image bound against the oracle is TOL_CHAIN = 2.5e-2 (at the benchmarked width the image error is 1.1-1.4e-2,
+    tests/test_gpu_fullsize.py); two noisy implementations compared with each other get TOL_PAIR = 3e-2;
   * G/D losses after one optimiser step <= 2e-2 relative (absolute floor 2e-2 for the hinge-G term, a mean of signed
     logits that nearly cancels)."""
 import os
@@ -22,7 +24,8 @@ from oracle import seg2eye_oracle as O
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL_ACT = 1e-2
-TOL_CHAIN = 3e-2
+TOL_CHAIN = 2.5e-2
+TOL_PAIR = 3e-2
 TOL_LOSS = 2e-2
 
 
@@ -308,7 +311,7 @@ def test_tcgen05_and_simt_paths_agree_on_a_step(ctx):
         out[impl] = ({k: float(v.reshape(-1)[0]) for k, v in tr.g_losses.items()}, tr.generated.detach().cpu())
     # both paths round at the same points; accumulation-order differences (1-ulp flips, 1e-4 per conv) are amplified
     # by the random-weight network exactly like the bf16 drift itself (measured 2.0e-2 on the image)
-    assert rel(out[None][1], out[L.IMPL_SIMT][1]) < TOL_CHAIN
+    assert rel(out[None][1], out[L.IMPL_SIMT][1]) < TOL_PAIR
     for k in out[None][0]:
         assert abs(out[None][0][k] - out[L.IMPL_SIMT][0][k]) <= TOL_LOSS * abs(out[L.IMPL_SIMT][0][k]) + 2e-2, k
 
@@ -333,7 +336,7 @@ def test_cuda_graph_steps_match_eager(ctx):
             # atomically-accumulated (order-dependent) weight gradients followed by Adam(beta1=0) ~ lr*sign(g)
             tight = it == 0 and not k.startswith("D/")
             assert abs(a - b) <= (2e-3 if tight else TOL_LOSS) * abs(a) + (1e-4 if tight else 2e-2), (it, k, a, b)
-    assert rel(graph.get_latest_generated(), eager.get_latest_generated()) < TOL_CHAIN
+    assert rel(graph.get_latest_generated(), eager.get_latest_generated()) < TOL_PAIR
     nbt = "up_3.norm_0.spade.param_free_norm.num_batches_tracked"
     assert int(graph.pix2pix_model.netG.state_dict()[nbt]) == int(eager.pix2pix_model.netG.state_dict()[nbt])
 
@@ -478,6 +481,15 @@ def test_eval_mode_inference_sweep_vs_oracle(ctx):
     from seg2eye_b200.models.pix2pix_model import Pix2PixModel
     m = Pix2PixModel(ctx.opt)
     sdG, sdE = O.synth_state(O.generator_shapes(ctx.oopt), ctx.seeds["G"]), O.synth_state(O.encoder_shapes(ctx.oopt), ctx.seeds["E"])
+    # eval mode uses the STORED u / v: random unit vectors would give sigma = u^T W v of arbitrary size and sign, i.e. a
+    # network far outside its operating range; converge them first (what any trained checkpoint holds)
+    for sd in (sdG, sdE):
+        for k in [k for k in sd if k.endswith("weight_orig")]:
+            wm = sd[k].reshape(sd[k].shape[0], -1)
+            u, v = sd[k[:-5] + "_u"], sd[k[:-5] + "_v"]
+            for _ in range(8):
+                v.copy_(torch.nn.functional.normalize(wm.t() @ u, dim=0))
+                u.copy_(torch.nn.functional.normalize(wm @ v, dim=0))
     load(m.netG, sdG)
     load(m.netE, sdE)
     m.eval()
@@ -496,3 +508,41 @@ def test_eval_mode_inference_sweep_vs_oracle(ctx):
     assert out.shape == ref.shape and rel(out, ref) < TOL_CHAIN, rel(out, ref)
     after = m.netG.state_dict()
     assert all(torch.equal(before[k], after[k]) for k in before), "eval-mode inference changed buffers"
+
+
+def test_optimizer_state_checkpoint_roundtrip(ctx, tmp_path):
+    """trainer.save() also writes the Adam moments / step counts (`<epoch>_optim_{G,D}.pth`, keyed by
+    parameter name); --continue_train restores networks AND optimizer state, so the resumed run continues the same
+    trajectory instead of restarting Adam from zero moments (what the reference does)."""
+    from seg2eye_b200.trainers.pix2pix_trainer import Pix2PixTrainer
+    opt = SimpleNamespace(**{**vars(ctx.opt), "checkpoints_dir": str(tmp_path), "name": "ck", "no_TTUR": True})
+    c2 = SimpleNamespace(oopt=ctx.oopt, opt=opt, bs=ctx.bs, seeds=ctx.seeds, batch=ctx.batch)
+    tr = _make_trainer(c2)
+    data = {k: v.clone() for k, v in ctx.batch.items()}
+    tr.run_generator_one_step(data)
+    tr.run_discriminator_one_step(data)
+    tr.save("latest")
+    blob = torch.load(os.path.join(str(tmp_path), "ck", "latest_optim_G.pth"))
+    assert blob["groups"][0]["step"] == 1.0 and "G.fc.weight" in blob["state"] and "E.fc_mu.weight" in blob["state"]
+    assert "E.fc_var.weight" not in blob["state"]            # never receives a gradient, never gets Adam state
+    opt2 = SimpleNamespace(**{**vars(opt), "continue_train": True})
+    tr2 = Pix2PixTrainer(opt2)
+    for (n1, p1), (n2, p2) in zip(tr.pix2pix_model.netG.named_parameters(), tr2.pix2pix_model.netG.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2)
+        s1, s2 = tr.optimizer_G.state.get(p1), tr2.optimizer_G.state.get(p2)
+        assert (not s1) == (not s2)
+        if s1:
+            assert torch.equal(s1["exp_avg"], s2["exp_avg"]) and torch.equal(s1["exp_avg_sq"], s2["exp_avg_sq"])
+    assert float(tr2.optimizer_D.param_groups[0]["_s2e_state"][0]) == 1.0
+    # both continue with the same second step (beta1 = 0.5 here, so the restored first moment matters)
+    for t in (tr, tr2):
+        d = {k: v.clone() for k, v in ctx.batch.items()}
+        t.run_generator_one_step(d)
+    a, b = tr.pix2pix_model.netG.state_dict(), tr2.pix2pix_model.netG.state_dict()
+    assert rel(a["up_2.conv_0.weight_orig"], b["up_2.conv_0.weight_orig"]) < 1e-4
+    assert rel(a["up_2.conv_0.weight_orig"] - ctx_sd(ctx)["up_2.conv_0.weight_orig"].cuda(),
+               b["up_2.conv_0.weight_orig"] - ctx_sd(ctx)["up_2.conv_0.weight_orig"].cuda()) < 5e-2
+
+
+def ctx_sd(ctx):
+    return O.synth_state(O.generator_shapes(ctx.oopt), ctx.seeds["G"])
