@@ -198,7 +198,10 @@ int s2e_norm_finalize(const double* acc, int G, int C, double count, double coun
  * backward pass needs to know about `out` (read instead of it: 0.125 B/element instead of 2). */
 /* up_w != 0: x is the [B][H/2][W/2][C] tensor whose nearest-2x up-sampling (generator.py:50) is the block input; up_w = W
  * of the up-sampled map.  The up-sampled copy is never materialised; mean / rstd of the two are identical.  In backward
- * dx is still the gradient w.r.t. the UP-SAMPLED input (B*HW*C); reduce it with s2e_upsample2x_bwd. */
+ * dx is then the gradient w.r.t. the HALF-RESOLUTION x itself, [B][HW/4][C]: the kernel adds the four output pixels of
+ * every source pixel on the spot (the adjoint of the up-sampling), the full-resolution gradient is never written.
+ * style == NULL selects plain SPADE: out = act(norm(x) (1 + gamma) + beta), no style term, no factor 1/2 (dstyle must
+ * be NULL then). */
 /* per-(sample, channel) constants of the fused variant (s2e_conv_t.spade_par): par[b][0..3][c] = rstd, -mean*rstd,
  * 1 + style[b][c], style[b][C + c]; mean / rstd are [G][C] with G = per_sample ? B : 1 */
 int s2e_spade_params(const float* mean, const float* rstd, const float* style, int B, int C, int per_sample, float* par,

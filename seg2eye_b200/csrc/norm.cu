@@ -8,6 +8,13 @@ namespace {
 
 constexpr int NT = 256;
 
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == S2E_ACT_LRELU) return fmaxf(v, 0.2f * v);
+  if (ACT == S2E_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
 // ---------------------------------------------------------------- per-channel sum / sum of squares
 // grid = (chunks, G) ; G = B when per_sample else 1 (then the chunk range spans all samples)
 // body(p, c, acc) consumes one pixel; body4(p, stride, c, acc) consumes pixels p, p+stride, p+2 stride, p+3 stride with all
@@ -143,145 +150,267 @@ __global__ void spade_params_kernel(const float* __restrict__ mean, const float*
 }
 
 // ---------------------------------------------------------------- SPADE+Style forward (elementwise, 8 B/elem)
-// grid = (pixel chunks, B).  A thread owns one 8-channel group: its per-channel constants (mean, rstd, style) are
-// loaded once into registers, then it streams pixels: 3 x 16-byte loads + 1 x 16-byte store per pixel, two pixels in
-// flight per iteration.
-__global__ void __launch_bounds__(NT) spade_style_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
-                                                             const float* __restrict__ style, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, int HW, int C, int per_sample,
-                                                             int act, bf16* __restrict__ out, uint8_t* __restrict__ amask, int up_w) {
-  // amask (optional): one bit per element, set where out > 0 -- all the backward pass needs of `out` (16x fewer bytes)
+// grid = (unit chunks, B).  A thread owns one 8-channel group: its per-channel constants (mean, rstd, style, with the output
+// scale folded in) live in registers, then it streams pixels: 3 x 16-byte loads + 1 x 16-byte store per pixel.
+//   out = act( t (1 + gamma) + os beta + v ),   t = os (x - mu) rs,   v = os (x (1 + s0) + s1)      (os = 1/2; plain SPADE: os = 1, v = 0)
+// UP (nearest-2x up-sampled input): a thread walks SOURCE pixels, so x, t and v are formed once per four output pixels.
+// amask (optional): one bit per element, set where out > 0 -- all the backward pass needs of `out` (16x fewer bytes).
+template <int ACT, bool UP>
+__global__ void __launch_bounds__(NT) spade_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gb,
+                                                       const float* __restrict__ style, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, int HW, int C, int per_sample,
+                                                       bf16* __restrict__ out, uint8_t* __restrict__ amask, int W) {
   const int b = blockIdx.y;
-  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const int units = UP ? (HW >> 2) : HW;
+  const long long chunk = ((long long)units + gridDim.x - 1) / gridDim.x;
   const long long q0 = (long long)blockIdx.x * chunk;
-  const long long q1 = min((long long)HW, q0 + chunk);
+  const long long q1 = min((long long)units, q0 + chunk);
   const int cg = C >> 3;
   const float* mu_b = mean + (per_sample ? b * C : 0);
   const float* rs_b = rstd + (per_sample ? b * C : 0);
-  // style == NULL: plain SPADE (normalization.py:91-105 alone): out = act((x*rs - mu*rs)*(1+g) + beta), no style term, no 1/2
   const float* st_b = style ? style + (size_t)b * 2 * C : nullptr;
   const float os = style ? 0.5f : 1.0f;
+  const long long base = (long long)b * HW;
   for (int cg0 = 0; cg0 < cg; cg0 += NT) {
     const int ncg = min(NT, cg - cg0);
     const int lanes = NT / ncg;
     const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
     if (my_lane >= lanes) continue;
     const int c = (cg0 + my_cg) * 8;
-    float k_a[8], k_b[8], k_c[8];  // out = os*( (x*rs - mu*rs)*(1+g) + beta + x*(1+s0) + s1 )
+    const int mcol = cg0 + my_cg;
+    float kA[8], kB[8], kC[8], kD[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float rs = rs_b[c + j];
-      k_a[j] = rs;
-      k_b[j] = -mu_b[c + j] * rs;
-      k_c[j] = st_b ? 1.f + st_b[c + j] : 0.f;
+      kA[j] = os * rs;
+      kB[j] = -os * mu_b[c + j] * rs;
+      kC[j] = st_b ? os * (1.f + st_b[c + j]) : 0.f;
+      kD[j] = st_b ? os * st_b[C + c + j] : 0.f;
     }
-    float s1v[8];
+    auto emit = [&](long long p, const float* t, const float* v, const bf16x8& vg, const bf16x8& vb) {
+      float gf[8], bf_[8], o[8];
+      unpack8(vg, gf);
+      unpack8(vb, bf_);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s1v[j] = st_b ? st_b[C + c + j] : 0.f;
-    const long long base = (long long)b * HW;
-    long long q = q0 + my_lane;
-    for (; q + lanes < q1; q += 2 * lanes) {
-      const long long pA = base + q, pB = base + q + lanes;
-      const bf16x8 xa = ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), xb = ld_stream8(x + x_pixel(b, q + lanes, HW, up_w) * C + c);
-      const bf16x8 ga = ld_stream8(gb + pA * 2 * C + c), gbb = ld_stream8(gb + pB * 2 * C + c);
-      const bf16x8 ba = ld_stream8(gb + pA * 2 * C + C + c), bb = ld_stream8(gb + pB * 2 * C + C + c);
-      float xf[8], gf[8], bf_[8], o[8];
-      unpack8(xa, xf); unpack8(ga, gf); unpack8(ba, bf_);
+      for (int j = 0; j < 8; ++j) o[j] = act_t<ACT>(fmaf(t[j], gf[j], t[j]) + fmaf(os, bf_[j], v[j]));
+      st_stream8(out + p * C + c, pack8(o));
+      if (amask) amask[p * cg + mcol] = sign_bits8(o);
+    };
+    if (UP) {
+      const unsigned Ws = (unsigned)W >> 1;
+      for (long long u = q0 + my_lane; u < q1; u += lanes) {
+        const unsigned uu = (unsigned)u;
+        const unsigned hs = uu / Ws, ws = uu - hs * Ws;
+        const long long p00 = base + (long long)(2u * hs) * W + 2u * ws;
+        const long long pk[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+        const bf16x8 vx = ld_stream8(x + ((long long)b * units + u) * C + c);
+        bf16x8 vg[4], vb[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = act_apply(os * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
-      st_stream8(out + pA * C + c, pack8(o));
-      if (amask) amask[pA * cg + cg0 + my_cg] = sign_bits8(o);
-      unpack8(xb, xf); unpack8(gbb, gf); unpack8(bb, bf_);
+        for (int k = 0; k < 4; ++k) {
+          vg[k] = ld_stream8(gb + pk[k] * 2 * C + c);
+          vb[k] = ld_stream8(gb + pk[k] * 2 * C + C + c);
+        }
+        float xf[8], t[8], v[8];
+        unpack8(vx, xf);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = act_apply(os * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
-      st_stream8(out + pB * C + c, pack8(o));
-      if (amask) amask[pB * cg + cg0 + my_cg] = sign_bits8(o);
-    }
-    for (; q < q1; q += lanes) {
-      const long long pA = base + q;
-      float xf[8], gf[8], bf_[8], o[8];
-      unpack8(ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), xf);
-      unpack8(ld_stream8(gb + pA * 2 * C + c), gf);
-      unpack8(ld_stream8(gb + pA * 2 * C + C + c), bf_);
+        for (int j = 0; j < 8; ++j) {
+          t[j] = fmaf(xf[j], kA[j], kB[j]);
+          v[j] = fmaf(xf[j], kC[j], kD[j]);
+        }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = act_apply(os * (fmaf(fmaf(xf[j], k_a[j], k_b[j]), 1.f + gf[j], bf_[j]) + fmaf(xf[j], k_c[j], s1v[j])), act);
-      st_stream8(out + pA * C + c, pack8(o));
-      if (amask) amask[pA * cg + cg0 + my_cg] = sign_bits8(o);
+        for (int k = 0; k < 4; ++k) emit(pk[k], t, v, vg[k], vb[k]);
+      }
+    } else {
+      auto one = [&](long long p, const bf16x8& vx, const bf16x8& vg, const bf16x8& vb) {
+        float xf[8], t[8], v[8];
+        unpack8(vx, xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          t[j] = fmaf(xf[j], kA[j], kB[j]);
+          v[j] = fmaf(xf[j], kC[j], kD[j]);
+        }
+        emit(p, t, v, vg, vb);
+      };
+      long long q = q0 + my_lane;
+      for (; q + lanes < q1; q += 2 * lanes) {      // two pixels in flight
+        const long long pA = base + q, pB = base + q + lanes;
+        const bf16x8 xa = ld_stream8(x + pA * C + c), xb = ld_stream8(x + pB * C + c);
+        const bf16x8 ga = ld_stream8(gb + pA * 2 * C + c), gbb = ld_stream8(gb + pB * 2 * C + c);
+        const bf16x8 ba = ld_stream8(gb + pA * 2 * C + C + c), bb = ld_stream8(gb + pB * 2 * C + C + c);
+        one(pA, xa, ga, ba);
+        one(pB, xb, gbb, bb);
+      }
+      for (; q < q1; q += lanes) {
+        const long long p = base + q;
+        one(p, ld_stream8(x + p * C + c), ld_stream8(gb + p * 2 * C + c), ld_stream8(gb + p * 2 * C + C + c));
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------- SPADE+Style backward
-// pass 1: per (sample, channel) sums  S1 = sum dxh, S2 = sum dxh*xh, S3 = sum g*x, S4 = sum g, S5 = sum g*xh
-// (S4 / S5 are also the per-channel sums of dbeta / dgamma, i.e. the bias gradients of the gamma|beta convolution)
-__global__ void __launch_bounds__(NT) spade_style_bwd_reduce_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ amask,
-                                                                    const bf16* __restrict__ x, const bf16* __restrict__ gb,
-                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                    int HW, int C, int per_sample, int act, double* __restrict__ racc,
-                                                                    int up_w, int gstride, float os) {
-  const int b = blockIdx.y;
-  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
-  const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
-  const long long b1 = min((long long)(b + 1) * HW, b0 + chunk);
-  const float* mu = mean + (per_sample ? b * C : 0);
-  const float* rs = rstd + (per_sample ? b * C : 0);
-  auto one = [&](long long p, int c, float(*a)[8]) {
-    float df[8], xf[8], gf[8];
-    unpack8(ld_stream8(dout + p * C + c), df);
-    unpack8(ld_stream8(x + x_pixel(b, p - (long long)b * HW, HW, up_w) * C + c), xf);
-    unpack8(ld_stream8(gb + p * gstride + c), gf);
-    const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * (C >> 3) + (c >> 3)] : 0xffu;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float g = os * df[j];
-      if (act == S2E_ACT_LRELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.2f;
-      if (act == S2E_ACT_RELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.f;
-      const float xh = (xf[j] - __ldg(mu + c + j)) * __ldg(rs + c + j);
-      const float dxh = g * (1.f + gf[j]);
-      a[0][j] += dxh;
-      a[1][j] = fmaf(dxh, xh, a[1][j]);
-      a[2][j] = fmaf(g, xf[j], a[2][j]);
-      a[3][j] += g;
-      a[4][j] = fmaf(g, xh, a[4][j]);
-    }
-  };
-  auto four = [&](long long p, long long st, int c, float(*a)[8]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) one(p + i * st, c, a);   // the compiler hoists the independent streaming loads
-  };
-  block_channel_reduce<5>(C, b0, b1, racc + (size_t)b * 5 * C, one, four);
+// Notation: g = os * dout * act'(out) (os = 1/2 with the style half, 1 for plain SPADE), xh = (x - mu) * rs,
+// dxh = g * (1 + gamma).  BatchNorm / InstanceNorm backward needs m1 = mean(dxh), m2 = mean(dxh * xh) first:
+//   pass 1 (reduce): per (sample, channel) raw moments  T1 = sum g, T2 = sum g x, T3 = sum g gamma, T4 = sum g gamma x
+//                    -- no per-channel constants in the hot loop; everything else is linear in them (fold kernel)
+//   fold           : S1 = sum dxh = T1 + T3,  S2 = sum dxh xh = rs (T2 + T4) + E (T1 + T3),  E = -mu rs,
+//                    dstyle = (T2, T1),  sum dgamma = rs T2 + E T1,  sum dbeta = T1,  m1, m2
+//   pass 2 (apply) : dx = g (rs (1 + gamma) + s0') + x (-rs^2 m2) + (rs^2 m2 mu - rs m1),  dgamma = g (x rs + E),  dbeta = g
+// Nearest-2x up-sampled input (UP): a thread walks SOURCE pixels; the four output pixels of a source pixel share x, so x is
+// loaded once, and pass 2 adds their four dx on the spot: the gradient leaves at the source resolution (the adjoint of the
+// up-sampling costs no pass of its own and the full-resolution dx is never written).
+template <int ACT>
+__device__ __forceinline__ float gate(uint32_t mbits, int j, float os, float osn) {
+  if (ACT == S2E_ACT_NONE) return os;
+  return ((mbits >> j) & 1u) ? os : osn;
 }
 
-// fold the per-sample sums: m1/m2 per stat group (float [G][2][C]), dstyle [B][2C] and, optionally, chsum [3][C] =
-// per-channel sums over the whole batch of dgamma, dbeta and dx.  The last one needs no extra pass: the normalisation
-// part of dx sums to zero over the pixels its statistics were taken from, so sum dx = sum_b (1 + s0[b]) * S4[b].
+// block_channel_reduce with U units (pixels / source pixels) per loop trip, their loads free to overlap
+template <int NACC, int U, typename F>
+__device__ __forceinline__ void block_channel_reduce_u(int C, long long u_begin, long long u_end, double* out /*[NACC][C]*/, F&& body) {
+  extern __shared__ float red[];
+  const int cg = C >> 3;
+  const int tid = threadIdx.x;
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = tid % ncg, my_lane = tid / ncg;
+    float acc[NACC][8];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+    if (my_lane < lanes) {
+      long long p = u_begin + my_lane;
+      for (; p + (long long)(U - 1) * lanes < u_end; p += (long long)U * lanes) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) body(p + (long long)i * lanes, (cg0 + my_cg) * 8, acc);
+      }
+      for (; p < u_end; p += lanes) body(p, (cg0 + my_cg) * 8, acc);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      __syncthreads();
+      if (my_lane < lanes) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(my_lane * ncg + my_cg) * 8 + j] = acc[a][j];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < ncg * 8; idx += NT) {
+        float sum = 0.f;
+        for (int l = 0; l < lanes; ++l) sum += red[l * ncg * 8 + idx];
+        atomicAdd(out + (size_t)a * C + cg0 * 8 + idx, (double)sum);
+      }
+    }
+  }
+}
+
+// pass 1.  racc[b][0..3][C] += T1..T4 (row 4 unused).  W = output width (UP only).
+template <int ACT, bool UP>
+__global__ void __launch_bounds__(NT) spade_bwd_reduce_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ amask,
+                                                              const bf16* __restrict__ x, const bf16* __restrict__ gb, int HW, int C,
+                                                              double* __restrict__ racc, int W, int gstride, float os) {
+  const int b = blockIdx.y;
+  const int units = UP ? (HW >> 2) : HW;
+  const long long chunk = ((long long)units + gridDim.x - 1) / gridDim.x;
+  const long long u0 = (long long)blockIdx.x * chunk;
+  const long long u1 = min((long long)units, u0 + chunk);
+  const float osn = ACT == S2E_ACT_LRELU ? 0.2f * os : 0.f;
+  const int cgs = C >> 3;
+  const long long base = (long long)b * HW;
+  auto body = [&](long long u, int c, float(*a)[8]) {
+    if (UP) {
+      const unsigned Ws = (unsigned)W >> 1, uu = (unsigned)u;
+      const unsigned hs = uu / Ws, ws = uu - hs * Ws;
+      const long long p00 = base + (long long)(2u * hs) * W + 2u * ws;
+      const long long pk[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+      bf16x8 vd[4], vg[4];
+      uint32_t mb[4];
+      const bf16x8 vx = ld_stream8(x + ((long long)b * units + u) * C + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vd[k] = ld_stream8(dout + pk[k] * C + c);
+        vg[k] = ld_stream8(gb + pk[k] * gstride + c);
+        mb[k] = ACT != S2E_ACT_NONE ? (uint32_t)amask[pk[k] * cgs + (c >> 3)] : 0xffu;
+      }
+      float xf[8], G[8], GG[8];
+      unpack8(vx, xf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) G[j] = GG[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float df[8], gf[8];
+        unpack8(vd[k], df);
+        unpack8(vg[k], gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = df[j] * gate<ACT>(mb[k], j, os, osn);
+          G[j] += g;
+          GG[j] = fmaf(g, gf[j], GG[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[0][j] += G[j];
+        a[1][j] = fmaf(G[j], xf[j], a[1][j]);
+        a[2][j] += GG[j];
+        a[3][j] = fmaf(GG[j], xf[j], a[3][j]);
+      }
+    } else {
+      const long long p = base + u;
+      const bf16x8 vd = ld_stream8(dout + p * C + c), vx = ld_stream8(x + p * C + c), vg = ld_stream8(gb + p * gstride + c);
+      const uint32_t mbits = ACT != S2E_ACT_NONE ? (uint32_t)amask[p * cgs + (c >> 3)] : 0xffu;
+      float df[8], xf[8], gf[8];
+      unpack8(vd, df);
+      unpack8(vx, xf);
+      unpack8(vg, gf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = df[j] * gate<ACT>(mbits, j, os, osn);
+        const float gg = g * gf[j];
+        a[0][j] += g;
+        a[1][j] = fmaf(g, xf[j], a[1][j]);
+        a[2][j] += gg;
+        a[3][j] = fmaf(gg, xf[j], a[3][j]);
+      }
+    }
+  };
+  block_channel_reduce_u<4, UP ? 1 : 4>(C, u0, u1, racc + (size_t)b * 5 * C, body);
+}
+
+// fold: raw moments -> m1 / m2 per statistics group (float [G][2][C]), dstyle [B][2C] and, optionally, chsum [3][C] =
+// per-channel sums over the whole batch of dgamma, dbeta and dx.  The last one needs no extra pass: the normalisation part
+// of dx sums to zero over the pixels its statistics were taken from, so sum dx = sum_b (1 + s0[b]) * T1[b].
 __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int B, int C, int per_sample, double count,
-                                            const float* __restrict__ style, float* __restrict__ m12,
+                                            const float* __restrict__ style, const float* __restrict__ mean,
+                                            const float* __restrict__ rstd, float* __restrict__ m12,
                                             float* __restrict__ dstyle, float* __restrict__ chsum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
   const double* r = racc + (size_t)b * 5 * C;
   if (dstyle) {
-    dstyle[(size_t)b * 2 * C + c] = (float)r[2 * C + c];
-    dstyle[(size_t)b * 2 * C + C + c] = (float)r[3 * C + c];
+    dstyle[(size_t)b * 2 * C + c] = (float)r[C + c];        // d s0 = sum g x
+    dstyle[(size_t)b * 2 * C + C + c] = (float)r[c];        // d s1 = sum g
   }
   if (per_sample) {
-    m12[(size_t)b * 2 * C + c] = (float)(r[c] / count);
-    m12[(size_t)b * 2 * C + C + c] = (float)(r[C + c] / count);
+    const double rs = (double)rstd[(size_t)b * C + c], E = -(double)mean[(size_t)b * C + c] * rs;
+    const double s1 = r[c] + r[2 * C + c];
+    const double s2 = rs * (r[C + c] + r[3 * C + c]) + E * s1;
+    m12[(size_t)b * 2 * C + c] = (float)(s1 / count);
+    m12[(size_t)b * 2 * C + C + c] = (float)(s2 / count);
   }
   if (b == 0 && (!per_sample || chsum)) {
     double s1 = 0, s2 = 0, sg = 0, sb = 0, sx = 0;
     for (int bb = 0; bb < B; ++bb) {
       const double* q = racc + (size_t)bb * 5 * C;
-      s1 += q[c];
-      s2 += q[C + c];
-      sb += q[3 * C + c];
-      sg += q[4 * C + c];
-      if (style) sx += (1.0 + (double)style[(size_t)bb * 2 * C + c]) * q[3 * C + c];
+      const int so = per_sample ? bb * C : 0;
+      const double rs = (double)rstd[so + c], E = -(double)mean[so + c] * rs;
+      const double t1 = q[c], t2 = q[C + c], t3 = q[2 * C + c], t4 = q[3 * C + c];
+      s1 += t1 + t3;
+      s2 += rs * (t2 + t4) + E * (t1 + t3);
+      sb += t1;
+      sg += rs * t2 + E * t1;
+      if (style) sx += (1.0 + (double)style[(size_t)bb * 2 * C + c]) * t1;
     }
     if (!per_sample) {
       m12[c] = (float)(s1 / count);
@@ -295,77 +424,127 @@ __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int
   }
 }
 
-// pass 2: dx = rstd*(dxh - m1 - xh*m2) + g*(1+s0) ; dgamma = g*xh ; dbeta = g     (same thread mapping as the forward)
-__global__ void __launch_bounds__(NT) spade_style_bwd_apply_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ amask,
-                                                                   const bf16* __restrict__ x, const bf16* __restrict__ gb,
-                                                                   const float* __restrict__ style, const float* __restrict__ mean,
-                                                                   const float* __restrict__ rstd, const float* __restrict__ m12,
-                                                                   int HW, int C, int per_sample, int act,
-                                                                   bf16* __restrict__ dx, int dx_acc, bf16* __restrict__ dgb, int up_w,
-                                                                   int gstride) {
+// pass 2.  dx: [B][HW][C], or with UP the gradient w.r.t. the half-resolution source [B][HW/4][C] (2x2 sums folded in).
+template <int ACT, bool UP>
+__global__ void __launch_bounds__(NT) spade_bwd_apply_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ amask,
+                                                             const bf16* __restrict__ x, const bf16* __restrict__ gb,
+                                                             const float* __restrict__ style, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ m12, int HW,
+                                                             int C, int per_sample, bf16* __restrict__ dx, int dx_acc,
+                                                             bf16* __restrict__ dgb, int W, int gstride) {
   const int b = blockIdx.y;
-  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const int units = UP ? (HW >> 2) : HW;
+  const long long chunk = ((long long)units + gridDim.x - 1) / gridDim.x;
   const long long q0 = (long long)blockIdx.x * chunk;
-  const long long q1 = min((long long)HW, q0 + chunk);
+  const long long q1 = min((long long)units, q0 + chunk);
   const int cg = C >> 3;
   const int so = per_sample ? b * C : 0;
   const float* m1p = m12 + (per_sample ? (size_t)b * 2 * C : 0);
   const float* s0p = style ? style + (size_t)b * 2 * C : nullptr;
   const float os = style ? 0.5f : 1.0f;
+  const float osn = ACT == S2E_ACT_LRELU ? 0.2f * os : 0.f;
+  const long long base = (long long)b * HW;
   for (int cg0 = 0; cg0 < cg; cg0 += NT) {
     const int ncg = min(NT, cg - cg0);
     const int lanes = NT / ncg;
     const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
     if (my_lane >= lanes) continue;
     const int c = (cg0 + my_cg) * 8;
-    float rsd[8], mu[8], m1[8], m2[8], s0[8];
+    const int mcol = cg0 + my_cg;
+    float kA[8], kR[8], kC[8], kD[8], kE[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      rsd[j] = rstd[so + c + j];
-      mu[j] = mean[so + c + j];
-      m1[j] = m1p[c + j];
-      m2[j] = m1p[C + c + j];
-      s0[j] = s0p ? 1.f + s0p[c + j] : 0.f;
+      const float rs = rstd[so + c + j], mu = mean[so + c + j], m1 = m1p[c + j], m2 = m1p[C + c + j];
+      kR[j] = rs;
+      kA[j] = rs + (s0p ? 1.f + s0p[c + j] : 0.f);
+      kC[j] = -rs * rs * m2;
+      kD[j] = rs * rs * m2 * mu - rs * m1;
+      kE[j] = -mu * rs;
     }
-    // two pixels per iteration: all six 16-byte loads are issued before the first use (memory-level parallelism)
-    auto finish = [&](long long p, const bf16x8& vd, const bf16x8& vx, const bf16x8& vg, uint32_t mbits) {
-      float df[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
-      if (dx_acc) unpack8(*reinterpret_cast<const bf16x8*>(dx + p * C + c), prev);
-      unpack8(vd, df); unpack8(vx, xf); unpack8(vg, gf);
+    if (UP) {
+      const unsigned Ws = (unsigned)W >> 1;
+      for (long long u = q0 + my_lane; u < q1; u += lanes) {
+        const unsigned uu = (unsigned)u;
+        const unsigned hs = uu / Ws, ws = uu - hs * Ws;
+        const long long p00 = base + (long long)(2u * hs) * W + 2u * ws;
+        const long long pk[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+        const long long ps = ((long long)b * units + u) * C + c;
+        bf16x8 vd[4], vg[4];
+        uint32_t mb[4];
+        const bf16x8 vx = ld_stream8(x + ps);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float g = os * df[j];
-        if (act == S2E_ACT_LRELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.2f;
-        if (act == S2E_ACT_RELU) g *= ((mbits >> j) & 1u) ? 1.f : 0.f;
-        const float xh = (xf[j] - mu[j]) * rsd[j];
-        const float dxh = g * (1.f + gf[j]);
-        float d = rsd[j] * (dxh - m1[j] - xh * m2[j]) + g * s0[j];
-        if (dx_acc) d += prev[j];
-        odx[j] = d;
-        odg[j] = g * xh;
-        odb[j] = g;
+        for (int k = 0; k < 4; ++k) {
+          vd[k] = ld_stream8(dout + pk[k] * C + c);
+          vg[k] = ld_stream8(gb + pk[k] * gstride + c);
+          mb[k] = ACT != S2E_ACT_NONE ? (uint32_t)amask[pk[k] * cg + mcol] : 0xffu;
+        }
+        float xf[8], xh[8], acc[8];
+        unpack8(vx, xf);
+        if (dx_acc) {
+          unpack8(*reinterpret_cast<const bf16x8*>(dx + ps), acc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[j] = fmaf(xf[j], kR[j], kE[j]);
+          acc[j] = fmaf(4.f, fmaf(xf[j], kC[j], kD[j]), acc[j]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float df[8], gf[8], odg[8], odb[8];
+          unpack8(vd[k], df);
+          unpack8(vg[k], gf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float g = df[j] * gate<ACT>(mb[k], j, os, osn);
+            acc[j] = fmaf(g, fmaf(kR[j], gf[j], kA[j]), acc[j]);
+            odg[j] = g * xh[j];
+            odb[j] = g;
+          }
+          st_stream8(dgb + pk[k] * 2 * C + c, pack8(odg));
+          st_stream8(dgb + pk[k] * 2 * C + C + c, pack8(odb));
+        }
+        *reinterpret_cast<bf16x8*>(dx + ps) = pack8(acc);
       }
-      *reinterpret_cast<bf16x8*>(dx + p * C + c) = pack8(odx);
-      st_stream8(dgb + p * 2 * C + c, pack8(odg));
-      st_stream8(dgb + p * 2 * C + C + c, pack8(odb));
-    };
-    const long long base = (long long)b * HW;
-    const int mcol = cg0 + my_cg;
-    long long q = q0 + my_lane;
-    for (; q + lanes < q1; q += 2 * lanes) {
-      const long long pA = base + q, pB = base + q + lanes;
-      const bf16x8 da = ld_stream8(dout + pA * C + c), db = ld_stream8(dout + pB * C + c);
-      const bf16x8 xa = ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), xb = ld_stream8(x + x_pixel(b, q + lanes, HW, up_w) * C + c);
-      const bf16x8 ga = ld_stream8(gb + pA * gstride + c), gb2 = ld_stream8(gb + pB * gstride + c);
-      const uint32_t ma = act != S2E_ACT_NONE ? (uint32_t)amask[pA * cg + mcol] : 0xffu;
-      const uint32_t mb = act != S2E_ACT_NONE ? (uint32_t)amask[pB * cg + mcol] : 0xffu;
-      finish(pA, da, xa, ga, ma);
-      finish(pB, db, xb, gb2, mb);
-    }
-    for (; q < q1; q += lanes) {
-      const long long p = base + q;
-      const uint32_t mbits = act != S2E_ACT_NONE ? (uint32_t)amask[p * cg + mcol] : 0xffu;
-      finish(p, ld_stream8(dout + p * C + c), ld_stream8(x + x_pixel(b, q, HW, up_w) * C + c), ld_stream8(gb + p * gstride + c), mbits);
+    } else {
+      // two pixels per iteration: all six 16-byte loads are issued before the first use
+      auto finish = [&](long long p, const bf16x8& vd, const bf16x8& vx, const bf16x8& vg, uint32_t mbits) {
+        float df[8], xf[8], gf[8], odx[8], odg[8], odb[8], prev[8];
+        if (dx_acc) unpack8(*reinterpret_cast<const bf16x8*>(dx + p * C + c), prev);
+        unpack8(vd, df);
+        unpack8(vx, xf);
+        unpack8(vg, gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = df[j] * gate<ACT>(mbits, j, os, osn);
+          float d = fmaf(g, fmaf(kR[j], gf[j], kA[j]), fmaf(xf[j], kC[j], kD[j]));
+          if (dx_acc) d += prev[j];
+          odx[j] = d;
+          odg[j] = g * fmaf(xf[j], kR[j], kE[j]);
+          odb[j] = g;
+        }
+        *reinterpret_cast<bf16x8*>(dx + p * C + c) = pack8(odx);
+        st_stream8(dgb + p * 2 * C + c, pack8(odg));
+        st_stream8(dgb + p * 2 * C + C + c, pack8(odb));
+      };
+      long long q = q0 + my_lane;
+      for (; q + lanes < q1; q += 2 * lanes) {
+        const long long pA = base + q, pB = base + q + lanes;
+        const bf16x8 da = ld_stream8(dout + pA * C + c), db = ld_stream8(dout + pB * C + c);
+        const bf16x8 xa = ld_stream8(x + pA * C + c), xb = ld_stream8(x + pB * C + c);
+        const bf16x8 ga = ld_stream8(gb + pA * gstride + c), gb2 = ld_stream8(gb + pB * gstride + c);
+        const uint32_t ma = ACT != S2E_ACT_NONE ? (uint32_t)amask[pA * cg + mcol] : 0xffu;
+        const uint32_t mb = ACT != S2E_ACT_NONE ? (uint32_t)amask[pB * cg + mcol] : 0xffu;
+        finish(pA, da, xa, ga, ma);
+        finish(pB, db, xb, gb2, mb);
+      }
+      for (; q < q1; q += lanes) {
+        const long long p = base + q;
+        const uint32_t mbits = ACT != S2E_ACT_NONE ? (uint32_t)amask[p * cg + mcol] : 0xffu;
+        finish(p, ld_stream8(dout + p * C + c), ld_stream8(x + p * C + c), ld_stream8(gb + p * gstride + c), mbits);
+      }
     }
   }
 }
@@ -500,9 +679,9 @@ int ew_chunks(int HW, int B, int C) {
   if (want > maxc) want = maxc;
   return (int)(want < 1 ? 1 : want);
 }
-int red_chunks(long long pixels, int G) {
-  // aim for ~4 blocks per SM overall, at least 64 pixels per block
-  long long want = ((long long)s2e_num_sms() * 4 + G - 1) / G;
+int red_chunks(long long pixels, int G, int blocks_per_sm = 4) {
+  // aim for `blocks_per_sm` resident blocks per SM overall (one full wave), at least 64 pixels per block
+  long long want = blocks_per_sm == 4 ? ((long long)s2e_num_sms() * 4 + G - 1) / G : ((long long)s2e_num_sms() * blocks_per_sm) / G;
   long long maxc = (pixels + 63) / 64;
   if (want > maxc) want = maxc;
   return (int)(want < 1 ? 1 : want);
@@ -583,9 +762,20 @@ int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const
   S2E_REQUIRE(C % 8 == 0, "spade_style_fwd needs C %% 8 == 0 (C=%d)", C);
   S2E_REQUIRE(up_w == 0 || (up_w % 2 == 0 && HW % up_w == 0 && (HW / up_w) % 2 == 0), "spade_style_fwd: bad up-sampled width %d", up_w);
   if ((long long)B * HW == 0) return S2E_OK;
-  dim3 grid(ew_chunks(HW, B, C), B);
-  spade_style_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gb, style, mean, rstd, HW, C,
-                                                                 per_sample, act, (bf16*)out, act_mask, up_w);
+  dim3 grid(ew_chunks(up_w ? HW / 4 : HW, B, C), B);
+#define S2E_SPADE_FWD(ACT_, UP_)                                                                                          \
+  spade_fwd_kernel<ACT_, UP_><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gb, style, mean, rstd, HW, C, \
+                                                                     per_sample, (bf16*)out, act_mask, up_w)
+  if (up_w) {
+    if (act == S2E_ACT_LRELU) S2E_SPADE_FWD(S2E_ACT_LRELU, true);
+    else if (act == S2E_ACT_RELU) S2E_SPADE_FWD(S2E_ACT_RELU, true);
+    else S2E_SPADE_FWD(S2E_ACT_NONE, true);
+  } else {
+    if (act == S2E_ACT_LRELU) S2E_SPADE_FWD(S2E_ACT_LRELU, false);
+    else if (act == S2E_ACT_RELU) S2E_SPADE_FWD(S2E_ACT_RELU, false);
+    else S2E_SPADE_FWD(S2E_ACT_NONE, false);
+  }
+#undef S2E_SPADE_FWD
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }
@@ -604,19 +794,34 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
   S2E_REQUIRE(style || !dstyle, "spade_style_bwd: plain SPADE (style == NULL) has no style gradient");
   S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 5 * C, st));
   float* m12 = (float*)(racc + (size_t)B * 5 * C);
-  dim3 grid(red_chunks(HW, B), B);
-  spade_style_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x,
-                                                                (const bf16*)gb, mean, rstd, HW, C, per_sample, act, racc, up_w, gstride,
-                                                                style ? 0.5f : 1.0f);
-  S2E_LAUNCH_CHECK();
+  const float os = style ? 0.5f : 1.0f;
+  const int units = up_w ? HW / 4 : HW;     // source pixels when the up-sampling is folded in
+  dim3 grid(red_chunks(units, B, 3), B);     // ~75-98 registers: three resident blocks per SM, one wave
+  dim3 grid2(ew_chunks(units, B, C), B);
   const double count = per_sample ? (double)HW : (double)B * HW;
-  spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, m12, dstyle, chsum);
-  S2E_LAUNCH_CHECK();
-  dim3 grid2(ew_chunks(HW, B, C), B);
-  spade_style_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, style,
-                                                     mean, rstd, m12, HW, C, per_sample, act, (bf16*)dx, dx_accumulate,
-                                                     (bf16*)dgb, up_w, gstride);
-  S2E_LAUNCH_CHECK();
+#define S2E_SPADE_BWD(ACT_, UP_)                                                                                              \
+  do {                                                                                                                        \
+    spade_bwd_reduce_kernel<ACT_, UP_><<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, \
+                                                                      HW, C, racc, up_w, gstride, os);                        \
+    S2E_LAUNCH_CHECK();                                                                                                       \
+    spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, mean, rstd, m12,  \
+                                                                      dstyle, chsum);                                         \
+    S2E_LAUNCH_CHECK();                                                                                                       \
+    spade_bwd_apply_kernel<ACT_, UP_><<<grid2, NT, 0, st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, style, \
+                                                            mean, rstd, m12, HW, C, per_sample, (bf16*)dx, dx_accumulate,     \
+                                                            (bf16*)dgb, up_w, gstride);                                       \
+    S2E_LAUNCH_CHECK();                                                                                                       \
+  } while (0)
+  if (up_w) {
+    if (act == S2E_ACT_LRELU) S2E_SPADE_BWD(S2E_ACT_LRELU, true);
+    else if (act == S2E_ACT_RELU) S2E_SPADE_BWD(S2E_ACT_RELU, true);
+    else S2E_SPADE_BWD(S2E_ACT_NONE, true);
+  } else {
+    if (act == S2E_ACT_LRELU) S2E_SPADE_BWD(S2E_ACT_LRELU, false);
+    else if (act == S2E_ACT_RELU) S2E_SPADE_BWD(S2E_ACT_RELU, false);
+    else S2E_SPADE_BWD(S2E_ACT_NONE, false);
+  }
+#undef S2E_SPADE_BWD
   return S2E_OK;
 }
 

@@ -633,7 +633,9 @@ class SpadeStyleFn(torch.autograd.Function):
         st = L.stream()
         racc = torch.empty(B * 5 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
         accumulate = sink is not None and sink.buf is not None
-        dx = sink.buf if accumulate else torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)   # w.r.t. the (H, W) input
+        # gradient w.r.t. x itself: with `up` the kernel adds the four output pixels of every source pixel on the spot (the
+        # adjoint of the nearest-2x up-sampling), so the full-resolution gradient is never written
+        dx = sink.buf if accumulate else torch.empty_like(x)
         last = True
         if sink is not None:
             sink.seen += 1
@@ -652,13 +654,9 @@ class SpadeStyleFn(torch.autograd.Function):
         dgb._s2e_chsum = chsum[:2 * Cc]
         gx = None
         if last:
-            if up:      # adjoint of the nearest-2x up-sampling: 2x2 sums
-                gx = torch.empty_like(x)
-                L.call("s2e_upsample2x_bwd", L.ptr(dx), B, H // 2, W // 2, Cc, L.ptr(gx), st)
-            else:
-                gx = dx
-                if sink is None:
-                    gx._s2e_chsum = chsum[2 * Cc:]
+            gx = dx
+            if sink is None and not up:
+                gx._s2e_chsum = chsum[2 * Cc:]
         return gx, dgb, dstyle, None, None, None, None, None, None
 
 
@@ -740,7 +738,7 @@ class SpadeConvFn(torch.autograd.Function):
         # ---- SPADE+Style backward (gamma kept alone: stride Cc)
         racc = torch.empty(B * 5 * Cc + (B * 2 * Cc + 1) // 2, dtype=torch.float64, device=x.device)
         accumulate = sink is not None and sink.buf is not None
-        dx = sink.buf if accumulate else torch.empty(B, H, W, Cc, dtype=BF16, device=x.device)
+        dx = sink.buf if accumulate else torch.empty_like(x)      # at x's own resolution (see SpadeStyleFn.backward)
         last = True
         if sink is not None:
             sink.seen += 1
@@ -756,13 +754,9 @@ class SpadeConvFn(torch.autograd.Function):
                     L.ptr(dstyle), L.ptr(chsum), W if up else 0, Cc, st, tag="bwd B%d HW%d C%d%s" % (B, H * W, Cc, " up" if up else ""))
         gx = None
         if last and ctx.needs_input_grad[1]:
-            if up:
-                gx = torch.empty_like(x)
-                L.call("s2e_upsample2x_bwd", L.ptr(dx), B, H // 2, W // 2, Cc, L.ptr(gx), st)
-            else:
-                gx = dx
-                if sink is None:
-                    gx._s2e_chsum = chsum[2 * Cc:]   # bias gradient of the convolution that produced x (see SpadeStyleFn)
+            gx = dx
+            if sink is None and not up:
+                gx._s2e_chsum = chsum[2 * Cc:]   # bias gradient of the convolution that produced x (see SpadeStyleFn)
         # ---- gamma|beta convolution backward
         taps = conv_taps(ccfg)
         dactv = None
