@@ -796,11 +796,14 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
   float* m12 = (float*)(racc + (size_t)B * 5 * C);
   const float os = style ? 0.5f : 1.0f;
   const int units = up_w ? HW / 4 : HW;     // source pixels when the up-sampling is folded in
-  dim3 grid(red_chunks(units, B, 3), B);     // ~75-98 registers: three resident blocks per SM, one wave
   dim3 grid2(ew_chunks(units, B, C), B);
   const double count = per_sample ? (double)HW : (double)B * HW;
 #define S2E_SPADE_BWD(ACT_, UP_)                                                                                              \
   do {                                                                                                                        \
+    /* the reduce pass runs as exactly ONE wave of resident blocks (its register count differs per instantiation) */        \
+    int nb = 2;                                                                                                               \
+    S2E_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spade_bwd_reduce_kernel<ACT_, UP_>, NT, red_smem(C)));  \
+    dim3 grid(red_chunks(units, B, nb < 1 ? 1 : (nb > 3 ? 3 : nb)), B);                                                       \
     spade_bwd_reduce_kernel<ACT_, UP_><<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, \
                                                                       HW, C, racc, up_w, gstride, os);                        \
     S2E_LAUNCH_CHECK();                                                                                                       \
