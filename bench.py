@@ -39,24 +39,32 @@ WORKLOADS = {
 # captures (profiler numbers, so they are constants here, never measured inside the timed region).  Key = the launch tag
 # of ops._timed_call at R2 / batch 16.
 NCU_TRAFFIC = {
-    "fwd B16 640x384 Cin128 Cout256 T9": (2.969e9,
-        "ncu --set full (profiles/r01_ncu_convprobe_fullres.txt): tapconv_fwd_kernel<256,0>, B16 640x384 128->256 3x3: dram read "
-        "1.010 GB + write 1.958 GB per launch vs 3.020 GB algorithmic (x 1.007 GB + y 2.013 GB); tensor pipe 78.8 % active at "
-        "the power-capped clock (1.385 GHz)"),
-    "dgrad B16 640x384 Cin256 Cout128 T9": (2.996e9,
-        "ncu --set full (profiles/r01_ncu_convprobe_fullres.txt, column 2): tapconv_fwd_kernel<128,0> as data gradient, B16 "
-        "640x384 256->128 3x3: dram read 2.015 GB + write 0.980 GB per launch vs 3.020 GB algorithmic; tensor pipe 59.8 %"),
-    "wgrad B16 640x384 Cin128 Cout256 T9": (3.615e9,
-        "ncu --set full (profiles/r01_ncu_convprobe_fullres.txt, column 3): tapconv_wgrad_kernel<256>: dram read 3.606 GB + "
-        "write 0.009 GB per launch vs 3.020 GB algorithmic (x 1.007 GB + dy 2.013 GB); tensor pipe 58.2 %"),
-    # the same gamma|beta convolution with the SPADE+Style modulation fused into its epilogue (added after the last ncu
-    # capture of the round): not captured yet -- algorithmic bytes only
-    "fwd+spade B16 640x384 Cin128 Cout256 T9": (None,
-        "not captured by ncu yet (kernel variant added after the round's last capture). Algorithmic bytes per launch: actv "
-        "1.007 GB + x 0.252 GB (half-resolution source) + out 1.007 GB [+ gamma 1.007 GB + mask 0.063 GB in training mode] = "
-        "2.27 / 3.34 GB. The unfused instantiation of the same main loop moved 2.969 GB for 3.020 GB algorithmic "
-        "(profiles/r01_ncu_convprobe_fullres.txt)"),
+    # round 2 capture of the dominant launch class (profiles/r02a_ncu_fused.txt): the gamma|beta convolution with the SPADE+Style
+    # modulation in its epilogue, training variant (also writes gamma and the 1-bit activation mask)
+    "fwd+spade B16 640x384 Cin128 Cout256 T9": (3.296e9,
+        "ncu --set full (profiles/r02a_ncu_fused.txt): tapconv_fwd_kernel<256,0,2,0> (training variant), B16 640x384 128->256 3x3 + "
+        "SPADE+Style epilogue: dram read 1.270 GB + write 2.025 GB per launch vs 3.34 GB algorithmic (actv 1.007 + x 0.252 at half "
+        "resolution + out 1.007 + gamma 1.007 + mask 0.063); tensor pipe 66.8 % active at 1.51 GHz (power-capped). The no-grad "
+        "variant <256,0,1,0> of the same class (D step / inference) moves 2.27 GB algorithmic"),
+    "fwd B16 640x384 Cin128 Cout256 T9": (2.982e9,
+        "ncu --set full (profiles/r02a_ncu_conv256.txt): tapconv_fwd_kernel<256,0,0,0>, B16 640x384 128->256 3x3: dram read 1.022 GB "
+        "+ write 1.960 GB per launch vs 3.020 GB algorithmic (x 1.007 GB + y 2.013 GB); tensor pipe 76.3 % active at 1.45 GHz"),
+    "dgrad B16 640x384 Cin256 Cout128 T9": (2.998e9,
+        "ncu --set full (profiles/r02a_ncu_conv256.txt): tapconv_fwd_kernel<128,0,0,0> as data gradient, B16 640x384 256->128 3x3: "
+        "dram read 2.019 GB + write 0.979 GB per launch vs 3.020 GB algorithmic; tensor pipe 58.7 %"),
+    "wgrad B16 640x384 Cin128 Cout256 T9": (3.749e9,
+        "ncu --set full (profiles/r02a_ncu_conv256.txt): tapconv_wgrad_kernel<256>: dram read 3.743 GB + write 0.006 GB per launch "
+        "vs 3.020 GB algorithmic (x 1.007 GB + dy 2.013 GB; 1.24x: taps whose CTAs are not co-resident re-read through DRAM); "
+        "tensor pipe 58.2 %"),
 }
+# SPADE+Style normalisation kernels, launch B16 HW245760 C128 with the nearest-2x index map (profiles/r02b_ncu_norm.txt)
+NCU_TRAFFIC_NORM_FWD = (3.281e9, "ncu --set full (profiles/r02b_ncu_norm.txt): spade_fwd_kernel<1,1>, B16 640x384 C128 reading x at half "
+                        "resolution: dram read 2.265 GB + write 1.016 GB vs 3.27 GB algorithmic (x 0.25 + gamma|beta 2.01 + out 1.01); "
+                        "77.6 % of ncu's DRAM peak, 6.35 TB/s")
+NCU_TRAFFIC_NORM_BWD = (6.867e9, "ncu --set full (profiles/r02b_ncu_norm.txt): spade_bwd_reduce_kernel<1,1> 2.328 GB read (0.631 ms) + "
+                        "spade_bwd_apply_kernel<1,1> 2.328 GB read + 2.208 GB written (0.773 ms) for the same launch: both passes read "
+                        "dout, gamma and the 1-bit mask at full and x at half resolution; the apply pass writes dgamma|dbeta and the "
+                        "half-resolution dx (2x2 adjoint of the up-sampling folded in)")
 
 
 def ncu_traffic_for(tag, res, batch):
@@ -399,16 +407,17 @@ def run_ours(args):
                              conv_n // 2, conv_ms / 2, ms / args.steps),
                          "peak_source": peaks["source"] + " (sustained bf16 cuBLAS; burst %.0f)" % peaks["tf"]},
             "roofline_norm": {"bound": "hbm", "achieved": norm_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                              "frac": norm_gbs / peaks["hbm"], "kernel": "spade_style_fwd_kernel (8 B/element)",
+                              "frac": norm_gbs / peaks["hbm"], "kernel": "spade_fwd_kernel (8 B/element: x, gamma, beta in, out; the SPADE blocks with C <= 128 run inside the gamma|beta "
+                                        "convolution's epilogue instead and are counted under `roofline`)",
                               "launches": prof["norm_n"],
-                              "traffic": 1.983e9, "traffic_note": "ncu --set full, launch B16 HW245760 C64: dram read 1.510 GB + write "
-                              "0.473 GB vs 2.013 GB algorithmic (profiles/r01_ncu_spade_style_fwd_C64_fullres.txt)"},
+                              "traffic": NCU_TRAFFIC_NORM_FWD[0], "traffic_note": NCU_TRAFFIC_NORM_FWD[1]},
         }
         if prof.get("normb_ms", 0) > 0:
             nb = prof["normb_bytes"] / 1e9 / (prof["normb_ms"] / 1e3)
             out["roofline_norm_bwd"] = {"bound": "hbm", "achieved": nb, "peak": peaks["hbm"], "unit": "GB/s", "frac": nb / peaks["hbm"],
                                         "kernel": "spade_style_bwd (reduce + fold + apply; 12 B/element algorithmic: dout, x, gamma in; "
-                                                  "dx, dgamma, dbeta out)", "launches": prof["normb_n"]}
+                                                  "dx, dgamma, dbeta out)", "launches": prof["normb_n"],
+                                        "traffic": NCU_TRAFFIC_NORM_BWD[0], "traffic_note": NCU_TRAFFIC_NORM_BWD[1]}
         if args.workload == "c2" and args.res in STEP_TFLOP:
             out["step_tflops_equiv"] = imgs * STEP_TFLOP[args.res] / (ms / 1e3)
     if world > 1:

@@ -77,6 +77,14 @@ class GradReducer:
             self.launched_during_backward += 1
 
     # ---- CUDA-graph mode: gradients live INSIDE the flat buckets ------------------------------------------------
+    def remove_hooks(self):
+        """Stop launching all-reduces from inside backward (allreduce() then gathers the gradients itself)."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for b in self.buckets or []:
+            b.pending, b.handle = len(b.params), None
+
     def bind_flat_grads(self):
         """After one eager step (which tells us which parameters receive gradients): make every such parameter's .grad a
         view into its bucket's flat buffer and drop the hooks.  Backward then accumulates straight into the buckets
@@ -84,9 +92,7 @@ class GradReducer:
         the buckets (`zero_flat()`) at the start of every step instead of setting .grad to None."""
         if self.buckets is None:
             self._build()
-        for h in self._hooks:
-            h.remove()
-        self._hooks = []
+        self.remove_hooks()
         for b in self.buckets:
             for p, off in zip(b.params, b.offsets):
                 p.grad = b.flat[off:off + p.numel()].view_as(p)

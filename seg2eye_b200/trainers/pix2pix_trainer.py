@@ -106,6 +106,9 @@ class Pix2PixTrainer():
             self._static['style_image'] = example_data['style_image'].float().to(dev).clone()
         tensors = [t for net in (m.netG, m.netD, m.netE) if net is not None for t in list(net.parameters()) + list(net.buffers())]
         opts = (self.optimizer_G, self.optimizer_D)
+        if multi:     # the capture set-up below runs on a side stream: no all-reduce launches from inside backward there
+            self.reducer_G.remove_hooks()
+            self.reducer_D.remove_hooks()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # one throw-away iteration so that optimizer state (and the buckets) exist

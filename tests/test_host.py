@@ -242,9 +242,9 @@ def test_fused_spade_shape_rules_and_bench_traffic_lookup():
     spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    t, note = bench.ncu_traffic_for("fwd B16 640x384 Cin128 Cout256 T9", "R2", 16)
-    assert t == 2.969e9 and "r01_ncu_convprobe_fullres" in note
-    assert bench.ncu_traffic_for("fwd+spade B16 640x384 Cin128 Cout256 T9", "R2", 16)[0] is None
+    t, note = bench.ncu_traffic_for("fwd+spade B16 640x384 Cin128 Cout256 T9", "R2", 16)     # the dominant class has a capture
+    assert t == 3.296e9 and "r02a_ncu_fused" in note
+    assert bench.ncu_traffic_for("fwd B16 320x192 Cin128 Cout512 T9", "R2", 16)[0] is None
     assert bench.ncu_traffic_for("fwd B16 640x384 Cin128 Cout256 T9", "R1", 16) == (None, None)
 
 
