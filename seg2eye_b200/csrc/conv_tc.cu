@@ -744,36 +744,33 @@ tapconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const uint32_t blk_bytes = (uint32_t)p.KP * 128u;  // one 64-channel block of KP pixels
 
   if (warp == 0) {
-    // one lane per 64-channel box: lane 0 waits for the stage and arms the barrier, then lanes 0 .. 1 + BN/64 issue their
-    // TMA loads from ONE warp instruction (six sequential issues from a single thread paced the whole pipeline)
-    int stage = 0;
-    uint32_t phase = 0;
-    const int dy = p.taps.dy[tap], dx = p.taps.dx[tap];
-    const bool is_a = lane < 2;
-    const int j = is_a ? lane : lane - 2;
-    const CUtensorMap* map = (is_a != (p.swap != 0)) ? &tmDY : &tmX;      // A = dY unless swapped; B = the other one
-    const bool shifted = (map == &tmX);
-    const int c0 = (is_a ? m0 : n0) + j * 64;
-    const int ox = shifted ? dx : 0, oy = shifted ? dy : 0;
-    for (int kt = k_begin; kt < k_end; ++kt) {
-      int r = kt;
-      const int w_idx = r % p.kt_w;
-      r /= p.kt_w;
-      const int h_idx = r % p.kt_h;
-      const int b_idx = r / p.kt_h;
-      const int w0 = w_idx * p.KTW, h0 = h_idx * p.KTH, b0 = b_idx * p.KTB;
-      if (lane == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int dy = p.taps.dy[tap], dx = p.taps.dx[tap];
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        int r = kt;
+        const int w_idx = r % p.kt_w;
+        r /= p.kt_w;
+        const int h_idx = r % p.kt_h;
+        const int b_idx = r / p.kt_h;
+        const int w0 = w_idx * p.KTW, h0 = h_idx * p.KTH, b0 = b_idx * p.KTB;
         ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
         ptx::mbar_expect_tx(&full[stage], blk_bytes * (2 + BN / 64));
-      }
-      __syncwarp();
-      if (lane < 2 + BN / 64) {
-        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + (is_a ? 0 : Cfg::A_BYTES) + j * blk_bytes;
-        ptx::tma_load_4d(dst, map, &full[stage], c0, w0 + ox, h0 + oy, b0);
-      }
-      if (++stage == Cfg::STAGES) {
-        stage = 0;
-        phase ^= 1;
+        const CUtensorMap* mapA = p.swap ? &tmX : &tmDY;
+        const CUtensorMap* mapB = p.swap ? &tmDY : &tmX;
+        const int ax = p.swap ? dx : 0, ay = p.swap ? dy : 0, bx = p.swap ? 0 : dx, by = p.swap ? 0 : dy;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) ptx::tma_load_4d(sa + j * blk_bytes, mapA, &full[stage], m0 + j * 64, w0 + ax, h0 + ay, b0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          ptx::tma_load_4d(sb + j * blk_bytes, mapB, &full[stage], n0 + j * 64, w0 + bx, h0 + by, b0);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else if (warp == 1) {
@@ -1003,37 +1000,35 @@ tapconv_wgrad_mt_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
   const uint32_t blk_bytes = (uint32_t)p.KP * 128u;
 
   if (warp == 0) {
-    // one lane per box (see tapconv_wgrad_kernel): lanes [0, shared_blocks) load the shared operand (dY), the following
-    // ntap * tap_blocks lanes the shifted copies of X
-    int stage = 0;
-    uint32_t phase = 0;
-    const int c_shared = p.swap ? n0 : m0;   // channel origin of the shared operand (dY: Cout axis)
-    const int c_tap = p.swap ? m0 : n0;      // channel origin of the per-tap operand (X: Cin axis)
-    const int nboxes = shared_blocks + ntap * tap_blocks;
-    const bool is_shared = lane < shared_blocks;
-    const int tt = is_shared ? 0 : (lane - shared_blocks) / tap_blocks;
-    const int j = is_shared ? lane : (lane - shared_blocks) % tap_blocks;
-    const bool active = lane < nboxes;
-    const CUtensorMap* map = is_shared ? &tmDY : &tmX;
-    const int c0 = (is_shared ? c_shared : c_tap) + j * 64;
-    const int ox = (!is_shared && active) ? p.taps.dx[tap0 + tt] : 0, oy = (!is_shared && active) ? p.taps.dy[tap0 + tt] : 0;
-    const uint32_t dst_off = is_shared ? (uint32_t)j * blk_bytes : (uint32_t)((shared_blocks + tt * tap_blocks) * WG_BLK) + (uint32_t)j * blk_bytes;
-    for (int kt = k_begin; kt < k_end; ++kt) {
-      int r = kt;
-      const int w_idx = r % p.kt_w;
-      r /= p.kt_w;
-      const int h_idx = r % p.kt_h;
-      const int b_idx = r / p.kt_h;
-      const int w0 = w_idx * p.KTW, h0 = h_idx * p.KTH, b0 = b_idx * p.KTB;
-      if (lane == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const CUtensorMap* map_shared = &tmDY;
+      const CUtensorMap* map_tap = &tmX;
+      const int c_shared = p.swap ? n0 : m0;   // channel origin of the shared operand (dY: Cout axis)
+      const int c_tap = p.swap ? m0 : n0;      // channel origin of the per-tap operand (X: Cin axis)
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        int r = kt;
+        const int w_idx = r % p.kt_w;
+        r /= p.kt_w;
+        const int h_idx = r % p.kt_h;
+        const int b_idx = r / p.kt_h;
+        const int w0 = w_idx * p.KTW, h0 = h_idx * p.KTH, b0 = b_idx * p.KTB;
         ptx::mbar_wait(&empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&full[stage], blk_bytes * (uint32_t)nboxes);
-      }
-      __syncwarp();
-      if (active) ptx::tma_load_4d(smem + stage * stage_bytes + dst_off, map, &full[stage], c0, w0 + ox, h0 + oy, b0);
-      if (++stage == stages) {
-        stage = 0;
-        phase ^= 1;
+        uint8_t* ss = smem + stage * stage_bytes;
+        ptx::mbar_expect_tx(&full[stage], blk_bytes * (uint32_t)(shared_blocks + ntap * tap_blocks));
+        for (int j = 0; j < shared_blocks; ++j)
+          ptx::tma_load_4d(ss + j * blk_bytes, map_shared, &full[stage], c_shared + j * 64, w0, h0, b0);
+        for (int tt = 0; tt < ntap; ++tt) {
+          uint8_t* st = ss + (shared_blocks + tt * tap_blocks) * WG_BLK;
+          const int dy = p.taps.dy[tap0 + tt], dx = p.taps.dx[tap0 + tt];
+          for (int j = 0; j < tap_blocks; ++j)
+            ptx::tma_load_4d(st + j * blk_bytes, map_tap, &full[stage], c_tap + j * 64, w0 + dx, h0 + dy, b0);
+        }
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else if (warp == 1) {
