@@ -313,6 +313,25 @@ int s2e_aggregate_fwd(const void* x, int x_is_f32, int G, int ns, long long n, i
 int s2e_aggregate_bwd(const float* dout, const uint8_t* argmax, int x_is_f32, int G, int ns, long long n, int mode, void* dx,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-side data layer: data/openeds_dataset.py:82-119 + data/base_dataset.py:50-80 ('fixed' mode) on
+ * raw uint8 frames resident in HBM.  `flip` (nullable) = one byte per sample, != 0: horizontal flip after the resize.
+ * ------------------------------------------------------------------------------------------ */
+/* mask (N,H0,W0) u8 -> cv2.resize(INTER_NEAREST) to (h,w) -> flip -> int64 (N,1,h,w): the `label` entry of the data dict */
+int s2e_label_nearest_flip(const uint8_t* mask, int N, int H0, int W0, int h, int w, const uint8_t* flip, int64_t* out,
+                           void* stream);
+/* one separable pass of PIL's 8-bit Image.resize (base_dataset.py:88-91): kk [out_size][ksize] 22-bit fixed-point taps and
+ * bounds [out_size][2] = (first source index, tap count), computed on the host like Pillow's precompute_coeffs /
+ * normalize_coeffs_8bpc.  horizontal != 0: (N,Hin,Win) -> (N,Hin,out_size); else -> (N,out_size,Win). */
+int s2e_pil_resample_u8(const uint8_t* in, int N, int Hin, int Win, int out_size, int horizontal, const int* kk,
+                        const int* bounds, int ksize, uint8_t* out, void* stream);
+/* flip + transforms.ToTensor + Normalize((0.5,), (0.5,)): u8 (N,h,w) -> fp32 ((v / 255) - 0.5) / 0.5; image n uses
+ * flip[n / images_per_flag] (the ns style images of a sample share its flag) */
+int s2e_u8_flip_normalize(const uint8_t* in, int N, int images_per_flag, int h, int w, const uint8_t* flip, float* out,
+                          void* stream);
+/* `target_original` (openeds_dataset.py:112-116): the raw target frame, flipped, as int32 */
+int s2e_u8_flip_to_i32(const uint8_t* in, int N, int h, int w, const uint8_t* flip, int* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

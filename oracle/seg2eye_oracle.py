@@ -648,3 +648,94 @@ class OracleTrainer:
         self.d_losses = discriminator_losses(self.sdG, self.sdD, self.sdE, batch, self.opt)
         sum(self.d_losses.values()).mean().backward()
         self.opt_D.step()
+
+
+# --------------------------------------------------------------------------------------
+# data layer (data/base_dataset.py:50-80, data/openeds_dataset.py:82-119), preprocess_mode 'fixed'
+# --------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2     # Pillow, src/libImaging/Resample.c
+
+
+def _pil_bicubic(x):
+    """Pillow's bicubic kernel (a = -0.5), Resample.c bicubic_filter."""
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_bicubic_table(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for Image.resize(..., BICUBIC) on 8-bit images: per output
+    index the first source index, the tap count and the taps as 22-bit fixed-point integers.  (The reference resizes
+    every style / target image with PIL, base_dataset.py:88-91 via :69-72.)"""
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    kk = np.zeros((out_size, ksize), np.int32)
+    bounds = np.zeros((out_size, 2), np.int32)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / filterscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [_pil_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x in range(xmax):
+            k = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(-0.5 + k * (1 << PIL_PRECISION_BITS)) if k < 0 else int(0.5 + k * (1 << PIL_PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return kk, bounds
+
+
+def _pil_resample_axis(img, kk, bounds, axis):
+    a = img.astype(np.int64)
+    if axis == 0:
+        a = a.T
+    out = np.zeros((a.shape[0], kk.shape[0]), np.int64)
+    for xx in range(kk.shape[0]):
+        xmin, n = bounds[xx]
+        out[:, xx] = (1 << (PIL_PRECISION_BITS - 1)) + (a[:, xmin:xmin + n] * kk[xx, :n].astype(np.int64)[None]).sum(1)
+    out = np.clip(out >> PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+    return out.T if axis == 0 else out
+
+
+def pil_resize_bicubic(img, w, h):
+    """Image.fromarray(img, 'L').resize((w, h), Image.BICUBIC) for a uint8 (H, W) array: horizontal pass, then vertical,
+    8-bit intermediate (Resample.c ImagingResampleInner)."""
+    out = img
+    if img.shape[1] != w:
+        out = _pil_resample_axis(out, *pil_bicubic_table(img.shape[1], w), 1)
+    if img.shape[0] != h:
+        out = _pil_resample_axis(out, *pil_bicubic_table(img.shape[0], h), 0)
+    return out
+
+
+def cv_nearest_index(dst, src):
+    """cv2.resize(INTER_NEAREST): source index min(floor(d * (1 / (dst / src))), src - 1) (resize.cpp resizeNN)."""
+    ifx = 1.0 / (float(dst) / float(src))
+    return np.minimum(np.floor(np.arange(dst) * ifx).astype(np.int64), src - 1)
+
+
+def preprocess_sample(mask, images, w, h, flip):
+    """OpenEDSDataset.__getitem__ (openeds_dataset.py:82-119) with get_transform in 'fixed' mode (base_dataset.py:69-80):
+    mask uint8 (H0, W0) -> cv2 nearest -> flip -> integer label (h, w); every image uint8 (H0, W0) -> PIL bicubic -> flip ->
+    ToTensor (/255) -> Normalize(0.5, 0.5) -> fp32 (1, h, w)."""
+    lab = mask[cv_nearest_index(h, mask.shape[0])][:, cv_nearest_index(w, mask.shape[1])]
+    if flip:
+        lab = lab[:, ::-1]
+    outs = []
+    for im in images:
+        r = pil_resize_bicubic(im, w, h)
+        if flip:
+            r = r[:, ::-1]
+        t = torch.from_numpy(np.ascontiguousarray(r)).to(torch.float32).div(255)
+        outs.append(t.sub(0.5).div(0.5).unsqueeze(0))
+    return torch.from_numpy(np.ascontiguousarray(lab)), outs

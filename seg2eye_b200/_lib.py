@@ -92,6 +92,10 @@ _SIGS = {
     "s2e_openeds_score": [_P, _P, _I, _I, _I, _P, _P, _P],
     "s2e_aggregate_fwd": [_P, _I, _I, _I, _LL, _I, _P, _P, _P],
     "s2e_aggregate_bwd": [_P, _P, _I, _I, _I, _LL, _I, _P, _P],
+    "s2e_label_nearest_flip": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "s2e_pil_resample_u8": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P],
+    "s2e_u8_flip_normalize": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "s2e_u8_flip_to_i32": [_P, _I, _I, _I, _P, _P, _P],
 }
 
 _lib = None

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libseg2eye_b200.so")
-SOURCES = ["misc.cu", "norm.cu", "conv_simt.cu", "conv_thin.cu", "conv_tc.cu", "tail.cu"]
+SOURCES = ["misc.cu", "norm.cu", "conv_simt.cu", "conv_thin.cu", "conv_tc.cu", "tail.cu", "data.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"]
 

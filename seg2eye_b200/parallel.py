@@ -45,6 +45,10 @@ class GradReducer:
         self._hooks = []
         self.launched_during_backward = 0   # diagnostics: buckets whose all-reduce started from a hook
         self.flat_bound = False
+        # Autograd runs a parameter's post-accumulate hooks even when the gradient that reached it is undefined (e.g. D's
+        # parameters inside the generator step, whose weight gradients are skipped): a reducer only listens while its own
+        # step is running (`armed`), and never to a parameter without a gradient
+        self.armed = True
 
     # ---- bucket construction (first step: we now know which parameters receive gradients)
     def _build(self):
@@ -67,6 +71,8 @@ class GradReducer:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     def _on_grad(self, p):
+        if not self.armed or p.grad is None:
+            return
         bi, pi = self._slot[p]
         b = self.buckets[bi]
         off = b.offsets[pi]

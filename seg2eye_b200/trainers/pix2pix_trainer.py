@@ -63,6 +63,7 @@ class Pix2PixTrainer():
 
     def _eager_step(self, which, data):
         opt_, red = (self.optimizer_G, self.reducer_G) if which == 'G' else (self.optimizer_D, self.reducer_D)
+        self.reducer_G.armed, self.reducer_D.armed = which == 'G', which == 'D'
         self.pix2pix_model.train()
         opt_.zero_grad()
         losses, generated = self._fb(which, data)
@@ -84,7 +85,10 @@ class Pix2PixTrainer():
         """Capture the G step and the D step for batches shaped like `example_data` (label (B,1,H,W),
         style_image (B,ns,1,H,W), target (B,1,H,W)).  Afterwards run_*_one_step copy the batch into static device
         buffers and replay.  Shapes must not change; call disable_cuda_graphs() to return to eager execution.
-        Capture is side-effect free: every piece of state the warm-up iterations touch is restored afterwards."""
+        Capture is side-effect free: every piece of state the warm-up iterations touch is restored afterwards.
+        Callers that ran eager steps before must not hold on to loss tensors of those steps (anything with a grad_fn):
+        they keep the parameters' gradient accumulators bound to the stream of the eager steps, which a capturing stream
+        cannot join ("operation would make the legacy stream depend on a capturing blocking stream")."""
         import gc
         from .. import ops
         dev = self.pix2pix_model.device()

@@ -74,53 +74,63 @@ def _worker(rank, port, tmp, q):
                  "up_3.norm_1.adain.linear.weight", "conv_img.weight"]
         pG = dict(m.netG.named_parameters())
         m.train()
-        # (2a) rank 0 alone: the step on the WHOLE batch, no collective (done first: the reducers have no hooks yet)
+
+        def reload():
+            for net, k in ((m.netG, "G"), (m.netD, "D"), (m.netE, "E")):
+                net.load_state_dict({a: b.clone() for a, b in sds[k].items()})
+            for o_ in (tr.optimizer_G, tr.optimizer_D):       # fresh Adam state
+                o_.state.clear()
+                for g in o_.param_groups:
+                    g.pop('_s2e_state', None)
+
+        def two_iterations():
+            out = []
+            for _ in range(2):
+                d = {k: v.clone() for k, v in shard.items()}
+                tr.run_generator_one_step(d)
+                tr.run_discriminator_one_step(d)
+                out.append(torch.stack([v.reshape(-1)[0].detach().float() for v in tr.get_latest_losses().values()]).cpu())
+            return out
+
+        # (2) multi-rank CUDA graphs ([fwd+bwd] graph -> NCCL all-reduce -> [Adam] graph) == multi-rank eager
+        tr.enable_cuda_graphs({k: v.cuda() for k, v in shard.items()}, warmup=1)
+        graph = two_iterations()
+        tr.disable_cuda_graphs()
+        reload()
+        eager = two_iterations()
+        res["graph_vs_eager"] = [float((a - b).abs().max()) for a, b in zip(eager, graph)]
+        res["eager_losses"] = eager[1]
+        tr.g_losses = tr.d_losses = None
+        tr.generated = None
+        reload()
+        # (3a) rank 0 alone: one generator step on the WHOLE batch with the collective switched off
         if rank == 0:
+            tr.reducer_G.remove_hooks()
             tr.optimizer_G.zero_grad()
             losses_f, _ = tr._fb('G', {k: v.clone() for k, v in full.items()})
             g_full = {n: pG[n].grad.detach().clone() for n in names}
             res["losses_full"] = torch.stack([v.reshape(-1)[0].detach() for v in losses_f.values()]).cpu()
+            del losses_f
             for net, k in ((m.netG, "G"), (m.netD, "D"), (m.netE, "E")):      # u / v advanced: start again from the same state
                 net.load_state_dict({a: b.clone() for a, b in sds[k].items()})
+        else:
+            tr.reducer_G.remove_hooks()
         dist.barrier()
-        # (2b) both ranks: sharded gradients, averaged across ranks
+        # (3b) both ranks: sharded gradients, averaged across ranks
         tr.optimizer_G.zero_grad()
+        tr.reducer_G.armed, tr.reducer_D.armed = True, False
         losses, _ = tr._fb('G', dict(shard))
         tr.reducer_G.allreduce()
         lsum = torch.stack([v.reshape(-1)[0].detach() for v in losses.values()])
         dist.all_reduce(lsum)
         res["losses_sharded_mean"] = (lsum / WORLD).cpu()
+        del losses
         if rank == 0:
             res["grad_err"] = {n: rel(pG[n].grad, g_full[n]) for n in names}
         dist.barrier()
-        # (3) rank-0-only checkpoint
+        # (4) rank-0-only checkpoint
         tr.save("latest")
         res["ckpt_exists"] = os.path.exists(os.path.join(tmp, "mr", "latest_net_G.pth"))
-        # (4) multi-rank CUDA graphs == multi-rank eager
-        def run(graphs):
-            for net, k in ((m.netG, "G"), (m.netD, "D"), (m.netE, "E")):
-                net.load_state_dict({a: b.clone() for a, b in sds[k].items()})
-            t2 = tr
-            out = []
-            if graphs:
-                t2.enable_cuda_graphs({k: v.cuda() for k, v in shard.items()}, warmup=1)
-            for _ in range(2):
-                d = {k: v.clone() for k, v in shard.items()}
-                t2.run_generator_one_step(d)
-                t2.run_discriminator_one_step(d)
-                out.append(torch.stack([v.reshape(-1)[0].detach().float() for v in t2.get_latest_losses().values()]).cpu())
-            if graphs:
-                t2.disable_cuda_graphs()
-            return out
-        eager = run(False)
-        # fresh optimizer state for the second run
-        for o_ in (tr.optimizer_G, tr.optimizer_D):
-            o_.state.clear()
-            for g in o_.param_groups:
-                g.pop('_s2e_state', None)
-        graph = run(True)
-        res["graph_vs_eager"] = [float((a - b).abs().max()) for a, b in zip(eager, graph)]
-        res["eager_losses"] = eager[1]
         q.put((rank, res, None))
         dist.barrier()
         dist.destroy_process_group()

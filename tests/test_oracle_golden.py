@@ -257,3 +257,21 @@ def test_spade_layer_with_35_classes_vs_reference_fixture():
         close(sub(sd["L.mlp_shared.0.weight"].grad)[0], ref[name + "|dw_shared_sub"], tol=2e-4)
         if "batch" in cfg:
             close(sd["L.param_free_norm.running_var"], ref[name + "|running_var"], tol=1e-5)
+
+
+def test_data_layer_bit_exact_vs_reference_fixture():
+    """oracle.preprocess_sample == the reference's get_transform pipeline ('fixed' mode: cv2 nearest for the mask, PIL bicubic +
+    ToTensor + Normalize for the images, optional flip; data/base_dataset.py:50-80 as used by data/openeds_dataset.py:82-119):
+    every label and every float bit (SHA-256 of the full results; fixture: oracle/make_golden_data.py)."""
+    from oracle.make_golden_data import CASES, data_inputs, digest
+    ref = np.load(os.path.join(GOLD, "ref_data.npz"))
+    for name, (crop, ar, flip) in CASES.items():
+        mask, images = data_inputs(name)
+        w, h = crop, round(crop / ar)
+        lab, ims = O.preprocess_sample(mask, images, w, h, flip)
+        ims = torch.stack(ims)
+        assert tuple(ims.shape) == tuple(ref[name + "|shape"]) and lab.shape == (h, w)
+        assert np.array_equal(lab.numpy().reshape(-1)[::397].astype(np.uint8), ref[name + "|label_sub"]), name
+        assert np.array_equal(digest(lab.numpy().astype(np.uint8)), ref[name + "|label_sha"]), name
+        assert np.array_equal(ims.numpy().reshape(-1)[::997], ref[name + "|images_sub"]), name
+        assert np.array_equal(digest(ims.numpy().astype(np.float32)), ref[name + "|images_sha"]), name
