@@ -36,9 +36,15 @@ class _Bucket:
 
 
 class GradReducer:
-    def __init__(self, params, bucket_bytes=32 << 20, overlap=True):
+    def __init__(self, params, bucket_bytes=32 << 20, overlap=None):
         self.params = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
+        # overlap = launch each bucket's all-reduce from inside backward (post-accumulate hooks).  Off by default since round 2:
+        # the CUDA-graph steps (the fast path) cannot use it, and under torch 2.11 the hooks were seen to run for parameters
+        # whose gradient had not been set, which desynchronises the ranks' collective order.  S2E_OVERLAP_ALLREDUCE=1 enables it.
+        if overlap is None:
+            import os
+            overlap = os.environ.get("S2E_OVERLAP_ALLREDUCE", "0") == "1"
         self.overlap = overlap
         self.buckets = None
         self._slot = {}

@@ -47,7 +47,10 @@ def _worker(rank, port, tmp, q):
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(WORLD), RANK=str(rank), LOCAL_RANK=str(rank))
         torch.cuda.set_device(rank)
+        import datetime
         import torch.distributed as dist
+        # a short collective timeout: a desynchronised rank must fail the test, not hang the box
+        dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=90), device_id=torch.device("cuda", rank))
         from seg2eye_b200 import parallel
         from seg2eye_b200.trainers.pix2pix_trainer import Pix2PixTrainer
         oopt, opt = _opts(tmp)
@@ -147,11 +150,20 @@ def test_two_ranks_match_one_rank_and_graph_path(tmp_path):
     procs = [ctx.Process(target=_worker, args=(r, port, str(tmp_path), q), daemon=True) for r in range(WORLD)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=900) for _ in procs]
-    for p in procs:
-        p.join(120)
+    got = []
+    try:
+        for _ in procs:
+            got.append(q.get(timeout=300))
+            if got[-1][2] is not None:      # a rank failed: its peers are stuck in a collective, do not wait for them
+                break
+    finally:
+        for p in procs:
+            p.join(5 if (got and got[-1][2] is not None) else 60)
+            if p.is_alive():
+                p.kill()
     for rank, res, err in got:
         assert err is None, "rank %d: %s" % (rank, err)
+    assert len(got) == WORLD
     res = {rank: r for rank, r, _ in got}
     for r in res.values():
         assert r["replicas_identical"] and r["ckpt_exists"]

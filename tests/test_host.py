@@ -132,7 +132,7 @@ def _dp_worker(rank, port, q):
     for t in ref:
         dist.broadcast(t, 0)
     ok = ok and all(torch.equal(a, b) for a, b in zip(ref, net.parameters()))
-    red = parallel.GradReducer(list(net.parameters()) + [unused], bucket_bytes=64 << 10)
+    red = parallel.GradReducer(list(net.parameters()) + [unused], bucket_bytes=64 << 10, overlap=True)
     g = torch.Generator().manual_seed(100 + rank)
     for step in range(3):
         x = torch.randn(16, 64, generator=g)

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_gpu_multirank.py -q -x ) > gpurun_out/c6_multirank.log 2>&1
+( time timeout 400 python -m pytest tests/test_gpu_multirank.py -q -x ) > gpurun_out/c6_multirank.log 2>&1
 tail -30 gpurun_out/c6_multirank.log | cut -c1-300
