@@ -10,8 +10,12 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libseg2eye_b200.so")
 SOURCES = ["misc.cu", "norm.cu", "conv_simt.cu", "conv_thin.cu", "conv_tc.cu", "tail.cu", "data.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"]
+# --use_fast_math only where it pays and cannot be seen: the convolution epilogues and the streaming normalisation kernels
+# (bf16 outputs).  tanh of the image head, losses, Adam, the spectral iteration, the validation tail and the data layer are
+# compiled with IEEE division / sqrt / transcendental functions.
+FAST_MATH = {"conv_tc.cu", "conv_simt.cu", "norm.cu"}
 
 
 def _nvcc():
@@ -38,7 +42,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+            jobs.append([nvcc] + NVCC_FLAGS + (["--use_fast_math"] if s in FAST_MATH else []) + (["-Xptxas", "-v"] if verbose else [])
+                        + ["-c", src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -459,6 +459,16 @@ __global__ void __launch_bounds__(MAXT) thin_wgrad_kernel(const bf16* __restrict
   }
 }
 
+// function attributes are per device: remember which devices were configured (one process may drive several GPUs)
+bool first_use_on_device(int* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const int bit = 1 << (dev & 31);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 ThinGeom make_thin_geom(const s2e_conv_t* d) {
   ThinGeom g;
   g.B = d->B;
@@ -497,11 +507,10 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     if (d->Cout % K1_CO_TILE != 0 && d->Cout > K1_CO_TILE) return 0;
     const size_t smem = (size_t)d->ntaps * d->Cin * cot * sizeof(float);
     if (smem > 200 * 1024) return 0;
-    static bool attr = false;
-    if (!attr) {
+    static int attr = 0;
+    if (first_use_on_device(&attr)) {
       S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_in_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_in_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
     const int qpr = ceil_div(d->Wo, K1_PX);
     const long long nquads = (long long)d->B * d->Ho * qpr;
@@ -524,10 +533,9 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     for (int t = 0; t < d->ntaps; ++t) halo1 = halo1 && d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
     if (halo1) {
       const int tiles_w = ceil_div(d->Wo, T1_TW), tiles_h = ceil_div(d->Ho, T1_TH);
-      static bool attr1 = false;
-      if (!attr1) {
+      static int attr1 = 0;
+      if (first_use_on_device(&attr1)) {
         S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out1_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
-        attr1 = true;
       }
       thin_out1_tile_kernel<<<(unsigned)(d->B * tiles_h * tiles_w), 256, T1_SMEM, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale,
                                                                                    (bf16*)y, g, tiles_w, tiles_h, d->img_out,
@@ -556,12 +564,11 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     long long gx = (P * lpp + 255) / 256;
     const long long cap = (long long)s2e_num_sms() * 8;
     if (gx > cap) gx = cap;
-    static bool attr = false;
-    if (!attr) {
+    static int attr = 0;
+    if (first_use_on_device(&attr)) {
       S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       S2E_CHECK_CUDA(cudaFuncSetAttribute(thin_out_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
     if (d->Cout == 1)
       thin_out_fwd_kernel<1><<<(unsigned)gx, 256, smem, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g, P, lpp);
