@@ -214,7 +214,9 @@ int s2e_spade_style_fwd(const void* x, const void* gb, const float* style, const
  * and dx -- the bias gradients of the gamma|beta convolution (normalization.py:88-89) and of the convolution that
  * produced x (architecture.py:24) -- which the statistics pass yields for free.  dx_accumulate != 0 adds into dx
  * (two SPADE+Style blocks that share their input, norm_0 / norm_s of architecture.py:51-58, write ONE gradient buffer);
- * the third row of chsum then covers this call's contribution only. */
+ * the third row of chsum then covers this call's contribution only.  per_sample: bit 0 = statistics per sample
+ * (InstanceNorm), bit 1 = the statistics are constants (BatchNorm in eval mode, running statistics): dx has no
+ * mean / projection terms (chsum's third row is not meaningful then). */
 int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x, const void* gb, const float* style,
                         const float* mean, const float* rstd, int B, int HW, int C, int per_sample, int act,
                         double* racc, void* dx, int dx_accumulate, void* dgb, float* dstyle, float* chsum, int up_w,

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(NT) spade_bwd_reduce_kernel(const bf16* __rest
 // fold: raw moments -> m1 / m2 per statistics group (float [G][2][C]), dstyle [B][2C] and, optionally, chsum [3][C] =
 // per-channel sums over the whole batch of dgamma, dbeta and dx.  The last one needs no extra pass: the normalisation part
 // of dx sums to zero over the pixels its statistics were taken from, so sum dx = sum_b (1 + s0[b]) * T1[b].
-__global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int B, int C, int per_sample, double count,
+__global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int B, int C, int per_sample, int frozen, double count,
                                             const float* __restrict__ style, const float* __restrict__ mean,
                                             const float* __restrict__ rstd, float* __restrict__ m12,
                                             float* __restrict__ dstyle, float* __restrict__ chsum) {
@@ -396,8 +396,8 @@ __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int
     const double rs = (double)rstd[(size_t)b * C + c], E = -(double)mean[(size_t)b * C + c] * rs;
     const double s1 = r[c] + r[2 * C + c];
     const double s2 = rs * (r[C + c] + r[3 * C + c]) + E * s1;
-    m12[(size_t)b * 2 * C + c] = (float)(s1 / count);
-    m12[(size_t)b * 2 * C + C + c] = (float)(s2 / count);
+    m12[(size_t)b * 2 * C + c] = frozen ? 0.f : (float)(s1 / count);
+    m12[(size_t)b * 2 * C + C + c] = frozen ? 0.f : (float)(s2 / count);
   }
   if (b == 0 && (!per_sample || chsum)) {
     double s1 = 0, s2 = 0, sg = 0, sb = 0, sx = 0;
@@ -413,12 +413,13 @@ __global__ void spade_style_bwd_fold_kernel(const double* __restrict__ racc, int
       if (style) sx += (1.0 + (double)style[(size_t)bb * 2 * C + c]) * t1;
     }
     if (!per_sample) {
-      m12[c] = (float)(s1 / count);
-      m12[C + c] = (float)(s2 / count);
+      m12[c] = frozen ? 0.f : (float)(s1 / count);
+      m12[C + c] = frozen ? 0.f : (float)(s2 / count);
     }
     if (chsum) {
       chsum[c] = (float)sg;
       chsum[C + c] = (float)sb;
+      // frozen statistics: the normalisation part of dx no longer sums to zero: sum dx = sum rstd dxh + (1 + s0) sum g
       chsum[2 * C + c] = (float)sx;
     }
   }
@@ -794,6 +795,9 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
   S2E_REQUIRE(style || !dstyle, "spade_style_bwd: plain SPADE (style == NULL) has no style gradient");
   S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 5 * C, st));
   float* m12 = (float*)(racc + (size_t)B * 5 * C);
+  // per_sample bit 1: the statistics are constants (BatchNorm in eval mode: running statistics) -- no m1 / m2 terms
+  const int frozen = (per_sample >> 1) & 1;
+  per_sample &= 1;
   const float os = style ? 0.5f : 1.0f;
   const int units = up_w ? HW / 4 : HW;     // source pixels when the up-sampling is folded in
   dim3 grid2(ew_chunks(units, B, C), B);
@@ -807,7 +811,7 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
     spade_bwd_reduce_kernel<ACT_, UP_><<<grid, NT, red_smem(C), st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, \
                                                                       HW, C, racc, up_w, gstride, os);                        \
     S2E_LAUNCH_CHECK();                                                                                                       \
-    spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, count, style, mean, rstd, m12,  \
+    spade_style_bwd_fold_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(racc, B, C, per_sample, frozen, count, style, mean, rstd, m12, \
                                                                       dstyle, chsum);                                         \
     S2E_LAUNCH_CHECK();                                                                                                       \
     spade_bwd_apply_kernel<ACT_, UP_><<<grid2, NT, 0, st>>>((const bf16*)dout, act_mask, (const bf16*)x, (const bf16*)gb, style, \

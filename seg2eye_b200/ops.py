@@ -420,7 +420,11 @@ class TapConvFn(torch.autograd.Function):
                     gw[i] = g
                 off += w.shape[0]
         if any(need_b):
+            # per-channel sums left on the gradient tensor by its producer (SPADE+Style backward) -- valid only if the tensor
+            # was not accumulated into since (autograd may add a second gradient in place: the version counter moves)
             pre = getattr(dy, '_s2e_chsum', None) if cfg.act == L.ACT_NONE else None
+            if pre is not None and getattr(dy, '_s2e_chsum_ver', None) != (dy._version, dy.data_ptr()):
+                pre = None
             if pre is not None and pre.numel() == Cout:
                 _state["chsum_hits"] = _state.get("chsum_hits", 0) + 1
                 sums = pre      # the producer of dy (SPADE+Style backward) already reduced it over the pixels
@@ -624,8 +628,6 @@ class SpadeStyleFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         cfg, up, sink = ctx.cfg, ctx.up, ctx.sink
-        if not ctx.batch_stats:
-            raise NotImplementedError("backward through SPADE BatchNorm in eval mode is not supported")
         x, gb, style, mean, rstd, amask = ctx.saved_tensors
         dout = _c(dout)
         B, Cc = x.shape[0], x.shape[3]
@@ -646,17 +648,19 @@ class SpadeStyleFn(torch.autograd.Function):
         dgb = torch.empty_like(gb)
         dstyle = torch.empty_like(style) if style is not None else None
         chsum = torch.empty(3 * Cc, dtype=F32, device=x.device)
+        # eval-mode BatchNorm (running statistics): the statistics are constants, bit 1 of the per_sample argument says so
+        stat_mode = int(cfg.per_sample) | (0 if ctx.batch_stats else 2)
         _timed_call("normb", 12.0 * B * H * W * Cc, "s2e_spade_style_bwd", L.ptr(dout), L.ptr(amask), L.ptr(x), L.ptr(gb), L.ptr(style), L.ptr(mean),
-                    L.ptr(rstd), B, H * W, Cc, int(cfg.per_sample), cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
+                    L.ptr(rstd), B, H * W, Cc, stat_mode, cfg.act, L.ptr(racc), L.ptr(dx), int(accumulate), L.ptr(dgb),
                     L.ptr(dstyle), L.ptr(chsum), W if up else 0, 0, st, tag="bwd B%d HW%d C%d%s" % (B, H * W, Cc, " up" if up else ""))
         # per-channel sums of the two gradients, for the bias gradients of the convolutions that receive them as dy
         # (TapConvFn.backward picks the attribute up when the tensor reaches it unmodified; otherwise it sums itself)
-        dgb._s2e_chsum = chsum[:2 * Cc]
+        dgb._s2e_chsum, dgb._s2e_chsum_ver = chsum[:2 * Cc], (dgb._version, dgb.data_ptr())
         gx = None
         if last:
             gx = dx
-            if sink is None and not up:
-                gx._s2e_chsum = chsum[2 * Cc:]
+            if sink is None and not up and ctx.batch_stats:
+                gx._s2e_chsum, gx._s2e_chsum_ver = chsum[2 * Cc:], (gx._version, gx.data_ptr())
         return gx, dgb, dstyle, None, None, None, None, None, None
 
 
@@ -755,8 +759,8 @@ class SpadeConvFn(torch.autograd.Function):
         gx = None
         if last and ctx.needs_input_grad[1]:
             gx = dx
-            if sink is None and not up:
-                gx._s2e_chsum = chsum[2 * Cc:]   # bias gradient of the convolution that produced x (see SpadeStyleFn)
+            if sink is None and not up:     # bias gradient of the convolution that produced x (see SpadeStyleFn)
+                gx._s2e_chsum, gx._s2e_chsum_ver = chsum[2 * Cc:], (gx._version, gx.data_ptr())
         # ---- gamma|beta convolution backward
         taps = conv_taps(ccfg)
         dactv = None

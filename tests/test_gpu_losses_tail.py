@@ -235,3 +235,37 @@ def test_image_head_conv_tanh_and_loss_sums_in_one_kernel(B, H, W, with_target):
     # the bias gradient is the sum over all pixels of the bf16-rounded pre-tanh gradient: a sum with cancellation over a few
     # hundred values in the small cases (measured 1.7e-2 at 21 x 18)
     assert rel(wc.grad, wr.grad) < 1e-2 and rel(bc.grad, br.grad) < 4e-2
+
+
+# ------------------------------------------------------------------------------------------ eval-mode SPADE backward
+@pytest.mark.parametrize("act,up", [(1, False), (0, True)])
+def test_spade_style_backward_with_running_statistics(act, up):
+    """SPADE+Style block in eval mode with autograd enabled (BatchNorm running statistics are constants): forward and the
+    gradients w.r.t. x, gamma|beta and the style vector against fp32 autograd; the running buffers must not move."""
+    from seg2eye_b200 import _lib as L, ops
+    bf = lambda t: t.to(torch.bfloat16).float()
+    g = torch.Generator().manual_seed(17)
+    B, C, H, W = 2, 64, 12, 16
+    hx, wx = (H // 2, W // 2) if up else (H, W)
+    x = bf(torch.randn(B, C, hx, wx, generator=g) * 1.5 + 0.3)
+    gb = bf(torch.randn(B, 2 * C, H, W, generator=g) * 0.5)
+    style = torch.randn(B, 2 * C, generator=g) * 0.5
+    rm, rv = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    dout = bf(torch.randn(B, C, H, W, generator=g))
+    xr, gr, sr = x.clone().requires_grad_(), gb.clone().requires_grad_(), style.clone().requires_grad_()
+    xu = F.interpolate(xr, scale_factor=2, mode="nearest") if up else xr
+    xn = F.batch_norm(xu, rm.clone(), rv.clone(), training=False, eps=1e-5)
+    ref = 0.5 * (xn * (1 + gr[:, :C]) + gr[:, C:] + xu * (1 + sr[:, :C, None, None]) + sr[:, C:, None, None])
+    if act:
+        ref = F.leaky_relu(ref, 0.2)
+    ref.backward(dout)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    xc, gc, sc = nhwc(x).requires_grad_(), nhwc(gb).requires_grad_(), style.cuda().requires_grad_()
+    rmc, rvc, nbt = rm.cuda(), rv.cuda(), torch.tensor(3, device="cuda")
+    cfg = ops.NormCfg(False, act, False, 0.1, 1e-5)
+    out = ops.SpadeStyleFn.apply(xc, gc, sc, cfg, rmc, rvc, nbt, up, None)
+    out.backward(nhwc(dout))
+    nchw = lambda t: t.float().permute(0, 3, 1, 2).cpu()
+    assert rel(nchw(out), ref) < 5e-3
+    assert rel(nchw(xc.grad), xr.grad) < 1e-2 and rel(nchw(gc.grad), gr.grad) < 1e-2 and rel(sc.grad, sr.grad) < 1e-2
+    assert torch.equal(rmc.cpu(), rm) and torch.equal(rvc.cpu(), rv) and int(nbt) == 3
