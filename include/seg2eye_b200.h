@@ -42,7 +42,7 @@ int s2e_abi_version(void);
  * key 2 = keep thin-channel layers on the generic SIMT kernel, key 3 = forward epilogue timing experiments (bit 0: skip
  * the TMA store), key 5 = 1: weight gradients with an N side < 256 go back to the one-tap-per-CTA kernel (default: several
  * taps per CTA), key 6: bit 0 = 3x3 / stride-1 convolutions with an N tile <= 128 take the halo-tile forward kernel, bit 1 =
- * its A descriptors carry an explicit base offset.  The Python binding sets them from S2E_DEBUG="key=value,...". */
+ * its A descriptors carry an explicit base offset, bit 2 = never fall back to single 128-pixel tiles on small maps.  The Python binding sets them from S2E_DEBUG="key=value,...". */
 int s2e_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------------------------

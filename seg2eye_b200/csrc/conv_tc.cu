@@ -83,6 +83,7 @@ struct FwdParams {
   int dbg;  // timing experiments only (debug key 3): bit0 skip TMA store
   int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles, tiles_m;  // tiles_m = pixel tiles; num_tiles = ceil(tiles_m/MT)*tiles_n
   int TW, TH, TB;
+  int mt;   // 128-pixel sub-tiles per work item (<= FwdCfg::MT; 1 on maps too small to fill the SMs with double tiles)
   int Cout, kc_per_tap, act;
   int B, Ho, Wo;
   const bf16* mask;   // fused ReLU backward: zero the output where mask <= 0
@@ -158,6 +159,175 @@ __device__ __forceinline__ float act_t(float v) {
   if (ACT == S2E_ACT_LRELU) return fmaxf(v, 0.2f * v);
   if (ACT == S2E_ACT_RELU) return fmaxf(v, 0.f);
   return v;
+}
+
+// Per-thread state of the forward kernel's epilogue warps, carried from tile to tile.
+struct EpiState {
+  int q, sub, row, et;
+  bool store_thread;
+  float scale;
+  int acc, buf;
+  uint32_t acc_phase;
+  uint32_t tmem_base, out_u32, bias_u32;
+  uint8_t* out_buf;
+  float* s_bias;
+  uint64_t* tmem_full;
+  uint64_t* tmem_empty;
+};
+
+// One output tile (MT sub-tiles of 128 pixels x BN channels): TMEM -> registers -> scale / bias / activation (or the fused
+// SPADE+Style modulation) -> bf16 -> swizzled staging buffer -> TMA store, 64 channels at a time.
+// SIDE = per-pixel side input shaped like the output: 0 none, 1 ReLU-backward mask, 2 residual added in fp32.
+template <int BN, int ACT, int MODE, int SIDE>
+__device__ __forceinline__ void epilogue_tile(const FwdParams& p, EpiState& es, const int t, const CUtensorMap* tmY,
+                                              const CUtensorMap* tmG) {
+  using Cfg = FwdCfg<BN>;
+  constexpr bool SPADE = MODE != 0, SPADE_TRAIN = MODE == 2;
+  constexpr bool LOADS = SPADE || SIDE != 0;   // reads 16 bf16 per thread and chunk next to the accumulator
+  const int q = es.q, sub = es.sub, row = es.row, et = es.et;
+  const float scale = es.scale;
+  const int n0 = (t % p.tiles_n) * BN;
+  const int grp = t / p.tiles_n;
+  if (et < BN) {
+    float bv = (p.bias && n0 + et < p.bias_n) ? __ldg(p.bias + n0 + et) : 0.f;
+    if (SPADE && et >= p.sC && et < 2 * p.sC) {   // fused SPADE: beta's bias absorbs the style offset s1 of this tile's sample
+      int w0t, h0t, b0t;
+      subtile_origin(p, grp * p.mt, w0t, h0t, b0t);
+      bv += __ldg(p.spar + ((size_t)min(b0t, p.B - 1) * 4 + 3) * p.sC + (et - p.sC));
+    }
+    es.s_bias[et] = bv;
+  }
+  ptx::mbar_wait(&es.tmem_full[es.acc], es.acc_phase);
+  ptx::tc_fence_after();
+#pragma unroll 1
+  for (int j = 0; j < p.mt; ++j) {
+    int w0, h0, b0;
+    subtile_origin(p, grp * p.mt + j, w0, h0, b0);
+    const bf16* mrow = nullptr;    // this pixel's row of the side input (mask / residual / x of the fused SPADE)
+    const float* par = nullptr;
+    uint8_t* mask_row = nullptr;   // fused SPADE, training: this pixel's activation-mask bytes
+    if (LOADS) {
+      const int tw = row % p.TW, r2 = row / p.TW;
+      const int th = r2 % p.TH, tb = r2 / p.TH;
+      if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo) {
+        const size_t pix = ((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw;
+        if (SPADE_TRAIN && p.smask) mask_row = p.smask + pix * (size_t)(p.sC >> 3);
+        if (SIDE == 1) {
+          mrow = p.mask + pix * p.Cout;
+        } else if (SIDE == 2) {
+          mrow = p.res + pix * p.Cout;
+        } else if (p.sup) {   // x lives at half resolution (nearest 2x up-sampling folded in)
+          mrow = p.sx + ((((size_t)(b0 + tb) * (p.Ho >> 1) + ((h0 + th) >> 1)) * (p.Wo >> 1) + ((w0 + tw) >> 1)) * p.sC);
+        } else {
+          mrow = p.sx + pix * p.sC;
+        }
+      }
+      if (SPADE) par = p.spar + (size_t)min(b0, p.B - 1) * 4 * p.sC;   // host guarantees TB == 1: one sample per tile
+    }
+    const int nch = SPADE ? (p.sC >> 6) : BN / 64;
+#pragma unroll 1
+    for (int ch = 0; ch < nch; ++ch) {
+      const int nbase = n0 + ch * 64;
+      if (!SPADE && nbase >= p.Cout) break;
+      uint32_t r[16], rb[16];
+      const uint32_t taddr =
+          es.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(es.acc * Cfg::MT * BN + j * BN + ch * 64 + sub * 16);
+      ptx::tmem_ld_32x16(taddr, r);
+      if (SPADE) ptx::tmem_ld_32x16(taddr + (uint32_t)p.sC, rb);   // beta sits sC columns after gamma
+      constexpr uint32_t dflt = SIDE == 1 ? 0x3f803f80u : 0u;   // pixel outside the map: mask keeps everything, residual / x are zero
+      uint4 mk[2] = {make_uint4(dflt, dflt, dflt, dflt), make_uint4(dflt, dflt, dflt, dflt)};
+      if (LOADS && mrow) {  // host guarantees Cout % 64 == 0 when a mask / residual is given
+#pragma unroll
+        for (int i = 0; i < 2; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + sub * 16) + i);
+      }
+      // the TMA store that last read this staging buffer must have finished reading it
+      if (es.store_thread) {
+        if (SPADE_TRAIN) ptx::tma_store_wait_read<0>();   // this chunk fills BOTH staging buffers (output and gamma)
+        else ptx::tma_store_wait_read<1>();
+      }
+      ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
+      ptx::tmem_ld_wait();
+      const uint32_t ob = es.out_u32 + (uint32_t)(es.buf * OUT_BUF_BYTES + row * 128);
+      const uint32_t bsrc = es.bias_u32 + (uint32_t)((ch * 64 + sub * 16) * 4);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4 b0v = ptx::lds128f(bsrc + 32 * i), b1v = ptx::lds128f(bsrc + 32 * i + 16);
+        uint32_t pk[4];
+        float v[8];
+        v[0] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 0]), scale, b0v.x));
+        v[1] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 1]), scale, b0v.y));
+        v[2] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 2]), scale, b0v.z));
+        v[3] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 3]), scale, b0v.w));
+        v[4] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 4]), scale, b1v.x));
+        v[5] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 5]), scale, b1v.y));
+        v[6] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 6]), scale, b1v.z));
+        v[7] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 7]), scale, b1v.w));
+        if (SIDE == 2) {  // residual add in fp32, one rounding on the sum (bf16 pair: low half = even channel)
+          const uint32_t rw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[2 * e] += __uint_as_float(rw[e] << 16);
+            v[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+          }
+        }
+        if (SPADE) {  // v = gamma (+bias); form the SPADE+Style output from x, beta and the per-channel constants
+          const int c0 = ch * 64 + sub * 16 + 8 * i;
+          const uint32_t bb = es.bias_u32 + (uint32_t)((p.sC + c0) * 4);
+          const float4 bb0 = ptx::lds128f(bb), bb1 = ptx::lds128f(bb + 16);
+          const float betab[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+          const float4* pa = reinterpret_cast<const float4*>(par + c0);
+          const float4* pb = reinterpret_cast<const float4*>(par + p.sC + c0);
+          const float4* pc = reinterpret_cast<const float4*>(par + 2 * p.sC + c0);
+          const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), k0 = __ldg(pb), k1 = __ldg(pb + 1), c0v = __ldg(pc), c1v = __ldg(pc + 1);
+          const float ka[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float kb[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+          const float kc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+          const uint32_t xw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+          if (SPADE_TRAIN) {   // gamma itself goes to the other staging buffer (rounded to bf16 exactly like backward reads it)
+            const uint32_t og = es.out_u32 + (uint32_t)((es.buf ^ 1) * OUT_BUF_BYTES + row * 128);
+            ptx::sts128(og + (uint32_t)(((sub * 2 + i) ^ (row & 7)) << 4), pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]),
+                        pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
+          }
+          uint32_t bits = 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xv = __uint_as_float((e & 1) ? (xw[e >> 1] & 0xffff0000u) : (xw[e >> 1] << 16));
+            const float beta = fmaf(__uint_as_float(rb[8 * i + e]), scale, betab[e]);   // includes the style offset s1
+            float o = p.sscale * (fmaf(fmaf(xv, ka[e], kb[e]), 1.f + v[e], beta) + xv * kc[e]);
+            if (p.sact == S2E_ACT_LRELU) o = fmaxf(o, 0.2f * o);
+            bits |= (o > 0.f ? 1u : 0u) << e;
+            v[e] = o;
+          }
+          if (SPADE_TRAIN && mask_row) mask_row[(ch * 64 + sub * 16 + 8 * i) >> 3] = (uint8_t)bits;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pk[e] = pack2_bf16(v[2 * e], v[2 * e + 1]);
+        if (SIDE == 1) {  // keep a value only where the bf16 mask element is > 0 (sign clear and magnitude non-zero)
+          const uint32_t mw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
+            const uint32_t keep = (((lo & 0x8000u) == 0u && (lo & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) |
+                                  (((hi & 0x8000u) == 0u && (hi & 0x7fffu) != 0u) ? 0xffff0000u : 0u);
+            pk[e] &= keep;
+          }
+        }
+        ptx::sts128(ob + (uint32_t)(((sub * 2 + i) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(2, FWD_EPI_THREADS);
+      if (es.store_thread && !(p.dbg & 1)) {
+        ptx::tma_store_4d(tmY, es.out_buf + es.buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
+        if (SPADE_TRAIN) ptx::tma_store_4d(tmG, es.out_buf + (es.buf ^ 1) * OUT_BUF_BYTES, nbase, w0, h0, b0);
+        ptx::tma_store_commit();
+      }
+      if (!SPADE_TRAIN) es.buf ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::mbar_arrive(&es.tmem_empty[es.acc]);
+  es.acc ^= 1;
+  if (es.acc == 0) es.acc_phase ^= 1;
 }
 
 // MODE 0: plain convolution epilogue; 1: fused SPADE+Style modulation (inference); 2: the same, also writing gamma and the
@@ -315,17 +485,18 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int grp = t / p.tiles_n;
         int w0[Cfg::MT], h0[Cfg::MT], b0[Cfg::MT];
 #pragma unroll
-        for (int j = 0; j < Cfg::MT; ++j) subtile_origin(p, grp * Cfg::MT + j, w0[j], h0[j], b0[j]);
+        for (int j = 0; j < Cfg::MT; ++j) subtile_origin(p, grp * p.mt + j, w0[j], h0[j], b0[j]);
         for (int tap = 0; tap < p.taps.n; ++tap) {
           const int dy = p.taps.dy[tap], dx = p.taps.dx[tap];
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::MT * A_STAGE_BYTES;
-            ptx::mbar_expect_tx(&full[stage], Cfg::MT * p.a_box_bytes + Cfg::B_STAGE_BYTES);
+            ptx::mbar_expect_tx(&full[stage], p.mt * p.a_box_bytes + Cfg::B_STAGE_BYTES);
 #pragma unroll
             for (int j = 0; j < Cfg::MT; ++j)
-              ptx::tma_load_4d(sa + j * A_STAGE_BYTES, &tmA, &full[stage], kc * BK, w0[j] + dx, h0[j] + dy, b0[j]);
+              if (j < p.mt)
+                ptx::tma_load_4d(sa + j * A_STAGE_BYTES, &tmA, &full[stage], kc * BK, w0[j] + dx, h0[j] + dy, b0[j]);
             ptx::tma_load_3d(sb, &tmB, &full[stage], kc * BK, n0, tap);
             if (++stage == Cfg::STAGES) {
               stage = 0;
@@ -357,6 +528,7 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 32, 0, 1024);
 #pragma unroll
             for (int j = 0; j < Cfg::MT; ++j) {
+              if (j >= p.mt) break;
               const uint64_t ad = ptx::umma_desc_sw128(a_addr + j * A_STAGE_BYTES + k * 32, 0, 1024);
               ptx::umma_bf16(d_tmem + (uint32_t)(j * BN), ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
             }
@@ -379,159 +551,33 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // 16-column slice of every 64-column chunk.  Sixteen warps, not eight: the epilogue is a chain of dependent
     // short-latency steps (tcgen05.ld -> convert -> st.shared -> barrier), so its throughput is set by how many warps
     // the schedulers can interleave (ncu: 41 % issue slots busy with two epilogue warps per scheduler).
-    // Bias is staged in shared memory once per tile.
-    const int q = warp & 3;
-    const int sub = (warp - 2) >> 2;          // 0..3: columns [sub*16, sub*16+16) of the chunk
-    const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
-    const bool store_thread = (et == 0);
-    const float scale = p.scale ? __ldg(p.scale) : 1.0f;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int buf = 0;
+    // Bias is staged in shared memory once per tile.  The per-pixel side input (ReLU-backward mask / residual) is a
+    // compile-time mode of the tile body: layers with K = 64 (mlp_shared, 1x1 shortcuts) are paced by this epilogue's
+    // instruction count, and the mask / residual arithmetic was two thirds of it.
+    EpiState es;
+    es.q = warp & 3;
+    es.sub = (warp - 2) >> 2;          // 0..3: columns [sub*16, sub*16+16) of the chunk
+    es.row = es.q * 32 + lane;
+    es.et = threadIdx.x - 64;
+    es.store_thread = (es.et == 0);
+    es.scale = p.scale ? __ldg(p.scale) : 1.0f;
+    es.acc = 0;
+    es.acc_phase = 0;
+    es.buf = 0;
+    es.tmem_base = tmem_base;
+    es.out_buf = out_buf;
+    es.out_u32 = ptx::smem_u32(out_buf);
+    es.bias_u32 = ptx::smem_u32(s_bias);
+    es.s_bias = s_bias;
+    es.tmem_full = tmem_full;
+    es.tmem_empty = tmem_empty;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int n0 = (t % p.tiles_n) * BN;
-      const int grp = t / p.tiles_n;
-      if (et < BN) {
-        float bv = (p.bias && n0 + et < p.bias_n) ? __ldg(p.bias + n0 + et) : 0.f;
-        if (SPADE && et >= p.sC && et < 2 * p.sC) {   // fused SPADE: beta's bias absorbs the style offset s1 of this tile's sample
-          int w0t, h0t, b0t;
-          subtile_origin(p, (t / p.tiles_n) * Cfg::MT, w0t, h0t, b0t);
-          bv += __ldg(p.spar + ((size_t)min(b0t, p.B - 1) * 4 + 3) * p.sC + (et - p.sC));
-        }
-        s_bias[et] = bv;
-      }
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < Cfg::MT; ++j) {
-        int w0, h0, b0;
-        subtile_origin(p, grp * Cfg::MT + j, w0, h0, b0);
-        const bf16* side = p.mask ? p.mask : p.res;   // per-pixel side input shaped like the output (mask or residual)
-        const bf16* mrow = nullptr;
-        const float* par = nullptr;
-        uint8_t* mask_row = nullptr;   // fused SPADE, training: this pixel's activation-mask bytes
-        if (side || SPADE) {
-          const int tw = row % p.TW, r2 = row / p.TW;
-          const int th = r2 % p.TH, tb = r2 / p.TH;
-          if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo) {
-            if (SPADE_TRAIN && p.smask) mask_row = p.smask + (((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * (size_t)(p.sC >> 3);
-            if (side) {
-              mrow = side + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout);
-            } else if (SPADE && p.sup) {   // x lives at half resolution (nearest 2x up-sampling folded in)
-              mrow = p.sx + ((((size_t)(b0 + tb) * (p.Ho >> 1) + ((h0 + th) >> 1)) * (p.Wo >> 1) + ((w0 + tw) >> 1)) * p.sC);
-            } else {
-              mrow = p.sx + ((((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.sC);
-            }
-          }
-          if (SPADE) par = p.spar + (size_t)min(b0, p.B - 1) * 4 * p.sC;   // host guarantees TB == 1: one sample per tile
-        }
-        const int nch = SPADE ? (p.sC >> 6) : BN / 64;
-#pragma unroll 1
-        for (int ch = 0; ch < nch; ++ch) {
-          const int nbase = n0 + ch * 64;
-          if (!SPADE && nbase >= p.Cout) break;
-          uint32_t r[16], rb[16];
-          const uint32_t taddr =
-              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::MT * BN + j * BN + ch * 64 + sub * 16);
-          ptx::tmem_ld_32x16(taddr, r);
-          if (SPADE) ptx::tmem_ld_32x16(taddr + (uint32_t)p.sC, rb);   // beta sits sC columns after gamma
-          const uint32_t dflt = p.mask ? 0x3f803f80u : 0u;   // mask: keep everything / residual, x: zero
-          uint4 mk[2] = {make_uint4(dflt, dflt, dflt, dflt), make_uint4(dflt, dflt, dflt, dflt)};
-          if (mrow) {  // host guarantees Cout % 64 == 0 when a mask / residual is given
-#pragma unroll
-            for (int i = 0; i < 2; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(mrow + nbase + sub * 16) + i);
-          }
-          // the TMA store that last read this staging buffer must have finished reading it
-          if (store_thread) {
-            if (SPADE_TRAIN) ptx::tma_store_wait_read<0>();   // this chunk fills BOTH staging buffers (output and gamma)
-            else ptx::tma_store_wait_read<1>();
-          }
-          ptx::named_bar_sync(1, FWD_EPI_THREADS);   // also orders the s_bias writes of this tile before the reads below
-          ptx::tmem_ld_wait();
-          uint8_t* ob = out_buf + buf * OUT_BUF_BYTES + row * 128;
-          const float4* bsrc = reinterpret_cast<const float4*>(s_bias + ch * 64 + sub * 16);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float4 b0v = bsrc[2 * i], b1v = bsrc[2 * i + 1];
-            uint32_t pk[4];
-            float v[8];
-            v[0] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 0]), scale, b0v.x));
-            v[1] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 1]), scale, b0v.y));
-            v[2] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 2]), scale, b0v.z));
-            v[3] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 3]), scale, b0v.w));
-            v[4] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 4]), scale, b1v.x));
-            v[5] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 5]), scale, b1v.y));
-            v[6] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 6]), scale, b1v.z));
-            v[7] = act_t<ACT>(fmaf(__uint_as_float(r[8 * i + 7]), scale, b1v.w));
-            if (p.res) {  // residual add in fp32, one rounding on the sum (bf16 pair: low half = even channel)
-              const uint32_t rw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[2 * e] += __uint_as_float(rw[e] << 16);
-                v[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
-              }
-            }
-            if (SPADE) {  // v = gamma (+bias); form the SPADE+Style output from x, beta and the per-channel constants
-              const int c0 = ch * 64 + sub * 16 + 8 * i;
-              const float4* bb = reinterpret_cast<const float4*>(s_bias + p.sC + c0);
-              const float4 bb0 = bb[0], bb1 = bb[1];
-              const float betab[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
-              const float4* pa = reinterpret_cast<const float4*>(par + c0);
-              const float4* pb = reinterpret_cast<const float4*>(par + p.sC + c0);
-              const float4* pc = reinterpret_cast<const float4*>(par + 2 * p.sC + c0);
-              const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), k0 = __ldg(pb), k1 = __ldg(pb + 1), c0v = __ldg(pc), c1v = __ldg(pc + 1);
-              const float ka[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-              const float kb[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-              const float kc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-              const uint32_t xw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
-              if (SPADE_TRAIN) {   // gamma itself goes to the other staging buffer (rounded to bf16 exactly like backward reads it)
-                uint8_t* og = out_buf + (buf ^ 1) * OUT_BUF_BYTES + row * 128;
-                *reinterpret_cast<uint4*>(og + (((sub * 2 + i) ^ (row & 7)) << 4)) =
-                    make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
-              }
-              uint32_t bits = 0;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float xv = __uint_as_float((e & 1) ? (xw[e >> 1] & 0xffff0000u) : (xw[e >> 1] << 16));
-                const float beta = fmaf(__uint_as_float(rb[8 * i + e]), scale, betab[e]);   // includes the style offset s1
-                float o = p.sscale * (fmaf(fmaf(xv, ka[e], kb[e]), 1.f + v[e], beta) + xv * kc[e]);
-                if (p.sact == S2E_ACT_LRELU) o = fmaxf(o, 0.2f * o);
-                bits |= (o > 0.f ? 1u : 0u) << e;
-                v[e] = o;
-              }
-              if (SPADE_TRAIN && mask_row) mask_row[(ch * 64 + sub * 16 + 8 * i) >> 3] = (uint8_t)bits;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pk[e] = pack2_bf16(v[2 * e], v[2 * e + 1]);
-            if (p.mask) {  // keep a value only where the bf16 mask element is > 0 (sign clear and magnitude non-zero)
-              const uint32_t mw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
-                const uint32_t keep = (((lo & 0x8000u) == 0u && (lo & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) |
-                                      (((hi & 0x8000u) == 0u && (hi & 0x7fffu) != 0u) ? 0xffff0000u : 0u);
-                pk[e] &= keep;
-              }
-            }
-            *reinterpret_cast<uint4*>(ob + (((sub * 2 + i) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-          ptx::fence_proxy_async_smem();
-          ptx::named_bar_sync(2, FWD_EPI_THREADS);
-          if (store_thread && !(p.dbg & 1)) {
-            ptx::tma_store_4d(&tmY, out_buf + buf * OUT_BUF_BYTES, nbase, w0, h0, b0);
-            if (SPADE_TRAIN) ptx::tma_store_4d(&tmG, out_buf + (buf ^ 1) * OUT_BUF_BYTES, nbase, w0, h0, b0);
-            ptx::tma_store_commit();
-          }
-          if (!SPADE_TRAIN) buf ^= 1;
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (SPADE) epilogue_tile<BN, ACT, MODE, 0>(p, es, t, &tmY, &tmG);
+      else if (p.mask) epilogue_tile<BN, ACT, MODE, 1>(p, es, t, &tmY, &tmG);
+      else if (p.res) epilogue_tile<BN, ACT, MODE, 2>(p, es, t, &tmY, &tmG);
+      else epilogue_tile<BN, ACT, MODE, 0>(p, es, t, &tmY, &tmG);
     }
-    if (store_thread) ptx::tma_store_wait<0>();
+    if (es.store_thread) ptx::tma_store_wait<0>();
   }
 
   ptx::tc_fence_before();
@@ -621,7 +667,15 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   p.tiles_b = ceil_div(d->B, tb);
   p.tiles_n = ceil_div(d->Cout, BN);
   p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
-  p.num_tiles = ceil_div(p.tiles_m, Cfg::MT) * p.tiles_n;
+  p.mt = Cfg::MT;
+  if (!HALO && !spade && Cfg::MT == 2 && !(s2e_debug_get(6) & 4)) {
+    // double tiles halve the number of work items: on small maps (the low-resolution gamma|beta data gradients: 120 or 30
+    // single tiles) they leave most SMs idle.  A single tile costs ~0.6 of a double one (the weight tile is not shared).
+    const int sms = s2e_num_sms();
+    const long long w1 = (long long)ceil_div(p.tiles_m * p.tiles_n, sms) * 6, w2 = (long long)ceil_div(ceil_div(p.tiles_m, 2) * p.tiles_n, sms) * 10;
+    if (w1 < w2) p.mt = 1;
+  }
+  p.num_tiles = ceil_div(p.tiles_m, p.mt) * p.tiles_n;
   p.TW = tw;
   p.TH = th;
   p.TB = tb;
@@ -646,7 +700,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
   S2E_REQUIRE(d->in_act == S2E_ACT_NONE && d->mask_slope == 0.f && !d->img_out, "tapconv_fwd: in_act / mask_slope / image head exist on the CUDA-core path only");
   S2E_REQUIRE(!(p.mask || p.res) || d->Cout % 64 == 0, "tapconv_fwd: relu_mask / residual need Cout %% 64 == 0 on the tcgen05 path");
   // fused SPADE: the MT sub-tiles of one work item must belong to one sample; a partial last row of tiles is fine (TMA clips)
-  S2E_REQUIRE(!spade || (p.tiles_w * p.tiles_h) % Cfg::MT == 0, "tapconv_fwd: fused SPADE: sub-tiles of one tile must share a sample");
+  S2E_REQUIRE(!spade || (p.tiles_w * p.tiles_h) % p.mt == 0, "tapconv_fwd: fused SPADE: sub-tiles of one tile must share a sample");
   p.a_box_bytes = (uint32_t)(tw * th * tb * BK * 2);
   p.halo_box_bytes = (uint32_t)((tw + 2) * (th + 2) * BK * 2);
   p.halo_bo = s2e_debug_get(6) & 2 ? 1 : 0;
