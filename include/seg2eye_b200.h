@@ -41,8 +41,9 @@ int s2e_abi_version(void);
 /* debug knobs (bring-up only): key 0 = swap LBO/SBO in MN-major UMMA descriptors, key 1 = force SIMT,
  * key 2 = keep thin-channel layers on the generic SIMT kernel, key 3 = forward epilogue timing experiments (bit 0: skip
  * the TMA store), key 5 = 1: weight gradients with an N side < 256 go back to the one-tap-per-CTA kernel (default: several
- * taps per CTA), key 6: bit 0 = 3x3 / stride-1 convolutions with an N tile <= 128 take the halo-tile forward kernel, bit 1 =
- * its A descriptors carry an explicit base offset, bit 2 = never fall back to single 128-pixel tiles on small maps.  The Python binding sets them from S2E_DEBUG="key=value,...". */
+ * taps per CTA; 2: these issue one MMA per tap even where the taps could share one), key 6: bit 0 = 3x3 / stride-1 convolutions with an N tile <= 128 take the halo-tile forward kernel, bit 1 =
+ * its A descriptors carry an explicit base offset, bit 2 = never fall back to single 128-pixel tiles on small maps, bit 3 = layers with Cout <= 128 keep pixels on the M side
+ * (no swapped-operand mode).  The Python binding sets them from S2E_DEBUG="key=value,...". */
 int s2e_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------------------------

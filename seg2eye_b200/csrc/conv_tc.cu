@@ -182,7 +182,7 @@ template <int BN, int ACT, int MODE, int SIDE>
 __device__ __forceinline__ void epilogue_tile(const FwdParams& p, EpiState& es, const int t, const CUtensorMap* tmY,
                                               const CUtensorMap* tmG) {
   using Cfg = FwdCfg<BN>;
-  constexpr bool SPADE = MODE != 0, SPADE_TRAIN = MODE == 2;
+  constexpr bool SPADE = MODE == 1 || MODE == 2, SPADE_TRAIN = MODE == 2;
   constexpr bool LOADS = SPADE || SIDE != 0;   // reads 16 bf16 per thread and chunk next to the accumulator
   const int q = es.q, sub = es.sub, row = es.row, et = es.et;
   const float scale = es.scale;
@@ -330,7 +330,92 @@ __device__ __forceinline__ void epilogue_tile(const FwdParams& p, EpiState& es, 
   if (es.acc == 0) es.acc_phase ^= 1;
 }
 
-// MODE 0: plain convolution epilogue; 1: fused SPADE+Style modulation (inference); 2: the same, also writing gamma and the
+// Swapped-operand mode (MODE 3, Cout <= 128): the accumulator is D^T -- TMEM lane = output channel, column = pixel (two
+// 128-pixel sub-tiles side by side).  A thread owns ONE channel (lane) and 32 pixels (columns) of a sub-tile and scatters
+// bf16 values into the pixel-major staging buffers (one per 64-channel half, both filled in the same phase).
+template <int ACT, int SIDE>
+__device__ __forceinline__ void epilogue_tile_swapped(const FwdParams& p, EpiState& es, const int t, const CUtensorMap* tmY) {
+  const int q = es.q, sub = es.sub;
+  const int co = es.row;                       // q * 32 + lane: this thread's output channel within the 128-wide tile
+  const int n0 = (t % p.tiles_n) * 128;
+  const int grp = t / p.tiles_n;
+  const int cout = n0 + co;
+  const bool live = cout < p.Cout;
+  const float bv = (p.bias && cout < p.bias_n) ? __ldg(p.bias + cout) : 0.f;
+  const float scale = es.scale;
+  ptx::mbar_wait(&es.tmem_full[es.acc], es.acc_phase);
+  ptx::tc_fence_after();
+  // staging address of (pixel row r, this channel): half (co >> 6), row r * 128, 16-byte chunk ((co & 63) >> 3) ^ (r & 7)
+  const int c8 = (co & 63) >> 3;
+  uint32_t sbase[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+    sbase[m] = es.out_u32 + (uint32_t)((co >> 6) * OUT_BUF_BYTES + sub * 32 * 128 + ((c8 ^ m) << 4) + (co & 7) * 2);
+#pragma unroll 1
+  for (int j = 0; j < p.mt; ++j) {
+    int w0, h0, b0;
+    subtile_origin(p, grp * p.mt + j, w0, h0, b0);
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(es.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(es.acc * 256 + j * 128 + sub * 32), r);
+    // Side input (mask / residual), pixel-major in memory: all 512 threads copy the tile's 128 x 128 values into the staging
+    // buffers with 16-byte accesses (thread = 2 pixel rows x 2 channel halves x 8 channels, the layout the TMA store reads);
+    // each channel thread then reads its 32 values from there and overwrites them with the result.  (Per-channel 2-byte global
+    // loads, the direct way, cost 1.1 ns per pixel on B200.)
+    uint4 sd[4];
+    if (SIDE != 0) {
+      const bf16* side = SIDE == 1 ? p.mask : p.res;
+      constexpr uint32_t dflt = SIDE == 1 ? 0x3f803f80u : 0u;   // pixel outside the map: mask keeps everything, residual is zero
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int prow = (es.et >> 3) + 64 * (v & 1), half = v >> 1;
+        const int tw = prow % p.TW, r2 = prow / p.TW;
+        const int th = r2 % p.TH, tb = r2 / p.TH;
+        sd[v] = make_uint4(dflt, dflt, dflt, dflt);
+        if (tb < p.TB && b0 + tb < p.B && h0 + th < p.Ho && w0 + tw < p.Wo && n0 + half * 64 < p.Cout)
+          sd[v] = __ldg(reinterpret_cast<const uint4*>(side + (((size_t)(b0 + tb) * p.Ho + h0 + th) * p.Wo + w0 + tw) * p.Cout + n0 +
+                                                       half * 64 + (es.et & 7) * 8));
+      }
+    }
+    if (es.store_thread) ptx::tma_store_wait_read<0>();   // both staging buffers are refilled below
+    ptx::named_bar_sync(1, FWD_EPI_THREADS);
+    if (SIDE != 0) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int prow = (es.et >> 3) + 64 * (v & 1), half = v >> 1;
+        ptx::sts128(es.out_u32 + (uint32_t)(half * OUT_BUF_BYTES + prow * 128 + (((es.et & 7) ^ (prow & 7)) << 4)), sd[v].x, sd[v].y,
+                    sd[v].z, sd[v].w);
+      }
+      ptx::named_bar_sync(3, FWD_EPI_THREADS);
+    }
+    ptx::tmem_ld_wait();
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const uint32_t addr = sbase[i & 7] + (uint32_t)(i * 128);
+        float v = act_t<ACT>(fmaf(__uint_as_float(r[i]), scale, bv));
+        uint32_t sv = 0;
+        if (SIDE != 0) sv = ptx::lds16(addr);
+        if (SIDE == 2) v += __uint_as_float(sv << 16);   // residual add in fp32, one rounding on the sum
+        uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+        if (SIDE == 1 && ((sv & 0x8000u) != 0u || (sv & 0x7fffu) == 0u)) h = 0u;   // keep only where the mask is > 0
+        ptx::sts16(addr, h);
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::named_bar_sync(2, FWD_EPI_THREADS);
+    if (es.store_thread && !(p.dbg & 1)) {
+      ptx::tma_store_4d(tmY, es.out_buf, n0, w0, h0, b0);
+      if (n0 + 64 < p.Cout) ptx::tma_store_4d(tmY, es.out_buf + OUT_BUF_BYTES, n0 + 64, w0, h0, b0);
+      ptx::tma_store_commit();
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::mbar_arrive(&es.tmem_empty[es.acc]);
+  es.acc ^= 1;
+  if (es.acc == 0) es.acc_phase ^= 1;
+}
+
+// MODE 0: plain convolution epilogue; 3: the same with swapped MMA operands (weights = A, pixels = B; see below); 1: fused SPADE+Style modulation (inference); 2: the same, also writing gamma and the
 // activation mask for backward.  A template parameter so that the ordinary instantiations do not carry the extra code.
 template <int BN, int ACT, int MODE, bool HALO>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
@@ -338,7 +423,8 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const FwdParams p) {
   using Cfg = FwdCfg<BN>;
   using HCfg = HaloCfg<BN>;
-  constexpr bool SPADE = MODE != 0, SPADE_TRAIN = MODE == 2;
+  constexpr bool SPADE = MODE == 1 || MODE == 2, SPADE_TRAIN = MODE == 2, SWAPPED = MODE == 3;
+  static_assert(!SWAPPED || (BN == 128 && !HALO), "swapped-operand mode: N tile 128, no halo staging");
   // ring barriers: non-HALO: full/empty[STAGES] guard (A | B) stages.  HALO: full/empty[0..B_STAGES) guard the weight
   // ring, full/empty[B_STAGES .. B_STAGES + A_SLOTS) guard the halo tiles
   constexpr int NBARS = HALO ? HCfg::B_STAGES + HCfg::A_SLOTS : Cfg::STAGES;
@@ -523,6 +609,16 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
           const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::MT * A_STAGE_BYTES;
+          if (SWAPPED) {
+            // weights are the A operand (M = 128 output channels; rows past Cout are TMA zero fill), the mt pixel sub-tiles
+            // -- contiguous in the stage -- one B operand of N = mt * 128: one MMA per k-step.  In SS mode an MMA costs at
+            // least the A read (~110 clk for 128 rows x 16), whatever its N; N = 64 / 128 issue could not hide that.
+            const uint32_t idesc_s = ptx::umma_idesc_bf16(128, p.mt * 128, 0, 0);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(b_addr + k * 32, 0, 1024), ptx::umma_desc_sw128(a_addr + k * 32, 0, 1024),
+                             idesc_s, (kb | k) != 0 ? 1u : 0u);
+          } else
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 32, 0, 1024);
@@ -572,7 +668,11 @@ tapconv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     es.tmem_full = tmem_full;
     es.tmem_empty = tmem_empty;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      if (SPADE) epilogue_tile<BN, ACT, MODE, 0>(p, es, t, &tmY, &tmG);
+      if (SWAPPED) {
+        if (p.mask) epilogue_tile_swapped<ACT, 1>(p, es, t, &tmY);
+        else if (p.res) epilogue_tile_swapped<ACT, 2>(p, es, t, &tmY);
+        else epilogue_tile_swapped<ACT, 0>(p, es, t, &tmY);
+      } else if (SPADE) epilogue_tile<BN, ACT, MODE, 0>(p, es, t, &tmY, &tmG);
       else if (p.mask) epilogue_tile<BN, ACT, MODE, 1>(p, es, t, &tmY, &tmG);
       else if (p.res) epilogue_tile<BN, ACT, MODE, 2>(p, es, t, &tmY, &tmG);
       else epilogue_tile<BN, ACT, MODE, 0>(p, es, t, &tmY, &tmG);
@@ -646,7 +746,7 @@ int launch_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float* 
     if ((rc = make_map_nhwc(&tmA, x, d->B, d->Hi, d->Wi, d->Cin, tw, th, tb)) != S2E_OK) return rc;
   }
   if ((rc = make_map_w(&tmB, wp, d->ntaps, d->Cout, d->Cin, BN)) != S2E_OK) return rc;
-  const bool spade = MODE != 0;
+  const bool spade = MODE == 1 || MODE == 2;
   S2E_REQUIRE(spade == (d->spade_x != nullptr) && (MODE == 2) == (spade && d->spade_gamma_out != nullptr), "tapconv_fwd: mode mismatch");
   if (spade) {
     S2E_REQUIRE(d->spade_par && (d->spade_C == 64 || d->spade_C == 128) && d->Cout == 2 * d->spade_C && BN == d->Cout,
@@ -732,6 +832,7 @@ struct WgParams {
   int kt_w, kt_h, kt_b, kt_total;  // pixel tiles
   int KTW, KTH, KTB, KP;
   int swap_lbo_sbo;
+  int merge_taps;   // multi-tap kernel, 64-channel taps on the N side: one MMA of N = ntap * 64 per k-step
   float* dwp;
   TapTable taps;
 };
@@ -948,6 +1049,7 @@ int launch_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp,
   p.KTB = tb;
   p.KP = KP;
   p.swap_lbo_sbo = s2e_debug_get(0);
+  p.merge_taps = 0;
   p.dwp = dwp;
   p.taps.n = d->ntaps;
   for (int i = 0; i < d->ntaps; ++i) {
@@ -1097,6 +1199,23 @@ tapconv_wgrad_mt_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
       ptx::tc_fence_after();
       if (lane == 0) {
         const uint32_t s_addr = ptx::smem_u32(smem + stage * stage_bytes);
+        if (p.merge_taps) {
+          // taps on the N side whose operand blocks sit WG_BLK apart ARE one MN-major operand of g * BN columns (64-column
+          // atoms WG_BLK apart): one MMA of N <= 256 per k-step covers g = 256 / BN taps and reads the shared dY operand once.
+          // In SS mode an MMA costs at least its A read (~110 clk for 128 rows x 16) whatever its N, so three N = 64 MMAs take
+          // 330 clk where one N = 192 MMA takes 110.
+          constexpr int G = 256 / BN;
+          for (int tt = 0; tt < ntap; tt += G) {
+            const int g = min(G, ntap - tt);
+            const uint32_t idesc_n = ptx::umma_idesc_bf16(128, g * BN, 1, 1);
+            const uint32_t t_addr = s_addr + (uint32_t)((shared_blocks + tt * tap_blocks) * WG_BLK);
+            for (int k = 0; k < kmma; ++k) {
+              const uint64_t ad = ptx::umma_desc_sw128(s_addr + k * 2048, lbo, sbo);
+              const uint64_t bd = ptx::umma_desc_sw128(t_addr + k * 2048, (uint32_t)WG_BLK, sbo);
+              ptx::umma_bf16(tmem_base + (uint32_t)(tt * BN), ad, bd, idesc_n, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+        } else
         for (int tt = 0; tt < ntap; ++tt) {
           const uint32_t t_addr = s_addr + (uint32_t)((shared_blocks + tt * tap_blocks) * WG_BLK);
           const uint32_t a_addr = p.swap ? t_addr : s_addr;   // A = M side: dY (shared) unless swapped
@@ -1186,12 +1305,15 @@ int launch_wgrad_mt(const s2e_conv_t* d, const void* x, const void* dy, float* d
   p.KTB = tb;
   p.KP = KP;
   p.swap_lbo_sbo = s2e_debug_get(0);
+  p.merge_taps = 0;
   p.dwp = dwp;
   p.taps.n = d->ntaps;
   for (int i = 0; i < d->ntaps; ++i) {
     p.taps.dy[i] = d->tap_dy[i];
     p.taps.dx[i] = d->tap_dx[i];
   }
+  // (BN = 128: the two 64-channel blocks of a tap are blk_bytes apart, the taps 2 * WG_BLK: uniform only for 64-pixel k tiles)
+  p.merge_taps = ((BN == 64 || KP * 128 == WG_BLK) && BN <= 128 && !swap && !p.swap_lbo_sbo && s2e_debug_get(5) != 2) ? 1 : 0;
   const int ngroups = ceil_div(d->ntaps, TPC);
   const int shared_blocks = swap ? BN / 64 : 2, tap_blocks = swap ? 2 : BN / 64;
   const int stage_bytes = (shared_blocks + TPC * tap_blocks) * WG_BLK;
@@ -1257,6 +1379,16 @@ int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const
     return launch_fwd<128, S2E_ACT_NONE, 1, false>(d, x, wp, bias, scale, y, stream);
   }
   if (d->Cout >= 256) { S2E_FWD_DISPATCH(256, false) }
+  // Cout <= 128: swapped operands (MODE 3) unless debug key 6 bit 3 is set or the halo kernel is asked for.  With Cout = 64 only
+  // half of the epilogue warps own live TMEM lanes, so short reductions (K < 512: 1x1 shortcuts, the 2x2 taps of stride-2
+  // 64-channel layers), which are paced by the epilogue, stay on the N = 64 kernel.
+  if (!halo && d->Cout >= 64 && (d->Cout >= 128 || d->ntaps * d->Cin >= 512) && !(s2e_debug_get(6) & 8)) {
+    switch (d->act) {
+      case S2E_ACT_LRELU: return launch_fwd<128, S2E_ACT_LRELU, 3, false>(d, x, wp, bias, scale, y, stream);
+      case S2E_ACT_RELU: return launch_fwd<128, S2E_ACT_RELU, 3, false>(d, x, wp, bias, scale, y, stream);
+      default: return launch_fwd<128, S2E_ACT_NONE, 3, false>(d, x, wp, bias, scale, y, stream);
+    }
+  }
   if (d->Cout >= 128) {
     if (halo) { S2E_FWD_DISPATCH(128, true) }
     S2E_FWD_DISPATCH(128, false)
@@ -1272,7 +1404,9 @@ int s2e_tapconv_wgrad_tc(const s2e_conv_t* d, const void* x, const void* dy, flo
               "tcgen05 wgrad needs Cin,Cout %% 8 == 0 and >= 64 (Cin=%d Cout=%d)", d->Cin, d->Cout);
   // orientation: the N side of the accumulator should be the wide one (N = 256 halves the shared-memory traffic
   // per MMA), and a 64-channel side should not occupy the 128-row M side
-  const int swap = (d->Cout > d->Cin) || (d->Cout < 128 && d->Cin >= 128);
+  // (debug key 5 = 2: the previous rule, which also swapped Cout < 128 <= Cin so that the 64-channel side left the M side;
+  //  with merged taps the unswapped form -- M = 64 live rows, N = 2 taps x 128 -- is the faster one)
+  const int swap = (d->Cout > d->Cin) || (s2e_debug_get(5) == 2 && d->Cout < 128 && d->Cin >= 128);
   const int nside = swap ? d->Cout : d->Cin;
   // narrow layers (N side < 256): several taps per CTA against one staged dY tile instead of one CTA per tap re-reading dY
   // nine times through L2 (B200, round 2: 64->64 196 -> 243, 128->64 389 -> 482, 128->128 752 -> 937 TFLOP/s at 640x384 x 16).
