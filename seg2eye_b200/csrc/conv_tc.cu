@@ -1381,8 +1381,10 @@ int s2e_tapconv_fwd_tc(const s2e_conv_t* d, const void* x, const void* wp, const
   if (d->Cout >= 256) { S2E_FWD_DISPATCH(256, false) }
   // Cout <= 128: swapped operands (MODE 3) unless debug key 6 bit 3 is set or the halo kernel is asked for.  With Cout = 64 only
   // half of the epilogue warps own live TMEM lanes, so short reductions (K < 512: 1x1 shortcuts, the 2x2 taps of stride-2
-  // 64-channel layers), which are paced by the epilogue, stay on the N = 64 kernel.
-  if (!halo && d->Cout >= 64 && (d->Cout >= 128 || d->ntaps * d->Cin >= 512) && !(s2e_debug_get(6) & 8)) {
+  // 64-channel layers), which are paced by the epilogue, and layers with a mask / residual input (B200: 64->64 + residual at
+  // 640x384 x 16: 0.59 -> 0.74 ms swapped) stay on the N = 64 kernel.
+  if (!halo && d->Cout >= 64 && !(s2e_debug_get(6) & 8) &&
+      (d->Cout >= 128 || (d->ntaps * d->Cin >= 512 && !d->relu_mask && !d->residual))) {
     switch (d->act) {
       case S2E_ACT_LRELU: return launch_fwd<128, S2E_ACT_LRELU, 3, false>(d, x, wp, bias, scale, y, stream);
       case S2E_ACT_RELU: return launch_fwd<128, S2E_ACT_RELU, 3, false>(d, x, wp, bias, scale, y, stream);

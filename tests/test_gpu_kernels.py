@@ -833,6 +833,30 @@ def test_spade_conv_fused_training_forward_backward(S, C, up, act):
     assert rel(bgc.grad, bgr.grad) < TOL_ACT and rel(bbc.grad, bbr.grad) < TOL_ACT
 
 
+# ------------------------------------------------------------------------------------------ forward kernel variants
+@pytest.mark.parametrize("key6", [8, 4, 12])
+def test_conv_tcgen05_forward_kernel_variants(S, key6):
+    """Layers with Cout <= 128 run with swapped MMA operands by default (weights = A, two pixel sub-tiles = one N = 256 operand,
+    transposed epilogue), and small maps take single 128-pixel tiles.  Debug key 6 bit 3 keeps the pixels on the M side (the
+    N = 64 / 128 kernels these layers used before, still used by the fused SPADE epilogues), bit 2 forces double tiles: all
+    combinations must agree with torch, on the plain cases and on the mask / residual / fused-SPADE epilogues."""
+    L, ops = S
+    L.call("s2e_debug_set", 6, key6)
+    L.call("s2e_debug_set", 5, 2 if key6 & 8 else 0)     # with bit 3 also the weight-gradient kernels without merged taps
+    try:
+        for case in [TC_CASES[0], TC_CASES[1], TC_CASES[3], TC_CASES[4], TC_CASES[5], TC_CASES[8], TC_CASES[10], TC_CASES[11],
+                     (1, 64, 64, 37, 29, 3, 1, 1, 0), (3, 128, 128, 40, 48, 3, 1, 1, 2)]:
+            conv_case(S, L.IMPL_TC, *case)
+        test_conv_residual_in_epilogue(S, "tc", 128)
+        test_conv_residual_in_epilogue(S, "tc", 64)
+        test_relu_backward_fused_into_dgrad_epilogue(S, "tc")
+        test_spade_modulation_fused_into_gamma_beta_conv(S, 64, False, 1, False)
+        test_spade_conv_fused_training_forward_backward(S, 64, False, 1)
+    finally:
+        L.call("s2e_debug_set", 6, 0)
+        L.call("s2e_debug_set", 5, 0)
+
+
 # ------------------------------------------------------------------------------------------ halo-tile forward kernel
 HALO_CASES = [
     (2, 128, 128, 24, 16, 3, 1, 1, 0),     # N = 128, two sub-tiles
