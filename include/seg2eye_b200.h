@@ -43,7 +43,8 @@ int s2e_abi_version(void);
  * the TMA store), key 5 = 1: weight gradients with an N side < 256 go back to the one-tap-per-CTA kernel (default: several
  * taps per CTA; 2: these issue one MMA per tap even where the taps could share one), key 6: bit 0 = 3x3 / stride-1 convolutions with an N tile <= 128 take the halo-tile forward kernel, bit 1 =
  * its A descriptors carry an explicit base offset, bit 2 = never fall back to single 128-pixel tiles on small maps, bit 3 = layers with Cout <= 128 keep pixels on the M side
- * (no swapped-operand mode).  The Python binding sets them from S2E_DEBUG="key=value,...". */
+ * (no swapped-operand mode), key 7 = 1: single-output-channel layers with a wide input (PatchGAN head) skip the tiled head kernel.
+ * The Python binding sets them from S2E_DEBUG="key=value,...". */
 int s2e_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------------------------
@@ -126,6 +127,17 @@ int s2e_tapconv_fwd(const s2e_conv_t* d, const void* x, const void* wp, const fl
                     void* y, int impl, void* stream);
 /* dWp[t][co][ci] += sum_pixels dy[p,co] * x[p+tap_t,ci]   (fp32, atomically accumulated; caller zeroes) */
 int s2e_tapconv_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dwp, int impl, void* stream);
+
+/* PatchGAN logit head (discriminator.py:38 / :96 in the stock layout: nn.Conv2d(8*ndf, 1, kernel_size=4, stride=1,
+ * padding=2), the last block of NLayerDiscriminator) in tap-channel form, y[p] = sum_t D[p + tap_t][t] with
+ * D[q][t] = x[q] . W[t]: the wide input is read once, not once per tap.
+ *   s2e_head_dots    D[P][16] fp32 (taps >= ntaps: 0) from x [P][Cin] bf16 and the tap-major weight copy wp [ntaps][Cin] bf16
+ *   s2e_head_gather  y [B][Ho][Wo][1] bf16 = act(scale * sum_t D[...] + bias); geometry, taps and act from the descriptor
+ *   s2e_head_scatter G [B][Hi][Wi][64] bf16, G[q][t] = dy[q - tap_t] (0 outside the output / for t >= ntaps): the data and
+ *                    weight gradients are then the 1x1 tap convolutions dx = G . W (64 -> Cin) and dW = G^T . x. */
+int s2e_head_dots(const void* x_bf16, const void* wp_bf16, long long P, int Cin, int ntaps, float* D, void* stream);
+int s2e_head_gather(const s2e_conv_t* d, const float* D, const float* bias, const float* scale, void* y_bf16, void* stream);
+int s2e_head_scatter(const s2e_conv_t* d, const void* dy_bf16, void* G_bf16, void* stream);
 
 /* OIHW fp32 master weight -> bf16 tap-major.  stride 1: taps (r,s) row-major, offset (r-pad, s-pad).
  * stride 2: space-to-depth taps (a,b), a in [floor(-pad/2), floor((k-1-pad)/2)], channel (i*2+j)*Cin+ci,

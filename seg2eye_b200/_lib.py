@@ -51,6 +51,9 @@ _SIGS = {
     "s2e_nhwc_bf16_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_tapconv_fwd": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _I, _P],
     "s2e_tapconv_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _I, _P],
+    "s2e_head_dots": [_P, _P, _LL, _I, _I, _P, _P],
+    "s2e_head_gather": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P],
+    "s2e_head_scatter": [C.POINTER(ConvDesc), _P, _P, _P],
     "s2e_pack_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "s2e_packed_taps": [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)],
     "s2e_unpack_wgrad": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],

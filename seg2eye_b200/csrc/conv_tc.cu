@@ -1008,7 +1008,12 @@ void choose_k_tile(int B, int H, int W, int* tw, int* th, int* tb) {
         if ((w > W && w > 16) || (h > H && h > 1 && prod > 16) || (b > B && b > 1)) continue;
         long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(B, b);
         long long padded = tiles * prod;
-        long long score = padded * 4096 + tiles * 8 - (w >= 8 ? 1 : 0);
+        // Boxes whose rows are one or two pixels long (the zero-padding choice for the odd-sized discriminator maps, e.g.
+        // {1, 2, 32} for 82 x 50) load far slower than boxes of >= 4 adjacent pixels with a few per cent of padding
+        // (B200, B32 82x50 256->512 4x4: 0.95 ms with {1,2,32}, 0.51-0.53 ms with {2,2,16} / {4,2,8}; B32 161x97 256->128
+        // 2x2: 0.334 / 0.178 / 0.131 ms with w = 1 / 2 / 4) -- profiles/r02e_ktile_probe.txt
+        const int pen = w >= 4 ? 100 : (w == 3 ? 108 : (w == 2 ? 120 : 160));
+        long long score = padded * pen * 41 + tiles * 8 - (w >= 8 ? 1 : 0);
         if (best < 0 || score < best) {
           best = score;
           bw = w;

@@ -358,6 +358,123 @@ __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __re
   }
 }
 
+// PatchGAN logit head (discriminator.py:38: Cin = 8*ndf -> 1, 4x4, stride 1, pad 2; K = 8192) in "tap-channel" form:
+//   y[p] = sum_t D[p + tap_t][t],   D[q][t] = x[q] . W[t]        (a 1x1 convolution Cin -> 16 tap channels + a gather)
+// so the input is read ONCE, not once per tap.  head_dots_kernel forms D in fp32 on the CUDA cores (2 * 16 * Cin FLOPs per
+// pixel: FMA-bound at ~30 us for B32 82x50x512, where zero-padding the single output channel to a 64-wide tensor-core tile
+// moved 16 taps x the whole input through shared memory: 0.21 ms): one warp per four pixels, each lane owns NCH 8-channel
+// chunks of the pixel (the pixel row is one coalesced read), tap weights come from shared memory as conflict-free
+// 16-byte loads and feed four pixels; the 64 lane-partial sums are combined with a halving butterfly (62 shuffles, not 320).
+// head_gather_kernel adds the taps' entries, scale, bias, activation.  Backward (ops.HeadConvFn): head_scatter_kernel builds
+// G[q][t] = dy[q - tap_t] (64 channels, 16 live), and dx = G . W, dW = G^T . x are 1x1 convolutions on the tcgen05 kernels.
+constexpr int HD_THREADS = 128;
+template <int NCH>
+__global__ void __launch_bounds__(HD_THREADS) head_dots_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                               float* __restrict__ D, int Cin, int ntaps, long long P) {
+  extern __shared__ __align__(16) float hd_ws[];          // [16 taps][NCH][2 halves][32 lanes][4]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 16 * NCH * 256; i += HD_THREADS) {
+    const int e = i & 3, l = (i >> 2) & 31, h = (i >> 7) & 1, r = i >> 8;
+    const int ch = r % NCH, t = r / NCH;
+    const int c = (ch * 32 + l) * 8 + h * 4 + e;
+    hd_ws[i] = (t < ntaps && c < Cin) ? __bfloat162float(wp[(long long)t * Cin + c]) : 0.f;
+  }
+  __syncthreads();
+  const long long ngroups = (P + 3) >> 2;
+  for (long long grp = (long long)blockIdx.x * (HD_THREADS / 32) + warp; grp < ngroups; grp += (long long)gridDim.x * (HD_THREADS / 32)) {
+    const long long p0 = grp << 2;
+    float xf[4][NCH][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c0 = (ch * 32 + lane) * 8;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (p0 + i < P && c0 < Cin) raw = __ldg(reinterpret_cast<const uint4*>(x + (p0 + i) * Cin + c0));
+        unpack8(*reinterpret_cast<const bf16x8*>(&raw), xf[i][ch]);
+      }
+    }
+    float v[64];   // v[i * 16 + t]: this lane's share of pixel i, tap t
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      float w[NCH][8];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float4 a = *reinterpret_cast<const float4*>(hd_ws + (((t * NCH + ch) * 2 + 0) * 32 + lane) * 4);
+        const float4 c = *reinterpret_cast<const float4*>(hd_ws + (((t * NCH + ch) * 2 + 1) * 32 + lane) * 4);
+        w[ch][0] = a.x; w[ch][1] = a.y; w[ch][2] = a.z; w[ch][3] = a.w;
+        w[ch][4] = c.x; w[ch][5] = c.y; w[ch][6] = c.z; w[ch][7] = c.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a = fmaf(xf[i][ch][j], w[ch][j], a);
+        v[i * 16 + t] = a;
+      }
+    }
+    // halving butterfly: after the step with offset o a lane keeps the half of its values selected by its bit o
+#pragma unroll
+    for (int o = 16, cnt = 64; o >= 1; o >>= 1, cnt >>= 1) {
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int j = 0; j < cnt / 2; ++j) {
+        const float lo = v[j], hi = v[j + cnt / 2];
+        const float send = upper ? lo : hi, keep = upper ? hi : lo;
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    // lane holds values 2*lane, 2*lane + 1: pixel lane >> 3, taps (lane & 7) * 2 + {0, 1}
+    const long long p = p0 + (lane >> 3);
+    if (p < P) *reinterpret_cast<float2*>(D + p * 16 + (lane & 7) * 2) = make_float2(v[0], v[1]);
+  }
+}
+
+__global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ D, const float* __restrict__ bias,
+                                                          const float* __restrict__ scale, bf16* __restrict__ y, const ThinGeom g,
+                                                          long long P) {
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= P) return;
+  const int wo = (int)(p % g.Wo);
+  const long long r = p / g.Wo;
+  const int ho = (int)(r % g.Ho);
+  const long long b = r / g.Ho;
+  float acc = 0.f;
+  for (int t = 0; t < g.ntaps; ++t) {
+    const int hi = ho + g.dy[t], wi = wo + g.dx[t];
+    if (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) acc += __ldg(D + ((b * g.Hi + hi) * g.Wi + wi) * 16 + t);
+  }
+  y[p] = __float2bfloat16(act_apply(acc * (scale ? __ldg(scale) : 1.f) + (bias ? __ldg(bias) : 0.f), g.act));
+}
+
+// G[q][t] = dy[q - tap_t] for t < ntaps (zero where that output pixel does not exist), zero for the other 64 - ntaps
+// channels; thread = one 8-channel chunk of one input pixel
+__global__ void __launch_bounds__(256) head_scatter_kernel(const bf16* __restrict__ dy, bf16* __restrict__ G, const ThinGeom g,
+                                                           long long nchunks) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= nchunks) return;
+  const int ch = (int)(i & 7);
+  const long long q = i >> 3;
+  const int wi = (int)(q % g.Wi);
+  const long long r = q / g.Wi;
+  const int hi = (int)(r % g.Hi);
+  const long long b = r / g.Hi;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int t = ch * 8 + j;
+    float v = 0.f;
+    if (t < g.ntaps) {
+      const int ho = hi - g.dy[t], wo = wi - g.dx[t];
+      if (ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo) v = __bfloat162float(dy[(b * g.Ho + ho) * g.Wo + wo]);
+    }
+    f[j] = v;
+  }
+  *reinterpret_cast<bf16x8*>(G + i * 8) = pack8(f);
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 // wide tensor A [.., Cw] walked pixel by pixel, thin tensor S [.., Cs] sampled at (pixel + sgn*tap).
 // thread = (8-channel chunk of A, one thin channel); acc[T][8] in registers; one atomic per output at the end.
@@ -622,3 +739,44 @@ int s2e_thin_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dw
   S2E_LAUNCH_CHECK();
   return 1;
 }
+
+extern "C" {
+
+int s2e_head_dots(const void* x, const void* wp, long long P, int Cin, int ntaps, float* D, void* stream) {
+  S2E_REQUIRE(Cin % 8 == 0 && Cin >= 8 && Cin <= 1024 && ntaps >= 1 && ntaps <= 16, "head_dots: Cin %% 8 == 0, <= 1024, <= 16 taps (Cin=%d taps=%d)", Cin, ntaps);
+  if (P == 0) return S2E_OK;
+  const int nch = ceil_div(Cin, 256);
+  static int attr = 0;
+  if (first_use_on_device(&attr)) {
+    S2E_CHECK_CUDA(cudaFuncSetAttribute(head_dots_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 4 * 256 * 4));
+  }
+  long long blocks = ceil_div_ll((P + 3) / 4, HD_THREADS / 32);
+  const long long cap = (long long)s2e_num_sms() * 3;      // three resident CTAs per SM (registers): weights are staged once per CTA
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nch == 1) head_dots_kernel<1><<<(unsigned)blocks, HD_THREADS, 16 * 1 * 256 * 4, st>>>((const bf16*)x, (const bf16*)wp, D, Cin, ntaps, P);
+  else if (nch == 2) head_dots_kernel<2><<<(unsigned)blocks, HD_THREADS, 16 * 2 * 256 * 4, st>>>((const bf16*)x, (const bf16*)wp, D, Cin, ntaps, P);
+  else head_dots_kernel<4><<<(unsigned)blocks, HD_THREADS, 16 * 4 * 256 * 4, st>>>((const bf16*)x, (const bf16*)wp, D, Cin, ntaps, P);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_head_gather(const s2e_conv_t* d, const float* D, const float* bias, const float* scale, void* y, void* stream) {
+  S2E_REQUIRE(d && d->Cout == 1 && d->ntaps >= 1 && d->ntaps <= 16, "head_gather: one output channel, <= 16 taps");
+  const long long P = (long long)d->B * d->Ho * d->Wo;
+  if (P == 0) return S2E_OK;
+  head_gather_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, (cudaStream_t)stream>>>(D, bias, scale, (bf16*)y, make_thin_geom(d), P);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+int s2e_head_scatter(const s2e_conv_t* d, const void* dy, void* G, void* stream) {
+  S2E_REQUIRE(d && d->Cout == 1 && d->ntaps >= 1 && d->ntaps <= 16, "head_scatter: one output channel, <= 16 taps");
+  const long long n = (long long)d->B * d->Hi * d->Wi * 8;
+  if (n == 0) return S2E_OK;
+  head_scatter_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)G, make_thin_geom(d), n);
+  S2E_LAUNCH_CHECK();
+  return S2E_OK;
+}
+
+}  // extern "C"

@@ -73,11 +73,15 @@ class Conv2d(nn.Module):
         if x.shape[-1] != self.in_channels:   # zero-padded activation channels (e.g. the 16-channel D input)
             assert x.shape[-1] > self.in_channels, "input has fewer channels than the layer expects"
             cfg = cfg._replace(cin_pad=x.shape[-1])
-        if self.out_channels < 8 and cfg.stride == 1 and self.in_channels * cfg.kh * cfg.kw >= 4096:
-            # few output channels but a long reduction (PatchGAN logit head, K = 8192): tensor cores with the output
-            # channels zero-padded to one 64-wide tile beat the CUDA-core kernel by ~5x
+        if ops.HEAD_ON_TC and self.out_channels < 8 and cfg.stride == 1 and self.in_channels * cfg.kh * cfg.kw >= 4096:
+            # few output channels but a long reduction (PatchGAN logit head, K = 8192) on the tensor cores with the output
+            # channels zero-padded to one 64-wide tile.  Off since the tiled CUDA-core head kernel (conv_thin.cu) exists:
+            # the padded GEMM moves 16 taps x the whole input through shared memory for one live output column
             cfg = cfg._replace(cout_pad=64)
         biases = (self.bias,) if self.bias is not None else ()
+        if (not ops.HEAD_ON_TC and residual is None and not self.spectral and cfg.cin_pad == 0
+                and ops.head_conv_ok(x, cfg, self.weight)):
+            return ops.head_conv(x, cfg, self.weight, self.bias)     # PatchGAN logit head: input read once, not once per tap
         return ops.tap_conv(x, cfg, (self.master_weight(),), biases, self.sn_state(), residual)
 
     def forward_nhwc_unscaled(self, x):

@@ -6,6 +6,7 @@ Every arithmetic step calls one of our CUDA kernels through ctypes; torch is use
 the autograd graph only.
 """
 import contextlib
+import os
 from collections import namedtuple
 
 import torch
@@ -15,6 +16,7 @@ from . import _lib as L
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+HEAD_ON_TC = os.environ.get("S2E_HEAD_TC", "0") == "1"   # A/B knob: PatchGAN head zero-padded onto the tcgen05 kernels
 ConvCfg = namedtuple("ConvCfg", "kh kw stride pad act relu_in cin_pad cout_pad in_act", defaults=(False, 0, 0, 0))
 # cin_pad: the activations carry cin_pad >= Cin channels (zero padded), packed weights get zero columns for them
 # relu_in: the input of this convolution is the output of a ReLU whose backward is fused into our data-gradient epilogue
@@ -148,6 +150,9 @@ def conv_out_hw(cfg, hi, wi):
     return (hi + 2 * cfg.pad - cfg.kh) // cfg.stride + 1, (wi + 2 * cfg.pad - cfg.kw) // cfg.stride + 1
 
 
+_KTILE = tuple(int(v) for v in os.environ["S2E_KTILE"].split(",")) if os.environ.get("S2E_KTILE") else None
+
+
 def _desc(B, Hi, Wi, Cin, Ho, Wo, Cout, taps, act, negate=False):
     d = L.ConvDesc()
     d.B, d.Hi, d.Wi, d.Cin, d.Ho, d.Wo, d.Cout = B, Hi, Wi, Cin, Ho, Wo, Cout
@@ -156,6 +161,8 @@ def _desc(B, Hi, Wi, Cin, Ho, Wo, Cout, taps, act, negate=False):
         d.tap_dy[i] = -dy if negate else dy
         d.tap_dx[i] = -dx if negate else dx
     d.act = act
+    if _KTILE:      # bring-up aid: S2E_KTILE="w,h,b" overrides the weight-gradient kernels' pixel tile
+        d.ktile_w, d.ktile_h, d.ktile_b = _KTILE
     return d
 
 
@@ -444,6 +451,88 @@ class TapConvFn(torch.autograd.Function):
 
 def tap_conv(x, cfg, weights, biases=(), sn=None, residual=None):
     return TapConvFn.apply(x, cfg, sn, len(weights), residual, *weights, *biases)
+
+
+_head_wd_cache = {}
+
+
+def _head_dgrad_weight(weight):
+    """[Cin][64] bf16 copy of a (1, Cin, kh, kw) head weight, column t = tap t (taps >= kh*kw zero): the weight of the 1x1
+    convolution G (64 tap channels) -> dx.  The buffer is zero-filled once; each call refreshes the live columns."""
+    ent = _head_wd_cache.get(id(weight))
+    Cin, nt = weight.shape[1], weight.shape[2] * weight.shape[3]
+    if ent is None or ent[0]() is not weight or ent[1].device != weight.device:
+        buf = torch.zeros(Cin, 64, dtype=BF16, device=weight.device)
+        _head_wd_cache[id(weight)] = ent = (_weakref.ref(weight), buf)
+    ent[1][:, :nt].copy_(weight.detach()[0].reshape(Cin, nt))
+    return ent[1]
+
+
+def head_conv_ok(x, cfg, weight, sn=None):
+    """Shapes HeadConvFn takes: one output channel, wide input, stride 1, at most 16 taps, no activation / spectral norm."""
+    return (weight.shape[0] == 1 and cfg.stride == 1 and cfg.kh * cfg.kw <= 16 and weight.shape[1] % 64 == 0
+            and 128 <= weight.shape[1] <= 1024 and x.shape[-1] == weight.shape[1] and cfg.act == L.ACT_NONE
+            and cfg.in_act == L.ACT_NONE and sn is None and _state["force_impl"] is None)
+
+
+class HeadConvFn(torch.autograd.Function):
+    """PatchGAN logit head conv(x, W) + b with W of shape (1, Cin, kh, kw), stride 1 (discriminator.py:38) in tap-channel
+    form: D[q][t] = x[q] . W[t] (the input is read once, CUDA cores, fp32), y[p] = sum_t D[p + tap_t][t] + b.  Backward:
+    G[q][t] = dy[q - tap_t] (64 channels, kh*kw live), dx = G . W and dW = G^T . x as 1x1 convolutions on the tcgen05 kernels."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, weight, bias):
+        x = _c(x)
+        B, Hi, Wi, Cin = x.shape
+        Ho, Wo = conv_out_hw(cfg, Hi, Wi)
+        taps = conv_taps(cfg)
+        wp = packed_weights((weight,), cfg, False)          # [tap][1][Cin] bf16
+        D = torch.empty(B * Hi * Wi, 16, dtype=F32, device=x.device)
+        y = torch.empty(B, Ho, Wo, 1, dtype=BF16, device=x.device)
+        d = _desc(B, Hi, Wi, Cin, Ho, Wo, 1, taps, L.ACT_NONE)
+        st = L.stream()
+        L.call("s2e_head_dots", L.ptr(x), L.ptr(wp), B * Hi * Wi, Cin, len(taps), L.ptr(D), st)
+        L.call("s2e_head_gather", d, L.ptr(D), L.ptr(bias.detach() if bias is not None else None), None, L.ptr(y), st)
+        ctx.cfg, ctx.has_b = cfg, bias is not None
+        ctx.skip_wgrad = _state["skip_wgrad"]
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        cfg = ctx.cfg
+        dy = _c(dy)
+        B, Hi, Wi, Cin = x.shape
+        _, Ho, Wo, _ = dy.shape
+        taps = conv_taps(cfg)
+        st = L.stream()
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[2] and not ctx.skip_wgrad
+        need_b = ctx.has_b and ctx.needs_input_grad[3] and not ctx.skip_wgrad
+        dx = gw = gb = None
+        if need_x or need_w:
+            G = torch.empty(B, Hi, Wi, 64, dtype=BF16, device=dy.device)
+            L.call("s2e_head_scatter", _desc(B, Hi, Wi, Cin, Ho, Wo, 1, taps, L.ACT_NONE), L.ptr(dy), L.ptr(G), st)
+            one = [(0, 0)]
+            flops = 2.0 * B * Ho * Wo * Cin * len(taps)
+        if need_x:
+            wd = _head_dgrad_weight(weight)
+            dx = torch.empty(B, Hi, Wi, Cin, dtype=BF16, device=dy.device)
+            _timed_call("tc", flops, "s2e_tapconv_fwd", _desc(B, Hi, Wi, 64, Hi, Wi, Cin, one, L.ACT_NONE), L.ptr(G), L.ptr(wd), None, None,
+                        L.ptr(dx), L.IMPL_TC, st, tag="dgrad-head B%d %dx%d Cin64 Cout%d T1" % (B, Hi, Wi, Cin))
+        if need_w:
+            dwp = torch.zeros(64, Cin, dtype=F32, device=dy.device)
+            _timed_call("tc", flops, "s2e_tapconv_wgrad", _desc(B, Hi, Wi, Cin, Hi, Wi, 64, one, L.ACT_NONE), L.ptr(x), L.ptr(G), L.ptr(dwp),
+                        L.IMPL_TC, st, tag="wgrad-head B%d %dx%d Cin%d Cout64 T1" % (B, Hi, Wi, Cin))
+            gw = dwp[:len(taps)].t().reshape(weight.shape).contiguous()
+        if need_b:
+            gb = dy.float().sum().reshape(1)
+        return dx, None, gw, gb
+
+
+def head_conv(x, cfg, weight, bias=None):
+    return HeadConvFn.apply(x, cfg, weight, bias)
 
 
 def _sn_scratch_floats(rows, cols):

@@ -124,6 +124,7 @@ SIMT_CASES = [
     (1, 24, 40, 9, 7, 1, 1, 0, 0),       # 1x1 with ragged channel counts
     (2, 16, 32, 13, 11, 4, 2, 2, 0),     # 4x4 s2 p2 mid layer, odd size
     (2, 64, 1, 21, 18, 3, 1, 1, 0),      # conv_img at ngf=64: register-weight single-output-channel kernel
+    (2, 128, 1, 19, 21, 4, 1, 2, 0),     # PatchGAN head shape on the generic thin-output kernels
 ]
 
 
@@ -633,6 +634,45 @@ def test_conv_residual_in_epilogue(S, impl_name, Cout):
     assert rel(nchw(xc.grad), xr.grad) < TOL_ACT and rel(bc.grad, br.grad) < TOL_ACT
 
 
+@pytest.mark.parametrize("case", [(3, 128, 11, 9, 4, 2), (2, 512, 33, 18, 4, 2), (1, 1024, 9, 7, 4, 2), (2, 192, 20, 16, 3, 1),
+                                  (2, 256, 5, 40, 4, 2)])
+def test_head_conv_tap_channel_form(S, case):
+    """PatchGAN logit head (discriminator.py:38) as D[q][t] = x[q] . W[t] + gather (ops.HeadConvFn): forward, data gradient,
+    weight and bias gradient vs torch; the layer module picks this route for a (1, Cin, k, k) weight."""
+    L, ops = S
+    B, Cin, H, W, k, pad = case
+    g = torch.Generator().manual_seed(31)
+    x = bf(torch.randn(B, Cin, H, W, generator=g))
+    w = bf(torch.randn(1, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5)
+    b = torch.randn(1, generator=g) * 0.1
+    xr, wr, br = [t.clone().requires_grad_() for t in (x, w, b)]
+    yr = F.conv2d(xr, wr, br, padding=pad)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    from seg2eye_b200.models.networks.layers import Conv2d
+    conv = Conv2d(Cin, 1, k, stride=1, padding=pad).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(w)
+        conv.bias.copy_(b)
+    xc = nhwc(x).requires_grad_()
+    assert ops.head_conv_ok(xc, conv.cfg, conv.weight)
+    y = conv.forward_nhwc(xc)
+    assert y.grad_fn.name().startswith("HeadConvFn")
+    y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < 5e-3, rel(nchw(y), yr)             # fp32 dot products, one bf16 rounding on the logit
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT, rel(nchw(xc.grad), xr.grad)
+    assert rel(conv.weight.grad, wr.grad) < TOL_ACT, rel(conv.weight.grad, wr.grad)
+    assert rel(conv.bias.grad, br.grad) < TOL_ACT
+    # a second call after a weight update sees the new weight (packed copy and the [Cin][64] data-gradient copy refresh)
+    with torch.no_grad():
+        conv.weight.mul_(-0.5)
+    xc.grad = None
+    y2 = conv.forward_nhwc(xc)
+    y2.backward(nhwc(dy))
+    assert rel(nchw(y2) - b.view(1, 1, 1, 1), -0.5 * (yr.detach() - b.view(1, 1, 1, 1))) < 1e-2
+    assert rel(nchw(xc.grad), -0.5 * xr.grad) < TOL_ACT
+
+
 def test_one_channel_head_on_tensor_cores(S):
     """PatchGAN logit head (512 -> 1, 4x4 s1 p2; discriminator.py:96) with cout_pad: zero-padded output channels on the
     tcgen05 kernels; forward, data gradient, weight and bias gradient vs torch."""
@@ -657,7 +697,7 @@ def test_one_channel_head_on_tensor_cores(S):
     assert rel(nchw(y), yr) < TOL_ACT
     assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
     assert rel(wc.grad, wr.grad) < TOL_ACT and rel(bc.grad, br.grad) < TOL_ACT
-    # the layer picks the padded path by itself
+    # the layer itself takes the tap-channel head route (test_head_conv_tap_channel_form)
     from seg2eye_b200.models.networks.layers import Conv2d
     conv = Conv2d(512, 1, 4, stride=1, padding=2).cuda()
     x2 = bf(torch.randn(2, 512, 6, 5, generator=g))

@@ -17,7 +17,8 @@ def run(B, H, W, Cin, Cout, k, once, n=5):
     x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16).requires_grad_()
     w = (torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).requires_grad_()
     b = torch.randn(Cout, device="cuda").requires_grad_()
-    dy = torch.randn(B, H, W, Cout, device="cuda").to(torch.bfloat16)
+    Ho, Wo = H + 2 * (k // 2) - k + 1, W + 2 * (k // 2) - k + 1
+    dy = torch.randn(B, Ho, Wo, Cout, device="cuda").to(torch.bfloat16)
     cfg = ops.ConvCfg(k, k, 1, k // 2, 0)
     reps = 1 if once else n + 2
     res = {}
