@@ -246,6 +246,7 @@ int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, co
  * (S2 = sum_hw g*xhat, the second accumulator of s2e_instnorm_bwd) is produced here.  coef: B floats scratch. */
 int s2e_sn_in_correction(const double* racc, const float* rstd, const float* inv_sigma, int Bn, int group, int C,
                          float eps, const float* U, const float* V, int K, float* coef, float* dw, void* stream);
+/* y is unused (may be NULL): the sign the activation saw is that of fma(x, rstd, -mean * rstd), which backward recomputes */
 int s2e_instnorm_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, int B, int HW,
                      int C, int act, double* racc, void* dx, void* stream);
 

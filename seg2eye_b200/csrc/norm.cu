@@ -573,63 +573,114 @@ __global__ void __launch_bounds__(NT) instnorm_apply_kernel(const bf16* __restri
       kb[j] = -mean[(size_t)b * C + c + j] * ka[j];
     }
     const long long base = (long long)b * HW;
+    auto emit = [&](long long p, const bf16x8& v) {
+      float f[8], o[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
+      st_stream8(y + p * C + c, pack8(o));
+    };
     long long q = q0 + my_lane;
-    for (; q + lanes < q1; q += 2 * lanes) {
-      const bf16x8 va = ld_stream8(x + (base + q) * C + c), vb = ld_stream8(x + (base + q + lanes) * C + c);
-      float f[8], o[8];
-      unpack8(va, f);
+    for (; q + 3LL * lanes < q1; q += 4LL * lanes) {   // four 16-byte loads in flight per thread
+      bf16x8 v[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
-      st_stream8(y + (base + q) * C + c, pack8(o));
-      unpack8(vb, f);
+      for (int i = 0; i < 4; ++i) v[i] = ld_stream8(x + (base + q + (long long)i * lanes) * C + c);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
-      st_stream8(y + (base + q + lanes) * C + c, pack8(o));
+      for (int i = 0; i < 4; ++i) emit(base + q + (long long)i * lanes, v[i]);
     }
-    for (; q < q1; q += lanes) {
-      float f[8], o[8];
-      unpack8(ld_stream8(x + (base + q) * C + c), f);
+    for (; q < q1; q += lanes) emit(base + q, ld_stream8(x + (base + q) * C + c));
+  }
+}
+
+// Backward, rewritten in round 2e like the SPADE kernels (section 4.2 of DESIGN.md).  The round-1 kernels read y only for
+// the sign of the activation (a third of the reduce pass's bytes) and fetched mean / rstd per ELEMENT through __ldg inside the
+// generic reduction helper (16 extra loads per 16-byte data load).  Now: the sign is that of fmaf(x, rstd, -mean*rstd) --
+// the very expression the forward kernel rounds to y, so the mask is bit-identical -- per-channel constants live in
+// registers, four pixels (eight 16-byte loads) are in flight per thread, and the apply pass uses folded constants:
+//   g = dy * act'(v),  v = x*ka + kb            reduce:  S1 = sum g,  S2 = ka * sum g (x - mu)   ( = sum g * xhat )
+//   dx = rstd (g - m1 - xhat m2) = g*ka + x*kc + kd,   kc = -ka^2 m2,  kd = -ka (m1 + kb m2)
+// Bytes per element: reduce 4 (dy, x), apply 6 (dy, x in, dx out); before 6 and 8.
+template <int ACT>
+__device__ __forceinline__ float in_gate(float d, float v) {
+  if (ACT == S2E_ACT_LRELU) return v > 0.f ? d : 0.2f * d;
+  if (ACT == S2E_ACT_RELU) return v > 0.f ? d : 0.f;
+  return d;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 int HW, int C, double* __restrict__ racc) {
+  extern __shared__ float red[];  // [lanes][ncg][8]
+  const int b = blockIdx.y;
+  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
+  const long long base = (long long)b * HW;
+  const long long q0 = (long long)blockIdx.x * chunk;
+  const long long q1 = min((long long)HW, q0 + chunk);
+  const int cg = C >> 3;
+  const int tid = threadIdx.x;
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = tid % ncg, my_lane = tid / ncg;
+    const int c = (cg0 + my_cg) * 8;
+    float ka[8], kb[8], mu[8], a0[8], a1[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
-      st_stream8(y + (base + q) * C + c, pack8(o));
+    for (int j = 0; j < 8; ++j) {
+      ka[j] = rstd[(size_t)b * C + c + j];
+      mu[j] = mean[(size_t)b * C + c + j];
+      kb[j] = -mu[j] * ka[j];
+      a0[j] = a1[j] = 0.f;
+    }
+    auto eat = [&](const bf16x8& vd, const bf16x8& vx) {
+      float df[8], xf[8];
+      unpack8(vd, df);
+      unpack8(vx, xf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = in_gate<ACT>(df[j], fmaf(xf[j], ka[j], kb[j]));
+        a0[j] += g;
+        a1[j] = fmaf(g, xf[j] - mu[j], a1[j]);
+      }
+    };
+    if (my_lane < lanes) {
+      long long q = q0 + my_lane;
+      for (; q + 3LL * lanes < q1; q += 4LL * lanes) {
+        bf16x8 vd[4], vx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vd[i] = ld_stream8(dy + (base + q + (long long)i * lanes) * C + c);
+          vx[i] = ld_stream8(x + (base + q + (long long)i * lanes) * C + c);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) eat(vd[i], vx[i]);
+      }
+      for (; q < q1; q += lanes) eat(ld_stream8(dy + (base + q) * C + c), ld_stream8(x + (base + q) * C + c));
+    }
+    // combine the pixel lanes through shared memory, one atomic per channel and block
+#pragma unroll 1
+    for (int a = 0; a < 2; ++a) {
+      __syncthreads();
+      if (my_lane < lanes) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(my_lane * ncg + my_cg) * 8 + j] = a == 0 ? a0[j] : a1[j];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < ncg * 8; idx += NT) {
+        float sum = 0.f;
+        for (int l = 0; l < lanes; ++l) sum += red[l * ncg * 8 + idx];
+        const int ch = cg0 * 8 + idx;
+        if (a == 1) sum *= rstd[(size_t)b * C + ch];
+        atomicAdd(racc + (size_t)b * 2 * C + (size_t)a * C + ch, (double)sum);
+      }
     }
   }
 }
 
-// reduce: S1 = sum g, S2 = sum g*xh  (g = dy * act'(y))
-__global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
-                                                                 const bf16* __restrict__ x, const float* __restrict__ mean,
-                                                                 const float* __restrict__ rstd, int HW, int C, int act,
-                                                                 double* __restrict__ racc) {
-  const int b = blockIdx.y;
-  const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
-  const long long b0 = (long long)b * HW + (long long)blockIdx.x * chunk;
-  const long long b1 = min((long long)(b + 1) * HW, b0 + chunk);
-  auto one = [&](long long p, int c, float(*a)[8]) {
-    float df[8], yf[8], xf[8];
-    unpack8(ld_stream8(dy + p * C + c), df);
-    unpack8(ld_stream8(x + p * C + c), xf);
-    if (act != S2E_ACT_NONE) unpack8(ld_stream8(y + p * C + c), yf);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float g = df[j];
-      if (act == S2E_ACT_LRELU) g *= (yf[j] > 0.f ? 1.f : 0.2f);
-      const float xh = (xf[j] - __ldg(mean + b * C + c + j)) * __ldg(rstd + b * C + c + j);
-      a[0][j] += g;
-      a[1][j] = fmaf(g, xh, a[1][j]);
-    }
-  };
-  auto four = [&](long long p, long long st, int c, float(*a)[8]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) one(p + i * st, c, a);
-  };
-  block_channel_reduce<2>(C, b0, b1, racc + (size_t)b * 2 * C, one, four);
-}
-
-__global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
-                                                                const bf16* __restrict__ x, const float* __restrict__ mean,
-                                                                const float* __restrict__ rstd, const double* __restrict__ racc,
-                                                                int HW, int C, int act, bf16* __restrict__ dx) {
+template <int ACT>
+__global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                const double* __restrict__ racc, int HW, int C, bf16* __restrict__ dx) {
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long q0 = (long long)blockIdx.x * chunk;
@@ -642,31 +693,40 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const bf16* __re
     const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
     if (my_lane >= lanes) continue;
     const int c = (cg0 + my_cg) * 8;
-    float rsd[8], mu[8], m1[8], m2[8];
+    float ka[8], kb[8], kc[8], kd[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      rsd[j] = rstd[(size_t)b * C + c + j];
-      mu[j] = mean[(size_t)b * C + c + j];
-      m1[j] = (float)racc[(size_t)b * 2 * C + c + j] * inv;
-      m2[j] = (float)racc[(size_t)b * 2 * C + C + c + j] * inv;
+      ka[j] = rstd[(size_t)b * C + c + j];
+      kb[j] = -mean[(size_t)b * C + c + j] * ka[j];
+      const float m1 = (float)racc[(size_t)b * 2 * C + c + j] * inv;
+      const float m2 = (float)racc[(size_t)b * 2 * C + C + c + j] * inv;
+      kc[j] = -ka[j] * ka[j] * m2;
+      kd[j] = -ka[j] * fmaf(kb[j], m2, m1);
     }
     const long long base = (long long)b * HW;
-    for (long long q = q0 + my_lane; q < q1; q += lanes) {
-      const long long p = base + q;
-      float df[8], yf[8], xf[8], o[8];
-      const bf16x8 vd = ld_stream8(dy + p * C + c), vx = ld_stream8(x + p * C + c);
-      if (act != S2E_ACT_NONE) unpack8(ld_stream8(y + p * C + c), yf);
+    auto emit = [&](long long p, const bf16x8& vd, const bf16x8& vx) {
+      float df[8], xf[8], o[8];
       unpack8(vd, df);
       unpack8(vx, xf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float g = df[j];
-        if (act == S2E_ACT_LRELU) g *= (yf[j] > 0.f ? 1.f : 0.2f);
-        const float xh = (xf[j] - mu[j]) * rsd[j];
-        o[j] = rsd[j] * (g - m1[j] - xh * m2[j]);
+        const float g = in_gate<ACT>(df[j], fmaf(xf[j], ka[j], kb[j]));
+        o[j] = fmaf(g, ka[j], fmaf(xf[j], kc[j], kd[j]));
       }
       st_stream8(dx + p * C + c, pack8(o));
+    };
+    long long q = q0 + my_lane;
+    for (; q + 3LL * lanes < q1; q += 4LL * lanes) {
+      bf16x8 vd[4], vx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        vd[i] = ld_stream8(dy + (base + q + (long long)i * lanes) * C + c);
+        vx[i] = ld_stream8(x + (base + q + (long long)i * lanes) * C + c);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) emit(base + q + (long long)i * lanes, vd[i], vx[i]);
     }
+    for (; q < q1; q += lanes) emit(base + q, ld_stream8(dy + (base + q) * C + c), ld_stream8(x + (base + q) * C + c));
   }
 }
 
@@ -863,13 +923,17 @@ int s2e_instnorm_bwd(const void* dy, const void* y, const void* x, const float* 
   S2E_REQUIRE(C % 8 == 0, "instnorm_bwd needs C %% 8 == 0 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
   S2E_CHECK_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * B * 2 * C, st));
-  dim3 grid(red_chunks(HW, B), B);
-  instnorm_bwd_reduce_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)x, mean, rstd, HW, C,
-                                                            act, racc);
-  S2E_LAUNCH_CHECK();
-  dim3 grid2(ew_chunks(HW, B, C), B);
-  instnorm_bwd_apply_kernel<<<grid2, NT, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)x, mean, rstd, racc, HW, C, act,
-                                                  (bf16*)dx);
+  dim3 grid(red_chunks(HW, B), B), grid2(ew_chunks(HW, B, C), B);
+  const bf16 *d_ = (const bf16*)dy, *x_ = (const bf16*)x;
+  (void)y;   // the activation's sign is recomputed from x (same expression as the forward pass): y is not read any more
+#define S2E_IN_BWD(ACT_)                                                                                             \
+  instnorm_bwd_reduce_kernel<ACT_><<<grid, NT, red_smem(C), st>>>(d_, x_, mean, rstd, HW, C, racc);                  \
+  S2E_LAUNCH_CHECK();                                                                                                \
+  instnorm_bwd_apply_kernel<ACT_><<<grid2, NT, 0, st>>>(d_, x_, mean, rstd, racc, HW, C, (bf16*)dx);
+  if (act == S2E_ACT_LRELU) { S2E_IN_BWD(S2E_ACT_LRELU) }
+  else if (act == S2E_ACT_RELU) { S2E_IN_BWD(S2E_ACT_RELU) }
+  else { S2E_IN_BWD(S2E_ACT_NONE) }
+#undef S2E_IN_BWD
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

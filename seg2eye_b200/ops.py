@@ -902,18 +902,18 @@ class InstNormFn(torch.autograd.Function):
         ctx.act, ctx.group = act, group
         ctx.skip_wgrad = _state["skip_wgrad"]    # captured at forward time, like TapConvFn
         ctx.has_sn = sn_inv is not None
-        ctx.save_for_backward(x, y, mean, rstd, sn_inv, sn_U, sn_V, weight_orig)
+        ctx.save_for_backward(x, mean, rstd, sn_inv, sn_U, sn_V, weight_orig)   # not y: backward takes the activation's sign from x
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, rstd, sn_inv, sn_U, sn_V, weight_orig = ctx.saved_tensors
+        x, mean, rstd, sn_inv, sn_U, sn_V, weight_orig = ctx.saved_tensors
         dy = _c(dy)
         B, H, W, Cc = x.shape
         racc = torch.empty(B * 2 * Cc, dtype=torch.float64, device=x.device)
         dx = torch.empty_like(x)
         st = L.stream()
-        L.call("s2e_instnorm_bwd", L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(mean), L.ptr(rstd), B, H * W, Cc, ctx.act,
+        L.call("s2e_instnorm_bwd", L.ptr(dy), None, L.ptr(x), L.ptr(mean), L.ptr(rstd), B, H * W, Cc, ctx.act,
                L.ptr(racc), L.ptr(dx), st)
         gw = None
         if ctx.has_sn and weight_orig is not None and ctx.needs_input_grad[6] and not ctx.skip_wgrad:

@@ -358,6 +358,25 @@ def test_instance_norm_fwd_bwd(S, act, C):
     assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
 
 
+@pytest.mark.parametrize("act,C,H,W", [(1, 128, 161, 97), (1, 512, 42, 26), (2, 256, 33, 40), (0, 2048, 8, 8), (1, 4096, 4, 4)])
+def test_instance_norm_streaming_paths(S, act, C, H, W):
+    """The discriminator's / encoder's shapes (discriminator.py:34-37, encoder.py:23-38): several pixels in flight per thread,
+    more channel groups than threads, activation sign recomputed from x in the backward pass (large-mean channels included)."""
+    L, ops = S
+    g = torch.Generator().manual_seed(6)
+    x = bf(torch.randn(2, C, H, W, generator=g) * torch.rand(1, C, 1, 1, generator=g) * 3 + torch.randn(1, C, 1, 1, generator=g) * 4)
+    xr = x.clone().requires_grad_()
+    yr = F.instance_norm(xr, eps=1e-5)
+    yr = F.leaky_relu(yr, 0.2) if act == 1 else (F.relu(yr) if act == 2 else yr)
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xc = nhwc(x).requires_grad_()
+    y = ops.InstNormFn.apply(xc, act)
+    y.backward(nhwc(dy))
+    assert rel(nchw(y), yr) < 5e-3
+    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT, rel(nchw(xc.grad), xr.grad)
+
+
 # ------------------------------------------------------------------------------------------ resampling / elementwise
 def test_upsample_avgpool_bilinear_add_act(S):
     L, ops = S
