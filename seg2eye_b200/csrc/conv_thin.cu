@@ -253,7 +253,38 @@ __global__ void __launch_bounds__(256) thin_out1_fwd_kernel(const bf16* __restri
 // shared memory.  Phase 2: one thread per output pixel adds its nine neighbours' entries
 // y[p] = sum_t d[p + tap_t][t].
 constexpr int T1_TW = 32, T1_TH = 8, T1_HW = T1_TW + 2, T1_NHP = (T1_TH + 2) * T1_HW;
-constexpr int T1_SMEM = T1_NHP * 128 + T1_NHP * 9 * 4;
+constexpr int T1_MT = (T1_NHP + 15) / 16;      // 16-pixel row blocks of the halo tile (the last one is partly padding)
+constexpr int T1_XP = 72;                      // pixel pitch of the staged tile in bf16: 144 bytes, so that the 16-byte fragment
+                                               // loads of eight consecutive pixels fall into different banks
+constexpr int T1_SMEM = T1_MT * 16 * T1_XP * 2 + T1_NHP * 9 * 4;
+
+// ---- warp-level bf16 MMA (mma.sync m16n8k16, fp32 accumulate) for the single-image-channel layers.  These layers are GEMMs
+// with N (or M, or K) = 9 taps: far too thin for a 128-row tcgen05 tile, and on the CUDA cores they were bound by instruction
+// issue (ncu, round 2e: 352 M / 415 M / 439 M warp instructions for forward / data gradient / weight gradient of conv_img at
+// B16 640x384, 0.44 / 0.59 / 0.70 ms against 0.1 - 0.2 ms of DRAM time).  One mma.sync replaces 128 FMAs + their unpacking.
+// Fragment layout (PTX ISA, m16n8k16 .bf16): g = lane / 4, t = lane % 4;
+//   A (16 x 16, row): a0 = (row g, k 2t..2t+1), a1 = (row g+8, same k), a2 = (row g, k 2t+8..2t+9), a3 = (row g+8, k 2t+8..)
+//   B (16 x 8, col):  b0 = (k 2t..2t+1, col g), b1 = (k 2t+8..2t+9, col g);   C: c0,c1 = (row g, cols 2t, 2t+1), c2,c3 = (row g+8, ..)
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// max(v, 0) / min(v, 0) on a bf16 pair: leaky_relu(x) . w = max(x,0) . w + 0.2 * (min(x,0) . w) -- both operands exact in bf16,
+// the factor 0.2 is applied to the fp32 accumulator (rounding 0.2 * x to bf16 first would cost 2^-9 on every negative input)
+__device__ __forceinline__ uint32_t bf2_pos(uint32_t v) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v), __float2bfloat162_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_neg(uint32_t v) {
+  const __nv_bfloat162 r = __hmin2(*reinterpret_cast<const __nv_bfloat162*>(&v), __float2bfloat162_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t pack_bf16_bits(bf16 lo, bf16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+__device__ __forceinline__ float in_act_slope(int in_act) { return in_act == S2E_ACT_LRELU ? 0.2f : 0.f; }
+
 __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                                 const float* __restrict__ bias, const float* __restrict__ scale,
                                                                 bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h,
@@ -263,8 +294,8 @@ __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __re
   // result is written as fp32 (no bf16 rounding of the pre-activation); with img_target the block also adds its partial
   // sums of |fake - target| and (fake - target)^2 to img_sums[0..1] (the L1 / L2 image losses, pix2pix_model.py:197-208)
   extern __shared__ __align__(16) uint8_t t1_smem[];
-  bf16* xs = reinterpret_cast<bf16*>(t1_smem);                               // [T1_NHP][64]
-  float* d = reinterpret_cast<float*>(t1_smem + T1_NHP * 128);               // [T1_NHP][9]
+  bf16* xs = reinterpret_cast<bf16*>(t1_smem);                               // [T1_MT * 16][T1_XP]  (64 channels + 16 bytes of padding)
+  float* d = reinterpret_cast<float*>(t1_smem + T1_MT * 16 * T1_XP * 2);     // [T1_NHP][9]
   int tile = blockIdx.x;
   const int tw_idx = tile % tiles_w;
   tile /= tiles_w;
@@ -278,43 +309,65 @@ __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __re
     const int hi = h0 + hh, wi = w0 + ww;
     const bool ok = hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi;
     const bf16* src = ok ? xb + ((long long)hi * g.Wi + wi) * 64 + ch * 8 : xb;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + hp * 64 + ch * 8);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + hp * T1_XP + ch * 8);
     const int nbytes = ok ? 16 : 0;   // src-size 0 => the 16 destination bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  const int sub = threadIdx.x & 7;
-  float wreg[9][8];   // this lane's 8-channel slice of every tap's weights (loaded while the tile is in flight)
+  // Phase 1 as a GEMM on mma.sync: d[pixel][tap] = act(x[pixel]) . W[tap] with M = 16 halo pixels per row block, N = 16 taps
+  // (two 8-wide halves, nine live), K = 64 channels (four steps).  Lane (g, t) reads the 32 bytes [16t, 16t+16) of pixels g and
+  // g + 8 as its A fragments: k index 2t+e of step s is physical channel 16t + 4s + e, k index 8+2t+e is channel 16t + 4s + 2 + e
+  // (any bijection works for a dot product, the B fragments below use the same one).
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fg = lane >> 2, ft = lane & 3;
+  uint32_t wb[2][4][2];   // [tap half][k step][b0 | b1], loaded while the tile is in flight
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (t < g.ntaps) unpack8(*reinterpret_cast<const bf16x8*>(wp + (long long)t * 64 + sub * 8), f);
+  for (int h = 0; h < 2; ++h) {
+    const int tap = h * 8 + fg;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wreg[t][j] = f[j];
+    for (int ks = 0; ks < 4; ++ks) {
+      const bf16* wsrc = wp + (long long)tap * 64 + 16 * ft + 4 * ks;
+      wb[h][ks][0] = tap < g.ntaps ? *reinterpret_cast<const uint32_t*>(wsrc) : 0u;
+      wb[h][ks][1] = tap < g.ntaps ? *reinterpret_cast<const uint32_t*>(wsrc + 2) : 0u;
+    }
   }
+  const float nslope = in_act_slope(g.in_act);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  for (int hp = threadIdx.x >> 3; hp < T1_NHP; hp += 32) {
-    float xf[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(xs + hp * 64 + sub * 8), xf);
-    if (g.in_act != S2E_ACT_NONE) {
+  for (int mt = warp; mt < T1_MT; mt += 8) {
+    const int rowA = mt * 16 + fg, rowB = rowA + 8;
+    const uint4 xa0 = *reinterpret_cast<const uint4*>(xs + rowA * T1_XP + 16 * ft), xa1 = *reinterpret_cast<const uint4*>(xs + rowA * T1_XP + 16 * ft + 8);
+    const uint4 xb0 = *reinterpret_cast<const uint4*>(xs + rowB * T1_XP + 16 * ft), xb1 = *reinterpret_cast<const uint4*>(xs + rowB * T1_XP + 16 * ft + 8);
+    const uint32_t wa[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
+    const uint32_t wbw[8] = {xb0.x, xb0.y, xb0.z, xb0.w, xb1.x, xb1.y, xb1.z, xb1.w};
+    float accp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accn[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xf[j] = act_apply(xf[j], g.in_act);
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t a0 = wa[2 * ks], a2 = wa[2 * ks + 1], a1 = wbw[2 * ks], a3 = wbw[2 * ks + 1];
+      if (g.in_act == S2E_ACT_NONE) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) mma16816(accp[h], a0, a1, a2, a3, wb[h][ks][0], wb[h][ks][1]);
+      } else {
+        const uint32_t p0 = bf2_pos(a0), p1 = bf2_pos(a1), p2 = bf2_pos(a2), p3 = bf2_pos(a3);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) mma16816(accp[h], p0, p1, p2, p3, wb[h][ks][0], wb[h][ks][1]);
+        if (g.in_act == S2E_ACT_LRELU) {
+          const uint32_t n0 = bf2_neg(a0), n1 = bf2_neg(a1), n2 = bf2_neg(a2), n3 = bf2_neg(a3);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) mma16816(accn[h], n0, n1, n2, n3, wb[h][ks][0], wb[h][ks][1]);
+        }
+      }
     }
-    float part[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      float a = xf[0] * wreg[t][0];
-#pragma unroll
-      for (int j = 1; j < 8; ++j) a = fmaf(xf[j], wreg[t][j], a);
-      a += __shfl_xor_sync(0xffffffffu, a, 1);
-      a += __shfl_xor_sync(0xffffffffu, a, 2);
-      a += __shfl_xor_sync(0xffffffffu, a, 4);
-      part[t] = a;
+    // c0, c1 = (pixel rowA, taps 2t, 2t+1), c2, c3 = (pixel rowB, same taps); second half: tap 8 sits in column 0 (t == 0)
+    if (rowA < T1_NHP) {
+      d[rowA * 9 + 2 * ft] = fmaf(nslope, accn[0][0], accp[0][0]);
+      d[rowA * 9 + 2 * ft + 1] = fmaf(nslope, accn[0][1], accp[0][1]);
+      if (ft == 0) d[rowA * 9 + 8] = fmaf(nslope, accn[1][0], accp[1][0]);
     }
-    if (sub == 0) {
-#pragma unroll
-      for (int t = 0; t < 9; ++t) d[hp * 9 + t] = part[t];
+    if (rowB < T1_NHP) {
+      d[rowB * 9 + 2 * ft] = fmaf(nslope, accn[0][2], accp[0][2]);
+      d[rowB * 9 + 2 * ft + 1] = fmaf(nslope, accn[0][3], accp[0][3]);
+      if (ft == 0) d[rowB * 9 + 8] = fmaf(nslope, accn[1][2], accp[1][2]);
     }
   }
   __syncthreads();
@@ -356,6 +409,189 @@ __global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __re
       atomicAdd(img_sums + threadIdx.x, t);
     }
   }
+}
+
+// ---- conv_img's data gradient (generator.py:97-99 backward): a 1 -> 64 channel tap convolution,
+//   y[q][c] = m(q, c) * scale * sum_t x1[q + tap_t] * W[t][c],   m = 1 or mask_slope where the mask tensor is <= 0,
+// as one mma.sync k-step per 16 pixels: A[pixel][tap] is gathered from a staged (TH+2) x (TW+2) tile of the one-channel
+// input, B[tap][c] are the weights, and the logical column (n-tile j, col 2t+e) is physical channel 16t + 2j + e, so that a
+// lane ends up with 16 CONTIGUOUS channels of pixels g and g + 8 (two 16-byte stores each, the mask read the same way).
+constexpr int IG_TW = 32, IG_TH = 8, IG_PW = IG_TW + 2;
+__global__ void __launch_bounds__(256) img_dgrad_mma_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ wp,
+                                                            const float* __restrict__ bias, const float* __restrict__ scale,
+                                                            bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h,
+                                                            const bf16* __restrict__ mask, float mask_slope) {
+  __shared__ bf16 xt[(IG_TH + 2) * IG_PW];
+  int tile = blockIdx.x;
+  const int tw_idx = tile % tiles_w;
+  tile /= tiles_w;
+  const int th_idx = tile % tiles_h;
+  const int b = tile / tiles_h;
+  const int h0 = th_idx * IG_TH, w0 = tw_idx * IG_TW;
+  const bf16* xb = x1 + (long long)b * g.Hi * g.Wi;
+  for (int i = threadIdx.x; i < (IG_TH + 2) * IG_PW; i += 256) {
+    const int r = i / IG_PW, c = i - r * IG_PW;
+    const int hi = h0 + r - 1, wi = w0 + c - 1;
+    xt[i] = (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) ? xb[(long long)hi * g.Wi + wi] : __float2bfloat16(0.f);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fg = lane >> 2, ft = lane & 3;
+  // B fragments: b0 = (taps 2t, 2t+1; column g), b1 = (taps 2t+8, 2t+9; column g); column g of n-tile j = channel 16(g/2) + 2j + (g&1)
+  uint32_t wb[8][2];
+  int off[3];   // staged-tile offsets of taps 2t, 2t+1 and 8 relative to the pixel itself
+  {
+    const int t0 = 2 * ft, t1 = 2 * ft + 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = 16 * (fg >> 1) + 2 * j + (fg & 1);
+      const bf16 z = __float2bfloat16(0.f);
+      wb[j][0] = pack_bf16_bits(t0 < g.ntaps ? wp[t0 * 64 + ch] : z, t1 < g.ntaps ? wp[t1 * 64 + ch] : z);
+      wb[j][1] = (ft == 0 && 8 < g.ntaps) ? pack_bf16_bits(wp[8 * 64 + ch], z) : 0u;
+    }
+    off[0] = t0 < g.ntaps ? g.dy[t0] * IG_PW + g.dx[t0] : 0;
+    off[1] = t1 < g.ntaps ? g.dy[t1] * IG_PW + g.dx[t1] : 0;
+    off[2] = 8 < g.ntaps ? g.dy[8] * IG_PW + g.dx[8] : 0;
+  }
+  const float sc = scale ? __ldg(scale) : 1.f;
+  __syncthreads();
+  // 16 row blocks of 16 pixels (tile row r = mt / 2, columns (mt & 1) * 16 ..): two per warp
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int mt = warp * 2 + it;
+    const int r = mt >> 1, c0 = (mt & 1) * 16;
+    const int pA = (r + 1) * IG_PW + c0 + fg + 1, pB = pA + 8;   // pixels g and g + 8 of the block, in the staged tile
+    const uint32_t a0 = pack_bf16_bits(xt[pA + off[0]], xt[pA + off[1]]);
+    const uint32_t a1 = pack_bf16_bits(xt[pB + off[0]], xt[pB + off[1]]);
+    const uint32_t a2 = ft == 0 ? pack_bf16_bits(xt[pA + off[2]], __float2bfloat16(0.f)) : 0u;
+    const uint32_t a3 = ft == 0 ? pack_bf16_bits(xt[pB + off[2]], __float2bfloat16(0.f)) : 0u;
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      mma16816(acc[j], a0, a1, a2, a3, wb[j][0], wb[j][1]);
+    }
+    const int ho = h0 + r;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {   // pixel g (c0, c1 of every n-tile), then pixel g + 8 (c2, c3)
+      const int wo = w0 + c0 + fg + 8 * half;
+      if (ho >= g.Ho || wo >= g.Wo) continue;
+      const long long pix = ((long long)b * g.Ho + ho) * g.Wo + wo;
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[2 * j] = acc[j][2 * half] * sc;
+        o[2 * j + 1] = acc[j][2 * half + 1] * sc;
+      }
+      if (bias) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] += __ldg(bias + 16 * ft + e);
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] = act_apply(o[e], g.act);
+      if (mask) {
+        float mf[16];
+        unpack8(ld_stream8(mask + pix * 64 + 16 * ft), mf);
+        unpack8(ld_stream8(mask + pix * 64 + 16 * ft + 8), mf + 8);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] *= (mf[e] > 0.f ? 1.f : mask_slope);
+      }
+      st_stream8(y + pix * 64 + 16 * ft, pack8(o));
+      st_stream8(y + pix * 64 + 16 * ft + 8, pack8(o + 8));
+    }
+  }
+}
+
+// ---- conv_img's weight gradient: dW[t][c] += sum_q act(x[q][c]) * dy1[q - tap_t]  (one output channel, 64 input channels) with
+// M = 16 taps (nine live), N = 64 channels, K = pixels: per 16 consecutive pixels of a row one k-step.  A^T is gathered from a
+// staged (TH+2) x (TW+2) tile of the one-channel gradient; for B a lane reads the 16 bytes [8g, 8g+8) of pixels 2t, 2t+1, 2t+8,
+// 2t+9 (column g of n-tile j = channel 8g + j) and pairs the two pixels of a k pair with byte permutes.  Persistent blocks keep
+// the 9 x 64 result in registers over all their tiles and reduce it once (shared-memory atomics, then one global atomic per value).
+constexpr int IW_TW = 128, IW_TH = 8, IW_PW = IW_TW + 2;
+__global__ void __launch_bounds__(256) img_wgrad_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy1,
+                                                            float* __restrict__ dwp, const ThinGeom g, int tiles_w, int tiles_h,
+                                                            int num_tiles) {
+  __shared__ bf16 dt[(IW_TH + 2) * IW_PW];
+  __shared__ float red[9 * 64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fg = lane >> 2, ft = lane & 3;
+  // staged-tile offsets: A^T[tap][pixel q] = dy1[q - tap]
+  const int offg = fg < g.ntaps ? -(g.dy[fg] * IW_PW + g.dx[fg]) : 0;
+  const int off8 = 8 < g.ntaps ? -(g.dy[8] * IW_PW + g.dx[8]) : 0;
+  const bool live_g = fg < g.ntaps, live_8 = fg == 0 && 8 < g.ntaps;
+  float accp[8][4], accn[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) accp[j][e] = accn[j][e] = 0.f;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int tt = tile;
+    const int tw_idx = tt % tiles_w;
+    tt /= tiles_w;
+    const int th_idx = tt % tiles_h;
+    const int b = tt / tiles_h;
+    const int h0 = th_idx * IW_TH, w0 = tw_idx * IW_TW;
+    const bf16* db = dy1 + (long long)b * g.Ho * g.Wo;
+    __syncthreads();   // the previous tile's fragments have been read
+    for (int i = threadIdx.x; i < (IW_TH + 2) * IW_PW; i += 256) {
+      const int r = i / IW_PW, c = i - r * IW_PW;
+      const int ho = h0 + r - 1, wo = w0 + c - 1;
+      dt[i] = (ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo) ? db[(long long)ho * g.Wo + wo] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    const int hi = h0 + warp;            // one tile row per warp
+    if (hi >= g.Hi) continue;
+    const bf16* xrow = x + (((long long)b * g.Hi + hi) * g.Wi) * 64 + 8 * fg;
+#pragma unroll 2
+    for (int kb = 0; kb < IW_TW / 16; ++kb) {
+      const int c0 = kb * 16;
+      if (w0 + c0 >= g.Wi) break;   // warp-uniform
+      // B: pixels 2t, 2t+1, 2t+8, 2t+9 of this block, channels [8g, 8g+8)
+      uint4 xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int wi = w0 + c0 + 2 * ft + (i & 1) + 8 * (i >> 1);
+        xv[i] = wi < g.Wi ? __ldg(reinterpret_cast<const uint4*>(xrow + (long long)wi * 64)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      // A^T: (tap g | tap 8; pixels 2t, 2t+1 | 2t+8, 2t+9)
+      const int pq = (warp + 1) * IW_PW + c0 + 2 * ft + 1;
+      const bf16 z = __float2bfloat16(0.f);
+      const uint32_t a0 = live_g ? pack_bf16_bits(dt[pq + offg], dt[pq + 1 + offg]) : 0u;
+      const uint32_t a2 = live_g ? pack_bf16_bits(dt[pq + 8 + offg], dt[pq + 9 + offg]) : 0u;
+      const uint32_t a1 = live_8 ? pack_bf16_bits(dt[pq + off8], dt[pq + 1 + off8]) : 0u;
+      const uint32_t a3 = live_8 ? pack_bf16_bits(dt[pq + 8 + off8], dt[pq + 9 + off8]) : 0u;
+      (void)z;
+      const uint32_t w[4][4] = {{xv[0].x, xv[0].y, xv[0].z, xv[0].w}, {xv[1].x, xv[1].y, xv[1].z, xv[1].w},
+                                {xv[2].x, xv[2].y, xv[2].z, xv[2].w}, {xv[3].x, xv[3].y, xv[3].z, xv[3].w}};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;   // channel 8g + j of two pixels -> one k pair (low half = first pixel)
+        const uint32_t b0 = __byte_perm(w[0][j >> 1], w[1][j >> 1], sel), b1 = __byte_perm(w[2][j >> 1], w[3][j >> 1], sel);
+        if (g.in_act == S2E_ACT_NONE) {
+          mma16816(accp[j], a0, a1, a2, a3, b0, b1);
+        } else {
+          mma16816(accp[j], a0, a1, a2, a3, bf2_pos(b0), bf2_pos(b1));
+          if (g.in_act == S2E_ACT_LRELU) mma16816(accn[j], a0, a1, a2, a3, bf2_neg(b0), bf2_neg(b1));
+        }
+      }
+    }
+  }
+  // c0, c1 = (tap g, columns 2t, 2t+1 of n-tile j = channels 8(2t) + j, 8(2t+1) + j); c2, c3 = the same for tap g + 8
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const float nslope = in_act_slope(g.in_act);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (live_g) {
+      atomicAdd(&red[fg * 64 + 16 * ft + j], fmaf(nslope, accn[j][0], accp[j][0]));
+      atomicAdd(&red[fg * 64 + 16 * ft + 8 + j], fmaf(nslope, accn[j][1], accp[j][1]));
+    }
+    if (live_8) {
+      atomicAdd(&red[8 * 64 + 16 * ft + j], fmaf(nslope, accn[j][2], accp[j][2]));
+      atomicAdd(&red[8 * 64 + 16 * ft + 8 + j], fmaf(nslope, accn[j][3], accp[j][3]));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.ntaps * 64; i += 256) atomicAdd(dwp + i, red[i]);
 }
 
 // PatchGAN logit head (discriminator.py:38: Cin = 8*ndf -> 1, 4x4, stride 1, pad 2; K = 8192) in "tap-channel" form:
@@ -619,6 +855,15 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
   const bool tile_ok = d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9 && d->Hi == d->Ho && d->Wi == d->Wo;
   if ((d->in_act != S2E_ACT_NONE || d->img_out) && !tile_ok) return 0;
   if (mask && !(d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8)) return 0;
+  bool halo1 = d->ntaps <= 9 && d->Hi == d->Ho && d->Wi == d->Wo;
+  for (int t = 0; t < d->ntaps && halo1; ++t) halo1 = d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
+  if (d->Cin == 1 && d->Cout == 64 && halo1 && !s2e_debug_get(7)) {   // conv_img's data gradient: one mma.sync k-step per 16 pixels
+    const int tiles_w = ceil_div(d->Wo, IG_TW), tiles_h = ceil_div(d->Ho, IG_TH);
+    img_dgrad_mma_kernel<<<(unsigned)(d->B * tiles_h * tiles_w), 256, 0, stream>>>((const bf16*)x, (const bf16*)wp, bias, scale, (bf16*)y, g,
+                                                                              tiles_w, tiles_h, mask, d->mask_slope);
+    S2E_LAUNCH_CHECK();
+    return 1;
+  }
   if (d->Cin <= 32 && d->Cout % 8 == 0 && d->Cout >= 8) {
     const int cot = d->Cout < K1_CO_TILE ? d->Cout : K1_CO_TILE;
     if (d->Cout % K1_CO_TILE != 0 && d->Cout > K1_CO_TILE) return 0;
@@ -646,8 +891,6 @@ int s2e_thin_fwd(const s2e_conv_t* d, const void* x, const void* wp, const float
     return 1;
   }
   if (d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9 && d->Hi == d->Ho && d->Wi == d->Wo) {
-    bool halo1 = true;
-    for (int t = 0; t < d->ntaps; ++t) halo1 = halo1 && d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
     if (halo1) {
       const int tiles_w = ceil_div(d->Wo, T1_TW), tiles_h = ceil_div(d->Ho, T1_TH);
       static int attr1 = 0;
@@ -709,6 +952,19 @@ int s2e_thin_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float* dw
   else
     return 0;
   if (d->ntaps > 16) return 0;
+  if (!thin_x && d->Cout == 1 && d->Cin == 64 && d->ntaps <= 9 && d->Hi == d->Ho && d->Wi == d->Wo && !s2e_debug_get(7)) {
+    bool halo1 = true;
+    for (int t = 0; t < d->ntaps; ++t) halo1 = halo1 && d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
+    if (halo1) {   // conv_img's weight gradient on mma.sync
+      const int tiles_w = ceil_div(d->Wi, IW_TW), tiles_h = ceil_div(d->Hi, IW_TH);
+      const int num_tiles = d->B * tiles_h * tiles_w;
+      if (num_tiles == 0) return 1;
+      const int grid = num_tiles < 2 * s2e_num_sms() ? num_tiles : 2 * s2e_num_sms();
+      img_wgrad_mma_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)dy, dwp, g, tiles_w, tiles_h, num_tiles);
+      S2E_LAUNCH_CHECK();
+      return 1;
+    }
+  }
   const bf16* A = thin_x ? (const bf16*)dy : (const bf16*)x;
   const bf16* S = thin_x ? (const bf16*)x : (const bf16*)dy;
   const int HA = thin_x ? d->Ho : d->Hi, WA = thin_x ? d->Wo : d->Wi, Cw = thin_x ? d->Cout : d->Cin;

@@ -123,7 +123,8 @@ SIMT_CASES = [
     (2, 1, 16, 32, 32, 3, 2, 1, 0),      # E layer0 (3x3 s2 p1, Cin = 1)
     (1, 24, 40, 9, 7, 1, 1, 0, 0),       # 1x1 with ragged channel counts
     (2, 16, 32, 13, 11, 4, 2, 2, 0),     # 4x4 s2 p2 mid layer, odd size
-    (2, 64, 1, 21, 18, 3, 1, 1, 0),      # conv_img at ngf=64: register-weight single-output-channel kernel
+    (2, 64, 1, 21, 18, 3, 1, 1, 0),      # conv_img at ngf=64 (mma.sync tile kernel; data / weight gradient on mma.sync too)
+    (1, 64, 1, 19, 141, 3, 1, 1, 0),     # the same, several tiles per row, ragged
     (2, 128, 1, 19, 21, 4, 1, 2, 0),     # PatchGAN head shape on the generic thin-output kernels
 ]
 
@@ -776,13 +777,13 @@ def test_spade_style_on_upsampled_input_without_materialising_it(S, act, C):
     assert sink.buf is None and sink.seen == 0
 
 
-def test_conv_img_with_fused_leaky_relu_input(S):
+@pytest.mark.parametrize("B,H,W", [(2, 21, 37), (1, 45, 150), (3, 8, 128), (1, 7, 300)])
+def test_conv_img_with_fused_leaky_relu_input(S, B, H, W):
     """leaky_relu(x, 0.2) -> conv 64->1 3x3 (generator.py:97-98) as ONE forward kernel; its backward applies the
     LeakyReLU derivative inside the data-gradient kernel and the activation inside the weight-gradient kernel."""
     L, ops = S
     from seg2eye_b200.models.networks.layers import Conv2d
     g = torch.Generator().manual_seed(31)
-    B, H, W = 2, 21, 37
     x = bf(torch.randn(B, 64, H, W, generator=g))
     conv = Conv2d(64, 1, 3, padding=1).cuda()
     w = bf(conv.weight.detach().cpu())
@@ -796,9 +797,10 @@ def test_conv_img_with_fused_leaky_relu_input(S):
     y = conv.forward_nhwc(xc, in_act=L.ACT_LRELU)
     assert L.launches - n0 <= 2          # (weight pack +) one convolution kernel: no separate activation pass
     y.backward(nhwc(dy))
-    assert rel(nchw(y), yr) < TOL_ACT
-    assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
-    assert rel(conv.weight.grad, wr.grad) < TOL_ACT and rel(conv.bias.grad, br.grad) < TOL_ACT
+    # mma.sync kernels with fp32 accumulation: only the bf16 rounding of the outputs is left
+    assert rel(nchw(y), yr) < 4e-3, rel(nchw(y), yr)
+    assert rel(nchw(xc.grad), xr.grad) < 4e-3, rel(nchw(xc.grad), xr.grad)
+    assert rel(conv.weight.grad, wr.grad) < 2e-3 and rel(conv.bias.grad, br.grad) < TOL_ACT, rel(conv.weight.grad, wr.grad)
     # other shapes fall back to the separate activation kernel with identical results
     conv2 = Conv2d(16, 1, 3, padding=1).cuda()
     x2 = bf(torch.randn(B, 16, H, W, generator=g))
