@@ -285,7 +285,7 @@ __device__ __forceinline__ uint32_t pack_bf16_bits(bf16 lo, bf16 hi) {
 }
 __device__ __forceinline__ float in_act_slope(int in_act) { return in_act == S2E_ACT_LRELU ? 0.2f : 0.f; }
 
-__global__ void __launch_bounds__(256, 2) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+__global__ void __launch_bounds__(256, 3) thin_out1_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                                 const float* __restrict__ bias, const float* __restrict__ scale,
                                                                 bf16* __restrict__ y, const ThinGeom g, int tiles_w, int tiles_h,
                                                                 float* __restrict__ img_out, const float* __restrict__ img_target,

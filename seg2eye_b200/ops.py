@@ -605,6 +605,9 @@ def prepare_spectral(convs, training, n_calls=1, keep_uv=False):
 NormCfg = namedtuple("NormCfg", "per_sample act training momentum eps")
 
 
+_stats_memo = {"ref": None, "key": None, "acc": None}
+
+
 def spade_statistics(x, cfg, running_mean, running_var, nbt, up):
     """mean / rstd of the param-free norm of SPADE (normalization.py:73-75,91): batch statistics in training mode (also
     advancing BatchNorm's running buffers exactly like torch does) or for InstanceNorm, running statistics in eval mode.
@@ -616,13 +619,22 @@ def spade_statistics(x, cfg, running_mean, running_var, nbt, up):
     batch_stats = cfg.per_sample or cfg.training or running_mean is None
     if not batch_stats:   # BatchNorm2d in eval mode
         return running_mean.detach().clone().view(1, Cc), torch.rsqrt(running_var.detach() + cfg.eps).view(1, Cc), False
-    acc = torch.empty(G * 2 * Cc, dtype=torch.float64, device=x.device)
     mean = torch.empty(G, Cc, dtype=F32, device=x.device)
     rstd = torch.empty(G, Cc, dtype=F32, device=x.device)
     upd = (not cfg.per_sample) and cfg.training and running_mean is not None
     count = float(H * W if cfg.per_sample else B * H * W)     # elements BatchNorm sees (unbiased running_var)
     count_stats = count / 4 if up else count                  # elements actually summed (the 4x smaller source)
-    L.call("s2e_norm_stats", L.ptr(x), B, Hx * Wx, Cc, int(cfg.per_sample), L.ptr(acc), st)
+    # norm_s and norm_0 of a block with a learned shortcut normalise the SAME tensor (architecture.py:44-49): the sums are
+    # taken once, each layer finalises them into its own mean / rstd / running buffers
+    memo = _stats_memo
+    key = (x.data_ptr(), x._version, tuple(x.shape), int(cfg.per_sample))
+    if memo["ref"] is not None and memo["ref"]() is not None and memo["key"] == key:   # the summed tensor is still alive: same data
+        acc = memo["acc"]
+        _state["stats_shared"] = _state.get("stats_shared", 0) + 1
+    else:
+        acc = torch.empty(G * 2 * Cc, dtype=torch.float64, device=x.device)
+        L.call("s2e_norm_stats", L.ptr(x), B, Hx * Wx, Cc, int(cfg.per_sample), L.ptr(acc), st)
+        memo["ref"], memo["key"], memo["acc"] = _weakref.ref(x), key, acc
     L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count_stats, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
            L.ptr(running_mean) if upd else None, L.ptr(running_var) if upd else None, cfg.momentum,
            L.ptr(nbt) if upd else None, st)

@@ -175,6 +175,8 @@ def test_generator_blocks_match_oracle_taps(ctx):
             prev = name
     assert max(fed.values()) < TOL_ACT, fed
     assert len(fed_up) == 5 and max(fed_up.values()) < TOL_ACT, fed_up
+    # norm_s and norm_0 of the four blocks with a learned shortcut share one statistics pass over their common input
+    assert ops._state.get("stats_shared", 0) >= 4, ops._state.get("stats_shared", 0)
     assert max(chained.values()) < TOL_CHAIN, chained
 
 
