@@ -150,6 +150,7 @@ def conv_out_hw(cfg, hi, wi):
     return (hi + 2 * cfg.pad - cfg.kh) // cfg.stride + 1, (wi + 2 * cfg.pad - cfg.kw) // cfg.stride + 1
 
 
+_FTILE = tuple(int(v) for v in os.environ["S2E_FTILE"].split(",")) if os.environ.get("S2E_FTILE") else None
 _KTILE = tuple(int(v) for v in os.environ["S2E_KTILE"].split(",")) if os.environ.get("S2E_KTILE") else None
 
 
@@ -163,6 +164,8 @@ def _desc(B, Hi, Wi, Cin, Ho, Wo, Cout, taps, act, negate=False):
     d.act = act
     if _KTILE:      # bring-up aid: S2E_KTILE="w,h,b" overrides the weight-gradient kernels' pixel tile
         d.ktile_w, d.ktile_h, d.ktile_b = _KTILE
+    if _FTILE:      # bring-up aid: S2E_FTILE="w,h,b" overrides the forward / data-gradient kernels' pixel tile
+        d.tile_w, d.tile_h, d.tile_b = _FTILE
     return d
 
 
