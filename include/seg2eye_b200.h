@@ -199,7 +199,9 @@ int s2e_depth_to_space(const void* dy, int B, int H, int W, int C, void* dx, voi
  * x [B,HW,C] bf16, gb [B,HW,2C] bf16 (gamma | beta), style [B,2C] fp32 (s0 | s1).  mean/rstd are per
  * channel (param-free BatchNorm2d, training mode) or per (sample, channel) (InstanceNorm2d).
  * ------------------------------------------------------------------------------------------ */
-/* acc: double [G][2][C] (G = per_sample ? B : 1), zeroed inside. */
+/* acc: double [G][3][C] (G = per_sample ? B : 1), written inside: rows sum (x - p), sum (x - p)^2 and the pivot p[c] = the
+ * group's first pixel.  Shifted moments: E[x^2] - E[x]^2 from fp32 partial sums cancels badly for channels whose mean is
+ * large against their spread.  Plain sum = row 0 + n * row 2. */
 int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* acc, void* stream);
 /* mean/rstd float [G][C]; running_* may be NULL; biased var for rstd, unbiased for running_var.
  * count = number of elements behind `acc`; count_unbiased (0 = count) = number of elements the normalised tensor has

@@ -17,79 +17,71 @@ __device__ __forceinline__ float act_t(float v) {
 
 // ---------------------------------------------------------------- per-channel sum / sum of squares
 // grid = (chunks, G) ; G = B when per_sample else 1 (then the chunk range spans all samples)
-// body(p, c, acc) consumes one pixel; body4(p, stride, c, acc) consumes pixels p, p+stride, p+2 stride, p+3 stride with all
-// of their loads issued before the first use (memory-level parallelism).
-template <int NACC, typename F, typename F4>
-__device__ __forceinline__ void block_channel_reduce(int C, long long pix_begin, long long pix_end, double* out /*[NACC][C]*/,
-                                                     F&& body, F4&& body4) {
-  extern __shared__ float red[];  // [NT][NACC*8] worst case handled by looping
-  const int cg = C >> 3;          // channel groups of 8
-  const int tid = threadIdx.x;
-  // thread -> (channel group, pixel lane); when cg > NT loop over channel-group passes
-  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
-    const int ncg = min(NT, cg - cg0);
-    const int lanes = NT / ncg;
-    const int my_cg = tid % ncg, my_lane = tid / ncg;
-    float acc[NACC][8];
-#pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-    if (my_lane < lanes) {
-      long long p = pix_begin + my_lane;
-      for (; p + 3LL * lanes < pix_end; p += 4LL * lanes) body4(p, (long long)lanes, (cg0 + my_cg) * 8, acc);
-      for (; p < pix_end; p += lanes) body(p, (cg0 + my_cg) * 8, acc);
-    }
-    // combine pixel lanes through smem: layout [lane][ncg][NACC*8]
-    for (int a = 0; a < NACC; ++a) {
-      __syncthreads();
-      if (my_lane < lanes) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[(my_lane * ncg + my_cg) * 8 + j] = acc[a][j];
-      }
-      __syncthreads();
-      for (int idx = tid; idx < ncg * 8; idx += NT) {
-        float s = 0.f;
-        for (int l = 0; l < lanes; ++l) s += red[l * ncg * 8 + idx];
-        atomicAdd(out + (size_t)a * C + cg0 * 8 + idx, (double)s);
-      }
-    }
-  }
-}
-
+// Statistics are accumulated on SHIFTED data: sum (x - p), sum (x - p)^2 with the pivot p[c] = the group's first pixel.  The raw
+// moments E[x^2] - E[x]^2 lose (mean / sigma)^2 of their relative precision to cancellation when they are built from fp32
+// per-thread partial sums; with a pivot that is a sample of the channel the loss is ((p - mean) / sigma)^2, i.e. O(1).
+// acc layout per group: [sum (x-p)][sum (x-p)^2][p], doubles.
 __global__ void __launch_bounds__(NT) stats_kernel(const bf16* __restrict__ x, int HW, int C, long long pix_total,
                                                    int per_sample, double* __restrict__ acc) {
+  extern __shared__ float red[];  // [lanes][ncg][8]
   const int g = blockIdx.y;
   const long long span = per_sample ? HW : pix_total;
   const long long base = per_sample ? (long long)g * HW : 0;
   const long long chunk = (span + gridDim.x - 1) / gridDim.x;
   const long long b0 = base + (long long)blockIdx.x * chunk;
   const long long b1 = min(base + span, b0 + chunk);
-  auto one = [&](long long p, int c, float(*a)[8]) {
-    float f[8];
-    unpack8(ld_stream8(x + p * C + c), f);
+  const int cg = C >> 3;
+  const int tid = threadIdx.x;
+  double* out = acc + (size_t)g * 3 * C;
+  for (int cg0 = 0; cg0 < cg; cg0 += NT) {
+    const int ncg = min(NT, cg - cg0);
+    const int lanes = NT / ncg;
+    const int my_cg = tid % ncg, my_lane = tid / ncg;
+    const int c = (cg0 + my_cg) * 8;
+    float pv[8], a0[8], a1[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + base * C + c), pv);
+    if (blockIdx.x == 0 && my_lane == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[0][j] += f[j];
-      a[1][j] = fmaf(f[j], f[j], a[1][j]);
+      for (int j = 0; j < 8; ++j) out[2 * (size_t)C + c + j] = (double)pv[j];
     }
-  };
-  auto four = [&](long long p, long long st, int c, float(*a)[8]) {
-    bf16x8 v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = ld_stream8(x + (p + i * st) * C + c);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    auto eat = [&](const bf16x8& v) {
       float f[8];
-      unpack8(v[i], f);
+      unpack8(v, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        a[0][j] += f[j];
-        a[1][j] = fmaf(f[j], f[j], a[1][j]);
+        const float d = f[j] - pv[j];
+        a0[j] += d;
+        a1[j] = fmaf(d, d, a1[j]);
+      }
+    };
+    if (my_lane < lanes) {
+      long long p = b0 + my_lane;
+      for (; p + 3LL * lanes < b1; p += 4LL * lanes) {
+        bf16x8 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = ld_stream8(x + (p + (long long)i * lanes) * C + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) eat(v[i]);
+      }
+      for (; p < b1; p += lanes) eat(ld_stream8(x + p * C + c));
+    }
+#pragma unroll 1
+    for (int a = 0; a < 2; ++a) {
+      __syncthreads();
+      if (my_lane < lanes) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(my_lane * ncg + my_cg) * 8 + j] = a == 0 ? a0[j] : a1[j];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < ncg * 8; idx += NT) {
+        float sum = 0.f;
+        for (int l = 0; l < lanes; ++l) sum += red[l * ncg * 8 + idx];
+        atomicAdd(out + (size_t)a * C + cg0 * 8 + idx, (double)sum);
       }
     }
-  };
-  block_channel_reduce<2>(C, b0, b1, acc + (size_t)g * 2 * C, one, four);
+  }
 }
 
 // in_scale (optional, one value per `group` consecutive statistic groups): statistics are those of x * in_scale without
@@ -101,9 +93,10 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int G, int C, do
   if (i == 0 && nbt) *nbt += 1;
   if (i >= G * C) return;
   const int g = i / C, c = i % C;
-  const double s = acc[(size_t)g * 2 * C + c], ss = acc[(size_t)g * 2 * C + C + c];
-  const double m = s / count;
-  double var = ss / count - m * m;
+  const double s = acc[(size_t)g * 3 * C + c], ss = acc[(size_t)g * 3 * C + C + c], pivot = acc[(size_t)g * 3 * C + 2 * (size_t)C + c];
+  const double ms = s / count;          // mean of the shifted data
+  const double m = pivot + ms;
+  double var = ss / count - ms * ms;
   if (var < 0) var = 0;
   mean[i] = (float)m;
   const double sc = in_scale ? (double)in_scale[g / group] : 1.0;
@@ -761,7 +754,7 @@ int s2e_norm_stats(const void* x, int B, int HW, int C, int per_sample, double* 
   S2E_REQUIRE(C % 8 == 0 && C >= 8, "norm_stats needs C %% 8 == 0 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
   const int G = per_sample ? B : 1;
-  S2E_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * G * 2 * C, st));
+  S2E_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * G * 3 * C, st));   // [sum (x-p)][sum (x-p)^2][pivot p] per group
   const long long span = per_sample ? HW : (long long)B * HW;
   dim3 grid(red_chunks(span, G), G);
   stats_kernel<<<grid, NT, red_smem(C), st>>>((const bf16*)x, HW, C, (long long)B * HW, per_sample, acc);

@@ -298,10 +298,11 @@ def space_to_depth(x):
 
 
 def channel_sums(x2d_c, B, HW, Cc):
-    """fp32 per-channel sum over all pixels of an NHWC bf16 tensor (bias gradients)."""
-    acc = torch.empty(2 * Cc, dtype=torch.float64, device=x2d_c.device)
+    """fp32 per-channel sum over all pixels of an NHWC bf16 tensor (bias gradients).  s2e_norm_stats accumulates shifted
+    data, sum (x - p) with the pivot p = first pixel: the plain sum is that + n * p."""
+    acc = torch.empty(3 * Cc, dtype=torch.float64, device=x2d_c.device)
     L.call("s2e_norm_stats", L.ptr(x2d_c), B, HW, Cc, 0, L.ptr(acc), L.stream())
-    return acc[:Cc].to(F32)
+    return (acc[:Cc] + float(B * HW) * acc[2 * Cc:]).to(F32)
 
 
 class TapConvFn(torch.autograd.Function):
@@ -635,7 +636,7 @@ def spade_statistics(x, cfg, running_mean, running_var, nbt, up):
         acc = memo["acc"]
         _state["stats_shared"] = _state.get("stats_shared", 0) + 1
     else:
-        acc = torch.empty(G * 2 * Cc, dtype=torch.float64, device=x.device)
+        acc = torch.empty(G * 3 * Cc, dtype=torch.float64, device=x.device)    # [sum (x-p)][sum (x-p)^2][pivot p] per group
         L.call("s2e_norm_stats", L.ptr(x), B, Hx * Wx, Cc, int(cfg.per_sample), L.ptr(acc), st)
         memo["ref"], memo["key"], memo["acc"] = _weakref.ref(x), key, acc
     L.call("s2e_norm_finalize", L.ptr(acc), G, Cc, count_stats, count, cfg.eps, L.ptr(mean), L.ptr(rstd),
@@ -908,7 +909,7 @@ class InstNormFn(torch.autograd.Function):
     def forward(ctx, x, act, sn_inv=None, sn_U=None, sn_V=None, group=1, weight_orig=None):
         x = _c(x)
         B, H, W, Cc = x.shape
-        acc = torch.empty(B * 2 * Cc, dtype=torch.float64, device=x.device)
+        acc = torch.empty(B * 3 * Cc, dtype=torch.float64, device=x.device)
         mean = torch.empty(B, Cc, dtype=F32, device=x.device)
         rstd = torch.empty(B, Cc, dtype=F32, device=x.device)
         y = torch.empty_like(x)

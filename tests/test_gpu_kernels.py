@@ -359,6 +359,29 @@ def test_instance_norm_fwd_bwd(S, act, C):
     assert rel(nchw(xc.grad), xr.grad) < TOL_ACT
 
 
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_statistics_of_large_mean_channels(S, per_sample):
+    """Per-channel mean / 1/sqrt(var + eps) of channels whose mean is 200 standard deviations away from zero: the shifted
+    accumulation (pivot = first pixel) keeps ~1e-6 where raw E[x^2] - E[x]^2 moments from fp32 partial sums lose (mean/sigma)^2
+    of their precision.  Also the plain channel sums derived from the shifted ones (bias gradients)."""
+    L, ops = S
+    g = torch.Generator().manual_seed(8)
+    B, H, W, C = 3, 96, 80, 64
+    x = (torch.randn(B, H, W, C, generator=g) * 0.25 + 50.0 * (1 + torch.arange(C).float() / C)).to(torch.bfloat16).cuda()
+    cfg = ops.NormCfg(per_sample, L.ACT_NONE, True, 0.1, 1e-5)
+    mean, rstd, _ = ops.spade_statistics(x, cfg, None, None, None, False)
+    xd = x.double()
+    dims = (1, 2) if per_sample else (0, 1, 2)
+    m_ref = xd.mean(dim=dims)
+    v_ref = xd.var(dim=dims, unbiased=False)
+    r_ref = 1.0 / torch.sqrt(v_ref + 1e-5)
+    assert float(((mean.double().view_as(m_ref) - m_ref).abs() / m_ref.abs()).max()) < 1e-6
+    assert float(((rstd.double().view_as(r_ref) - r_ref).abs() / r_ref).max()) < 1e-4
+    sums = ops.channel_sums(x.view(-1, C), B, H * W, C)
+    s_ref = xd.sum(dim=(0, 1, 2))
+    assert float(((sums.double() - s_ref).abs() / s_ref.abs()).max()) < 1e-6
+
+
 @pytest.mark.parametrize("act,C,H,W", [(1, 128, 161, 97), (1, 512, 42, 26), (2, 256, 33, 40), (0, 2048, 8, 8), (1, 4096, 4, 4)])
 def test_instance_norm_streaming_paths(S, act, C, H, W):
     """The discriminator's / encoder's shapes (discriminator.py:34-37, encoder.py:23-38): several pixels in flight per thread,
