@@ -45,13 +45,15 @@ NCU_TRAFFIC = {
         "ncu --set full (profiles/r02a_ncu_fused.txt): tapconv_fwd_kernel<256,0,2,0> (training variant), B16 640x384 128->256 3x3 + "
         "SPADE+Style epilogue: dram read 1.270 GB + write 2.025 GB per launch vs 3.34 GB algorithmic (actv 1.007 + x 0.252 at half "
         "resolution + out 1.007 + gamma 1.007 + mask 0.063); tensor pipe 66.8 % active at 1.51 GHz (power-capped). The no-grad "
-        "variant <256,0,1,0> of the same class (D step / inference) moves 2.27 GB algorithmic"),
+        "variant <256,0,1,0> of the same class (D step / inference) moves 2.27 GB algorithmic. Re-measured on the final binaries "
+        "inside a whole step (profiles/r02f_step_metrics_summary.txt): 1.266 GB read + 2.027 GB written, tensor pipe 63.3 %"),
     "fwd B16 640x384 Cin128 Cout256 T9": (2.982e9,
         "ncu --set full (profiles/r02a_ncu_conv256.txt): tapconv_fwd_kernel<256,0,0,0>, B16 640x384 128->256 3x3: dram read 1.022 GB "
         "+ write 1.960 GB per launch vs 3.020 GB algorithmic (x 1.007 GB + y 2.013 GB); tensor pipe 76.3 % active at 1.45 GHz"),
     "dgrad B16 640x384 Cin256 Cout128 T9": (2.998e9,
         "ncu --set full (profiles/r02a_ncu_conv256.txt): tapconv_fwd_kernel<128,0,0,0> as data gradient, B16 640x384 256->128 3x3: "
-        "dram read 2.019 GB + write 0.979 GB per launch vs 3.020 GB algorithmic; tensor pipe 58.7 %"),
+        "dram read 2.019 GB + write 0.979 GB per launch vs 3.020 GB algorithmic; tensor pipe 58.7 % (since round 2d this class "
+        "runs the swapped-operand kernel <128,0,3,0>: same traffic, tensor pipe 77.9 %, profiles/r02d_ncu_swapped256to128.txt)"),
     "wgrad B16 640x384 Cin128 Cout256 T9": (3.749e9,
         "ncu --set full (profiles/r02a_ncu_conv256.txt): tapconv_wgrad_kernel<256>: dram read 3.743 GB + write 0.006 GB per launch "
         "vs 3.020 GB algorithmic (x 1.007 GB + dy 2.013 GB; 1.24x: taps whose CTAs are not co-resident re-read through DRAM); "
