@@ -36,8 +36,14 @@ class _Bucket:
 
 
 class GradReducer:
-    def __init__(self, params, bucket_bytes=32 << 20, overlap=None):
+    def __init__(self, params, bucket_bytes=None, overlap=None):
         self.params = [p for p in params if p.requires_grad]
+        if bucket_bytes is None:
+            # S2E_BUCKET_MB: size of the flat gradient buffers.  The all-reduce runs between the two CUDA graphs of a step (nothing
+            # to overlap with), so buckets only need to be large enough for NCCL's peak bus bandwidth: 8 x B200, 396 MB of G + E
+            # gradients: 102.0 ms/step with 32 MB buckets, 100.4 with 128 MB, 100.3 with 512 MB (profiles/r02f_bench_n8_c2*.json)
+            import os
+            bucket_bytes = int(os.environ.get("S2E_BUCKET_MB", "128")) << 20
         self.bucket_bytes = bucket_bytes
         # overlap = launch each bucket's all-reduce from inside backward (post-accumulate hooks).  Off by default since round 2:
         # the CUDA-graph steps (the fast path) cannot use it, and under torch 2.11 the hooks were seen to run for parameters
