@@ -63,7 +63,10 @@ def seg_nearest_cached(segmap, h, w, cpad):
 
 
 def clear_seg_cache():
+    """Called at both ends of a generator forward: the resized / im2col'd segmaps and the shared statistics sums (ops) live for one
+    forward only, so nothing cached can outlive the tensors (or the CUDA-graph capture) it was computed from."""
     _col_cache["key"], _col_cache["cols"] = None, {}
+    ops.clear_stats_memo()
 
 
 class FC(nn.Module):

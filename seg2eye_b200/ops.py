@@ -612,6 +612,10 @@ NormCfg = namedtuple("NormCfg", "per_sample act training momentum eps")
 _stats_memo = {"ref": None, "key": None, "acc": None}
 
 
+def clear_stats_memo():
+    _stats_memo["ref"] = _stats_memo["key"] = _stats_memo["acc"] = None
+
+
 def spade_statistics(x, cfg, running_mean, running_var, nbt, up):
     """mean / rstd of the param-free norm of SPADE (normalization.py:73-75,91): batch statistics in training mode (also
     advancing BatchNorm's running buffers exactly like torch does) or for InstanceNorm, running statistics in eval mode.
