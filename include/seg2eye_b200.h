@@ -132,11 +132,15 @@ int s2e_tapconv_wgrad(const s2e_conv_t* d, const void* x, const void* dy, float*
  * padding=2), the last block of NLayerDiscriminator) in tap-channel form, y[p] = sum_t D[p + tap_t][t] with
  * D[q][t] = x[q] . W[t]: the wide input is read once, not once per tap.
  *   s2e_head_dots    D[P][16] fp32 (taps >= ntaps: 0) from x [P][Cin] bf16 and the tap-major weight copy wp [ntaps][Cin] bf16
- *   s2e_head_gather  y [B][Ho][Wo][1] bf16 = act(scale * sum_t D[...] + bias); geometry, taps and act from the descriptor
+ *   s2e_head_gather  y [B][Ho][Wo][1] bf16 = act(scale * sum_t D[...] + bias); geometry, taps and act from the descriptor.
+ *                    gan_sums (nullable, 6 floats, caller-zeroed): the batch is [fake ; real] (pix2pix_model.py:328-338) and the
+ *                    kernel adds, per half h, [3h] += sum y, [3h+1] += sum min(y-1, 0), [3h+2] += sum min(-y-1, 0): the reductions of
+ *                    GANLoss's hinge / Wasserstein terms (loss.py:58-83) fused into the epilogue that produces the logits
  *   s2e_head_scatter G [B][Hi][Wi][64] bf16, G[q][t] = dy[q - tap_t] (0 outside the output / for t >= ntaps): the data and
  *                    weight gradients are then the 1x1 tap convolutions dx = G . W (64 -> Cin) and dW = G^T . x. */
 int s2e_head_dots(const void* x_bf16, const void* wp_bf16, long long P, int Cin, int ntaps, float* D, void* stream);
-int s2e_head_gather(const s2e_conv_t* d, const float* D, const float* bias, const float* scale, void* y_bf16, void* stream);
+int s2e_head_gather(const s2e_conv_t* d, const float* D, const float* bias, const float* scale, void* y_bf16, float* gan_sums,
+                    void* stream);
 int s2e_head_scatter(const s2e_conv_t* d, const void* dy_bf16, void* G_bf16, void* stream);
 
 /* OIHW fp32 master weight -> bf16 tap-major.  stride 1: taps (r,s) row-major, offset (r-pad, s-pad).

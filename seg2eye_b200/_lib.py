@@ -52,7 +52,7 @@ _SIGS = {
     "s2e_tapconv_fwd": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _I, _P],
     "s2e_tapconv_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _I, _P],
     "s2e_head_dots": [_P, _P, _LL, _I, _I, _P, _P],
-    "s2e_head_gather": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P],
+    "s2e_head_gather": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P],
     "s2e_head_scatter": [C.POINTER(ConvDesc), _P, _P, _P],
     "s2e_pack_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "s2e_packed_taps": [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)],

@@ -668,21 +668,53 @@ __global__ void __launch_bounds__(HD_THREADS) head_dots_kernel(const bf16* __res
   }
 }
 
+// gan_sums (nullable, 6 floats, caller-zeroed): the GAN loss reductions over the logits ride in this kernel's epilogue -- the batch
+// holds [fake ; real] (pix2pix_model.py:328-338), half h = (b >= half_b), and for each half the kernel adds
+//   [3h + 0] += sum y,   [3h + 1] += sum min(y - 1, 0),   [3h + 2] += sum min(-y - 1, 0)      (y as rounded to bf16)
+// i.e. the sums behind the hinge / Wasserstein terms of loss.py:58-83 (generator: -mean y_fake; discriminator: -mean min(y_real - 1, 0),
+// -mean min(-y_fake - 1, 0)), so those losses need no pass of their own over the logits.
 __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ D, const float* __restrict__ bias,
                                                           const float* __restrict__ scale, bf16* __restrict__ y, const ThinGeom g,
-                                                          long long P) {
+                                                          long long P, float* __restrict__ gan_sums, int half_b) {
   const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (p >= P) return;
-  const int wo = (int)(p % g.Wo);
-  const long long r = p / g.Wo;
-  const int ho = (int)(r % g.Ho);
-  const long long b = r / g.Ho;
-  float acc = 0.f;
-  for (int t = 0; t < g.ntaps; ++t) {
-    const int hi = ho + g.dy[t], wi = wo + g.dx[t];
-    if (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) acc += __ldg(D + ((b * g.Hi + hi) * g.Wi + wi) * 16 + t);
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (p < P) {
+    const int wo = (int)(p % g.Wo);
+    const long long r = p / g.Wo;
+    const int ho = (int)(r % g.Ho);
+    const long long b = r / g.Ho;
+    float acc = 0.f;
+    for (int t = 0; t < g.ntaps; ++t) {
+      const int hi = ho + g.dy[t], wi = wo + g.dx[t];
+      if (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) acc += __ldg(D + ((b * g.Hi + hi) * g.Wi + wi) * 16 + t);
+    }
+    const bf16 yb = __float2bfloat16(act_apply(acc * (scale ? __ldg(scale) : 1.f) + (bias ? __ldg(bias) : 0.f), g.act));
+    y[p] = yb;
+    if (gan_sums) {
+      const float v = __bfloat162float(yb);
+      const int h = b >= half_b ? 3 : 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] = 0.f;
+      const float t0 = v, t1 = fminf(v - 1.f, 0.f), t2 = fminf(-v - 1.f, 0.f);
+      s[0] = h == 0 ? t0 : 0.f; s[1] = h == 0 ? t1 : 0.f; s[2] = h == 0 ? t2 : 0.f;
+      s[3] = h == 3 ? t0 : 0.f; s[4] = h == 3 ? t1 : 0.f; s[5] = h == 3 ? t2 : 0.f;
+    }
   }
-  y[p] = __float2bfloat16(act_apply(acc * (scale ? __ldg(scale) : 1.f) + (bias ? __ldg(bias) : 0.f), g.act));
+  if (gan_sums) {   // kernel-uniform branch
+    __shared__ float red[6][8];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float w = warp_sum(s[k]);
+      if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+      if (t != 0.f) atomicAdd(gan_sums + threadIdx.x, t);
+    }
+  }
 }
 
 // G[q][t] = dy[q - tap_t] for t < ntaps (zero where that output pixel does not exist), zero for the other 64 - ntaps
@@ -1017,11 +1049,13 @@ int s2e_head_dots(const void* x, const void* wp, long long P, int Cin, int ntaps
   return S2E_OK;
 }
 
-int s2e_head_gather(const s2e_conv_t* d, const float* D, const float* bias, const float* scale, void* y, void* stream) {
+int s2e_head_gather(const s2e_conv_t* d, const float* D, const float* bias, const float* scale, void* y, float* gan_sums, void* stream) {
   S2E_REQUIRE(d && d->Cout == 1 && d->ntaps >= 1 && d->ntaps <= 16, "head_gather: one output channel, <= 16 taps");
+  S2E_REQUIRE(!gan_sums || d->B % 2 == 0, "head_gather: the GAN sums need a [fake ; real] batch (B = %d)", d->B);
   const long long P = (long long)d->B * d->Ho * d->Wo;
   if (P == 0) return S2E_OK;
-  head_gather_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, (cudaStream_t)stream>>>(D, bias, scale, (bf16*)y, make_thin_geom(d), P);
+  head_gather_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, (cudaStream_t)stream>>>(D, bias, scale, (bf16*)y, make_thin_geom(d), P, gan_sums,
+                                                                                      d->B / 2);
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

@@ -35,12 +35,17 @@ class GANLoss(nn.Module):
             return ops.reduce_loss(x, None, L.RED_LS, 1.0 / n, label).view(())
         if self.gan_mode == 'hinge':
             if for_discriminator:
-                kind = L.RED_HINGE_REAL if target_is_real else L.RED_HINGE_FAKE
-                return ops.reduce_loss(x, None, kind, -1.0 / n).view(())
-            assert target_is_real, "The generator's hinge loss must be aiming for real"
-            return ops.reduce_loss(x, None, L.RED_SUM, -1.0 / n).view(())
-        # wgan
-        return ops.reduce_loss(x, None, L.RED_SUM, (-1.0 if target_is_real else 1.0) / n).view(())
+                kind, coef = (L.RED_HINGE_REAL if target_is_real else L.RED_HINGE_FAKE), -1.0 / n
+            else:
+                assert target_is_real, "The generator's hinge loss must be aiming for real"
+                kind, coef = L.RED_SUM, -1.0 / n
+        else:   # wgan
+            kind, coef = L.RED_SUM, (-1.0 if target_is_real else 1.0) / n
+        # logits straight out of the discriminator's head: their sums were reduced in the kernel that produced them
+        pre = ops.gan_presummed(input, kind, coef) if input is x else None
+        if pre is not None:
+            return pre.view(())
+        return ops.reduce_loss(x, None, kind, coef).view(())
 
     def __call__(self, input, target_is_real, for_discriminator=True):
         if isinstance(input, list):

@@ -254,7 +254,11 @@ class Pix2PixModel(torch.nn.Module):
     def divide_pred(self, pred):
         def halves(t):
             n = t.size(0) // 2
-            return t[:n], t[n:]
+            a, b = t[:n], t[n:]
+            sums = getattr(t, '_s2e_gan_sums', None)    # logits whose gather kernel already reduced both halves (ops.head_conv)
+            if sums is not None and t.size(0) == 2 * n:
+                a._s2e_gan_half, b._s2e_gan_half = (sums, 0, a._version), (sums, 1, b._version)
+            return a, b
         if isinstance(pred, list):
             split = [[halves(t) for t in scale] for scale in pred]
             return [[p[0] for p in s] for s in split], [[p[1] for p in s] for s in split]

@@ -493,17 +493,22 @@ class HeadConvFn(torch.autograd.Function):
         wp = packed_weights((weight,), cfg, False)          # [tap][1][Cin] bf16
         D = torch.empty(B * Hi * Wi, 16, dtype=F32, device=x.device)
         y = torch.empty(B, Ho, Wo, 1, dtype=BF16, device=x.device)
+        # [fake ; real] batches: the sums behind GANLoss's hinge / Wasserstein terms ride in the gather kernel's epilogue
+        sums = torch.zeros(6, dtype=F32, device=x.device) if B % 2 == 0 else None
         d = _desc(B, Hi, Wi, Cin, Ho, Wo, 1, taps, L.ACT_NONE)
         st = L.stream()
         L.call("s2e_head_dots", L.ptr(x), L.ptr(wp), B * Hi * Wi, Cin, len(taps), L.ptr(D), st)
-        L.call("s2e_head_gather", d, L.ptr(D), L.ptr(bias.detach() if bias is not None else None), None, L.ptr(y), st)
+        L.call("s2e_head_gather", d, L.ptr(D), L.ptr(bias.detach() if bias is not None else None), None, L.ptr(y), L.ptr(sums), st)
         ctx.cfg, ctx.has_b = cfg, bias is not None
         ctx.skip_wgrad = _state["skip_wgrad"]
         ctx.save_for_backward(x, weight)
-        return y
+        if sums is None:
+            return y, None
+        ctx.mark_non_differentiable(sums)
+        return y, sums
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dsums=None):
         x, weight = ctx.saved_tensors
         cfg = ctx.cfg
         dy = _c(dy)
@@ -536,7 +541,26 @@ class HeadConvFn(torch.autograd.Function):
 
 
 def head_conv(x, cfg, weight, bias=None):
-    return HeadConvFn.apply(x, cfg, weight, bias)
+    """-> logits (B, Ho, Wo, 1) bf16.  For an even batch the tensor carries `_s2e_gan_sums` (6 floats: per half of the batch
+    sum y, sum min(y-1, 0), sum min(-y-1, 0)), which GANLoss picks up instead of reducing the logits again."""
+    y, sums = HeadConvFn.apply(x, cfg, weight, bias)
+    if sums is not None:
+        y._s2e_gan_sums = sums
+    return y
+
+
+def gan_presummed(pred, kind, coef):
+    """coef * sum f(pred) for f = identity / hinge-real / hinge-fake when `pred` is one half of a logit tensor whose gather
+    kernel already reduced it (pix2pix_model.divide_pred tags the halves); None otherwise."""
+    tag = getattr(pred, '_s2e_gan_half', None)
+    col = {L.RED_SUM: 0, L.RED_HINGE_REAL: 1, L.RED_HINGE_FAKE: 2}.get(kind)
+    if tag is None or col is None:
+        return None
+    sums, half, version = tag
+    if pred._version != version or not pred.is_contiguous():
+        return None
+    _state["gan_presummed"] = _state.get("gan_presummed", 0) + 1
+    return PrecomputedLossFn.apply(pred, None, sums, 3 * half + col, kind, coef)
 
 
 def _sn_scratch_floats(rows, cols):
@@ -1572,7 +1596,7 @@ class PrecomputedLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         a, b = ctx.saved_tensors
-        a, b = _c(a), _c(b)
+        a, b = _c(a), (_c(b) if b is not None else None)
         gout = _c(gout.float())
         da = torch.empty_like(a)
         L.call("s2e_reduce_loss_bwd", L.ptr(a), L.ptr(b), a.numel(), int(a.dtype == F32), ctx.kind, ctx.coef, 0.0, L.ptr(gout),

@@ -716,6 +716,45 @@ def test_head_conv_tap_channel_form(S, case):
     assert rel(nchw(xc.grad), -0.5 * xr.grad) < TOL_ACT
 
 
+@pytest.mark.parametrize("mode", ["hinge", "w"])
+def test_gan_loss_sums_fused_into_the_logit_head(S, mode):
+    """The discriminator's logit head reduces, in its gather kernel, the sums behind GANLoss's hinge / Wasserstein terms
+    (loss.py:58-83) for both halves of a [fake ; real] batch; Pix2PixModel.divide_pred tags the halves and GANLoss then skips its
+    own reduction.  Values and gradients must equal the separate reduction kernels' (same bf16 logits, fp32 sums)."""
+    L, ops = S
+    from seg2eye_b200.models.networks.layers import Conv2d
+    from seg2eye_b200.models.networks.loss import GANLoss
+    from seg2eye_b200.models.pix2pix_model import Pix2PixModel
+    g = torch.Generator().manual_seed(17)
+    conv = Conv2d(128, 1, 4, stride=1, padding=2).cuda()
+    x = nhwc(bf(torch.randn(6, 128, 13, 11, generator=g) * 3)).requires_grad_()
+    crit = GANLoss(mode)
+    cases = [(0, True, False), (0, False, True), (1, True, True)]    # (half, target_is_real, for_discriminator)
+    res = {}
+    for fused in (True, False):
+        y = conv.forward_nhwc(x)
+        assert hasattr(y, "_s2e_gan_sums")
+        if not fused:
+            del y._s2e_gan_sums
+        halves = Pix2PixModel.divide_pred(None, y)
+        assert hasattr(halves[0], "_s2e_gan_half") == fused
+        hits0 = ops._state.get("gan_presummed", 0)
+        losses = [crit(halves[h], real, for_discriminator=ford) for h, real, ford in cases]
+        assert ops._state.get("gan_presummed", 0) - hits0 == (3 if fused else 0)
+        x.grad = None
+        sum(losses).backward()
+        res[fused] = ([float(l.detach()) for l in losses], x.grad.float().clone())
+    for a, b in zip(res[True][0], res[False][0]):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (res[True][0], res[False][0])
+    assert rel(res[True][1].cpu(), res[False][1].cpu()) < 1e-6
+    ref = nchw(conv.forward_nhwc(x).detach())
+    want = {("hinge", 0): -float(ref[:3].mean()), ("w", 0): -float(ref[:3].mean()),
+            ("hinge", 1): -float(torch.clamp(-ref[:3] - 1, max=0).mean()), ("w", 1): float(ref[:3].mean()),
+            ("hinge", 2): -float(torch.clamp(ref[3:] - 1, max=0).mean()), ("w", 2): -float(ref[3:].mean())}
+    for i in range(3):
+        assert abs(res[True][0][i] - want[(mode, i)]) < 1e-4 * max(1.0, abs(want[(mode, i)])), (i, res[True][0], want)
+
+
 def test_one_channel_head_on_tensor_cores(S):
     """PatchGAN logit head (512 -> 1, 4x4 s1 p2; discriminator.py:96) with cout_pad: zero-padded output channels on the
     tcgen05 kernels; forward, data gradient, weight and bias gradient vs torch."""
