@@ -261,3 +261,33 @@ def test_bf16_operand_floor_of_the_chained_generator():
     assert max(blocks.values()) < 1e-2 < img < 1.6e-2, (blocks, img)
     blocks_all, img_all = pf.measure(pf.ALL)
     assert img < img_all < 2e-2 and blocks_all["up_0"] < 1e-2 < blocks_all["up_3"] < 1.3e-2, (blocks_all, img_all)
+
+
+def test_logit_head_routing_and_gan_sum_tags():
+    """Host logic of the round-2e logit head: which convolutions take the tap-channel route (ops.head_conv_ok), and how
+    Pix2PixModel.divide_pred hands the sums reduced by the head's gather kernel to GANLoss (tags on the two halves; a tag is void
+    once the tensor was modified, for the wrong reduction kind, or without a producer)."""
+    from seg2eye_b200 import _lib as L, ops
+    from seg2eye_b200.models.pix2pix_model import Pix2PixModel
+    e = lambda *s: torch.empty(*s, device="meta")
+    cfg = ops.ConvCfg(4, 4, 1, 2, L.ACT_NONE)
+    assert ops.head_conv_ok(e(32, 82, 50, 512), cfg, e(1, 512, 4, 4))               # D's logit head at ndf = 64
+    assert ops.head_conv_ok(e(4, 11, 9, 128), cfg, e(1, 128, 4, 4))                 # ... and at ndf = 16
+    assert not ops.head_conv_ok(e(16, 640, 384, 64), ops.ConvCfg(3, 3, 1, 1, L.ACT_NONE), e(1, 64, 3, 3))   # conv_img: its own kernels
+    assert not ops.head_conv_ok(e(4, 11, 9, 128), cfg._replace(stride=2), e(1, 128, 4, 4))
+    assert not ops.head_conv_ok(e(4, 11, 9, 128), cfg._replace(act=L.ACT_LRELU), e(1, 128, 4, 4))
+    assert not ops.head_conv_ok(e(4, 11, 9, 128), cfg, e(2, 128, 4, 4))
+    assert not ops.head_conv_ok(e(4, 11, 9, 128), cfg, e(1, 128, 4, 4), sn=(None, None, None))
+    t = torch.zeros(6, 5, 4, 1)
+    a, b = Pix2PixModel.divide_pred(None, t)
+    assert not hasattr(a, "_s2e_gan_half") and ops.gan_presummed(a, L.RED_SUM, 1.0) is None
+    t._s2e_gan_sums = torch.arange(6.0)
+    a, b = Pix2PixModel.divide_pred(None, t)
+    assert a._s2e_gan_half[1] == 0 and b._s2e_gan_half[1] == 1 and a._s2e_gan_half[0] is t._s2e_gan_sums
+    assert ops.gan_presummed(b, L.RED_L1, 1.0) is None                              # only sum / hinge kinds are reduced by the head
+    assert float(ops.gan_presummed(b, L.RED_HINGE_REAL, 2.0)) == 2.0 * 4.0          # sums[3 * 1 + 1]
+    assert float(ops.gan_presummed(a, L.RED_SUM, -1.0)) == -0.0
+    b.add_(1.0)                                                                     # modified since the head produced it: tag void
+    assert ops.gan_presummed(b, L.RED_HINGE_REAL, 2.0) is None
+    nested = Pix2PixModel.divide_pred(None, [[torch.zeros(4, 2, 2, 8), t]])
+    assert hasattr(nested[0][0][1], "_s2e_gan_half") and not hasattr(nested[0][0][0], "_s2e_gan_half")
