@@ -244,8 +244,10 @@ int s2e_spade_style_bwd(const void* dout, const uint8_t* act_mask, const void* x
 
 /* InstanceNorm2d(affine=False)+optional LeakyReLU on NHWC bf16 (normalization.py:41; discriminator.py:88-92;
  * encoder.py:23-38).  in_scale (nullable): one factor per `group` consecutive images, applied to x implicitly. */
+/* pair_l1 (nullable, one float, caller-zeroed): the batch is the [fake ; real] pair of a discriminator feature map and the apply
+ * pass also adds sum |y[b] - y[b + B/2]| (bf16 values) to it: the feature-matching reduction of pix2pix_model.py:233-241. */
 int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, const float* in_scale, int group,
-                     double* acc, float* mean, float* rstd, void* y, void* stream);
+                     double* acc, float* mean, float* rstd, void* y, float* pair_l1, void* stream);
 /* Batched style encoder (pix2pix_model.py:285 calls netE once per sample, so sample b sees its own 1/sigma_b):
  * the convolution runs unscaled, in_scale[n / group] folds 1/sigma_b into the InstanceNorm statistics, and the
  * spectral chain-rule term  dW_orig -= sum_b c_b u_b v_b^T,  c_b = (eps/is_b) sum_{n in b, c} S2[n,c] rstd'[n,c]^2

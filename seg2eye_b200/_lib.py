@@ -69,7 +69,7 @@ _SIGS = {
     "s2e_spade_params": [_P, _P, _P, _I, _I, _I, _P, _P],
     "s2e_spade_style_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "s2e_spade_style_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _P],
-    "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P, _P],
+    "s2e_instnorm_fwd": [_P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P],
     "s2e_instnorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "s2e_upsample2x_fwd": [_P, _I, _I, _I, _I, _P, _P],
     "s2e_upsample2x_bwd": [_P, _I, _I, _I, _I, _P, _P],

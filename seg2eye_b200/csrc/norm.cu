@@ -545,27 +545,36 @@ __global__ void __launch_bounds__(NT) spade_bwd_apply_kernel(const bf16* __restr
 
 // ---------------------------------------------------------------- InstanceNorm (+act)
 // same streaming structure as the SPADE kernels: grid (pixel chunks, B), per-channel constants in registers
+// PAIR: the batch holds [fake ; real] halves of a discriminator feature (pix2pix_model.py:328-338) and the block normalises
+// sample b AND sample b + pair_off; the feature-matching term sum |y_fake - y_real| (pix2pix_model.py:233-241, on the values as
+// rounded to bf16) is reduced on the way and added to *pair_l1 -- no pass of its own over the feature map.
+template <bool PAIR>
 __global__ void __launch_bounds__(NT) instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int HW, int C, int act,
-                                                            bf16* __restrict__ y) {
+                                                            bf16* __restrict__ y, int pair_off, float* __restrict__ pair_l1) {
   const int b = blockIdx.y;
   const long long chunk = ((long long)HW + gridDim.x - 1) / gridDim.x;
   const long long q0 = (long long)blockIdx.x * chunk;
   const long long q1 = min((long long)HW, q0 + chunk);
   const int cg = C >> 3;
+  float l1 = 0.f;
   for (int cg0 = 0; cg0 < cg; cg0 += NT) {
     const int ncg = min(NT, cg - cg0);
     const int lanes = NT / ncg;
     const int my_cg = threadIdx.x % ncg, my_lane = threadIdx.x / ncg;
     if (my_lane >= lanes) continue;
     const int c = (cg0 + my_cg) * 8;
-    float ka[8], kb[8];
+    float ka[8], kb[8], ka2[8], kb2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       ka[j] = rstd[(size_t)b * C + c + j];
       kb[j] = -mean[(size_t)b * C + c + j] * ka[j];
+      if (PAIR) {
+        ka2[j] = rstd[(size_t)(b + pair_off) * C + c + j];
+        kb2[j] = -mean[(size_t)(b + pair_off) * C + c + j] * ka2[j];
+      }
     }
-    const long long base = (long long)b * HW;
+    const long long base = (long long)b * HW, base2 = (long long)(b + pair_off) * HW;
     auto emit = [&](long long p, const bf16x8& v) {
       float f[8], o[8];
       unpack8(v, f);
@@ -573,15 +582,54 @@ __global__ void __launch_bounds__(NT) instnorm_apply_kernel(const bf16* __restri
       for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
       st_stream8(y + p * C + c, pack8(o));
     };
+    auto emit2 = [&](long long q, const bf16x8& v, const bf16x8& v2) {
+      float f[8], f2[8], o[8], o2[8];
+      unpack8(v, f);
+      unpack8(v2, f2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = act_apply(fmaf(f[j], ka[j], kb[j]), act);
+        o2[j] = act_apply(fmaf(f2[j], ka2[j], kb2[j]), act);
+      }
+      const bf16x8 r = pack8(o), r2 = pack8(o2);
+      st_stream8(y + (base + q) * C + c, r);
+      st_stream8(y + (base2 + q) * C + c, r2);
+      unpack8(r, o);
+      unpack8(r2, o2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) l1 += fabsf(o[j] - o2[j]);
+    };
     long long q = q0 + my_lane;
-    for (; q + 3LL * lanes < q1; q += 4LL * lanes) {   // four 16-byte loads in flight per thread
-      bf16x8 v[4];
+    if (PAIR) {
+      for (; q + lanes < q1; q += 2LL * lanes) {   // two pixels of both samples in flight
+        const bf16x8 a0 = ld_stream8(x + (base + q) * C + c), a1 = ld_stream8(x + (base2 + q) * C + c);
+        const bf16x8 c0 = ld_stream8(x + (base + q + lanes) * C + c), c1 = ld_stream8(x + (base2 + q + lanes) * C + c);
+        emit2(q, a0, a1);
+        emit2(q + lanes, c0, c1);
+      }
+      for (; q < q1; q += lanes) emit2(q, ld_stream8(x + (base + q) * C + c), ld_stream8(x + (base2 + q) * C + c));
+    } else {
+      for (; q + 3LL * lanes < q1; q += 4LL * lanes) {   // four 16-byte loads in flight per thread
+        bf16x8 v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = ld_stream8(x + (base + q + (long long)i * lanes) * C + c);
+        for (int i = 0; i < 4; ++i) v[i] = ld_stream8(x + (base + q + (long long)i * lanes) * C + c);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) emit(base + q + (long long)i * lanes, v[i]);
+        for (int i = 0; i < 4; ++i) emit(base + q + (long long)i * lanes, v[i]);
+      }
+      for (; q < q1; q += lanes) emit(base + q, ld_stream8(x + (base + q) * C + c));
     }
-    for (; q < q1; q += lanes) emit(base + q, ld_stream8(x + (base + q) * C + c));
+  }
+  if (PAIR) {   // every thread arrives here (the `continue` above only skips channel passes)
+    __shared__ float red[NT / 32];
+    l1 = warp_sum(l1);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < NT / 32; ++i) t += red[i];
+      atomicAdd(pair_l1, t);
+    }
   }
 }
 
@@ -899,14 +947,20 @@ int s2e_sn_in_correction(const double* racc, const float* rstd, const float* inv
 }
 
 int s2e_instnorm_fwd(const void* x, int B, int HW, int C, int act, float eps, const float* in_scale, int group, double* acc,
-                     float* mean, float* rstd, void* y, void* stream) {
+                     float* mean, float* rstd, void* y, float* pair_l1, void* stream) {
+  S2E_REQUIRE(!pair_l1 || B % 2 == 0, "instnorm_fwd: the fake / real pair sum needs an even batch (B = %d)", B);
   int rc = s2e_norm_stats(x, B, HW, C, 1, acc, stream);
   if (rc) return rc;
   finalize_kernel<<<ceil_div(B * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, B, C, (double)HW, eps, mean, rstd, nullptr, nullptr,
                                                                            0.f, nullptr, in_scale, group > 0 ? group : 1, 0.0);
   S2E_LAUNCH_CHECK();
-  dim3 grid(ew_chunks(HW, B, C), B);
-  instnorm_apply_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, rstd, HW, C, act, (bf16*)y);
+  if (pair_l1) {
+    dim3 grid(ew_chunks(HW, B / 2, C), B / 2);
+    instnorm_apply_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, rstd, HW, C, act, (bf16*)y, B / 2, pair_l1);
+  } else {
+    dim3 grid(ew_chunks(HW, B, C), B);
+    instnorm_apply_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, rstd, HW, C, act, (bf16*)y, 0, nullptr);
+  }
   S2E_LAUNCH_CHECK();
   return S2E_OK;
 }

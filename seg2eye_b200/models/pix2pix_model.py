@@ -133,7 +133,11 @@ class Pix2PixModel(torch.nn.Module):
             self.netG.loss_target = target_image
         fake, w_real, feats_real = self.generate_fake(input_semantics, style_image)
         with ops.skip_weight_grads():
-            pred_fake, pred_real = self.discriminate(input_semantics, fake, target_image)
+            if opt.no_ganFeat_loss:
+                pred_fake, pred_real = self.discriminate(input_semantics, fake, target_image)
+            else:
+                with ops.fm_pair_sums():    # D's InstanceNorm kernels also reduce the feature-matching L1 of their [fake ; real] output
+                    pred_fake, pred_real = self.discriminate(input_semantics, fake, target_image)
         d_full, self._last_d_out = self._last_d_out, None
         losses = {'GAN': self.criterionGAN(pred_fake, True, for_discriminator=False)}
         for key, lam, crit in (('L2', opt.lambda_l2, self.criterionL2), ('L1', opt.lambda_l1, self.criterionL1)):
@@ -166,7 +170,11 @@ class Pix2PixModel(torch.nn.Module):
                 for j in range(len(pred_fake[i]) - 1):      # the last entry is the prediction itself
                     if d_full is not None:                   # L1(fake half, real half.detach()) on the un-split tensor
                         t = networks.loss._flat(d_full[i][j])
-                        term = ops.HalvesLossFn.apply(t, L.RED_L1, 2.0 / t.numel()).view(())
+                        pre = getattr(d_full[i][j], '_s2e_fm_sum', None)   # reduced by the InstanceNorm kernel that produced it
+                        if pre is not None and t is d_full[i][j] and pre[1] == t._version:
+                            term = ops.HalvesPresummedFn.apply(t, pre[0], L.RED_L1, 2.0 / t.numel()).view(())
+                        else:
+                            term = ops.HalvesLossFn.apply(t, L.RED_L1, 2.0 / t.numel()).view(())
                     else:
                         term = self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
                     fm = fm + term * opt.lambda_feat / n_scales

@@ -934,7 +934,9 @@ class InstNormFn(torch.autograd.Function):
     spectral chain-rule term  - sum_s c_s u_s v_s^T  (see s2e_sn_in_correction)."""
 
     @staticmethod
-    def forward(ctx, x, act, sn_inv=None, sn_U=None, sn_V=None, group=1, weight_orig=None):
+    def forward(ctx, x, act, sn_inv=None, sn_U=None, sn_V=None, group=1, weight_orig=None, pair_l1=None):
+        """pair_l1 (optional, one zeroed float): x holds the [fake ; real] halves of a discriminator feature; the kernel adds
+        sum |y[:B/2] - y[B/2:]| to it (the feature-matching reduction rides in the apply pass)."""
         x = _c(x)
         B, H, W, Cc = x.shape
         acc = torch.empty(B * 3 * Cc, dtype=torch.float64, device=x.device)
@@ -942,7 +944,7 @@ class InstNormFn(torch.autograd.Function):
         rstd = torch.empty(B, Cc, dtype=F32, device=x.device)
         y = torch.empty_like(x)
         L.call("s2e_instnorm_fwd", L.ptr(x), B, H * W, Cc, act, 1e-5, L.ptr(sn_inv), group, L.ptr(acc), L.ptr(mean),
-               L.ptr(rstd), L.ptr(y), L.stream())
+               L.ptr(rstd), L.ptr(y), L.ptr(pair_l1), L.stream())
         ctx.act, ctx.group = act, group
         ctx.skip_wgrad = _state["skip_wgrad"]    # captured at forward time, like TapConvFn
         ctx.has_sn = sn_inv is not None
@@ -967,7 +969,19 @@ class InstNormFn(torch.autograd.Function):
             gw = torch.empty_like(weight_orig)
             L.call("s2e_sn_in_correction", L.ptr(racc), L.ptr(rstd), L.ptr(sn_inv), S, ctx.group, Cc, 1e-5, L.ptr(sn_U),
                    L.ptr(sn_V), K, L.ptr(coef), L.ptr(gw), st)
-        return dx, None, None, None, None, None, gw
+        return dx, None, None, None, None, None, gw, None
+
+
+@contextlib.contextmanager
+def fm_pair_sums():
+    """While active, InstanceNorm layers fed with an even batch also reduce sum |y[:B/2] - y[B/2:]| (layers.InstanceNorm2d): the
+    generator step's discriminator pass, whose features enter the feature-matching loss."""
+    prev = _state.get("fm_pairs", False)
+    _state["fm_pairs"] = True
+    try:
+        yield
+    finally:
+        _state["fm_pairs"] = prev
 
 
 # ------------------------------------------------------------------------------------------------ elementwise / resampling
@@ -1343,6 +1357,21 @@ class HalvesLossFn(torch.autograd.Function):
         L.call("s2e_reduce_loss_bwd", L.ptr(flat), L.ptr(flat[n2:]), n2, ctx.f32, ctx.kind, ctx.coef, 0.0, L.ptr(gout),
                L.ptr(dflat), 0, L.stream())
         return dx, None, None
+
+
+class HalvesPresummedFn(torch.autograd.Function):
+    """HalvesLossFn whose forward reduction was already done by the kernel that produced `t` (InstNormFn with pair_l1):
+    coef * pre; backward is HalvesLossFn's."""
+
+    @staticmethod
+    def forward(ctx, t, pre, kind, coef):
+        ctx.kind, ctx.coef, ctx.f32 = kind, coef, int(t.dtype == F32)
+        ctx.save_for_backward(_c(t))
+        return pre * coef
+
+    @staticmethod
+    def backward(ctx, gout):
+        return HalvesLossFn.backward(ctx, gout)[0], None, None, None
 
 
 class PairLossFn(torch.autograd.Function):

@@ -401,6 +401,37 @@ def test_instance_norm_streaming_paths(S, act, C, H, W):
     assert rel(nchw(xc.grad), xr.grad) < TOL_ACT, rel(nchw(xc.grad), xr.grad)
 
 
+@pytest.mark.parametrize("B,C,H,W", [(6, 128, 21, 17), (4, 512, 9, 11), (32, 256, 40, 24), (2, 4096, 3, 3)])
+def test_feature_matching_sum_fused_into_instance_norm(S, B, C, H, W):
+    """Inside ops.fm_pair_sums() an InstanceNorm layer fed with a [fake ; real] batch normalises both halves in one block and
+    reduces sum |y_fake - y_real| on the way (pix2pix_model.py:233-241): same output bits as the plain kernel, same loss value
+    and gradient as the separate reduction (ops.HalvesLossFn)."""
+    L, ops = S
+    from seg2eye_b200.models.networks.layers import InstanceNorm2d
+    g = torch.Generator().manual_seed(23)
+    x0 = (torch.randn(B, H, W, C, generator=g) * 2 + 0.5).to(torch.bfloat16).cuda()
+    norm = InstanceNorm2d(C, L.ACT_LRELU)
+    dy = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).cuda()
+    out = {}
+    for fused in (False, True):
+        x = x0.clone().requires_grad_()
+        if fused:
+            with ops.fm_pair_sums():
+                y = norm.forward_nhwc(x)
+            assert hasattr(y, "_s2e_fm_sum")
+            term = ops.HalvesPresummedFn.apply(y, y._s2e_fm_sum[0], L.RED_L1, 2.0 / y.numel())
+        else:
+            y = norm.forward_nhwc(x)
+            assert not hasattr(y, "_s2e_fm_sum")
+            term = ops.HalvesLossFn.apply(y, L.RED_L1, 2.0 / y.numel())
+        (term.sum() * 3.0 + (y.float() * dy.float()).sum() * 1e-3).backward()
+        out[fused] = (y.detach().clone(), float(term.detach()), x.grad.float().clone())
+    assert torch.equal(out[True][0], out[False][0])
+    ref = float((out[False][0][:B // 2].float() - out[False][0][B // 2:].float()).abs().mean())
+    assert abs(out[True][1] - ref) < 1e-4 * ref and abs(out[False][1] - ref) < 1e-4 * ref, (out[True][1], out[False][1], ref)
+    assert rel(out[True][2].cpu(), out[False][2].cpu()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------ resampling / elementwise
 def test_upsample_avgpool_bilinear_add_act(S):
     L, ops = S
