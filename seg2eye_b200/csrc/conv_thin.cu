@@ -554,12 +554,10 @@ __global__ void __launch_bounds__(256) img_wgrad_mma_kernel(const bf16* __restri
       }
       // A^T: (tap g | tap 8; pixels 2t, 2t+1 | 2t+8, 2t+9)
       const int pq = (warp + 1) * IW_PW + c0 + 2 * ft + 1;
-      const bf16 z = __float2bfloat16(0.f);
       const uint32_t a0 = live_g ? pack_bf16_bits(dt[pq + offg], dt[pq + 1 + offg]) : 0u;
       const uint32_t a2 = live_g ? pack_bf16_bits(dt[pq + 8 + offg], dt[pq + 9 + offg]) : 0u;
       const uint32_t a1 = live_8 ? pack_bf16_bits(dt[pq + off8], dt[pq + 1 + off8]) : 0u;
       const uint32_t a3 = live_8 ? pack_bf16_bits(dt[pq + 8 + off8], dt[pq + 9 + off8]) : 0u;
-      (void)z;
       const uint32_t w[4][4] = {{xv[0].x, xv[0].y, xv[0].z, xv[0].w}, {xv[1].x, xv[1].y, xv[1].z, xv[1].w},
                                 {xv[2].x, xv[2].y, xv[2].z, xv[2].w}, {xv[3].x, xv[3].y, xv[3].z, xv[3].w}};
 #pragma unroll
